@@ -1,0 +1,590 @@
+// K2: backward of K1 for every FeatureEmbedding parameter, fused with the FM backward and with
+// the L2 penalty gradient (reference: autograd through embedding.py:76-126 + fm.py:18-23, and
+// base.py:78-83; ATen embedding_dense_backward / _embedding_bag_dense_backward / mm).
+//
+//   sort      stable LSB radix sort of (key = global row, payload = b*S + slot), PAD keys last
+//   segreduce one lane group per chunk of CHUNK sorted positions; the upstream gradient of a slot
+//             g_raw = g_flat + P^T (g_field + g_fm (fm_sum - e)) is rebuilt on the fly, so the
+//             FM gradient never exists in HBM; segments inside a chunk are written directly
+//             (+ 2*l2*w[row]); the open head/tail partial sums go to a side buffer
+//   stitch    one lane group per segment that spans chunks adds the partials in chunk order
+//   pgrads    DENSE-field Linear and projection gradients: per-slice partial sums in shared
+//             memory, then a fixed-order reduction over slices (+ 2*l2*p)
+// No float atomics anywhere: every output element has exactly one writer and a fixed summation
+// order, so the gradients are bit-reproducible run to run.
+#include <cub/device/device_radix_sort.cuh>
+
+#include "plan.cuh"
+
+namespace dfm {
+
+constexpr int CHUNK = 32;      // sorted positions per lane group in segreduce
+constexpr int PG_TILE = 32;    // samples per shared-memory tile in pgrads
+constexpr int PG_THREADS = 256;
+
+struct BwdArgs {
+    const float* g_first;
+    const float* g_field;
+    const float* g_flat;
+    const float* g_fm;
+    const float* fe;      // field embeddings (B, F, D)
+    const float* flat;    // raw concat (B, T)
+    const float* fm_sum;  // (B, D)
+    const uint32_t* aux;
+    const float* l2_gscale;
+    float l2x2;           // 2 * lambda
+    int mode;
+    long long B, N;       // N = B * S
+    const uint32_t* skeys;
+    const uint32_t* spay;
+    float* row_grad2;
+    float* row_grad1;
+    float* head2; float* head1; float* tail2; float* tail1;  // per-chunk open partial sums
+    unsigned long long* counters;  // {n_valid, n_unique}
+};
+
+__global__ void iota_kernel(uint32_t* p, long long n) {
+    for (long long i = (long long)blockIdx.x * blockDim.x + threadIdx.x; i < n; i += (long long)gridDim.x * blockDim.x)
+        p[i] = (uint32_t)i;
+}
+
+// g[i] = coef * p[i]   (dense-mode L2 gradient for every row; coef may be 0 -> zero fill)
+__global__ void l2_fill_kernel(const float* __restrict__ p, float* __restrict__ g, long long n,
+                               float l2x2, const float* __restrict__ gscale) {
+    const float coef = l2x2 * (gscale ? __ldg(gscale) : 1.f);
+    const long long n4 = n >> 2;
+    const bool al = ((reinterpret_cast<uintptr_t>(p) | reinterpret_cast<uintptr_t>(g)) & 15u) == 0;
+    const long long stride = (long long)gridDim.x * blockDim.x;
+    long long i = (long long)blockIdx.x * blockDim.x + threadIdx.x;
+    if (al) {
+        if (coef == 0.f) {
+            for (; i < n4; i += stride) __stcs(reinterpret_cast<float4*>(g) + i, make_float4(0.f, 0.f, 0.f, 0.f));
+        } else {
+            for (; i < n4; i += stride) {
+                float4 w = __ldcs(reinterpret_cast<const float4*>(p) + i);
+                __stcs(reinterpret_cast<float4*>(g) + i, make_float4(coef * w.x, coef * w.y, coef * w.z, coef * w.w));
+            }
+        }
+        for (long long t = (n4 << 2) + (long long)blockIdx.x * blockDim.x + threadIdx.x; t < n; t += stride)
+            g[t] = coef == 0.f ? 0.f : coef * p[t];
+    } else {
+        for (; i < n; i += stride) g[i] = coef == 0.f ? 0.f : coef * p[i];
+    }
+}
+
+// ---- upstream gradient of one id slot, chunk c (V floats) of the raw embedding row
+template <int V>
+__device__ __forceinline__ VecF<V> slot_grad(const DevPlan& P, const BwdArgs& a, const FieldDev& fd,
+                                             int f, long long b, int l, int c) {
+    const int D = P.D;
+    VecF<V> g = vzero<V>();
+    if (a.g_flat) g = vload_stream<V>(a.g_flat + (size_t)b * P.T + fd.flat_off + c * V);
+    const float gfm = a.g_fm ? __ldg(a.g_fm + b) : 0.f;
+    const size_t eoff = ((size_t)b * P.n_fields + f) * D;
+    if (fd.proj == nullptr) {
+        if (a.g_field) {
+            VecF<V> t = vload_stream<V>(a.g_field + eoff + c * V);
+#pragma unroll
+            for (int v = 0; v < V; ++v) g.v[v] += t.v[v];
+        }
+        if (a.g_fm) {
+            VecF<V> s = vload<V>(a.fm_sum + (size_t)b * D + c * V);
+            VecF<V> e = vload_stream<V>(a.fe + eoff + c * V);
+#pragma unroll
+            for (int v = 0; v < V; ++v) g.v[v] = fmaf(gfm, s.v[v] - e.v[v], g.v[v]);
+        }
+    } else if (a.g_field || a.g_fm) {
+        const int d = fd.dim;
+        for (int k = 0; k < D; ++k) {
+            float gek = a.g_field ? __ldg(a.g_field + eoff + k) : 0.f;
+            if (a.g_fm) gek = fmaf(gfm, __ldg(a.fm_sum + (size_t)b * D + k) - __ldg(a.fe + eoff + k), gek);
+#pragma unroll
+            for (int v = 0; v < V; ++v) g.v[v] = fmaf(gek, __ldg(fd.proj + (size_t)k * d + c * V + v), g.v[v]);
+        }
+    }
+    if (fd.kind == DFM_SEQUENCE) {
+        if (fd.combiner == DFM_MEAN) {
+            const float inv = __uint_as_float(__ldg(a.aux + (size_t)b * P.A + fd.aux_off));
+#pragma unroll
+            for (int v = 0; v < V; ++v) g.v[v] *= inv;
+        } else if (fd.combiner == DFM_MAX) {
+#pragma unroll
+            for (int v = 0; v < V; ++v)
+                if ((int)__ldg(a.aux + (size_t)b * P.A + fd.aux_off + c * V + v) != l) g.v[v] = 0.f;
+        }
+    }
+    return g;
+}
+
+__device__ __forceinline__ float slot_grad1(const DevPlan& P, const BwdArgs& a, const FieldDev& fd,
+                                            long long b, int l) {
+    float g = a.g_first ? __ldg(a.g_first + b) : 0.f;
+    if (fd.kind == DFM_SEQUENCE) {
+        if (fd.combiner == DFM_MEAN) g *= __uint_as_float(__ldg(a.aux + (size_t)b * P.A + fd.aux_off));
+        else if (fd.combiner == DFM_MAX && (int)__ldg(a.aux + (size_t)b * P.A + fd.aux_off + fd.dim) != l) g = 0.f;
+    }
+    return g;
+}
+
+// ---- write the finished gradient of one row (segment) : + 2*l2*w[row]
+template <int V>
+__device__ __forceinline__ void write_row(const DevPlan& P, const DevGrads& GR, const BwdArgs& a, float coef,
+                                          uint32_t key, int f, long long head_pos, int j, int G,
+                                          const VecF<V>& acc, float acc1) {
+    const FieldDev& fd = P.f[f];
+    const long long row = (long long)key - fd.row_base;
+    const int nch = fd.dim / V;
+    if (j < nch) {   // table dims are <= G * V (checked on the host)
+        VecF<V> out = acc;
+        if (coef != 0.f) {
+            VecF<V> w = vload<V>(fd.w2 + (size_t)row * fd.dim + j * V);
+#pragma unroll
+            for (int v = 0; v < V; ++v) out.v[v] = fmaf(coef, w.v[v], out.v[v]);
+        }
+        if (a.mode == DFM_GRAD_DENSE) vstore<V>(GR.g[f].gw2 + (size_t)row * fd.dim + j * V, out);
+        else vstore<V>(a.row_grad2 + (size_t)head_pos * P.max_tdim + j * V, out);
+    }
+    if (j == 0) {
+        float o1 = acc1;
+        if (coef != 0.f) o1 = fmaf(coef, __ldg(fd.w1 + row), o1);
+        if (a.mode == DFM_GRAD_DENSE) GR.g[f].gw1[row] = o1;
+        else a.row_grad1[head_pos] = o1;
+    }
+}
+
+template <int V>
+__global__ void __launch_bounds__(256)
+segreduce_kernel(const __grid_constant__ DevPlan P, const __grid_constant__ DevGrads GR,
+                 const __grid_constant__ BwdArgs a, int G) {
+    const int gpb = blockDim.x / G;
+    const int gl = threadIdx.x / G;
+    const int j = threadIdx.x - gl * G;
+    const long long q = (long long)blockIdx.x * gpb + gl;   // chunk index
+    const long long p0 = q * CHUNK;
+    if (p0 >= a.N) return;
+    const long long p1 = (p0 + CHUNK < a.N) ? p0 + CHUNK : a.N;
+    const uint32_t PAD = P.pad_key;
+    const float coef = a.l2x2 * (a.l2_gscale ? __ldg(a.l2_gscale) : 1.f);
+    const int S = P.S, tdim = P.max_tdim;
+
+    uint32_t cur = __ldg(a.skeys + p0);
+    if (cur == PAD) return;                                  // everything from here on is padding
+    const bool head_open = p0 > 0 && __ldg(a.skeys + p0 - 1) == cur;
+    bool started_before = head_open;
+    long long seg_start = p0;
+    int n_heads = head_open ? 0 : 1, n_valid = 0;
+    VecF<V> acc = vzero<V>();
+    float acc1 = 0.f;
+    int f = 0;
+    long long p = p0;
+    for (; p < p1; ++p) {
+        const uint32_t k = __ldg(a.skeys + p);
+        if (k == PAD) break;
+        const uint32_t pay = __ldg(a.spay + p);
+        const long long b = pay / (uint32_t)S;
+        const int s = (int)(pay - (uint32_t)b * (uint32_t)S);
+        if (k != cur) {   // previous segment ended inside this chunk
+            if (started_before) {
+                if (j < tdim / V) vstore<V>(a.head2 + (size_t)q * tdim + j * V, acc);
+                if (j == 0) a.head1[q] = acc1;
+            } else {
+                write_row<V>(P, GR, a, coef, cur, f, seg_start, j, G, acc, acc1);
+            }
+            cur = k; seg_start = p; started_before = false; ++n_heads;
+            acc = vzero<V>(); acc1 = 0.f;
+        }
+        f = P.slot_field[s];
+        const FieldDev& fd = P.f[f];
+        const int l = P.slot_pos[s];
+        if (j < fd.dim / V) {
+            VecF<V> g = slot_grad<V>(P, a, fd, f, b, l, j);
+#pragma unroll
+            for (int v = 0; v < V; ++v) acc.v[v] += g.v[v];
+        }
+        if (j == 0) acc1 += slot_grad1(P, a, fd, b, l);
+        ++n_valid;
+    }
+    const bool continues = (p == p1) && p1 < a.N && __ldg(a.skeys + p1) == cur;
+    if (started_before) {
+        if (j < tdim / V) vstore<V>(a.head2 + (size_t)q * tdim + j * V, acc);
+        if (j == 0) a.head1[q] = acc1;
+    } else if (continues) {
+        if (j < tdim / V) vstore<V>(a.tail2 + (size_t)q * tdim + j * V, acc);
+        if (j == 0) a.tail1[q] = acc1;
+    } else {
+        write_row<V>(P, GR, a, coef, cur, f, seg_start, j, G, acc, acc1);
+    }
+    if (j == 0) {
+        atomicAdd(a.counters + 0, (unsigned long long)n_valid);   // integer: order-independent
+        atomicAdd(a.counters + 1, (unsigned long long)n_heads);
+    }
+}
+
+// One lane group per chunk; only the chunk in which a multi-chunk segment STARTS does work.
+template <int V>
+__global__ void __launch_bounds__(256)
+stitch_kernel(const __grid_constant__ DevPlan P, const __grid_constant__ DevGrads GR,
+              const __grid_constant__ BwdArgs a, int G) {
+    const int gpb = blockDim.x / G;
+    const int gl = threadIdx.x / G;
+    const int j = threadIdx.x - gl * G;
+    const long long q = (long long)blockIdx.x * gpb + gl;
+    const long long p0 = q * CHUNK;
+    if (p0 >= a.N) return;
+    const long long p1 = p0 + CHUNK;
+    if (p1 >= a.N) return;                                   // last chunk cannot continue
+    const uint32_t k = __ldg(a.skeys + p1 - 1);
+    if (k == P.pad_key || __ldg(a.skeys + p1) != k) return;  // no segment leaves this chunk
+    if (__ldg(a.skeys + p0) == k && p0 > 0 && __ldg(a.skeys + p0 - 1) == k) return;  // not the owner
+    const int tdim = P.max_tdim;
+    const float coef = a.l2x2 * (a.l2_gscale ? __ldg(a.l2_gscale) : 1.f);
+    VecF<V> acc = vzero<V>();
+    if (j < tdim / V) acc = vload<V>(a.tail2 + (size_t)q * tdim + j * V);
+    float acc1 = j == 0 ? a.tail1[q] : 0.f;
+    for (long long qq = q + 1;; ++qq) {
+        if (j < tdim / V) {
+            VecF<V> h = vload<V>(a.head2 + (size_t)qq * tdim + j * V);
+#pragma unroll
+            for (int v = 0; v < V; ++v) acc.v[v] += h.v[v];
+        }
+        if (j == 0) acc1 += a.head1[qq];
+        const long long e = (qq + 1) * CHUNK;
+        if (e < a.N && __ldg(a.skeys + e - 1) == k && __ldg(a.skeys + e) == k) continue;
+        break;
+    }
+    long long hp = p1 - 1;
+    while (hp > p0 && __ldg(a.skeys + hp - 1) == k) --hp;
+    const uint32_t pay = __ldg(a.spay + hp);
+    const int s = (int)(pay % (uint32_t)P.S);
+    write_row<V>(P, GR, a, coef, k, P.slot_field[s], hp, j, G, acc, acc1);
+}
+
+// ---- DENSE-field Linear grads and projection grads -------------------------------------
+struct PgField {
+    int f, nvals, part_off;   // part_off: offset (floats) of this field inside one slice's partials
+};
+struct PgArgs {
+    PgField pf[MAX_FIELDS];
+    int n_pf, n_slices, vals_per_slice;
+    long long slice_len;
+    float* partials;          // (n_slices, vals_per_slice)
+};
+
+// value layout of one field: [proj (D*d)] [gW2 (d)] [gb2 (d)] [gw1] [gb1]   (present parts only)
+__global__ void __launch_bounds__(PG_THREADS)
+pgrads_kernel(const __grid_constant__ DevPlan P, const __grid_constant__ BwdArgs a,
+              const __grid_constant__ PgArgs pg) {
+    extern __shared__ float sm[];
+    const PgField pfd = pg.pf[blockIdx.y];
+    const int f = pfd.f;
+    const FieldDev& fd = P.f[f];
+    const int D = P.D, d = fd.dim, F = P.n_fields;
+    const bool proj = fd.proj != nullptr, dense = fd.kind == DFM_DENSE;
+    float* s_ge = sm;                         // PG_TILE x D
+    float* s_gr = s_ge + PG_TILE * D;         // PG_TILE x d   g_raw (DENSE fields)
+    float* s_raw = s_gr + PG_TILE * d;        // PG_TILE x d   raw row (projection)
+    float* s_x = s_raw + PG_TILE * d;         // PG_TILE
+    float* s_g1 = s_x + PG_TILE;              // PG_TILE
+    float* s_acc = s_g1 + PG_TILE;            // nvals
+    const int tid = threadIdx.x;
+    for (int o = tid; o < pfd.nvals; o += PG_THREADS) s_acc[o] = 0.f;
+    const long long b_lo = (long long)blockIdx.x * pg.slice_len;
+    const long long b_hi = (b_lo + pg.slice_len < a.B) ? b_lo + pg.slice_len : a.B;
+    const int n_proj = proj ? D * d : 0;
+    for (long long t0 = b_lo; t0 < b_hi; t0 += PG_TILE) {
+        const int ts = (int)((b_hi - t0 < PG_TILE) ? b_hi - t0 : PG_TILE);
+        __syncthreads();
+        for (int i = tid; i < PG_TILE * D; i += PG_THREADS) {
+            const int s = i / D, k = i - s * D;
+            float ge = 0.f;
+            if (s < ts) {
+                const long long b = t0 + s;
+                const size_t eoff = ((size_t)b * F + f) * D + k;
+                if (a.g_field) ge = __ldcs(a.g_field + eoff);
+                if (a.g_fm) ge = fmaf(__ldg(a.g_fm + b), __ldg(a.fm_sum + (size_t)b * D + k) - __ldcs(a.fe + eoff), ge);
+            }
+            s_ge[i] = ge;
+        }
+        for (int i = tid; i < PG_TILE * d; i += PG_THREADS) {
+            const int s = i / d, c = i - s * d;
+            float gr = 0.f, raw = 0.f;
+            if (s < ts) {
+                const long long b = t0 + s;
+                if (a.g_flat) gr = __ldcs(a.g_flat + (size_t)b * P.T + fd.flat_off + c);
+                if (proj) raw = __ldcs(a.flat + (size_t)b * P.T + fd.flat_off + c);
+            }
+            s_gr[i] = gr;
+            s_raw[i] = raw;
+        }
+        if (tid < PG_TILE) {
+            const bool ok = tid < ts;
+            s_x[tid] = (ok && dense) ? __ldg(reinterpret_cast<const float*>(fd.in) + t0 + tid) : 0.f;
+            s_g1[tid] = (ok && a.g_first) ? __ldg(a.g_first + t0 + tid) : 0.f;
+        }
+        __syncthreads();
+        if (dense) {   // g_raw = g_flat + P^T g_e   (or + g_e when there is no projection)
+            for (int i = tid; i < PG_TILE * d; i += PG_THREADS) {
+                const int s = i / d, c = i - s * d;
+                float gr = s_gr[i];
+                if (proj) {
+                    for (int k = 0; k < D; ++k) gr = fmaf(s_ge[s * D + k], __ldg(fd.proj + (size_t)k * d + c), gr);
+                } else {
+                    gr += s_ge[s * D + c];
+                }
+                s_gr[i] = gr;
+            }
+            __syncthreads();
+        }
+        for (int o = tid; o < pfd.nvals; o += PG_THREADS) {
+            float acc = 0.f;
+            if (o < n_proj) {                       // dP[k][c] = sum_b g_e[b,k] * raw[b,c]
+                const int k = o / d, c = o - k * d;
+                for (int s = 0; s < PG_TILE; ++s) acc = fmaf(s_ge[s * D + k], s_raw[s * d + c], acc);
+            } else {
+                const int r = o - n_proj;
+                if (r < d) { for (int s = 0; s < PG_TILE; ++s) acc = fmaf(s_gr[s * d + r], s_x[s], acc); }
+                else if (r < 2 * d) { for (int s = 0; s < PG_TILE; ++s) acc += s_gr[s * d + (r - d)]; }
+                else if (r == 2 * d) { for (int s = 0; s < PG_TILE; ++s) acc = fmaf(s_g1[s], s_x[s], acc); }
+                else { for (int s = 0; s < PG_TILE; ++s) acc += s_g1[s]; }
+            }
+            s_acc[o] += acc;
+        }
+    }
+    __syncthreads();
+    float* out = pg.partials + (size_t)blockIdx.x * pg.vals_per_slice + pfd.part_off;
+    for (int o = tid; o < pfd.nvals; o += PG_THREADS) out[o] = s_acc[o];
+}
+
+__global__ void pgrads_finish_kernel(const __grid_constant__ DevPlan P, const __grid_constant__ DevGrads GR,
+                                     const __grid_constant__ BwdArgs a, const __grid_constant__ PgArgs pg) {
+    const PgField pfd = pg.pf[blockIdx.y];
+    const FieldDev& fd = P.f[pfd.f];
+    const GradDev& gd = GR.g[pfd.f];
+    const int o = blockIdx.x * blockDim.x + threadIdx.x;
+    if (o >= pfd.nvals) return;
+    const float coef = a.l2x2 * (a.l2_gscale ? __ldg(a.l2_gscale) : 1.f);
+    float acc = 0.f;
+    for (int s = 0; s < pg.n_slices; ++s) acc += pg.partials[(size_t)s * pg.vals_per_slice + pfd.part_off + o];
+    const int d = fd.dim;
+    const int n_proj = fd.proj ? P.D * d : 0;
+    if (o < n_proj) { gd.gproj[o] = fmaf(coef, __ldg(fd.proj + o), acc); return; }
+    const int r = o - n_proj;
+    if (r < d) gd.gw2[r] = fmaf(coef, __ldg(fd.w2 + r), acc);
+    else if (r < 2 * d) gd.gb2[r - d] = fmaf(coef, __ldg(fd.b2 + r - d), acc);
+    else if (r == 2 * d) gd.gw1[0] = fmaf(coef, __ldg(fd.w1), acc);
+    else gd.gb1[0] = fmaf(coef, __ldg(fd.b1), acc);
+}
+
+// ---- host-side workspace carving --------------------------------------------------------
+struct BwdLayout {
+    size_t cub_bytes, off_cub, off_payload, off_head2, off_head1, off_tail2, off_tail1, off_counters,
+        off_partials, total;
+    long long n_chunks;
+    int n_slices, vals_per_slice;
+    long long slice_len;
+};
+
+static int sort_temp_bytes(long long n, int bits, size_t* out) {
+    size_t bytes = 0;
+    cudaError_t e = cub::DeviceRadixSort::SortPairs(nullptr, bytes, (const uint32_t*)nullptr, (uint32_t*)nullptr,
+                                                    (const uint32_t*)nullptr, (uint32_t*)nullptr, (int)n, 0, bits);
+    if (e != cudaSuccess) { set_error("cub SortPairs size query: %s", cudaGetErrorString(e)); return DFM_ERR_CUDA; }
+    *out = bytes;
+    return DFM_OK;
+}
+
+static int pg_count_vals(const dfm_plan* plan, int f) {
+    const int d = plan->dim[f];
+    int n = 0;
+    if (d != plan->fm_dim) n += plan->fm_dim * d;
+    if (plan->kind[f] == DFM_DENSE) n += 2 * d + 2;
+    return n;
+}
+
+static int make_layout(const dfm_plan* plan, long long B, BwdLayout& L) {
+    const long long N = B * plan->S;
+    L.cub_bytes = 0;
+    if (N > 0) { int rc = sort_temp_bytes(N, plan->key_bits, &L.cub_bytes); if (rc) return rc; }
+    L.n_chunks = ceil_div(N > 0 ? N : 1, CHUNK);
+    int vals = 0, n_pf = 0;
+    for (int f = 0; f < plan->n_fields; ++f) { int n = pg_count_vals(plan, f); if (n) { vals += n; ++n_pf; } }
+    L.vals_per_slice = vals;
+    int want = n_pf ? (int)ceil_div(4 * sm_count(), n_pf) : 1;
+    long long max_slices = ceil_div(B > 0 ? B : 1, 2 * PG_TILE);
+    if (want > max_slices) want = (int)max_slices;
+    if (want < 1) want = 1;
+    L.slice_len = ceil_div(ceil_div(B > 0 ? B : 1, want), PG_TILE) * PG_TILE;
+    L.n_slices = (int)ceil_div(B > 0 ? B : 1, L.slice_len);
+    size_t off = 0;
+    auto take = [&](size_t bytes) { size_t o = off; off = align_up(off + bytes, 256); return o; };
+    L.off_cub = take(L.cub_bytes);
+    L.off_payload = take((size_t)N * 4);
+    L.off_head2 = take((size_t)L.n_chunks * plan->max_tdim * 4);
+    L.off_head1 = take((size_t)L.n_chunks * 4);
+    L.off_tail2 = take((size_t)L.n_chunks * plan->max_tdim * 4);
+    L.off_tail1 = take((size_t)L.n_chunks * 4);
+    L.off_counters = take(16);
+    L.off_partials = take((size_t)L.n_slices * vals * 4);
+    L.total = off;
+    return DFM_OK;
+}
+
+}  // namespace dfm
+
+using namespace dfm;
+
+extern "C" {
+
+size_t dfm_embed_bwd_workspace_bytes(const dfm_plan* plan, int64_t batch) {
+    if (!plan || batch < 0) return 0;
+    BwdLayout L;
+    if (make_layout(plan, batch, L) != DFM_OK) return 0;
+    return L.total;
+}
+
+int dfm_sort_keys(const dfm_plan* plan, int64_t n, const uint32_t* keys, uint32_t* sorted_keys,
+                  uint32_t* sorted_payload, void* workspace, size_t workspace_bytes, void* stream) {
+    DFM_REQUIRE(plan && keys && sorted_keys && sorted_payload && workspace, DFM_ERR_INVALID, "dfm_sort_keys: null argument");
+    if (n <= 0) return DFM_OK;
+    DFM_REQUIRE(n < 0x7fffffffLL, DFM_ERR_UNSUPPORTED, "dfm_sort_keys: %lld keys do not fit a 32-bit sort", (long long)n);
+    size_t cub_bytes = 0;
+    int rc = sort_temp_bytes(n, plan->key_bits, &cub_bytes);
+    if (rc) return rc;
+    const size_t off_payload = align_up(cub_bytes, 256);
+    DFM_REQUIRE(workspace_bytes >= off_payload + (size_t)n * 4, DFM_ERR_WORKSPACE,
+                "dfm_sort_keys: workspace %zu < %zu", workspace_bytes, off_payload + (size_t)n * 4);
+    cudaStream_t st = static_cast<cudaStream_t>(stream);
+    uint32_t* payload = reinterpret_cast<uint32_t*>(static_cast<char*>(workspace) + off_payload);
+    const int blocks = (int)(ceil_div(n, 256) < 8LL * sm_count() ? ceil_div(n, 256) : 8LL * sm_count());
+    iota_kernel<<<blocks, 256, 0, st>>>(payload, n);
+    DFM_CHECK_LAUNCH();
+    DFM_CHECK_CUDA(cub::DeviceRadixSort::SortPairs(workspace, cub_bytes, keys, sorted_keys, payload, sorted_payload,
+                                                   (int)n, 0, plan->key_bits, st));
+    return DFM_OK;
+}
+
+int dfm_embed_bwd(const dfm_plan* plan, int64_t batch, const void* const* inputs,
+                  const float* const* params, const float* g_first, const float* g_field,
+                  const float* g_flat, const float* g_fm, const float* field_emb,
+                  const float* flat, const float* fm_sum, const uint32_t* keys,
+                  const uint32_t* aux, float l2, const float* l2_gscale, int mode,
+                  float* const* grads, uint32_t* sorted_keys, uint32_t* sorted_payload,
+                  float* row_grad2, float* row_grad1, int64_t* n_valid, void* workspace,
+                  size_t workspace_bytes, void* stream) {
+    DFM_REQUIRE(plan && inputs && params && grads && workspace, DFM_ERR_INVALID, "dfm_embed_bwd: null argument");
+    DFM_REQUIRE(batch >= 0, DFM_ERR_INVALID, "dfm_embed_bwd: negative batch");
+    DFM_REQUIRE(mode == DFM_GRAD_DENSE || mode == DFM_GRAD_ROWSPARSE, DFM_ERR_INVALID, "dfm_embed_bwd: unknown mode %d", mode);
+    DFM_REQUIRE(!g_fm || (fm_sum && field_emb), DFM_ERR_INVALID, "dfm_embed_bwd: g_fm needs fm_sum and field_emb");
+    DFM_REQUIRE(plan->A == 0 || aux, DFM_ERR_INVALID, "dfm_embed_bwd: aux required");
+    DFM_REQUIRE(plan->S == 0 || (sorted_keys && sorted_payload && keys), DFM_ERR_INVALID, "dfm_embed_bwd: key buffers required");
+    DFM_REQUIRE(mode == DFM_GRAD_DENSE || plan->S == 0 || (row_grad2 && row_grad1 && n_valid), DFM_ERR_INVALID,
+                "dfm_embed_bwd: row-sparse outputs required");
+    DFM_REQUIRE(plan->n_proj_expected == 0 || flat, DFM_ERR_INVALID, "dfm_embed_bwd: flat needed for projection grads");
+    BwdLayout L;
+    int rc = make_layout(plan, batch, L);
+    if (rc) return rc;
+    DFM_REQUIRE(workspace_bytes >= L.total, DFM_ERR_WORKSPACE, "dfm_embed_bwd: workspace %zu < %zu", workspace_bytes, L.total);
+    cudaStream_t st = static_cast<cudaStream_t>(stream);
+    char* ws = static_cast<char*>(workspace);
+    const long long N = (long long)batch * plan->S;
+    DFM_REQUIRE(N < 0x7fffffffLL, DFM_ERR_UNSUPPORTED, "dfm_embed_bwd: batch * slots must fit 31 bits");
+
+    DevPlan* P = new DevPlan;
+    DevGrads* GR = new DevGrads;
+    struct Guard { DevPlan* p; DevGrads* g; ~Guard() { delete p; delete g; } } guard{P, GR};
+    int V = plan->fill(*P, inputs, params, true);
+    P->aliased = field_emb == flat ? 1 : 0;
+    memset(GR, 0, sizeof(*GR));
+    auto al16 = [](const void* p) { return (reinterpret_cast<uintptr_t>(p) & 15u) == 0; };
+    bool aligned = al16(g_flat) && al16(g_field) && al16(field_emb) && al16(fm_sum) && al16(row_grad2);
+    for (int f = 0; f < plan->n_fields; ++f) {
+        GradDev& g = GR->g[f];
+        g.gw2 = grads[5 * f + 0]; g.gb2 = grads[5 * f + 1]; g.gw1 = grads[5 * f + 2];
+        g.gb1 = grads[5 * f + 3]; g.gproj = grads[5 * f + 4];
+        const bool table = plan->kind[f] != DFM_DENSE;
+        if (table && mode == DFM_GRAD_DENSE) {
+            DFM_REQUIRE(g.gw2 && g.gw1, DFM_ERR_INVALID, "dfm_embed_bwd: dense mode needs table grads for field %d", f);
+            aligned = aligned && al16(g.gw2);
+        }
+        if (!table) DFM_REQUIRE(g.gw2 && g.gb2 && g.gw1 && g.gb1, DFM_ERR_INVALID, "dfm_embed_bwd: DENSE field %d grads missing", f);
+        if (plan->dim[f] != plan->fm_dim) DFM_REQUIRE(g.gproj, DFM_ERR_INVALID, "dfm_embed_bwd: projection grad of field %d missing", f);
+    }
+    if (!aligned) V = 1;
+    const int lanes = plan->max_tdim > 0 ? plan->max_tdim / V : 1;
+    DFM_REQUIRE(lanes <= 32, DFM_ERR_UNSUPPORTED, "dfm_embed_bwd: table dim %d needs %d lanes per row (max 32 x %d floats)",
+                plan->max_tdim, lanes, V);
+    const int G = next_pow2(lanes);
+
+    BwdArgs a;
+    memset(&a, 0, sizeof(a));
+    a.g_first = g_first; a.g_field = g_field; a.g_flat = g_flat; a.g_fm = g_fm;
+    a.fe = field_emb; a.flat = flat; a.fm_sum = fm_sum; a.aux = aux; a.l2_gscale = l2_gscale;
+    a.l2x2 = 2.f * l2; a.mode = mode; a.B = batch; a.N = N;
+    a.skeys = sorted_keys; a.spay = sorted_payload; a.row_grad2 = row_grad2; a.row_grad1 = row_grad1;
+    a.head2 = reinterpret_cast<float*>(ws + L.off_head2); a.head1 = reinterpret_cast<float*>(ws + L.off_head1);
+    a.tail2 = reinterpret_cast<float*>(ws + L.off_tail2); a.tail1 = reinterpret_cast<float*>(ws + L.off_tail1);
+    a.counters = n_valid ? reinterpret_cast<unsigned long long*>(n_valid)
+                         : reinterpret_cast<unsigned long long*>(ws + L.off_counters);
+    const int fill_blocks = 8 * sm_count();
+
+    // 1. dense mode: every element of every table gradient starts as 2*l2*w (or 0)
+    if (mode == DFM_GRAD_DENSE) {
+        for (int f = 0; f < plan->n_fields; ++f) {
+            if (plan->kind[f] == DFM_DENSE) continue;
+            const long long n2 = plan->vocab[f] * plan->dim[f], n1 = plan->vocab[f];
+            int b2 = (int)(ceil_div(n2, 1024) < fill_blocks ? ceil_div(n2, 1024) : fill_blocks);
+            int b1 = (int)(ceil_div(n1, 1024) < fill_blocks ? ceil_div(n1, 1024) : fill_blocks);
+            l2_fill_kernel<<<b2, 256, 0, st>>>(params[5 * f + 0], grads[5 * f + 0], n2, a.l2x2, l2_gscale);
+            l2_fill_kernel<<<b1, 256, 0, st>>>(params[5 * f + 2], grads[5 * f + 2], n1, a.l2x2, l2_gscale);
+        }
+        DFM_CHECK_LAUNCH();
+    }
+    // 2. sort + segmented reduction of the id slots
+    if (N > 0 && batch > 0) {
+        DFM_CHECK_CUDA(cudaMemsetAsync(a.counters, 0, 16, st));
+        rc = dfm_sort_keys(plan, N, keys, sorted_keys, sorted_payload, ws + L.off_cub,
+                           L.off_payload + (size_t)N * 4 - L.off_cub, stream);
+        if (rc) return rc;
+        const int gpb = 256 / G;
+        const unsigned blocks = (unsigned)ceil_div(L.n_chunks, gpb);
+        if (V == 4) {
+            segreduce_kernel<4><<<blocks, 256, 0, st>>>(*P, *GR, a, G);
+            stitch_kernel<4><<<blocks, 256, 0, st>>>(*P, *GR, a, G);
+        } else {
+            segreduce_kernel<1><<<blocks, 256, 0, st>>>(*P, *GR, a, G);
+            stitch_kernel<1><<<blocks, 256, 0, st>>>(*P, *GR, a, G);
+        }
+        DFM_CHECK_LAUNCH();
+    } else if (n_valid) {
+        DFM_CHECK_CUDA(cudaMemsetAsync(n_valid, 0, 16, st));
+    }
+    // 3. DENSE-field Linear and projection gradients
+    PgArgs* pg = new PgArgs;
+    struct G2 { PgArgs* p; ~G2() { delete p; } } g2{pg};
+    memset(pg, 0, sizeof(*pg));
+    int max_smem_floats = 0, max_vals = 0;
+    for (int f = 0; f < plan->n_fields; ++f) {
+        const int n = pg_count_vals(plan, f);
+        if (!n) continue;
+        PgField& pf = pg->pf[pg->n_pf];
+        pf.f = f; pf.nvals = n; pf.part_off = pg->vals_per_slice;
+        pg->vals_per_slice += n; pg->n_pf++;
+        const int fl = PG_TILE * (plan->fm_dim + 2 * plan->dim[f] + 2) + n;
+        if (fl > max_smem_floats) max_smem_floats = fl;
+        if (n > max_vals) max_vals = n;
+    }
+    if (pg->n_pf > 0) {
+        pg->n_slices = batch > 0 ? L.n_slices : 0; pg->slice_len = L.slice_len;
+        pg->partials = reinterpret_cast<float*>(ws + L.off_partials);
+        const size_t smem = (size_t)max_smem_floats * 4;
+        DFM_REQUIRE(smem <= 200 * 1024, DFM_ERR_UNSUPPORTED, "dfm_embed_bwd: projection/dense grads need %zu B shared memory", smem);
+        if (smem > 48 * 1024)
+            DFM_CHECK_CUDA(cudaFuncSetAttribute(pgrads_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
+        if (batch > 0) pgrads_kernel<<<dim3(pg->n_slices, pg->n_pf), PG_THREADS, smem, st>>>(*P, a, *pg);
+        pgrads_finish_kernel<<<dim3((unsigned)ceil_div(max_vals, 128), pg->n_pf), 128, 0, st>>>(*P, *GR, a, *pg);
+        DFM_CHECK_LAUNCH();
+    }
+    return DFM_OK;
+}
+
+}  // extern "C"

@@ -1,0 +1,7 @@
+"""Layer modules of the hot path (same names as deepfm/models/layers/__init__.py:3-15)."""
+
+from .dnn import DNN
+from .embedding import FeatureEmbedding, RowSparseGrads
+from .fm import FMInteraction
+
+__all__ = ["DNN", "FeatureEmbedding", "FMInteraction", "RowSparseGrads"]

@@ -1,0 +1,334 @@
+"""Drop-in ``FeatureEmbedding`` running on the fused sm_100a kernels K1 / K2.
+
+Mirrors the reference module (deepfm/models/layers/embedding.py:14-126): same constructor,
+attributes (``schema``, ``fm_embed_dim``, ``field_names``, ``second_order_embeddings``,
+``first_order_embeddings``, ``projections``), ``state_dict`` keys, parameter enumeration order and
+initialisation, and the same ``forward(batch) -> (first_order, field_embeddings, flat)``.
+The per-field ``nn.Embedding`` / ``nn.EmbeddingBag`` / ``nn.Linear`` children are kept as
+parameter containers only -- their ATen forwards are never called; forward and backward are one
+``torch.autograd.Function`` over ``dfm_embed_fwd`` / ``dfm_embed_bwd``.
+
+Extras that do not exist in the reference (all default to reference semantics):
+  * ``grad_mode``: ``"dense"`` (reference: dense ``(V, d)`` table gradients, ``2*l2*w`` on every
+    row) or ``"row_sparse"`` (Criteo scale: table gradients stay as sorted unique rows in
+    ``self.row_grads``; L2 applied to touched rows only; see ``RowSparseGrads``).
+  * the FM term is computed by the same kernel and handed to ``FMInteraction`` through the
+    returned ``field_embeddings`` tensor, so DeepFM reads the embeddings from HBM once.
+"""
+
+from __future__ import annotations
+
+import ctypes as C
+import weakref
+from typing import Dict, List, Optional, Tuple
+
+import torch
+import torch.nn as nn
+
+from .. import _lib
+from ..schema import kind_of
+
+
+class RowSparseGrads:
+    """Table gradients of one backward pass in sorted-segment form (no host sync to build).
+
+    ``sorted_keys[p]`` is the global row (``row_base[field] + id``) at sorted position ``p``;
+    positions ``>= n_valid`` hold the PAD key.  At the first position of every run of equal keys
+    ``row_grad2[p, :d_field]`` / ``row_grad1[p]`` hold that row's summed gradient (+ ``2*l2*w``).
+    ``counts`` is a device int64[2] = (n_valid, n_unique).
+    """
+
+    def __init__(self, sorted_keys, sorted_payload, row_grad2, row_grad1, counts, row_base, dims, names):
+        self.sorted_keys, self.sorted_payload = sorted_keys, sorted_payload
+        self.row_grad2, self.row_grad1, self.counts = row_grad2, row_grad1, counts
+        self.row_base, self.dims, self.names = row_base, dims, names
+
+    def heads(self) -> torch.Tensor:
+        """Sorted positions that start a segment (one host sync)."""
+        k = self.sorted_keys
+        n_valid = int(self.counts[0].item())
+        k = k[:n_valid]
+        if n_valid == 0:
+            return torch.empty(0, dtype=torch.long, device=k.device)
+        head = torch.ones(n_valid, dtype=torch.bool, device=k.device)
+        head[1:] = k[1:] != k[:-1]
+        return head.nonzero(as_tuple=True)[0]
+
+    def per_table(self) -> Dict[str, Tuple[torch.Tensor, torch.Tensor, torch.Tensor]]:
+        """{field: (local_rows int64 (U,), grad2 (U, d), grad1 (U,))} -- the unique touched rows."""
+        pos = self.heads()
+        keys = self.sorted_keys[pos].long()
+        out = {}
+        for f, name in enumerate(self.names):
+            lo, hi = self.row_base[f], self.row_base[f + 1]
+            if hi == lo:
+                continue
+            m = (keys >= lo) & (keys < hi)
+            p = pos[m]
+            out[name] = (keys[m] - lo, self.row_grad2[p, : self.dims[f]], self.row_grad1[p])
+        return out
+
+
+class _EmbedFn(torch.autograd.Function):
+    """forward = K1 (dfm_embed_fwd), backward = K2 (dfm_embed_bwd)."""
+
+    @staticmethod
+    def forward(ctx, mod: "FeatureEmbedding", n_inputs: int, *tensors):
+        inputs, params = tensors[:n_inputs], tensors[n_inputs:]
+        lib = _lib.lib()
+        dev = params[0].device
+        B = inputs[0].shape[0]
+        F, D, T, S, A = mod.num_fields, mod.fm_embed_dim, mod._T, mod._S, mod._A
+        need_bwd = torch.is_grad_enabled() and any(p.requires_grad for p in params)
+        flat = torch.empty((B, T), device=dev, dtype=torch.float32)
+        field = flat.view(B, F, D) if mod._aliasable else torch.empty((B, F, D), device=dev, dtype=torch.float32)
+        first = torch.empty((B, 1), device=dev, dtype=torch.float32)
+        fm_out = torch.empty((B, 1), device=dev, dtype=torch.float32)
+        fm_sum = torch.empty((B, D), device=dev, dtype=torch.float32) if need_bwd else None
+        keys = torch.empty((B * S,), device=dev, dtype=torch.int32) if (need_bwd and S) else None
+        aux = torch.empty((B, A), device=dev, dtype=torch.int32) if A else None
+        status = mod._status if mod.check_indices else None
+        if status is not None:
+            status.zero_()
+        in_arr = _lib.ptr_array(inputs)
+        par_arr = mod._param_ptrs(params)
+        _lib.check(lib.dfm_embed_fwd(mod._plan, B, in_arr, par_arr, first.data_ptr(), field.data_ptr(),
+                                     flat.data_ptr(), fm_out.data_ptr(), _lib.ptr(fm_sum), _lib.ptr(keys),
+                                     _lib.ptr(aux), _lib.ptr(status), _lib.stream_ptr()), "dfm_embed_fwd")
+        if status is not None and int(status.item()) != 0:
+            raise IndexError("index out of range in FeatureEmbedding (an id is outside [0, vocabulary_size))")
+        ctx.mod = mod
+        ctx.n_inputs = n_inputs
+        ctx.set_materialize_grads(False)
+        ctx.l2 = None            # (lambda, upstream-grad tensor) set by the L2 penalty node
+        ctx.done = False
+        if need_bwd:
+            ctx.save_for_backward(field, flat, fm_sum, keys, aux, *inputs, *params)
+            mod._live_ctx = weakref.ref(ctx)
+        return first, field, flat, fm_out
+
+    @staticmethod
+    def backward(ctx, g_first, g_field, g_flat, g_fm):
+        mod: FeatureEmbedding = ctx.mod
+        lib = _lib.lib()
+        saved = ctx.saved_tensors
+        field, flat, fm_sum, keys, aux = saved[:5]
+        inputs = saved[5:5 + ctx.n_inputs]
+        params = saved[5 + ctx.n_inputs:]
+        dev = flat.device
+        B = flat.shape[0]
+        S = mod._S
+        N = B * S
+        cont = lambda g: None if g is None else g.contiguous()
+        g_first, g_field, g_flat, g_fm = cont(g_first), cont(g_field), cont(g_flat), cont(g_fm)
+        rowsparse = mod.grad_mode == "row_sparse"
+        grads: List[Optional[torch.Tensor]] = []
+        for p, is_table in zip(params, mod._param_is_table):
+            grads.append(None if (rowsparse and is_table) else torch.empty_like(p))
+        lam, gscale = (0.0, None)
+        if ctx.l2 is not None:
+            lam, gscale = ctx.l2
+        ctx.done = True
+        ws_bytes = lib.dfm_embed_bwd_workspace_bytes(mod._plan, B)
+        ws = torch.empty((max(ws_bytes, 16),), device=dev, dtype=torch.uint8)
+        skeys = torch.empty((max(N, 1),), device=dev, dtype=torch.int32)
+        spay = torch.empty((max(N, 1),), device=dev, dtype=torch.int32)
+        counts = torch.zeros((2,), device=dev, dtype=torch.int64)
+        rg2 = rg1 = None
+        if rowsparse:
+            rg2 = torch.empty((max(N, 1), max(mod._max_tdim, 1)), device=dev, dtype=torch.float32)
+            rg1 = torch.empty((max(N, 1),), device=dev, dtype=torch.float32)
+        _lib.check(lib.dfm_embed_bwd(
+            mod._plan, B, _lib.ptr_array(inputs), mod._param_ptrs(params),
+            _lib.ptr(g_first), _lib.ptr(g_field), _lib.ptr(g_flat), _lib.ptr(g_fm),
+            field.data_ptr(), flat.data_ptr(), _lib.ptr(fm_sum), _lib.ptr(keys), _lib.ptr(aux),
+            float(lam), _lib.ptr(gscale), _lib.GRAD_ROWSPARSE if rowsparse else _lib.GRAD_DENSE,
+            mod._param_ptrs(grads), skeys.data_ptr(), spay.data_ptr(), _lib.ptr(rg2), _lib.ptr(rg1),
+            counts.data_ptr(), ws.data_ptr(), ws.numel(), _lib.stream_ptr()), "dfm_embed_bwd")
+        if rowsparse:
+            mod.row_grads = RowSparseGrads(skeys, spay, rg2, rg1, counts, mod._row_base, mod._dims, mod.field_names)
+        else:
+            mod.row_grads = None
+        mod.last_counts = counts
+        return (None, None) + (None,) * ctx.n_inputs + tuple(grads)
+
+
+class FeatureEmbedding(nn.Module):
+    """Three views from one fused pass: ``first_order (B,1)``, ``field_embeddings (B,F,D)``,
+    ``flat_embeddings (B,T)``  (reference: embedding.py:14-126)."""
+
+    def __init__(self, schema, fm_embed_dim: int = 16) -> None:
+        super().__init__()
+        self.schema = schema
+        self.fm_embed_dim = fm_embed_dim
+        self.field_names = list(schema.fields.keys())
+        self.second_order_embeddings = nn.ModuleDict()
+        self.first_order_embeddings = nn.ModuleDict()
+        self.projections = nn.ModuleDict()
+        kinds, dims, vocabs, lens, combs = [], [], [], [], []
+        for name in self.field_names:
+            fs = schema.fields[name]
+            kind = kind_of(fs)
+            if kind not in _lib.KIND:
+                raise ValueError(f"field {name!r}: unknown feature type {kind!r}")
+            d = int(fs.embedding_dim)
+            if kind == "sparse":
+                second = nn.Embedding(fs.vocabulary_size, d, padding_idx=0)
+                first = nn.Embedding(fs.vocabulary_size, 1, padding_idx=0)
+            elif kind == "sequence":
+                if fs.combiner not in _lib.COMBINER:
+                    raise ValueError(f"field {name!r}: unknown combiner {fs.combiner!r}")
+                second = nn.EmbeddingBag(fs.vocabulary_size, d, mode=fs.combiner, padding_idx=0)
+                first = nn.EmbeddingBag(fs.vocabulary_size, 1, mode=fs.combiner, padding_idx=0)
+            else:
+                second, first = nn.Linear(1, d), nn.Linear(1, 1)
+            self.second_order_embeddings[name] = second
+            self.first_order_embeddings[name] = first
+            if d != fm_embed_dim:
+                self.projections[name] = nn.Linear(d, fm_embed_dim, bias=False)
+            kinds.append(_lib.KIND[kind])
+            dims.append(d)
+            vocabs.append(int(fs.vocabulary_size) if kind != "dense" else 0)
+            lens.append(int(fs.max_length) if kind == "sequence" else 1)
+            combs.append(_lib.COMBINER[fs.combiner] if kind == "sequence" else _lib.SUM)
+        self._kinds, self._dims = kinds, dims
+        self._init_weights()
+
+        # extras
+        self.grad_mode = "dense"
+        self.check_indices = False
+        self.row_grads: Optional[RowSparseGrads] = None
+        self.last_counts = None
+        self._live_ctx = None
+        self._status = None
+        self._plan = None
+        self._plan_args = (kinds, dims, vocabs, lens, combs)
+        self.num_fields = len(self.field_names)
+        # static derived sizes (pure host arithmetic, identical to dfm_plan_info)
+        self._T = sum(dims)
+        self._S = sum(l for k, l in zip(kinds, lens) if k != _lib.DENSE)
+        self._A = sum((1 if c == _lib.MEAN else d + 1 if c == _lib.MAX else 0)
+                      for k, d, c in zip(kinds, dims, combs) if k == _lib.SEQUENCE)
+        self._aliasable = all(d == fm_embed_dim for d in dims)
+        self._max_tdim = max([d for k, d in zip(kinds, dims) if k != _lib.DENSE], default=0)
+        rb = [0]
+        for k, v in zip(kinds, vocabs):
+            rb.append(rb[-1] + (v if k != _lib.DENSE else 0))
+        self._row_base = rb
+        # parameter order handed to the kernels: per field (w2, b2, w1, b1, proj)
+        self._param_is_table: List[bool] = []
+        self._slot_of_param: List[int] = []
+
+    # -- reference: embedding.py:66-74 ------------------------------------------------------
+    def _init_weights(self) -> None:
+        for m in self.modules():
+            if isinstance(m, (nn.Embedding, nn.EmbeddingBag)):
+                nn.init.xavier_uniform_(m.weight.data[1:])      # row 0 (padding) stays zero
+            elif isinstance(m, nn.Linear):
+                nn.init.xavier_uniform_(m.weight.data)
+                if m.bias is not None:
+                    nn.init.zeros_(m.bias.data)
+
+    # -- kernel plumbing -----------------------------------------------------------------------
+    def _ensure_plan(self):
+        if self._plan is None:
+            lib = _lib.lib()
+            kinds, dims, vocabs, lens, combs = self._plan_args
+            plan = lib.dfm_plan_create(len(kinds), _lib.i32_array(kinds), _lib.i32_array(dims),
+                                       _lib.i64_array(vocabs), _lib.i32_array(lens), _lib.i32_array(combs),
+                                       int(self.fm_embed_dim))
+            if not plan:
+                raise ValueError(f"dfm_plan_create: {_lib.last_error()}")
+            self._plan = C.c_void_p(plan)
+            info = (C.c_int64 * 8)()
+            _lib.check(lib.dfm_plan_info(self._plan, info), "dfm_plan_info")
+            assert (info[0], info[1], info[3], bool(info[4]), info[5]) == \
+                (self._T, self._S, self._A, self._aliasable, self._max_tdim), "plan/host size mismatch"
+        return self._plan
+
+    def __del__(self):
+        plan = getattr(self, "_plan", None)
+        if plan is not None:
+            try:
+                _lib.lib().dfm_plan_destroy(plan)
+            except Exception:
+                pass
+
+    def _ordered_params(self) -> List[torch.Tensor]:
+        """Present parameters in kernel order; also records which are tables / their slot 5f+k."""
+        out, is_table, slots = [], [], []
+        for f, name in enumerate(self.field_names):
+            second, first = self.second_order_embeddings[name], self.first_order_embeddings[name]
+            dense = self._kinds[f] == _lib.DENSE
+            entries = [(0, second.weight, not dense)]
+            if dense:
+                entries.append((1, second.bias, False))
+            entries.append((2, first.weight, not dense))
+            if dense:
+                entries.append((3, first.bias, False))
+            if name in self.projections:
+                entries.append((4, self.projections[name].weight, False))
+            for k, p, tab in entries:
+                out.append(p)
+                is_table.append(tab)
+                slots.append(5 * f + k)
+        self._param_is_table, self._slot_of_param = is_table, slots
+        return out
+
+    def _param_ptrs(self, tensors) -> C.Array:
+        arr = (C.c_void_p * (5 * self.num_fields))()
+        for slot, t in zip(self._slot_of_param, tensors):
+            arr[slot] = None if t is None else t.data_ptr()
+        return arr
+
+    def _prepare_input(self, name: str, f: int, x: torch.Tensor) -> torch.Tensor:
+        _lib.require_cuda(x, f"batch[{name!r}]")
+        kind = self._kinds[f]
+        if kind == _lib.DENSE:
+            if x.dtype != torch.float32:
+                x = x.float()
+            if x.dim() != 1:
+                x = x.reshape(x.shape[0])
+        else:
+            if x.dtype != torch.int64:
+                x = x.long()
+            L = self._plan_args[3][f]
+            if kind == _lib.SEQUENCE:
+                if x.dim() != 2 or x.shape[1] != L:
+                    raise ValueError(f"batch[{name!r}] must have shape (B, {L}), got {tuple(x.shape)}")
+            elif x.dim() != 1:
+                raise ValueError(f"batch[{name!r}] must have shape (B,), got {tuple(x.shape)}")
+        return x.contiguous()
+
+    def forward_fused(self, batch: Dict[str, torch.Tensor]):
+        """(first_order, field_embeddings, flat, fm_value) -- the FM term comes for free."""
+        self._ensure_plan()
+        params = self._ordered_params()
+        for p in params:
+            _lib.require_cuda(p, "FeatureEmbedding parameter")
+        if self.check_indices and (self._status is None or self._status.device != params[0].device):
+            self._status = torch.zeros(1, dtype=torch.int32, device=params[0].device)
+        inputs = [self._prepare_input(n, f, batch[n]) for f, n in enumerate(self.field_names)]
+        B = inputs[0].shape[0]
+        for n, x in zip(self.field_names, inputs):
+            if x.shape[0] != B:
+                raise ValueError(f"batch[{n!r}] has {x.shape[0]} rows, expected {B}")
+        first, field, flat, fm = _EmbedFn.apply(self, len(inputs), *inputs, *params)
+        field._dfm_fm = (fm, field._version)     # picked up by FMInteraction (same tensor object)
+        return first, field, flat, fm
+
+    def forward(self, batch: Dict[str, torch.Tensor]):
+        first, field, flat, _ = self.forward_fused(batch)
+        return first, field, flat
+
+    # -- row-sparse helpers ------------------------------------------------------------------
+    def materialize_sparse_grads(self) -> None:
+        """Turn ``self.row_grads`` into ``torch.sparse_coo`` ``.grad`` tensors (one host sync),
+        the layout ``nn.Embedding(sparse=True)`` produces and ``torch.optim.SparseAdam`` eats."""
+        if self.row_grads is None:
+            return
+        for name, (rows, g2, g1) in self.row_grads.per_table().items():
+            w2 = self.second_order_embeddings[name].weight
+            w1 = self.first_order_embeddings[name].weight
+            w2.grad = torch.sparse_coo_tensor(rows[None], g2, w2.shape).coalesce()
+            w1.grad = torch.sparse_coo_tensor(rows[None], g1[:, None], w1.shape).coalesce()

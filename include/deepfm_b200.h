@@ -1,0 +1,163 @@
+/*
+ * deepfm_b200.h -- C ABI of libdeepfm_b200.so: the sm_100a CUDA kernels behind the drop-in
+ * FeatureEmbedding / FMInteraction / CIN / MultiHeadSelfAttention modules.
+ *
+ * The reference (CodexploreRepo/deepfm) has no FFI: its hot path is PyTorch nn.Modules calling
+ * ATen.  The boundary a maintainer binds instead is this header -- one entry point per ATen
+ * call-site cluster the kernels replace (cited per function as reference file:line).
+ * INTEGRATION.md shows the ctypes stub and the autograd.Function that sit on top.
+ *
+ * Conventions
+ *   - plain C types only: device pointers, sizes, an opaque host-side plan; no torch types.
+ *   - every function returns DFM_OK (0) or a negative dfm_status; dfm_last_error() gives the
+ *     message for the calling thread.  Nothing throws across the boundary.
+ *   - the CALLER owns every buffer (outputs, workspaces): nothing is allocated or freed here
+ *     except the host-side plan objects.
+ *   - all work is enqueued on `stream` (a cudaStream_t passed as void*); no internal sync.
+ *   - fp32 values, int64 ids, row-major contiguous tensors, exactly as the reference modules
+ *     produce/consume them (deepfm/data/dataset.py:32-37).
+ */
+#ifndef DEEPFM_B200_H
+#define DEEPFM_B200_H
+
+#include <stddef.h>
+#include <stdint.h>
+
+#if defined(__GNUC__)
+#define DFM_API __attribute__((visibility("default")))
+#else
+#define DFM_API
+#endif
+
+#ifdef __cplusplus
+extern "C" {
+#endif
+
+typedef enum dfm_status {
+    DFM_OK = 0,
+    DFM_ERR_INVALID = -1,      /* bad argument (null pointer, negative size, unknown enum) */
+    DFM_ERR_UNSUPPORTED = -2,  /* shape outside what the kernels are instantiated for */
+    DFM_ERR_CUDA = -3,         /* a CUDA runtime call failed; see dfm_last_error() */
+    DFM_ERR_WORKSPACE = -4     /* workspace smaller than dfm_*_workspace_bytes() */
+} dfm_status;
+
+/* Field kinds / combiners: deepfm/data/schema.py:7-21 (FeatureType, FieldSchema.combiner). */
+enum { DFM_SPARSE = 0, DFM_SEQUENCE = 1, DFM_DENSE = 2 };
+enum { DFM_SUM = 0, DFM_MEAN = 1, DFM_MAX = 2 };
+/* Gradient layout of the embedding tables produced by dfm_embed_bwd. */
+enum { DFM_GRAD_DENSE = 0, DFM_GRAD_ROWSPARSE = 1 };
+
+DFM_API const char* dfm_last_error(void);
+DFM_API int dfm_version(void);
+/* Device properties the host side sizes grids with: out[0]=SM count, out[1]=cc major,
+ * out[2]=cc minor, out[3]=max opt-in shared memory per block. */
+DFM_API int dfm_device_info(int device, int64_t out[4]);
+
+/* ------------------------------------------------------------------------------------------
+ * Embedding plan: the immutable per-module description of FeatureEmbedding.__init__
+ * (deepfm/models/layers/embedding.py:20-64).  Host memory only.
+ * ---------------------------------------------------------------------------------------- */
+typedef struct dfm_plan dfm_plan;
+
+DFM_API dfm_plan* dfm_plan_create(int n_fields, const int32_t* kind, const int32_t* dim,
+                          const int64_t* vocab, const int32_t* max_len,
+                          const int32_t* combiner, int fm_dim);
+DFM_API void dfm_plan_destroy(dfm_plan* plan);
+
+/* Derived sizes.  out[0]=T (total_embedding_dim), out[1]=S (id slots per sample: 1 per SPARSE
+ * field, max_len per SEQUENCE field), out[2]=total table rows (sum of vocab over id fields;
+ * also the PAD key), out[3]=aux 4-byte words per sample (bag scales / arg-max positions),
+ * out[4]=1 if flat and field_embeddings are byte-identical (all dims == fm_dim, no projection),
+ * out[5]=max table dim, out[6]=number of sort key bits, out[7]=vector width (4 or 1). */
+DFM_API int dfm_plan_info(const dfm_plan* plan, int64_t out[8]);
+
+/* Integer artefacts (bit-exact contracts, oracle: slot_layout / emit_keys). */
+DFM_API int dfm_plan_slots(const dfm_plan* plan, int32_t* slot_field, int32_t* slot_pos,
+                   int64_t* row_base /* n_fields+1 */);
+
+/* ------------------------------------------------------------------------------------------
+ * K1  FeatureEmbedding.forward fused with FMInteraction.forward
+ *     (embedding.py:76-126 and fm.py:18-23; ATen: embedding, embedding_bag, linear, stack,
+ *      sum, cat, pow, sub, mul).
+ *
+ *   inputs[f] : device pointer to the field's batch column -- int64 (B,) SPARSE,
+ *               int64 (B, max_len) zero-padded SEQUENCE, float (B,) DENSE.
+ *   params[5f+0..4] : second-order weight, second-order bias (DENSE only), first-order weight,
+ *               first-order bias (DENSE only), projection weight (D, d_f) or NULL.
+ *   first_order (B,1), field_emb (B,F,D), flat (B,T): outputs.  field_emb may equal flat when
+ *               dfm_plan_info()[4] == 1; the tensor is then written once.
+ *   fm_out (B,1), fm_sum (B,D): optional (NULL to skip) FM value and per-dim field sum
+ *               (kept for the backward).
+ *   keys (B*S) uint32: optional; global row of every id slot, PAD key for id 0 (input of the
+ *               sorted backward).   aux (B*A) 4-byte words: required iff A > 0.
+ *   status: optional device int32, set to 1 if an id was outside [0, vocab) (the id is then
+ *               treated as padding; the reference raises IndexError on CPU).
+ * ---------------------------------------------------------------------------------------- */
+DFM_API int dfm_embed_fwd(const dfm_plan* plan, int64_t batch, const void* const* inputs,
+                  const float* const* params, float* first_order, float* field_emb,
+                  float* flat, float* fm_out, float* fm_sum, uint32_t* keys, uint32_t* aux,
+                  int32_t* status, void* stream);
+
+/* ------------------------------------------------------------------------------------------
+ * K2  backward of K1 w.r.t. every FeatureEmbedding parameter, fused with the FM backward
+ *     (g_e = g_field + g_fm * (fm_sum - e)) and with the L2 penalty gradient 2*l2*p of
+ *     BaseCTRModel.get_l2_reg_loss (base.py:78-83).  Replaces ATen embedding_dense_backward,
+ *     _embedding_bag_dense_backward, linear backward.
+ *
+ *   Sorted-index segmented reduction: keys are radix-sorted (stable, payload = b*S+slot), equal
+ *   keys form a segment, each segment is summed in payload order by exactly one thread group;
+ *   segments longer than one chunk are stitched by a second fixed-order pass.  No float
+ *   atomics; bit-reproducible.
+ *
+ *   g_first (B,1), g_field (B,F,D), g_flat (B,T), g_fm (B,1): upstream gradients, any may be NULL.
+ *   l2 : lambda (0 disables).  l2_gscale: optional device scalar multiplying the L2 gradient
+ *        (the upstream gradient of the penalty term; NULL = 1).
+ *   mode DFM_GRAD_DENSE: grads[5f+k] are dense gradients with the shapes of params[5f+k]
+ *        (reference semantics: every element receives 2*l2*p, row 0 gets no lookup gradient).
+ *   mode DFM_GRAD_ROWSPARSE: table entries of grads[] are ignored; instead
+ *        sorted_keys/sorted_payload (B*S) hold the sorted pairs and, at the first position of
+ *        every segment, row_grad2 (B*S, max table dim) / row_grad1 (B*S) hold the row's summed
+ *        gradient plus 2*l2*w[row] (L2 on touched rows only).  n_valid (device int64[2]) gets
+ *        {number of non-PAD keys, number of unique rows}.  Non-table entries of grads[] (DENSE
+ *        field Linears, projections) are always written densely.
+ * ---------------------------------------------------------------------------------------- */
+DFM_API size_t dfm_embed_bwd_workspace_bytes(const dfm_plan* plan, int64_t batch);
+
+DFM_API int dfm_embed_bwd(const dfm_plan* plan, int64_t batch, const void* const* inputs,
+                  const float* const* params, const float* g_first, const float* g_field,
+                  const float* g_flat, const float* g_fm, const float* field_emb,
+                  const float* flat, const float* fm_sum, const uint32_t* keys,
+                  const uint32_t* aux, float l2, const float* l2_gscale, int mode,
+                  float* const* grads, uint32_t* sorted_keys, uint32_t* sorted_payload,
+                  float* row_grad2, float* row_grad1, int64_t* n_valid, void* workspace,
+                  size_t workspace_bytes, void* stream);
+
+/* Stand-alone pieces of K2, exposed so the integer artefacts can be checked bit-exactly
+ * against the oracle (emit_keys / sort_pairs / segment_heads). */
+DFM_API int dfm_emit_keys(const dfm_plan* plan, int64_t batch, const void* const* inputs,
+                  uint32_t* keys, void* stream);
+DFM_API int dfm_sort_keys(const dfm_plan* plan, int64_t n, const uint32_t* keys, uint32_t* sorted_keys,
+                  uint32_t* sorted_payload, void* workspace, size_t workspace_bytes,
+                  void* stream);
+
+/* ------------------------------------------------------------------------------------------
+ * FMInteraction stand-alone (fm.py:18-23) for inputs that do not come out of K1.
+ * ---------------------------------------------------------------------------------------- */
+DFM_API int dfm_fm_fwd(const float* e, int64_t batch, int n_fields, int dim, float* out, void* stream);
+DFM_API int dfm_fm_bwd(const float* e, const float* g_out, int64_t batch, int n_fields, int dim,
+               float* g_e, void* stream);
+
+/* ------------------------------------------------------------------------------------------
+ * lambda * sum_p ||p||^2 over a list of tensors (base.py:78-83; ATen norm + pow per param).
+ * Deterministic two-stage reduction; `out` is one device float; workspace >= 4096 floats.
+ * ---------------------------------------------------------------------------------------- */
+DFM_API int dfm_sumsq(int n_tensors, const float* const* ptrs, const int64_t* numel, float scale,
+              float* out, float* workspace, void* stream);
+/* g[i] (+)= coef * scale_dev[0] * p[i]  (the dense L2 gradient when K2 is not in the graph). */
+DFM_API int dfm_axpy(const float* p, int64_t numel, float coef, const float* scale_dev, float* g,
+             int accumulate, void* stream);
+
+#ifdef __cplusplus
+}
+#endif
+#endif /* DEEPFM_B200_H */

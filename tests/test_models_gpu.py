@@ -1,0 +1,62 @@
+"""Whole-model parity on the GPU against the golden fixtures of the unmodified reference:
+logits, loss (BCE mean + L2) and every parameter gradient; reference tests/test_models.py facts."""
+
+import numpy as np
+import pytest
+import torch
+
+from deepfm_b200.models import create_model
+from tests.golden import spec
+from tests.helpers import assert_close_rel, load_golden, split_prefixed, to_dev
+
+pytestmark = pytest.mark.gpu
+
+
+def _model(name):
+    g = load_golden(f"model_{name}.npz")
+    model = create_model(name, spec.golden_schema(), spec.golden_config())
+    model.load_state_dict({k: torch.from_numpy(np.asarray(v)) for k, v in split_prefixed(g, "param/").items()})
+    return g, model.cuda()
+
+
+@pytest.mark.parametrize("name", ["deepfm", "xdeepfm", "attention_deepfm"])
+def test_model_logits_loss_and_grads_match_reference(name):
+    g, model = _model(name)
+    batch = to_dev(spec.golden_batch())
+    labels = torch.from_numpy(spec.golden_labels()).cuda()
+    model.train()
+    logits = model(batch)
+    assert logits.shape == (6, 1)
+    assert_close_rel(logits.detach().cpu(), g["logits"], 1e-5, "logits", floor=1e-6)
+    loss = torch.nn.BCEWithLogitsLoss()(logits.squeeze(1), labels) + model.get_l2_reg_loss()
+    assert abs(loss.item() - float(g["loss"])) < 1e-5 * abs(float(g["loss"]))
+    loss.backward()
+    ref = split_prefixed(g, "grad/")
+    for k, p in model.named_parameters():
+        assert p.grad is not None, k
+        # analytically-zero grads (W_k.bias; Linear bias feeding BatchNorm) are rounding noise
+        assert_close_rel(p.grad.cpu(), ref[k], 1e-4, k, floor=1e-6)
+    model.eval()
+    with torch.no_grad():
+        probs = model.predict(batch)
+    assert probs.min() >= 0 and probs.max() <= 1                      # tests/test_models.py:36-41
+    assert_close_rel(probs.cpu(), g["probs_eval"], 1e-5, "probs")
+    assert model.get_l2_reg_loss().item() > 0                         # tests/test_models.py:43-46
+
+
+def test_train_step_changes_weights_like_reference_trainer():
+    """trainer.py:219-237 step body (BCE + L2, clip, Adam) runs unmodified on the drop-in model."""
+    _, model = _model("deepfm")
+    batch = to_dev(spec.golden_batch())
+    labels = torch.from_numpy(spec.golden_labels()).cuda()
+    opt = torch.optim.Adam(model.parameters(), lr=1e-3)
+    before = {k: v.clone() for k, v in model.state_dict().items()}
+    model.train()
+    for _ in range(2):
+        loss = torch.nn.BCEWithLogitsLoss()(model(batch).squeeze(1), labels) + model.get_l2_reg_loss()
+        opt.zero_grad()
+        loss.backward()
+        torch.nn.utils.clip_grad_norm_(model.parameters(), 1.0)
+        opt.step()
+    changed = [k for k, v in model.state_dict().items() if v.dtype.is_floating_point and not torch.equal(v, before[k])]
+    assert any(k.startswith("embedding.second_order") for k in changed) and any(k.startswith("dnn") for k in changed)
