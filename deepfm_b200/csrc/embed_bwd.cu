@@ -39,7 +39,8 @@ struct BwdArgs {
     const uint32_t* spay;
     float* row_grad2;
     float* row_grad1;
-    float* head2; float* head1; float* tail2; float* tail1;  // per-chunk open partial sums
+    float* head2; float* head1; float* tail2; float* tail1;  // per-unit open partial sums
+    long long* tail_start;
     unsigned long long* counters;  // {n_valid, n_unique}
 };
 
@@ -152,108 +153,163 @@ __device__ __forceinline__ void write_row(const DevPlan& P, const DevGrads& GR, 
     }
 }
 
+// Shared-memory image of one chunk's open partial sums (see segreduce_kernel).
+//   flag bit0: the chunk's first segment started in an earlier chunk; its partial sum is in sH
+//        bit1: that segment covers the whole chunk AND continues into the next one ("through")
+//        bit2: the chunk's last segment starts here and continues into the next chunk; sum in sT
 template <int V>
 __global__ void __launch_bounds__(256)
 segreduce_kernel(const __grid_constant__ DevPlan P, const __grid_constant__ DevGrads GR,
                  const __grid_constant__ BwdArgs a, int G) {
+    extern __shared__ float sm[];
     const int gpb = blockDim.x / G;
     const int gl = threadIdx.x / G;
     const int j = threadIdx.x - gl * G;
-    const long long q = (long long)blockIdx.x * gpb + gl;   // chunk index
-    const long long p0 = q * CHUNK;
-    if (p0 >= a.N) return;
-    const long long p1 = (p0 + CHUNK < a.N) ? p0 + CHUNK : a.N;
+    const int tdim = P.max_tdim, nlane = tdim / V;
+    float* sH = sm;
+    float* sT = sH + gpb * tdim;
+    float* sH1 = sT + gpb * tdim;
+    float* sT1 = sH1 + gpb;
+    int* sFlag = reinterpret_cast<int*>(sT1 + gpb);
+    const long long unit0 = (long long)blockIdx.x * gpb * CHUNK;   // first position of this block
+    const long long p0 = unit0 + (long long)gl * CHUNK;
     const uint32_t PAD = P.pad_key;
     const float coef = a.l2x2 * (a.l2_gscale ? __ldg(a.l2_gscale) : 1.f);
-    const int S = P.S, tdim = P.max_tdim;
+    const int S = P.S;
 
-    uint32_t cur = __ldg(a.skeys + p0);
-    if (cur == PAD) return;                                  // everything from here on is padding
-    const bool head_open = p0 > 0 && __ldg(a.skeys + p0 - 1) == cur;
-    bool started_before = head_open;
+    int flag = 0, f = 0, n_heads = 0, n_valid = 0;
+    uint32_t cur = PAD;
     long long seg_start = p0;
-    int n_heads = head_open ? 0 : 1, n_valid = 0;
-    VecF<V> acc = vzero<V>();
-    float acc1 = 0.f;
-    int f = 0;
-    long long p = p0;
-    for (; p < p1; ++p) {
-        const uint32_t k = __ldg(a.skeys + p);
-        if (k == PAD) break;
-        const uint32_t pay = __ldg(a.spay + p);
-        const long long b = pay / (uint32_t)S;
-        const int s = (int)(pay - (uint32_t)b * (uint32_t)S);
-        if (k != cur) {   // previous segment ended inside this chunk
-            if (started_before) {
-                if (j < tdim / V) vstore<V>(a.head2 + (size_t)q * tdim + j * V, acc);
-                if (j == 0) a.head1[q] = acc1;
-            } else {
-                write_row<V>(P, GR, a, coef, cur, f, seg_start, j, G, acc, acc1);
+    if (p0 < a.N) cur = __ldg(a.skeys + p0);
+    if (cur != PAD) {
+        const long long p1 = (p0 + CHUNK < a.N) ? p0 + CHUNK : a.N;
+        bool started_before = p0 > 0 && __ldg(a.skeys + p0 - 1) == cur;
+        n_heads = started_before ? 0 : 1;
+        VecF<V> acc = vzero<V>();
+        float acc1 = 0.f;
+        long long p = p0;
+        for (; p < p1; ++p) {
+            const uint32_t k = __ldg(a.skeys + p);
+            if (k == PAD) break;
+            const uint32_t pay = __ldg(a.spay + p);
+            const long long b = pay / (uint32_t)S;
+            const int s = (int)(pay - (uint32_t)b * (uint32_t)S);
+            if (k != cur) {   // previous segment ended inside this chunk
+                if (started_before) {
+                    if (j < nlane) vstore<V>(sH + gl * tdim + j * V, acc);
+                    if (j == 0) sH1[gl] = acc1;
+                    flag |= 1;
+                } else {
+                    write_row<V>(P, GR, a, coef, cur, f, seg_start, j, G, acc, acc1);
+                }
+                cur = k; seg_start = p; started_before = false; ++n_heads;
+                acc = vzero<V>(); acc1 = 0.f;
             }
-            cur = k; seg_start = p; started_before = false; ++n_heads;
-            acc = vzero<V>(); acc1 = 0.f;
-        }
-        f = P.slot_field[s];
-        const FieldDev& fd = P.f[f];
-        const int l = P.slot_pos[s];
-        if (j < fd.dim / V) {
-            VecF<V> g = slot_grad<V>(P, a, fd, f, b, l, j);
+            f = P.slot_field[s];
+            const FieldDev& fd = P.f[f];
+            const int l = P.slot_pos[s];
+            if (j < fd.dim / V) {
+                VecF<V> g = slot_grad<V>(P, a, fd, f, b, l, j);
 #pragma unroll
-            for (int v = 0; v < V; ++v) acc.v[v] += g.v[v];
+                for (int v = 0; v < V; ++v) acc.v[v] += g.v[v];
+            }
+            if (j == 0) acc1 += slot_grad1(P, a, fd, b, l);
+            ++n_valid;
         }
-        if (j == 0) acc1 += slot_grad1(P, a, fd, b, l);
-        ++n_valid;
+        const bool continues = (p == p1) && p1 < a.N && __ldg(a.skeys + p1) == cur;
+        if (started_before) {
+            if (j < nlane) vstore<V>(sH + gl * tdim + j * V, acc);
+            if (j == 0) sH1[gl] = acc1;
+            flag |= 1 | (continues ? 2 : 0);
+        } else if (continues) {
+            if (j < nlane) vstore<V>(sT + gl * tdim + j * V, acc);
+            if (j == 0) sT1[gl] = acc1;
+            flag |= 4;
+        } else {
+            write_row<V>(P, GR, a, coef, cur, f, seg_start, j, G, acc, acc1);
+        }
     }
-    const bool continues = (p == p1) && p1 < a.N && __ldg(a.skeys + p1) == cur;
-    if (started_before) {
-        if (j < tdim / V) vstore<V>(a.head2 + (size_t)q * tdim + j * V, acc);
-        if (j == 0) a.head1[q] = acc1;
-    } else if (continues) {
-        if (j < tdim / V) vstore<V>(a.tail2 + (size_t)q * tdim + j * V, acc);
-        if (j == 0) a.tail1[q] = acc1;
-    } else {
-        write_row<V>(P, GR, a, coef, cur, f, seg_start, j, G, acc, acc1);
+    if (j == 0) sFlag[gl] = flag;
+    __syncthreads();
+
+    // ---- in-block stitching, fixed order: chunk gl, gl+1, ...
+    // role 0: this chunk's tail segment (starts here, continues);  role 1 (chunk 0 only): the
+    // block's head segment (started in an earlier block).
+    for (int role = 0; role < 2; ++role) {
+        const bool is_tail = role == 0;
+        if (is_tail ? !(flag & 4) : !(gl == 0 && (flag & 1))) continue;
+        VecF<V> acc = vzero<V>();
+        float acc1 = 0.f;
+        const float* src = is_tail ? sT : sH;
+        if (j < nlane) acc = *reinterpret_cast<const VecF<V>*>(src + gl * tdim + j * V);
+        if (j == 0) acc1 = is_tail ? sT1[gl] : sH1[gl];
+        bool closed = !is_tail && !(flag & 2);
+        if (!closed) {
+            for (int g2 = gl + 1; g2 < gpb; ++g2) {
+                const int f2 = sFlag[g2];
+                if (j < nlane) {
+                    const VecF<V> h = *reinterpret_cast<const VecF<V>*>(sH + g2 * tdim + j * V);
+#pragma unroll
+                    for (int v = 0; v < V; ++v) acc.v[v] += h.v[v];
+                }
+                if (j == 0) acc1 += sH1[g2];
+                if (!(f2 & 2)) { closed = true; break; }
+            }
+        }
+        if (is_tail && closed) {
+            write_row<V>(P, GR, a, coef, cur, f, seg_start, j, G, acc, acc1);
+        } else {
+            // open at block level: the segment started in an earlier block (head) or leaves this
+            // block (tail, not closed); the unit stitch pass finishes it
+            float* dst2 = is_tail ? a.tail2 : a.head2;
+            float* dst1 = is_tail ? a.tail1 : a.head1;
+            if (j < nlane) vstore<V>(dst2 + (size_t)blockIdx.x * tdim + j * V, acc);
+            if (j == 0) {
+                dst1[blockIdx.x] = acc1;
+                if (is_tail) a.tail_start[blockIdx.x] = seg_start;
+            }
+        }
     }
-    if (j == 0) {
+    if (j == 0 && (n_valid | n_heads)) {
         atomicAdd(a.counters + 0, (unsigned long long)n_valid);   // integer: order-independent
         atomicAdd(a.counters + 1, (unsigned long long)n_heads);
     }
 }
 
-// One lane group per chunk; only the chunk in which a multi-chunk segment STARTS does work.
+// One lane group per unit (= the positions one segreduce block covered); only the unit in which a
+// multi-unit segment STARTS does work: it adds the later units' head partials in unit order.
 template <int V>
 __global__ void __launch_bounds__(256)
 stitch_kernel(const __grid_constant__ DevPlan P, const __grid_constant__ DevGrads GR,
-              const __grid_constant__ BwdArgs a, int G) {
+              const __grid_constant__ BwdArgs a, int G, long long unit) {
     const int gpb = blockDim.x / G;
     const int gl = threadIdx.x / G;
     const int j = threadIdx.x - gl * G;
-    const long long q = (long long)blockIdx.x * gpb + gl;
-    const long long p0 = q * CHUNK;
+    const long long u = (long long)blockIdx.x * gpb + gl;
+    const long long p0 = u * unit;
     if (p0 >= a.N) return;
-    const long long p1 = p0 + CHUNK;
-    if (p1 >= a.N) return;                                   // last chunk cannot continue
+    const long long p1 = p0 + unit;
+    if (p1 >= a.N) return;                                   // the last unit cannot continue
     const uint32_t k = __ldg(a.skeys + p1 - 1);
-    if (k == P.pad_key || __ldg(a.skeys + p1) != k) return;  // no segment leaves this chunk
+    if (k == P.pad_key || __ldg(a.skeys + p1) != k) return;  // no segment leaves this unit
     if (__ldg(a.skeys + p0) == k && p0 > 0 && __ldg(a.skeys + p0 - 1) == k) return;  // not the owner
-    const int tdim = P.max_tdim;
+    const int tdim = P.max_tdim, nlane = tdim / V;
     const float coef = a.l2x2 * (a.l2_gscale ? __ldg(a.l2_gscale) : 1.f);
     VecF<V> acc = vzero<V>();
-    if (j < tdim / V) acc = vload<V>(a.tail2 + (size_t)q * tdim + j * V);
-    float acc1 = j == 0 ? a.tail1[q] : 0.f;
-    for (long long qq = q + 1;; ++qq) {
-        if (j < tdim / V) {
-            VecF<V> h = vload<V>(a.head2 + (size_t)qq * tdim + j * V);
+    if (j < nlane) acc = vload<V>(a.tail2 + (size_t)u * tdim + j * V);
+    float acc1 = j == 0 ? a.tail1[u] : 0.f;
+    for (long long uu = u + 1;; ++uu) {
+        if (j < nlane) {
+            VecF<V> h = vload<V>(a.head2 + (size_t)uu * tdim + j * V);
 #pragma unroll
             for (int v = 0; v < V; ++v) acc.v[v] += h.v[v];
         }
-        if (j == 0) acc1 += a.head1[qq];
-        const long long e = (qq + 1) * CHUNK;
+        if (j == 0) acc1 += a.head1[uu];
+        const long long e = (uu + 1) * unit;
         if (e < a.N && __ldg(a.skeys + e - 1) == k && __ldg(a.skeys + e) == k) continue;
         break;
     }
-    long long hp = p1 - 1;
-    while (hp > p0 && __ldg(a.skeys + hp - 1) == k) --hp;
+    const long long hp = a.tail_start[u];
     const uint32_t pay = __ldg(a.spay + hp);
     const int s = (int)(pay % (uint32_t)P.S);
     write_row<V>(P, GR, a, coef, k, P.slot_field[s], hp, j, G, acc, acc1);
@@ -263,9 +319,11 @@ stitch_kernel(const __grid_constant__ DevPlan P, const __grid_constant__ DevGrad
 struct PgField {
     int f, nvals, part_off;   // part_off: offset (floats) of this field inside one slice's partials
 };
+// DENSE fields without projection are streamed (dense_stream_kernel); fields with a projection
+// go through the shared-memory tile kernel (pgrads_kernel).  pf[] lists the tile fields first.
 struct PgArgs {
     PgField pf[MAX_FIELDS];
-    int n_pf, n_slices, vals_per_slice;
+    int n_pf, n_tile, n_slices, vals_per_slice;
     long long slice_len;
     float* partials;          // (n_slices, vals_per_slice)
 };
@@ -355,6 +413,67 @@ pgrads_kernel(const __grid_constant__ DevPlan P, const __grid_constant__ BwdArgs
     for (int o = tid; o < pfd.nvals; o += PG_THREADS) out[o] = s_acc[o];
 }
 
+// DENSE field without projection: g_raw = g_flat + g_field + g_fm (fm_sum - e) is streamed once with
+// 128-bit loads; lane c of a sample group owns dims [cV, cV+V) and keeps sum(g_raw * x), sum(g_raw)
+// in registers; one fixed-order shared-memory reduction over the sample groups at the end.
+template <int V>
+__global__ void __launch_bounds__(PG_THREADS)
+dense_stream_kernel(const __grid_constant__ DevPlan P, const __grid_constant__ BwdArgs a,
+                    const __grid_constant__ PgArgs pg, int lanes) {
+    extern __shared__ float sm[];
+    const PgField pfd = pg.pf[pg.n_tile + blockIdx.y];
+    const int f = pfd.f;
+    const FieldDev& fd = P.f[f];
+    const int D = P.D, d = fd.dim, F = P.n_fields, nch = d / V;
+    const int rows = PG_THREADS / lanes;
+    const int s = threadIdx.x / lanes, c = threadIdx.x - s * lanes;
+    const long long b_lo = (long long)blockIdx.x * pg.slice_len;
+    const long long b_hi = (b_lo + pg.slice_len < a.B) ? b_lo + pg.slice_len : a.B;
+    VecF<V> aw = vzero<V>(), ab = vzero<V>();
+    float a1w = 0.f, a1b = 0.f;
+    if (c < nch) {
+        for (long long b = b_lo + s; b < b_hi; b += rows) {
+            const float x = __ldg(reinterpret_cast<const float*>(fd.in) + b);
+            VecF<V> g = vzero<V>();
+            if (a.g_flat) g = vload_stream<V>(a.g_flat + (size_t)b * P.T + fd.flat_off + c * V);
+            const size_t eoff = ((size_t)b * F + f) * D + c * V;
+            if (a.g_field) {
+                const VecF<V> t = vload_stream<V>(a.g_field + eoff);
+#pragma unroll
+                for (int v = 0; v < V; ++v) g.v[v] += t.v[v];
+            }
+            if (a.g_fm) {
+                const float gfm = __ldg(a.g_fm + b);
+                const VecF<V> sv = vload<V>(a.fm_sum + (size_t)b * D + c * V);
+                const VecF<V> e = vload_stream<V>(a.fe + eoff);
+#pragma unroll
+                for (int v = 0; v < V; ++v) g.v[v] = fmaf(gfm, sv.v[v] - e.v[v], g.v[v]);
+            }
+#pragma unroll
+            for (int v = 0; v < V; ++v) { aw.v[v] = fmaf(g.v[v], x, aw.v[v]); ab.v[v] += g.v[v]; }
+            if (c == 0 && a.g_first) {
+                const float g1 = __ldg(a.g_first + b);
+                a1w = fmaf(g1, x, a1w);
+                a1b += g1;
+            }
+        }
+    }
+    // sm[s][0..d) = aw, [d..2d) = ab, [2d] = a1w, [2d+1] = a1b
+    const int stride = 2 * d + 2;
+    if (c < nch) {
+#pragma unroll
+        for (int v = 0; v < V; ++v) { sm[s * stride + c * V + v] = aw.v[v]; sm[s * stride + d + c * V + v] = ab.v[v]; }
+        if (c == 0) { sm[s * stride + 2 * d] = a1w; sm[s * stride + 2 * d + 1] = a1b; }
+    }
+    __syncthreads();
+    float* out = pg.partials + (size_t)blockIdx.x * pg.vals_per_slice + pfd.part_off;
+    for (int o = threadIdx.x; o < stride; o += PG_THREADS) {
+        float acc = 0.f;
+        for (int r = 0; r < rows; ++r) acc += sm[r * stride + o];
+        out[o] = acc;
+    }
+}
+
 __global__ void pgrads_finish_kernel(const __grid_constant__ DevPlan P, const __grid_constant__ DevGrads GR,
                                      const __grid_constant__ BwdArgs a, const __grid_constant__ PgArgs pg) {
     const PgField pfd = pg.pf[blockIdx.y];
@@ -377,7 +496,7 @@ __global__ void pgrads_finish_kernel(const __grid_constant__ DevPlan P, const __
 
 // ---- host-side workspace carving --------------------------------------------------------
 struct BwdLayout {
-    size_t cub_bytes, off_cub, off_payload, off_head2, off_head1, off_tail2, off_tail1, off_counters,
+    size_t cub_bytes, off_cub, off_payload, off_head2, off_head1, off_tail2, off_tail1, off_tstart, off_counters,
         off_partials, total;
     long long n_chunks;
     int n_slices, vals_per_slice;
@@ -405,7 +524,7 @@ static int make_layout(const dfm_plan* plan, long long B, BwdLayout& L) {
     const long long N = B * plan->S;
     L.cub_bytes = 0;
     if (N > 0) { int rc = sort_temp_bytes(N, plan->key_bits, &L.cub_bytes); if (rc) return rc; }
-    L.n_chunks = ceil_div(N > 0 ? N : 1, CHUNK);
+    L.n_chunks = ceil_div(N > 0 ? N : 1, 8 * CHUNK);   // units: >= 8 chunks per segreduce block
     int vals = 0, n_pf = 0;
     for (int f = 0; f < plan->n_fields; ++f) { int n = pg_count_vals(plan, f); if (n) { vals += n; ++n_pf; } }
     L.vals_per_slice = vals;
@@ -423,6 +542,7 @@ static int make_layout(const dfm_plan* plan, long long B, BwdLayout& L) {
     L.off_head1 = take((size_t)L.n_chunks * 4);
     L.off_tail2 = take((size_t)L.n_chunks * plan->max_tdim * 4);
     L.off_tail1 = take((size_t)L.n_chunks * 4);
+    L.off_tstart = take((size_t)L.n_chunks * 8);
     L.off_counters = take(16);
     L.off_partials = take((size_t)L.n_slices * vals * 4);
     L.total = off;
@@ -475,11 +595,11 @@ int dfm_embed_bwd(const dfm_plan* plan, int64_t batch, const void* const* inputs
     DFM_REQUIRE(batch >= 0, DFM_ERR_INVALID, "dfm_embed_bwd: negative batch");
     DFM_REQUIRE(mode == DFM_GRAD_DENSE || mode == DFM_GRAD_ROWSPARSE, DFM_ERR_INVALID, "dfm_embed_bwd: unknown mode %d", mode);
     DFM_REQUIRE(!g_fm || (fm_sum && field_emb), DFM_ERR_INVALID, "dfm_embed_bwd: g_fm needs fm_sum and field_emb");
-    DFM_REQUIRE(plan->A == 0 || aux, DFM_ERR_INVALID, "dfm_embed_bwd: aux required");
-    DFM_REQUIRE(plan->S == 0 || (sorted_keys && sorted_payload && keys), DFM_ERR_INVALID, "dfm_embed_bwd: key buffers required");
-    DFM_REQUIRE(mode == DFM_GRAD_DENSE || plan->S == 0 || (row_grad2 && row_grad1 && n_valid), DFM_ERR_INVALID,
+    DFM_REQUIRE(batch == 0 || plan->A == 0 || aux, DFM_ERR_INVALID, "dfm_embed_bwd: aux required");
+    DFM_REQUIRE(batch == 0 || plan->S == 0 || (sorted_keys && sorted_payload && keys), DFM_ERR_INVALID, "dfm_embed_bwd: key buffers required");
+    DFM_REQUIRE(batch == 0 || mode == DFM_GRAD_DENSE || plan->S == 0 || (row_grad2 && row_grad1 && n_valid), DFM_ERR_INVALID,
                 "dfm_embed_bwd: row-sparse outputs required");
-    DFM_REQUIRE(plan->n_proj_expected == 0 || flat, DFM_ERR_INVALID, "dfm_embed_bwd: flat needed for projection grads");
+    DFM_REQUIRE(batch == 0 || plan->n_proj_expected == 0 || flat, DFM_ERR_INVALID, "dfm_embed_bwd: flat needed for projection grads");
     BwdLayout L;
     int rc = make_layout(plan, batch, L);
     if (rc) return rc;
@@ -523,6 +643,7 @@ int dfm_embed_bwd(const dfm_plan* plan, int64_t batch, const void* const* inputs
     a.skeys = sorted_keys; a.spay = sorted_payload; a.row_grad2 = row_grad2; a.row_grad1 = row_grad1;
     a.head2 = reinterpret_cast<float*>(ws + L.off_head2); a.head1 = reinterpret_cast<float*>(ws + L.off_head1);
     a.tail2 = reinterpret_cast<float*>(ws + L.off_tail2); a.tail1 = reinterpret_cast<float*>(ws + L.off_tail1);
+    a.tail_start = reinterpret_cast<long long*>(ws + L.off_tstart);
     a.counters = n_valid ? reinterpret_cast<unsigned long long*>(n_valid)
                          : reinterpret_cast<unsigned long long*>(ws + L.off_counters);
     const int fill_blocks = 8 * sm_count();
@@ -546,32 +667,47 @@ int dfm_embed_bwd(const dfm_plan* plan, int64_t batch, const void* const* inputs
                            L.off_payload + (size_t)N * 4 - L.off_cub, stream);
         if (rc) return rc;
         const int gpb = 256 / G;
-        const unsigned blocks = (unsigned)ceil_div(L.n_chunks, gpb);
+        const long long unit = (long long)gpb * CHUNK;               // positions per segreduce block
+        const long long n_units = ceil_div(N, unit);
+        const unsigned blocks = (unsigned)n_units;
+        const unsigned sblocks = (unsigned)ceil_div(n_units, gpb);
+        const size_t smem = (size_t)gpb * (2 * plan->max_tdim + 2) * 4 + (size_t)gpb * 4;
         if (V == 4) {
-            segreduce_kernel<4><<<blocks, 256, 0, st>>>(*P, *GR, a, G);
-            stitch_kernel<4><<<blocks, 256, 0, st>>>(*P, *GR, a, G);
+            segreduce_kernel<4><<<blocks, 256, smem, st>>>(*P, *GR, a, G);
+            stitch_kernel<4><<<sblocks, 256, 0, st>>>(*P, *GR, a, G, unit);
         } else {
-            segreduce_kernel<1><<<blocks, 256, 0, st>>>(*P, *GR, a, G);
-            stitch_kernel<1><<<blocks, 256, 0, st>>>(*P, *GR, a, G);
+            segreduce_kernel<1><<<blocks, 256, smem, st>>>(*P, *GR, a, G);
+            stitch_kernel<1><<<sblocks, 256, 0, st>>>(*P, *GR, a, G, unit);
         }
         DFM_CHECK_LAUNCH();
     } else if (n_valid) {
         DFM_CHECK_CUDA(cudaMemsetAsync(n_valid, 0, 16, st));
     }
-    // 3. DENSE-field Linear and projection gradients
+    // 3. DENSE-field Linear and projection gradients (tile fields first, then streamed fields)
     PgArgs* pg = new PgArgs;
     struct G2 { PgArgs* p; ~G2() { delete p; } } g2{pg};
     memset(pg, 0, sizeof(*pg));
-    int max_smem_floats = 0, max_vals = 0;
-    for (int f = 0; f < plan->n_fields; ++f) {
-        const int n = pg_count_vals(plan, f);
-        if (!n) continue;
-        PgField& pf = pg->pf[pg->n_pf];
-        pf.f = f; pf.nvals = n; pf.part_off = pg->vals_per_slice;
-        pg->vals_per_slice += n; pg->n_pf++;
-        const int fl = PG_TILE * (plan->fm_dim + 2 * plan->dim[f] + 2) + n;
-        if (fl > max_smem_floats) max_smem_floats = fl;
-        if (n > max_vals) max_vals = n;
+    int max_smem_floats = 0, max_vals = 0, stream_smem_floats = 0, stream_lanes = 1;
+    auto streamable = [&](int f) {
+        return plan->kind[f] == DFM_DENSE && plan->dim[f] == plan->fm_dim && plan->dim[f] / V <= 32;
+    };
+    for (int pass = 0; pass < 2; ++pass) {
+        for (int f = 0; f < plan->n_fields; ++f) {
+            const int n = pg_count_vals(plan, f);
+            if (!n || (streamable(f) ? 1 : 0) != pass) continue;
+            PgField& pf = pg->pf[pg->n_pf];
+            pf.f = f; pf.nvals = n; pf.part_off = pg->vals_per_slice;
+            pg->vals_per_slice += n; pg->n_pf++;
+            if (n > max_vals) max_vals = n;
+            if (pass == 0) {
+                pg->n_tile++;
+                const int fl = PG_TILE * (plan->fm_dim + 2 * plan->dim[f] + 2) + n;
+                if (fl > max_smem_floats) max_smem_floats = fl;
+            } else {
+                stream_lanes = next_pow2(plan->dim[f] / V);   // every streamed field has dim == fm_dim
+                stream_smem_floats = (PG_THREADS / stream_lanes) * (2 * plan->dim[f] + 2);
+            }
+        }
     }
     if (pg->n_pf > 0) {
         pg->n_slices = batch > 0 ? L.n_slices : 0; pg->slice_len = L.slice_len;
@@ -580,7 +716,14 @@ int dfm_embed_bwd(const dfm_plan* plan, int64_t batch, const void* const* inputs
         DFM_REQUIRE(smem <= 200 * 1024, DFM_ERR_UNSUPPORTED, "dfm_embed_bwd: projection/dense grads need %zu B shared memory", smem);
         if (smem > 48 * 1024)
             DFM_CHECK_CUDA(cudaFuncSetAttribute(pgrads_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
-        if (batch > 0) pgrads_kernel<<<dim3(pg->n_slices, pg->n_pf), PG_THREADS, smem, st>>>(*P, a, *pg);
+        const int n_stream = pg->n_pf - pg->n_tile;
+        if (batch > 0 && pg->n_tile > 0)
+            pgrads_kernel<<<dim3(pg->n_slices, pg->n_tile), PG_THREADS, smem, st>>>(*P, a, *pg);
+        if (batch > 0 && n_stream > 0) {
+            const size_t ssm = (size_t)stream_smem_floats * 4;
+            if (V == 4) dense_stream_kernel<4><<<dim3(pg->n_slices, n_stream), PG_THREADS, ssm, st>>>(*P, a, *pg, stream_lanes);
+            else dense_stream_kernel<1><<<dim3(pg->n_slices, n_stream), PG_THREADS, ssm, st>>>(*P, a, *pg, stream_lanes);
+        }
         pgrads_finish_kernel<<<dim3((unsigned)ceil_div(max_vals, 128), pg->n_pf), 128, 0, st>>>(*P, *GR, a, *pg);
         DFM_CHECK_LAUNCH();
     }

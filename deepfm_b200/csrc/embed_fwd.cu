@@ -165,7 +165,7 @@ embed_fwd_kernel(const __grid_constant__ DevPlan P, long long B, int G, int smem
 #pragma unroll
                         for (int v = 0; v < V; ++v) {
                             Sacc.v[v] += r[u].v[v];
-                            Qacc.v[v] += r[u].v[v] * r[u].v[v];
+                            Qacc.v[v] += __fmul_rn(r[u].v[v], r[u].v[v]);
                         }
                 }
                 f += 4;
@@ -203,7 +203,7 @@ embed_fwd_kernel(const __grid_constant__ DevPlan P, long long B, int G, int smem
 #pragma unroll
                 for (int v = 0; v < V; ++v) {
                     Sacc.v[v] += r.v[v];
-                    Qacc.v[v] += r.v[v] * r.v[v];
+                    Qacc.v[v] += __fmul_rn(r.v[v], r.v[v]);
                 }
             } else {
 #pragma unroll
@@ -224,7 +224,7 @@ embed_fwd_kernel(const __grid_constant__ DevPlan P, long long B, int G, int smem
 #pragma unroll
                 for (int v = 0; v < V; ++v) {
                     Sacc.v[v] += e.v[v];
-                    Qacc.v[v] += e.v[v] * e.v[v];
+                    Qacc.v[v] += __fmul_rn(e.v[v], e.v[v]);
                 }
             }
             __syncwarp(gmask);
@@ -260,7 +260,7 @@ embed_fwd_kernel(const __grid_constant__ DevPlan P, long long B, int G, int smem
     float part = 0.f;
     if (j < nch_e) {
 #pragma unroll
-        for (int v = 0; v < V; ++v) part += Sacc.v[v] * Sacc.v[v] - Qacc.v[v];
+        for (int v = 0; v < V; ++v) part += __fmul_rn(Sacc.v[v], Sacc.v[v]) - Qacc.v[v];   // no contraction: one field => exactly 0
     }
     part = group_sum(part, G, gmask);
     fo_acc = group_sum(fo_acc, G, gmask);
@@ -405,9 +405,10 @@ int dfm_embed_fwd(const dfm_plan* plan, int64_t batch, const void* const* inputs
                   const float* const* params, float* first_order, float* field_emb,
                   float* flat, float* fm_out, float* fm_sum, uint32_t* keys, uint32_t* aux,
                   int32_t* status, void* stream) {
+    DFM_REQUIRE(batch >= 0, DFM_ERR_INVALID, "dfm_embed_fwd: negative batch");
+    if (batch == 0 && plan) return DFM_OK;   // empty tensors have null data pointers
     DFM_REQUIRE(plan && inputs && params && first_order && field_emb && flat, DFM_ERR_INVALID,
                 "dfm_embed_fwd: null argument");
-    DFM_REQUIRE(batch >= 0, DFM_ERR_INVALID, "dfm_embed_fwd: negative batch");
     DFM_REQUIRE(plan->A == 0 || aux, DFM_ERR_INVALID, "dfm_embed_fwd: aux buffer required (%d words/sample)", plan->A);
     DFM_REQUIRE(field_emb != flat || plan->aliasable, DFM_ERR_INVALID,
                 "dfm_embed_fwd: field_emb may alias flat only when every dim == fm_dim");

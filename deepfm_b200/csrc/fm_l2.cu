@@ -17,9 +17,9 @@ fm_fwd_kernel(const float* __restrict__ e, long long B, int F, int D, float* __r
         for (int f = 0; f < F; ++f) {
             const float x = __ldg(eb + (size_t)f * D + d);
             s += x;
-            q = fmaf(x, x, q);
+            q += __fmul_rn(x, x);
         }
-        part += s * s - q;
+        part += __fmul_rn(s, s) - q;   // no FMA contraction: a single field must give exactly 0
     }
     for (int o = 16; o > 0; o >>= 1) part += __shfl_xor_sync(0xffffffffu, part, o);
     if (lane == 0) out[b] = 0.5f * part;

@@ -73,13 +73,12 @@ class _EmbedFn(torch.autograd.Function):
     """forward = K1 (dfm_embed_fwd), backward = K2 (dfm_embed_bwd)."""
 
     @staticmethod
-    def forward(ctx, mod: "FeatureEmbedding", n_inputs: int, *tensors):
+    def forward(ctx, mod: "FeatureEmbedding", n_inputs: int, need_bwd: bool, *tensors):
         inputs, params = tensors[:n_inputs], tensors[n_inputs:]
         lib = _lib.lib()
         dev = params[0].device
         B = inputs[0].shape[0]
         F, D, T, S, A = mod.num_fields, mod.fm_embed_dim, mod._T, mod._S, mod._A
-        need_bwd = torch.is_grad_enabled() and any(p.requires_grad for p in params)
         flat = torch.empty((B, T), device=dev, dtype=torch.float32)
         field = flat.view(B, F, D) if mod._aliasable else torch.empty((B, F, D), device=dev, dtype=torch.float32)
         first = torch.empty((B, 1), device=dev, dtype=torch.float32)
@@ -150,7 +149,7 @@ class _EmbedFn(torch.autograd.Function):
         else:
             mod.row_grads = None
         mod.last_counts = counts
-        return (None, None) + (None,) * ctx.n_inputs + tuple(grads)
+        return (None, None, None) + (None,) * ctx.n_inputs + tuple(grads)
 
 
 class FeatureEmbedding(nn.Module):
@@ -313,7 +312,8 @@ class FeatureEmbedding(nn.Module):
         for n, x in zip(self.field_names, inputs):
             if x.shape[0] != B:
                 raise ValueError(f"batch[{n!r}] has {x.shape[0]} rows, expected {B}")
-        first, field, flat, fm = _EmbedFn.apply(self, len(inputs), *inputs, *params)
+        need_bwd = torch.is_grad_enabled() and any(p.requires_grad for p in params)
+        first, field, flat, fm = _EmbedFn.apply(self, len(inputs), need_bwd, *inputs, *params)
         field._dfm_fm = (fm, field._version)     # picked up by FMInteraction (same tensor object)
         return first, field, flat, fm
 
