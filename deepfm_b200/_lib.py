@@ -44,11 +44,11 @@ SIGNATURES = {
     "dfm_fm_bwd": (C.c_int, [_vp, _vp, _i64, C.c_int, C.c_int, _vp, _vp]),
     "dfm_sumsq": (C.c_int, [C.c_int, _pp, _pi64, _f32, _vp, _vp, _vp]),
     "dfm_axpy": (C.c_int, [_vp, _i64, _f32, _vp, _vp, C.c_int, _vp]),
-    "dfm_cin_workspace_bytes": (_sz, [_i64, C.c_int, C.c_int, C.c_int, _pi32, C.c_int, C.c_int]),
+    "dfm_cin_sizes": (C.c_int, [C.c_int, C.c_int, C.c_int, _pi32, C.c_int, _i64, _pi64]),
     "dfm_cin_fwd": (C.c_int, [_vp, _i64, C.c_int, C.c_int, C.c_int, _pi32, C.c_int, _pp, _pp, C.c_int,
-                              _vp, _vp, _sz, _vp]),
-    "dfm_cin_bwd": (C.c_int, [_vp, _vp, _i64, C.c_int, C.c_int, C.c_int, _pi32, C.c_int, _pp, _pp, C.c_int,
-                              _vp, _pp, _pp, _vp, _sz, _vp]),
+                              _vp, _vp, _vp]),
+    "dfm_cin_bwd": (C.c_int, [_vp, _vp, _i64, C.c_int, C.c_int, C.c_int, _pi32, C.c_int, _pp, C.c_int,
+                              _vp, _vp, _pp, _pp, _vp, _sz, _vp]),
     "dfm_attn_workspace_bytes": (_sz, [_i64, C.c_int, C.c_int, C.c_int, C.c_int]),
     "dfm_attn_fwd": (C.c_int, [_vp, _i64, C.c_int, C.c_int, C.c_int, C.c_int, C.c_int, _pp, _vp, _vp]),
     "dfm_attn_bwd": (C.c_int, [_vp, _vp, _i64, C.c_int, C.c_int, C.c_int, C.c_int, C.c_int, _pp, _vp, _pp,

@@ -157,6 +157,43 @@ DFM_API int dfm_sumsq(int n_tensors, const float* const* ptrs, const int64_t* nu
 DFM_API int dfm_axpy(const float* p, int64_t numel, float coef, const float* scale_dev, float* g,
              int accumulate, void* stream);
 
+/* ------------------------------------------------------------------------------------------
+ * CIN (deepfm/models/layers/cin.py:26-105; ATen einsum + reshape + conv1d(k=1) + relu + split +
+ * sum).  layer_sizes[i] = L_i; weights[i] (L_i, K_i) with K_i = H_i * F, channel k = h*F + f;
+ * split is [direct first, next second] (cin.py:93-96).  The (B, H*F, D) outer product is never
+ * written to memory.  precision 0 = fp32 CUDA cores (reference-exact up to summation order).
+ *   dfm_cin_sizes: out[0] = output_dim, out[1] = bytes of `acts` (post-ReLU activations of every
+ *   layer, kept for the backward), out[2] = bytes of the backward workspace, out[3] = activation
+ *   floats per sample.
+ * ---------------------------------------------------------------------------------------- */
+DFM_API int dfm_cin_sizes(int n_fields, int dim, int n_layers, const int32_t* layer_sizes,
+                          int split_half, int64_t batch, int64_t out[4]);
+DFM_API int dfm_cin_fwd(const float* x0, int64_t batch, int n_fields, int dim, int n_layers,
+                        const int32_t* layer_sizes, int split_half, const float* const* weights,
+                        const float* const* biases, int precision, float* out, float* acts,
+                        void* stream);
+DFM_API int dfm_cin_bwd(const float* x0, const float* g_out, int64_t batch, int n_fields, int dim,
+                        int n_layers, const int32_t* layer_sizes, int split_half,
+                        const float* const* weights, int precision, const float* acts, float* g_x0,
+                        float* const* g_weights, float* const* g_biases, void* workspace,
+                        size_t workspace_bytes, void* stream);
+
+/* ------------------------------------------------------------------------------------------
+ * One _AttentionBlock (deepfm/models/layers/attention.py:70-120) fused in shared memory.
+ * params[0..9] = W_q.weight (A,D), W_q.bias, W_k.weight, W_k.bias, W_v.weight, W_v.bias,
+ * W_out.weight (D,A), W_out.bias, layer_norm.weight, layer_norm.bias (last two only when
+ * use_residual).  The backward recomputes the forward from x; g_params has the same order.
+ * ---------------------------------------------------------------------------------------- */
+DFM_API size_t dfm_attn_workspace_bytes(int64_t batch, int n_fields, int dim, int attention_dim,
+                                        int heads);
+DFM_API int dfm_attn_fwd(const float* x, int64_t batch, int n_fields, int dim, int attention_dim,
+                         int heads, int use_residual, const float* const* params, float* out,
+                         void* stream);
+DFM_API int dfm_attn_bwd(const float* x, const float* g_out, int64_t batch, int n_fields, int dim,
+                         int attention_dim, int heads, int use_residual,
+                         const float* const* params, float* g_x, float* const* g_params,
+                         void* workspace, size_t workspace_bytes, void* stream);
+
 #ifdef __cplusplus
 }
 #endif

@@ -1,0 +1,128 @@
+"""GPU parity of the CIN and field self-attention kernels against the golden fixtures produced by
+the unmodified reference modules and against the numpy oracle (fp32: forward 1e-5, gradients 1e-4
+per-tensor max-norm relative); reference tests/test_layers.py:143-210 facts."""
+
+import numpy as np
+import pytest
+import torch
+
+from deepfm_b200.layers.attention import MultiHeadSelfAttention
+from deepfm_b200.layers.cin import CIN
+from oracle import deepfm_oracle as O
+from tests.helpers import assert_close_rel, load_golden, split_prefixed
+
+pytestmark = pytest.mark.gpu
+
+
+@pytest.mark.parametrize("tag", ["split", "nosplit", "one"])
+def test_cin_golden(tag):
+    g = load_golden(f"cin_{tag}.npz")
+    sizes, split = [int(v) for v in g["sizes"]], bool(g["split"])
+    cin = CIN(num_fields=4, embed_dim=6, layer_sizes=sizes, split_half=split)
+    with torch.no_grad():
+        for i, c in enumerate(cin.conv_layers):
+            c.weight.copy_(torch.from_numpy(g[f"w{i}"]))
+            c.bias.copy_(torch.from_numpy(g[f"b{i}"]))
+    cin = cin.cuda()
+    x = torch.from_numpy(g["x"]).cuda().requires_grad_(True)
+    out = cin(x)
+    assert out.shape == g["out"].shape
+    assert_close_rel(out.detach().cpu(), g["out"], 1e-5, "cin out")
+    out.backward(torch.from_numpy(g["g"]).cuda())
+    assert_close_rel(x.grad.cpu(), g["gx"], 1e-4, "cin gx")
+    for i, c in enumerate(cin.conv_layers):
+        assert_close_rel(c.weight.grad.cpu(), g[f"gw{i}"], 1e-4, f"gw{i}")
+        assert_close_rel(c.bias.grad.cpu(), g[f"gb{i}"], 1e-4, f"gb{i}")
+
+
+def test_cin_reference_shape_facts():
+    # tests/test_layers.py:143-168
+    x = torch.randn(4, 5, 8, device="cuda")
+    assert CIN(5, 8, [64, 64], split_half=False).cuda()(x).shape == (4, 128)
+    c = CIN(5, 8, [64, 64], split_half=True).cuda()
+    assert c.output_dim == 32 + 64 and c(x).shape == (4, c.output_dim)
+    xg = x.clone().requires_grad_(True)
+    c(xg).sum().backward()
+    assert xg.grad is not None and all(p.grad is not None for p in c.parameters())
+    assert CIN(5, 8).layer_sizes == [128, 128]
+
+
+@pytest.mark.parametrize("B,F,D,sizes,split", [(300, 16, 16, [64], True), (130, 16, 16, [128, 128, 64], True),
+                                                (65, 39, 64, [24, 20], True), (37, 7, 12, [9, 5, 3], False)])
+def test_cin_vs_oracle_larger(B, F, D, sizes, split):
+    rng = np.random.default_rng(B)
+    cin = CIN(F, D, sizes, split).cuda()
+    x = (rng.standard_normal((B, F, D)) * 0.5).astype(np.float32)
+    W = [c.weight.detach().cpu().numpy()[:, :, 0].astype(np.float64) for c in cin.conv_layers]
+    b = [c.bias.detach().cpu().numpy().astype(np.float64) for c in cin.conv_layers]
+    xt = torch.from_numpy(x).cuda().requires_grad_(True)
+    out = cin(xt)
+    want = O.cin_forward(x.astype(np.float64), W, b, split)
+    assert_close_rel(out.detach().cpu(), want, 2e-5, "cin out")
+    g = rng.standard_normal(want.shape).astype(np.float32)
+    out.backward(torch.from_numpy(g).cuda())
+    gx, gW, gb = O.cin_backward(x.astype(np.float64), W, b, split, g.astype(np.float64))
+    assert_close_rel(xt.grad.cpu(), gx, 1e-4, "gx")
+    for i, c in enumerate(cin.conv_layers):
+        assert_close_rel(c.weight.grad.cpu()[:, :, 0], gW[i], 1e-4, f"gW{i}")
+        assert_close_rel(c.bias.grad.cpu(), gb[i], 1e-4, f"gb{i}")
+
+
+@pytest.mark.parametrize("tag", ["res", "nores"])
+def test_attention_golden(tag):
+    g = load_golden(f"attention_{tag}.npz")
+    params, ref = split_prefixed(g, "param/"), split_prefixed(g, "grad/")
+    D = g["x"].shape[2]
+    A = params["layers.0.W_q.weight"].shape[0]
+    att = MultiHeadSelfAttention(embed_dim=D, num_heads=int(g["num_heads"]), attention_dim=A,
+                                 num_layers=int(g["num_layers"]), use_residual=bool(g["use_residual"]))
+    att.load_state_dict({k: torch.from_numpy(v) for k, v in params.items()})
+    att = att.cuda()
+    x = torch.from_numpy(g["x"]).cuda().requires_grad_(True)
+    out = att(x)
+    assert out.shape == x.shape                                         # tests/test_layers.py:175-179
+    assert_close_rel(out.detach().cpu(), g["out"], 1e-5, "attention out")
+    out.backward(torch.from_numpy(g["g"]).cuda())
+    assert_close_rel(x.grad.cpu(), g["gx"], 1e-4, "gx")
+    for k, p in att.named_parameters():
+        # W_k.bias grad is analytically zero (softmax shift invariance): absolute tolerance only
+        if k.endswith("W_k.bias"):
+            assert np.abs(p.grad.cpu().numpy() - ref[k]).max() < 1e-5, k
+        else:
+            assert_close_rel(p.grad.cpu(), ref[k], 1e-4, k)
+
+
+@pytest.mark.parametrize("B,F,D,A,H,res", [(1000, 16, 16, 64, 4, True), (77, 39, 64, 64, 4, True), (33, 5, 6, 12, 3, False)])
+def test_attention_vs_oracle_larger(B, F, D, A, H, res):
+    rng = np.random.default_rng(B + F)
+    att = MultiHeadSelfAttention(D, H, A, 1, res).cuda()
+    with torch.no_grad():
+        for p in att.parameters():
+            p.add_(0.1 * torch.randn_like(p))
+    p64 = {k[len("layers.0."):]: v.detach().cpu().numpy().astype(np.float64) for k, v in att.state_dict().items()}
+    x = rng.standard_normal((B, F, D)).astype(np.float32)
+    xt = torch.from_numpy(x).cuda().requires_grad_(True)
+    out = att(xt)
+    want = O.attn_block_forward(x.astype(np.float64), p64, H, res)
+    assert_close_rel(out.detach().cpu(), want, 2e-5, "out")
+    g = rng.standard_normal(x.shape).astype(np.float32)
+    out.backward(torch.from_numpy(g).cuda())
+    gx, pg = O.attn_block_backward(x.astype(np.float64), p64, H, res, g.astype(np.float64))
+    assert_close_rel(xt.grad.cpu(), gx, 1e-4, "gx")
+    for k, v in pg.items():
+        got = dict(att.named_parameters())[f"layers.0.{k}"].grad.cpu().numpy()
+        if k == "W_k.bias":
+            assert np.abs(got - v).max() < 1e-4 * max(1.0, np.abs(pg["W_q.bias"]).max())
+        else:
+            assert_close_rel(got, v, 1e-4, k)
+
+
+def test_attention_reference_shape_facts():
+    # tests/test_layers.py:181-210: 3 layers; no residual with 2 heads / attention_dim 16
+    x = torch.randn(4, 5, 16, device="cuda")
+    assert MultiHeadSelfAttention(16, num_heads=2, attention_dim=16, num_layers=3).cuda()(x).shape == (4, 5, 16)
+    att = MultiHeadSelfAttention(16, num_heads=2, attention_dim=16, use_residual=False).cuda()
+    assert att(x).shape == (4, 5, 16) and not hasattr(att.layers[0], "layer_norm")
+    xg = x.clone().requires_grad_(True)
+    att(xg).sum().backward()
+    assert xg.grad is not None
