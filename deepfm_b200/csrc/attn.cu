@@ -18,7 +18,7 @@ struct AttnArgs {
     const float* g_out;       // backward only
     float* out;               // forward: y ; backward: g_x
     long long B;
-    int F, D, A, heads, hd, residual, spb;
+    int F, D, A, heads, hd, residual, spb, acc_global;
     float eps, inv_scale;
     const float *Wq, *bq, *Wk, *bk, *Wv, *bv, *Wo, *bo, *gamma, *beta;
     float* partials;          // backward: (gridDim.x, NP)
@@ -45,15 +45,16 @@ __device__ __forceinline__ void attn_carve(float* base, const AttnArgs& a, bool 
     s.p = take(spb * a.heads * F * F); s.o = take(spb * F * A); s.y = take(spb * F * D);
     if (bwd) {
         s.gy = take(spb * F * D); s.go = take(spb * F * A); s.gq = take(spb * F * A);
-        s.gk = take(spb * F * A); s.gv = take(spb * F * A); s.acc = take(attn_np(D, A));
+        s.gk = take(spb * F * A); s.gv = take(spb * F * A);
+        s.acc = a.acc_global ? nullptr : take(attn_np(D, A));
     }
 }
 
-static size_t attn_smem_floats(int F, int D, int A, int heads, int spb, bool bwd) {
+static size_t attn_smem_floats(int F, int D, int A, int heads, int spb, bool bwd, bool acc_global = false) {
     auto r4 = [](size_t n) { return (n + 3) & ~(size_t)3; };
     size_t n = 3 * r4((size_t)D * (A + 1)) + r4((size_t)A * (D + 1)) + 3 * r4(A) + 3 * r4(D);
     n += 2 * r4((size_t)spb * F * D) + 4 * r4((size_t)spb * F * A) + r4((size_t)spb * heads * F * F);
-    if (bwd) n += r4((size_t)spb * F * D) + 4 * r4((size_t)spb * F * A) + r4(attn_np(D, A));
+    if (bwd) n += r4((size_t)spb * F * D) + 4 * r4((size_t)spb * F * A) + (acc_global ? 0 : r4(attn_np(D, A)));
     return n;
 }
 
@@ -176,7 +177,8 @@ attn_bwd_kernel(const __grid_constant__ AttnArgs a) {
     attn_load_weights(a, s);
     const int F = a.F, D = a.D, A = a.A, H = a.heads, hd = a.hd, nt = blockDim.x, tid = threadIdx.x;
     const int NP = attn_np(D, A);
-    // accumulator layout
+    // accumulator layout (shared memory, or this block's own row of the partials when that does not fit)
+    if (a.acc_global) s.acc = a.partials + (size_t)blockIdx.x * NP;
     float* dWq = s.acc; float* dbq = dWq + A * D;
     float* dWk = dbq + A; float* dbk = dWk + A * D;
     float* dWv = dbk + A; float* dbv = dWv + A * D;
@@ -318,7 +320,8 @@ attn_bwd_kernel(const __grid_constant__ AttnArgs a) {
         }
     }
     __syncthreads();
-    for (int i = tid; i < NP; i += nt) a.partials[(size_t)blockIdx.x * NP + i] = s.acc[i];
+    if (!a.acc_global)
+        for (int i = tid; i < NP; i += nt) a.partials[(size_t)blockIdx.x * NP + i] = s.acc[i];
 }
 
 struct AttnGradPtrs { float* p[10]; int n[10]; };
@@ -337,13 +340,19 @@ __global__ void attn_reduce_kernel(const float* __restrict__ partials, int n_blo
     }
 }
 
-static int attn_config(int64_t B, int F, int D, int A, int heads, bool bwd, int& spb, size_t& smem, int& grid) {
+static int attn_config(int64_t B, int F, int D, int A, int heads, bool bwd, int& spb, size_t& smem, int& grid,
+                       int* acc_global = nullptr) {
     DFM_REQUIRE(F > 0 && D > 0 && A > 0 && heads > 0 && A % heads == 0, DFM_ERR_INVALID,
                 "attn: need F, D, A > 0 and attention_dim %% num_heads == 0");
     const size_t budget = 200 * 1024;
     spb = 8;
     while (spb > 1 && attn_smem_floats(F, D, A, heads, spb, bwd) * 4 > budget) spb >>= 1;
     smem = attn_smem_floats(F, D, A, heads, spb, bwd) * 4;
+    if (acc_global) *acc_global = 0;
+    if (bwd && smem > budget && acc_global) {   // keep the parameter-gradient accumulators in global memory
+        *acc_global = 1;
+        smem = attn_smem_floats(F, D, A, heads, spb, bwd, true) * 4;
+    }
     DFM_REQUIRE(smem <= 227 * 1024, DFM_ERR_UNSUPPORTED, "attn: F=%d D=%d A=%d needs %zu B shared memory per sample", F, D, A, smem);
     long long tiles = ceil_div(B > 0 ? B : 1, spb);
     grid = (int)(tiles < sm_count() ? tiles : sm_count());
@@ -355,7 +364,7 @@ static void attn_fill(AttnArgs& a, const float* x, const float* g_out, float* ou
     a.x = x; a.g_out = g_out; a.out = out; a.B = B; a.F = F; a.D = D; a.A = A; a.heads = heads; a.hd = A / heads;
     a.residual = residual; a.spb = spb; a.eps = 1e-5f; a.inv_scale = 1.f / sqrtf((float)(A / heads));
     a.Wq = p[0]; a.bq = p[1]; a.Wk = p[2]; a.bk = p[3]; a.Wv = p[4]; a.bv = p[5]; a.Wo = p[6]; a.bo = p[7];
-    a.gamma = residual ? p[8] : nullptr; a.beta = residual ? p[9] : nullptr; a.partials = nullptr;
+    a.gamma = residual ? p[8] : nullptr; a.beta = residual ? p[9] : nullptr; a.partials = nullptr; a.acc_global = 0;
 }
 
 }  // namespace dfm
@@ -366,7 +375,8 @@ extern "C" {
 
 size_t dfm_attn_workspace_bytes(int64_t batch, int n_fields, int dim, int attention_dim, int heads) {
     int spb, grid; size_t smem;
-    if (attn_config(batch, n_fields, dim, attention_dim, heads, true, spb, smem, grid) != DFM_OK) return 0;
+    int ag = 0;
+    if (attn_config(batch, n_fields, dim, attention_dim, heads, true, spb, smem, grid, &ag) != DFM_OK) return 0;
     return (size_t)grid * attn_np(dim, attention_dim) * 4 + 256;
 }
 
@@ -394,7 +404,8 @@ int dfm_attn_bwd(const float* x, const float* g_out, int64_t batch, int n_fields
     for (int i = 0; i < (use_residual ? 10 : 8); ++i)
         DFM_REQUIRE(params[i] && g_params[i], DFM_ERR_INVALID, "dfm_attn_bwd: parameter %d is null", i);
     int spb, grid; size_t smem;
-    int rc = attn_config(batch, n_fields, dim, attention_dim, heads, true, spb, smem, grid);
+    int acc_global = 0;
+    int rc = attn_config(batch, n_fields, dim, attention_dim, heads, true, spb, smem, grid, &acc_global);
     if (rc) return rc;
     const int D = dim, A = attention_dim, NP = attn_np(D, A);
     cudaStream_t st = static_cast<cudaStream_t>(stream);
@@ -408,6 +419,7 @@ int dfm_attn_bwd(const float* x, const float* g_out, int64_t batch, int n_fields
         AttnArgs a;
         attn_fill(a, x, g_out, g_x, batch, n_fields, dim, attention_dim, heads, use_residual, params, spb);
         a.partials = static_cast<float*>(workspace);
+        a.acc_global = acc_global;
         if (smem > 48 * 1024) DFM_CHECK_CUDA(cudaFuncSetAttribute(attn_bwd_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
         attn_bwd_kernel<<<grid, 256, smem, st>>>(a);
     }
