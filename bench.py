@@ -1,0 +1,314 @@
+#!/usr/bin/env python
+"""bench.py -- train samples/sec (fwd+bwd) of DeepFM on the Criteo-shaped synthetic workload.
+
+    python bench.py [--gpus N] [--steps K] [--warmup W] [--impl ours|reference]
+
+Workload (BASELINE.json configs[3], the one the metric is quoted on): DeepFM, 13 DENSE + 26 SPARSE
+fields, embedding_dim = fm_embed_dim = 64, Criteo-Kaggle cardinalities (33.76 M rows, 8.6 GB of
+tables), DNN [256,128,64] + BatchNorm + dropout 0.1, batch 65536 PER GPU (weak scaling).
+A step is the reference trainer's forward + loss + backward (trainer.py:219-229):
+    logits = model(batch); loss = BCEWithLogits(logits, y) + model.get_l2_reg_loss(); loss.backward()
+`value`  : inputs already resident in HBM (4 rotating batches), device-timed with CUDA events.
+`e2e`    : the same step through the public module API with the batch in pinned HOST memory, the
+           host->device copies and the loss.item() read inside the timed region.
+`roofline`: the fused embedding+FM forward kernel (K1), algorithmic bytes / CUDA-event time of the
+           C-ABI call, against MEASURED_PEAKS.json.
+`cpu_baseline` / `--impl reference`: the reference's own PyTorch-CPU code path (oracle/torch_port.py:
+           the same ATen ops in the same order; the reference package itself cannot travel to the
+           GPU box) on a bounded sample of the same workload, all host cores.
+"""
+
+from __future__ import annotations
+
+import argparse
+import json
+import os
+import subprocess
+import sys
+import threading
+import time
+
+ROOT = os.path.dirname(os.path.abspath(__file__))
+sys.path.insert(0, ROOT)
+
+METRIC = "train samples/sec (fwd+bwd)"
+UNIT = "samples/s"
+BATCH = 65536
+EMBED_DIM = 64
+WORKLOAD = "deepfm_criteo_13dense_26sparse_d64_b65536_per_gpu"
+K1_BYTES_PER_SAMPLE = 26 * (8 + 4 * EMBED_DIM + 4) + 13 * 4 + 4 * 39 * EMBED_DIM + 8   # 17012
+CPU_SAMPLE_BATCH = 8192
+CPU_SAMPLE_MAX_VOCAB = 1_000_000
+
+
+def bench_config():
+    from deepfm_b200.config import ExperimentConfig
+    cfg = ExperimentConfig()
+    cfg.feature.fm_embed_dim = EMBED_DIM
+    return cfg
+
+
+def base_line(args, n_gpus):
+    return {
+        "metric": METRIC, "unit": UNIT, "n_gpus": n_gpus, "steps": args.steps, "warmup": args.warmup,
+        "higher_is_better": True, "scaling": "weak", "vs_baseline": None, "dtype": "f32", "data": "synthetic",
+        "config": {"workload": WORKLOAD, "model": "DeepFM", "batch_per_gpu": BATCH, "global_batch": BATCH * n_gpus,
+                   "fields": "13 dense + 26 sparse", "embed_dim": EMBED_DIM, "table_rows": 33762577,
+                   "dnn": [256, 128, 64], "table_grad": "row_sparse (sorted unique rows), L2 value exact",
+                   "cache": "working set >> L2: 8.6 GB tables, 654 MB embeddings written per step, 4 rotating batches",
+                   "parallelism": f"dp{n_gpus}"},
+    }
+
+
+# ------------------------------------------------------------------------------------ clocks
+class ClockSampler:
+    FIELDS = ("clocks.sm,clocks.max.sm,clocks_event_reasons.hw_slowdown,clocks_event_reasons.hw_thermal_slowdown,"
+              "clocks_event_reasons.sw_thermal_slowdown,clocks_event_reasons.sw_power_cap")
+
+    def __init__(self, index: int):
+        self.index, self.rows, self.proc = index, [], None
+
+    def start(self):
+        try:
+            self.proc = subprocess.Popen(["nvidia-smi", f"--id={self.index}", f"--query-gpu={self.FIELDS}",
+                                          "--format=csv,noheader,nounits", "-lms", "100"],
+                                         stdout=subprocess.PIPE, stderr=subprocess.DEVNULL, text=True)
+            threading.Thread(target=self._read, daemon=True).start()
+        except Exception:
+            self.proc = None
+
+    def _read(self):
+        for line in self.proc.stdout:
+            self.rows.append([c.strip() for c in line.split(",")])
+
+    def stop(self):
+        if self.proc is None:
+            return {"sm_mhz": None, "sm_max_mhz": None, "reasons": ["nvidia-smi unavailable"]}
+        self.proc.terminate()
+        try:
+            self.proc.wait(timeout=2)
+        except Exception:
+            pass
+        sm = sorted(int(r[0]) for r in self.rows if r and r[0].isdigit())
+        mx = [int(r[1]) for r in self.rows if len(r) > 1 and r[1].isdigit()]
+        names = ["hw_slowdown", "hw_thermal_slowdown", "sw_thermal_slowdown", "sw_power_cap"]
+        reasons = sorted({n for r in self.rows if len(r) >= 6 for n, v in zip(names, r[2:6]) if v.lower().startswith("active")})
+        return {"sm_mhz": sm[len(sm) // 2] if sm else None, "sm_max_mhz": max(mx) if mx else None,
+                "reasons": reasons, "samples": len(sm)}
+
+
+# ------------------------------------------------------------------------------------ CPU arm
+def cpu_reference_run(steps: int, warmup: int, budget_s: float = 240.0):
+    """Reference PyTorch-CPU path (torch-CPU port of the reference modules) on a bounded sample."""
+    import torch
+    from deepfm_b200 import workloads as W
+    from oracle import torch_port as TP
+    cores = os.cpu_count() or 1
+    torch.set_num_threads(cores)
+    schema = W.criteo_schema(EMBED_DIM, max_vocab=CPU_SAMPLE_MAX_VOCAB)
+    cfg = bench_config()
+    model = TP.PortedModel("deepfm", schema, cfg, seed=0)
+    batch = W.synthetic_batch(schema, CPU_SAMPLE_BATCH, seed=0)
+    labels = W.synthetic_labels(CPU_SAMPLE_BATCH, seed=0)
+    times = []
+    t_start = time.perf_counter()
+    for i in range(warmup + steps):
+        for p in model.trainable():
+            p.grad = None
+        t0 = time.perf_counter()
+        loss = model.loss(batch, labels)
+        loss.backward()
+        dt = time.perf_counter() - t0
+        if i >= warmup:
+            times.append(dt)
+        if time.perf_counter() - t_start > budget_s and len(times) >= 2:
+            break
+    ms = 1e3 * sum(times) / len(times)
+    rows = sum(f.vocabulary_size for f in schema.fields.values())
+    return {"value": CPU_SAMPLE_BATCH / (ms / 1e3), "ms_per_step": ms, "cores": cores, "steps": len(times),
+            "sample": f"batch {CPU_SAMPLE_BATCH}, tables capped at {CPU_SAMPLE_MAX_VOCAB} rows each ({rows} rows), "
+                      f"{len(times)} timed steps of fwd+loss+L2+backward, torch {torch.__version__} CPU"}
+
+
+def run_reference(args, rank: int, n_gpus: int):
+    if rank != 0:
+        return
+    r = cpu_reference_run(args.steps, args.warmup)
+    line = base_line(args, n_gpus)
+    line.update({"impl": "reference", "value": r["value"], "ms_per_step": r["ms_per_step"], "steps": r["steps"],
+                 "cpu_baseline": {"value": r["value"], "unit": UNIT, "cores": r["cores"], "kind": "port", "sample": r["sample"]},
+                 "e2e": {"value": r["value"], "unit": UNIT, "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0},
+                 "gpu_launches": 0, "dtype": "f32"})
+    print(json.dumps(line), flush=True)
+
+
+# ------------------------------------------------------------------------------------ GPU arm
+def run_ours(args, rank: int, local_rank: int, n_gpus: int):
+    import torch
+    import torch.distributed as dist
+    from deepfm_b200 import _lib, workloads as W
+    from deepfm_b200.models import create_model
+
+    if not torch.cuda.is_available():
+        raise RuntimeError("bench.py needs a CUDA device: the deepfm_b200 kernels have no CPU fallback")
+    _lib.lib()
+    torch.cuda.set_device(local_rank)
+    dev = torch.device("cuda", local_rank)
+    if n_gpus > 1:
+        dist.init_process_group("nccl", device_id=dev)
+    torch.manual_seed(1234)                      # identical replicas of the dense parameters
+    schema = W.criteo_schema(EMBED_DIM)
+    cfg = bench_config()
+    with torch.device(dev):
+        model = create_model("deepfm", schema, cfg)
+    model.train()
+    model.embedding.grad_mode = "row_sparse"
+    emb = model.embedding
+    ordered = emb._ordered_params()
+    table_ids = {id(p) for p, is_table in zip(ordered, emb._param_is_table) if is_table}
+    dense_params = [p for p in model.parameters() if id(p) not in table_ids]
+    n_batches = 4
+    host = [W.synthetic_batch(schema, BATCH, seed=100 * rank + s) for s in range(n_batches)]
+    host = [{k: v.pin_memory() for k, v in b.items()} for b in host]
+    host_y = [W.synthetic_labels(BATCH, seed=100 * rank + s).pin_memory() for s in range(n_batches)]
+    devb = [{k: v.to(dev) for k, v in b.items()} for b in host]
+    devy = [y.to(dev) for y in host_y]
+    bce = torch.nn.BCEWithLogitsLoss()
+
+    def allreduce_dense():
+        if n_gpus == 1:
+            return
+        grads = [p.grad for p in dense_params if p.grad is not None]
+        flat = torch.cat([g.reshape(-1) for g in grads])
+        dist.all_reduce(flat)
+        flat.div_(n_gpus)
+        off = 0
+        for g in grads:
+            g.copy_(flat[off:off + g.numel()].view_as(g))
+            off += g.numel()
+
+    def step(batch, labels):
+        model.zero_grad(set_to_none=True)
+        logits = model(batch).squeeze(1)
+        loss = bce(logits, labels) + model.get_l2_reg_loss()
+        loss.backward()
+        allreduce_dense()
+        return loss
+
+    def barrier():
+        if n_gpus > 1:
+            dist.barrier()
+        torch.cuda.synchronize()
+
+    def timed(fn, steps):
+        barrier()
+        a, b = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+        a.record()
+        for i in range(steps):
+            fn(i)
+        b.record()
+        barrier()
+        ms = torch.tensor([a.elapsed_time(b)], device=dev)
+        if n_gpus > 1:
+            dist.all_reduce(ms, op=dist.ReduceOp.MAX)
+        return ms.item()
+
+    W_, K_ = max(args.warmup, 3), args.steps
+    for i in range(W_):
+        step(devb[i % n_batches], devy[i % n_batches])
+    sampler = ClockSampler(local_rank)
+    if rank == 0:
+        sampler.start()
+    model.embedding.profile_events = {}
+    total_ms = timed(lambda i: step(devb[i % n_batches], devy[i % n_batches]), K_)
+    ev = model.embedding.profile_events
+    model.embedding.profile_events = None
+    k1_ms = sum(a.elapsed_time(b) for a, b in ev["fwd"]) / len(ev["fwd"])
+    k2_ms = sum(a.elapsed_time(b) for a, b in ev["bwd"]) / len(ev["bwd"])
+
+    # end to end: pinned host batch -> device copies -> step -> loss.item()
+    def e2e_step(i):
+        hb, hy = host[i % n_batches], host_y[i % n_batches]
+        batch = {k: v.to(dev, non_blocking=True) for k, v in hb.items()}
+        labels = hy.to(dev, non_blocking=True)
+        return step(batch, labels).item()
+
+    for i in range(2):
+        e2e_step(i)
+    e2e_ms = timed(e2e_step, K_)
+    clocks = sampler.stop() if rank == 0 else None
+    h2d = sum(v.numel() * v.element_size() for v in host[0].values()) + host_y[0].numel() * 4
+
+    # launch count of OUR kernels in one step (profiled outside the timed region)
+    launches = None
+    if rank == 0:
+        from torch.profiler import ProfilerActivity, profile
+        with profile(activities=[ProfilerActivity.CUDA]) as prof:
+            step(devb[0], devy[0])
+            torch.cuda.synchronize()
+        launches = sum(e.count for e in prof.key_averages() if "dfm::" in e.key or "DeviceRadixSort" in e.key)
+
+    if rank != 0:
+        if n_gpus > 1:
+            dist.destroy_process_group()
+        return
+    peaks = {}
+    try:
+        peaks = json.load(open(os.path.join(ROOT, "MEASURED_PEAKS.json")))
+    except Exception:
+        pass
+    hbm_peak = float(peaks.get("hbm_gbs", 6650.0))
+    peak_src = "measured (MEASURED_PEAKS.json)" if "hbm_gbs" in peaks else "fallback 6650 GB/s"
+    k1_gbs = K1_BYTES_PER_SAMPLE * BATCH / (k1_ms * 1e-3) / 1e9
+    k2_bytes = 33_500 * BATCH                                     # SURVEY 8(d) upper bound, all rows unique
+    ms_step = total_ms / K_
+    line = base_line(args, n_gpus)
+    line.update({
+        "value": BATCH * n_gpus / (ms_step * 1e-3), "ms_per_step": ms_step, "warmup": W_,
+        "clocks": clocks,
+        "e2e": {"value": BATCH * n_gpus / (e2e_ms / K_ * 1e-3), "unit": UNIT, "ms_per_step": e2e_ms / K_,
+                "h2d_bytes_per_step": h2d, "d2h_bytes_per_step": 4},
+        "gpu_launches": (launches or 0) * K_,
+        "roofline": {"kernel": "dfm::embed_fwd_kernel<4> (K1: gather+pool+FM forward)", "bound": "hbm",
+                     "achieved": k1_gbs, "peak": hbm_peak, "unit": "GB/s", "frac": k1_gbs / hbm_peak,
+                     "traffic": None, "ms": k1_ms, "algorithmic_bytes": K1_BYTES_PER_SAMPLE * BATCH,
+                     "peak_source": peak_src},
+        "roofline_bwd": {"kernel": "K2 = sort + segreduce + stitch + dense_stream (dfm_embed_bwd)", "bound": "hbm",
+                         "achieved": k2_bytes / (k2_ms * 1e-3) / 1e9, "peak": hbm_peak, "unit": "GB/s",
+                         "frac": k2_bytes / (k2_ms * 1e-3) / 1e9 / hbm_peak, "ms": k2_ms,
+                         "algorithmic_bytes": k2_bytes},
+    })
+    if n_gpus == 1 and not args.no_cpu_baseline:
+        r = cpu_reference_run(steps=3, warmup=1, budget_s=60.0)
+        line["cpu_baseline"] = {"value": r["value"], "unit": UNIT, "cores": r["cores"], "kind": "port", "sample": r["sample"]}
+    print(json.dumps(line), flush=True)
+    if n_gpus > 1:
+        dist.destroy_process_group()
+
+
+def main():
+    ap = argparse.ArgumentParser()
+    ap.add_argument("--gpus", type=int, default=1)
+    ap.add_argument("--steps", type=int, default=20)
+    ap.add_argument("--warmup", type=int, default=5)
+    ap.add_argument("--impl", default="ours", choices=["ours", "reference"])
+    ap.add_argument("--no-cpu-baseline", action="store_true")
+    args = ap.parse_args()
+    rank = int(os.environ.get("RANK", "0"))
+    local_rank = int(os.environ.get("LOCAL_RANK", "0"))
+    world = int(os.environ.get("WORLD_SIZE", "1"))
+    n_gpus = world if world > 1 else 1
+    if args.gpus != n_gpus and world == 1 and args.gpus > 1:
+        # launched without torchrun: re-exec under it (the driver normally does this itself)
+        cmd = [sys.executable, "-m", "torch.distributed.run", "--nnodes=1", f"--nproc-per-node={args.gpus}",
+               "--master-addr", "127.0.0.1", "--master-port", os.environ.get("MASTER_PORT", "29533"), __file__,
+               "--gpus", str(args.gpus), "--steps", str(args.steps), "--warmup", str(args.warmup), "--impl", args.impl]
+        sys.exit(subprocess.call(cmd))
+    if args.impl == "reference":
+        run_reference(args, rank, n_gpus)
+    else:
+        run_ours(args, rank, local_rank, n_gpus)
+
+
+if __name__ == "__main__":
+    main()

@@ -22,6 +22,8 @@ constexpr int CHUNK = 32;      // sorted positions per lane group in segreduce
 constexpr int PG_TILE = 32;    // samples per shared-memory tile in pgrads
 constexpr int PG_THREADS = 256;
 
+static inline int slot_bits_of(int S) { int b = 0; while ((1 << b) < S) ++b; return b; }
+
 struct BwdArgs {
     const float* g_first;
     const float* g_field;
@@ -41,12 +43,17 @@ struct BwdArgs {
     float* row_grad1;
     float* head2; float* head1; float* tail2; float* tail1;  // per-unit open partial sums
     long long* tail_start;
+    float* headg; float* tailg;          // per-unit open partial sums of g_fm (plain SPARSE fields)
+    int slot_bits;                        // payload = (b << slot_bits) | slot
     unsigned long long* counters;  // {n_valid, n_unique}
 };
 
-__global__ void iota_kernel(uint32_t* p, long long n) {
-    for (long long i = (long long)blockIdx.x * blockDim.x + threadIdx.x; i < n; i += (long long)gridDim.x * blockDim.x)
-        p[i] = (uint32_t)i;
+// payload of key position i = b*S + slot:  (b << bits) | slot   (decoded with a shift and a mask)
+__global__ void payload_kernel(uint32_t* p, long long n, int S, int bits) {
+    for (long long i = (long long)blockIdx.x * blockDim.x + threadIdx.x; i < n; i += (long long)gridDim.x * blockDim.x) {
+        const uint32_t b = (uint32_t)(i / S);
+        p[i] = (b << bits) | (uint32_t)(i - (long long)b * S);
+    }
 }
 
 // g[i] = coef * p[i]   (dense-mode L2 gradient for every row; coef may be 0 -> zero fill)
@@ -127,29 +134,159 @@ __device__ __forceinline__ float slot_grad1(const DevPlan& P, const BwdArgs& a, 
     return g;
 }
 
-// ---- write the finished gradient of one row (segment) : + 2*l2*w[row]
+// Per-field record staged in shared memory by segreduce / stitch (lane-divergent reads of the
+// by-value plan would serialise in the constant bank).
+struct FieldB {
+    const float* w2;
+    const float* w1;
+    unsigned row_base;
+    int dim, flat_off, aux_off;
+    int flags;              // kind | combiner << 4 | plain << 8   (plain: SPARSE without projection)
+};
+
+__device__ __forceinline__ void stage_fields(const DevPlan& P, FieldB* t) {
+    for (int f = threadIdx.x; f < P.n_fields; f += blockDim.x) {
+        const FieldDev& fd = P.f[f];
+        FieldB e;
+        e.w2 = fd.w2; e.w1 = fd.w1; e.row_base = (unsigned)fd.row_base; e.dim = fd.dim;
+        e.flat_off = fd.flat_off; e.aux_off = fd.aux_off;
+        e.flags = fd.kind | (fd.combiner << 4) | ((fd.kind == DFM_SPARSE && fd.proj == nullptr) ? 0x100 : 0);
+        t[f] = e;
+    }
+}
+
+// ---- write the finished gradient of one row (segment)
+// For plain SPARSE fields the FM term sum_b g_fm[b] (S[b] - e[b,f]) has e[b,f] == w[row] for every
+// member of the segment, so the kernel only accumulates sum_b g_fm[b] S[b] and gs = sum_b g_fm[b]
+// and folds  -gs * w[row]  in here, together with the L2 term  coef * w[row]:  the field
+// embeddings are never re-read.
 template <int V>
 __device__ __forceinline__ void write_row(const DevPlan& P, const DevGrads& GR, const BwdArgs& a, float coef,
-                                          uint32_t key, int f, long long head_pos, int j, int G,
-                                          const VecF<V>& acc, float acc1) {
-    const FieldDev& fd = P.f[f];
-    const long long row = (long long)key - fd.row_base;
-    const int nch = fd.dim / V;
-    if (j < nch) {   // table dims are <= G * V (checked on the host)
+                                          const FieldB& fb, uint32_t key, int f, long long head_pos, int j,
+                                          const VecF<V>& acc, float acc1, float gs) {
+    const long long row = (long long)(key - fb.row_base);
+    if (j < fb.dim / V) {   // table dims are <= G * V (checked on the host)
         VecF<V> out = acc;
-        if (coef != 0.f) {
-            VecF<V> w = vload<V>(fd.w2 + (size_t)row * fd.dim + j * V);
+        const float cw = coef - gs;
+        if (cw != 0.f) {
+            const VecF<V> w = vload<V>(fb.w2 + (size_t)row * fb.dim + j * V);
 #pragma unroll
-            for (int v = 0; v < V; ++v) out.v[v] = fmaf(coef, w.v[v], out.v[v]);
+            for (int v = 0; v < V; ++v) out.v[v] = fmaf(cw, w.v[v], out.v[v]);
         }
-        if (a.mode == DFM_GRAD_DENSE) vstore<V>(GR.g[f].gw2 + (size_t)row * fd.dim + j * V, out);
+        if (a.mode == DFM_GRAD_DENSE) vstore<V>(GR.g[f].gw2 + (size_t)row * fb.dim + j * V, out);
         else vstore<V>(a.row_grad2 + (size_t)head_pos * P.max_tdim + j * V, out);
     }
     if (j == 0) {
         float o1 = acc1;
-        if (coef != 0.f) o1 = fmaf(coef, __ldg(fd.w1 + row), o1);
+        if (coef != 0.f) o1 = fmaf(coef, __ldg(fb.w1 + row), o1);
         if (a.mode == DFM_GRAD_DENSE) GR.g[f].gw1[row] = o1;
         else a.row_grad1[head_pos] = o1;
+    }
+}
+
+template <int V>
+struct ChunkState {
+    int flag, f, n_heads, n_valid;
+    uint32_t cur;
+    long long seg_start;
+    VecF<V> acc;
+    float acc1, gs;
+};
+
+struct SegCtx {
+    float *sH, *sT, *sH1, *sT1, *sHg, *sTg;
+    const uint32_t *s_keys, *s_pay;
+    const unsigned short *s_slotf, *s_slotl;
+    const FieldB* t_field;
+    int gl, j, tdim, nlane, c0;
+    long long p0, unit0;
+    float coef;
+    int bits;
+    uint32_t smask;
+};
+
+// One chunk of CHUNK sorted positions: NB items are loaded before any is consumed (all loads of a
+// batch are in flight together), then the segment logic runs over them in sorted order.
+// GENERIC = true (NB = 1) additionally handles sequence-bag / projected fields.
+template <int V, int NB, bool GENERIC>
+__device__ __forceinline__ void process_chunk(const DevPlan& P, const DevGrads& GR, const BwdArgs& a,
+                                              const SegCtx& cx, ChunkState<V>& st) {
+    const int j = cx.j, gl = cx.gl, tdim = cx.tdim, nlane = cx.nlane, c0 = cx.c0;
+    const uint32_t PAD = P.pad_key;
+    const bool has_fm = a.g_fm != nullptr;
+    const int cend = (int)((a.N - cx.p0 < CHUNK) ? a.N - cx.p0 : CHUNK);
+    uint32_t prev = PAD;
+    if (c0 > 0) prev = cx.s_keys[c0 - 1];
+    else if (cx.unit0 > 0) prev = __ldg(a.skeys + cx.unit0 - 1);
+    bool started_before = prev == st.cur;
+    st.n_heads = started_before ? 0 : 1;
+    bool ended = false;
+    for (int pb = 0; pb < cend && !ended; pb += NB) {
+        uint32_t k4[NB];
+        int f4[NB];
+        VecF<V> gA[NB], gB[NB], sv4[NB];
+        float m4[NB], o4[NB];
+#pragma unroll
+        for (int i = 0; i < NB; ++i) {
+            const int idx = c0 + pb + i;
+            k4[i] = (pb + i < cend) ? cx.s_keys[idx] : PAD;
+            f4[i] = 0; gA[i] = vzero<V>(); gB[i] = vzero<V>(); sv4[i] = vzero<V>(); m4[i] = 0.f; o4[i] = 0.f;
+            if (k4[i] == PAD) continue;
+            const uint32_t pay = cx.s_pay[idx];
+            const long long b = pay >> cx.bits;
+            const int slot = (int)(pay & cx.smask);
+            const int ff = cx.s_slotf[slot];
+            f4[i] = ff;
+            const FieldB& fb = cx.t_field[ff];
+            if (!GENERIC || (fb.flags & 0x100)) {
+                const bool on = j < fb.dim / V;
+                if (on && a.g_flat) gA[i] = vload_stream<V>(a.g_flat + (size_t)b * P.T + fb.flat_off + j * V);
+                if (on && a.g_field) gB[i] = vload_stream<V>(a.g_field + ((size_t)b * P.n_fields + ff) * P.D + j * V);
+                if (has_fm) {
+                    m4[i] = __ldg(a.g_fm + b);
+                    if (on) sv4[i] = vload<V>(a.fm_sum + (size_t)b * P.D + j * V);
+                }
+                if (j == 0 && a.g_first) o4[i] = __ldg(a.g_first + b);
+            } else {
+                const FieldDev& fd = P.f[ff];
+                const int l = cx.s_slotl[slot];
+                if (j < fd.dim / V) gA[i] = slot_grad<V>(P, a, fd, ff, b, l, j);
+                if (j == 0) o4[i] = slot_grad1(P, a, fd, b, l);
+            }
+        }
+#pragma unroll
+        for (int i = 0; i < NB; ++i) {
+            if (k4[i] == PAD) { ended = true; break; }
+            if (k4[i] != st.cur) {   // previous segment ended inside this chunk
+                if (started_before) {
+                    if (j < nlane) vstore<V>(cx.sH + gl * tdim + j * V, st.acc);
+                    if (j == 0) { cx.sH1[gl] = st.acc1; cx.sHg[gl] = st.gs; }
+                    st.flag |= 1;
+                } else {
+                    write_row<V>(P, GR, a, cx.coef, cx.t_field[st.f], st.cur, st.f, st.seg_start, j, st.acc, st.acc1, st.gs);
+                }
+                st.cur = k4[i]; st.seg_start = cx.p0 + pb + i; started_before = false; ++st.n_heads;
+                st.acc = vzero<V>(); st.acc1 = 0.f; st.gs = 0.f;
+            }
+            st.f = f4[i];
+#pragma unroll
+            for (int v = 0; v < V; ++v) st.acc.v[v] += fmaf(m4[i], sv4[i].v[v], gA[i].v[v] + gB[i].v[v]);
+            st.gs += m4[i];
+            st.acc1 += o4[i];
+            ++st.n_valid;
+        }
+    }
+    const bool continues = !ended && cend == CHUNK && cx.s_keys[c0 + CHUNK] == st.cur;
+    if (started_before) {
+        if (j < nlane) vstore<V>(cx.sH + gl * tdim + j * V, st.acc);
+        if (j == 0) { cx.sH1[gl] = st.acc1; cx.sHg[gl] = st.gs; }
+        st.flag |= 1 | (continues ? 2 : 0);
+    } else if (continues) {
+        if (j < nlane) vstore<V>(cx.sT + gl * tdim + j * V, st.acc);
+        if (j == 0) { cx.sT1[gl] = st.acc1; cx.sTg[gl] = st.gs; }
+        st.flag |= 4;
+    } else {
+        write_row<V>(P, GR, a, cx.coef, cx.t_field[st.f], st.cur, st.f, st.seg_start, j, st.acc, st.acc1, st.gs);
     }
 }
 
@@ -157,78 +294,67 @@ __device__ __forceinline__ void write_row(const DevPlan& P, const DevGrads& GR, 
 //   flag bit0: the chunk's first segment started in an earlier chunk; its partial sum is in sH
 //        bit1: that segment covers the whole chunk AND continues into the next one ("through")
 //        bit2: the chunk's last segment starts here and continues into the next chunk; sum in sT
-template <int V>
+template <int V, bool ANY_GENERIC>
 __global__ void __launch_bounds__(256)
 segreduce_kernel(const __grid_constant__ DevPlan P, const __grid_constant__ DevGrads GR,
                  const __grid_constant__ BwdArgs a, int G) {
-    extern __shared__ float sm[];
+    extern __shared__ __align__(16) float sm[];
     const int gpb = blockDim.x / G;
     const int gl = threadIdx.x / G;
     const int j = threadIdx.x - gl * G;
     const int tdim = P.max_tdim, nlane = tdim / V;
+    const int unit = gpb * CHUNK, S = P.S;
     float* sH = sm;
     float* sT = sH + gpb * tdim;
     float* sH1 = sT + gpb * tdim;
     float* sT1 = sH1 + gpb;
-    int* sFlag = reinterpret_cast<int*>(sT1 + gpb);
-    const long long unit0 = (long long)blockIdx.x * gpb * CHUNK;   // first position of this block
-    const long long p0 = unit0 + (long long)gl * CHUNK;
+    float* sHg = sT1 + gpb;
+    float* sTg = sHg + gpb;
+    int* sFlag = reinterpret_cast<int*>(sTg + gpb);
+    uint32_t* s_keys = reinterpret_cast<uint32_t*>(sFlag + gpb);     // unit + 1 (one look-ahead key)
+    uint32_t* s_pay = s_keys + unit + 1;                              // unit
+    unsigned short* s_slotf = reinterpret_cast<unsigned short*>(s_pay + unit);
+    unsigned short* s_slotl = s_slotf + ((S + 1) & ~1);
+    FieldB* t_field = reinterpret_cast<FieldB*>(reinterpret_cast<uintptr_t>(s_slotl + ((S + 1) & ~1) + 7) & ~(uintptr_t)15);
+    const long long unit0 = (long long)blockIdx.x * unit;   // first position of this block
     const uint32_t PAD = P.pad_key;
-    const float coef = a.l2x2 * (a.l2_gscale ? __ldg(a.l2_gscale) : 1.f);
-    const int S = P.S;
-
-    int flag = 0, f = 0, n_heads = 0, n_valid = 0;
-    uint32_t cur = PAD;
-    long long seg_start = p0;
-    if (p0 < a.N) cur = __ldg(a.skeys + p0);
-    if (cur != PAD) {
-        const long long p1 = (p0 + CHUNK < a.N) ? p0 + CHUNK : a.N;
-        bool started_before = p0 > 0 && __ldg(a.skeys + p0 - 1) == cur;
-        n_heads = started_before ? 0 : 1;
-        VecF<V> acc = vzero<V>();
-        float acc1 = 0.f;
-        long long p = p0;
-        for (; p < p1; ++p) {
-            const uint32_t k = __ldg(a.skeys + p);
-            if (k == PAD) break;
-            const uint32_t pay = __ldg(a.spay + p);
-            const long long b = pay / (uint32_t)S;
-            const int s = (int)(pay - (uint32_t)b * (uint32_t)S);
-            if (k != cur) {   // previous segment ended inside this chunk
-                if (started_before) {
-                    if (j < nlane) vstore<V>(sH + gl * tdim + j * V, acc);
-                    if (j == 0) sH1[gl] = acc1;
-                    flag |= 1;
-                } else {
-                    write_row<V>(P, GR, a, coef, cur, f, seg_start, j, G, acc, acc1);
-                }
-                cur = k; seg_start = p; started_before = false; ++n_heads;
-                acc = vzero<V>(); acc1 = 0.f;
-            }
-            f = P.slot_field[s];
-            const FieldDev& fd = P.f[f];
-            const int l = P.slot_pos[s];
-            if (j < fd.dim / V) {
-                VecF<V> g = slot_grad<V>(P, a, fd, f, b, l, j);
-#pragma unroll
-                for (int v = 0; v < V; ++v) acc.v[v] += g.v[v];
-            }
-            if (j == 0) acc1 += slot_grad1(P, a, fd, b, l);
-            ++n_valid;
-        }
-        const bool continues = (p == p1) && p1 < a.N && __ldg(a.skeys + p1) == cur;
-        if (started_before) {
-            if (j < nlane) vstore<V>(sH + gl * tdim + j * V, acc);
-            if (j == 0) sH1[gl] = acc1;
-            flag |= 1 | (continues ? 2 : 0);
-        } else if (continues) {
-            if (j < nlane) vstore<V>(sT + gl * tdim + j * V, acc);
-            if (j == 0) sT1[gl] = acc1;
-            flag |= 4;
-        } else {
-            write_row<V>(P, GR, a, coef, cur, f, seg_start, j, G, acc, acc1);
-        }
+    for (int i = threadIdx.x; i <= unit; i += blockDim.x) {
+        const long long p = unit0 + i;
+        s_keys[i] = p < a.N ? __ldg(a.skeys + p) : PAD;
+        if (i < unit) s_pay[i] = p < a.N ? __ldg(a.spay + p) : 0u;
     }
+    for (int s = threadIdx.x; s < S; s += blockDim.x) { s_slotf[s] = P.slot_field[s]; s_slotl[s] = P.slot_pos[s]; }
+    stage_fields(P, t_field);
+    __syncthreads();
+
+    const int c0 = gl * CHUNK;
+    const long long p0 = unit0 + c0;
+    const float coef = a.l2x2 * (a.l2_gscale ? __ldg(a.l2_gscale) : 1.f);
+    const int bits = a.slot_bits;
+    const uint32_t smask = (1u << bits) - 1u;
+
+    // does any position of this unit belong to a field that needs the generic gradient
+    // (sequence bag / projected)?  Sorted keys group by field, so units are nearly always uniform.
+    int any_generic = 0;
+    if (ANY_GENERIC) {
+        int generic_here = 0;
+        for (int i = threadIdx.x; i < unit; i += blockDim.x)
+            if (s_keys[i] != PAD && !(t_field[s_slotf[s_pay[i] & smask]].flags & 0x100)) generic_here = 1;
+        any_generic = __syncthreads_or(generic_here);
+    }
+
+    ChunkState<V> st;
+    st.flag = 0; st.f = 0; st.n_heads = 0; st.n_valid = 0; st.cur = s_keys[c0]; st.seg_start = p0;
+    st.acc = vzero<V>(); st.acc1 = 0.f; st.gs = 0.f;
+    if (st.cur != PAD) {
+        const SegCtx cx{sH, sT, sH1, sT1, sHg, sTg, s_keys, s_pay, s_slotf, s_slotl, t_field,
+                        gl, j, tdim, nlane, c0, p0, unit0, coef, bits, smask};
+        if (ANY_GENERIC && any_generic) process_chunk<V, 1, true>(P, GR, a, cx, st);
+        else process_chunk<V, 4, false>(P, GR, a, cx, st);
+    }
+    const int flag = st.flag, f = st.f, n_heads = st.n_heads, n_valid = st.n_valid;
+    const uint32_t cur = st.cur;
+    const long long seg_start = st.seg_start;
     if (j == 0) sFlag[gl] = flag;
     __syncthreads();
 
@@ -239,10 +365,10 @@ segreduce_kernel(const __grid_constant__ DevPlan P, const __grid_constant__ DevG
         const bool is_tail = role == 0;
         if (is_tail ? !(flag & 4) : !(gl == 0 && (flag & 1))) continue;
         VecF<V> acc = vzero<V>();
-        float acc1 = 0.f;
         const float* src = is_tail ? sT : sH;
         if (j < nlane) acc = *reinterpret_cast<const VecF<V>*>(src + gl * tdim + j * V);
-        if (j == 0) acc1 = is_tail ? sT1[gl] : sH1[gl];
+        float acc1 = is_tail ? sT1[gl] : sH1[gl];
+        float gs = is_tail ? sTg[gl] : sHg[gl];
         bool closed = !is_tail && !(flag & 2);
         if (!closed) {
             for (int g2 = gl + 1; g2 < gpb; ++g2) {
@@ -252,32 +378,38 @@ segreduce_kernel(const __grid_constant__ DevPlan P, const __grid_constant__ DevG
 #pragma unroll
                     for (int v = 0; v < V; ++v) acc.v[v] += h.v[v];
                 }
-                if (j == 0) acc1 += sH1[g2];
+                acc1 += sH1[g2];
+                gs += sHg[g2];
                 if (!(f2 & 2)) { closed = true; break; }
             }
         }
         if (is_tail && closed) {
-            write_row<V>(P, GR, a, coef, cur, f, seg_start, j, G, acc, acc1);
+            write_row<V>(P, GR, a, coef, t_field[f], cur, f, seg_start, j, acc, acc1, gs);
         } else {
             // open at block level: the segment started in an earlier block (head) or leaves this
             // block (tail, not closed); the unit stitch pass finishes it
             float* dst2 = is_tail ? a.tail2 : a.head2;
-            float* dst1 = is_tail ? a.tail1 : a.head1;
             if (j < nlane) vstore<V>(dst2 + (size_t)blockIdx.x * tdim + j * V, acc);
             if (j == 0) {
-                dst1[blockIdx.x] = acc1;
+                (is_tail ? a.tail1 : a.head1)[blockIdx.x] = acc1;
+                (is_tail ? a.tailg : a.headg)[blockIdx.x] = gs;
                 if (is_tail) a.tail_start[blockIdx.x] = seg_start;
             }
         }
     }
-    if (j == 0 && (n_valid | n_heads)) {
-        atomicAdd(a.counters + 0, (unsigned long long)n_valid);   // integer: order-independent
-        atomicAdd(a.counters + 1, (unsigned long long)n_heads);
-    }
+    // counters: one pair of integer atomics per block (order-independent, so still deterministic)
+    __shared__ int s_cnt[2];
+    if (threadIdx.x < 2) s_cnt[threadIdx.x] = 0;
+    __syncthreads();
+    if (j == 0 && (n_valid | n_heads)) { atomicAdd(&s_cnt[0], n_valid); atomicAdd(&s_cnt[1], n_heads); }
+    __syncthreads();
+    if (threadIdx.x < 2 && s_cnt[threadIdx.x])
+        atomicAdd(a.counters + threadIdx.x, (unsigned long long)s_cnt[threadIdx.x]);
 }
 
 // One lane group per unit (= the positions one segreduce block covered); only the unit in which a
-// multi-unit segment STARTS does work: it adds the later units' head partials in unit order.
+// multi-unit segment STARTS does work: the lanes first find where the segment ends (one unit per
+// lane), then the later units' head partials are added in unit order.
 template <int V>
 __global__ void __launch_bounds__(256)
 stitch_kernel(const __grid_constant__ DevPlan P, const __grid_constant__ DevGrads GR,
@@ -293,26 +425,41 @@ stitch_kernel(const __grid_constant__ DevPlan P, const __grid_constant__ DevGrad
     const uint32_t k = __ldg(a.skeys + p1 - 1);
     if (k == P.pad_key || __ldg(a.skeys + p1) != k) return;  // no segment leaves this unit
     if (__ldg(a.skeys + p0) == k && p0 > 0 && __ldg(a.skeys + p0 - 1) == k) return;  // not the owner
+    const unsigned gmask = group_mask(G);
+    const unsigned lane_base = (threadIdx.x & 31u) & ~(unsigned)(G - 1);
     const int tdim = P.max_tdim, nlane = tdim / V;
     const float coef = a.l2x2 * (a.l2_gscale ? __ldg(a.l2_gscale) : 1.f);
+    // last unit of the segment: the first unit after u that is not "through"
+    long long last = u + 1;
+    for (long long base = u + 1;; base += G) {
+        const long long uu = base + j;
+        const long long e = (uu + 1) * unit;
+        const bool through = e < a.N && __ldg(a.skeys + e - 1) == k && __ldg(a.skeys + e) == k;
+        unsigned stop = __ballot_sync(gmask, !through) >> lane_base;
+        if (G < 32) stop &= (1u << G) - 1u;
+        if (stop) { last = base + (__ffs(stop) - 1); break; }
+    }
     VecF<V> acc = vzero<V>();
     if (j < nlane) acc = vload<V>(a.tail2 + (size_t)u * tdim + j * V);
-    float acc1 = j == 0 ? a.tail1[u] : 0.f;
-    for (long long uu = u + 1;; ++uu) {
+    float acc1 = a.tail1[u], gs = a.tailg[u];
+#pragma unroll 4
+    for (long long uu = u + 1; uu <= last; ++uu) {
         if (j < nlane) {
-            VecF<V> h = vload<V>(a.head2 + (size_t)uu * tdim + j * V);
+            const VecF<V> h = vload<V>(a.head2 + (size_t)uu * tdim + j * V);
 #pragma unroll
             for (int v = 0; v < V; ++v) acc.v[v] += h.v[v];
         }
-        if (j == 0) acc1 += a.head1[uu];
-        const long long e = (uu + 1) * unit;
-        if (e < a.N && __ldg(a.skeys + e - 1) == k && __ldg(a.skeys + e) == k) continue;
-        break;
+        acc1 += __ldg(a.head1 + uu);
+        gs += __ldg(a.headg + uu);
     }
     const long long hp = a.tail_start[u];
     const uint32_t pay = __ldg(a.spay + hp);
-    const int s = (int)(pay % (uint32_t)P.S);
-    write_row<V>(P, GR, a, coef, k, P.slot_field[s], hp, j, G, acc, acc1);
+    const int f = P.slot_field[pay & ((1u << a.slot_bits) - 1u)];
+    const FieldDev& fd = P.f[f];
+    FieldB fb;
+    fb.w2 = fd.w2; fb.w1 = fd.w1; fb.row_base = (unsigned)fd.row_base; fb.dim = fd.dim;
+    fb.flat_off = fd.flat_off; fb.aux_off = fd.aux_off; fb.flags = 0;
+    write_row<V>(P, GR, a, coef, fb, k, f, hp, j, acc, acc1, gs);
 }
 
 // ---- DENSE-field Linear grads and projection grads -------------------------------------
@@ -432,6 +579,9 @@ dense_stream_kernel(const __grid_constant__ DevPlan P, const __grid_constant__ B
     VecF<V> aw = vzero<V>(), ab = vzero<V>();
     float a1w = 0.f, a1b = 0.f;
     if (c < nch) {
+        // e[b, f, :] = x[b] * w2 + b2 is recomputed, not re-read
+        const VecF<V> w2c = vload<V>(fd.w2 + c * V), b2c = vload<V>(fd.b2 + c * V);
+#pragma unroll 2
         for (long long b = b_lo + s; b < b_hi; b += rows) {
             const float x = __ldg(reinterpret_cast<const float*>(fd.in) + b);
             VecF<V> g = vzero<V>();
@@ -445,9 +595,8 @@ dense_stream_kernel(const __grid_constant__ DevPlan P, const __grid_constant__ B
             if (a.g_fm) {
                 const float gfm = __ldg(a.g_fm + b);
                 const VecF<V> sv = vload<V>(a.fm_sum + (size_t)b * D + c * V);
-                const VecF<V> e = vload_stream<V>(a.fe + eoff);
 #pragma unroll
-                for (int v = 0; v < V; ++v) g.v[v] = fmaf(gfm, sv.v[v] - e.v[v], g.v[v]);
+                for (int v = 0; v < V; ++v) g.v[v] = fmaf(gfm, sv.v[v] - fmaf(x, w2c.v[v], b2c.v[v]), g.v[v]);
             }
 #pragma unroll
             for (int v = 0; v < V; ++v) { aw.v[v] = fmaf(g.v[v], x, aw.v[v]); ab.v[v] += g.v[v]; }
@@ -496,7 +645,7 @@ __global__ void pgrads_finish_kernel(const __grid_constant__ DevPlan P, const __
 
 // ---- host-side workspace carving --------------------------------------------------------
 struct BwdLayout {
-    size_t cub_bytes, off_cub, off_payload, off_head2, off_head1, off_tail2, off_tail1, off_tstart, off_counters,
+    size_t cub_bytes, off_cub, off_payload, off_head2, off_head1, off_tail2, off_tail1, off_tstart, off_headg, off_tailg, off_counters,
         off_partials, total;
     long long n_chunks;
     int n_slices, vals_per_slice;
@@ -543,6 +692,8 @@ static int make_layout(const dfm_plan* plan, long long B, BwdLayout& L) {
     L.off_tail2 = take((size_t)L.n_chunks * plan->max_tdim * 4);
     L.off_tail1 = take((size_t)L.n_chunks * 4);
     L.off_tstart = take((size_t)L.n_chunks * 8);
+    L.off_headg = take((size_t)L.n_chunks * 4);
+    L.off_tailg = take((size_t)L.n_chunks * 4);
     L.off_counters = take(16);
     L.off_partials = take((size_t)L.n_slices * vals * 4);
     L.total = off;
@@ -566,7 +717,8 @@ int dfm_sort_keys(const dfm_plan* plan, int64_t n, const uint32_t* keys, uint32_
                   uint32_t* sorted_payload, void* workspace, size_t workspace_bytes, void* stream) {
     DFM_REQUIRE(plan && keys && sorted_keys && sorted_payload && workspace, DFM_ERR_INVALID, "dfm_sort_keys: null argument");
     if (n <= 0) return DFM_OK;
-    DFM_REQUIRE(n < 0x7fffffffLL, DFM_ERR_UNSUPPORTED, "dfm_sort_keys: %lld keys do not fit a 32-bit sort", (long long)n);
+    DFM_REQUIRE(n < 0x7fffffffLL && ((n / plan->S + 1) << slot_bits_of(plan->S)) < 0xffffffffLL, DFM_ERR_UNSUPPORTED,
+                "dfm_sort_keys: %lld keys do not fit a 32-bit sort", (long long)n);
     size_t cub_bytes = 0;
     int rc = sort_temp_bytes(n, plan->key_bits, &cub_bytes);
     if (rc) return rc;
@@ -576,7 +728,7 @@ int dfm_sort_keys(const dfm_plan* plan, int64_t n, const uint32_t* keys, uint32_
     cudaStream_t st = static_cast<cudaStream_t>(stream);
     uint32_t* payload = reinterpret_cast<uint32_t*>(static_cast<char*>(workspace) + off_payload);
     const int blocks = (int)(ceil_div(n, 256) < 8LL * sm_count() ? ceil_div(n, 256) : 8LL * sm_count());
-    iota_kernel<<<blocks, 256, 0, st>>>(payload, n);
+    payload_kernel<<<blocks, 256, 0, st>>>(payload, n, plan->S, slot_bits_of(plan->S));
     DFM_CHECK_LAUNCH();
     DFM_CHECK_CUDA(cub::DeviceRadixSort::SortPairs(workspace, cub_bytes, keys, sorted_keys, payload, sorted_payload,
                                                    (int)n, 0, plan->key_bits, st));
@@ -607,7 +759,8 @@ int dfm_embed_bwd(const dfm_plan* plan, int64_t batch, const void* const* inputs
     cudaStream_t st = static_cast<cudaStream_t>(stream);
     char* ws = static_cast<char*>(workspace);
     const long long N = (long long)batch * plan->S;
-    DFM_REQUIRE(N < 0x7fffffffLL, DFM_ERR_UNSUPPORTED, "dfm_embed_bwd: batch * slots must fit 31 bits");
+    DFM_REQUIRE(N < 0x7fffffffLL && ((long long)batch << slot_bits_of(plan->S)) < 0xffffffffLL, DFM_ERR_UNSUPPORTED,
+                "dfm_embed_bwd: batch * slots must fit 31 bits");
 
     DevPlan* P = new DevPlan;
     DevGrads* GR = new DevGrads;
@@ -644,6 +797,8 @@ int dfm_embed_bwd(const dfm_plan* plan, int64_t batch, const void* const* inputs
     a.head2 = reinterpret_cast<float*>(ws + L.off_head2); a.head1 = reinterpret_cast<float*>(ws + L.off_head1);
     a.tail2 = reinterpret_cast<float*>(ws + L.off_tail2); a.tail1 = reinterpret_cast<float*>(ws + L.off_tail1);
     a.tail_start = reinterpret_cast<long long*>(ws + L.off_tstart);
+    a.headg = reinterpret_cast<float*>(ws + L.off_headg); a.tailg = reinterpret_cast<float*>(ws + L.off_tailg);
+    a.slot_bits = slot_bits_of(plan->S);
     a.counters = n_valid ? reinterpret_cast<unsigned long long*>(n_valid)
                          : reinterpret_cast<unsigned long long*>(ws + L.off_counters);
     const int fill_blocks = 8 * sm_count();
@@ -671,12 +826,24 @@ int dfm_embed_bwd(const dfm_plan* plan, int64_t batch, const void* const* inputs
         const long long n_units = ceil_div(N, unit);
         const unsigned blocks = (unsigned)n_units;
         const unsigned sblocks = (unsigned)ceil_div(n_units, gpb);
-        const size_t smem = (size_t)gpb * (2 * plan->max_tdim + 2) * 4 + (size_t)gpb * 4;
+        const size_t smem = (size_t)gpb * (2 * plan->max_tdim + 4) * 4 + (size_t)gpb * 4 + (size_t)(2 * unit + 1) * 4 +
+                            (size_t)2 * ((plan->S + 1) & ~1) * 2 + 32 + (size_t)plan->n_fields * sizeof(FieldB);
+        bool any_generic = false;
+        for (int f = 0; f < plan->n_fields; ++f)
+            any_generic = any_generic || plan->kind[f] == DFM_SEQUENCE || (plan->kind[f] == DFM_SPARSE && plan->dim[f] != plan->fm_dim);
+        if (smem > 48 * 1024) {
+            DFM_CHECK_CUDA(cudaFuncSetAttribute(segreduce_kernel<4, true>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
+            DFM_CHECK_CUDA(cudaFuncSetAttribute(segreduce_kernel<1, true>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
+            DFM_CHECK_CUDA(cudaFuncSetAttribute(segreduce_kernel<4, false>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
+            DFM_CHECK_CUDA(cudaFuncSetAttribute(segreduce_kernel<1, false>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
+        }
         if (V == 4) {
-            segreduce_kernel<4><<<blocks, 256, smem, st>>>(*P, *GR, a, G);
+            if (any_generic) segreduce_kernel<4, true><<<blocks, 256, smem, st>>>(*P, *GR, a, G);
+            else segreduce_kernel<4, false><<<blocks, 256, smem, st>>>(*P, *GR, a, G);
             stitch_kernel<4><<<sblocks, 256, 0, st>>>(*P, *GR, a, G, unit);
         } else {
-            segreduce_kernel<1><<<blocks, 256, smem, st>>>(*P, *GR, a, G);
+            if (any_generic) segreduce_kernel<1, true><<<blocks, 256, smem, st>>>(*P, *GR, a, G);
+            else segreduce_kernel<1, false><<<blocks, 256, smem, st>>>(*P, *GR, a, G);
             stitch_kernel<1><<<sblocks, 256, 0, st>>>(*P, *GR, a, G, unit);
         }
         DFM_CHECK_LAUNCH();

@@ -90,93 +90,191 @@ __device__ __forceinline__ VecF<V> pool_chunk(const FieldDev& fd, const int* s_i
     return acc;
 }
 
+// Block-shared lookup tables, staged once per block from the by-value plan so that the per-slot /
+// per-field loops read shared memory (lane-divergent constant-bank reads would serialise).
+struct SlotS {              // one id slot
+    const long long* in;    // id column
+    const float* w1;        // first-order table
+    unsigned row_base;      // key = row_base + id
+    int vocab;
+    int stride_pos;         // (ids per sample << 16) | position in the bag
+    int sparse;             // 1: SPARSE (first-order term taken in phase 1)
+};
+struct FieldS {             // one field, what the plain runs need
+    const float* w2;
+    const float* b2;
+};
+struct DenseS {             // one DENSE field
+    const float* in;
+    const float* w1;
+    const float* b1;
+};
+
+__host__ __device__ inline size_t fwd_table_bytes(int S, int F, int n_dense) {
+    return (size_t)S * sizeof(SlotS) + (size_t)F * sizeof(FieldS) + (size_t)n_dense * sizeof(DenseS);
+}
+
 template <int V>
-__global__ void __launch_bounds__(256)
+__global__ void __launch_bounds__(256, 3)
 embed_fwd_kernel(const __grid_constant__ DevPlan P, long long B, int G, int smem_words_per_group,
                  float* __restrict__ first_order, float* __restrict__ field_emb,
                  float* __restrict__ flat, float* __restrict__ fm_out,
                  float* __restrict__ fm_sum, uint32_t* __restrict__ keys,
                  uint32_t* __restrict__ aux, int* __restrict__ status) {
-    extern __shared__ int smem[];
+    extern __shared__ __align__(16) unsigned char smem_raw[];
+    const int D = P.D, F = P.n_fields, S = P.S, ND = P.n_dense;
+    SlotS* t_slot = reinterpret_cast<SlotS*>(smem_raw);
+    FieldS* t_field = reinterpret_cast<FieldS*>(t_slot + S);
+    DenseS* t_dense = reinterpret_cast<DenseS*>(t_field + F);
+    int* group_base = reinterpret_cast<int*>(smem_raw + ((fwd_table_bytes(S, F, ND) + 15) & ~(size_t)15));
+    for (int s = threadIdx.x; s < S; s += blockDim.x) {
+        const FieldDev& fd = P.f[P.slot_field[s]];
+        SlotS e;
+        e.in = reinterpret_cast<const long long*>(fd.in); e.w1 = fd.w1;
+        e.row_base = (unsigned)fd.row_base; e.vocab = fd.vocab;
+        e.stride_pos = (fd.max_len << 16) | P.slot_pos[s]; e.sparse = fd.kind == DFM_SPARSE;
+        t_slot[s] = e;
+    }
+    for (int f = threadIdx.x; f < F; f += blockDim.x) { t_field[f].w2 = P.f[f].w2; t_field[f].b2 = P.f[f].b2; }
+    for (int i = threadIdx.x; i < ND; i += blockDim.x) {
+        const FieldDev& fd = P.f[P.dense_field[i]];
+        t_dense[i].in = reinterpret_cast<const float*>(fd.in); t_dense[i].w1 = fd.w1; t_dense[i].b1 = fd.b1;
+    }
+    __syncthreads();
+
     const int gpb = blockDim.x / G;
     const int gl = threadIdx.x / G;
     const int j = threadIdx.x - gl * G;
-    const long long b = (long long)blockIdx.x * gpb + gl;
-    const bool active = b < B;
     const unsigned gmask = group_mask(G);
-    int* s_ids = smem + gl * smem_words_per_group;
-    float* s_raw = reinterpret_cast<float*>(s_ids + P.S);
-    const int D = P.D, F = P.n_fields, S = P.S;
+    int* s_ids = group_base + gl * smem_words_per_group;
+    float* s_x = reinterpret_cast<float*>(s_ids + S);
+    float* s_raw = s_x + ND;
     const int nch_e = D / V;
+    const long long n_tiles = (B + gpb - 1) / gpb;
+    // persistent blocks: the tables above are staged once, then the block walks sample tiles
+    for (long long tile = blockIdx.x; tile < n_tiles; tile += gridDim.x) {
+    const long long b = tile * gpb + gl;
+    const bool active = b < B;
+    const long long bb = active ? b : 0;          // inactive groups read sample 0, write nothing
+    __syncwarp(gmask);                            // previous tile's reads of s_ids / s_x are done
 
-    // ---- phase 1: ids -> shared memory; sort keys; SPARSE first-order terms
+    // ---- phase 1: ids and dense values -> shared memory; sort keys; SPARSE / DENSE first-order
     float fo_acc = 0.f;
     for (int s = j; s < S; s += G) {
-        const int f = P.slot_field[s];
-        const FieldDev& fd = P.f[f];
-        long long id = 0;
-        if (active) id = __ldg(reinterpret_cast<const long long*>(fd.in) + b * fd.max_len + P.slot_pos[s]);
-        if (id < 0 || id >= fd.vocab) {
+        const SlotS e = t_slot[s];
+        long long id = __ldg(e.in + bb * (e.stride_pos >> 16) + (e.stride_pos & 0xffff));
+        if ((unsigned long long)id >= (unsigned long long)e.vocab) {   // also catches id < 0
             if (status) *status = 1;
             id = 0;
         }
         s_ids[s] = (int)id;
-        if (active) {
-            if (keys) keys[b * S + s] = id ? (uint32_t)(fd.row_base + id) : P.pad_key;
-            if (fd.kind == DFM_SPARSE) fo_acc += __ldg(fd.w1 + id);  // row 0 returned as stored
-        }
+        if (keys && active) keys[b * S + s] = id ? e.row_base + (unsigned)id : P.pad_key;
+        if (e.sparse) fo_acc += __ldg(e.w1 + id);                      // row 0 returned as stored
+    }
+    for (int i = j; i < ND; i += G) {
+        const DenseS e = t_dense[i];
+        const float x = __ldg(e.in + bb);
+        s_x[i] = x;
+        fo_acc += x * __ldg(e.w1) + __ldg(e.b1);                      // Linear(1, 1)
     }
     __syncwarp(gmask);
 
     // ---- phase 2: gather / pool / affine, projection, FM accumulation
     VecF<V> Sacc = vzero<V>(), Qacc = vzero<V>();
-    float* flat_b = flat + (size_t)(active ? b : 0) * P.T;
-    float* fe_b = field_emb + (size_t)(active ? b : 0) * F * D;
-    uint32_t* aux_b = aux ? aux + (size_t)(active ? b : 0) * P.A : nullptr;
+    float* flat_b = flat + (size_t)bb * P.T;
+    float* fe_b = field_emb + (size_t)bb * F * D;
+    uint32_t* aux_b = aux ? aux + (size_t)bb * P.A : nullptr;
+    const bool lane_on = j < nch_e;
+    const bool two_views = !P.aliased;
 
-    int f = 0;
-    while (f < F) {
-        // fast path: 4 consecutive plain SPARSE fields of dim D without projection
-        if (f + 4 <= F) {
-            bool simple = true;
+    for (int ri = 0; ri < P.n_runs; ++ri) {
+        const FieldRun run = P.runs[ri];
+        if (run.cls == 0) {
+            // plain SPARSE fields of dim D: row chunk -> flat (== field embedding), 4 gathers in flight
+            if (lane_on) {
+                const int* ids = s_ids + P.f[run.f0].slot_base;
+                float* dst = flat_b + P.f[run.f0].flat_off + j * V;
+                float* dst2 = fe_b + (size_t)run.f0 * D + j * V;
+                const FieldS* tf = t_field + run.f0;
+                int u = 0;
+                // software pipeline: the next 4 row gathers are issued before the current 4 rows are
+                // stored, so every lane always has gathers in flight
+                VecF<V> r[4], nx[4];
+                if (run.n >= 4) {
 #pragma unroll
-            for (int u = 0; u < 4; ++u) {
-                const FieldDev& fd = P.f[f + u];
-                simple = simple && fd.kind == DFM_SPARSE && fd.proj == nullptr && fd.dim == D;
-            }
-            if (simple) {
-                if (j < nch_e) {
-                    VecF<V> r[4];
+                    for (int i = 0; i < 4; ++i) r[i] = vload<V>(tf[i].w2 + (size_t)ids[i] * D + j * V);
+                }
+                for (; u + 4 <= run.n; u += 4) {
+                    const bool more = u + 8 <= run.n;
+                    if (more) {
 #pragma unroll
-                    for (int u = 0; u < 4; ++u) {
-                        const FieldDev& fd = P.f[f + u];
-                        r[u] = gather_row_chunk<V>(fd, s_ids[fd.slot_base], j);
+                        for (int i = 0; i < 4; ++i) nx[i] = vload<V>(tf[u + 4 + i].w2 + (size_t)ids[u + 4 + i] * D + j * V);
                     }
                     if (active) {
 #pragma unroll
-                        for (int u = 0; u < 4; ++u) {
-                            const FieldDev& fd = P.f[f + u];
-                            vstore_stream<V>(flat_b + fd.flat_off + j * V, r[u]);
-                            if (!P.aliased) vstore_stream<V>(fe_b + (size_t)(f + u) * D + j * V, r[u]);
+                        for (int i = 0; i < 4; ++i) {
+                            vstore_stream<V>(dst + (u + i) * D, r[i]);
+                            if (two_views) vstore_stream<V>(dst2 + (u + i) * D, r[i]);
                         }
                     }
 #pragma unroll
-                    for (int u = 0; u < 4; ++u)
+                    for (int i = 0; i < 4; ++i)
 #pragma unroll
                         for (int v = 0; v < V; ++v) {
-                            Sacc.v[v] += r[u].v[v];
-                            Qacc.v[v] += __fmul_rn(r[u].v[v], r[u].v[v]);
+                            Sacc.v[v] += r[i].v[v];
+                            Qacc.v[v] += __fmul_rn(r[i].v[v], r[i].v[v]);
                         }
+                    if (more) {
+#pragma unroll
+                        for (int i = 0; i < 4; ++i) r[i] = nx[i];
+                    }
                 }
-                f += 4;
-                continue;
+                for (; u < run.n; ++u) {
+                    const VecF<V> r = vload<V>(tf[u].w2 + (size_t)ids[u] * D + j * V);
+                    if (active) {
+                        vstore_stream<V>(dst + u * D, r);
+                        if (two_views) vstore_stream<V>(dst2 + u * D, r);
+                    }
+#pragma unroll
+                    for (int v = 0; v < V; ++v) { Sacc.v[v] += r.v[v]; Qacc.v[v] += __fmul_rn(r.v[v], r.v[v]); }
+                }
             }
+            continue;
         }
+        if (run.cls == 1) {
+            // plain DENSE fields of dim D: Linear(1, D) on the staged scalar
+            if (lane_on) {
+                float* dst = flat_b + P.f[run.f0].flat_off + j * V;
+                float* dst2 = fe_b + (size_t)run.f0 * D + j * V;
+                const FieldS* tf = t_field + run.f0;
+                for (int u = 0; u < run.n; ++u) {
+                    const float x = s_x[run.x0 + u];
+                    const VecF<V> w = vload<V>(tf[u].w2 + j * V);
+                    const VecF<V> c = vload<V>(tf[u].b2 + j * V);
+                    VecF<V> r;
+#pragma unroll
+                    for (int v = 0; v < V; ++v) r.v[v] = x * w.v[v] + c.v[v];
+                    if (active) {
+                        vstore_stream<V>(dst + u * D, r);
+                        if (two_views) vstore_stream<V>(dst2 + u * D, r);
+                    }
+#pragma unroll
+                    for (int v = 0; v < V; ++v) { Sacc.v[v] += r.v[v]; Qacc.v[v] += __fmul_rn(r.v[v], r.v[v]); }
+                }
+            }
+            continue;
+        }
+        // ---- generic field: sequence bags, projected fields (any kind)
+        const int f = run.f0;
         const FieldDev& fd = P.f[f];
         const int nch = fd.dim / V;
         const bool proj = fd.proj != nullptr;
         float x = 0.f;
-        if (fd.kind == DFM_DENSE && active) x = __ldg(reinterpret_cast<const float*>(fd.in) + b);
+        int xi = 0;
+        if (fd.kind == DFM_DENSE) {
+            for (int i = 0; i < ND; ++i) if (P.dense_field[i] == f) xi = i;
+            x = s_x[xi];
+        }
         for (int c = j; c < nch; c += G) {
             VecF<V> r;
             if (fd.kind == DFM_SPARSE) {
@@ -199,7 +297,7 @@ embed_fwd_kernel(const __grid_constant__ DevPlan P, long long B, int G, int smem
             }
             if (active) vstore_stream<V>(flat_b + fd.flat_off + c * V, r);
             if (!proj) {  // dim == D: chunk c of the raw row is chunk c of the field embedding
-                if (active && !P.aliased) vstore_stream<V>(fe_b + (size_t)f * D + c * V, r);
+                if (active && two_views) vstore_stream<V>(fe_b + (size_t)f * D + c * V, r);
 #pragma unroll
                 for (int v = 0; v < V; ++v) {
                     Sacc.v[v] += r.v[v];
@@ -212,7 +310,7 @@ embed_fwd_kernel(const __grid_constant__ DevPlan P, long long B, int G, int smem
         }
         if (proj) {  // e = raw @ P^T, P is (D, d) row-major (Linear(d, D, bias=False))
             __syncwarp(gmask);
-            if (j < nch_e) {
+            if (lane_on) {
                 VecF<V> e = vzero<V>();
                 const int d = fd.dim;
                 for (int k = 0; k < d; ++k) {
@@ -229,36 +327,31 @@ embed_fwd_kernel(const __grid_constant__ DevPlan P, long long B, int G, int smem
             }
             __syncwarp(gmask);
         }
-        // first-order term of SEQUENCE / DENSE fields: one lane per field
-        if (j == (f & (G - 1))) {
-            if (fd.kind == DFM_DENSE) {
-                fo_acc += x * __ldg(fd.w1) + __ldg(fd.b1);
-            } else if (fd.kind == DFM_SEQUENCE) {
-                float acc = fd.combiner == DFM_MAX ? -INFINITY : 0.f;
-                int cnt = 0, arg = -1;
-                for (int l = 0; l < fd.max_len; ++l) {
-                    int id = s_ids[fd.slot_base + l];
-                    if (id == 0) continue;
-                    float w = __ldg(fd.w1 + id);
-                    ++cnt;
-                    if (fd.combiner == DFM_MAX) {
-                        if (w > acc) { acc = w; arg = l; }
-                    } else {
-                        acc += w;
-                    }
+        // first-order term of a SEQUENCE field: one lane per field
+        if (fd.kind == DFM_SEQUENCE && j == (f & (G - 1))) {
+            float acc = fd.combiner == DFM_MAX ? -INFINITY : 0.f;
+            int cnt = 0, arg = -1;
+            for (int l = 0; l < fd.max_len; ++l) {
+                int id = s_ids[fd.slot_base + l];
+                if (id == 0) continue;
+                float w = __ldg(fd.w1 + id);
+                ++cnt;
+                if (fd.combiner == DFM_MAX) {
+                    if (w > acc) { acc = w; arg = l; }
+                } else {
+                    acc += w;
                 }
-                if (cnt == 0) acc = 0.f;
-                else if (fd.combiner == DFM_MEAN) acc = acc / (float)cnt;
-                if (fd.combiner == DFM_MAX && active && aux_b) aux_b[fd.aux_off + fd.dim] = (uint32_t)arg;
-                fo_acc += acc;
             }
+            if (cnt == 0) acc = 0.f;
+            else if (fd.combiner == DFM_MEAN) acc = acc / (float)cnt;
+            if (fd.combiner == DFM_MAX && active && aux_b) aux_b[fd.aux_off + fd.dim] = (uint32_t)arg;
+            fo_acc += acc;
         }
-        ++f;
     }
 
     // ---- epilogue: FM value 0.5 * sum_d (S_d^2 - Q_d), first-order sum, per-dim field sum
     float part = 0.f;
-    if (j < nch_e) {
+    if (lane_on) {
 #pragma unroll
         for (int v = 0; v < V; ++v) part += __fmul_rn(Sacc.v[v], Sacc.v[v]) - Qacc.v[v];   // no contraction: one field => exactly 0
     }
@@ -269,8 +362,9 @@ embed_fwd_kernel(const __grid_constant__ DevPlan P, long long B, int G, int smem
             first_order[b] = fo_acc;
             if (fm_out) fm_out[b] = 0.5f * part;
         }
-        if (fm_sum && j < nch_e) vstore<V>(fm_sum + (size_t)b * D + j * V, Sacc);
+        if (fm_sum && lane_on) vstore<V>(fm_sum + (size_t)b * D + j * V, Sacc);
     }
+    }   // tile loop
 }
 
 // Keys only (bit-exact integer artefact; also used when the forward ran without key emission).
@@ -316,6 +410,20 @@ int dfm_plan::fill(DevPlan& P, const void* const* inputs, const float* const* pa
         P.slot_field[s] = (unsigned short)slot_field[s];
         P.slot_pos[s] = (unsigned short)slot_pos[s];
     }
+    int n_dense = 0, n_runs = 0;
+    for (int f = 0; f < n_fields; ++f) {
+        const bool plain = dim[f] == fm_dim;
+        const int cls = (plain && kind[f] == DFM_SPARSE) ? 0 : (plain && kind[f] == DFM_DENSE) ? 1 : 2;
+        if (n_runs > 0 && P.runs[n_runs - 1].cls == cls && cls != 2) {
+            P.runs[n_runs - 1].n++;
+        } else {
+            P.runs[n_runs].cls = (short)cls; P.runs[n_runs].f0 = (short)f; P.runs[n_runs].n = 1;
+            P.runs[n_runs].x0 = (short)n_dense;
+            ++n_runs;
+        }
+        if (kind[f] == DFM_DENSE) P.dense_field[n_dense++] = (unsigned short)f;
+    }
+    P.n_runs = n_runs; P.n_dense = n_dense;
     return (vec == 4 && aligned) ? 4 : 1;
 }
 
@@ -437,11 +545,13 @@ int dfm_embed_fwd(const dfm_plan* plan, int64_t batch, const void* const* inputs
     int max_proj_dim = 0;
     for (int f = 0; f < plan->n_fields; ++f)
         if (plan->dim[f] != plan->fm_dim && plan->dim[f] > max_proj_dim) max_proj_dim = plan->dim[f];
-    const int words = plan->S + max_proj_dim;
+    const int words = plan->S + Pp->n_dense + max_proj_dim;
     const int threads = 256;
     const int gpb = threads / G;
-    const size_t smem = (size_t)gpb * words * sizeof(int);
-    const long long blocks = ceil_div(batch, gpb);
+    const size_t smem = ((fwd_table_bytes(plan->S, plan->n_fields, Pp->n_dense) + 15) & ~(size_t)15) +
+                        (size_t)gpb * words * sizeof(int);
+    long long blocks = ceil_div(batch, gpb);
+    if (blocks > 3LL * sm_count()) blocks = 3LL * sm_count();   // persistent: 3 resident blocks per SM
     cudaStream_t st = static_cast<cudaStream_t>(stream);
     cudaError_t e = cudaSuccess;
     if (V == 4) {

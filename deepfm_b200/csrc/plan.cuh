@@ -25,12 +25,21 @@ struct GradDev {
     float *gw2, *gb2, *gw1, *gb1, *gproj;
 };
 
+// A run of consecutive fields of one class (forward kernel): 0 = plain SPARSE of dim D (no
+// projection), 1 = plain DENSE of dim D, 2 = anything else (sequence bags, projected fields).
+struct FieldRun {
+    short cls, f0, n, x0;   // x0: index of the run's first DENSE field among the DENSE fields
+};
+
 struct DevPlan {
     int n_fields, D, T, S, A, aliased, max_tdim;
     unsigned pad_key;
+    int n_runs, n_dense;
     FieldDev f[MAX_FIELDS];
+    FieldRun runs[MAX_FIELDS];
     unsigned short slot_field[MAX_SLOTS];
     unsigned short slot_pos[MAX_SLOTS];
+    unsigned short dense_field[MAX_FIELDS];   // field index of the i-th DENSE field
 };
 
 struct DevGrads {

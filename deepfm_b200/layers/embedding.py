@@ -91,9 +91,12 @@ class _EmbedFn(torch.autograd.Function):
             status.zero_()
         in_arr = _lib.ptr_array(inputs)
         par_arr = mod._param_ptrs(params)
+        ev = mod._event_pair("fwd")
         _lib.check(lib.dfm_embed_fwd(mod._plan, B, in_arr, par_arr, first.data_ptr(), field.data_ptr(),
                                      flat.data_ptr(), fm_out.data_ptr(), _lib.ptr(fm_sum), _lib.ptr(keys),
                                      _lib.ptr(aux), _lib.ptr(status), _lib.stream_ptr()), "dfm_embed_fwd")
+        if ev is not None:
+            ev[1].record()
         if status is not None and int(status.item()) != 0:
             raise IndexError("index out of range in FeatureEmbedding (an id is outside [0, vocabulary_size))")
         ctx.mod = mod
@@ -137,6 +140,7 @@ class _EmbedFn(torch.autograd.Function):
         if rowsparse:
             rg2 = torch.empty((max(N, 1), max(mod._max_tdim, 1)), device=dev, dtype=torch.float32)
             rg1 = torch.empty((max(N, 1),), device=dev, dtype=torch.float32)
+        ev = mod._event_pair("bwd")
         _lib.check(lib.dfm_embed_bwd(
             mod._plan, B, _lib.ptr_array(inputs), mod._param_ptrs(params),
             _lib.ptr(g_first), _lib.ptr(g_field), _lib.ptr(g_flat), _lib.ptr(g_fm),
@@ -144,6 +148,8 @@ class _EmbedFn(torch.autograd.Function):
             float(lam), _lib.ptr(gscale), _lib.GRAD_ROWSPARSE if rowsparse else _lib.GRAD_DENSE,
             mod._param_ptrs(grads), skeys.data_ptr(), spay.data_ptr(), _lib.ptr(rg2), _lib.ptr(rg1),
             counts.data_ptr(), ws.data_ptr(), ws.numel(), _lib.stream_ptr()), "dfm_embed_bwd")
+        if ev is not None:
+            ev[1].record()
         if rowsparse:
             mod.row_grads = RowSparseGrads(skeys, spay, rg2, rg1, counts, mod._row_base, mod._dims, mod.field_names)
         else:
@@ -195,6 +201,7 @@ class FeatureEmbedding(nn.Module):
 
         # extras
         self.grad_mode = "dense"
+        self.profile_events = None      # set to {} to collect (start, end) CUDA events per call
         self.check_indices = False
         self.row_grads: Optional[RowSparseGrads] = None
         self.last_counts = None
@@ -227,6 +234,16 @@ class FeatureEmbedding(nn.Module):
                 nn.init.xavier_uniform_(m.weight.data)
                 if m.bias is not None:
                     nn.init.zeros_(m.bias.data)
+
+    # -- measurement hook: CUDA events around the C-ABI calls on the launching stream -----------
+    def _event_pair(self, which: str):
+        store = getattr(self, "profile_events", None)
+        if store is None:
+            return None
+        pair = (torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True))
+        store.setdefault(which, []).append(pair)
+        pair[0].record()
+        return pair
 
     # -- kernel plumbing -----------------------------------------------------------------------
     def _ensure_plan(self):

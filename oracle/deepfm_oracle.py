@@ -434,7 +434,7 @@ PAD_KEY = np.uint32(0xFFFFFFFF)
 
 def emit_keys(schema, batch) -> Tuple[np.ndarray, np.ndarray]:
     """(keys uint32 (B*S,), payload uint32 (B*S,)): key = global row of the id in that slot,
-    PAD_KEY for id 0; payload = b*S + slot."""
+    PAD_KEY for id 0; payload = (b << ceil(log2 S)) | slot  (sample and slot, shift/mask decodable)."""
     slot_field, slot_pos, row_base = slot_layout(schema)
     names = list(schema.fields.keys())
     B = len(next(iter(batch.values())))
@@ -445,8 +445,9 @@ def emit_keys(schema, batch) -> Tuple[np.ndarray, np.ndarray]:
         x = np.asarray(batch[names[slot_field[s]]])
         ids = x if x.ndim == 1 else x[:, slot_pos[s]]
         keys[:, s] = np.where(ids != 0, row_base[slot_field[s]] + ids, PAD_KEY).astype(np.uint32)
-    payload = np.arange(B * S, dtype=np.uint32)
-    return keys.reshape(-1), payload
+    bits = int(np.ceil(np.log2(S))) if S > 1 else 0
+    payload = ((np.arange(B, dtype=np.uint32)[:, None] << np.uint32(bits)) | np.arange(S, dtype=np.uint32)[None, :])
+    return keys.reshape(-1), payload.reshape(-1).astype(np.uint32)
 
 
 def sort_pairs(keys: np.ndarray, payload: np.ndarray):
