@@ -1,0 +1,52 @@
+"""Turn gpurun_out/ ncu artefacts into the tracked summaries under profiles/ (round tag as argv[1])."""
+import collections, csv, gzip, json, os, re, shutil, subprocess, sys
+
+tag = sys.argv[1] if len(sys.argv) > 1 else "r1"
+root = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
+src, dst = os.path.join(root, "gpurun_out"), os.path.join(root, "profiles")
+os.makedirs(dst, exist_ok=True)
+
+# 1. launch list: share of every kernel in the bench command
+lines = [l for l in open(os.path.join(src, f"launches_{tag}.csv")) if not l.startswith("==")]
+agg = collections.OrderedDict()
+for row in csv.DictReader(lines):
+    if row.get("Metric Name") != "gpu__time_duration.sum":
+        continue
+    v = float(row["Metric Value"].replace(",", ""))
+    v = v / 1e3 if row["Metric Unit"] == "ns" else v * 1e3 if row["Metric Unit"] == "ms" else v
+    name = re.sub(r"\(.*", "", row["Kernel Name"])[:90]
+    a = agg.setdefault(name, [0, 0.0])
+    a[0] += 1
+    a[1] += v
+tot = sum(a[1] for a in agg.values())
+with open(os.path.join(dst, f"{tag}_launches_summary.csv"), "w") as fh:
+    fh.write("# ncu --metrics gpu__time_duration.sum --clock-control none : python bench.py --steps 2 --warmup 3 --no-cpu-baseline\n")
+    fh.write("# per-launch times are cold-cache and serialised: compare SHARES, not absolutes\n")
+    fh.write("kernel,launches,total_us,avg_us,share_pct,ours\n")
+    for k, (c, t) in sorted(agg.items(), key=lambda kv: -kv[1][1]):
+        ours = int("dfm::" in k or "DeviceRadixSort" in k)
+        fh.write(f"\"{k}\",{c},{t:.1f},{t / c:.2f},{100 * t / tot:.2f},{ours}\n")
+with gzip.open(os.path.join(dst, f"{tag}_launches_raw.csv.gz"), "wt") as fh:
+    fh.writelines(lines)
+
+# 2. ncu --set full capture: the counters quoted in DESIGN.md / bench.py
+rep = os.path.join(src, f"prof_{tag}.ncu-rep")
+raw = subprocess.run(["ncu", "-i", rep, "--page", "raw", "--csv"], capture_output=True, text=True).stdout
+rows = list(csv.reader(raw.splitlines()))
+hdr, units = rows[0], rows[1]
+want = ["Kernel Name", "gpu__time_duration.sum", "dram__bytes_read.sum", "dram__bytes_write.sum",
+        "gpu__dram_throughput.avg.pct_of_peak_sustained_elapsed", "sm__throughput.avg.pct_of_peak_sustained_elapsed",
+        "sm__warps_active.avg.pct_of_peak_sustained_active", "launch__registers_per_thread", "launch__grid_size",
+        "launch__block_size", "smsp__inst_executed.sum", "l1tex__t_sector_hit_rate.pct", "lts__t_sector_hit_rate.pct",
+        "sm__inst_executed_pipe_tensor.sum", "sm__pipe_tensor_cycles_active.avg.pct_of_peak_sustained_active"]
+idx = [(w, hdr.index(w)) for w in want if w in hdr]
+with open(os.path.join(dst, f"{tag}_ncu_full_kernels.csv"), "w") as fh:
+    fh.write("# ncu --set full --clock-control none --import-source on : python scripts/ncu_target.py (Criteo shape, B=65536)\n")
+    fh.write(",".join(f"{w} [{units[i]}]" for w, i in idx) + "\n")
+    for r in rows[2:]:
+        fh.write(",".join('"' + r[i].replace('"', "'")[:80] + '"' if w == "Kernel Name" else r[i].replace(",", "") for w, i in idx) + "\n")
+for name in (f"bench_{tag}.json",):
+    if os.path.exists(os.path.join(src, name)):
+        shutil.copy(os.path.join(src, name), os.path.join(dst, name))
+print(open(os.path.join(dst, f"{tag}_launches_summary.csv")).read()[:3000])
+print(open(os.path.join(dst, f"{tag}_ncu_full_kernels.csv")).read())
