@@ -44,6 +44,8 @@ struct BwdArgs {
     float* head2; float* head1; float* tail2; float* tail1;  // per-unit open partial sums
     long long* tail_start;
     float* headg; float* tailg;          // per-unit open partial sums of g_fm (plain SPARSE fields)
+    int* tail_field;                      // field of the segment that leaves the unit
+    int direct;                           // 1: payload = row index into g_flat (M, max_tdim); field from key
     int slot_bits;                        // payload = (b << slot_bits) | slot
     unsigned long long* counters;  // {n_valid, n_unique}
 };
@@ -163,13 +165,14 @@ __device__ __forceinline__ void stage_fields(const DevPlan& P, FieldB* t) {
 template <int V>
 __device__ __forceinline__ void write_row(const DevPlan& P, const DevGrads& GR, const BwdArgs& a, float coef,
                                           const FieldB& fb, uint32_t key, int f, long long head_pos, int j,
-                                          const VecF<V>& acc, float acc1, float gs) {
+                                          const VecF<V>& acc, float acc1, float gs,
+                                          bool have_pre = false, VecF<V> wpre = VecF<V>(), float w1pre = 0.f) {
     const long long row = (long long)(key - fb.row_base);
     if (j < fb.dim / V) {   // table dims are <= G * V (checked on the host)
         VecF<V> out = acc;
         const float cw = coef - gs;
         if (cw != 0.f) {
-            const VecF<V> w = vload<V>(fb.w2 + (size_t)row * fb.dim + j * V);
+            const VecF<V> w = have_pre ? wpre : vload<V>(fb.w2 + (size_t)row * fb.dim + j * V);
 #pragma unroll
             for (int v = 0; v < V; ++v) out.v[v] = fmaf(cw, w.v[v], out.v[v]);
         }
@@ -178,7 +181,7 @@ __device__ __forceinline__ void write_row(const DevPlan& P, const DevGrads& GR, 
     }
     if (j == 0) {
         float o1 = acc1;
-        if (coef != 0.f) o1 = fmaf(coef, __ldg(fb.w1 + row), o1);
+        if (coef != 0.f) o1 = fmaf(coef, have_pre ? w1pre : __ldg(fb.w1 + row), o1);
         if (a.mode == DFM_GRAD_DENSE) GR.g[f].gw1[row] = o1;
         else a.row_grad1[head_pos] = o1;
     }
@@ -189,15 +192,54 @@ struct ChunkState {
     int flag, f, n_heads, n_valid;
     uint32_t cur;
     long long seg_start;
-    VecF<V> acc;
-    float acc1, gs;
+    VecF<V> acc, w;      // w: prefetched table row chunk of the current segment (plain path)
+    float acc1, gs, w1;
 };
 
+// Shared-memory image of one segreduce block (one "unit" of gpb * CHUNK sorted positions).
+struct SegSmem {
+    float *sH, *sT, *sH1, *sT1, *sHg, *sTg;     // per-chunk open partial sums
+    int* sFlag;
+    unsigned long long* s_goff;                 // per position: element offset of its gradient row
+    const float** s_wptr;                       // per position: &w2[row][0] and &w1[row] of its table row
+    const float** s_w1ptr;
+    uint32_t *s_keys, *s_pay, *s_b;             // sorted key (+1 look-ahead), payload, sample index
+    float *s_m, *s_o;                           // per position: g_fm[b], first-order upstream gradient
+    unsigned short *s_f, *s_slotf, *s_slotl;    // per position field; slot -> field / bag position
+    FieldB* t_field;
+};
+
+__host__ __device__ inline size_t seg_smem_bytes(int gpb, int tdim, int unit, int S, int F) {
+    size_t n = (size_t)gpb * (2 * tdim + 4) * 4 + (size_t)gpb * 4;   // partials + flags
+    n = (n + 7) & ~(size_t)7;
+    n += (size_t)unit * 8 * 3;                                       // s_goff, s_wptr, s_w1ptr
+    n += (size_t)(unit + 1) * 4 + (size_t)unit * 4 * 4;              // keys, pay, b, m, o
+    n += (size_t)(((unit + 1) & ~1) + 2 * ((S + 1) & ~1)) * 2;       // s_f, slot tables
+    n = (n + 15) & ~(size_t)15;
+    return n + (size_t)F * sizeof(FieldB);
+}
+
+__device__ __forceinline__ void seg_carve(unsigned char* base, int gpb, int tdim, int unit, int S, SegSmem& m) {
+    float* fp = reinterpret_cast<float*>(base);
+    m.sH = fp; m.sT = m.sH + gpb * tdim; m.sH1 = m.sT + gpb * tdim; m.sT1 = m.sH1 + gpb;
+    m.sHg = m.sT1 + gpb; m.sTg = m.sHg + gpb;
+    m.sFlag = reinterpret_cast<int*>(m.sTg + gpb);
+    uintptr_t q = (reinterpret_cast<uintptr_t>(m.sFlag + gpb) + 7) & ~(uintptr_t)7;
+    m.s_goff = reinterpret_cast<unsigned long long*>(q);
+    m.s_wptr = reinterpret_cast<const float**>(m.s_goff + unit);
+    m.s_w1ptr = m.s_wptr + unit;
+    m.s_keys = reinterpret_cast<uint32_t*>(m.s_w1ptr + unit);
+    m.s_pay = m.s_keys + unit + 1;
+    m.s_b = m.s_pay + unit;
+    m.s_m = reinterpret_cast<float*>(m.s_b + unit);
+    m.s_o = m.s_m + unit;
+    m.s_f = reinterpret_cast<unsigned short*>(m.s_o + unit);
+    m.s_slotf = m.s_f + ((unit + 1) & ~1);
+    m.s_slotl = m.s_slotf + ((S + 1) & ~1);
+    m.t_field = reinterpret_cast<FieldB*>((reinterpret_cast<uintptr_t>(m.s_slotl + ((S + 1) & ~1)) + 15) & ~(uintptr_t)15);
+}
+
 struct SegCtx {
-    float *sH, *sT, *sH1, *sT1, *sHg, *sTg;
-    const uint32_t *s_keys, *s_pay;
-    const unsigned short *s_slotf, *s_slotl;
-    const FieldB* t_field;
     int gl, j, tdim, nlane, c0;
     long long p0, unit0;
     float coef;
@@ -205,53 +247,66 @@ struct SegCtx {
     uint32_t smask;
 };
 
-// One chunk of CHUNK sorted positions: NB items are loaded before any is consumed (all loads of a
-// batch are in flight together), then the segment logic runs over them in sorted order.
+// One chunk of CHUNK sorted positions.  Per-position metadata (row offset, sample, g_fm, first-order
+// gradient, field) was decoded ONCE per block into shared memory, so an item costs two address
+// computes and two 128-bit loads per lane.  NB items are loaded before any is consumed (all loads of
+// a batch in flight together), then the segment logic runs over them in sorted order.
 // GENERIC = true (NB = 1) additionally handles sequence-bag / projected fields.
-template <int V, int NB, bool GENERIC>
+template <int V, int NB, bool GENERIC, bool HAS_FIELD>
 __device__ __forceinline__ void process_chunk(const DevPlan& P, const DevGrads& GR, const BwdArgs& a,
-                                              const SegCtx& cx, ChunkState<V>& st) {
+                                              const SegSmem& m, const SegCtx& cx, ChunkState<V>& st) {
     const int j = cx.j, gl = cx.gl, tdim = cx.tdim, nlane = cx.nlane, c0 = cx.c0;
     const uint32_t PAD = P.pad_key;
     const bool has_fm = a.g_fm != nullptr;
     const int cend = (int)((a.N - cx.p0 < CHUNK) ? a.N - cx.p0 : CHUNK);
     uint32_t prev = PAD;
-    if (c0 > 0) prev = cx.s_keys[c0 - 1];
+    if (c0 > 0) prev = m.s_keys[c0 - 1];
     else if (cx.unit0 > 0) prev = __ldg(a.skeys + cx.unit0 - 1);
     bool started_before = prev == st.cur;
     st.n_heads = started_before ? 0 : 1;
     bool ended = false;
+    const bool need_w = has_fm || cx.coef != 0.f;
     for (int pb = 0; pb < cend && !ended; pb += NB) {
         uint32_t k4[NB];
-        int f4[NB];
-        VecF<V> gA[NB], gB[NB], sv4[NB];
-        float m4[NB], o4[NB];
+        VecF<V> gA[NB], gB[HAS_FIELD ? NB : 1], sv4[NB], wv4[GENERIC ? 1 : NB];
+        float m4[NB], o4[NB], w14[GENERIC ? 1 : NB];
 #pragma unroll
         for (int i = 0; i < NB; ++i) {
             const int idx = c0 + pb + i;
-            k4[i] = (pb + i < cend) ? cx.s_keys[idx] : PAD;
-            f4[i] = 0; gA[i] = vzero<V>(); gB[i] = vzero<V>(); sv4[i] = vzero<V>(); m4[i] = 0.f; o4[i] = 0.f;
+            k4[i] = (pb + i < cend) ? m.s_keys[idx] : PAD;
+            gA[i] = vzero<V>(); sv4[i] = vzero<V>(); m4[i] = 0.f; o4[i] = 0.f;
+            if (HAS_FIELD) gB[i] = vzero<V>();
+            if (!GENERIC) { wv4[i] = vzero<V>(); w14[i] = 0.f; }
             if (k4[i] == PAD) continue;
-            const uint32_t pay = cx.s_pay[idx];
-            const long long b = pay >> cx.bits;
-            const int slot = (int)(pay & cx.smask);
-            const int ff = cx.s_slotf[slot];
-            f4[i] = ff;
-            const FieldB& fb = cx.t_field[ff];
-            if (!GENERIC || (fb.flags & 0x100)) {
-                const bool on = j < fb.dim / V;
-                if (on && a.g_flat) gA[i] = vload_stream<V>(a.g_flat + (size_t)b * P.T + fb.flat_off + j * V);
-                if (on && a.g_field) gB[i] = vload_stream<V>(a.g_field + ((size_t)b * P.n_fields + ff) * P.D + j * V);
-                if (has_fm) {
-                    m4[i] = __ldg(a.g_fm + b);
-                    if (on) sv4[i] = vload<V>(a.fm_sum + (size_t)b * P.D + j * V);
+            bool plain = true;
+            int dimf = tdim;
+            if (GENERIC) {
+                const FieldB& fb = m.t_field[m.s_f[idx]];
+                plain = (fb.flags & 0x100) != 0;
+                dimf = fb.dim;
+            }
+            if (plain) {
+                const bool on = j < dimf / V;
+                if (on && a.g_flat) gA[i] = vload_stream<V>(a.g_flat + m.s_goff[idx] + j * V);
+                if (HAS_FIELD && on && a.g_field)
+                    gB[i] = vload_stream<V>(a.g_field + ((size_t)m.s_b[idx] * P.n_fields + m.s_f[idx]) * P.D + j * V);
+                if (!GENERIC) {   // table row of this key, for the -(sum g_fm) w and 2 l2 w terms at the segment end
+                    if (on && need_w) wv4[i] = vload<V>(m.s_wptr[idx] + j * V);
+                    if (j == 0 && cx.coef != 0.f) w14[i] = __ldg(m.s_w1ptr[idx]);
                 }
-                if (j == 0 && a.g_first) o4[i] = __ldg(a.g_first + b);
+                if (has_fm) {
+                    m4[i] = m.s_m[idx];
+                    if (on) sv4[i] = vload<V>(a.fm_sum + (size_t)m.s_b[idx] * P.D + j * V);
+                }
+                o4[i] = m.s_o[idx];
             } else {
+                const int ff = m.s_f[idx];
                 const FieldDev& fd = P.f[ff];
-                const int l = cx.s_slotl[slot];
+                const uint32_t pay = m.s_pay[idx];
+                const int l = m.s_slotl[pay & cx.smask];
+                const long long b = pay >> cx.bits;
                 if (j < fd.dim / V) gA[i] = slot_grad<V>(P, a, fd, ff, b, l, j);
-                if (j == 0) o4[i] = slot_grad1(P, a, fd, b, l);
+                o4[i] = slot_grad1(P, a, fd, b, l);
             }
         }
 #pragma unroll
@@ -259,38 +314,138 @@ __device__ __forceinline__ void process_chunk(const DevPlan& P, const DevGrads& 
             if (k4[i] == PAD) { ended = true; break; }
             if (k4[i] != st.cur) {   // previous segment ended inside this chunk
                 if (started_before) {
-                    if (j < nlane) vstore<V>(cx.sH + gl * tdim + j * V, st.acc);
-                    if (j == 0) { cx.sH1[gl] = st.acc1; cx.sHg[gl] = st.gs; }
+                    if (j < nlane) vstore<V>(m.sH + gl * tdim + j * V, st.acc);
+                    if (j == 0) { m.sH1[gl] = st.acc1; m.sHg[gl] = st.gs; }
                     st.flag |= 1;
                 } else {
-                    write_row<V>(P, GR, a, cx.coef, cx.t_field[st.f], st.cur, st.f, st.seg_start, j, st.acc, st.acc1, st.gs);
+                    write_row<V>(P, GR, a, cx.coef, m.t_field[st.f], st.cur, st.f, st.seg_start, j, st.acc, st.acc1, st.gs, !GENERIC, st.w, st.w1);
                 }
                 st.cur = k4[i]; st.seg_start = cx.p0 + pb + i; started_before = false; ++st.n_heads;
+                st.f = m.s_f[c0 + pb + i];
                 st.acc = vzero<V>(); st.acc1 = 0.f; st.gs = 0.f;
             }
-            st.f = f4[i];
+            if (!GENERIC) { st.w = wv4[i]; st.w1 = w14[i]; }
 #pragma unroll
-            for (int v = 0; v < V; ++v) st.acc.v[v] += fmaf(m4[i], sv4[i].v[v], gA[i].v[v] + gB[i].v[v]);
+            for (int v = 0; v < V; ++v) {
+                float g = gA[i].v[v];
+                if (HAS_FIELD) g += gB[i].v[v];
+                st.acc.v[v] += fmaf(m4[i], sv4[i].v[v], g);
+            }
             st.gs += m4[i];
             st.acc1 += o4[i];
             ++st.n_valid;
         }
     }
-    const bool continues = !ended && cend == CHUNK && cx.s_keys[c0 + CHUNK] == st.cur;
+    const bool continues = !ended && cend == CHUNK && m.s_keys[c0 + CHUNK] == st.cur;
     if (started_before) {
-        if (j < nlane) vstore<V>(cx.sH + gl * tdim + j * V, st.acc);
-        if (j == 0) { cx.sH1[gl] = st.acc1; cx.sHg[gl] = st.gs; }
+        if (j < nlane) vstore<V>(m.sH + gl * tdim + j * V, st.acc);
+        if (j == 0) { m.sH1[gl] = st.acc1; m.sHg[gl] = st.gs; }
         st.flag |= 1 | (continues ? 2 : 0);
     } else if (continues) {
-        if (j < nlane) vstore<V>(cx.sT + gl * tdim + j * V, st.acc);
-        if (j == 0) { cx.sT1[gl] = st.acc1; cx.sTg[gl] = st.gs; }
+        if (j < nlane) vstore<V>(m.sT + gl * tdim + j * V, st.acc);
+        if (j == 0) { m.sT1[gl] = st.acc1; m.sTg[gl] = st.gs; }
         st.flag |= 4;
     } else {
-        write_row<V>(P, GR, a, cx.coef, cx.t_field[st.f], st.cur, st.f, st.seg_start, j, st.acc, st.acc1, st.gs);
+        write_row<V>(P, GR, a, cx.coef, m.t_field[st.f], st.cur, st.f, st.seg_start, j, st.acc, st.acc1, st.gs, !GENERIC, st.w, st.w1);
     }
 }
 
-// Shared-memory image of one chunk's open partial sums (see segreduce_kernel).
+// Fast path of process_chunk for units whose fields are all plain SPARSE, with g_flat present and
+// every lane owning a chunk (max_tdim == G * V).  Every load is UNCONDITIONAL (invalid items re-read
+// the chunk's first position and are never consumed) and nothing derived from a loaded value is
+// touched before all loads of the batch are issued; the table row of the current segment is taken
+// from the batch registers by compile-time index, so ptxas keeps NB x (2..4) 128-bit loads in flight.
+template <int V, int NB, bool HAS_FIELD>
+__device__ __forceinline__ void process_chunk_fast(const DevPlan& P, const DevGrads& GR, const BwdArgs& a,
+                                                   const SegSmem& m, const SegCtx& cx, ChunkState<V>& st) {
+    const int j = cx.j, gl = cx.gl, tdim = cx.tdim, c0 = cx.c0;
+    const uint32_t PAD = P.pad_key;
+    const bool has_fm = a.g_fm != nullptr;
+    const bool need_w = has_fm || cx.coef != 0.f;
+    const bool need_w1 = cx.coef != 0.f;
+    const int cend = (int)((a.N - cx.p0 < CHUNK) ? a.N - cx.p0 : CHUNK);
+    uint32_t prev = PAD;
+    if (c0 > 0) prev = m.s_keys[c0 - 1];
+    else if (cx.unit0 > 0) prev = __ldg(a.skeys + cx.unit0 - 1);
+    bool started_before = prev == st.cur;
+    st.n_heads = started_before ? 0 : 1;
+    bool ended = false;
+    for (int pb = 0; pb < cend && !ended; pb += NB) {
+        uint32_t k4[NB];
+        VecF<V> gA[NB], gB[NB], sv4[NB], wv4[NB];
+        float m4[NB], o4[NB], w14[NB];
+#pragma unroll
+        for (int i = 0; i < NB; ++i) {
+            const int real = c0 + pb + i;
+            k4[i] = (pb + i < cend) ? m.s_keys[real] : PAD;
+            const int idx = k4[i] == PAD ? c0 : real;      // always a valid, decoded position
+            gA[i] = vload_stream<V>(a.g_flat + m.s_goff[idx] + j * V);
+            if (HAS_FIELD) gB[i] = vload_stream<V>(a.g_field + ((size_t)m.s_b[idx] * P.n_fields + m.s_f[idx]) * P.D + j * V);
+            if (has_fm) sv4[i] = vload<V>(a.fm_sum + (size_t)m.s_b[idx] * P.D + j * V);
+            if (need_w) wv4[i] = vload<V>(m.s_wptr[idx] + j * V);
+            if (need_w1) w14[i] = __ldg(m.s_w1ptr[idx]);
+            m4[i] = m.s_m[idx];
+            o4[i] = m.s_o[idx];
+        }
+#pragma unroll
+        for (int i = 0; i < NB; ++i) {
+            if (k4[i] == PAD) {
+                if (i > 0) { if (need_w) st.w = wv4[i > 0 ? i - 1 : 0]; if (need_w1) st.w1 = w14[i > 0 ? i - 1 : 0]; }
+                ended = true;
+                break;
+            }
+            if (k4[i] != st.cur) {   // previous segment ended inside this chunk
+                if (started_before) {
+                    vstore<V>(m.sH + gl * tdim + j * V, st.acc);
+                    if (j == 0) { m.sH1[gl] = st.acc1; m.sHg[gl] = st.gs; }
+                    st.flag |= 1;
+                } else {
+                    VecF<V> wrow = st.w;
+                    float w1row = st.w1;
+                    if (i > 0) { wrow = wv4[i > 0 ? i - 1 : 0]; w1row = w14[i > 0 ? i - 1 : 0]; }
+                    write_row<V>(P, GR, a, cx.coef, m.t_field[st.f], st.cur, st.f, st.seg_start, j, st.acc, st.acc1, st.gs,
+                                 true, wrow, w1row);
+                }
+                st.cur = k4[i]; st.seg_start = cx.p0 + pb + i; started_before = false; ++st.n_heads;
+                st.f = m.s_f[c0 + pb + i];
+                st.acc = vzero<V>(); st.acc1 = 0.f; st.gs = 0.f;
+            }
+#pragma unroll
+            for (int v = 0; v < V; ++v) {
+                float g = gA[i].v[v];
+                if (HAS_FIELD) g += gB[i].v[v];
+                if (has_fm) g = fmaf(m4[i], sv4[i].v[v], g);
+                st.acc.v[v] += g;
+            }
+            st.gs += m4[i];
+            st.acc1 += o4[i];
+            ++st.n_valid;
+        }
+        if (!ended) { if (need_w) st.w = wv4[NB - 1]; if (need_w1) st.w1 = w14[NB - 1]; }
+    }
+    const bool continues = !ended && cend == CHUNK && m.s_keys[c0 + CHUNK] == st.cur;
+    if (started_before) {
+        vstore<V>(m.sH + gl * tdim + j * V, st.acc);
+        if (j == 0) { m.sH1[gl] = st.acc1; m.sHg[gl] = st.gs; }
+        st.flag |= 1 | (continues ? 2 : 0);
+    } else if (continues) {
+        vstore<V>(m.sT + gl * tdim + j * V, st.acc);
+        if (j == 0) { m.sT1[gl] = st.acc1; m.sTg[gl] = st.gs; }
+        st.flag |= 4;
+    } else {
+        write_row<V>(P, GR, a, cx.coef, m.t_field[st.f], st.cur, st.f, st.seg_start, j, st.acc, st.acc1, st.gs, true, st.w, st.w1);
+    }
+}
+
+// field of a global row key (direct mode: the payload carries no slot)
+__device__ __forceinline__ int field_of_key(const FieldB* t, int n_fields, uint32_t key) {
+    int f = 0;
+    for (int i = 0; i < n_fields; ++i)
+        if (t[i].dim > 0 && (t[i].flags & 0xf) != DFM_DENSE && key >= t[i].row_base) f = i;
+    return f;
+}
+
+// Shared-memory image of one chunk's open partial sums:
 //   flag bit0: the chunk's first segment started in an earlier chunk; its partial sum is in sH
 //        bit1: that segment covers the whole chunk AND continues into the next one ("through")
 //        bit2: the chunk's last segment starts here and continues into the next chunk; sum in sT
@@ -298,59 +453,76 @@ template <int V, bool ANY_GENERIC>
 __global__ void __launch_bounds__(256)
 segreduce_kernel(const __grid_constant__ DevPlan P, const __grid_constant__ DevGrads GR,
                  const __grid_constant__ BwdArgs a, int G) {
-    extern __shared__ __align__(16) float sm[];
+    extern __shared__ __align__(16) unsigned char sm_raw[];
     const int gpb = blockDim.x / G;
     const int gl = threadIdx.x / G;
     const int j = threadIdx.x - gl * G;
     const int tdim = P.max_tdim, nlane = tdim / V;
     const int unit = gpb * CHUNK, S = P.S;
-    float* sH = sm;
-    float* sT = sH + gpb * tdim;
-    float* sH1 = sT + gpb * tdim;
-    float* sT1 = sH1 + gpb;
-    float* sHg = sT1 + gpb;
-    float* sTg = sHg + gpb;
-    int* sFlag = reinterpret_cast<int*>(sTg + gpb);
-    uint32_t* s_keys = reinterpret_cast<uint32_t*>(sFlag + gpb);     // unit + 1 (one look-ahead key)
-    uint32_t* s_pay = s_keys + unit + 1;                              // unit
-    unsigned short* s_slotf = reinterpret_cast<unsigned short*>(s_pay + unit);
-    unsigned short* s_slotl = s_slotf + ((S + 1) & ~1);
-    FieldB* t_field = reinterpret_cast<FieldB*>(reinterpret_cast<uintptr_t>(s_slotl + ((S + 1) & ~1) + 7) & ~(uintptr_t)15);
+    SegSmem m;
+    seg_carve(sm_raw, gpb, tdim, unit, S, m);
     const long long unit0 = (long long)blockIdx.x * unit;   // first position of this block
     const uint32_t PAD = P.pad_key;
+    const int bits = a.slot_bits;
+    const uint32_t smask = (1u << bits) - 1u;
     for (int i = threadIdx.x; i <= unit; i += blockDim.x) {
         const long long p = unit0 + i;
-        s_keys[i] = p < a.N ? __ldg(a.skeys + p) : PAD;
-        if (i < unit) s_pay[i] = p < a.N ? __ldg(a.spay + p) : 0u;
+        m.s_keys[i] = p < a.N ? __ldg(a.skeys + p) : PAD;
+        if (i < unit) m.s_pay[i] = p < a.N ? __ldg(a.spay + p) : 0u;
     }
-    for (int s = threadIdx.x; s < S; s += blockDim.x) { s_slotf[s] = P.slot_field[s]; s_slotl[s] = P.slot_pos[s]; }
-    stage_fields(P, t_field);
+    for (int s = threadIdx.x; s < S; s += blockDim.x) { m.s_slotf[s] = P.slot_field[s]; m.s_slotl[s] = P.slot_pos[s]; }
+    stage_fields(P, m.t_field);
     __syncthreads();
+    // decode every position once: gradient-row offset, sample, g_fm, first-order gradient, field
+    int generic_here = 0;
+    for (int i = threadIdx.x; i < unit; i += blockDim.x) {
+        const uint32_t key = m.s_keys[i];
+        if (key == PAD) continue;
+        const uint32_t pay = m.s_pay[i];
+        if (a.direct) {
+            const int fd_ = field_of_key(m.t_field, P.n_fields, key);
+            const FieldB& fk = m.t_field[fd_];
+            m.s_f[i] = (unsigned short)fd_;
+            m.s_wptr[i] = fk.w2 + (size_t)(key - fk.row_base) * fk.dim;
+            m.s_w1ptr[i] = fk.w1 + (key - fk.row_base);
+            m.s_goff[i] = (unsigned long long)pay * tdim;
+            m.s_b[i] = 0; m.s_m[i] = 0.f;
+            m.s_o[i] = a.g_first ? __ldg(a.g_first + pay) : 0.f;
+        } else {
+            const uint32_t b = pay >> bits;
+            const int f = m.s_slotf[pay & smask];
+            const FieldB& fb = m.t_field[f];
+            m.s_f[i] = (unsigned short)f;
+            m.s_wptr[i] = fb.w2 + (size_t)(key - fb.row_base) * fb.dim;
+            m.s_w1ptr[i] = fb.w1 + (key - fb.row_base);
+            m.s_goff[i] = (unsigned long long)b * P.T + fb.flat_off;
+            m.s_b[i] = b;
+            m.s_m[i] = a.g_fm ? __ldg(a.g_fm + b) : 0.f;
+            m.s_o[i] = a.g_first ? __ldg(a.g_first + b) : 0.f;
+            if (!(fb.flags & 0x100)) generic_here = 1;
+        }
+    }
+    // does any position of this unit need the generic gradient (sequence bag / projected field)?
+    // Sorted keys group by field, so units are nearly always uniform.
+    const int any_generic = ANY_GENERIC ? __syncthreads_or(generic_here) : (__syncthreads(), 0);
 
     const int c0 = gl * CHUNK;
     const long long p0 = unit0 + c0;
     const float coef = a.l2x2 * (a.l2_gscale ? __ldg(a.l2_gscale) : 1.f);
-    const int bits = a.slot_bits;
-    const uint32_t smask = (1u << bits) - 1u;
-
-    // does any position of this unit belong to a field that needs the generic gradient
-    // (sequence bag / projected)?  Sorted keys group by field, so units are nearly always uniform.
-    int any_generic = 0;
-    if (ANY_GENERIC) {
-        int generic_here = 0;
-        for (int i = threadIdx.x; i < unit; i += blockDim.x)
-            if (s_keys[i] != PAD && !(t_field[s_slotf[s_pay[i] & smask]].flags & 0x100)) generic_here = 1;
-        any_generic = __syncthreads_or(generic_here);
-    }
+    float* sH = m.sH; float* sT = m.sT; float* sH1 = m.sH1; float* sT1 = m.sT1; float* sHg = m.sHg; float* sTg = m.sTg;
+    int* sFlag = m.sFlag;
+    const FieldB* t_field = m.t_field;
 
     ChunkState<V> st;
-    st.flag = 0; st.f = 0; st.n_heads = 0; st.n_valid = 0; st.cur = s_keys[c0]; st.seg_start = p0;
-    st.acc = vzero<V>(); st.acc1 = 0.f; st.gs = 0.f;
+    st.flag = 0; st.f = 0; st.n_heads = 0; st.n_valid = 0; st.cur = m.s_keys[c0]; st.seg_start = p0;
+    st.acc = vzero<V>(); st.acc1 = 0.f; st.gs = 0.f; st.w = vzero<V>(); st.w1 = 0.f;
     if (st.cur != PAD) {
-        const SegCtx cx{sH, sT, sH1, sT1, sHg, sTg, s_keys, s_pay, s_slotf, s_slotl, t_field,
-                        gl, j, tdim, nlane, c0, p0, unit0, coef, bits, smask};
-        if (ANY_GENERIC && any_generic) process_chunk<V, 1, true>(P, GR, a, cx, st);
-        else process_chunk<V, 4, false>(P, GR, a, cx, st);
+        st.f = m.s_f[c0];
+        const SegCtx cx{gl, j, tdim, nlane, c0, p0, unit0, coef, bits, smask};
+        const bool fast = !(ANY_GENERIC && any_generic) && a.g_flat != nullptr && nlane == G;
+        if (!fast) process_chunk<V, 1, true, true>(P, GR, a, m, cx, st);
+        else if (a.g_field) process_chunk_fast<V, 2, true>(P, GR, a, m, cx, st);
+        else process_chunk_fast<V, 4, false>(P, GR, a, m, cx, st);
     }
     const int flag = st.flag, f = st.f, n_heads = st.n_heads, n_valid = st.n_valid;
     const uint32_t cur = st.cur;
@@ -393,7 +565,7 @@ segreduce_kernel(const __grid_constant__ DevPlan P, const __grid_constant__ DevG
             if (j == 0) {
                 (is_tail ? a.tail1 : a.head1)[blockIdx.x] = acc1;
                 (is_tail ? a.tailg : a.headg)[blockIdx.x] = gs;
-                if (is_tail) a.tail_start[blockIdx.x] = seg_start;
+                if (is_tail) { a.tail_start[blockIdx.x] = seg_start; a.tail_field[blockIdx.x] = f; }
             }
         }
     }
@@ -453,8 +625,7 @@ stitch_kernel(const __grid_constant__ DevPlan P, const __grid_constant__ DevGrad
         gs += __ldg(a.headg + uu);
     }
     const long long hp = a.tail_start[u];
-    const uint32_t pay = __ldg(a.spay + hp);
-    const int f = P.slot_field[pay & ((1u << a.slot_bits) - 1u)];
+    const int f = a.tail_field[u];
     const FieldDev& fd = P.f[f];
     FieldB fb;
     fb.w2 = fd.w2; fb.w1 = fd.w1; fb.row_base = (unsigned)fd.row_base; fb.dim = fd.dim;
@@ -645,7 +816,7 @@ __global__ void pgrads_finish_kernel(const __grid_constant__ DevPlan P, const __
 
 // ---- host-side workspace carving --------------------------------------------------------
 struct BwdLayout {
-    size_t cub_bytes, off_cub, off_payload, off_head2, off_head1, off_tail2, off_tail1, off_tstart, off_headg, off_tailg, off_counters,
+    size_t cub_bytes, off_cub, off_payload, off_head2, off_head1, off_tail2, off_tail1, off_tstart, off_headg, off_tailg, off_tfield, off_counters,
         off_partials, total;
     long long n_chunks;
     int n_slices, vals_per_slice;
@@ -694,6 +865,7 @@ static int make_layout(const dfm_plan* plan, long long B, BwdLayout& L) {
     L.off_tstart = take((size_t)L.n_chunks * 8);
     L.off_headg = take((size_t)L.n_chunks * 4);
     L.off_tailg = take((size_t)L.n_chunks * 4);
+    L.off_tfield = take((size_t)L.n_chunks * 4);
     L.off_counters = take(16);
     L.off_partials = take((size_t)L.n_slices * vals * 4);
     L.total = off;
@@ -799,6 +971,8 @@ int dfm_embed_bwd(const dfm_plan* plan, int64_t batch, const void* const* inputs
     a.tail_start = reinterpret_cast<long long*>(ws + L.off_tstart);
     a.headg = reinterpret_cast<float*>(ws + L.off_headg); a.tailg = reinterpret_cast<float*>(ws + L.off_tailg);
     a.slot_bits = slot_bits_of(plan->S);
+    a.tail_field = reinterpret_cast<int*>(ws + L.off_tfield);
+    a.direct = 0;
     a.counters = n_valid ? reinterpret_cast<unsigned long long*>(n_valid)
                          : reinterpret_cast<unsigned long long*>(ws + L.off_counters);
     const int fill_blocks = 8 * sm_count();
@@ -826,8 +1000,7 @@ int dfm_embed_bwd(const dfm_plan* plan, int64_t batch, const void* const* inputs
         const long long n_units = ceil_div(N, unit);
         const unsigned blocks = (unsigned)n_units;
         const unsigned sblocks = (unsigned)ceil_div(n_units, gpb);
-        const size_t smem = (size_t)gpb * (2 * plan->max_tdim + 4) * 4 + (size_t)gpb * 4 + (size_t)(2 * unit + 1) * 4 +
-                            (size_t)2 * ((plan->S + 1) & ~1) * 2 + 32 + (size_t)plan->n_fields * sizeof(FieldB);
+        const size_t smem = seg_smem_bytes(gpb, plan->max_tdim, (int)unit, plan->S, plan->n_fields) + 16;
         bool any_generic = false;
         for (int f = 0; f < plan->n_fields; ++f)
             any_generic = any_generic || plan->kind[f] == DFM_SEQUENCE || (plan->kind[f] == DFM_SPARSE && plan->dim[f] != plan->fm_dim);
