@@ -37,6 +37,7 @@ BATCH = 65536
 EMBED_DIM = 64
 WORKLOAD = "deepfm_criteo_13dense_26sparse_d64_b65536_per_gpu"
 K1_BYTES_PER_SAMPLE = 26 * (8 + 4 * EMBED_DIM + 4) + 13 * 4 + 4 * 39 * EMBED_DIM + 8   # 17012
+K1_DRAM_TRAFFIC = 752_747_520          # bytes per launch, ncu --set full (profiles/r1_ncu_full_kernels.csv)
 CPU_SAMPLE_BATCH = 8192
 CPU_SAMPLE_MAX_VOCAB = 1_000_000
 
@@ -56,7 +57,8 @@ def base_line(args, n_gpus):
                    "fields": "13 dense + 26 sparse", "embed_dim": EMBED_DIM, "table_rows": 33762577,
                    "dnn": [256, 128, 64], "table_grad": "row_sparse (sorted unique rows), L2 value exact",
                    "cache": "working set >> L2: 8.6 GB tables, 654 MB embeddings written per step, 4 rotating batches",
-                   "parallelism": f"dp{n_gpus}"},
+                   "parallelism": f"dp{n_gpus}" if n_gpus == 1 else
+                   f"dp{n_gpus} dense params (NCCL allreduce) + tables row-sharded over {n_gpus} ranks (NCCL all-to-all)"},
     }
 
 
@@ -159,6 +161,14 @@ def run_ours(args, rank: int, local_rank: int, n_gpus: int):
     torch.manual_seed(1234)                      # identical replicas of the dense parameters
     schema = W.criteo_schema(EMBED_DIM)
     cfg = bench_config()
+    if n_gpus > 1:
+        # tables row-sharded over the ranks (all-to-all of looked-up vectors and their gradients),
+        # everything else replicated and data-parallel (one flat NCCL allreduce)
+        from deepfm_b200 import models as M
+        from deepfm_b200.sharded import ShardedFeatureEmbedding, TorchDistComm
+        comm = TorchDistComm()
+        M.BaseCTRModel.embedding_factory = staticmethod(
+            lambda schema, fm_embed_dim: ShardedFeatureEmbedding(schema, fm_embed_dim, n_gpus, rank, comm))
     with torch.device(dev):
         model = create_model("deepfm", schema, cfg)
     model.train()
@@ -167,6 +177,9 @@ def run_ours(args, rank: int, local_rank: int, n_gpus: int):
     ordered = emb._ordered_params()
     table_ids = {id(p) for p, is_table in zip(ordered, emb._param_is_table) if is_table}
     dense_params = [p for p in model.parameters() if id(p) not in table_ids]
+    if n_gpus > 1:      # identical replicas of the data-parallel parameters
+        for p in dense_params:
+            dist.broadcast(p.data, src=0)
     n_batches = 4
     host = [W.synthetic_batch(schema, BATCH, seed=100 * rank + s) for s in range(n_batches)]
     host = [{k: v.pin_memory() for k, v in b.items()} for b in host]
@@ -176,16 +189,9 @@ def run_ours(args, rank: int, local_rank: int, n_gpus: int):
     bce = torch.nn.BCEWithLogitsLoss()
 
     def allreduce_dense():
-        if n_gpus == 1:
-            return
-        grads = [p.grad for p in dense_params if p.grad is not None]
-        flat = torch.cat([g.reshape(-1) for g in grads])
-        dist.all_reduce(flat)
-        flat.div_(n_gpus)
-        off = 0
-        for g in grads:
-            g.copy_(flat[off:off + g.numel()].view_as(g))
-            off += g.numel()
+        if n_gpus > 1:
+            from deepfm_b200.sharded import allreduce_dense as ar
+            ar(dense_params, n_gpus)
 
     def step(batch, labels):
         model.zero_grad(set_to_none=True)
@@ -223,8 +229,10 @@ def run_ours(args, rank: int, local_rank: int, n_gpus: int):
     total_ms = timed(lambda i: step(devb[i % n_batches], devy[i % n_batches]), K_)
     ev = model.embedding.profile_events
     model.embedding.profile_events = None
-    k1_ms = sum(a.elapsed_time(b) for a, b in ev["fwd"]) / len(ev["fwd"])
-    k2_ms = sum(a.elapsed_time(b) for a, b in ev["bwd"]) / len(ev["bwd"])
+    k1_ms = k2_ms = None
+    if ev.get("fwd"):
+        k1_ms = sum(a.elapsed_time(b) for a, b in ev["fwd"]) / len(ev["fwd"])
+        k2_ms = sum(a.elapsed_time(b) for a, b in ev["bwd"]) / len(ev["bwd"])
 
     # end to end: pinned host batch -> device copies -> step -> loss.item()
     def e2e_step(i):
@@ -259,7 +267,6 @@ def run_ours(args, rank: int, local_rank: int, n_gpus: int):
         pass
     hbm_peak = float(peaks.get("hbm_gbs", 6650.0))
     peak_src = "measured (MEASURED_PEAKS.json)" if "hbm_gbs" in peaks else "fallback 6650 GB/s"
-    k1_gbs = K1_BYTES_PER_SAMPLE * BATCH / (k1_ms * 1e-3) / 1e9
     k2_bytes = 33_500 * BATCH                                     # SURVEY 8(d) upper bound, all rows unique
     ms_step = total_ms / K_
     line = base_line(args, n_gpus)
@@ -269,15 +276,21 @@ def run_ours(args, rank: int, local_rank: int, n_gpus: int):
         "e2e": {"value": BATCH * n_gpus / (e2e_ms / K_ * 1e-3), "unit": UNIT, "ms_per_step": e2e_ms / K_,
                 "h2d_bytes_per_step": h2d, "d2h_bytes_per_step": 4},
         "gpu_launches": (launches or 0) * K_,
-        "roofline": {"kernel": "dfm::embed_fwd_kernel<4> (K1: gather+pool+FM forward)", "bound": "hbm",
-                     "achieved": k1_gbs, "peak": hbm_peak, "unit": "GB/s", "frac": k1_gbs / hbm_peak,
-                     "traffic": None, "ms": k1_ms, "algorithmic_bytes": K1_BYTES_PER_SAMPLE * BATCH,
-                     "peak_source": peak_src},
-        "roofline_bwd": {"kernel": "K2 = sort + segreduce + stitch + dense_stream (dfm_embed_bwd)", "bound": "hbm",
-                         "achieved": k2_bytes / (k2_ms * 1e-3) / 1e9, "peak": hbm_peak, "unit": "GB/s",
-                         "frac": k2_bytes / (k2_ms * 1e-3) / 1e9 / hbm_peak, "ms": k2_ms,
-                         "algorithmic_bytes": k2_bytes},
     })
+    if k1_ms:
+        k1_gbs = K1_BYTES_PER_SAMPLE * BATCH / (k1_ms * 1e-3) / 1e9
+        line["roofline"] = {"kernel": "dfm::embed_fwd_kernel<4> (K1: gather+pool+FM forward)", "bound": "hbm",
+                            "achieved": k1_gbs, "peak": hbm_peak, "unit": "GB/s", "frac": k1_gbs / hbm_peak,
+                            "traffic": K1_DRAM_TRAFFIC, "ms": k1_ms, "algorithmic_bytes": K1_BYTES_PER_SAMPLE * BATCH,
+                            "peak_source": peak_src,
+                            "traffic_source": "profiles/r1_ncu_full_kernels.csv (dram__bytes_read+write, one launch)"}
+        line["roofline_bwd"] = {"kernel": "K2 = sort + segreduce + stitch + dense_stream (dfm_embed_bwd)", "bound": "hbm",
+                                "achieved": k2_bytes / (k2_ms * 1e-3) / 1e9, "peak": hbm_peak, "unit": "GB/s",
+                                "frac": k2_bytes / (k2_ms * 1e-3) / 1e9 / hbm_peak, "ms": k2_ms,
+                                "algorithmic_bytes": k2_bytes}
+    else:
+        line["roofline"] = {"bound": "hbm", "achieved": None, "peak": hbm_peak, "unit": "GB/s", "frac": None,
+                            "traffic": None, "note": "per-kernel roofline is reported by the N=1 run (unsharded K1)"}
     if n_gpus == 1 and not args.no_cpu_baseline:
         r = cpu_reference_run(steps=3, warmup=1, budget_s=60.0)
         line["cpu_baseline"] = {"value": r["value"], "unit": UNIT, "cores": r["cores"], "kind": "port", "sample": r["sample"]}

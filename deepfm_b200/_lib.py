@@ -17,7 +17,7 @@ LIB_PATH = os.path.join(HERE, "libdeepfm_b200.so")
 OK, ERR_INVALID, ERR_UNSUPPORTED, ERR_CUDA, ERR_WORKSPACE = 0, -1, -2, -3, -4
 SPARSE, SEQUENCE, DENSE = 0, 1, 2
 SUM, MEAN, MAX = 0, 1, 2
-GRAD_DENSE, GRAD_ROWSPARSE = 0, 1
+GRAD_DENSE, GRAD_ROWSPARSE, GRAD_SKIP_TABLES = 0, 1, 2
 KIND = {"sparse": SPARSE, "sequence": SEQUENCE, "dense": DENSE}
 COMBINER = {"sum": SUM, "mean": MEAN, "max": MAX}
 
@@ -49,6 +49,11 @@ SIGNATURES = {
                               _vp, _vp, _vp]),
     "dfm_cin_bwd": (C.c_int, [_vp, _vp, _i64, C.c_int, C.c_int, C.c_int, _pi32, C.c_int, _pp, C.c_int,
                               _vp, _vp, _pp, _pp, _vp, _sz, _vp]),
+    "dfm_shard_gather": (C.c_int, [_vp, C.c_int, C.c_int, _pi64, _i64, _vp, _pp, _vp, _vp, _vp, _vp]),
+    "dfm_shard_pack_grad": (C.c_int, [_vp, _i64, _vp, _vp, _vp, _vp, _vp, _vp, _vp, _vp, _vp, _vp]),
+    "dfm_rows_bwd_workspace_bytes": (_sz, [_vp, _i64]),
+    "dfm_rows_bwd": (C.c_int, [_vp, _i64, _pp, _vp, _vp, _vp, _f32, _vp, C.c_int, _pp, _vp, _vp, _vp, _vp, _vp,
+                               _vp, _sz, _vp]),
     "dfm_attn_workspace_bytes": (_sz, [_i64, C.c_int, C.c_int, C.c_int, C.c_int]),
     "dfm_attn_fwd": (C.c_int, [_vp, _i64, C.c_int, C.c_int, C.c_int, C.c_int, C.c_int, _pp, _vp, _vp]),
     "dfm_attn_bwd": (C.c_int, [_vp, _vp, _i64, C.c_int, C.c_int, C.c_int, C.c_int, C.c_int, _pp, _vp, _pp,

@@ -840,8 +840,8 @@ static int pg_count_vals(const dfm_plan* plan, int f) {
     return n;
 }
 
-static int make_layout(const dfm_plan* plan, long long B, BwdLayout& L) {
-    const long long N = B * plan->S;
+static int make_layout(const dfm_plan* plan, long long B, BwdLayout& L, long long direct_rows = -1) {
+    const long long N = direct_rows >= 0 ? direct_rows : B * plan->S;
     L.cub_bytes = 0;
     if (N > 0) { int rc = sort_temp_bytes(N, plan->key_bits, &L.cub_bytes); if (rc) return rc; }
     L.n_chunks = ceil_div(N > 0 ? N : 1, 8 * CHUNK);   // units: >= 8 chunks per segreduce block
@@ -885,11 +885,21 @@ size_t dfm_embed_bwd_workspace_bytes(const dfm_plan* plan, int64_t batch) {
     return L.total;
 }
 
+static int sort_keys_impl(const dfm_plan* plan, int64_t n, int S, const uint32_t* keys, uint32_t* sorted_keys,
+                          uint32_t* sorted_payload, void* workspace, size_t workspace_bytes, void* stream);
+
 int dfm_sort_keys(const dfm_plan* plan, int64_t n, const uint32_t* keys, uint32_t* sorted_keys,
                   uint32_t* sorted_payload, void* workspace, size_t workspace_bytes, void* stream) {
+    DFM_REQUIRE(plan, DFM_ERR_INVALID, "dfm_sort_keys: null argument");
+    return sort_keys_impl(plan, n, plan->S, keys, sorted_keys, sorted_payload, workspace, workspace_bytes, stream);
+}
+
+// S = slots per sample of the payload encoding (1: payload = key position, the row-list mode)
+static int sort_keys_impl(const dfm_plan* plan, int64_t n, int S, const uint32_t* keys, uint32_t* sorted_keys,
+                          uint32_t* sorted_payload, void* workspace, size_t workspace_bytes, void* stream) {
     DFM_REQUIRE(plan && keys && sorted_keys && sorted_payload && workspace, DFM_ERR_INVALID, "dfm_sort_keys: null argument");
     if (n <= 0) return DFM_OK;
-    DFM_REQUIRE(n < 0x7fffffffLL && ((n / plan->S + 1) << slot_bits_of(plan->S)) < 0xffffffffLL, DFM_ERR_UNSUPPORTED,
+    DFM_REQUIRE(n < 0x7fffffffLL && ((n / S + 1) << slot_bits_of(S)) < 0xffffffffLL, DFM_ERR_UNSUPPORTED,
                 "dfm_sort_keys: %lld keys do not fit a 32-bit sort", (long long)n);
     size_t cub_bytes = 0;
     int rc = sort_temp_bytes(n, plan->key_bits, &cub_bytes);
@@ -900,14 +910,14 @@ int dfm_sort_keys(const dfm_plan* plan, int64_t n, const uint32_t* keys, uint32_
     cudaStream_t st = static_cast<cudaStream_t>(stream);
     uint32_t* payload = reinterpret_cast<uint32_t*>(static_cast<char*>(workspace) + off_payload);
     const int blocks = (int)(ceil_div(n, 256) < 8LL * sm_count() ? ceil_div(n, 256) : 8LL * sm_count());
-    payload_kernel<<<blocks, 256, 0, st>>>(payload, n, plan->S, slot_bits_of(plan->S));
+    payload_kernel<<<blocks, 256, 0, st>>>(payload, n, S, slot_bits_of(S));
     DFM_CHECK_LAUNCH();
     DFM_CHECK_CUDA(cub::DeviceRadixSort::SortPairs(workspace, cub_bytes, keys, sorted_keys, payload, sorted_payload,
                                                    (int)n, 0, plan->key_bits, st));
     return DFM_OK;
 }
 
-int dfm_embed_bwd(const dfm_plan* plan, int64_t batch, const void* const* inputs,
+static int embed_bwd_impl(const dfm_plan* plan, int64_t batch, long long direct_rows, const void* const* inputs,
                   const float* const* params, const float* g_first, const float* g_field,
                   const float* g_flat, const float* g_fm, const float* field_emb,
                   const float* flat, const float* fm_sum, const uint32_t* keys,
@@ -915,23 +925,27 @@ int dfm_embed_bwd(const dfm_plan* plan, int64_t batch, const void* const* inputs
                   float* const* grads, uint32_t* sorted_keys, uint32_t* sorted_payload,
                   float* row_grad2, float* row_grad1, int64_t* n_valid, void* workspace,
                   size_t workspace_bytes, void* stream) {
-    DFM_REQUIRE(plan && inputs && params && grads && workspace, DFM_ERR_INVALID, "dfm_embed_bwd: null argument");
+    const bool direct = direct_rows >= 0;
+    const bool skip_tables = mode == DFM_GRAD_SKIP_TABLES;
+    DFM_REQUIRE(plan && params && grads && workspace && (inputs || direct), DFM_ERR_INVALID, "dfm_embed_bwd: null argument");
     DFM_REQUIRE(batch >= 0, DFM_ERR_INVALID, "dfm_embed_bwd: negative batch");
-    DFM_REQUIRE(mode == DFM_GRAD_DENSE || mode == DFM_GRAD_ROWSPARSE, DFM_ERR_INVALID, "dfm_embed_bwd: unknown mode %d", mode);
+    DFM_REQUIRE(mode == DFM_GRAD_DENSE || mode == DFM_GRAD_ROWSPARSE || (skip_tables && !direct), DFM_ERR_INVALID,
+                "dfm_embed_bwd: unknown mode %d", mode);
     DFM_REQUIRE(!g_fm || (fm_sum && field_emb), DFM_ERR_INVALID, "dfm_embed_bwd: g_fm needs fm_sum and field_emb");
     DFM_REQUIRE(batch == 0 || plan->A == 0 || aux, DFM_ERR_INVALID, "dfm_embed_bwd: aux required");
-    DFM_REQUIRE(batch == 0 || plan->S == 0 || (sorted_keys && sorted_payload && keys), DFM_ERR_INVALID, "dfm_embed_bwd: key buffers required");
-    DFM_REQUIRE(batch == 0 || mode == DFM_GRAD_DENSE || plan->S == 0 || (row_grad2 && row_grad1 && n_valid), DFM_ERR_INVALID,
+    DFM_REQUIRE(batch == 0 || plan->S == 0 || skip_tables || (sorted_keys && sorted_payload && keys), DFM_ERR_INVALID, "dfm_embed_bwd: key buffers required");
+    DFM_REQUIRE(batch == 0 || mode != DFM_GRAD_ROWSPARSE || plan->S == 0 || (row_grad2 && row_grad1 && n_valid), DFM_ERR_INVALID,
                 "dfm_embed_bwd: row-sparse outputs required");
     DFM_REQUIRE(batch == 0 || plan->n_proj_expected == 0 || flat, DFM_ERR_INVALID, "dfm_embed_bwd: flat needed for projection grads");
     BwdLayout L;
-    int rc = make_layout(plan, batch, L);
+    int rc = make_layout(plan, batch, L, direct_rows);
     if (rc) return rc;
     DFM_REQUIRE(workspace_bytes >= L.total, DFM_ERR_WORKSPACE, "dfm_embed_bwd: workspace %zu < %zu", workspace_bytes, L.total);
     cudaStream_t st = static_cast<cudaStream_t>(stream);
     char* ws = static_cast<char*>(workspace);
-    const long long N = (long long)batch * plan->S;
-    DFM_REQUIRE(N < 0x7fffffffLL && ((long long)batch << slot_bits_of(plan->S)) < 0xffffffffLL, DFM_ERR_UNSUPPORTED,
+    const long long N = direct ? direct_rows : (long long)batch * plan->S;
+    const int payS = direct ? 1 : plan->S;
+    DFM_REQUIRE(N < 0x7fffffffLL && (direct || ((long long)batch << slot_bits_of(plan->S)) < 0xffffffffLL), DFM_ERR_UNSUPPORTED,
                 "dfm_embed_bwd: batch * slots must fit 31 bits");
 
     DevPlan* P = new DevPlan;
@@ -939,6 +953,7 @@ int dfm_embed_bwd(const dfm_plan* plan, int64_t batch, const void* const* inputs
     struct Guard { DevPlan* p; DevGrads* g; ~Guard() { delete p; delete g; } } guard{P, GR};
     int V = plan->fill(*P, inputs, params, true);
     P->aliased = field_emb == flat ? 1 : 0;
+    if (direct) P->S = 0;      // no slot tables in the row-list mode (field comes from the key)
     memset(GR, 0, sizeof(*GR));
     auto al16 = [](const void* p) { return (reinterpret_cast<uintptr_t>(p) & 15u) == 0; };
     bool aligned = al16(g_flat) && al16(g_field) && al16(field_emb) && al16(fm_sum) && al16(row_grad2);
@@ -951,8 +966,8 @@ int dfm_embed_bwd(const dfm_plan* plan, int64_t batch, const void* const* inputs
             DFM_REQUIRE(g.gw2 && g.gw1, DFM_ERR_INVALID, "dfm_embed_bwd: dense mode needs table grads for field %d", f);
             aligned = aligned && al16(g.gw2);
         }
-        if (!table) DFM_REQUIRE(g.gw2 && g.gb2 && g.gw1 && g.gb1, DFM_ERR_INVALID, "dfm_embed_bwd: DENSE field %d grads missing", f);
-        if (plan->dim[f] != plan->fm_dim) DFM_REQUIRE(g.gproj, DFM_ERR_INVALID, "dfm_embed_bwd: projection grad of field %d missing", f);
+        if (!table && !direct) DFM_REQUIRE(g.gw2 && g.gb2 && g.gw1 && g.gb1, DFM_ERR_INVALID, "dfm_embed_bwd: DENSE field %d grads missing", f);
+        if (plan->dim[f] != plan->fm_dim && !direct) DFM_REQUIRE(g.gproj, DFM_ERR_INVALID, "dfm_embed_bwd: projection grad of field %d missing", f);
     }
     if (!aligned) V = 1;
     const int lanes = plan->max_tdim > 0 ? plan->max_tdim / V : 1;
@@ -970,9 +985,9 @@ int dfm_embed_bwd(const dfm_plan* plan, int64_t batch, const void* const* inputs
     a.tail2 = reinterpret_cast<float*>(ws + L.off_tail2); a.tail1 = reinterpret_cast<float*>(ws + L.off_tail1);
     a.tail_start = reinterpret_cast<long long*>(ws + L.off_tstart);
     a.headg = reinterpret_cast<float*>(ws + L.off_headg); a.tailg = reinterpret_cast<float*>(ws + L.off_tailg);
-    a.slot_bits = slot_bits_of(plan->S);
+    a.slot_bits = slot_bits_of(payS);
     a.tail_field = reinterpret_cast<int*>(ws + L.off_tfield);
-    a.direct = 0;
+    a.direct = direct ? 1 : 0;
     a.counters = n_valid ? reinterpret_cast<unsigned long long*>(n_valid)
                          : reinterpret_cast<unsigned long long*>(ws + L.off_counters);
     const int fill_blocks = 8 * sm_count();
@@ -990,17 +1005,17 @@ int dfm_embed_bwd(const dfm_plan* plan, int64_t batch, const void* const* inputs
         DFM_CHECK_LAUNCH();
     }
     // 2. sort + segmented reduction of the id slots
-    if (N > 0 && batch > 0) {
+    if (N > 0 && (batch > 0 || direct) && !skip_tables) {
         DFM_CHECK_CUDA(cudaMemsetAsync(a.counters, 0, 16, st));
-        rc = dfm_sort_keys(plan, N, keys, sorted_keys, sorted_payload, ws + L.off_cub,
-                           L.off_payload + (size_t)N * 4 - L.off_cub, stream);
+        rc = sort_keys_impl(plan, N, payS, keys, sorted_keys, sorted_payload, ws + L.off_cub,
+                            L.off_payload + (size_t)N * 4 - L.off_cub, stream);
         if (rc) return rc;
         const int gpb = 256 / G;
         const long long unit = (long long)gpb * CHUNK;               // positions per segreduce block
         const long long n_units = ceil_div(N, unit);
         const unsigned blocks = (unsigned)n_units;
         const unsigned sblocks = (unsigned)ceil_div(n_units, gpb);
-        const size_t smem = seg_smem_bytes(gpb, plan->max_tdim, (int)unit, plan->S, plan->n_fields) + 16;
+        const size_t smem = seg_smem_bytes(gpb, plan->max_tdim, (int)unit, direct ? 0 : plan->S, plan->n_fields) + 16;
         bool any_generic = false;
         for (int f = 0; f < plan->n_fields; ++f)
             any_generic = any_generic || plan->kind[f] == DFM_SEQUENCE || (plan->kind[f] == DFM_SPARSE && plan->dim[f] != plan->fm_dim);
@@ -1023,6 +1038,7 @@ int dfm_embed_bwd(const dfm_plan* plan, int64_t batch, const void* const* inputs
     } else if (n_valid) {
         DFM_CHECK_CUDA(cudaMemsetAsync(n_valid, 0, 16, st));
     }
+    if (direct) return DFM_OK;   // the row-list mode has no DENSE-field / projection parameters
     // 3. DENSE-field Linear and projection gradients (tile fields first, then streamed fields)
     PgArgs* pg = new PgArgs;
     struct G2 { PgArgs* p; ~G2() { delete p; } } g2{pg};
@@ -1068,6 +1084,37 @@ int dfm_embed_bwd(const dfm_plan* plan, int64_t batch, const void* const* inputs
         DFM_CHECK_LAUNCH();
     }
     return DFM_OK;
+}
+
+int dfm_embed_bwd(const dfm_plan* plan, int64_t batch, const void* const* inputs,
+                  const float* const* params, const float* g_first, const float* g_field,
+                  const float* g_flat, const float* g_fm, const float* field_emb,
+                  const float* flat, const float* fm_sum, const uint32_t* keys,
+                  const uint32_t* aux, float l2, const float* l2_gscale, int mode,
+                  float* const* grads, uint32_t* sorted_keys, uint32_t* sorted_payload,
+                  float* row_grad2, float* row_grad1, int64_t* n_valid, void* workspace,
+                  size_t workspace_bytes, void* stream) {
+    return embed_bwd_impl(plan, batch, -1, inputs, params, g_first, g_field, g_flat, g_fm, field_emb, flat, fm_sum, keys,
+                          aux, l2, l2_gscale, mode, grads, sorted_keys, sorted_payload, row_grad2, row_grad1, n_valid,
+                          workspace, workspace_bytes, stream);
+}
+
+size_t dfm_rows_bwd_workspace_bytes(const dfm_plan* plan, int64_t n_rows) {
+    if (!plan || n_rows < 0) return 0;
+    BwdLayout L;
+    if (make_layout(plan, 0, L, n_rows) != DFM_OK) return 0;
+    return L.total;
+}
+
+int dfm_rows_bwd(const dfm_plan* plan, int64_t n_rows, const float* const* params, const uint32_t* keys,
+                 const float* g_rows, const float* g_first, float l2, const float* l2_gscale, int mode,
+                 float* const* grads, uint32_t* sorted_keys, uint32_t* sorted_payload, float* row_grad2,
+                 float* row_grad1, int64_t* n_valid, void* workspace, size_t workspace_bytes, void* stream) {
+    DFM_REQUIRE(n_rows >= 0, DFM_ERR_INVALID, "dfm_rows_bwd: negative row count");
+    DFM_REQUIRE(n_rows == 0 || (keys && g_rows), DFM_ERR_INVALID, "dfm_rows_bwd: null argument");
+    return embed_bwd_impl(plan, 0, n_rows, nullptr, params, g_first, nullptr, g_rows, nullptr, nullptr, nullptr, nullptr, keys,
+                          nullptr, l2, l2_gscale, mode, grads, sorted_keys, sorted_payload, row_grad2, row_grad1, n_valid,
+                          workspace, workspace_bytes, stream);
 }
 
 }  // extern "C"

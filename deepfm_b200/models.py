@@ -22,11 +22,16 @@ from .layers.l2 import l2_penalty
 
 
 class BaseCTRModel(nn.Module, ABC):
+    # Optional hook (not in the reference): a callable (schema, fm_embed_dim) -> module used instead of
+    # FeatureEmbedding, e.g. a row-sharded ShardedFeatureEmbedding for multi-GPU runs.
+    embedding_factory = None
+
     def __init__(self, schema, config) -> None:
         super().__init__()
         self.schema = schema
         self.config = config
-        self.embedding = FeatureEmbedding(schema, fm_embed_dim=config.feature.fm_embed_dim)
+        factory = type(self).embedding_factory or FeatureEmbedding
+        self.embedding = factory(schema, fm_embed_dim=config.feature.fm_embed_dim)
         self._build_components()
 
     @abstractmethod

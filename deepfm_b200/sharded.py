@@ -1,0 +1,412 @@
+"""Row-sharded ``FeatureEmbedding`` for one 8xB200 box (the reference is single-device).
+
+Every embedding table (second- and first-order) is sharded by row over the ``W`` ranks of a
+``torch.distributed`` NCCL group: ``owner(id) = id mod W``, ``local_row = id div W`` (uniform load
+under skewed ids; bit-exact contract: ``oracle.shard_route``).  Samples stay data-parallel:
+rank ``r`` owns its ``b`` samples.  One step is
+
+    forward   route ids by owner -> all-to-all(keys) -> owners gather rows (dfm_shard_gather)
+              -> all-to-all(vectors, first-order weights) back -> fused gather/FM kernel K1 reads the
+              received rows instead of a table (dfm_embed_fwd on a "received rows" plan)
+    backward  dfm_shard_pack_grad builds the per-row gradient (FM backward fused) in send order
+              -> all-to-all to the owners -> sorted segmented reduction on the owner (dfm_rows_bwd),
+              so each row's gradient is produced on exactly one GPU: no allreduce of table gradients.
+
+Dense-field Linears and everything else (DNN, CIN, attention) are replicated and data-parallel;
+``allreduce_dense`` averages their gradients in one flat bucket.  Supported here: SPARSE and DENSE
+fields with ``embedding_dim == fm_embed_dim`` (the Criteo shapes); multi-hot bags are not sharded yet.
+
+The phases are plain methods so that a single process can emulate ``W`` ranks (tests) and so that
+the routing logic (pure torch ops) runs on CPU tensors under gloo.
+"""
+
+from __future__ import annotations
+
+import ctypes as C
+import weakref
+from dataclasses import dataclass
+from typing import Dict, List, Optional, Sequence
+
+import torch
+import torch.nn as nn
+
+from . import _lib
+from .layers.embedding import RowSparseGrads
+from .schema import kind_of
+
+VIRTUAL_VOCAB = 1 << 26     # capacity of the "received rows" pseudo table of the sample-side plan
+
+
+def local_rows(vocab: int, world: int, rank: int) -> int:
+    """Number of ids in [0, vocab) owned by ``rank`` (id mod world == rank); at least 1 row is kept."""
+    return max((vocab - rank + world - 1) // world, 1)
+
+
+@dataclass
+class Route:
+    send_keys: torch.Tensor      # (n,) int32 (u32 bits): global rows in send order (grouped by owner)
+    counts: torch.Tensor         # (W,) int64: keys per destination
+    order: torch.Tensor          # (n,) int64: send position -> slot index b*S + s
+    pos_sb: torch.Tensor         # (S, b) int64: slot -> send position
+
+
+def route_ids(ids: torch.Tensor, row_base: torch.Tensor, world: int) -> Route:
+    """ids (b, S) int64, row_base (S,) int64.  Stable grouping by owner = id mod W (pure torch ops:
+    works on CPU and CUDA tensors; matches oracle.shard_route bit-exactly)."""
+    b, S = ids.shape
+    owner = (ids % world).reshape(-1)
+    keys = (ids + row_base[None, :]).reshape(-1)
+    order = torch.sort(owner, stable=True).indices
+    counts = torch.bincount(owner, minlength=world)
+    pos = torch.empty_like(order)
+    pos[order] = torch.arange(order.numel(), device=order.device, dtype=order.dtype)
+    return Route(send_keys=keys[order].to(torch.int32), counts=counts, order=order,
+                 pos_sb=pos.view(b, S).t().contiguous())
+
+
+class TorchDistComm:
+    """all-to-all over the default (NCCL or gloo) process group; sizes travel through the host."""
+
+    def __init__(self, group=None):
+        import torch.distributed as dist
+        self.dist, self.group = dist, group
+        self.world = dist.get_world_size(group)
+        self.rank = dist.get_rank(group)
+
+    def exchange_counts(self, counts: torch.Tensor) -> List[int]:
+        out = torch.empty_like(counts)
+        self.dist.all_to_all_single(out, counts, group=self.group)
+        return out.tolist()
+
+    def all_to_all(self, send: torch.Tensor, send_counts: Sequence[int], recv_counts: Sequence[int]) -> torch.Tensor:
+        out = send.new_empty((int(sum(recv_counts)),) + tuple(send.shape[1:]))
+        self.dist.all_to_all_single(out, send.contiguous(), list(recv_counts), list(send_counts), group=self.group)
+        return out
+
+
+class _ShardedEmbedFn(torch.autograd.Function):
+    @staticmethod
+    def forward(ctx, mod: "ShardedFeatureEmbedding", n_inputs: int, need_bwd: bool, *tensors):
+        inputs, params = tensors[:n_inputs], tensors[n_inputs:]
+        comm = mod.comm
+        route = mod.route(inputs)
+        send_counts = route.counts.tolist()                     # host sync: split sizes of the exchange
+        recv_counts = comm.exchange_counts(route.counts)
+        recv_keys = comm.all_to_all(route.send_keys, send_counts, recv_counts)
+        vec, fo, lkeys = mod.gather(recv_keys)
+        got_vec = comm.all_to_all(vec, recv_counts, send_counts)
+        got_fo = comm.all_to_all(fo, recv_counts, send_counts)
+        first, field, flat, fm, fm_sum, fin_inputs = mod.finish(inputs, route.pos_sb, got_vec, got_fo, need_bwd)
+        ctx.mod, ctx.n_inputs = mod, n_inputs
+        ctx.counts = (send_counts, recv_counts)
+        ctx.set_materialize_grads(False)
+        ctx.l2, ctx.done = None, False
+        if need_bwd:
+            ctx.save_for_backward(field, flat, fm_sum, route.pos_sb, lkeys, got_vec, got_fo, *fin_inputs, *params)
+            mod._live_ctx = weakref.ref(ctx)
+        return first, field, flat, fm
+
+    @staticmethod
+    def backward(ctx, g_first, g_field, g_flat, g_fm):
+        mod: ShardedFeatureEmbedding = ctx.mod
+        saved = ctx.saved_tensors
+        field, flat, fm_sum, pos_sb, lkeys, got_vec, got_fo = saved[:7]
+        n_f = len(mod.field_names)
+        fin_inputs = saved[7:7 + n_f]
+        params = saved[7 + n_f:]
+        send_counts, recv_counts = ctx.counts
+        lam, gscale = ctx.l2 if ctx.l2 is not None else (0.0, None)
+        ctx.done = True
+        cont = lambda g: None if g is None else g.contiguous()
+        g_vec, g_fo, dense_grads = mod.pack_grads(fin_inputs, pos_sb, got_vec, got_fo, cont(g_first), cont(g_field),
+                                                  cont(g_flat), cont(g_fm), field, flat, fm_sum, params, lam, gscale)
+        g_recv = mod.comm.all_to_all(g_vec, send_counts, recv_counts)
+        g1_recv = mod.comm.all_to_all(g_fo, send_counts, recv_counts)
+        table_grads = mod.owner_backward(lkeys, g_recv, g1_recv, params, lam, gscale)
+        grads = [dense_grads.get(i, table_grads.get(i)) for i in range(len(params))]
+        return (None, None, None) + (None,) * ctx.n_inputs + tuple(grads)
+
+
+class ShardedFeatureEmbedding(nn.Module):
+    def __init__(self, schema, fm_embed_dim: int = 16, world: int = 1, rank: int = 0, comm=None) -> None:
+        super().__init__()
+        self.schema, self.fm_embed_dim = schema, fm_embed_dim
+        self.world, self.rank, self.comm = world, rank, comm
+        self.field_names = list(schema.fields.keys())
+        self.second_order_embeddings = nn.ModuleDict()
+        self.first_order_embeddings = nn.ModuleDict()
+        self.projections = nn.ModuleDict()            # always empty here (dims == fm_embed_dim)
+        kinds, dims, vocabs, lvocabs = [], [], [], []
+        for name in self.field_names:
+            fs = schema.fields[name]
+            kind = kind_of(fs)
+            if kind not in ("sparse", "dense") or int(fs.embedding_dim) != fm_embed_dim:
+                raise NotImplementedError(
+                    f"field {name!r}: sharded tables support SPARSE/DENSE fields with embedding_dim == fm_embed_dim")
+            d = int(fs.embedding_dim)
+            if kind == "sparse":
+                rows = local_rows(int(fs.vocabulary_size), world, rank)
+                self.second_order_embeddings[name] = nn.Embedding(rows, d)
+                self.first_order_embeddings[name] = nn.Embedding(rows, 1)
+                vocabs.append(int(fs.vocabulary_size))
+                lvocabs.append(rows)
+            else:
+                self.second_order_embeddings[name] = nn.Linear(1, d)
+                self.first_order_embeddings[name] = nn.Linear(1, 1)
+                vocabs.append(0)
+                lvocabs.append(0)
+            kinds.append(_lib.KIND[kind])
+            dims.append(d)
+        self._kinds, self._dims, self._vocabs, self._lvocabs = kinds, dims, vocabs, lvocabs
+        self._init_weights()
+        self.num_fields = len(kinds)
+        self._sparse_idx = [i for i, k in enumerate(kinds) if k == _lib.SPARSE]
+        self._S = len(self._sparse_idx)
+        self._T = sum(dims)
+        grb, lrb = [0], [0]
+        for k, v, lv in zip(kinds, vocabs, lvocabs):
+            grb.append(grb[-1] + (v if k == _lib.SPARSE else 0))
+            lrb.append(lrb[-1] + (lv if k == _lib.SPARSE else 0))
+        if grb[-1] >= 2 ** 31:
+            raise NotImplementedError("sharded tables: total rows must stay below 2^31")
+        self._global_row_base, self._row_base = grb, lrb
+        self._max_tdim = fm_embed_dim if self._S else 0
+        self.grad_mode = "row_sparse"
+        self.row_grads: Optional[RowSparseGrads] = None
+        self.last_counts = None
+        self._live_ctx = None
+        self._plans = None
+        self._param_is_table: List[bool] = []
+        self._slot_of_param: List[int] = []
+        self._rb_dev = None
+
+    def _init_weights(self) -> None:
+        """Same family as the reference (embedding.py:66-74): xavier-uniform rows, zero padding row
+        (global id 0 lives on rank 0, local row 0), xavier Linears with zero bias."""
+        for name, m in list(self.second_order_embeddings.items()) + list(self.first_order_embeddings.items()):
+            if isinstance(m, nn.Embedding):
+                nn.init.xavier_uniform_(m.weight.data)
+                if self.rank == 0:
+                    m.weight.data[0].zero_()
+            else:
+                nn.init.xavier_uniform_(m.weight.data)
+                nn.init.zeros_(m.bias.data)
+
+    @torch.no_grad()
+    def load_from_full(self, full) -> None:
+        """Take this rank's rows (id = rank + W * local_row) and the replicated Linears from an
+        unsharded FeatureEmbedding."""
+        for name in self.field_names:
+            for mine, theirs in ((self.second_order_embeddings[name], full.second_order_embeddings[name]),
+                                 (self.first_order_embeddings[name], full.first_order_embeddings[name])):
+                if isinstance(mine, nn.Embedding):
+                    rows = theirs.weight[self.rank::self.world]
+                    mine.weight[: rows.shape[0]].copy_(rows)
+                else:
+                    mine.weight.copy_(theirs.weight)
+                    mine.bias.copy_(theirs.bias)
+
+    # -- plans --------------------------------------------------------------------------------
+    def _ensure_plans(self):
+        if self._plans is None:
+            lib = _lib.lib()
+            n = self.num_fields
+            ones, sums = [1] * n, [_lib.SUM] * n
+
+            def make(vocabs):
+                p = lib.dfm_plan_create(n, _lib.i32_array(self._kinds), _lib.i32_array(self._dims),
+                                        _lib.i64_array(vocabs), _lib.i32_array(ones), _lib.i32_array(sums),
+                                        int(self.fm_embed_dim))
+                if not p:
+                    raise ValueError(f"dfm_plan_create: {_lib.last_error()}")
+                return C.c_void_p(p)
+            cap = min(VIRTUAL_VOCAB, (2 ** 32 - 2) // max(self._S, 1))
+            virt = [cap if k == _lib.SPARSE else 0 for k in self._kinds]
+            self._plans = (make(self._lvocabs), make(virt))
+        return self._plans
+
+    def __del__(self):
+        plans = getattr(self, "_plans", None)
+        if plans:
+            for p in plans:
+                try:
+                    _lib.lib().dfm_plan_destroy(p)
+                except Exception:
+                    pass
+
+    def _ordered_params(self) -> List[torch.Tensor]:
+        out, is_table, slots = [], [], []
+        for f, name in enumerate(self.field_names):
+            second, first = self.second_order_embeddings[name], self.first_order_embeddings[name]
+            dense = self._kinds[f] == _lib.DENSE
+            entries = [(0, second.weight, not dense)] + ([(1, second.bias, False)] if dense else []) + \
+                      [(2, first.weight, not dense)] + ([(3, first.bias, False)] if dense else [])
+            for k, p, tab in entries:
+                out.append(p)
+                is_table.append(tab)
+                slots.append(5 * f + k)
+        self._param_is_table, self._slot_of_param = is_table, slots
+        return out
+
+    def _ptrs(self, tensors, override: Optional[Dict[int, torch.Tensor]] = None) -> C.Array:
+        arr = (C.c_void_p * (5 * self.num_fields))()
+        for slot, t in zip(self._slot_of_param, tensors):
+            arr[slot] = None if t is None else t.data_ptr()
+        for slot, t in (override or {}).items():
+            arr[slot] = t.data_ptr()
+        return arr
+
+    # -- phases -------------------------------------------------------------------------------
+    def route(self, inputs: Sequence[torch.Tensor]) -> Route:
+        ids = torch.stack([inputs[i] for i in self._sparse_idx], dim=1)
+        if self._rb_dev is None or self._rb_dev.device != ids.device:
+            self._rb_dev = torch.tensor([self._global_row_base[i] for i in self._sparse_idx], dtype=torch.int64,
+                                        device=ids.device)
+        return route_ids(ids, self._rb_dev, self.world)
+
+    def gather(self, recv_keys: torch.Tensor):
+        lib = _lib.lib()
+        local_plan, _ = self._ensure_plans()
+        params = self._ordered_params()
+        M = recv_keys.numel()
+        dev = params[0].device
+        vec = torch.empty((M, self.fm_embed_dim), device=dev, dtype=torch.float32)
+        fo = torch.empty((M,), device=dev, dtype=torch.float32)
+        lkeys = torch.empty((M,), device=dev, dtype=torch.int32)
+        _lib.check(lib.dfm_shard_gather(local_plan, self.world, self.rank, _lib.i64_array(self._global_row_base), M,
+                                        _lib.ptr(recv_keys), self._ptrs(params), _lib.ptr(vec), _lib.ptr(fo),
+                                        _lib.ptr(lkeys), _lib.stream_ptr()), "dfm_shard_gather")
+        return vec, fo, lkeys
+
+    def _virtual_ptrs(self, params, got_vec, got_fo):
+        over = {}
+        for i in self._sparse_idx:
+            over[5 * i + 0] = got_vec
+            over[5 * i + 2] = got_fo
+        return self._ptrs(params, over)
+
+    def finish(self, inputs, pos_sb, got_vec, got_fo, need_bwd: bool):
+        lib = _lib.lib()
+        _, sample_plan = self._ensure_plans()
+        params = self._ordered_params()
+        dev = got_vec.device
+        b = inputs[0].shape[0]
+        F, D, T = self.num_fields, self.fm_embed_dim, self._T
+        fin_inputs, s = [], 0
+        for i in range(F):
+            if self._kinds[i] == _lib.SPARSE:
+                fin_inputs.append(pos_sb[s])
+                s += 1
+            else:
+                fin_inputs.append(inputs[i])
+        flat = torch.empty((b, T), device=dev, dtype=torch.float32)
+        field = flat.view(b, F, D)
+        first = torch.empty((b, 1), device=dev, dtype=torch.float32)
+        fm = torch.empty((b, 1), device=dev, dtype=torch.float32)
+        fm_sum = torch.empty((b, D), device=dev, dtype=torch.float32) if need_bwd else None
+        _lib.check(lib.dfm_embed_fwd(sample_plan, b, _lib.ptr_array(fin_inputs), self._virtual_ptrs(params, got_vec, got_fo),
+                                     first.data_ptr(), field.data_ptr(), flat.data_ptr(), fm.data_ptr(),
+                                     _lib.ptr(fm_sum), None, None, None, _lib.stream_ptr()), "dfm_embed_fwd")
+        return first, field, flat, fm, fm_sum, fin_inputs
+
+    def pack_grads(self, fin_inputs, pos_sb, got_vec, got_fo, g_first, g_field, g_flat, g_fm, field, flat, fm_sum,
+                   params, lam, gscale):
+        lib = _lib.lib()
+        _, sample_plan = self._ensure_plans()
+        self._ordered_params()
+        dev = flat.device
+        b = flat.shape[0]
+        n = b * self._S
+        g_vec = torch.empty((n, self.fm_embed_dim), device=dev, dtype=torch.float32)
+        g_fo = torch.empty((n,), device=dev, dtype=torch.float32)
+        _lib.check(lib.dfm_shard_pack_grad(sample_plan, b, _lib.ptr(pos_sb), _lib.ptr(g_first), _lib.ptr(g_field),
+                                           _lib.ptr(g_flat), _lib.ptr(g_fm), field.data_ptr(), _lib.ptr(fm_sum),
+                                           _lib.ptr(g_vec), _lib.ptr(g_fo), _lib.stream_ptr()), "dfm_shard_pack_grad")
+        # DENSE-field Linear gradients (data-parallel parameters): K2 with the table part skipped
+        dense_grads: Dict[int, torch.Tensor] = {}
+        grads = []
+        for i, (p, tab) in enumerate(zip(params, self._param_is_table)):
+            g = None if tab else torch.empty_like(p)
+            grads.append(g)
+            if g is not None:
+                dense_grads[i] = g
+        if dense_grads:
+            ws = torch.empty((max(lib.dfm_embed_bwd_workspace_bytes(sample_plan, b), 16),), device=dev, dtype=torch.uint8)
+            _lib.check(lib.dfm_embed_bwd(
+                sample_plan, b, _lib.ptr_array(fin_inputs), self._virtual_ptrs(params, got_vec, got_fo),
+                _lib.ptr(g_first), _lib.ptr(g_field), _lib.ptr(g_flat), _lib.ptr(g_fm), field.data_ptr(), flat.data_ptr(),
+                _lib.ptr(fm_sum), None, None, float(lam), _lib.ptr(gscale), _lib.GRAD_SKIP_TABLES, self._ptrs(grads),
+                None, None, None, None, None, ws.data_ptr(), ws.numel(), _lib.stream_ptr()), "dfm_embed_bwd")
+        return g_vec, g_fo, dense_grads
+
+    def owner_backward(self, lkeys, g_recv, g1_recv, params, lam, gscale):
+        lib = _lib.lib()
+        local_plan, _ = self._ensure_plans()
+        self._ordered_params()
+        dev = g_recv.device
+        M = lkeys.numel()
+        rowsparse = self.grad_mode == "row_sparse"
+        grads, table_grads = [], {}
+        for i, (p, tab) in enumerate(zip(params, self._param_is_table)):
+            g = torch.empty_like(p) if (tab and not rowsparse) else None
+            grads.append(g)
+            if g is not None:
+                table_grads[i] = g
+        ws = torch.empty((max(lib.dfm_rows_bwd_workspace_bytes(local_plan, M), 16),), device=dev, dtype=torch.uint8)
+        skeys = torch.empty((max(M, 1),), device=dev, dtype=torch.int32)
+        spay = torch.empty((max(M, 1),), device=dev, dtype=torch.int32)
+        counts = torch.zeros((2,), device=dev, dtype=torch.int64)
+        rg2 = rg1 = None
+        if rowsparse:
+            rg2 = torch.empty((max(M, 1), self.fm_embed_dim), device=dev, dtype=torch.float32)
+            rg1 = torch.empty((max(M, 1),), device=dev, dtype=torch.float32)
+        _lib.check(lib.dfm_rows_bwd(local_plan, M, self._ptrs(params), _lib.ptr(lkeys), _lib.ptr(g_recv), _lib.ptr(g1_recv),
+                                    float(lam), _lib.ptr(gscale), _lib.GRAD_ROWSPARSE if rowsparse else _lib.GRAD_DENSE,
+                                    self._ptrs(grads), skeys.data_ptr(), spay.data_ptr(), _lib.ptr(rg2), _lib.ptr(rg1),
+                                    counts.data_ptr(), ws.data_ptr(), ws.numel(), _lib.stream_ptr()), "dfm_rows_bwd")
+        self.row_grads = RowSparseGrads(skeys, spay, rg2, rg1, counts, self._row_base, self._dims, self.field_names) \
+            if rowsparse else None
+        self.last_counts = counts
+        return table_grads
+
+    # -- module API ---------------------------------------------------------------------------
+    def _prepare(self, batch):
+        out = []
+        for i, name in enumerate(self.field_names):
+            x = _lib.require_cuda(batch[name], f"batch[{name!r}]")
+            x = x.float() if self._kinds[i] == _lib.DENSE else x.long()
+            out.append(x.reshape(x.shape[0]).contiguous())
+        return out
+
+    def forward_fused(self, batch):
+        if self.comm is None:
+            raise RuntimeError("ShardedFeatureEmbedding needs a communicator (e.g. TorchDistComm())")
+        self._ensure_plans()
+        params = self._ordered_params()
+        inputs = self._prepare(batch)
+        need_bwd = torch.is_grad_enabled() and any(p.requires_grad for p in params)
+        first, field, flat, fm = _ShardedEmbedFn.apply(self, len(inputs), need_bwd, *inputs, *params)
+        field._dfm_fm = (fm, field._version)
+        return first, field, flat, fm
+
+    def forward(self, batch):
+        first, field, flat, _ = self.forward_fused(batch)
+        return first, field, flat
+
+    def table_parameters(self):
+        return [p for p, t in zip(self._ordered_params(), self._param_is_table) if t]
+
+
+def allreduce_dense(params, world: int, group=None) -> None:
+    """Average the gradients of the data-parallel (replicated) parameters in one flat NCCL allreduce."""
+    import torch.distributed as dist
+    grads = [p.grad for p in params if p.grad is not None]
+    if not grads or world == 1:
+        return
+    flat = torch.cat([g.reshape(-1) for g in grads])
+    dist.all_reduce(flat, group=group)
+    flat.div_(world)
+    off = 0
+    for g in grads:
+        g.copy_(flat[off:off + g.numel()].view_as(g))
+        off += g.numel()

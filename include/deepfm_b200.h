@@ -45,7 +45,7 @@ typedef enum dfm_status {
 enum { DFM_SPARSE = 0, DFM_SEQUENCE = 1, DFM_DENSE = 2 };
 enum { DFM_SUM = 0, DFM_MEAN = 1, DFM_MAX = 2 };
 /* Gradient layout of the embedding tables produced by dfm_embed_bwd. */
-enum { DFM_GRAD_DENSE = 0, DFM_GRAD_ROWSPARSE = 1 };
+enum { DFM_GRAD_DENSE = 0, DFM_GRAD_ROWSPARSE = 1, DFM_GRAD_SKIP_TABLES = 2 /* only DENSE-field / projection grads */ };
 
 DFM_API const char* dfm_last_error(void);
 DFM_API int dfm_version(void);
@@ -192,6 +192,34 @@ DFM_API int dfm_attn_fwd(const float* x, int64_t batch, int n_fields, int dim, i
 DFM_API int dfm_attn_bwd(const float* x, const float* g_out, int64_t batch, int n_fields, int dim,
                          int attention_dim, int heads, int use_residual,
                          const float* const* params, float* g_x, float* const* g_params,
+                         void* workspace, size_t workspace_bytes, void* stream);
+
+/* ------------------------------------------------------------------------------------------
+ * Row-sharded tables over W GPUs (new; the reference is single-device).  owner(id) = id mod W,
+ * local_row = id div W, per field (oracle: shard_route).  The NCCL all-to-all of keys / vectors /
+ * vector gradients is issued by the host side between these calls.
+ *   dfm_shard_gather : owner side.  keys = global rows (row_base[f] + id) as received; writes the
+ *       looked-up rows vec (n, d_max), first-order weights fo (n) and the local sort keys
+ *       (local_row_base[f] + local_row, PAD for id 0) the owner-side backward consumes.
+ *   dfm_shard_pack_grad : sample side.  positions (S, B) int64 = send position of every id slot;
+ *       writes g_vec[pos] = g_flat + g_field + g_fm (fm_sum - e), g_fo[pos] = g_first.
+ *   dfm_rows_bwd : owner side backward = K2 on a row list: keys (n) with one gradient row each
+ *       (g_rows (n, d_max), g_first (n)); same sort / segreduce / stitch kernels and modes as
+ *       dfm_embed_bwd, the field is derived from the key.
+ * ---------------------------------------------------------------------------------------- */
+DFM_API int dfm_shard_gather(const dfm_plan* local_plan, int world, int rank,
+                             const int64_t* global_row_base, int64_t n_keys, const uint32_t* keys,
+                             const float* const* params, float* vec, float* fo, uint32_t* local_keys,
+                             void* stream);
+DFM_API int dfm_shard_pack_grad(const dfm_plan* plan, int64_t batch, const int64_t* positions,
+                                const float* g_first, const float* g_field, const float* g_flat,
+                                const float* g_fm, const float* field_emb, const float* fm_sum,
+                                float* g_vec, float* g_fo, void* stream);
+DFM_API size_t dfm_rows_bwd_workspace_bytes(const dfm_plan* plan, int64_t n_rows);
+DFM_API int dfm_rows_bwd(const dfm_plan* plan, int64_t n_rows, const float* const* params,
+                         const uint32_t* keys, const float* g_rows, const float* g_first, float l2,
+                         const float* l2_gscale, int mode, float* const* grads, uint32_t* sorted_keys,
+                         uint32_t* sorted_payload, float* row_grad2, float* row_grad1, int64_t* n_valid,
                          void* workspace, size_t workspace_bytes, void* stream);
 
 #ifdef __cplusplus

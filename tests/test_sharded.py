@@ -1,0 +1,185 @@
+"""Row-sharded embedding path.
+
+CPU (gloo, world_size 2): the routing rule and the all-to-all plumbing, bit-exact vs oracle.shard_route.
+GPU: W ranks emulated in one process (the exchange is done by slicing) -- forward views and every
+gradient of the sharded module must equal the unsharded FeatureEmbedding on the concatenated batch."""
+
+import os
+
+import numpy as np
+import pytest
+import torch
+import torch.multiprocessing as mp
+
+from deepfm_b200.schema import DatasetSchema, FeatureType, FieldSchema
+from deepfm_b200.sharded import Route, local_rows, route_ids
+from oracle import deepfm_oracle as O
+from tests.helpers import assert_close_rel
+
+
+def test_route_ids_matches_oracle_shard_route():
+    rng = np.random.default_rng(0)
+    b, S, W = 57, 5, 4
+    vocab = [11, 300, 7, 1000, 50]
+    ids = np.stack([rng.integers(0, v, b) for v in vocab], axis=1).astype(np.int64)
+    row_base = np.concatenate([[0], np.cumsum(vocab)[:-1]]).astype(np.int64)
+    r = route_ids(torch.from_numpy(ids), torch.from_numpy(row_base), W)
+    owner, local, counts, offsets, perm = O.shard_route(ids.reshape(-1), W)
+    assert r.counts.tolist() == counts.tolist()
+    assert r.order.tolist() == perm.tolist()
+    keys = (ids + row_base[None, :]).reshape(-1)
+    assert r.send_keys.tolist() == keys[perm].tolist()
+    pos = r.pos_sb.t().reshape(-1).numpy()                       # slot index -> send position
+    assert np.array_equal(perm[pos], np.arange(b * S))
+    for w in range(W):                                            # every key of bucket w is owned by w
+        seg = perm[offsets[w]:offsets[w + 1]]
+        assert np.all(ids.reshape(-1)[seg] % W == w)
+    assert local_rows(10, 4, 0) == 3 and local_rows(10, 4, 1) == 3 and local_rows(10, 4, 2) == 2 and local_rows(2, 4, 3) == 1
+
+
+def _gloo_worker(rank, world, port, out):
+    import torch.distributed as dist
+    os.environ.update(MASTER_ADDR="127.0.0.1", MASTER_PORT=str(port))
+    dist.init_process_group("gloo", rank=rank, world_size=world)
+    from deepfm_b200.sharded import TorchDistComm
+    comm = TorchDistComm()
+    gen = torch.Generator().manual_seed(100 + rank)
+    vocab = [13, 40, 9]
+    ids = torch.stack([torch.randint(0, v, (20,), generator=gen) for v in vocab], dim=1)
+    row_base = torch.tensor([0, 13, 53])
+    r = route_ids(ids, row_base, world)
+    send_counts = r.counts.tolist()
+    recv_counts = comm.exchange_counts(r.counts)
+    recv_keys = comm.all_to_all(r.send_keys, send_counts, recv_counts)
+    # owner check: (key - row_base[field]) mod W == rank
+    k = recv_keys.long()
+    field = (k[:, None] >= row_base[None, :]).sum(1) - 1
+    ok_owner = bool(torch.all((k - row_base[field]) % world == rank))
+    # reply with a function of the key; the sender must get it back in send order
+    reply = comm.all_to_all((k * 3 + 1).float()[:, None].repeat(1, 2), recv_counts, send_counts)
+    ok_reply = bool(torch.equal(reply[:, 0], r.send_keys.float() * 3 + 1))
+    back = reply[:, 0][r.pos_sb.t().reshape(-1)]                  # slot order
+    ok_slot = bool(torch.equal(back, ((ids + row_base[None, :]).reshape(-1) * 3 + 1).float()))
+    out.put((rank, ok_owner, ok_reply, ok_slot, sum(recv_counts)))
+    dist.destroy_process_group()
+
+
+def test_all_to_all_plumbing_gloo_world2():
+    ctx = mp.get_context("spawn")
+    q = ctx.Queue()
+    port = 29000 + os.getpid() % 2000
+    procs = [ctx.Process(target=_gloo_worker, args=(r, 2, port, q)) for r in range(2)]
+    for p in procs:
+        p.start()
+    res = [q.get(timeout=120) for _ in procs]
+    for p in procs:
+        p.join(timeout=60)
+        assert p.exitcode == 0
+    assert all(r[1] and r[2] and r[3] for r in res), res
+    assert sum(r[4] for r in res) == 2 * 20 * 3                   # every key arrived somewhere
+
+
+# ------------------------------------------------------------------------------------------ GPU
+
+def _schema(D):
+    fields = {}
+    for i in range(3):
+        fields[f"d{i}"] = FieldSchema(f"d{i}", FeatureType.DENSE, embedding_dim=D)
+    for i, v in enumerate((50, 2000, 7, 301, 11)):
+        fields[f"s{i}"] = FieldSchema(f"s{i}", FeatureType.SPARSE, vocabulary_size=v, embedding_dim=D)
+    return DatasetSchema(fields=fields)
+
+
+def _exchange(bufs, counts, reverse=False):
+    """bufs[s]: send buffer of rank s; counts[s][r]: items s sends to r (forward direction).
+    reverse=True routes owner replies back (bufs[r] is ordered by source s)."""
+    W = len(bufs)
+    out = []
+    if not reverse:
+        offs = [np.concatenate([[0], np.cumsum(c)]) for c in counts]
+        for r in range(W):
+            out.append(torch.cat([bufs[s][offs[s][r]:offs[s][r + 1]] for s in range(W)]))
+    else:
+        roffs = [np.concatenate([[0], np.cumsum([counts[s][r] for s in range(W)])]) for r in range(W)]
+        for s in range(W):
+            out.append(torch.cat([bufs[r][roffs[r][s]:roffs[r][s + 1]] for r in range(W)]))
+    return out
+
+
+@pytest.mark.gpu
+@pytest.mark.parametrize("W,D", [(2, 16), (3, 64)])
+def test_sharded_equals_unsharded_emulated_ranks(W, D):
+    from deepfm_b200.layers.embedding import FeatureEmbedding
+    from deepfm_b200.layers.fm import FMInteraction
+    from deepfm_b200.layers.l2 import l2_penalty
+    from deepfm_b200.sharded import ShardedFeatureEmbedding
+    torch.manual_seed(0)
+    rng = np.random.default_rng(W * D)
+    schema = _schema(D)
+    b, lam = 301, 1e-3
+    full = FeatureEmbedding(schema, D).cuda()
+    with torch.no_grad():
+        for p in full.parameters():
+            p.add_(0.05 * torch.randn_like(p))
+    batches = []
+    for r in range(W):
+        bt = {}
+        for n, f in schema.fields.items():
+            if f.feature_type == FeatureType.DENSE:
+                bt[n] = torch.from_numpy(rng.uniform(-1, 1, b).astype(np.float32)).cuda()
+            else:
+                bt[n] = torch.from_numpy(((rng.zipf(1.3, b) - 1) % f.vocabulary_size).astype(np.int64)).cuda()
+        batches.append(bt)
+    whole = {n: torch.cat([bt[n] for bt in batches]) for n in schema.fields}
+    T = schema.total_embedding_dim
+    g_first = torch.randn(W * b, 1, device="cuda")
+    g_flat = torch.randn(W * b, T, device="cuda")
+    g_fm = torch.randn(W * b, 1, device="cuda") * 0.1
+    fo, fe, fl = full(whole)
+    fm = FMInteraction()(fe)
+    ((fo * g_first).sum() + (fl * g_flat).sum() + (fm * g_fm).sum() + l2_penalty(full, lam)).backward()
+
+    mods = [ShardedFeatureEmbedding(schema, D, W, r).cuda() for r in range(W)]
+    for m in mods:
+        m.load_from_full(full)
+        m.grad_mode = "dense"
+    ins = [m._prepare(bt) for m, bt in zip(mods, batches)]
+    routes = [m.route(x) for m, x in zip(mods, ins)]
+    counts = [r.counts.tolist() for r in routes]
+    recv_keys = _exchange([r.send_keys for r in routes], counts)
+    gathered = [m.gather(k) for m, k in zip(mods, recv_keys)]
+    got_vec = _exchange([g[0] for g in gathered], counts, reverse=True)
+    got_fo = _exchange([g[1] for g in gathered], counts, reverse=True)
+    outs = [m.finish(x, r.pos_sb, v, f1, True) for m, x, r, v, f1 in zip(mods, ins, routes, got_vec, got_fo)]
+    assert torch.equal(torch.cat([o[0] for o in outs]), fo.detach())      # same rows, same order: bit-identical
+    assert torch.equal(torch.cat([o[2] for o in outs]), fl.detach())
+    assert torch.equal(torch.cat([o[3] for o in outs]), fm.detach())
+    # backward
+    gscale = torch.ones((), device="cuda")
+    packed = []
+    for r, (m, o) in enumerate(zip(mods, outs)):
+        sl = slice(r * b, (r + 1) * b)
+        params = m._ordered_params()
+        packed.append(m.pack_grads(o[5], routes[r].pos_sb, got_vec[r], got_fo[r], g_first[sl].contiguous(), None,
+                                   g_flat[sl].contiguous(), g_fm[sl].contiguous(), o[1], o[2], o[4], params, lam / W, gscale))
+    g_recv = _exchange([p[0] for p in packed], counts)
+    g1_recv = _exchange([p[1] for p in packed], counts)
+    for r, m in enumerate(mods):
+        params = m._ordered_params()
+        tg = m.owner_backward(gathered[r][2], g_recv[r], g1_recv[r], params, lam, gscale)
+        for i, g in tg.items():
+            slot = m._slot_of_param[i]
+            name = m.field_names[slot // 5]
+            ref = (full.second_order_embeddings if slot % 5 == 0 else full.first_order_embeddings)[name].weight.grad
+            ref = ref[r::W]
+            assert_close_rel(g[: ref.shape[0]].cpu(), ref.cpu(), 2e-5, f"rank {r} {name} slot {slot % 5}")
+    # replicated DENSE-field Linears: the sum over ranks of the per-rank gradients is the full gradient
+    for i, tab in enumerate(mods[0]._param_is_table):
+        if tab:
+            continue
+        slot = mods[0]._slot_of_param[i]
+        name = mods[0].field_names[slot // 5]
+        mod = (full.second_order_embeddings if slot % 5 < 2 else full.first_order_embeddings)[name]
+        ref = (mod.weight if slot % 5 in (0, 2) else mod.bias).grad
+        got = sum(p[2][i] for p in packed)
+        assert_close_rel(got.cpu(), ref.cpu(), 2e-5, f"dense {name} slot {slot % 5}")
