@@ -220,8 +220,11 @@ def run_ours(args, rank: int, local_rank: int, n_gpus: int):
         return ms.item()
 
     W_, K_ = max(args.warmup, 3), args.steps
+    dbg = (lambda m: print(f"[bench rank {rank}] {m}", file=sys.stderr, flush=True)) if os.environ.get("DFM_BENCH_DEBUG") else (lambda m: None)
+    dbg("model and batches ready")
     for i in range(W_):
         step(devb[i % n_batches], devy[i % n_batches])
+        dbg(f"warmup {i} done")
     sampler = ClockSampler(local_rank)
     if rank == 0:
         sampler.start()
@@ -248,6 +251,7 @@ def run_ours(args, rank: int, local_rank: int, n_gpus: int):
     h2d = sum(v.numel() * v.element_size() for v in host[0].values()) + host_y[0].numel() * 4
 
     # launch count of OUR kernels in one step (profiled outside the timed region)
+    # (every rank runs the step -- it contains collectives -- only rank 0 profiles it)
     launches = None
     if rank == 0:
         from torch.profiler import ProfilerActivity, profile
@@ -255,6 +259,9 @@ def run_ours(args, rank: int, local_rank: int, n_gpus: int):
             step(devb[0], devy[0])
             torch.cuda.synchronize()
         launches = sum(e.count for e in prof.key_averages() if "dfm::" in e.key or "DeviceRadixSort" in e.key)
+    else:
+        step(devb[0], devy[0])
+        torch.cuda.synchronize()
 
     if rank != 0:
         if n_gpus > 1:

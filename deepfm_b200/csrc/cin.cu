@@ -288,6 +288,12 @@ static int launch_opgemm(const OpGemmArgs& a, cudaStream_t st) {
     return DFM_OK;
 }
 
+// tcgen05 path (cin_tc.cu)
+int cin_layer_fwd_tc(const float* x0, long long x_bs, const float* hid, long long h_bs, const float* w,
+                     const float* bias, float* act, long long B, int F, int H, int D, int L, float* wpad,
+                     cudaStream_t st);
+size_t cin_tc_wpad_floats(int F, int Hmax, int Lmax);
+
 }  // namespace dfm
 
 using namespace dfm;
@@ -302,7 +308,7 @@ int dfm_cin_sizes(int n_fields, int dim, int n_layers, const int32_t* layer_size
     if (rc) return rc;
     const long long M = batch * dim;
     out[0] = c.out_dim;
-    out[1] = c.act_per_sample * batch * 4;                      // bytes of the activation buffer
+    out[1] = (c.act_per_sample * batch + (long long)cin_tc_wpad_floats(c.F, c.Hmax, c.Lmax)) * 4;   // activations + padded-W scratch
     size_t ws = 0;
     ws += align_up((size_t)batch * c.Lmax * dim * 4, 256);      // g_pre
     ws += 2 * align_up((size_t)batch * c.Hmax * dim * 4, 256);  // g_hidden ping-pong
@@ -318,12 +324,13 @@ int dfm_cin_fwd(const float* x0, int64_t batch, int n_fields, int dim, int n_lay
                 const float* const* biases, int precision, float* out, float* acts, void* stream) {
     DFM_REQUIRE(weights && biases && layer_sizes, DFM_ERR_INVALID, "dfm_cin_fwd: null argument");
     DFM_REQUIRE(batch >= 0, DFM_ERR_INVALID, "dfm_cin_fwd: negative batch");
-    DFM_REQUIRE(precision == 0, DFM_ERR_UNSUPPORTED, "dfm_cin_fwd: precision %d not built", precision);
+    DFM_REQUIRE(precision == 0 || precision == 1, DFM_ERR_UNSUPPORTED, "dfm_cin_fwd: precision %d not built", precision);
     CinPlan c;
     int rc = cin_plan(n_fields, dim, n_layers, layer_sizes, split_half, c);
     if (rc) return rc;
     if (batch == 0) return DFM_OK;
     DFM_REQUIRE(x0 && out && acts, DFM_ERR_INVALID, "dfm_cin_fwd: null tensor");
+    float* wpad = acts + c.act_per_sample * batch;
     cudaStream_t st = static_cast<cudaStream_t>(stream);
     const int F = c.F, D = c.D;
     const float* hid = x0;
@@ -338,7 +345,10 @@ int dfm_cin_fwd(const float* x0, int64_t batch, int n_fields, int dim, int n_lay
         a.out = act; a.o_bs = (long long)c.L[i] * D;
         a.bias = biases[i]; a.relu = 1; a.accumulate = 0;
         DFM_REQUIRE(weights[i] && biases[i], DFM_ERR_INVALID, "dfm_cin_fwd: layer %d weight/bias null", i);
-        rc = launch_opgemm(a, st);
+        if (precision == 1)   // tensor cores: TF32 inputs, FP32 accumulate
+            rc = cin_layer_fwd_tc(x0, (long long)F * D, hid, h_bs, weights[i], biases[i], act, batch, F, c.H[i], D, c.L[i], wpad, st);
+        else
+            rc = launch_opgemm(a, st);
         if (rc) return rc;
         const long long np = batch * c.direct[i];
         cin_pool_kernel<<<(unsigned)ceil_div(np, 256), 256, 0, st>>>(act, batch, c.L[i], D, c.direct[i], out, c.out_dim, c.col_off[i]);
@@ -357,7 +367,7 @@ int dfm_cin_bwd(const float* x0, const float* g_out, int64_t batch, int n_fields
                 void* workspace, size_t workspace_bytes, void* stream) {
     DFM_REQUIRE(weights && g_weights && g_biases && layer_sizes, DFM_ERR_INVALID, "dfm_cin_bwd: null argument");
     DFM_REQUIRE(batch >= 0, DFM_ERR_INVALID, "dfm_cin_bwd: negative batch");
-    DFM_REQUIRE(precision == 0, DFM_ERR_UNSUPPORTED, "dfm_cin_bwd: precision %d not built", precision);
+    DFM_REQUIRE(precision == 0 || precision == 1, DFM_ERR_UNSUPPORTED, "dfm_cin_bwd: precision %d not built", precision);
     CinPlan c;
     int rc = cin_plan(n_fields, dim, n_layers, layer_sizes, split_half, c);
     if (rc) return rc;

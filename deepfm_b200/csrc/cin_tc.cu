@@ -1,0 +1,278 @@
+// CIN layer forward on the 5th-generation tensor cores (tcgen05, TF32 inputs, FP32 accumulate).
+//
+// The layer is the GEMM  C[(b,d)][l] = sum_k Z[(b,d)][k] * W[l][k],  k = h*F + f,
+// Z[(b,d)][k] = hidden[b,h,d] * x0[b,f,d]   (reference: deepfm/models/layers/cin.py:84-91).
+// Z never exists in memory: 8 producer warps synthesise 128 x 32 tiles of it straight into the
+// 128B-swizzled K-major shared-memory layout a UMMA descriptor expects (one thread per GEMM row,
+// the row's x0 values parked in shared memory, the hidden value streamed), while the same warps
+// stage the matching W tile; one elected thread of a ninth warp issues
+// `tcgen05.mma.cta_group::1.kind::tf32` (M = 128, N = L, K = 8 per instruction) into two TMEM
+// accumulators (two 128-row tiles share every W tile); `tcgen05.commit` hands shared-memory stages
+// back to the producers through mbarriers.  The epilogue reads the accumulators with
+// `tcgen05.ld.32x32b`, adds the bias, applies ReLU and writes the (B, L, D) activation.
+// Persistent grid: one CTA per SM walks 256-row super-tiles.
+#include "common.cuh"
+
+namespace dfm {
+namespace tc {
+
+constexpr int ROWS = 256;        // GEMM rows per CTA super-tile (2 UMMA tiles of 128)
+constexpr int KB = 32;           // k per stage: 32 tf32 = one 128-byte swizzle row
+constexpr int NSTAGE = 3;
+constexpr int PRODUCER_WARPS = 8;
+constexpr int THREADS = (PRODUCER_WARPS + 1) * 32;
+
+__device__ __forceinline__ uint32_t smem_u32(const void* p) { return (uint32_t)__cvta_generic_to_shared(p); }
+
+__device__ __forceinline__ void mbar_init(uint64_t* bar, int count) {
+    asm volatile("mbarrier.init.shared::cta.b64 [%0], %1;" ::"r"(smem_u32(bar)), "r"(count));
+}
+__device__ __forceinline__ void mbar_arrive(uint64_t* bar) {
+    asm volatile("{\n\t.reg .b64 st;\n\tmbarrier.arrive.shared::cta.b64 st, [%0];\n\t}" ::"r"(smem_u32(bar)) : "memory");
+}
+__device__ __forceinline__ void mbar_wait(uint64_t* bar, uint32_t parity) {
+    asm volatile(
+        "{\n\t.reg .pred p;\n\t"
+        "WAIT_%=:\n\t"
+        "mbarrier.try_wait.parity.shared::cta.b64 p, [%0], %1;\n\t"
+        "@p bra DONE_%=;\n\t"
+        "bra WAIT_%=;\n\t"
+        "DONE_%=:\n\t}" ::"r"(smem_u32(bar)), "r"(parity) : "memory");
+}
+__device__ __forceinline__ void fence_proxy_async() { asm volatile("fence.proxy.async.shared::cta;" ::: "memory"); }
+__device__ __forceinline__ void tc_fence_before() { asm volatile("tcgen05.fence::before_thread_sync;" ::: "memory"); }
+__device__ __forceinline__ void tc_fence_after() { asm volatile("tcgen05.fence::after_thread_sync;" ::: "memory"); }
+
+__device__ __forceinline__ void tmem_alloc(uint32_t* dst_smem, uint32_t cols) {
+    asm volatile("tcgen05.alloc.cta_group::1.sync.aligned.shared::cta.b32 [%0], %1;" ::"r"(smem_u32(dst_smem)), "r"(cols) : "memory");
+    asm volatile("tcgen05.relinquish_alloc_permit.cta_group::1.sync.aligned;" ::: "memory");
+}
+__device__ __forceinline__ void tmem_dealloc(uint32_t addr, uint32_t cols) {
+    asm volatile("tcgen05.dealloc.cta_group::1.sync.aligned.b32 %0, %1;" ::"r"(addr), "r"(cols) : "memory");
+}
+__device__ __forceinline__ void umma_commit(uint64_t* bar) {
+    asm volatile("tcgen05.commit.cta_group::1.mbarrier::arrive::one.shared::cluster.b64 [%0];" ::"r"(smem_u32(bar)) : "memory");
+}
+// D[tmem] (+)= A[smem] * B[smem]^T, TF32 inputs, M = 128
+__device__ __forceinline__ void umma_tf32(uint32_t tmem_d, uint64_t desc_a, uint64_t desc_b, uint32_t idesc, uint32_t accumulate) {
+    asm volatile(
+        "{\n\t.reg .pred p;\n\t"
+        "setp.ne.b32 p, %4, 0;\n\t"
+        "tcgen05.mma.cta_group::1.kind::tf32 [%0], %1, %2, %3, p;\n\t}"
+        ::"r"(tmem_d), "l"(desc_a), "l"(desc_b), "r"(idesc), "r"(accumulate) : "memory");
+}
+// K-major, 128-byte swizzle, 8-row groups 1024 B apart (cute::UMMA::SmemDescriptor, sm_100 version 1)
+__device__ __forceinline__ uint64_t make_desc(uint32_t smem_addr) {
+    uint64_t d = 0;
+    d |= (uint64_t)((smem_addr & 0x3FFFFu) >> 4);
+    d |= (uint64_t)1 << 16;                 // leading byte offset (unused for swizzled K-major)
+    d |= (uint64_t)(1024 >> 4) << 32;       // stride byte offset: 8 rows x 128 B
+    d |= (uint64_t)1 << 46;                 // descriptor version (Blackwell)
+    d |= (uint64_t)2 << 61;                 // SWIZZLE_128B
+    return d;
+}
+__device__ __forceinline__ void tmem_ld32(uint32_t addr, float* v) {
+    uint32_t* r = reinterpret_cast<uint32_t*>(v);
+    asm volatile(
+        "tcgen05.ld.sync.aligned.32x32b.x32.b32 "
+        "{%0, %1, %2, %3, %4, %5, %6, %7, %8, %9, %10, %11, %12, %13, %14, %15, "
+        "%16, %17, %18, %19, %20, %21, %22, %23, %24, %25, %26, %27, %28, %29, %30, %31}, [%32];"
+        : "=r"(r[0]), "=r"(r[1]), "=r"(r[2]), "=r"(r[3]), "=r"(r[4]), "=r"(r[5]), "=r"(r[6]), "=r"(r[7]),
+          "=r"(r[8]), "=r"(r[9]), "=r"(r[10]), "=r"(r[11]), "=r"(r[12]), "=r"(r[13]), "=r"(r[14]), "=r"(r[15]),
+          "=r"(r[16]), "=r"(r[17]), "=r"(r[18]), "=r"(r[19]), "=r"(r[20]), "=r"(r[21]), "=r"(r[22]), "=r"(r[23]),
+          "=r"(r[24]), "=r"(r[25]), "=r"(r[26]), "=r"(r[27]), "=r"(r[28]), "=r"(r[29]), "=r"(r[30]), "=r"(r[31])
+        : "r"(addr) : "memory");
+    asm volatile("tcgen05.wait::ld.sync.aligned;" ::: "memory");
+}
+
+struct CinTcArgs {
+    const float* x0; long long x_bs;       // x0[b*x_bs + f*D + d]
+    const float* hid; long long h_bs;      // hidden[b*h_bs + h*D + d]
+    const float* wpad;                     // (Np, Kp) zero-padded weight, row-major
+    const float* bias;                     // (L)
+    float* act;                            // (B, L, D)
+    long long M;                           // B * D rows
+    int F, H, D, L, Np, Kp;
+    uint32_t tmem_cols;
+};
+
+// (L, K) -> (Np, Kp) zero padded
+__global__ void cin_pad_w_kernel(const float* __restrict__ w, int L, int K, int Np, int Kp, float* __restrict__ out) {
+    const long long n = (long long)Np * Kp;
+    for (long long i = (long long)blockIdx.x * blockDim.x + threadIdx.x; i < n; i += (long long)gridDim.x * blockDim.x) {
+        const int l = (int)(i / Kp), k = (int)(i - (long long)l * Kp);
+        out[i] = (l < L && k < K) ? __ldg(w + (size_t)l * K + k) : 0.f;
+    }
+}
+
+__global__ void __launch_bounds__(THREADS, 1)
+cin_tc_fwd_kernel(const __grid_constant__ CinTcArgs a) {
+    extern __shared__ unsigned char smem_raw[];
+    // the 128-byte swizzle is a function of the absolute shared address: tiles must be 1024-B aligned
+    unsigned char* smem = smem_raw + ((1024u - (smem_u32(smem_raw) & 1023u)) & 1023u);
+    // carve: [stage A tiles: 2 x 16 KB][stage B tile: Np x 128 B] x NSTAGE, then x0 rows, barriers
+    const int a_bytes = 2 * 128 * 128, b_bytes = a.Np * 128;
+    const int stage_bytes = (a_bytes + b_bytes + 1023) & ~1023;
+    unsigned char* stage0 = smem;
+    float* s_x0 = reinterpret_cast<float*>(smem + (size_t)NSTAGE * stage_bytes);          // [F][ROWS]
+    uint64_t* bars = reinterpret_cast<uint64_t*>(s_x0 + (size_t)a.F * ROWS);
+    uint64_t* full = bars;                 // [NSTAGE] producers -> MMA
+    uint64_t* empty = bars + NSTAGE;       // [NSTAGE] MMA (commit) -> producers
+    uint64_t* acc_full = bars + 2 * NSTAGE;
+    uint64_t* acc_empty = acc_full + 1;
+    uint32_t* tmem_slot = reinterpret_cast<uint32_t*>(acc_empty + 1);
+
+    const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
+    if (threadIdx.x == 0) {
+        for (int s = 0; s < NSTAGE; ++s) { mbar_init(full + s, PRODUCER_WARPS); mbar_init(empty + s, 1); }
+        mbar_init(acc_full, 1);
+        mbar_init(acc_empty, PRODUCER_WARPS);
+        asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
+    }
+    if (warp == PRODUCER_WARPS) tmem_alloc(tmem_slot, a.tmem_cols);
+    tc_fence_before();
+    __syncthreads();
+    tc_fence_after();
+    const uint32_t tmem_base = *tmem_slot;
+
+    const int n_kb = a.Kp / KB;
+    const long long n_super = (a.M + ROWS - 1) / ROWS;
+    // instruction descriptor: D = F32, A = B = TF32, both K-major, N, M = 128
+    const uint32_t idesc = (1u << 4) | (2u << 7) | (2u << 10) | ((uint32_t)(a.Np >> 3) << 17) | ((128u >> 4) << 24);
+
+    if (warp < PRODUCER_WARPS) {
+        // ------------------------------------------------------------------ producers + epilogue
+        const int r = threadIdx.x;                   // row inside the super-tile
+        const int tile = r >> 7, row = r & 127;
+        uint32_t it = 0;                             // running stage counter (k-blocks produced so far)
+        uint32_t acc_phase = 0;
+        for (long long st = blockIdx.x; st < n_super; st += gridDim.x) {
+            const long long m = st * ROWS + r;
+            const bool live = m < a.M;
+            const long long b = live ? m / a.D : 0;
+            const int d = live ? (int)(m - b * a.D) : 0;
+            const float* xrow = a.x0 + b * a.x_bs + d;
+            const float* hrow = a.hid + b * a.h_bs + d;
+            for (int f = 0; f < a.F; ++f) s_x0[f * ROWS + r] = live ? __ldg(xrow + (size_t)f * a.D) : 0.f;
+            int h = 0, f = 0;
+            float hv = live ? __ldg(hrow) : 0.f;
+            float hv_next = (live && a.H > 1) ? __ldg(hrow + a.D) : 0.f;
+            for (int kb = 0; kb < n_kb; ++kb, ++it) {
+                const uint32_t s = it % NSTAGE, ph = (it / NSTAGE) & 1u;
+                mbar_wait(empty + s, ph ^ 1u);                          // stage free (first pass: immediately)
+                unsigned char* sa = stage0 + (size_t)s * stage_bytes + tile * (128 * 128) + row * 128;
+#pragma unroll
+                for (int c = 0; c < 8; ++c) {
+                    float4 v;
+                    float* pv = reinterpret_cast<float*>(&v);
+#pragma unroll
+                    for (int e = 0; e < 4; ++e) {
+                        pv[e] = hv * s_x0[f * ROWS + r];
+                        if (++f == a.F) {
+                            f = 0; ++h;
+                            hv = hv_next;
+                            hv_next = (live && h + 1 < a.H) ? __ldg(hrow + (size_t)(h + 1) * a.D) : 0.f;
+                            if (h >= a.H) hv = 0.f;                     // zero padding beyond K
+                        }
+                    }
+                    *reinterpret_cast<float4*>(sa + ((c ^ (row & 7)) << 4)) = v;
+                }
+                // W tile: Np rows x 128 B, 16-byte chunks spread over the 256 producer threads
+                unsigned char* sb = stage0 + (size_t)s * stage_bytes + a_bytes;
+                for (int q = r; q < a.Np * 8; q += PRODUCER_WARPS * 32) {
+                    const int n = q >> 3, c = q & 7;
+                    const float4 w = __ldg(reinterpret_cast<const float4*>(a.wpad + (size_t)n * a.Kp + kb * KB) + c);
+                    *reinterpret_cast<float4*>(sb + n * 128 + ((c ^ (n & 7)) << 4)) = w;
+                }
+                fence_proxy_async();                                     // generic-proxy writes -> async proxy (UMMA)
+                __syncwarp();
+                if (lane == 0) mbar_arrive(full + s);
+            }
+            // ---- epilogue: TMEM -> registers -> bias + ReLU -> act[b][l][d]
+            mbar_wait(acc_full, acc_phase);
+            acc_phase ^= 1u;
+            tc_fence_after();
+            const uint32_t taddr = tmem_base + ((uint32_t)((warp & 3) * 32) << 16) + (uint32_t)(tile * a.Np);
+            float* out = a.act + (size_t)b * a.L * a.D + d;
+            for (int c0 = 0; c0 < a.Np; c0 += 32) {
+                float v[32];
+                tmem_ld32(taddr + c0, v);
+                if (live) {
+#pragma unroll
+                    for (int i = 0; i < 32; ++i) {
+                        const int l = c0 + i;
+                        if (l < a.L) out[(size_t)l * a.D] = fmaxf(v[i] + __ldg(a.bias + l), 0.f);
+                    }
+                }
+            }
+            tc_fence_before();
+            __syncwarp();
+            if (lane == 0) mbar_arrive(acc_empty);
+        }
+    } else if (lane == 0) {
+        // ------------------------------------------------------------------ MMA issuer (one thread)
+        uint32_t it = 0, acc_phase = 0;
+        for (long long st = blockIdx.x; st < n_super; st += gridDim.x) {
+            mbar_wait(acc_empty, acc_phase ^ 1u);                       // epilogue drained the accumulators
+            acc_phase ^= 1u;
+            tc_fence_after();
+            for (int kb = 0; kb < n_kb; ++kb, ++it) {
+                const uint32_t s = it % NSTAGE, ph = (it / NSTAGE) & 1u;
+                mbar_wait(full + s, ph);
+                tc_fence_after();
+                const uint32_t sa = smem_u32(stage0 + (size_t)s * stage_bytes);
+                const uint64_t db = make_desc(sa + a_bytes);
+#pragma unroll
+                for (int t = 0; t < 2; ++t) {
+                    const uint64_t da = make_desc(sa + t * (128 * 128));
+#pragma unroll
+                    for (int k = 0; k < KB / 8; ++k)                     // K = 8 tf32 = 32 B per instruction
+                        umma_tf32(tmem_base + (uint32_t)(t * a.Np), da + (uint64_t)(k * 2), db + (uint64_t)(k * 2), idesc,
+                                  (kb | k) ? 1u : 0u);
+                }
+                umma_commit(empty + s);                                  // stage reusable once these MMAs retire
+            }
+            umma_commit(acc_full);                                       // accumulators complete
+        }
+    }
+    __syncthreads();
+    if (warp == PRODUCER_WARPS) tmem_dealloc(tmem_base, a.tmem_cols);
+}
+
+}  // namespace tc
+
+// One CIN layer forward on tcgen05.  wpad: workspace of Np*Kp floats.
+int cin_layer_fwd_tc(const float* x0, long long x_bs, const float* hid, long long h_bs, const float* w,
+                     const float* bias, float* act, long long B, int F, int H, int D, int L, float* wpad,
+                     cudaStream_t st) {
+    using namespace tc;
+    const int K = H * F;
+    const int Np = (L + 15) & ~15, Kp = (K + KB - 1) / KB * KB;
+    DFM_REQUIRE(Np <= 256, DFM_ERR_UNSUPPORTED, "cin tcgen05: layer size %d > 256", L);
+    long long pb = ceil_div((long long)Np * Kp, 256);
+    if (pb > 4LL * sm_count()) pb = 4LL * sm_count();
+    cin_pad_w_kernel<<<(unsigned)pb, 256, 0, st>>>(w, L, K, Np, Kp, wpad);
+    CinTcArgs a;
+    a.x0 = x0; a.x_bs = x_bs; a.hid = hid; a.h_bs = h_bs; a.wpad = wpad; a.bias = bias; a.act = act;
+    a.M = B * D; a.F = F; a.H = H; a.D = D; a.L = L; a.Np = Np; a.Kp = Kp;
+    uint32_t cols = 32;
+    while (cols < (uint32_t)(2 * Np)) cols <<= 1;
+    a.tmem_cols = cols;
+    const int stage_bytes = (2 * 128 * 128 + Np * 128 + 1023) & ~1023;
+    const size_t smem = (size_t)NSTAGE * stage_bytes + (size_t)F * ROWS * 4 + (2 * NSTAGE + 2) * 8 + 16 + 1024;
+    DFM_REQUIRE(smem <= 227 * 1024, DFM_ERR_UNSUPPORTED, "cin tcgen05: %d fields need %zu B shared memory", F, smem);
+    DFM_CHECK_CUDA(cudaFuncSetAttribute(cin_tc_fwd_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
+    long long grid = ceil_div(a.M, ROWS);
+    if (grid > sm_count()) grid = sm_count();
+    cin_tc_fwd_kernel<<<(unsigned)grid, THREADS, smem, st>>>(a);
+    DFM_CHECK_LAUNCH();
+    return DFM_OK;
+}
+
+size_t cin_tc_wpad_floats(int F, int Hmax, int Lmax) {
+    const int Np = (Lmax + 15) & ~15;
+    const long long Kp = ((long long)Hmax * F + tc::KB - 1) / tc::KB * tc::KB;
+    return (size_t)Np * Kp;
+}
+
+}  // namespace dfm

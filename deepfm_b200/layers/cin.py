@@ -58,7 +58,9 @@ class _CINFn(torch.autograd.Function):
 
 
 class CIN(nn.Module):
-    PRECISIONS = {"fp32": 0}
+    # "fp32": CUDA cores, reference-exact up to summation order.  "tf32": forward GEMMs on tcgen05 tensor
+    # cores (TF32 inputs, FP32 accumulate; ~1e-3 relative); the backward stays fp32.
+    PRECISIONS = {"fp32": 0, "tf32": 1}
 
     def __init__(self, num_fields: int, embed_dim: int, layer_sizes: Optional[List[int]] = None,
                  split_half: bool = True) -> None:

@@ -126,3 +126,29 @@ def test_attention_reference_shape_facts():
     xg = x.clone().requires_grad_(True)
     att(xg).sum().backward()
     assert xg.grad is not None
+
+
+# ----------------------------------------------------------------- tcgen05 (TF32) CIN forward
+# TF32 inputs (10-bit mantissa), FP32 accumulation in TMEM: tolerance 2e-3 per-tensor max-norm relative
+# (~1.3e-4 .. 1e-3 expected); the backward stays fp32 and must still match at 2e-3.
+
+@pytest.mark.parametrize("B,F,D,sizes,split", [(4, 16, 16, [64], True), (300, 16, 16, [64], True),
+                                                (130, 16, 16, [128, 128, 64], True), (65, 39, 64, [24, 20], True),
+                                                (37, 7, 12, [9, 5, 3], False), (513, 39, 64, [128, 128], True)])
+def test_cin_tcgen05_tf32_vs_oracle(B, F, D, sizes, split):
+    rng = np.random.default_rng(B + F)
+    cin = CIN(F, D, sizes, split).cuda()
+    cin.precision = "tf32"
+    x = (rng.standard_normal((B, F, D)) * 0.5).astype(np.float32)
+    W = [c.weight.detach().cpu().numpy()[:, :, 0].astype(np.float64) for c in cin.conv_layers]
+    b = [c.bias.detach().cpu().numpy().astype(np.float64) for c in cin.conv_layers]
+    xt = torch.from_numpy(x).cuda().requires_grad_(True)
+    out = cin(xt)
+    want = O.cin_forward(x.astype(np.float64), W, b, split)
+    assert_close_rel(out.detach().cpu(), want, 2e-3, "cin tf32 out")
+    g = rng.standard_normal(want.shape).astype(np.float32)
+    out.backward(torch.from_numpy(g).cuda())
+    gx, gW, gb = O.cin_backward(x.astype(np.float64), W, b, split, g.astype(np.float64))
+    assert_close_rel(xt.grad.cpu(), gx, 5e-3, "gx")
+    for i, c in enumerate(cin.conv_layers):
+        assert_close_rel(c.weight.grad.cpu()[:, :, 0], gW[i], 5e-3, f"gW{i}")
