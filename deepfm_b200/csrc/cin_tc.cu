@@ -11,6 +11,8 @@
 // back to the producers through mbarriers.  The epilogue reads the accumulators with
 // `tcgen05.ld.32x32b`, adds the bias, applies ReLU and writes the (B, L, D) activation.
 // Persistent grid: one CTA per SM walks 256-row super-tiles.
+#include <cuda.h>
+
 #include "common.cuh"
 
 namespace dfm {
@@ -92,21 +94,33 @@ struct CinTcArgs {
     const float* bias;                     // (L)
     float* act;                            // (B, L, D)
     long long M;                           // B * D rows
-    int F, H, D, L, Np, Kp;
+    int F, FP, H, D, L, Np, Kp;            // FP: F padded to a multiple of 4 (k = h*FP + f)
     uint32_t tmem_cols;
 };
 
-// (L, K) -> (Np, Kp) zero padded
-__global__ void cin_pad_w_kernel(const float* __restrict__ w, int L, int K, int Np, int Kp, float* __restrict__ out) {
+// (L, H*F) -> (Np, Kp) zero padded, column k' = h*FP + f
+__global__ void cin_pad_w_kernel(const float* __restrict__ w, int L, int H, int F, int FP, int Np, int Kp,
+                                 float* __restrict__ out) {
     const long long n = (long long)Np * Kp;
     for (long long i = (long long)blockIdx.x * blockDim.x + threadIdx.x; i < n; i += (long long)gridDim.x * blockDim.x) {
         const int l = (int)(i / Kp), k = (int)(i - (long long)l * Kp);
-        out[i] = (l < L && k < K) ? __ldg(w + (size_t)l * K + k) : 0.f;
+        const int h = k / FP, f = k - h * FP;
+        out[i] = (l < L && h < H && f < F) ? __ldg(w + (size_t)l * H * F + h * F + f) : 0.f;
     }
 }
 
+__device__ __forceinline__ void mbar_arrive_expect_tx(uint64_t* bar, uint32_t bytes) {
+    asm volatile("{\n\t.reg .b64 st;\n\tmbarrier.arrive.expect_tx.shared::cta.b64 st, [%0], %1;\n\t}" ::"r"(smem_u32(bar)), "r"(bytes) : "memory");
+}
+// TMA: 2-D tile of the padded weight (box = 32 floats x Np rows, 128-byte swizzle) -> shared memory
+__device__ __forceinline__ void tma_load_2d(void* dst, const CUtensorMap* map, int x, int y, uint64_t* bar) {
+    asm volatile(
+        "cp.async.bulk.tensor.2d.shared::cluster.global.tile.mbarrier::complete_tx::bytes [%0], [%1, {%2, %3}], [%4];"
+        ::"r"(smem_u32(dst)), "l"(reinterpret_cast<uint64_t>(map)), "r"(x), "r"(y), "r"(smem_u32(bar)) : "memory");
+}
+
 __global__ void __launch_bounds__(THREADS, 1)
-cin_tc_fwd_kernel(const __grid_constant__ CinTcArgs a) {
+cin_tc_fwd_kernel(const __grid_constant__ CinTcArgs a, const __grid_constant__ CUtensorMap wmap) {
     extern __shared__ unsigned char smem_raw[];
     // the 128-byte swizzle is a function of the absolute shared address: tiles must be 1024-B aligned
     unsigned char* smem = smem_raw + ((1024u - (smem_u32(smem_raw) & 1023u)) & 1023u);
@@ -114,8 +128,9 @@ cin_tc_fwd_kernel(const __grid_constant__ CinTcArgs a) {
     const int a_bytes = 2 * 128 * 128, b_bytes = a.Np * 128;
     const int stage_bytes = (a_bytes + b_bytes + 1023) & ~1023;
     unsigned char* stage0 = smem;
-    float* s_x0 = reinterpret_cast<float*>(smem + (size_t)NSTAGE * stage_bytes);          // [F][ROWS]
-    uint64_t* bars = reinterpret_cast<uint64_t*>(s_x0 + (size_t)a.F * ROWS);
+    const int FPS = a.FP + 4;              // row stride (floats): 128-bit reads of 8 lanes hit 8 distinct bank groups
+    float* s_x0 = reinterpret_cast<float*>(smem + (size_t)NSTAGE * stage_bytes);          // [ROWS][FPS]
+    uint64_t* bars = reinterpret_cast<uint64_t*>(s_x0 + (size_t)ROWS * FPS);
     uint64_t* full = bars;                 // [NSTAGE] producers -> MMA
     uint64_t* empty = bars + NSTAGE;       // [NSTAGE] MMA (commit) -> producers
     uint64_t* acc_full = bars + 2 * NSTAGE;
@@ -124,7 +139,8 @@ cin_tc_fwd_kernel(const __grid_constant__ CinTcArgs a) {
 
     const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
     if (threadIdx.x == 0) {
-        for (int s = 0; s < NSTAGE; ++s) { mbar_init(full + s, PRODUCER_WARPS); mbar_init(empty + s, 1); }
+        for (int s = 0; s < NSTAGE; ++s) { mbar_init(full + s, PRODUCER_WARPS + 1); mbar_init(empty + s, 1); }
+        asm volatile("prefetch.tensormap [%0];" ::"l"(reinterpret_cast<uint64_t>(&wmap)) : "memory");
         mbar_init(acc_full, 1);
         mbar_init(acc_empty, PRODUCER_WARPS);
         asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
@@ -153,36 +169,30 @@ cin_tc_fwd_kernel(const __grid_constant__ CinTcArgs a) {
             const int d = live ? (int)(m - b * a.D) : 0;
             const float* xrow = a.x0 + b * a.x_bs + d;
             const float* hrow = a.hid + b * a.h_bs + d;
-            for (int f = 0; f < a.F; ++f) s_x0[f * ROWS + r] = live ? __ldg(xrow + (size_t)f * a.D) : 0.f;
-            int h = 0, f = 0;
+            float* xr = s_x0 + (size_t)r * FPS;          // this thread's x0 row, zero padded to FP
+            for (int f = 0; f < a.FP; ++f) xr[f] = (live && f < a.F) ? __ldg(xrow + (size_t)f * a.D) : 0.f;
+            int h = 0, f4 = 0;
             float hv = live ? __ldg(hrow) : 0.f;
             float hv_next = (live && a.H > 1) ? __ldg(hrow + a.D) : 0.f;
             for (int kb = 0; kb < n_kb; ++kb, ++it) {
                 const uint32_t s = it % NSTAGE, ph = (it / NSTAGE) & 1u;
                 mbar_wait(empty + s, ph ^ 1u);                          // stage free (first pass: immediately)
+                if (r == 0) {   // W tile: one TMA box (32 x Np floats), lands swizzled, completes on `full`
+                    mbar_arrive_expect_tx(full + s, (uint32_t)a.Np * 128u);
+                    tma_load_2d(stage0 + (size_t)s * stage_bytes + a_bytes, &wmap, kb * KB, 0, full + s);
+                }
                 unsigned char* sa = stage0 + (size_t)s * stage_bytes + tile * (128 * 128) + row * 128;
 #pragma unroll
-                for (int c = 0; c < 8; ++c) {
-                    float4 v;
-                    float* pv = reinterpret_cast<float*>(&v);
-#pragma unroll
-                    for (int e = 0; e < 4; ++e) {
-                        pv[e] = hv * s_x0[f * ROWS + r];
-                        if (++f == a.F) {
-                            f = 0; ++h;
-                            hv = hv_next;
-                            hv_next = (live && h + 1 < a.H) ? __ldg(hrow + (size_t)(h + 1) * a.D) : 0.f;
-                            if (h >= a.H) hv = 0.f;                     // zero padding beyond K
-                        }
-                    }
+                for (int c = 0; c < 8; ++c) {         // 8 x (4 consecutive f of one h): LDS.128, 4 FMUL, STS.128
+                    const float4 x4 = *reinterpret_cast<const float4*>(xr + f4);
+                    const float4 v = make_float4(hv * x4.x, hv * x4.y, hv * x4.z, hv * x4.w);
                     *reinterpret_cast<float4*>(sa + ((c ^ (row & 7)) << 4)) = v;
-                }
-                // W tile: Np rows x 128 B, 16-byte chunks spread over the 256 producer threads
-                unsigned char* sb = stage0 + (size_t)s * stage_bytes + a_bytes;
-                for (int q = r; q < a.Np * 8; q += PRODUCER_WARPS * 32) {
-                    const int n = q >> 3, c = q & 7;
-                    const float4 w = __ldg(reinterpret_cast<const float4*>(a.wpad + (size_t)n * a.Kp + kb * KB) + c);
-                    *reinterpret_cast<float4*>(sb + n * 128 + ((c ^ (n & 7)) << 4)) = w;
+                    f4 += 4;
+                    if (f4 == a.FP) {
+                        f4 = 0; ++h;
+                        hv = h < a.H ? hv_next : 0.f;                   // zero padding beyond K
+                        hv_next = (live && h + 1 < a.H) ? __ldg(hrow + (size_t)(h + 1) * a.D) : 0.f;
+                    }
                 }
                 fence_proxy_async();                                     // generic-proxy writes -> async proxy (UMMA)
                 __syncwarp();
@@ -241,37 +251,58 @@ cin_tc_fwd_kernel(const __grid_constant__ CinTcArgs a) {
 
 }  // namespace tc
 
+typedef CUresult (*EncodeTiledFn)(CUtensorMap*, CUtensorMapDataType, cuuint32_t, void*, const cuuint64_t*, const cuuint64_t*,
+                                  const cuuint32_t*, const cuuint32_t*, CUtensorMapInterleave, CUtensorMapSwizzle,
+                                  CUtensorMapL2promotion, CUtensorMapFloatOOBfill);
+
 // One CIN layer forward on tcgen05.  wpad: workspace of Np*Kp floats.
 int cin_layer_fwd_tc(const float* x0, long long x_bs, const float* hid, long long h_bs, const float* w,
                      const float* bias, float* act, long long B, int F, int H, int D, int L, float* wpad,
                      cudaStream_t st) {
     using namespace tc;
-    const int K = H * F;
-    const int Np = (L + 15) & ~15, Kp = (K + KB - 1) / KB * KB;
+    const int FP = (F + 3) & ~3;
+    const int Np = (L + 15) & ~15, Kp = (H * FP + KB - 1) / KB * KB;
     DFM_REQUIRE(Np <= 256, DFM_ERR_UNSUPPORTED, "cin tcgen05: layer size %d > 256", L);
     long long pb = ceil_div((long long)Np * Kp, 256);
     if (pb > 4LL * sm_count()) pb = 4LL * sm_count();
-    cin_pad_w_kernel<<<(unsigned)pb, 256, 0, st>>>(w, L, K, Np, Kp, wpad);
+    cin_pad_w_kernel<<<(unsigned)pb, 256, 0, st>>>(w, L, H, F, FP, Np, Kp, wpad);
     CinTcArgs a;
     a.x0 = x0; a.x_bs = x_bs; a.hid = hid; a.h_bs = h_bs; a.wpad = wpad; a.bias = bias; a.act = act;
-    a.M = B * D; a.F = F; a.H = H; a.D = D; a.L = L; a.Np = Np; a.Kp = Kp;
+    a.M = B * D; a.F = F; a.FP = FP; a.H = H; a.D = D; a.L = L; a.Np = Np; a.Kp = Kp;
     uint32_t cols = 32;
     while (cols < (uint32_t)(2 * Np)) cols <<= 1;
     a.tmem_cols = cols;
     const int stage_bytes = (2 * 128 * 128 + Np * 128 + 1023) & ~1023;
-    const size_t smem = (size_t)NSTAGE * stage_bytes + (size_t)F * ROWS * 4 + (2 * NSTAGE + 2) * 8 + 16 + 1024;
+    const size_t smem = (size_t)NSTAGE * stage_bytes + (size_t)ROWS * (FP + 4) * 4 + (2 * NSTAGE + 2) * 8 + 16 + 1024;
     DFM_REQUIRE(smem <= 227 * 1024, DFM_ERR_UNSUPPORTED, "cin tcgen05: %d fields need %zu B shared memory", F, smem);
     DFM_CHECK_CUDA(cudaFuncSetAttribute(cin_tc_fwd_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
     long long grid = ceil_div(a.M, ROWS);
     if (grid > sm_count()) grid = sm_count();
-    cin_tc_fwd_kernel<<<(unsigned)grid, THREADS, smem, st>>>(a);
+    // tensor map of the padded weight: (Kp inner, Np outer) fp32, box 32 x Np, 128-byte swizzle
+    static EncodeTiledFn encode = nullptr;
+    if (!encode) {
+        void* fn = nullptr;
+        cudaDriverEntryPointQueryResult qres;
+        DFM_CHECK_CUDA(cudaGetDriverEntryPoint("cuTensorMapEncodeTiled", &fn, cudaEnableDefault, &qres));
+        DFM_REQUIRE(fn && qres == cudaDriverEntryPointSuccess, DFM_ERR_CUDA, "cuTensorMapEncodeTiled is not available");
+        encode = reinterpret_cast<EncodeTiledFn>(fn);
+    }
+    CUtensorMap wmap;
+    const cuuint64_t dims[2] = {(cuuint64_t)Kp, (cuuint64_t)Np};
+    const cuuint64_t strides[1] = {(cuuint64_t)Kp * 4};
+    const cuuint32_t box[2] = {(cuuint32_t)KB, (cuuint32_t)Np};
+    const cuuint32_t estr[2] = {1, 1};
+    CUresult cr = encode(&wmap, CU_TENSOR_MAP_DATA_TYPE_FLOAT32, 2, wpad, dims, strides, box, estr, CU_TENSOR_MAP_INTERLEAVE_NONE,
+                         CU_TENSOR_MAP_SWIZZLE_128B, CU_TENSOR_MAP_L2_PROMOTION_L2_256B, CU_TENSOR_MAP_FLOAT_OOB_FILL_NONE);
+    DFM_REQUIRE(cr == CUDA_SUCCESS, DFM_ERR_CUDA, "cuTensorMapEncodeTiled failed (%d)", (int)cr);
+    cin_tc_fwd_kernel<<<(unsigned)grid, THREADS, smem, st>>>(a, wmap);
     DFM_CHECK_LAUNCH();
     return DFM_OK;
 }
 
 size_t cin_tc_wpad_floats(int F, int Hmax, int Lmax) {
     const int Np = (Lmax + 15) & ~15;
-    const long long Kp = ((long long)Hmax * F + tc::KB - 1) / tc::KB * tc::KB;
+    const long long Kp = ((long long)Hmax * ((F + 3) & ~3) + tc::KB - 1) / tc::KB * tc::KB;
     return (size_t)Np * Kp;
 }
 
