@@ -20,7 +20,7 @@ namespace tc {
 
 constexpr int ROWS = 256;        // GEMM rows per CTA super-tile (2 UMMA tiles of 128)
 constexpr int KB = 32;           // k per stage: 32 tf32 = one 128-byte swizzle row
-constexpr int NSTAGE = 3;
+constexpr int NSTAGE = 4;
 constexpr int PRODUCER_WARPS = 8;
 constexpr int THREADS = (PRODUCER_WARPS + 1) * 32;
 
@@ -63,6 +63,28 @@ __device__ __forceinline__ void umma_tf32(uint32_t tmem_d, uint64_t desc_a, uint
         "tcgen05.mma.cta_group::1.kind::tf32 [%0], %1, %2, %3, p;\n\t}"
         ::"r"(tmem_d), "l"(desc_a), "l"(desc_b), "r"(idesc), "r"(accumulate) : "memory");
 }
+// D[tmem] (+)= A[tmem] * B[smem]^T : the A tile (128 lanes x 8 columns of tf32) is read from tensor memory
+__device__ __forceinline__ void umma_tf32_ts(uint32_t tmem_d, uint32_t tmem_a, uint64_t desc_b, uint32_t idesc, uint32_t accumulate) {
+    asm volatile(
+        "{\n\t.reg .pred p;\n\t"
+        "setp.ne.b32 p, %4, 0;\n\t"
+        "tcgen05.mma.cta_group::1.kind::tf32 [%0], [%1], %2, %3, p;\n\t}"
+        ::"r"(tmem_d), "r"(tmem_a), "l"(desc_b), "r"(idesc), "r"(accumulate) : "memory");
+}
+// registers -> tensor memory: 32 consecutive 32-bit columns of this thread's lane
+__device__ __forceinline__ void tmem_st32(uint32_t addr, const float* v) {
+    const uint32_t* r = reinterpret_cast<const uint32_t*>(v);
+    asm volatile(
+        "tcgen05.st.sync.aligned.32x32b.x32.b32 [%0], "
+        "{%1, %2, %3, %4, %5, %6, %7, %8, %9, %10, %11, %12, %13, %14, %15, %16, "
+        "%17, %18, %19, %20, %21, %22, %23, %24, %25, %26, %27, %28, %29, %30, %31, %32};"
+        ::"r"(addr), "r"(r[0]), "r"(r[1]), "r"(r[2]), "r"(r[3]), "r"(r[4]), "r"(r[5]), "r"(r[6]), "r"(r[7]),
+          "r"(r[8]), "r"(r[9]), "r"(r[10]), "r"(r[11]), "r"(r[12]), "r"(r[13]), "r"(r[14]), "r"(r[15]),
+          "r"(r[16]), "r"(r[17]), "r"(r[18]), "r"(r[19]), "r"(r[20]), "r"(r[21]), "r"(r[22]), "r"(r[23]),
+          "r"(r[24]), "r"(r[25]), "r"(r[26]), "r"(r[27]), "r"(r[28]), "r"(r[29]), "r"(r[30]), "r"(r[31])
+        : "memory");
+    asm volatile("tcgen05.wait::st.sync.aligned;" ::: "memory");
+}
 // K-major, 128-byte swizzle, 8-row groups 1024 B apart (cute::UMMA::SmemDescriptor, sm_100 version 1)
 __device__ __forceinline__ uint64_t make_desc(uint32_t smem_addr) {
     uint64_t d = 0;
@@ -96,6 +118,7 @@ struct CinTcArgs {
     long long M;                           // B * D rows
     int F, FP, H, D, L, Np, Kp;            // FP: F padded to a multiple of 4 (k = h*FP + f)
     uint32_t tmem_cols;
+    int nstage;                            // ring depth (<= NSTAGE)
 };
 
 // (L, H*F) -> (Np, Kp) zero padded, column k' = h*FP + f
@@ -119,17 +142,21 @@ __device__ __forceinline__ void tma_load_2d(void* dst, const CUtensorMap* map, i
         ::"r"(smem_u32(dst)), "l"(reinterpret_cast<uint64_t>(map)), "r"(x), "r"(y), "r"(smem_u32(bar)) : "memory");
 }
 
+// A_TMEM = true: the synthesised A tiles go registers -> tensor memory (tcgen05.st) and the MMA reads A from
+// TMEM, B from shared memory: shared-memory traffic per k-block drops from 144 KB to 80 KB (the SS form
+// at N = 128 is shared-memory-bandwidth bound).  Needs 2*Np + NSTAGE*64 <= 512 TMEM columns (Np <= 128).
+template <bool A_TMEM>
 __global__ void __launch_bounds__(THREADS, 1)
 cin_tc_fwd_kernel(const __grid_constant__ CinTcArgs a, const __grid_constant__ CUtensorMap wmap) {
     extern __shared__ unsigned char smem_raw[];
     // the 128-byte swizzle is a function of the absolute shared address: tiles must be 1024-B aligned
     unsigned char* smem = smem_raw + ((1024u - (smem_u32(smem_raw) & 1023u)) & 1023u);
     // carve: [stage A tiles: 2 x 16 KB][stage B tile: Np x 128 B] x NSTAGE, then x0 rows, barriers
-    const int a_bytes = 2 * 128 * 128, b_bytes = a.Np * 128;
+    const int a_bytes = A_TMEM ? 0 : 2 * 128 * 128, b_bytes = a.Np * 128;
     const int stage_bytes = (a_bytes + b_bytes + 1023) & ~1023;
     unsigned char* stage0 = smem;
     const int FPS = a.FP + 4;              // row stride (floats): 128-bit reads of 8 lanes hit 8 distinct bank groups
-    float* s_x0 = reinterpret_cast<float*>(smem + (size_t)NSTAGE * stage_bytes);          // [ROWS][FPS]
+    float* s_x0 = reinterpret_cast<float*>(smem + (size_t)a.nstage * stage_bytes);          // [ROWS][FPS]
     uint64_t* bars = reinterpret_cast<uint64_t*>(s_x0 + (size_t)ROWS * FPS);
     uint64_t* full = bars;                 // [NSTAGE] producers -> MMA
     uint64_t* empty = bars + NSTAGE;       // [NSTAGE] MMA (commit) -> producers
@@ -155,12 +182,13 @@ cin_tc_fwd_kernel(const __grid_constant__ CinTcArgs a, const __grid_constant__ C
     const long long n_super = (a.M + ROWS - 1) / ROWS;
     // instruction descriptor: D = F32, A = B = TF32, both K-major, N, M = 128
     const uint32_t idesc = (1u << 4) | (2u << 7) | (2u << 10) | ((uint32_t)(a.Np >> 3) << 17) | ((128u >> 4) << 24);
+    const uint32_t a_col0 = (uint32_t)(2 * a.Np);      // TMEM columns of the A-tile ring (A_TMEM)
 
     if (warp < PRODUCER_WARPS) {
         // ------------------------------------------------------------------ producers + epilogue
         const int r = threadIdx.x;                   // row inside the super-tile
         const int tile = r >> 7, row = r & 127;
-        uint32_t it = 0;                             // running stage counter (k-blocks produced so far)
+        uint32_t s = 0, ph = 0;                      // ring position and phase of the next k-block
         uint32_t acc_phase = 0;
         for (long long st = blockIdx.x; st < n_super; st += gridDim.x) {
             const long long m = st * ROWS + r;
@@ -170,33 +198,64 @@ cin_tc_fwd_kernel(const __grid_constant__ CinTcArgs a, const __grid_constant__ C
             const float* xrow = a.x0 + b * a.x_bs + d;
             const float* hrow = a.hid + b * a.h_bs + d;
             float* xr = s_x0 + (size_t)r * FPS;          // this thread's x0 row, zero padded to FP
-            for (int f = 0; f < a.FP; ++f) xr[f] = (live && f < a.F) ? __ldg(xrow + (size_t)f * a.D) : 0.f;
+            for (int f0 = 0; f0 < a.FP; f0 += 8) {       // 8 independent loads in flight, then 2 STS.128
+                float t[8];
+#pragma unroll
+                for (int u = 0; u < 8; ++u) t[u] = (live && f0 + u < a.F) ? __ldg(xrow + (size_t)(f0 + u) * a.D) : 0.f;
+                *reinterpret_cast<float4*>(xr + f0) = make_float4(t[0], t[1], t[2], t[3]);
+                if (f0 + 4 < a.FP) *reinterpret_cast<float4*>(xr + f0 + 4) = make_float4(t[4], t[5], t[6], t[7]);
+            }
+            // hidden values of the current and the next two h (a k-block of 32 spans at most 3: FP >= 16)
             int h = 0, f4 = 0;
-            float hv = live ? __ldg(hrow) : 0.f;
-            float hv_next = (live && a.H > 1) ? __ldg(hrow + a.D) : 0.f;
-            for (int kb = 0; kb < n_kb; ++kb, ++it) {
-                const uint32_t s = it % NSTAGE, ph = (it / NSTAGE) & 1u;
+            auto ldh = [&](int hh) { return (live && hh < a.H) ? __ldg(hrow + (size_t)hh * a.D) : 0.f; };
+            float hw0 = ldh(0), hw1 = ldh(1), hw2 = ldh(2), hw3 = ldh(3), hw4 = ldh(4);   // hw3/hw4: prefetched, not yet needed
+            for (int kb = 0; kb < n_kb; ++kb) {
                 mbar_wait(empty + s, ph ^ 1u);                          // stage free (first pass: immediately)
                 if (r == 0) {   // W tile: one TMA box (32 x Np floats), lands swizzled, completes on `full`
                     mbar_arrive_expect_tx(full + s, (uint32_t)a.Np * 128u);
                     tma_load_2d(stage0 + (size_t)s * stage_bytes + a_bytes, &wmap, kb * KB, 0, full + s);
                 }
                 unsigned char* sa = stage0 + (size_t)s * stage_bytes + tile * (128 * 128) + row * 128;
+                // 8 chunks of 4 consecutive f of one h: all 8 LDS.128 first, then 4 FMUL + STS.128 each
+                float4 x4[8];
+                int wc[8];
 #pragma unroll
-                for (int c = 0; c < 8; ++c) {         // 8 x (4 consecutive f of one h): LDS.128, 4 FMUL, STS.128
-                    const float4 x4 = *reinterpret_cast<const float4*>(xr + f4);
-                    const float4 v = make_float4(hv * x4.x, hv * x4.y, hv * x4.z, hv * x4.w);
-                    *reinterpret_cast<float4*>(sa + ((c ^ (row & 7)) << 4)) = v;
-                    f4 += 4;
-                    if (f4 == a.FP) {
-                        f4 = 0; ++h;
-                        hv = h < a.H ? hv_next : 0.f;                   // zero padding beyond K
-                        hv_next = (live && h + 1 < a.H) ? __ldg(hrow + (size_t)(h + 1) * a.D) : 0.f;
+                for (int c = 0; c < 8; ++c) {
+                    int fc = f4 + 4 * c, w = 0;
+                    if (fc >= a.FP) { fc -= a.FP; w = 1; }
+                    if (fc >= a.FP) { fc -= a.FP; w = 2; }
+                    x4[c] = *reinterpret_cast<const float4*>(xr + fc);
+                    wc[c] = w;
+                }
+                if (A_TMEM) {
+                    float z[32];
+#pragma unroll
+                    for (int c = 0; c < 8; ++c) {
+                        const float hv = wc[c] == 0 ? hw0 : (wc[c] == 1 ? hw1 : hw2);
+                        z[4 * c] = hv * x4[c].x; z[4 * c + 1] = hv * x4[c].y; z[4 * c + 2] = hv * x4[c].z; z[4 * c + 3] = hv * x4[c].w;
+                    }
+                    // lane = row inside the 128-row tile, columns = the 32 k of this stage
+                    tmem_st32(tmem_base + ((uint32_t)((warp & 3) * 32) << 16) + a_col0 + s * 64 + tile * 32, z);
+                } else {
+#pragma unroll
+                    for (int c = 0; c < 8; ++c) {
+                        const float hv = wc[c] == 0 ? hw0 : (wc[c] == 1 ? hw1 : hw2);
+                        *reinterpret_cast<float4*>(sa + ((c ^ (row & 7)) << 4)) =
+                            make_float4(hv * x4[c].x, hv * x4[c].y, hv * x4[c].z, hv * x4[c].w);
                     }
                 }
-                fence_proxy_async();                                     // generic-proxy writes -> async proxy (UMMA)
+                int fe = f4 + KB, nw = 0;
+                if (fe >= a.FP) { fe -= a.FP; nw = 1; }
+                if (fe >= a.FP) { fe -= a.FP; nw = 2; }
+                f4 = fe; h += nw;
+                // slide the window; the freshly issued loads land in slots that are not read for >= 1 k-block
+                if (nw == 1) { hw0 = hw1; hw1 = hw2; hw2 = hw3; hw3 = hw4; hw4 = ldh(h + 4); }
+                else if (nw == 2) { hw0 = hw2; hw1 = hw3; hw2 = hw4; hw3 = ldh(h + 3); hw4 = ldh(h + 4); }
+                if (A_TMEM) tc_fence_before();                           // tcgen05.st (waited) ordered before the arrive
+                else fence_proxy_async();                                // generic-proxy writes -> async proxy (UMMA)
                 __syncwarp();
                 if (lane == 0) mbar_arrive(full + s);
+                if (++s == (uint32_t)a.nstage) { s = 0; ph ^= 1u; }
             }
             // ---- epilogue: TMEM -> registers -> bias + ReLU -> act[b][l][d]
             mbar_wait(acc_full, acc_phase);
@@ -221,13 +280,12 @@ cin_tc_fwd_kernel(const __grid_constant__ CinTcArgs a, const __grid_constant__ C
         }
     } else if (lane == 0) {
         // ------------------------------------------------------------------ MMA issuer (one thread)
-        uint32_t it = 0, acc_phase = 0;
+        uint32_t s = 0, ph = 0, acc_phase = 0;
         for (long long st = blockIdx.x; st < n_super; st += gridDim.x) {
             mbar_wait(acc_empty, acc_phase ^ 1u);                       // epilogue drained the accumulators
             acc_phase ^= 1u;
             tc_fence_after();
-            for (int kb = 0; kb < n_kb; ++kb, ++it) {
-                const uint32_t s = it % NSTAGE, ph = (it / NSTAGE) & 1u;
+            for (int kb = 0; kb < n_kb; ++kb) {
                 mbar_wait(full + s, ph);
                 tc_fence_after();
                 const uint32_t sa = smem_u32(stage0 + (size_t)s * stage_bytes);
@@ -236,11 +294,17 @@ cin_tc_fwd_kernel(const __grid_constant__ CinTcArgs a, const __grid_constant__ C
                 for (int t = 0; t < 2; ++t) {
                     const uint64_t da = make_desc(sa + t * (128 * 128));
 #pragma unroll
-                    for (int k = 0; k < KB / 8; ++k)                     // K = 8 tf32 = 32 B per instruction
-                        umma_tf32(tmem_base + (uint32_t)(t * a.Np), da + (uint64_t)(k * 2), db + (uint64_t)(k * 2), idesc,
-                                  (kb | k) ? 1u : 0u);
+                    for (int k = 0; k < KB / 8; ++k) {                   // K = 8 tf32 = 32 B (8 TMEM columns) per instruction
+                        if (A_TMEM)
+                            umma_tf32_ts(tmem_base + (uint32_t)(t * a.Np), tmem_base + a_col0 + s * 64 + t * 32 + k * 8,
+                                         db + (uint64_t)(k * 2), idesc, (kb | k) ? 1u : 0u);
+                        else
+                            umma_tf32(tmem_base + (uint32_t)(t * a.Np), da + (uint64_t)(k * 2), db + (uint64_t)(k * 2), idesc,
+                                      (kb | k) ? 1u : 0u);
+                    }
                 }
                 umma_commit(empty + s);                                  // stage reusable once these MMAs retire
+                if (++s == (uint32_t)a.nstage) { s = 0; ph ^= 1u; }
             }
             umma_commit(acc_full);                                       // accumulators complete
         }
@@ -260,7 +324,7 @@ int cin_layer_fwd_tc(const float* x0, long long x_bs, const float* hid, long lon
                      const float* bias, float* act, long long B, int F, int H, int D, int L, float* wpad,
                      cudaStream_t st) {
     using namespace tc;
-    const int FP = (F + 3) & ~3;
+    const int FP = F <= 16 ? 16 : (F + 3) & ~3;     // k = h*FP + f; a 32-wide k-block then spans <= 3 values of h
     const int Np = (L + 15) & ~15, Kp = (H * FP + KB - 1) / KB * KB;
     DFM_REQUIRE(Np <= 256, DFM_ERR_UNSUPPORTED, "cin tcgen05: layer size %d > 256", L);
     long long pb = ceil_div((long long)Np * Kp, 256);
@@ -269,13 +333,19 @@ int cin_layer_fwd_tc(const float* x0, long long x_bs, const float* hid, long lon
     CinTcArgs a;
     a.x0 = x0; a.x_bs = x_bs; a.hid = hid; a.h_bs = h_bs; a.wpad = wpad; a.bias = bias; a.act = act;
     a.M = B * D; a.F = F; a.FP = FP; a.H = H; a.D = D; a.L = L; a.Np = Np; a.Kp = Kp;
+    const bool a_tmem = 2 * Np + NSTAGE * 64 <= 512;
     uint32_t cols = 32;
-    while (cols < (uint32_t)(2 * Np)) cols <<= 1;
+    while (cols < (uint32_t)(2 * Np + (a_tmem ? NSTAGE * 64 : 0))) cols <<= 1;
     a.tmem_cols = cols;
-    const int stage_bytes = (2 * 128 * 128 + Np * 128 + 1023) & ~1023;
-    const size_t smem = (size_t)NSTAGE * stage_bytes + (size_t)ROWS * (FP + 4) * 4 + (2 * NSTAGE + 2) * 8 + 16 + 1024;
+    const int stage_bytes = ((a_tmem ? 0 : 2 * 128 * 128) + Np * 128 + 1023) & ~1023;
+    const size_t fixed = (size_t)ROWS * (FP + 4) * 4 + (2 * NSTAGE + 2) * 8 + 16 + 1024;
+    int nstage = NSTAGE;
+    while (nstage > 2 && (size_t)nstage * stage_bytes + fixed > 227 * 1024) --nstage;
+    a.nstage = nstage;
+    const size_t smem = (size_t)nstage * stage_bytes + fixed;
     DFM_REQUIRE(smem <= 227 * 1024, DFM_ERR_UNSUPPORTED, "cin tcgen05: %d fields need %zu B shared memory", F, smem);
-    DFM_CHECK_CUDA(cudaFuncSetAttribute(cin_tc_fwd_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
+    DFM_CHECK_CUDA(cudaFuncSetAttribute(cin_tc_fwd_kernel<true>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
+    DFM_CHECK_CUDA(cudaFuncSetAttribute(cin_tc_fwd_kernel<false>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
     long long grid = ceil_div(a.M, ROWS);
     if (grid > sm_count()) grid = sm_count();
     // tensor map of the padded weight: (Kp inner, Np outer) fp32, box 32 x Np, 128-byte swizzle
@@ -295,14 +365,15 @@ int cin_layer_fwd_tc(const float* x0, long long x_bs, const float* hid, long lon
     CUresult cr = encode(&wmap, CU_TENSOR_MAP_DATA_TYPE_FLOAT32, 2, wpad, dims, strides, box, estr, CU_TENSOR_MAP_INTERLEAVE_NONE,
                          CU_TENSOR_MAP_SWIZZLE_128B, CU_TENSOR_MAP_L2_PROMOTION_L2_256B, CU_TENSOR_MAP_FLOAT_OOB_FILL_NONE);
     DFM_REQUIRE(cr == CUDA_SUCCESS, DFM_ERR_CUDA, "cuTensorMapEncodeTiled failed (%d)", (int)cr);
-    cin_tc_fwd_kernel<<<(unsigned)grid, THREADS, smem, st>>>(a, wmap);
+    if (a_tmem) cin_tc_fwd_kernel<true><<<(unsigned)grid, THREADS, smem, st>>>(a, wmap);
+    else cin_tc_fwd_kernel<false><<<(unsigned)grid, THREADS, smem, st>>>(a, wmap);
     DFM_CHECK_LAUNCH();
     return DFM_OK;
 }
 
 size_t cin_tc_wpad_floats(int F, int Hmax, int Lmax) {
     const int Np = (Lmax + 15) & ~15;
-    const long long Kp = ((long long)Hmax * ((F + 3) & ~3) + tc::KB - 1) / tc::KB * tc::KB;
+    const long long Kp = ((long long)Hmax * (F <= 16 ? 16 : (F + 3) & ~3) + tc::KB - 1) / tc::KB * tc::KB;
     return (size_t)Np * Kp;
 }
 
