@@ -45,7 +45,8 @@ struct BwdArgs {
     long long* tail_start;
     float* headg; float* tailg;          // per-unit open partial sums of g_fm (plain SPARSE fields)
     int* tail_field;                      // field of the segment that leaves the unit
-    int direct;                           // 1: payload = row index into g_flat (M, max_tdim); field from key
+    int direct;                           // 1: payload = row index into g_flat (M, row_stride); field from key
+    int row_stride;                       // direct mode: floats per row = max_tdim + 4 ([g, g_first, g_fm, 0, 0])
     int slot_bits;                        // payload = (b << slot_bits) | slot
     unsigned long long* counters;  // {n_valid, n_unique}
 };
@@ -265,7 +266,7 @@ __device__ __forceinline__ void process_chunk(const DevPlan& P, const DevGrads& 
     bool started_before = prev == st.cur;
     st.n_heads = started_before ? 0 : 1;
     bool ended = false;
-    const bool need_w = has_fm || cx.coef != 0.f;
+    const bool need_w = has_fm || cx.coef != 0.f || a.direct;
     for (int pb = 0; pb < cend && !ended; pb += NB) {
         uint32_t k4[NB];
         VecF<V> gA[NB], gB[HAS_FIELD ? NB : 1], sv4[NB], wv4[GENERIC ? 1 : NB];
@@ -361,7 +362,7 @@ __device__ __forceinline__ void process_chunk_fast(const DevPlan& P, const DevGr
     const int j = cx.j, gl = cx.gl, tdim = cx.tdim, c0 = cx.c0;
     const uint32_t PAD = P.pad_key;
     const bool has_fm = a.g_fm != nullptr;
-    const bool need_w = has_fm || cx.coef != 0.f;
+    const bool need_w = has_fm || cx.coef != 0.f || a.direct;
     const bool need_w1 = cx.coef != 0.f;
     const int cend = (int)((a.N - cx.p0 < CHUNK) ? a.N - cx.p0 : CHUNK);
     uint32_t prev = PAD;
@@ -485,9 +486,10 @@ segreduce_kernel(const __grid_constant__ DevPlan P, const __grid_constant__ DevG
             m.s_f[i] = (unsigned short)fd_;
             m.s_wptr[i] = fk.w2 + (size_t)(key - fk.row_base) * fk.dim;
             m.s_w1ptr[i] = fk.w1 + (key - fk.row_base);
-            m.s_goff[i] = (unsigned long long)pay * tdim;
-            m.s_b[i] = 0; m.s_m[i] = 0.f;
-            m.s_o[i] = a.g_first ? __ldg(a.g_first + pay) : 0.f;
+            m.s_goff[i] = (unsigned long long)pay * a.row_stride;
+            m.s_b[i] = 0;
+            m.s_o[i] = __ldg(a.g_flat + (size_t)pay * a.row_stride + tdim);        // packed first-order gradient
+            m.s_m[i] = __ldg(a.g_flat + (size_t)pay * a.row_stride + tdim + 1);    // packed g_fm (for -(sum g_fm) w)
         } else {
             const uint32_t b = pay >> bits;
             const int f = m.s_slotf[pay & smask];
@@ -988,6 +990,7 @@ static int embed_bwd_impl(const dfm_plan* plan, int64_t batch, long long direct_
     a.slot_bits = slot_bits_of(payS);
     a.tail_field = reinterpret_cast<int*>(ws + L.off_tfield);
     a.direct = direct ? 1 : 0;
+    a.row_stride = plan->max_tdim + 4;
     a.counters = n_valid ? reinterpret_cast<unsigned long long*>(n_valid)
                          : reinterpret_cast<unsigned long long*>(ws + L.off_counters);
     const int fill_blocks = 8 * sm_count();
@@ -1107,12 +1110,12 @@ size_t dfm_rows_bwd_workspace_bytes(const dfm_plan* plan, int64_t n_rows) {
 }
 
 int dfm_rows_bwd(const dfm_plan* plan, int64_t n_rows, const float* const* params, const uint32_t* keys,
-                 const float* g_rows, const float* g_first, float l2, const float* l2_gscale, int mode,
+                 const float* g_rows, float l2, const float* l2_gscale, int mode,
                  float* const* grads, uint32_t* sorted_keys, uint32_t* sorted_payload, float* row_grad2,
                  float* row_grad1, int64_t* n_valid, void* workspace, size_t workspace_bytes, void* stream) {
     DFM_REQUIRE(n_rows >= 0, DFM_ERR_INVALID, "dfm_rows_bwd: negative row count");
     DFM_REQUIRE(n_rows == 0 || (keys && g_rows), DFM_ERR_INVALID, "dfm_rows_bwd: null argument");
-    return embed_bwd_impl(plan, 0, n_rows, nullptr, params, g_first, nullptr, g_rows, nullptr, nullptr, nullptr, nullptr, keys,
+    return embed_bwd_impl(plan, 0, n_rows, nullptr, params, nullptr, nullptr, g_rows, nullptr, nullptr, nullptr, nullptr, keys,
                           nullptr, l2, l2_gscale, mode, grads, sorted_keys, sorted_payload, row_grad2, row_grad1, n_valid,
                           workspace, workspace_bytes, stream);
 }

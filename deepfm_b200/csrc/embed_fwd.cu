@@ -150,6 +150,8 @@ embed_fwd_kernel(const __grid_constant__ DevPlan P, long long B, int G, int smem
     float* s_x = reinterpret_cast<float*>(s_ids + S);
     float* s_raw = s_x + ND;
     const int nch_e = D / V;
+    const int rs = P.row_stride ? P.row_stride : D;      // table row stride of the plain SPARSE runs
+    const int w1s = P.w1_stride ? P.w1_stride : 1;
     const long long n_tiles = (B + gpb - 1) / gpb;
     // persistent blocks: the tables above are staged once, then the block walks sample tiles
     for (long long tile = blockIdx.x; tile < n_tiles; tile += gridDim.x) {
@@ -169,7 +171,7 @@ embed_fwd_kernel(const __grid_constant__ DevPlan P, long long B, int G, int smem
         }
         s_ids[s] = (int)id;
         if (keys && active) keys[b * S + s] = id ? e.row_base + (unsigned)id : P.pad_key;
-        if (e.sparse) fo_acc += __ldg(e.w1 + id);                      // row 0 returned as stored
+        if (e.sparse) fo_acc += __ldg(e.w1 + (size_t)id * w1s);        // row 0 returned as stored
     }
     for (int i = j; i < ND; i += G) {
         const DenseS e = t_dense[i];
@@ -202,13 +204,13 @@ embed_fwd_kernel(const __grid_constant__ DevPlan P, long long B, int G, int smem
                 VecF<V> r[4], nx[4];
                 if (run.n >= 4) {
 #pragma unroll
-                    for (int i = 0; i < 4; ++i) r[i] = vload<V>(tf[i].w2 + (size_t)ids[i] * D + j * V);
+                    for (int i = 0; i < 4; ++i) r[i] = vload<V>(tf[i].w2 + (size_t)ids[i] * rs + j * V);
                 }
                 for (; u + 4 <= run.n; u += 4) {
                     const bool more = u + 8 <= run.n;
                     if (more) {
 #pragma unroll
-                        for (int i = 0; i < 4; ++i) nx[i] = vload<V>(tf[u + 4 + i].w2 + (size_t)ids[u + 4 + i] * D + j * V);
+                        for (int i = 0; i < 4; ++i) nx[i] = vload<V>(tf[u + 4 + i].w2 + (size_t)ids[u + 4 + i] * rs + j * V);
                     }
                     if (active) {
 #pragma unroll
@@ -230,7 +232,7 @@ embed_fwd_kernel(const __grid_constant__ DevPlan P, long long B, int G, int smem
                     }
                 }
                 for (; u < run.n; ++u) {
-                    const VecF<V> r = vload<V>(tf[u].w2 + (size_t)ids[u] * D + j * V);
+                    const VecF<V> r = vload<V>(tf[u].w2 + (size_t)ids[u] * rs + j * V);
                     if (active) {
                         vstore_stream<V>(dst + u * D, r);
                         if (two_views) vstore_stream<V>(dst2 + u * D, r);
@@ -424,6 +426,7 @@ int dfm_plan::fill(DevPlan& P, const void* const* inputs, const float* const* pa
         if (kind[f] == DFM_DENSE) P.dense_field[n_dense++] = (unsigned short)f;
     }
     P.n_runs = n_runs; P.n_dense = n_dense;
+    P.row_stride = row_stride; P.w1_stride = w1_stride;
     return (vec == 4 && aligned) ? 4 : 1;
 }
 
@@ -494,6 +497,16 @@ dfm_plan* dfm_plan_create(int n_fields, const int32_t* kind, const int32_t* dim,
 }
 
 void dfm_plan_destroy(dfm_plan* plan) { delete plan; }
+
+int dfm_plan_set_table_stride(dfm_plan* plan, int row_stride, int w1_stride) {
+    DFM_REQUIRE(plan && row_stride >= 0 && w1_stride >= 0, DFM_ERR_INVALID, "dfm_plan_set_table_stride: bad argument");
+    for (int f = 0; f < plan->n_fields; ++f)
+        DFM_REQUIRE(plan->kind[f] == DFM_DENSE || (plan->kind[f] == DFM_SPARSE && plan->dim[f] == plan->fm_dim), DFM_ERR_UNSUPPORTED,
+                    "dfm_plan_set_table_stride: only plain SPARSE fields (dim == fm_dim) may use a strided row buffer");
+    DFM_REQUIRE(row_stride == 0 || row_stride >= plan->fm_dim, DFM_ERR_INVALID, "dfm_plan_set_table_stride: stride < dim");
+    plan->row_stride = row_stride; plan->w1_stride = w1_stride;
+    return DFM_OK;
+}
 
 int dfm_plan_info(const dfm_plan* plan, int64_t out[8]) {
     DFM_REQUIRE(plan && out, DFM_ERR_INVALID, "dfm_plan_info: null argument");

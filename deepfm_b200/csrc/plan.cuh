@@ -35,6 +35,7 @@ struct DevPlan {
     int n_fields, D, T, S, A, aliased, max_tdim;
     unsigned pad_key;
     int n_runs, n_dense;
+    int row_stride, w1_stride;   // floats between consecutive rows of every id table (0: dim / 1)
     FieldDev f[MAX_FIELDS];
     FieldRun runs[MAX_FIELDS];
     unsigned short slot_field[MAX_SLOTS];
@@ -56,6 +57,7 @@ struct dfm_plan {
     int T = 0, S = 0, A = 0, aliasable = 0, max_tdim = 0, key_bits = 0, vec = 1;
     long long total_rows = 0;
     int n_proj_expected = 0;
+    int row_stride = 0, w1_stride = 0;   // see dfm_plan_set_table_stride
 
     // Fill the per-call device image.  Returns the vector width usable for this call
     // (4 only if every dimension is a multiple of 4 and every pointer is 16-byte aligned).

@@ -30,7 +30,7 @@ struct ShardArgs {
 template <int V>
 __global__ void __launch_bounds__(256)
 shard_gather_kernel(const __grid_constant__ ShardArgs a, long long M, const uint32_t* __restrict__ keys, int G,
-                    float* __restrict__ vec, float* __restrict__ fo, uint32_t* __restrict__ lkeys) {
+                    float* __restrict__ vec, uint32_t* __restrict__ lkeys) {
     __shared__ ShardField t[MAX_FIELDS];
     for (int i = threadIdx.x; i < a.n; i += blockDim.x) t[i] = a.f[i];
     __syncthreads();
@@ -43,10 +43,11 @@ shard_gather_kernel(const __grid_constant__ ShardArgs a, long long M, const uint
         const ShardField& sf = t[fi];
         const uint32_t id = key - sf.gbase;
         const uint32_t lrow = id / (uint32_t)a.world;         // id mod world == rank by construction
+        // packed reply row: [row (d), first-order weight, 0, 0, 0]
         if (j < sf.dim / V)
-            vstore_stream<V>(vec + (size_t)i * a.dmax + j * V, vload<V>(sf.w2 + (size_t)lrow * sf.dim + j * V));
+            vstore_stream<V>(vec + (size_t)i * (a.dmax + 4) + j * V, vload<V>(sf.w2 + (size_t)lrow * sf.dim + j * V));
         if (j == 0) {
-            fo[i] = __ldg(sf.w1 + lrow);
+            *reinterpret_cast<float4*>(vec + (size_t)i * (a.dmax + 4) + a.dmax) = make_float4(__ldg(sf.w1 + lrow), 0.f, 0.f, 0.f);
             lkeys[i] = id ? sf.lbase + lrow : a.pad_local;    // id 0 is the padding row: no gradient
         }
     }
@@ -59,11 +60,14 @@ struct PackArgs {
     int S, T, F, D, dmax;
 };
 
-// one lane group per (slot, sample): g_vec[pos] = g_flat + g_field + g_fm (fm_sum - e);  g_fo[pos] = g_first
+// one lane group per (slot, sample): packed gradient row in send order
+//   [ g_flat + g_field + g_fm * fm_sum  (d) , g_first , g_fm , 0 , 0 ]
+// The owner folds -(sum g_fm) * w[row] in at the end of the segment (e == w[row] for every member), so the
+// field embeddings are not re-read here.
 template <int V>
 __global__ void __launch_bounds__(256)
 shard_pack_kernel(const __grid_constant__ ShardArgs a, const __grid_constant__ PackArgs p, int G,
-                  float* __restrict__ g_vec, float* __restrict__ g_fo) {
+                  float* __restrict__ g_vec) {
     const int gpb = blockDim.x / G;
     const int gl = threadIdx.x / G, j = threadIdx.x - gl * G;
     const long long n = p.B * p.S;
@@ -84,13 +88,101 @@ shard_pack_kernel(const __grid_constant__ ShardArgs a, const __grid_constant__ P
             if (p.g_fm) {
                 const float m = __ldg(p.g_fm + b);
                 const VecF<V> sv = vload<V>(p.fm_sum + (size_t)b * p.D + j * V);
-                const VecF<V> e = vload_stream<V>(p.fe + eoff);
 #pragma unroll
-                for (int v = 0; v < V; ++v) g.v[v] = fmaf(m, sv.v[v] - e.v[v], g.v[v]);
+                for (int v = 0; v < V; ++v) g.v[v] = fmaf(m, sv.v[v], g.v[v]);
             }
-            vstore_stream<V>(g_vec + (size_t)q * p.dmax + j * V, g);
+            vstore_stream<V>(g_vec + (size_t)q * (p.dmax + 4) + j * V, g);
         }
-        if (j == 0) g_fo[q] = p.g_first ? __ldg(p.g_first + b) : 0.f;
+        if (j == 0)
+            *reinterpret_cast<float4*>(g_vec + (size_t)q * (p.dmax + 4) + p.dmax) =
+                make_float4(p.g_first ? __ldg(p.g_first + b) : 0.f, p.g_fm ? __ldg(p.g_fm + b) : 0.f, 0.f, 0.f);
+    }
+}
+
+// ---- routing: stable grouping of the id slots by owner = id mod W (oracle.shard_route) --------
+// count (per-block owner histogram) -> scan (one block) -> scatter (stable inside and across blocks).
+constexpr int RT_TILE = 2048;     // id slots per block
+constexpr int RT_MAXW = 16;       // ranks
+
+struct RouteArgs {
+    const long long* ids[MAX_FIELDS];   // per id slot: the field's id column (B,)
+    unsigned gbase[MAX_FIELDS];         // per id slot: global row base
+    int S, world;
+    long long B;
+};
+
+__global__ void __launch_bounds__(256)
+route_count_kernel(const __grid_constant__ RouteArgs a, int* __restrict__ block_counts) {
+    __shared__ int hist[RT_MAXW];
+    if (threadIdx.x < RT_MAXW) hist[threadIdx.x] = 0;
+    __syncthreads();
+    const long long n = a.B * a.S, i0 = (long long)blockIdx.x * RT_TILE;
+    for (int t = threadIdx.x; t < RT_TILE; t += 256) {
+        const long long i = i0 + t;
+        if (i >= n) break;
+        const long long b = i / a.S;
+        const int s = (int)(i - b * a.S);
+        atomicAdd(&hist[(int)(__ldg(a.ids[s] + b) % a.world)], 1);
+    }
+    __syncthreads();
+    if (threadIdx.x < RT_MAXW) block_counts[blockIdx.x * RT_MAXW + threadIdx.x] = hist[threadIdx.x];
+}
+
+__global__ void route_scan_kernel(const int* __restrict__ block_counts, int nblk, int world,
+                                  long long* __restrict__ offsets, long long* __restrict__ counts) {
+    __shared__ long long total[RT_MAXW];
+    const int w = threadIdx.x;
+    if (w < world) {
+        long long run = 0;
+        for (int b = 0; b < nblk; ++b) { offsets[(size_t)w * nblk + b] = run; run += block_counts[b * RT_MAXW + w]; }
+        total[w] = run;
+        counts[w] = run;
+    }
+    __syncthreads();
+    if (w < world) {
+        long long base = 0;
+        for (int q = 0; q < w; ++q) base += total[q];
+        for (int b = 0; b < nblk; ++b) offsets[(size_t)w * nblk + b] += base;
+    }
+}
+
+__global__ void __launch_bounds__(256)
+route_scatter_kernel(const __grid_constant__ RouteArgs a, const long long* __restrict__ offsets, int nblk,
+                     uint32_t* __restrict__ send_keys, long long* __restrict__ pos_sb) {
+    __shared__ long long run[RT_MAXW];
+    __shared__ int warp_cnt[8][RT_MAXW];
+    const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
+    if (threadIdx.x < a.world) run[threadIdx.x] = offsets[(size_t)threadIdx.x * nblk + blockIdx.x];
+    const long long n = a.B * a.S, i0 = (long long)blockIdx.x * RT_TILE;
+    for (int c = 0; c < RT_TILE; c += 256) {
+        __syncthreads();
+        const long long i = i0 + c + threadIdx.x;
+        int o = -1, s = 0;
+        long long b = 0, id = 0;
+        if (i < n) {
+            b = i / a.S; s = (int)(i - b * a.S);
+            id = __ldg(a.ids[s] + b);
+            o = (int)(id % a.world);
+        }
+        int rank = 0;
+        for (int w = 0; w < a.world; ++w) {
+            const unsigned m = __ballot_sync(0xffffffffu, o == w);
+            if (o == w) rank = __popc(m & ((1u << lane) - 1u));
+            if (lane == 0) warp_cnt[warp][w] = __popc(m);
+        }
+        __syncthreads();
+        if (o >= 0) {
+            long long q = run[o] + rank;
+            for (int w2 = 0; w2 < warp; ++w2) q += warp_cnt[w2][o];
+            send_keys[q] = a.gbase[s] + (uint32_t)id;
+            pos_sb[(long long)s * a.B + b] = q;
+        }
+        __syncthreads();
+        if (threadIdx.x < a.world) {
+            int add = 0;
+            for (int w2 = 0; w2 < 8; ++w2) add += warp_cnt[w2][threadIdx.x];
+            run[threadIdx.x] += add;
+        }
     }
 }
 
@@ -105,8 +197,8 @@ static int fill_shard_args(const dfm_plan* local_plan, const int64_t* global_row
     int n = 0;
     for (int f = 0; f < local_plan->n_fields; ++f) {
         if (local_plan->kind[f] == DFM_DENSE) continue;
-        if (local_plan->kind[f] != DFM_SPARSE || local_plan->dim[f] != local_plan->fm_dim) {
-            set_error("sharded tables support SPARSE fields with embedding_dim == fm_embed_dim only (field %d)", f);
+        if (local_plan->kind[f] != DFM_SPARSE || local_plan->dim[f] != local_plan->fm_dim || local_plan->dim[f] % 4) {
+            set_error("sharded tables support SPARSE fields with embedding_dim == fm_embed_dim, a multiple of 4 (field %d)", f);
             return DFM_ERR_UNSUPPORTED;
         }
         ShardField& sf = a.f[n++];
@@ -126,12 +218,12 @@ static int fill_shard_args(const dfm_plan* local_plan, const int64_t* global_row
 extern "C" {
 
 int dfm_shard_gather(const dfm_plan* local_plan, int world, int rank, const int64_t* global_row_base,
-                     int64_t n_keys, const uint32_t* keys, const float* const* params, float* vec, float* fo,
+                     int64_t n_keys, const uint32_t* keys, const float* const* params, float* vec,
                      uint32_t* local_keys, void* stream) {
     DFM_REQUIRE(local_plan && global_row_base && params && world > 0 && rank >= 0 && rank < world, DFM_ERR_INVALID,
                 "dfm_shard_gather: bad argument");
     if (n_keys <= 0) return DFM_OK;
-    DFM_REQUIRE(keys && vec && fo && local_keys, DFM_ERR_INVALID, "dfm_shard_gather: null tensor");
+    DFM_REQUIRE(keys && vec && local_keys, DFM_ERR_INVALID, "dfm_shard_gather: null tensor");
     ShardArgs* a = new ShardArgs;
     struct Gd { ShardArgs* p; ~Gd() { delete p; } } gd{a};
     int rc = fill_shard_args(local_plan, global_row_base, params, world, rank, *a, true);
@@ -143,18 +235,18 @@ int dfm_shard_gather(const dfm_plan* local_plan, int world, int rank, const int6
     long long blocks = ceil_div(n_keys, 256 / G);
     if (blocks > 8LL * sm_count()) blocks = 8LL * sm_count();
     cudaStream_t st = static_cast<cudaStream_t>(stream);
-    if (v4) shard_gather_kernel<4><<<(unsigned)blocks, 256, 0, st>>>(*a, n_keys, keys, G, vec, fo, local_keys);
-    else shard_gather_kernel<1><<<(unsigned)blocks, 256, 0, st>>>(*a, n_keys, keys, G, vec, fo, local_keys);
+    if (v4) shard_gather_kernel<4><<<(unsigned)blocks, 256, 0, st>>>(*a, n_keys, keys, G, vec, local_keys);
+    else shard_gather_kernel<1><<<(unsigned)blocks, 256, 0, st>>>(*a, n_keys, keys, G, vec, local_keys);
     DFM_CHECK_LAUNCH();
     return DFM_OK;
 }
 
 int dfm_shard_pack_grad(const dfm_plan* plan, int64_t batch, const int64_t* positions, const float* g_first,
-                        const float* g_field, const float* g_flat, const float* g_fm, const float* field_emb,
-                        const float* fm_sum, float* g_vec, float* g_fo, void* stream) {
+                        const float* g_field, const float* g_flat, const float* g_fm, const float* fm_sum,
+                        float* g_vec, void* stream) {
     DFM_REQUIRE(plan && batch >= 0, DFM_ERR_INVALID, "dfm_shard_pack_grad: bad argument");
     if (batch == 0 || plan->S == 0) return DFM_OK;
-    DFM_REQUIRE(positions && g_vec && g_fo && (!g_fm || (field_emb && fm_sum)), DFM_ERR_INVALID, "dfm_shard_pack_grad: null tensor");
+    DFM_REQUIRE(positions && g_vec && (!g_fm || fm_sum), DFM_ERR_INVALID, "dfm_shard_pack_grad: null tensor");
     ShardArgs* a = new ShardArgs;
     struct Gd { ShardArgs* p; ~Gd() { delete p; } } gd{a};
     std::vector<int64_t> zeros(plan->n_fields + 1, 0);
@@ -162,19 +254,55 @@ int dfm_shard_pack_grad(const dfm_plan* plan, int64_t batch, const int64_t* posi
     if (rc) return rc;
     DFM_REQUIRE(a->n == plan->S, DFM_ERR_UNSUPPORTED, "dfm_shard_pack_grad: one slot per table field expected");
     PackArgs p;
-    p.g_first = g_first; p.g_field = g_field; p.g_flat = g_flat; p.g_fm = g_fm; p.fe = field_emb; p.fm_sum = fm_sum;
+    p.g_first = g_first; p.g_field = g_field; p.g_flat = g_flat; p.g_fm = g_fm; p.fe = nullptr; p.fm_sum = fm_sum;
     p.pos = reinterpret_cast<const long long*>(positions); p.B = batch; p.S = plan->S; p.T = plan->T;
     p.F = plan->n_fields; p.D = plan->fm_dim; p.dmax = plan->max_tdim;
     auto al16 = [](const void* q) { return (reinterpret_cast<uintptr_t>(q) & 15u) == 0; };
-    const bool v4 = plan->vec == 4 && al16(g_flat) && al16(g_field) && al16(field_emb) && al16(fm_sum) && al16(g_vec);
+    const bool v4 = plan->vec == 4 && al16(g_flat) && al16(g_field) && al16(fm_sum) && al16(g_vec);
     const int lanes = p.dmax / (v4 ? 4 : 1);
     DFM_REQUIRE(lanes <= 32, DFM_ERR_UNSUPPORTED, "dfm_shard_pack_grad: table dim %d too wide", p.dmax);
     const int G = next_pow2(lanes);
     long long blocks = ceil_div(batch * plan->S, 256 / G);
     if (blocks > 8LL * sm_count()) blocks = 8LL * sm_count();
     cudaStream_t st = static_cast<cudaStream_t>(stream);
-    if (v4) shard_pack_kernel<4><<<(unsigned)blocks, 256, 0, st>>>(*a, p, G, g_vec, g_fo);
-    else shard_pack_kernel<1><<<(unsigned)blocks, 256, 0, st>>>(*a, p, G, g_vec, g_fo);
+    if (v4) shard_pack_kernel<4><<<(unsigned)blocks, 256, 0, st>>>(*a, p, G, g_vec);
+    else shard_pack_kernel<1><<<(unsigned)blocks, 256, 0, st>>>(*a, p, G, g_vec);
+    DFM_CHECK_LAUNCH();
+    return DFM_OK;
+}
+
+size_t dfm_shard_route_workspace_bytes(const dfm_plan* plan, int64_t batch) {
+    if (!plan || batch < 0) return 0;
+    const long long nblk = ceil_div((long long)batch * (plan->S > 0 ? plan->S : 1), RT_TILE) + 1;
+    return (size_t)nblk * RT_MAXW * 4 + (size_t)nblk * RT_MAXW * 8 + 512;
+}
+
+int dfm_shard_route(const dfm_plan* plan, int world, const int64_t* global_row_base, int64_t batch,
+                    const void* const* inputs, uint32_t* send_keys, int64_t* positions, int64_t* counts,
+                    void* workspace, size_t workspace_bytes, void* stream) {
+    DFM_REQUIRE(plan && global_row_base && inputs && counts && world > 0 && world <= RT_MAXW && batch >= 0, DFM_ERR_INVALID,
+                "dfm_shard_route: bad argument (world must be 1..%d)", RT_MAXW);
+    cudaStream_t st = static_cast<cudaStream_t>(stream);
+    const long long n = (long long)batch * plan->S;
+    if (n == 0) { DFM_CHECK_CUDA(cudaMemsetAsync(counts, 0, (size_t)world * 8, st)); return DFM_OK; }
+    DFM_REQUIRE(send_keys && positions && workspace, DFM_ERR_INVALID, "dfm_shard_route: null tensor");
+    DFM_REQUIRE(workspace_bytes >= dfm_shard_route_workspace_bytes(plan, batch), DFM_ERR_WORKSPACE, "dfm_shard_route: workspace too small");
+    RouteArgs* a = new RouteArgs;
+    struct Gd { RouteArgs* p; ~Gd() { delete p; } } gd{a};
+    memset(a, 0, sizeof(*a));
+    a->S = plan->S; a->world = world; a->B = batch;
+    for (int s = 0; s < plan->S; ++s) {
+        const int f = plan->slot_field[s];
+        DFM_REQUIRE(plan->kind[f] == DFM_SPARSE && inputs[f], DFM_ERR_INVALID, "dfm_shard_route: field %d is not a SPARSE column", f);
+        a->ids[s] = static_cast<const long long*>(inputs[f]);
+        a->gbase[s] = (unsigned)global_row_base[f];
+    }
+    const int nblk = (int)ceil_div(n, RT_TILE);
+    int* block_counts = static_cast<int*>(workspace);
+    long long* offsets = reinterpret_cast<long long*>(static_cast<char*>(workspace) + align_up((size_t)nblk * RT_MAXW * 4, 256));
+    route_count_kernel<<<nblk, 256, 0, st>>>(*a, block_counts);
+    route_scan_kernel<<<1, 32, 0, st>>>(block_counts, nblk, world, offsets, reinterpret_cast<long long*>(counts));
+    route_scatter_kernel<<<nblk, 256, 0, st>>>(*a, offsets, nblk, send_keys, reinterpret_cast<long long*>(positions));
     DFM_CHECK_LAUNCH();
     return DFM_OK;
 }

@@ -73,10 +73,12 @@ class TorchDistComm:
         self.world = dist.get_world_size(group)
         self.rank = dist.get_rank(group)
 
-    def exchange_counts(self, counts: torch.Tensor) -> List[int]:
-        out = torch.empty_like(counts)
-        self.dist.all_to_all_single(out, counts, group=self.group)
-        return out.tolist()
+    def exchange_counts(self, counts: torch.Tensor):
+        """(send_counts, recv_counts) as host lists: ONE all-gather of the W x W count matrix, one sync."""
+        rows = [torch.empty_like(counts) for _ in range(self.world)]
+        self.dist.all_gather(rows, counts.contiguous(), group=self.group)
+        host = torch.stack(rows).tolist()
+        return host[self.rank], [host[src][self.rank] for src in range(self.world)]
 
     def all_to_all(self, send: torch.Tensor, send_counts: Sequence[int], recv_counts: Sequence[int]) -> torch.Tensor:
         out = send.new_empty((int(sum(recv_counts)),) + tuple(send.shape[1:]))
@@ -90,19 +92,17 @@ class _ShardedEmbedFn(torch.autograd.Function):
         inputs, params = tensors[:n_inputs], tensors[n_inputs:]
         comm = mod.comm
         route = mod.route(inputs)
-        send_counts = route.counts.tolist()                     # host sync: split sizes of the exchange
-        recv_counts = comm.exchange_counts(route.counts)
+        send_counts, recv_counts = comm.exchange_counts(route.counts)     # the only host sync of the step
         recv_keys = comm.all_to_all(route.send_keys, send_counts, recv_counts)
-        vec, fo, lkeys = mod.gather(recv_keys)
-        got_vec = comm.all_to_all(vec, recv_counts, send_counts)
-        got_fo = comm.all_to_all(fo, recv_counts, send_counts)
-        first, field, flat, fm, fm_sum, fin_inputs = mod.finish(inputs, route.pos_sb, got_vec, got_fo, need_bwd)
+        rows, lkeys = mod.gather(recv_keys)
+        got = comm.all_to_all(rows, recv_counts, send_counts)              # (n, D + 4): vector + first-order weight
+        first, field, flat, fm, fm_sum, fin_inputs = mod.finish(inputs, route.pos_sb, got, need_bwd)
         ctx.mod, ctx.n_inputs = mod, n_inputs
         ctx.counts = (send_counts, recv_counts)
         ctx.set_materialize_grads(False)
         ctx.l2, ctx.done = None, False
         if need_bwd:
-            ctx.save_for_backward(field, flat, fm_sum, route.pos_sb, lkeys, got_vec, got_fo, *fin_inputs, *params)
+            ctx.save_for_backward(field, flat, fm_sum, route.pos_sb, lkeys, got, *fin_inputs, *params)
             mod._live_ctx = weakref.ref(ctx)
         return first, field, flat, fm
 
@@ -110,19 +110,18 @@ class _ShardedEmbedFn(torch.autograd.Function):
     def backward(ctx, g_first, g_field, g_flat, g_fm):
         mod: ShardedFeatureEmbedding = ctx.mod
         saved = ctx.saved_tensors
-        field, flat, fm_sum, pos_sb, lkeys, got_vec, got_fo = saved[:7]
+        field, flat, fm_sum, pos_sb, lkeys, got = saved[:6]
         n_f = len(mod.field_names)
-        fin_inputs = saved[7:7 + n_f]
-        params = saved[7 + n_f:]
+        fin_inputs = saved[6:6 + n_f]
+        params = saved[6 + n_f:]
         send_counts, recv_counts = ctx.counts
         lam, gscale = ctx.l2 if ctx.l2 is not None else (0.0, None)
         ctx.done = True
         cont = lambda g: None if g is None else g.contiguous()
-        g_vec, g_fo, dense_grads = mod.pack_grads(fin_inputs, pos_sb, got_vec, got_fo, cont(g_first), cont(g_field),
-                                                  cont(g_flat), cont(g_fm), field, flat, fm_sum, params, lam, gscale)
-        g_recv = mod.comm.all_to_all(g_vec, send_counts, recv_counts)
-        g1_recv = mod.comm.all_to_all(g_fo, send_counts, recv_counts)
-        table_grads = mod.owner_backward(lkeys, g_recv, g1_recv, params, lam, gscale)
+        g_rows, dense_grads = mod.pack_grads(fin_inputs, pos_sb, got, cont(g_first), cont(g_field), cont(g_flat),
+                                             cont(g_fm), field, flat, fm_sum, params, lam, gscale)
+        g_recv = mod.comm.all_to_all(g_rows, send_counts, recv_counts)    # (M, D + 4): gradient row + scalars
+        table_grads = mod.owner_backward(lkeys, g_recv, params, lam, gscale)
         grads = [dense_grads.get(i, table_grads.get(i)) for i in range(len(params))]
         return (None, None, None) + (None,) * ctx.n_inputs + tuple(grads)
 
@@ -222,7 +221,10 @@ class ShardedFeatureEmbedding(nn.Module):
                 return C.c_void_p(p)
             cap = min(VIRTUAL_VOCAB, (2 ** 32 - 2) // max(self._S, 1))
             virt = [cap if k == _lib.SPARSE else 0 for k in self._kinds]
-            self._plans = (make(self._lvocabs), make(virt))
+            sample_plan = make(virt)
+            _lib.check(lib.dfm_plan_set_table_stride(sample_plan, self.fm_embed_dim + 4, self.fm_embed_dim + 4),
+                       "dfm_plan_set_table_stride")
+            self._plans = (make(self._lvocabs), sample_plan)
         return self._plans
 
     def __del__(self):
@@ -258,7 +260,20 @@ class ShardedFeatureEmbedding(nn.Module):
 
     # -- phases -------------------------------------------------------------------------------
     def route(self, inputs: Sequence[torch.Tensor]) -> Route:
-        ids = torch.stack([inputs[i] for i in self._sparse_idx], dim=1)
+        if inputs[self._sparse_idx[0]].is_cuda:                 # product path: the routing kernels
+            lib = _lib.lib()
+            _, sample_plan = self._ensure_plans()
+            dev = inputs[0].device
+            b, S, W = inputs[0].shape[0], self._S, self.world
+            send_keys = torch.empty((b * S,), device=dev, dtype=torch.int32)
+            pos_sb = torch.empty((S, b), device=dev, dtype=torch.int64)
+            counts = torch.empty((W,), device=dev, dtype=torch.int64)
+            ws = torch.empty((max(lib.dfm_shard_route_workspace_bytes(sample_plan, b), 16),), device=dev, dtype=torch.uint8)
+            _lib.check(lib.dfm_shard_route(sample_plan, W, _lib.i64_array(self._global_row_base), b, _lib.ptr_array(inputs),
+                                           _lib.ptr(send_keys), _lib.ptr(pos_sb), _lib.ptr(counts), ws.data_ptr(), ws.numel(),
+                                           _lib.stream_ptr()), "dfm_shard_route")
+            return Route(send_keys=send_keys, counts=counts, order=None, pos_sb=pos_sb)
+        ids = torch.stack([inputs[i] for i in self._sparse_idx], dim=1)   # CPU tensors: host-logic tests (gloo)
         if self._rb_dev is None or self._rb_dev.device != ids.device:
             self._rb_dev = torch.tensor([self._global_row_base[i] for i in self._sparse_idx], dtype=torch.int64,
                                         device=ids.device)
@@ -270,26 +285,28 @@ class ShardedFeatureEmbedding(nn.Module):
         params = self._ordered_params()
         M = recv_keys.numel()
         dev = params[0].device
-        vec = torch.empty((M, self.fm_embed_dim), device=dev, dtype=torch.float32)
-        fo = torch.empty((M,), device=dev, dtype=torch.float32)
+        rows = torch.empty((M, self.fm_embed_dim + 4), device=dev, dtype=torch.float32)
         lkeys = torch.empty((M,), device=dev, dtype=torch.int32)
         _lib.check(lib.dfm_shard_gather(local_plan, self.world, self.rank, _lib.i64_array(self._global_row_base), M,
-                                        _lib.ptr(recv_keys), self._ptrs(params), _lib.ptr(vec), _lib.ptr(fo),
-                                        _lib.ptr(lkeys), _lib.stream_ptr()), "dfm_shard_gather")
-        return vec, fo, lkeys
+                                        _lib.ptr(recv_keys), self._ptrs(params), _lib.ptr(rows), _lib.ptr(lkeys),
+                                        _lib.stream_ptr()), "dfm_shard_gather")
+        return rows, lkeys
 
-    def _virtual_ptrs(self, params, got_vec, got_fo):
-        over = {}
+    def _virtual_ptrs(self, params, got):
+        """Sample-side plan: every SPARSE table is the received row buffer (row stride D + 4, first-order
+        weight at column D)."""
+        arr = self._ptrs(params)
+        D = self.fm_embed_dim
         for i in self._sparse_idx:
-            over[5 * i + 0] = got_vec
-            over[5 * i + 2] = got_fo
-        return self._ptrs(params, over)
+            arr[5 * i + 0] = got.data_ptr()
+            arr[5 * i + 2] = got.data_ptr() + 4 * D
+        return arr
 
-    def finish(self, inputs, pos_sb, got_vec, got_fo, need_bwd: bool):
+    def finish(self, inputs, pos_sb, got, need_bwd: bool):
         lib = _lib.lib()
         _, sample_plan = self._ensure_plans()
         params = self._ordered_params()
-        dev = got_vec.device
+        dev = got.device
         b = inputs[0].shape[0]
         F, D, T = self.num_fields, self.fm_embed_dim, self._T
         fin_inputs, s = [], 0
@@ -304,12 +321,12 @@ class ShardedFeatureEmbedding(nn.Module):
         first = torch.empty((b, 1), device=dev, dtype=torch.float32)
         fm = torch.empty((b, 1), device=dev, dtype=torch.float32)
         fm_sum = torch.empty((b, D), device=dev, dtype=torch.float32) if need_bwd else None
-        _lib.check(lib.dfm_embed_fwd(sample_plan, b, _lib.ptr_array(fin_inputs), self._virtual_ptrs(params, got_vec, got_fo),
+        _lib.check(lib.dfm_embed_fwd(sample_plan, b, _lib.ptr_array(fin_inputs), self._virtual_ptrs(params, got),
                                      first.data_ptr(), field.data_ptr(), flat.data_ptr(), fm.data_ptr(),
                                      _lib.ptr(fm_sum), None, None, None, _lib.stream_ptr()), "dfm_embed_fwd")
         return first, field, flat, fm, fm_sum, fin_inputs
 
-    def pack_grads(self, fin_inputs, pos_sb, got_vec, got_fo, g_first, g_field, g_flat, g_fm, field, flat, fm_sum,
+    def pack_grads(self, fin_inputs, pos_sb, got, g_first, g_field, g_flat, g_fm, field, flat, fm_sum,
                    params, lam, gscale):
         lib = _lib.lib()
         _, sample_plan = self._ensure_plans()
@@ -317,11 +334,10 @@ class ShardedFeatureEmbedding(nn.Module):
         dev = flat.device
         b = flat.shape[0]
         n = b * self._S
-        g_vec = torch.empty((n, self.fm_embed_dim), device=dev, dtype=torch.float32)
-        g_fo = torch.empty((n,), device=dev, dtype=torch.float32)
+        g_rows = torch.empty((n, self.fm_embed_dim + 4), device=dev, dtype=torch.float32)
         _lib.check(lib.dfm_shard_pack_grad(sample_plan, b, _lib.ptr(pos_sb), _lib.ptr(g_first), _lib.ptr(g_field),
-                                           _lib.ptr(g_flat), _lib.ptr(g_fm), field.data_ptr(), _lib.ptr(fm_sum),
-                                           _lib.ptr(g_vec), _lib.ptr(g_fo), _lib.stream_ptr()), "dfm_shard_pack_grad")
+                                           _lib.ptr(g_flat), _lib.ptr(g_fm), _lib.ptr(fm_sum), _lib.ptr(g_rows),
+                                           _lib.stream_ptr()), "dfm_shard_pack_grad")
         # DENSE-field Linear gradients (data-parallel parameters): K2 with the table part skipped
         dense_grads: Dict[int, torch.Tensor] = {}
         grads = []
@@ -333,13 +349,13 @@ class ShardedFeatureEmbedding(nn.Module):
         if dense_grads:
             ws = torch.empty((max(lib.dfm_embed_bwd_workspace_bytes(sample_plan, b), 16),), device=dev, dtype=torch.uint8)
             _lib.check(lib.dfm_embed_bwd(
-                sample_plan, b, _lib.ptr_array(fin_inputs), self._virtual_ptrs(params, got_vec, got_fo),
+                sample_plan, b, _lib.ptr_array(fin_inputs), self._virtual_ptrs(params, got),
                 _lib.ptr(g_first), _lib.ptr(g_field), _lib.ptr(g_flat), _lib.ptr(g_fm), field.data_ptr(), flat.data_ptr(),
                 _lib.ptr(fm_sum), None, None, float(lam), _lib.ptr(gscale), _lib.GRAD_SKIP_TABLES, self._ptrs(grads),
                 None, None, None, None, None, ws.data_ptr(), ws.numel(), _lib.stream_ptr()), "dfm_embed_bwd")
-        return g_vec, g_fo, dense_grads
+        return g_rows, dense_grads
 
-    def owner_backward(self, lkeys, g_recv, g1_recv, params, lam, gscale):
+    def owner_backward(self, lkeys, g_recv, params, lam, gscale):
         lib = _lib.lib()
         local_plan, _ = self._ensure_plans()
         self._ordered_params()
@@ -360,7 +376,7 @@ class ShardedFeatureEmbedding(nn.Module):
         if rowsparse:
             rg2 = torch.empty((max(M, 1), self.fm_embed_dim), device=dev, dtype=torch.float32)
             rg1 = torch.empty((max(M, 1),), device=dev, dtype=torch.float32)
-        _lib.check(lib.dfm_rows_bwd(local_plan, M, self._ptrs(params), _lib.ptr(lkeys), _lib.ptr(g_recv), _lib.ptr(g1_recv),
+        _lib.check(lib.dfm_rows_bwd(local_plan, M, self._ptrs(params), _lib.ptr(lkeys), _lib.ptr(g_recv),
                                     float(lam), _lib.ptr(gscale), _lib.GRAD_ROWSPARSE if rowsparse else _lib.GRAD_DENSE,
                                     self._ptrs(grads), skeys.data_ptr(), spay.data_ptr(), _lib.ptr(rg2), _lib.ptr(rg1),
                                     counts.data_ptr(), ws.data_ptr(), ws.numel(), _lib.stream_ptr()), "dfm_rows_bwd")

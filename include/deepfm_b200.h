@@ -198,26 +198,37 @@ DFM_API int dfm_attn_bwd(const float* x, const float* g_out, int64_t batch, int 
  * Row-sharded tables over W GPUs (new; the reference is single-device).  owner(id) = id mod W,
  * local_row = id div W, per field (oracle: shard_route).  The NCCL all-to-all of keys / vectors /
  * vector gradients is issued by the host side between these calls.
+ *   Exchanged rows are d_max + 4 floats wide (16-byte aligned): one collective carries the vector and
+ *   its scalars.
+ *   dfm_shard_route : sample side.  Stable grouping of the B*S id slots by owner: send_keys (B*S)
+ *       global rows in send order, positions (S, B) send position of every slot, counts (W).
  *   dfm_shard_gather : owner side.  keys = global rows (row_base[f] + id) as received; writes the
- *       looked-up rows vec (n, d_max), first-order weights fo (n) and the local sort keys
+ *       reply rows [row (d), first-order weight, 0, 0, 0] and the local sort keys
  *       (local_row_base[f] + local_row, PAD for id 0) the owner-side backward consumes.
- *   dfm_shard_pack_grad : sample side.  positions (S, B) int64 = send position of every id slot;
- *       writes g_vec[pos] = g_flat + g_field + g_fm (fm_sum - e), g_fo[pos] = g_first.
- *   dfm_rows_bwd : owner side backward = K2 on a row list: keys (n) with one gradient row each
- *       (g_rows (n, d_max), g_first (n)); same sort / segreduce / stitch kernels and modes as
- *       dfm_embed_bwd, the field is derived from the key.
+ *   dfm_plan_set_table_stride : lets K1 (dfm_embed_fwd) read every plain SPARSE table with a row
+ *       stride != dim, i.e. straight out of the received reply rows (first-order at column d).
+ *   dfm_shard_pack_grad : sample side.  positions (S, B) as above; writes the gradient rows
+ *       [g_flat + g_field + g_fm * fm_sum (d), g_first, g_fm, 0, 0] in send order.
+ *   dfm_rows_bwd : owner side backward = K2 on a row list: keys (n) with one packed gradient row
+ *       each; same sort / segreduce / stitch kernels and modes as dfm_embed_bwd, the field is
+ *       derived from the key and -(sum g_fm) w[row] + 2 l2 w[row] is folded in at the segment end.
  * ---------------------------------------------------------------------------------------- */
+DFM_API size_t dfm_shard_route_workspace_bytes(const dfm_plan* plan, int64_t batch);
+DFM_API int dfm_shard_route(const dfm_plan* plan, int world, const int64_t* global_row_base,
+                            int64_t batch, const void* const* inputs, uint32_t* send_keys,
+                            int64_t* positions, int64_t* counts, void* workspace,
+                            size_t workspace_bytes, void* stream);
 DFM_API int dfm_shard_gather(const dfm_plan* local_plan, int world, int rank,
                              const int64_t* global_row_base, int64_t n_keys, const uint32_t* keys,
-                             const float* const* params, float* vec, float* fo, uint32_t* local_keys,
+                             const float* const* params, float* rows, uint32_t* local_keys,
                              void* stream);
 DFM_API int dfm_shard_pack_grad(const dfm_plan* plan, int64_t batch, const int64_t* positions,
                                 const float* g_first, const float* g_field, const float* g_flat,
-                                const float* g_fm, const float* field_emb, const float* fm_sum,
-                                float* g_vec, float* g_fo, void* stream);
+                                const float* g_fm, const float* fm_sum, float* g_rows, void* stream);
+DFM_API int dfm_plan_set_table_stride(dfm_plan* plan, int row_stride, int w1_stride);
 DFM_API size_t dfm_rows_bwd_workspace_bytes(const dfm_plan* plan, int64_t n_rows);
 DFM_API int dfm_rows_bwd(const dfm_plan* plan, int64_t n_rows, const float* const* params,
-                         const uint32_t* keys, const float* g_rows, const float* g_first, float l2,
+                         const uint32_t* keys, const float* g_rows, float l2,
                          const float* l2_gscale, int mode, float* const* grads, uint32_t* sorted_keys,
                          uint32_t* sorted_payload, float* row_grad2, float* row_grad1, int64_t* n_valid,
                          void* workspace, size_t workspace_bytes, void* stream);
