@@ -193,12 +193,14 @@ def run_ours(args, rank: int, local_rank: int, n_gpus: int):
             from deepfm_b200.sharded import allreduce_dense as ar
             ar(dense_params, n_gpus)
 
-    def step(batch, labels):
+    def step(batch, labels, next_batch=None):
         model.zero_grad(set_to_none=True)
         logits = model(batch).squeeze(1)
         loss = bce(logits, labels) + model.get_l2_reg_loss()
         loss.backward()
         allreduce_dense()
+        if next_batch is not None and n_gpus > 1:
+            model.embedding.prefetch(next_batch)      # input pipeline: route the next batch behind this step
         return loss
 
     def barrier():
@@ -223,13 +225,13 @@ def run_ours(args, rank: int, local_rank: int, n_gpus: int):
     dbg = (lambda m: print(f"[bench rank {rank}] {m}", file=sys.stderr, flush=True)) if os.environ.get("DFM_BENCH_DEBUG") else (lambda m: None)
     dbg("model and batches ready")
     for i in range(W_):
-        step(devb[i % n_batches], devy[i % n_batches])
+        step(devb[i % n_batches], devy[i % n_batches], devb[(i + 1) % n_batches])
         dbg(f"warmup {i} done")
     sampler = ClockSampler(local_rank)
     if rank == 0:
         sampler.start()
     model.embedding.profile_events = {}
-    total_ms = timed(lambda i: step(devb[i % n_batches], devy[i % n_batches]), K_)
+    total_ms = timed(lambda i: step(devb[(W_ + i) % n_batches], devy[(W_ + i) % n_batches], devb[(W_ + i + 1) % n_batches]), K_)
     ev = model.embedding.profile_events
     model.embedding.profile_events = None
     k1_ms = k2_ms = None

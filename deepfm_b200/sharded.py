@@ -80,6 +80,26 @@ class TorchDistComm:
         host = torch.stack(rows).tolist()
         return host[self.rank], [host[src][self.rank] for src in range(self.world)]
 
+    def exchange_counts_async(self, counts: torch.Tensor):
+        """Same exchange, but the W x W matrix is copied to pinned host memory without blocking; call
+        ``finish_counts`` later (normally the copy finished long before)."""
+        rows = [torch.empty_like(counts) for _ in range(self.world)]
+        self.dist.all_gather(rows, counts.contiguous(), group=self.group)
+        mat = torch.stack(rows)
+        host = torch.empty(mat.shape, dtype=mat.dtype, pin_memory=mat.is_cuda)
+        host.copy_(mat, non_blocking=True)
+        ev = torch.cuda.Event() if mat.is_cuda else None
+        if ev is not None:
+            ev.record()
+        return host, ev
+
+    def finish_counts(self, pending):
+        host, ev = pending
+        if ev is not None:
+            ev.synchronize()
+        mat = host.tolist()
+        return mat[self.rank], [mat[src][self.rank] for src in range(self.world)]
+
     def all_to_all(self, send: torch.Tensor, send_counts: Sequence[int], recv_counts: Sequence[int]) -> torch.Tensor:
         out = send.new_empty((int(sum(recv_counts)),) + tuple(send.shape[1:]))
         self.dist.all_to_all_single(out, send.contiguous(), list(recv_counts), list(send_counts), group=self.group)
@@ -91,8 +111,13 @@ class _ShardedEmbedFn(torch.autograd.Function):
     def forward(ctx, mod: "ShardedFeatureEmbedding", n_inputs: int, need_bwd: bool, *tensors):
         inputs, params = tensors[:n_inputs], tensors[n_inputs:]
         comm = mod.comm
-        route = mod.route(inputs)
-        send_counts, recv_counts = comm.exchange_counts(route.counts)     # the only host sync of the step
+        pref = mod._take_prefetch(inputs)
+        if pref is not None:      # routed ahead of time (prefetch): the counts are already on the host
+            route, pending = pref
+            send_counts, recv_counts = comm.finish_counts(pending)
+        else:
+            route = mod.route(inputs)
+            send_counts, recv_counts = comm.exchange_counts(route.counts)     # the only host sync of the step
         recv_keys = comm.all_to_all(route.send_keys, send_counts, recv_counts)
         rows, lkeys = mod.gather(recv_keys)
         got = comm.all_to_all(rows, recv_counts, send_counts)              # (n, D + 4): vector + first-order weight
@@ -384,6 +409,24 @@ class ShardedFeatureEmbedding(nn.Module):
             if rowsparse else None
         self.last_counts = counts
         return table_grads
+
+    # -- input pipeline hook ------------------------------------------------------------------
+    def prefetch(self, batch) -> None:
+        """Route a FUTURE batch now (routing depends on the ids only, not on the weights): the routing
+        kernels and the count exchange are enqueued behind the current step, the W x W counts travel to
+        pinned host memory asynchronously, and the forward of that batch starts without a host sync.
+        Every rank must call this at the same point of its step (it contains a collective)."""
+        inputs = self._prepare(batch)
+        route = self.route(inputs)
+        pending = self.comm.exchange_counts_async(route.counts)
+        self._prefetched = (tuple(t.data_ptr() for t in inputs), inputs, route, pending)
+
+    def _take_prefetch(self, inputs):
+        pref = getattr(self, "_prefetched", None)
+        if pref is None or pref[0] != tuple(t.data_ptr() for t in inputs):
+            return None
+        self._prefetched = None
+        return pref[2], pref[3]
 
     # -- module API ---------------------------------------------------------------------------
     def _prepare(self, batch):
