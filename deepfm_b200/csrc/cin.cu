@@ -293,6 +293,10 @@ int cin_layer_fwd_tc(const float* x0, long long x_bs, const float* hid, long lon
                      const float* bias, float* act, long long B, int F, int H, int D, int L, float* wpad,
                      cudaStream_t st);
 size_t cin_tc_wpad_floats(int F, int Hmax, int Lmax);
+size_t cin_tc_bwd_scratch_floats(long long B, int F, int D, int Hmax, int Lmax);
+int cin_layer_bwd_data_tc(const float* g_pre, const float* x0, long long x_bs, const float* hid, long long h_bs,
+                          const float* w, float* g_hid, long long gh_bs, int gh_accumulate, float* g_x0, long long B,
+                          int F, int H, int D, int L, float* scratch, cudaStream_t st);
 
 }  // namespace dfm
 
@@ -314,6 +318,7 @@ int dfm_cin_sizes(int n_fields, int dim, int n_layers, const int32_t* layer_size
     ws += 2 * align_up((size_t)batch * c.Hmax * dim * 4, 256);  // g_hidden ping-pong
     ws += align_up((size_t)dw_slices(M) * c.LKmax * 4, 256);    // dW partials
     ws += align_up((size_t)dw_slices(M) * c.Lmax * 4, 256);     // db partials
+    ws += align_up(cin_tc_bwd_scratch_floats(batch, c.F, dim, c.Hmax, c.Lmax) * 4, 256);   // tcgen05 backward scratch
     out[2] = (int64_t)ws;                                       // bytes of the backward workspace
     out[3] = c.act_per_sample;
     return DFM_OK;
@@ -392,6 +397,7 @@ int dfm_cin_bwd(const float* x0, const float* g_out, int64_t batch, int n_fields
     g_hid[1] = reinterpret_cast<float*>(take((size_t)batch * c.Hmax * D * 4));
     float* part_w = reinterpret_cast<float*>(take((size_t)n_slices * c.LKmax * 4));
     float* part_b = reinterpret_cast<float*>(take((size_t)n_slices * c.Lmax * 4));
+    float* tc_scratch = reinterpret_cast<float*>(take(cin_tc_bwd_scratch_floats(batch, c.F, D, c.Hmax, c.Lmax) * 4));
     DFM_REQUIRE(off <= workspace_bytes, DFM_ERR_WORKSPACE, "dfm_cin_bwd: workspace %zu < %zu", workspace_bytes, off);
     DFM_CHECK_CUDA(cudaMemsetAsync(g_x0, 0, (size_t)batch * F * D * 4, st));
     const float* g_hnext = nullptr;   // gradient w.r.t. the hidden input of layer i+1
@@ -428,13 +434,20 @@ int dfm_cin_bwd(const float* x0, const float* g_out, int64_t batch, int n_fields
         cin_reduce_kernel<<<(unsigned)ceil_div((long long)L * K, 256), 256, 0, st>>>(part_w, real_slices, (long long)L * K, g_weights[i]);
         cin_reduce_kernel<<<(unsigned)ceil_div(L, 256), 256, 0, st>>>(part_b, real_slices, L, g_biases[i]);
         DFM_CHECK_LAUNCH();
+        float* gh = g_hid[i & 1];
+        if (precision == 1) {   // tensor cores: gz = g_pre W stays in TMEM, contracted per row in the epilogue
+            rc = cin_layer_bwd_data_tc(g_pre, x0, (long long)F * D, hid, h_bs, weights[i], i == 0 ? g_x0 : gh,
+                                       i == 0 ? (long long)F * D : (long long)H * D, i == 0 ? 1 : 0, g_x0, batch, F, H, D, L,
+                                       tc_scratch, st);
+            if (rc == DFM_OK) { g_hnext = gh; continue; }
+            if (rc != DFM_ERR_UNSUPPORTED) return rc;       // unsupported tile shape: fp32 CUDA-core path below
+        }
         // d/d hidden  (layer 0: the hidden input is x0 itself -> accumulate into g_x0)
         OpGemmArgs a;
         a.U = g_pre; a.u_bs = (long long)L * D; a.P = L;
         a.Vt = x0; a.v_bs = (long long)F * D; a.Q = F;
         a.W = weights[i]; a.sp = K; a.sq = 1; a.sn = F; a.N = H;
         a.D = D; a.M = M; a.bias = nullptr; a.relu = 0;
-        float* gh = g_hid[i & 1];
         if (i == 0) { a.out = g_x0; a.o_bs = (long long)F * D; a.accumulate = 1; }
         else { a.out = gh; a.o_bs = (long long)H * D; a.accumulate = 0; }
         rc = launch_opgemm(a, st);

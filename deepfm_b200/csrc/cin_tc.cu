@@ -11,9 +11,7 @@
 // back to the producers through mbarriers.  The epilogue reads the accumulators with
 // `tcgen05.ld.32x32b`, adds the bias, applies ReLU and writes the (B, L, D) activation.
 // Persistent grid: one CTA per SM walks 256-row super-tiles.
-#include <cuda.h>
-
-#include "common.cuh"
+#include "tc_common.cuh"
 
 namespace dfm {
 namespace tc {
@@ -23,91 +21,6 @@ constexpr int KB = 32;           // k per stage: 32 tf32 = one 128-byte swizzle 
 constexpr int NSTAGE = 4;
 constexpr int PRODUCER_WARPS = 8;
 constexpr int THREADS = (PRODUCER_WARPS + 1) * 32;
-
-__device__ __forceinline__ uint32_t smem_u32(const void* p) { return (uint32_t)__cvta_generic_to_shared(p); }
-
-__device__ __forceinline__ void mbar_init(uint64_t* bar, int count) {
-    asm volatile("mbarrier.init.shared::cta.b64 [%0], %1;" ::"r"(smem_u32(bar)), "r"(count));
-}
-__device__ __forceinline__ void mbar_arrive(uint64_t* bar) {
-    asm volatile("{\n\t.reg .b64 st;\n\tmbarrier.arrive.shared::cta.b64 st, [%0];\n\t}" ::"r"(smem_u32(bar)) : "memory");
-}
-__device__ __forceinline__ void mbar_wait(uint64_t* bar, uint32_t parity) {
-    asm volatile(
-        "{\n\t.reg .pred p;\n\t"
-        "WAIT_%=:\n\t"
-        "mbarrier.try_wait.parity.shared::cta.b64 p, [%0], %1;\n\t"
-        "@p bra DONE_%=;\n\t"
-        "bra WAIT_%=;\n\t"
-        "DONE_%=:\n\t}" ::"r"(smem_u32(bar)), "r"(parity) : "memory");
-}
-__device__ __forceinline__ void fence_proxy_async() { asm volatile("fence.proxy.async.shared::cta;" ::: "memory"); }
-__device__ __forceinline__ void tc_fence_before() { asm volatile("tcgen05.fence::before_thread_sync;" ::: "memory"); }
-__device__ __forceinline__ void tc_fence_after() { asm volatile("tcgen05.fence::after_thread_sync;" ::: "memory"); }
-
-__device__ __forceinline__ void tmem_alloc(uint32_t* dst_smem, uint32_t cols) {
-    asm volatile("tcgen05.alloc.cta_group::1.sync.aligned.shared::cta.b32 [%0], %1;" ::"r"(smem_u32(dst_smem)), "r"(cols) : "memory");
-    asm volatile("tcgen05.relinquish_alloc_permit.cta_group::1.sync.aligned;" ::: "memory");
-}
-__device__ __forceinline__ void tmem_dealloc(uint32_t addr, uint32_t cols) {
-    asm volatile("tcgen05.dealloc.cta_group::1.sync.aligned.b32 %0, %1;" ::"r"(addr), "r"(cols) : "memory");
-}
-__device__ __forceinline__ void umma_commit(uint64_t* bar) {
-    asm volatile("tcgen05.commit.cta_group::1.mbarrier::arrive::one.shared::cluster.b64 [%0];" ::"r"(smem_u32(bar)) : "memory");
-}
-// D[tmem] (+)= A[smem] * B[smem]^T, TF32 inputs, M = 128
-__device__ __forceinline__ void umma_tf32(uint32_t tmem_d, uint64_t desc_a, uint64_t desc_b, uint32_t idesc, uint32_t accumulate) {
-    asm volatile(
-        "{\n\t.reg .pred p;\n\t"
-        "setp.ne.b32 p, %4, 0;\n\t"
-        "tcgen05.mma.cta_group::1.kind::tf32 [%0], %1, %2, %3, p;\n\t}"
-        ::"r"(tmem_d), "l"(desc_a), "l"(desc_b), "r"(idesc), "r"(accumulate) : "memory");
-}
-// D[tmem] (+)= A[tmem] * B[smem]^T : the A tile (128 lanes x 8 columns of tf32) is read from tensor memory
-__device__ __forceinline__ void umma_tf32_ts(uint32_t tmem_d, uint32_t tmem_a, uint64_t desc_b, uint32_t idesc, uint32_t accumulate) {
-    asm volatile(
-        "{\n\t.reg .pred p;\n\t"
-        "setp.ne.b32 p, %4, 0;\n\t"
-        "tcgen05.mma.cta_group::1.kind::tf32 [%0], [%1], %2, %3, p;\n\t}"
-        ::"r"(tmem_d), "r"(tmem_a), "l"(desc_b), "r"(idesc), "r"(accumulate) : "memory");
-}
-// registers -> tensor memory: 32 consecutive 32-bit columns of this thread's lane
-__device__ __forceinline__ void tmem_st32(uint32_t addr, const float* v) {
-    const uint32_t* r = reinterpret_cast<const uint32_t*>(v);
-    asm volatile(
-        "tcgen05.st.sync.aligned.32x32b.x32.b32 [%0], "
-        "{%1, %2, %3, %4, %5, %6, %7, %8, %9, %10, %11, %12, %13, %14, %15, %16, "
-        "%17, %18, %19, %20, %21, %22, %23, %24, %25, %26, %27, %28, %29, %30, %31, %32};"
-        ::"r"(addr), "r"(r[0]), "r"(r[1]), "r"(r[2]), "r"(r[3]), "r"(r[4]), "r"(r[5]), "r"(r[6]), "r"(r[7]),
-          "r"(r[8]), "r"(r[9]), "r"(r[10]), "r"(r[11]), "r"(r[12]), "r"(r[13]), "r"(r[14]), "r"(r[15]),
-          "r"(r[16]), "r"(r[17]), "r"(r[18]), "r"(r[19]), "r"(r[20]), "r"(r[21]), "r"(r[22]), "r"(r[23]),
-          "r"(r[24]), "r"(r[25]), "r"(r[26]), "r"(r[27]), "r"(r[28]), "r"(r[29]), "r"(r[30]), "r"(r[31])
-        : "memory");
-    asm volatile("tcgen05.wait::st.sync.aligned;" ::: "memory");
-}
-// K-major, 128-byte swizzle, 8-row groups 1024 B apart (cute::UMMA::SmemDescriptor, sm_100 version 1)
-__device__ __forceinline__ uint64_t make_desc(uint32_t smem_addr) {
-    uint64_t d = 0;
-    d |= (uint64_t)((smem_addr & 0x3FFFFu) >> 4);
-    d |= (uint64_t)1 << 16;                 // leading byte offset (unused for swizzled K-major)
-    d |= (uint64_t)(1024 >> 4) << 32;       // stride byte offset: 8 rows x 128 B
-    d |= (uint64_t)1 << 46;                 // descriptor version (Blackwell)
-    d |= (uint64_t)2 << 61;                 // SWIZZLE_128B
-    return d;
-}
-__device__ __forceinline__ void tmem_ld32(uint32_t addr, float* v) {
-    uint32_t* r = reinterpret_cast<uint32_t*>(v);
-    asm volatile(
-        "tcgen05.ld.sync.aligned.32x32b.x32.b32 "
-        "{%0, %1, %2, %3, %4, %5, %6, %7, %8, %9, %10, %11, %12, %13, %14, %15, "
-        "%16, %17, %18, %19, %20, %21, %22, %23, %24, %25, %26, %27, %28, %29, %30, %31}, [%32];"
-        : "=r"(r[0]), "=r"(r[1]), "=r"(r[2]), "=r"(r[3]), "=r"(r[4]), "=r"(r[5]), "=r"(r[6]), "=r"(r[7]),
-          "=r"(r[8]), "=r"(r[9]), "=r"(r[10]), "=r"(r[11]), "=r"(r[12]), "=r"(r[13]), "=r"(r[14]), "=r"(r[15]),
-          "=r"(r[16]), "=r"(r[17]), "=r"(r[18]), "=r"(r[19]), "=r"(r[20]), "=r"(r[21]), "=r"(r[22]), "=r"(r[23]),
-          "=r"(r[24]), "=r"(r[25]), "=r"(r[26]), "=r"(r[27]), "=r"(r[28]), "=r"(r[29]), "=r"(r[30]), "=r"(r[31])
-        : "r"(addr) : "memory");
-    asm volatile("tcgen05.wait::ld.sync.aligned;" ::: "memory");
-}
 
 struct CinTcArgs {
     const float* x0; long long x_bs;       // x0[b*x_bs + f*D + d]
@@ -130,16 +43,6 @@ __global__ void cin_pad_w_kernel(const float* __restrict__ w, int L, int H, int 
         const int h = k / FP, f = k - h * FP;
         out[i] = (l < L && h < H && f < F) ? __ldg(w + (size_t)l * H * F + h * F + f) : 0.f;
     }
-}
-
-__device__ __forceinline__ void mbar_arrive_expect_tx(uint64_t* bar, uint32_t bytes) {
-    asm volatile("{\n\t.reg .b64 st;\n\tmbarrier.arrive.expect_tx.shared::cta.b64 st, [%0], %1;\n\t}" ::"r"(smem_u32(bar)), "r"(bytes) : "memory");
-}
-// TMA: 2-D tile of the padded weight (box = 32 floats x Np rows, 128-byte swizzle) -> shared memory
-__device__ __forceinline__ void tma_load_2d(void* dst, const CUtensorMap* map, int x, int y, uint64_t* bar) {
-    asm volatile(
-        "cp.async.bulk.tensor.2d.shared::cluster.global.tile.mbarrier::complete_tx::bytes [%0], [%1, {%2, %3}], [%4];"
-        ::"r"(smem_u32(dst)), "l"(reinterpret_cast<uint64_t>(map)), "r"(x), "r"(y), "r"(smem_u32(bar)) : "memory");
 }
 
 // A_TMEM = true: the synthesised A tiles go registers -> tensor memory (tcgen05.st) and the MMA reads A from
@@ -315,10 +218,6 @@ cin_tc_fwd_kernel(const __grid_constant__ CinTcArgs a, const __grid_constant__ C
 
 }  // namespace tc
 
-typedef CUresult (*EncodeTiledFn)(CUtensorMap*, CUtensorMapDataType, cuuint32_t, void*, const cuuint64_t*, const cuuint64_t*,
-                                  const cuuint32_t*, const cuuint32_t*, CUtensorMapInterleave, CUtensorMapSwizzle,
-                                  CUtensorMapL2promotion, CUtensorMapFloatOOBfill);
-
 // One CIN layer forward on tcgen05.  wpad: workspace of Np*Kp floats.
 int cin_layer_fwd_tc(const float* x0, long long x_bs, const float* hid, long long h_bs, const float* w,
                      const float* bias, float* act, long long B, int F, int H, int D, int L, float* wpad,
@@ -349,22 +248,9 @@ int cin_layer_fwd_tc(const float* x0, long long x_bs, const float* hid, long lon
     long long grid = ceil_div(a.M, ROWS);
     if (grid > sm_count()) grid = sm_count();
     // tensor map of the padded weight: (Kp inner, Np outer) fp32, box 32 x Np, 128-byte swizzle
-    static EncodeTiledFn encode = nullptr;
-    if (!encode) {
-        void* fn = nullptr;
-        cudaDriverEntryPointQueryResult qres;
-        DFM_CHECK_CUDA(cudaGetDriverEntryPoint("cuTensorMapEncodeTiled", &fn, cudaEnableDefault, &qres));
-        DFM_REQUIRE(fn && qres == cudaDriverEntryPointSuccess, DFM_ERR_CUDA, "cuTensorMapEncodeTiled is not available");
-        encode = reinterpret_cast<EncodeTiledFn>(fn);
-    }
     CUtensorMap wmap;
-    const cuuint64_t dims[2] = {(cuuint64_t)Kp, (cuuint64_t)Np};
-    const cuuint64_t strides[1] = {(cuuint64_t)Kp * 4};
-    const cuuint32_t box[2] = {(cuuint32_t)KB, (cuuint32_t)Np};
-    const cuuint32_t estr[2] = {1, 1};
-    CUresult cr = encode(&wmap, CU_TENSOR_MAP_DATA_TYPE_FLOAT32, 2, wpad, dims, strides, box, estr, CU_TENSOR_MAP_INTERLEAVE_NONE,
-                         CU_TENSOR_MAP_SWIZZLE_128B, CU_TENSOR_MAP_L2_PROMOTION_L2_256B, CU_TENSOR_MAP_FLOAT_OOB_FILL_NONE);
-    DFM_REQUIRE(cr == CUDA_SUCCESS, DFM_ERR_CUDA, "cuTensorMapEncodeTiled failed (%d)", (int)cr);
+    int rc = make_tmap_2d(&wmap, wpad, Np, Kp, Np);
+    if (rc) return rc;
     if (a_tmem) cin_tc_fwd_kernel<true><<<(unsigned)grid, THREADS, smem, st>>>(a, wmap);
     else cin_tc_fwd_kernel<false><<<(unsigned)grid, THREADS, smem, st>>>(a, wmap);
     DFM_CHECK_LAUNCH();

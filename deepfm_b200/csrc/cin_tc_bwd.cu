@@ -1,0 +1,296 @@
+// CIN backward w.r.t. the layer inputs on tcgen05 (TF32 inputs, FP32 accumulate).
+//
+// With g_pre = relu'(act) * upstream (rows (b,d), columns l), the gradient of the outer-product operand is
+//     gz[(b,d)][k] = sum_l g_pre[(b,d)][l] * W[l][k],        k = h*F + f            (a plain GEMM, N = K)
+// and the two input gradients are per-row contractions of gz:
+//     g_hidden[(b,d)][h] = sum_f gz[(b,d)][h,f] * x0[(b,d)][f],   g_x0[(b,d)][f] += sum_h gz[(b,d)][h,f] * hidden[(b,d)][h]
+// gz (as large as the never-materialised outer product) stays in tensor memory: the kernel computes
+// it 128 rows x (HT*FP) columns at a time -- HT whole values of h per tile, so column c of a tile is
+// f = c % FP, h = tile*HT + c / FP at COMPILE time -- and four epilogue warps (thread = row = TMEM lane)
+// contract each tile against the row's x0 / hidden values held in registers while the next tile's
+// MMAs run into the second accumulator.  Both operands are real tensors, staged by TMA:
+//     A = g_pre^T  (B*D, Lp)  row-major (written in that layout by the g_pre kernel),
+//     B = W^T pad  (Hp*FP, Lp) row-major, row k' = h*FP + f.
+#include "tc_common.cuh"
+
+namespace dfm {
+namespace tc {
+
+constexpr int BW_NSTAGE = 3;
+constexpr int BW_THREADS = 6 * 32;     // 4 epilogue warps, 1 TMA warp, 1 MMA warp
+
+__device__ __forceinline__ void tmem_ld16(uint32_t addr, float* v) {
+    uint32_t* r = reinterpret_cast<uint32_t*>(v);
+    asm volatile(
+        "tcgen05.ld.sync.aligned.32x32b.x16.b32 {%0, %1, %2, %3, %4, %5, %6, %7, %8, %9, %10, %11, %12, %13, %14, %15}, [%16];"
+        : "=r"(r[0]), "=r"(r[1]), "=r"(r[2]), "=r"(r[3]), "=r"(r[4]), "=r"(r[5]), "=r"(r[6]), "=r"(r[7]),
+          "=r"(r[8]), "=r"(r[9]), "=r"(r[10]), "=r"(r[11]), "=r"(r[12]), "=r"(r[13]), "=r"(r[14]), "=r"(r[15])
+        : "r"(addr) : "memory");
+}
+__device__ __forceinline__ void tmem_ld8(uint32_t addr, float* v) {
+    uint32_t* r = reinterpret_cast<uint32_t*>(v);
+    asm volatile("tcgen05.ld.sync.aligned.32x32b.x8.b32 {%0, %1, %2, %3, %4, %5, %6, %7}, [%8];"
+                 : "=r"(r[0]), "=r"(r[1]), "=r"(r[2]), "=r"(r[3]), "=r"(r[4]), "=r"(r[5]), "=r"(r[6]), "=r"(r[7])
+                 : "r"(addr) : "memory");
+}
+__device__ __forceinline__ void tmem_ld_wait() { asm volatile("tcgen05.wait::ld.sync.aligned;" ::: "memory"); }
+
+// FP consecutive TMEM columns of this thread's lane -> registers (FP multiple of 8, <= 64)
+template <int FP>
+__device__ __forceinline__ void tmem_ld_row(uint32_t addr, float* v) {
+    int c = 0;
+#pragma unroll
+    for (; c + 16 <= FP; c += 16) tmem_ld16(addr + c, v + c);
+    if (FP % 16) tmem_ld8(addr + c, v + c);
+    tmem_ld_wait();
+}
+
+struct BwdDataArgs {
+    const float* x0; long long x_bs;       // x0[b*x_bs + f*D + d]
+    const float* hid; long long h_bs;      // hidden[b*h_bs + h*D + d]
+    float* g_hid; long long gh_bs;         // out[b*gh_bs + h*D + d]
+    float* g_x0;                           // (B, F, D), accumulated into
+    long long M;                           // B * D
+    int F, H, D, Lp, n_tiles;              // n_tiles = ceil(H / HT)
+    int gh_accumulate;                     // layer 0: hidden is x0 itself, g_hid is added to g_x0
+    int nstage;
+};
+
+template <int FP>
+__global__ void __launch_bounds__(BW_THREADS, 1)
+cin_tc_bwd_data_kernel(const __grid_constant__ BwdDataArgs a, const __grid_constant__ CUtensorMap amap,
+                       const __grid_constant__ CUtensorMap bmap) {
+    constexpr int HT = 256 / FP;           // values of h per N tile
+    constexpr int NT = HT * FP;            // MMA N (240 or 256)
+    extern __shared__ unsigned char smem_raw[];
+    unsigned char* smem = smem_raw + ((1024u - (smem_u32(smem_raw) & 1023u)) & 1023u);
+    const int n_kb = a.Lp / 32;
+    const int a_bytes = n_kb * 128 * 128;                       // g_pre^T rows of this M tile, all of L
+    const int b_stage = (NT * 128 + 1023) & ~1023;
+    unsigned char* sA = smem;
+    unsigned char* sB = smem + a_bytes;
+    uint64_t* bars = reinterpret_cast<uint64_t*>(sB + (size_t)a.nstage * b_stage);
+    uint64_t* a_full = bars;               // TMA -> MMA (A tile resident)
+    uint64_t* a_empty = bars + 1;          // MMA -> TMA (all MMAs of the M tile retired)
+    uint64_t* b_full = bars + 2;           // [BW_NSTAGE]
+    uint64_t* b_empty = b_full + BW_NSTAGE;
+    uint64_t* acc_full = b_empty + BW_NSTAGE;   // [2]
+    uint64_t* acc_empty = acc_full + 2;         // [2]
+    uint32_t* tmem_slot = reinterpret_cast<uint32_t*>(acc_empty + 2);
+
+    const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
+    if (threadIdx.x == 0) {
+        mbar_init(a_full, 1); mbar_init(a_empty, 1);
+        for (int s = 0; s < BW_NSTAGE; ++s) { mbar_init(b_full + s, 1); mbar_init(b_empty + s, 1); }
+        for (int s = 0; s < 2; ++s) { mbar_init(acc_full + s, 1); mbar_init(acc_empty + s, 4); }
+        asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
+        asm volatile("prefetch.tensormap [%0];" ::"l"(reinterpret_cast<uint64_t>(&amap)) : "memory");
+        asm volatile("prefetch.tensormap [%0];" ::"l"(reinterpret_cast<uint64_t>(&bmap)) : "memory");
+    }
+    if (warp == 5) tmem_alloc(tmem_slot, 512);
+    tc_fence_before();
+    __syncthreads();
+    tc_fence_after();
+    const uint32_t tmem_base = *tmem_slot;
+    const long long n_mtiles = (a.M + 127) / 128;
+    const uint32_t idesc = (1u << 4) | (2u << 7) | (2u << 10) | ((uint32_t)(NT >> 3) << 17) | ((128u >> 4) << 24);
+
+    if (warp < 4) {
+        // ------------------------------------------------------------ epilogue: thread = row = TMEM lane
+        const int r = threadIdx.x;
+        uint32_t accph[2] = {0u, 0u};
+        uint32_t jt = 0;                                       // running N-tile counter (selects the accumulator)
+        for (long long mt = blockIdx.x; mt < n_mtiles; mt += gridDim.x) {
+            const long long m = mt * 128 + r;
+            const bool live = m < a.M;
+            const long long b = live ? m / a.D : 0;
+            const int d = live ? (int)(m - b * a.D) : 0;
+            const float* xrow = a.x0 + b * a.x_bs + d;
+            const float* hrow = a.hid + b * a.h_bs + d;
+            float xr[FP], gx[FP];
+#pragma unroll
+            for (int f = 0; f < FP; ++f) { xr[f] = (live && f < a.F) ? __ldg(xrow + (size_t)f * a.D) : 0.f; gx[f] = 0.f; }
+            for (int j = 0; j < a.n_tiles; ++j, ++jt) {
+                const uint32_t ab = jt & 1u;
+                float hv[HT];
+#pragma unroll
+                for (int t = 0; t < HT; ++t) {
+                    const int h = j * HT + t;
+                    hv[t] = (live && h < a.H) ? __ldg(hrow + (size_t)h * a.D) : 0.f;
+                }
+                mbar_wait(acc_full + ab, accph[ab]);
+                accph[ab] ^= 1u;
+                tc_fence_after();
+                const uint32_t taddr = tmem_base + ((uint32_t)(warp * 32) << 16) + ab * 256u;
+#pragma unroll
+                for (int t = 0; t < HT; ++t) {
+                    float gz[FP];
+                    tmem_ld_row<FP>(taddr + t * FP, gz);
+                    float gh = 0.f;
+#pragma unroll
+                    for (int f = 0; f < FP; ++f) {
+                        gh = fmaf(gz[f], xr[f], gh);
+                        gx[f] = fmaf(gz[f], hv[t], gx[f]);
+                    }
+                    const int h = j * HT + t;
+                    if (live && h < a.H) {
+                        float* o = a.g_hid + b * a.gh_bs + (size_t)h * a.D + d;
+                        *o = a.gh_accumulate ? *o + gh : gh;
+                    }
+                }
+                tc_fence_before();
+                __syncwarp();
+                if (lane == 0) mbar_arrive(acc_empty + ab);
+            }
+            if (live) {
+                float* o = a.g_x0 + b * (long long)a.F * a.D + d;
+#pragma unroll
+                for (int f = 0; f < FP; ++f)
+                    if (f < a.F) o[(size_t)f * a.D] += gx[f];
+            }
+        }
+    } else if (warp == 4 && lane == 0) {
+        // ------------------------------------------------------------ TMA producer
+        uint32_t s = 0, ph = 0, aph = 0;
+        for (long long mt = blockIdx.x; mt < n_mtiles; mt += gridDim.x) {
+            mbar_wait(a_empty, aph ^ 1u);
+            aph ^= 1u;
+            mbar_arrive_expect_tx(a_full, (uint32_t)a_bytes);
+            for (int kb = 0; kb < n_kb; ++kb)
+                tma_load_2d(sA + (size_t)kb * 128 * 128, &amap, kb * 32, (int)(mt * 128), a_full);
+            for (int j = 0; j < a.n_tiles; ++j)
+                for (int kb = 0; kb < n_kb; ++kb) {
+                    mbar_wait(b_empty + s, ph ^ 1u);
+                    mbar_arrive_expect_tx(b_full + s, (uint32_t)NT * 128u);
+                    tma_load_2d(sB + (size_t)s * b_stage, &bmap, kb * 32, j * NT, b_full + s);
+                    if (++s == (uint32_t)a.nstage) { s = 0; ph ^= 1u; }
+                }
+        }
+    } else if (warp == 5 && lane == 0) {
+        // ------------------------------------------------------------ MMA issuer
+        uint32_t s = 0, ph = 0, aph = 0, accph[2] = {0u, 0u}, jt = 0;
+        for (long long mt = blockIdx.x; mt < n_mtiles; mt += gridDim.x) {
+            mbar_wait(a_full, aph);
+            aph ^= 1u;
+            for (int j = 0; j < a.n_tiles; ++j, ++jt) {
+                const uint32_t ab = jt & 1u;
+                mbar_wait(acc_empty + ab, accph[ab] ^ 1u);
+                accph[ab] ^= 1u;
+                tc_fence_after();
+                for (int kb = 0; kb < n_kb; ++kb) {
+                    mbar_wait(b_full + s, ph);
+                    tc_fence_after();
+                    const uint64_t da = make_desc(smem_u32(sA + (size_t)kb * 128 * 128));
+                    const uint64_t db = make_desc(smem_u32(sB + (size_t)s * b_stage));
+#pragma unroll
+                    for (int k = 0; k < 4; ++k)
+                        umma_tf32(tmem_base + ab * 256u, da + (uint64_t)(k * 2), db + (uint64_t)(k * 2), idesc, (kb | k) ? 1u : 0u);
+                    umma_commit(b_empty + s);
+                    if (++s == (uint32_t)a.nstage) { s = 0; ph ^= 1u; }
+                }
+                umma_commit(acc_full + ab);
+            }
+            umma_commit(a_empty);
+        }
+    }
+    __syncthreads();
+    if (warp == 5) tmem_dealloc(tmem_base, 512);
+}
+
+// g_pre (B, L, D) -> g_pre^T (B*D, Lp), zero padded: one block per sample, through shared memory
+__global__ void __launch_bounds__(256)
+cin_gpre_transpose_kernel(const float* __restrict__ gp, long long B, int L, int D, int Lp, float* __restrict__ gT) {
+    extern __shared__ float tile[];                      // [L][D + 1]
+    const long long b = blockIdx.x;
+    const float* src = gp + b * L * D;
+    for (int i = threadIdx.x; i < L * D; i += 256) { const int l = i / D, d = i - l * D; tile[l * (D + 1) + d] = __ldg(src + i); }
+    __syncthreads();
+    float* dst = gT + b * D * Lp;
+    for (int i = threadIdx.x; i < D * Lp; i += 256) {
+        const int d = i / Lp, l = i - d * Lp;
+        dst[i] = l < L ? tile[l * (D + 1) + d] : 0.f;
+    }
+}
+
+// W (L, H*F) -> W^T pad (Hp*FP, Lp): row k' = h*FP + f, column l
+__global__ void cin_wt_pad_kernel(const float* __restrict__ w, int L, int H, int F, int FP, int Hp, int Lp,
+                                  float* __restrict__ out) {
+    const long long n = (long long)Hp * FP * Lp;
+    for (long long i = (long long)blockIdx.x * blockDim.x + threadIdx.x; i < n; i += (long long)gridDim.x * blockDim.x) {
+        const int l = (int)(i % Lp);
+        const int k = (int)(i / Lp);
+        const int h = k / FP, f = k - h * FP;
+        out[i] = (l < L && h < H && f < F) ? __ldg(w + (size_t)l * H * F + h * F + f) : 0.f;
+    }
+}
+
+template <int FP>
+static int launch_bwd_data(const BwdDataArgs& a, const CUtensorMap& amap, const CUtensorMap& bmap, size_t smem, int grid,
+                           cudaStream_t st) {
+    DFM_CHECK_CUDA(cudaFuncSetAttribute(cin_tc_bwd_data_kernel<FP>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
+    cin_tc_bwd_data_kernel<FP><<<grid, BW_THREADS, smem, st>>>(a, amap, bmap);
+    DFM_CHECK_LAUNCH();
+    return DFM_OK;
+}
+
+}  // namespace tc
+
+int cin_tc_fp(int F) { return F <= 16 ? 16 : F <= 24 ? 24 : F <= 32 ? 32 : F <= 40 ? 40 : F <= 48 ? 48 : F <= 64 ? 64 : 0; }
+
+// scratch floats: g_pre^T (B*D*Lp) + W^T pad (Hp*FP*Lp)
+size_t cin_tc_bwd_scratch_floats(long long B, int F, int D, int Hmax, int Lmax) {
+    const int FP = cin_tc_fp(F);
+    if (!FP) return 0;
+    const int HT = 256 / FP, Lp = (Lmax + 31) & ~31, Hp = (Hmax + HT - 1) / HT * HT;
+    return (size_t)B * D * Lp + (size_t)Hp * FP * Lp + 64;
+}
+
+// d/d hidden and d/d x0 of one CIN layer on tcgen05.  Returns DFM_ERR_UNSUPPORTED if the shape is outside
+// the instantiated tiles (the caller then uses the fp32 CUDA-core path).
+int cin_layer_bwd_data_tc(const float* g_pre, const float* x0, long long x_bs, const float* hid, long long h_bs,
+                          const float* w, float* g_hid, long long gh_bs, int gh_accumulate, float* g_x0, long long B,
+                          int F, int H, int D, int L, float* scratch, cudaStream_t st) {
+    using namespace tc;
+    const int FP = cin_tc_fp(F);
+    DFM_REQUIRE(FP > 0 && L <= 256, DFM_ERR_UNSUPPORTED, "cin tcgen05 backward: F=%d / L=%d outside the instantiated tiles", F, L);
+    const int HT = 256 / FP, NT = HT * FP;
+    const int Lp = (L + 31) & ~31, Hp = (H + HT - 1) / HT * HT;
+    const long long M = B * D;
+    float* gT = scratch;
+    float* wt = scratch + (((size_t)M * Lp + 31) & ~(size_t)31);
+    const size_t tile_smem = (size_t)L * (D + 1) * 4;
+    DFM_REQUIRE(tile_smem <= 200 * 1024, DFM_ERR_UNSUPPORTED, "cin tcgen05 backward: L*D too large for the transpose tile");
+    if (tile_smem > 48 * 1024)
+        DFM_CHECK_CUDA(cudaFuncSetAttribute(cin_gpre_transpose_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)tile_smem));
+    cin_gpre_transpose_kernel<<<(unsigned)B, 256, tile_smem, st>>>(g_pre, B, L, D, Lp, gT);
+    long long pb = ceil_div((long long)Hp * FP * Lp, 256);
+    if (pb > 4LL * sm_count()) pb = 4LL * sm_count();
+    cin_wt_pad_kernel<<<(unsigned)pb, 256, 0, st>>>(w, L, H, F, FP, Hp, Lp, wt);
+    DFM_CHECK_LAUNCH();
+    CUtensorMap amap, bmap;
+    int rc = make_tmap_2d(&amap, gT, M, Lp, 128);
+    if (rc) return rc;
+    rc = make_tmap_2d(&bmap, wt, (long long)Hp * FP, Lp, NT);
+    if (rc) return rc;
+    BwdDataArgs a;
+    a.x0 = x0; a.x_bs = x_bs; a.hid = hid; a.h_bs = h_bs; a.g_hid = g_hid; a.gh_bs = gh_bs; a.g_x0 = g_x0;
+    a.M = M; a.F = F; a.H = H; a.D = D; a.Lp = Lp; a.n_tiles = Hp / HT; a.gh_accumulate = gh_accumulate;
+    const size_t a_bytes = (size_t)(Lp / 32) * 128 * 128, b_stage = ((size_t)NT * 128 + 1023) & ~(size_t)1023;
+    int nstage = BW_NSTAGE;
+    while (nstage > 1 && a_bytes + nstage * b_stage + 256 + 1024 > 227 * 1024) --nstage;
+    a.nstage = nstage;
+    const size_t smem = a_bytes + nstage * b_stage + 256 + 1024;
+    DFM_REQUIRE(smem <= 227 * 1024, DFM_ERR_UNSUPPORTED, "cin tcgen05 backward: %zu B shared memory", smem);
+    long long grid = ceil_div(M, 128);
+    if (grid > sm_count()) grid = sm_count();
+    switch (FP) {
+        case 16: return launch_bwd_data<16>(a, amap, bmap, smem, (int)grid, st);
+        case 24: return launch_bwd_data<24>(a, amap, bmap, smem, (int)grid, st);
+        case 32: return launch_bwd_data<32>(a, amap, bmap, smem, (int)grid, st);
+        case 40: return launch_bwd_data<40>(a, amap, bmap, smem, (int)grid, st);
+        case 48: return launch_bwd_data<48>(a, amap, bmap, smem, (int)grid, st);
+        default: return launch_bwd_data<64>(a, amap, bmap, smem, (int)grid, st);
+    }
+}
+
+}  // namespace dfm

@@ -156,3 +156,28 @@ def test_cin_tcgen05_tf32_vs_oracle(B, F, D, sizes, split):
     assert rel_l2(xt.grad.cpu().numpy(), gx) < 3e-2
     for i, c in enumerate(cin.conv_layers):
         assert rel_l2(c.weight.grad.cpu().numpy()[:, :, 0], gW[i]) < 3e-2, i
+
+
+@pytest.mark.parametrize("B,F,D,sizes", [(130, 16, 16, [128, 128, 64]), (70, 39, 64, [128, 128]), (33, 20, 8, [24, 16])])
+def test_cin_tcgen05_backward_matches_fp32_backward_on_same_activations(B, F, D, sizes):
+    """Isolates the tensor-core backward: ONE tf32 forward (so the ReLU masks are shared), then the same
+    graph is back-propagated twice -- tcgen05 (TF32) and CUDA-core fp32.  Only TF32 rounding differs:
+    per-tensor max-norm relative error <= 3e-3."""
+    torch.manual_seed(B)
+    cin = CIN(F, D, sizes, True).cuda()
+    cin.precision = "tf32"
+    x = (torch.randn(B, F, D, device="cuda") * 0.5).requires_grad_(True)
+    out = cin(x)
+    g = torch.randn_like(out)
+    grads = {}
+    for prec in ("tf32", "fp32"):
+        cin.precision = prec                      # read at backward time by the autograd Function
+        cin.zero_grad(set_to_none=True)
+        x.grad = None
+        out.backward(g, retain_graph=True)
+        grads[prec] = (x.grad.clone(), [c.weight.grad.clone() for c in cin.conv_layers],
+                       [c.bias.grad.clone() for c in cin.conv_layers])
+    assert_close_rel(grads["tf32"][0].cpu(), grads["fp32"][0].cpu(), 3e-3, "gx")
+    for i in range(len(sizes)):
+        assert_close_rel(grads["tf32"][1][i].cpu(), grads["fp32"][1][i].cpu(), 3e-3, f"gW{i}")
+        assert_close_rel(grads["tf32"][2][i].cpu(), grads["fp32"][2][i].cpu(), 3e-3, f"gb{i}")
