@@ -294,6 +294,9 @@ int cin_layer_fwd_tc(const float* x0, long long x_bs, const float* hid, long lon
                      cudaStream_t st);
 size_t cin_tc_wpad_floats(int F, int Hmax, int Lmax);
 size_t cin_tc_bwd_scratch_floats(long long B, int F, int D, int Hmax, int Lmax);
+size_t cin_tc_dw_scratch_floats(long long B, int F, int D, int Hmax, int Lmax);
+int cin_layer_dw_tc(const float* g_pre, const float* x0, long long x_bs, const float* hid, long long h_bs, float* gw,
+                    float* gb, long long B, int F, int H, int D, int L, float* scratch, cudaStream_t st);
 int cin_layer_bwd_data_tc(const float* g_pre, const float* x0, long long x_bs, const float* hid, long long h_bs,
                           const float* w, float* g_hid, long long gh_bs, int gh_accumulate, float* g_x0, long long B,
                           int F, int H, int D, int L, float* scratch, cudaStream_t st);
@@ -319,6 +322,7 @@ int dfm_cin_sizes(int n_fields, int dim, int n_layers, const int32_t* layer_size
     ws += align_up((size_t)dw_slices(M) * c.LKmax * 4, 256);    // dW partials
     ws += align_up((size_t)dw_slices(M) * c.Lmax * 4, 256);     // db partials
     ws += align_up(cin_tc_bwd_scratch_floats(batch, c.F, dim, c.Hmax, c.Lmax) * 4, 256);   // tcgen05 backward scratch
+    ws += align_up(cin_tc_dw_scratch_floats(batch, c.F, dim, c.Hmax, c.Lmax) * 4, 256);
     out[2] = (int64_t)ws;                                       // bytes of the backward workspace
     out[3] = c.act_per_sample;
     return DFM_OK;
@@ -398,6 +402,7 @@ int dfm_cin_bwd(const float* x0, const float* g_out, int64_t batch, int n_fields
     float* part_w = reinterpret_cast<float*>(take((size_t)n_slices * c.LKmax * 4));
     float* part_b = reinterpret_cast<float*>(take((size_t)n_slices * c.Lmax * 4));
     float* tc_scratch = reinterpret_cast<float*>(take(cin_tc_bwd_scratch_floats(batch, c.F, D, c.Hmax, c.Lmax) * 4));
+    float* dw_scratch = reinterpret_cast<float*>(take(cin_tc_dw_scratch_floats(batch, c.F, D, c.Hmax, c.Lmax) * 4));
     DFM_REQUIRE(off <= workspace_bytes, DFM_ERR_WORKSPACE, "dfm_cin_bwd: workspace %zu < %zu", workspace_bytes, off);
     DFM_CHECK_CUDA(cudaMemsetAsync(g_x0, 0, (size_t)batch * F * D * 4, st));
     const float* g_hnext = nullptr;   // gradient w.r.t. the hidden input of layer i+1
@@ -421,6 +426,13 @@ int dfm_cin_bwd(const float* x0, const float* g_out, int64_t batch, int n_fields
             h_bs = (long long)c.L[i - 1] * D;
         }
         // weight / bias gradients
+        bool dw_done = false;
+        if (precision == 1) {
+            rc = cin_layer_dw_tc(g_pre, x0, (long long)F * D, hid, h_bs, g_weights[i], g_biases[i], batch, F, H, D, L, dw_scratch, st);
+            if (rc == DFM_OK) dw_done = true;
+            else if (rc != DFM_ERR_UNSUPPORTED) return rc;
+        }
+        if (!dw_done) {
         DwArgs d;
         d.gp = g_pre; d.hid = hid; d.h_bs = h_bs; d.H = H; d.x0 = x0; d.F = F; d.L = L; d.K = K; d.D = D;
         d.M = M; d.slice_rows = ceil_div(ceil_div(M, n_slices), RC) * RC;
@@ -434,6 +446,7 @@ int dfm_cin_bwd(const float* x0, const float* g_out, int64_t batch, int n_fields
         cin_reduce_kernel<<<(unsigned)ceil_div((long long)L * K, 256), 256, 0, st>>>(part_w, real_slices, (long long)L * K, g_weights[i]);
         cin_reduce_kernel<<<(unsigned)ceil_div(L, 256), 256, 0, st>>>(part_b, real_slices, L, g_biases[i]);
         DFM_CHECK_LAUNCH();
+        }
         float* gh = g_hid[i & 1];
         if (precision == 1) {   // tensor cores: gz = g_pre W stays in TMEM, contracted per row in the epilogue
             rc = cin_layer_bwd_data_tc(g_pre, x0, (long long)F * D, hid, h_bs, weights[i], i == 0 ? g_x0 : gh,

@@ -294,3 +294,282 @@ int cin_layer_bwd_data_tc(const float* g_pre, const float* x0, long long x_bs, c
 }
 
 }  // namespace dfm
+
+// =====================================================================================================
+// Weight gradient on tcgen05, transposed form:  dW^T[k'][l] = sum_r z[r][k'] * g_pre[r][l],
+//   k' = h*FP + f (128 rows per CTA tile = UMMA M), N = Lp, reduction over the rows r = (b,d).
+// The A operand z[r][k'] = hidden[r][h] * x0[r][f] is synthesised per 32-row block: the hidden / x0
+// values of the block are staged in (padded) shared memory, 8 producer warps (row k' x half block)
+// multiply them and write the tile straight into tensor memory (tcgen05.st, TS-mode MMA); the B operand
+// g_pre as (Lp, M) row-major arrives by TMA.  One CTA = one k' tile x one slice of rows; the partial
+// dW^T of every slice is reduced in slice order afterwards (deterministic).
+namespace dfm {
+namespace tc {
+
+constexpr int DW_NSTAGE = 4;
+constexpr int DW_PRODUCERS = 256;
+constexpr int DW_THREADS = DW_PRODUCERS + 64;   // + MMA warp + TMA warp
+constexpr int SLAB = 36;                        // floats per staged channel row: 32 r + 4 pad (bank spread)
+
+__device__ __forceinline__ void tmem_st16(uint32_t addr, const float* v) {
+    const uint32_t* r = reinterpret_cast<const uint32_t*>(v);
+    asm volatile(
+        "tcgen05.st.sync.aligned.32x32b.x16.b32 [%0], {%1, %2, %3, %4, %5, %6, %7, %8, %9, %10, %11, %12, %13, %14, %15, %16};"
+        ::"r"(addr), "r"(r[0]), "r"(r[1]), "r"(r[2]), "r"(r[3]), "r"(r[4]), "r"(r[5]), "r"(r[6]), "r"(r[7]),
+          "r"(r[8]), "r"(r[9]), "r"(r[10]), "r"(r[11]), "r"(r[12]), "r"(r[13]), "r"(r[14]), "r"(r[15]) : "memory");
+    asm volatile("tcgen05.wait::st.sync.aligned;" ::: "memory");
+}
+__device__ __forceinline__ void producer_bar() { asm volatile("bar.sync 1, 256;" ::: "memory"); }
+
+struct DwTcArgs {
+    const float* x0; long long x_bs;
+    const float* hid; long long h_bs;
+    float* part;                 // (n_slices, Kt, Lp)   Kt = n_ktiles * 128
+    long long M, slice_rows;
+    int F, FP, H, D, Lp, Kt;
+};
+
+__global__ void __launch_bounds__(DW_THREADS, 1)
+cin_tc_dw_kernel(const __grid_constant__ DwTcArgs a, const __grid_constant__ CUtensorMap gmap) {
+    extern __shared__ unsigned char smem_raw[];
+    unsigned char* smem = smem_raw + ((1024u - (smem_u32(smem_raw) & 1023u)) & 1023u);
+    const int ktile = blockIdx.x, slice = blockIdx.y;
+    const int b_stage = (a.Lp * 128 + 1023) & ~1023;
+    const int h_lo = (ktile * 128) / a.FP;
+    const int h_hi = (ktile * 128 + 127) / a.FP;
+    const int nh = h_hi - h_lo + 1;
+    const int nch = nh + a.F;                               // staged channels: nh hidden rows, then F x0 rows
+    unsigned char* sB = smem;
+    float* slab = reinterpret_cast<float*>(smem + (size_t)DW_NSTAGE * b_stage);          // [2][nch][SLAB]
+    uint64_t* bars = reinterpret_cast<uint64_t*>(slab + (size_t)2 * nch * SLAB);
+    uint64_t* full = bars;                   // [DW_NSTAGE] 8 producer warps + TMA
+    uint64_t* empty = bars + DW_NSTAGE;      // [DW_NSTAGE] MMA commit
+    uint64_t* acc_full = bars + 2 * DW_NSTAGE;
+    uint32_t* tmem_slot = reinterpret_cast<uint32_t*>(acc_full + 1);
+    const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
+    if (threadIdx.x == 0) {
+        for (int s = 0; s < DW_NSTAGE; ++s) { mbar_init(full + s, 9); mbar_init(empty + s, 1); }
+        mbar_init(acc_full, 1);
+        asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
+        asm volatile("prefetch.tensormap [%0];" ::"l"(reinterpret_cast<uint64_t>(&gmap)) : "memory");
+    }
+    if (warp == 8) tmem_alloc(tmem_slot, 512);
+    tc_fence_before();
+    __syncthreads();
+    tc_fence_after();
+    const uint32_t tmem_base = *tmem_slot;
+    const uint32_t a_col0 = (uint32_t)a.Lp;                 // A ring behind the accumulator
+    const long long r_lo = (long long)slice * a.slice_rows;
+    const long long r_hi = (r_lo + a.slice_rows < a.M) ? r_lo + a.slice_rows : a.M;
+    const int n_kb = (int)((r_hi - r_lo + 31) / 32);
+    const uint32_t idesc = (1u << 4) | (2u << 7) | (2u << 10) | ((uint32_t)(a.Lp >> 3) << 17) | ((128u >> 4) << 24);
+
+    if (warp < 8) {
+        // ---------------------------------------------------------------- producers
+        const int t = threadIdx.x, row = t & 127, half = t >> 7;
+        const int kp = ktile * 128 + row;
+        const int h = kp / a.FP, f = kp - h * a.FP;
+        const bool row_ok = h < a.H && f < a.F;
+        const int hs = (h - h_lo) * SLAB + half * 16, xs = (nh + f) * SLAB + half * 16;
+        // slab staging assignment: quads of 4 consecutive r of one channel
+        const int n_quads = nch * 8;
+        auto load_quad = [&](int idx, long long r0) -> float4 {
+            const int c = idx >> 3, q = idx & 7;
+            const long long r = r0 + 4 * q;
+            if (r >= r_hi) return make_float4(0.f, 0.f, 0.f, 0.f);
+            const long long b = r / a.D;
+            const int d = (int)(r - b * a.D);
+            const float* src = c < nh ? a.hid + b * a.h_bs + (size_t)(h_lo + c) * a.D + d
+                                      : a.x0 + b * a.x_bs + (size_t)(c - nh) * a.D + d;
+            if (c < nh && h_lo + c >= a.H) return make_float4(0.f, 0.f, 0.f, 0.f);
+            return __ldg(reinterpret_cast<const float4*>(src));
+        };
+        float4 pre[3];
+#pragma unroll
+        for (int u = 0; u < 3; ++u) pre[u] = (t + u * DW_PRODUCERS < n_quads) ? load_quad(t + u * DW_PRODUCERS, r_lo) : make_float4(0, 0, 0, 0);
+        uint32_t s = 0, ph = 0;
+        for (int kb = 0; kb < n_kb; ++kb) {
+            float* sl = slab + (size_t)(kb & 1) * nch * SLAB;
+#pragma unroll
+            for (int u = 0; u < 3; ++u) {
+                const int idx = t + u * DW_PRODUCERS;
+                if (idx < n_quads) *reinterpret_cast<float4*>(sl + (idx >> 3) * SLAB + (idx & 7) * 4) = pre[u];
+            }
+            producer_bar();                                  // slab kb complete (slab kb-1 was consumed before its own bar)
+            if (kb + 1 < n_kb) {
+#pragma unroll
+                for (int u = 0; u < 3; ++u)
+                    pre[u] = (t + u * DW_PRODUCERS < n_quads) ? load_quad(t + u * DW_PRODUCERS, r_lo + (long long)(kb + 1) * 32) : make_float4(0, 0, 0, 0);
+            }
+            float z[16];
+            if (row_ok) {
+#pragma unroll
+                for (int q = 0; q < 4; ++q) {
+                    const float4 hv = *reinterpret_cast<const float4*>(sl + hs + 4 * q);
+                    const float4 xv = *reinterpret_cast<const float4*>(sl + xs + 4 * q);
+                    z[4 * q] = hv.x * xv.x; z[4 * q + 1] = hv.y * xv.y; z[4 * q + 2] = hv.z * xv.z; z[4 * q + 3] = hv.w * xv.w;
+                }
+            } else {
+#pragma unroll
+                for (int i = 0; i < 16; ++i) z[i] = 0.f;
+            }
+            mbar_wait(empty + s, ph ^ 1u);
+            tmem_st16(tmem_base + ((uint32_t)((warp & 3) * 32) << 16) + a_col0 + s * 32 + half * 16, z);
+            tc_fence_before();
+            __syncwarp();
+            if (lane == 0) mbar_arrive(full + s);
+            if (++s == DW_NSTAGE) { s = 0; ph ^= 1u; }
+        }
+        // ---------------------------------------------------------------- epilogue (warps 0-3: lane = k' row)
+        if (warp < 4) {
+            mbar_wait(acc_full, 0);
+            tc_fence_after();
+            float* out = a.part + ((size_t)slice * a.Kt + (size_t)ktile * 128 + (warp * 32 + lane)) * a.Lp;
+            for (int c0 = 0; c0 < a.Lp; c0 += 32) {
+                float v[32];
+                tmem_ld32(tmem_base + ((uint32_t)(warp * 32) << 16) + c0, v);
+#pragma unroll
+                for (int i = 0; i < 32; i += 4) *reinterpret_cast<float4*>(out + c0 + i) = make_float4(v[i], v[i + 1], v[i + 2], v[i + 3]);
+            }
+            tc_fence_before();
+        }
+    } else if (warp == 9 && lane == 0) {
+        // ---------------------------------------------------------------- TMA: g_pre (Lp, M) box 32 r x Lp rows
+        uint32_t s = 0, ph = 0;
+        for (int kb = 0; kb < n_kb; ++kb) {
+            mbar_wait(empty + s, ph ^ 1u);
+            mbar_arrive_expect_tx(full + s, (uint32_t)a.Lp * 128u);
+            tma_load_2d(sB + (size_t)s * b_stage, &gmap, (int)(r_lo + (long long)kb * 32), 0, full + s);
+            if (++s == DW_NSTAGE) { s = 0; ph ^= 1u; }
+        }
+    } else if (warp == 8 && lane == 0) {
+        // ---------------------------------------------------------------- MMA issuer
+        uint32_t s = 0, ph = 0;
+        for (int kb = 0; kb < n_kb; ++kb) {
+            mbar_wait(full + s, ph);
+            tc_fence_after();
+            const uint64_t db = make_desc(smem_u32(sB + (size_t)s * b_stage));
+#pragma unroll
+            for (int k = 0; k < 4; ++k)
+                umma_tf32_ts(tmem_base, tmem_base + a_col0 + s * 32 + k * 8, db + (uint64_t)(k * 2), idesc, (kb | k) ? 1u : 0u);
+            umma_commit(empty + s);
+            if (++s == DW_NSTAGE) { s = 0; ph ^= 1u; }
+        }
+        umma_commit(acc_full);
+    }
+    __syncthreads();
+    if (warp == 8) tmem_dealloc(tmem_base, 512);
+}
+
+// g_pre (B, L, D) -> (Lp, M) row-major (column r = b*D + d), zero padded rows l >= L
+__global__ void cin_gpre_lm_kernel(const float* __restrict__ gp, long long B, int L, int D, int Lp, long long Mld,
+                                   float* __restrict__ out) {
+    const long long n = (long long)Lp * B * D;
+    for (long long i = (long long)blockIdx.x * blockDim.x + threadIdx.x; i < n; i += (long long)gridDim.x * blockDim.x) {
+        const long long r = i % (B * D);
+        const int l = (int)(i / (B * D));
+        const long long b = r / D;
+        const int d = (int)(r - b * D);
+        out[(size_t)l * Mld + r] = l < L ? __ldg(gp + (b * L + l) * D + d) : 0.f;
+    }
+}
+
+// gW[l][h*F+f] = sum_slices part[s][h*FP+f][l]
+__global__ void cin_dw_reduce_kernel(const float* __restrict__ part, int n_slices, int Kt, int Lp, int L, int H, int F,
+                                     int FP, float* __restrict__ gw) {
+    const long long n = (long long)L * H * F;
+    const long long i = (long long)blockIdx.x * blockDim.x + threadIdx.x;
+    if (i >= n) return;
+    const int l = (int)(i / (H * F)), k = (int)(i - (long long)l * H * F);
+    const int h = k / F, f = k - h * F;
+    const size_t src = (size_t)(h * FP + f) * Lp + l;
+    float acc = 0.f;
+    for (int s = 0; s < n_slices; ++s) acc += part[(size_t)s * Kt * Lp + src];
+    gw[i] = acc;
+}
+
+// gb[l] = sum_r g_pre[b][l][d] : block partials then fixed-order final sum
+__global__ void __launch_bounds__(256)
+cin_db_partial_kernel(const float* __restrict__ gp, long long B, int L, int D, float* __restrict__ part) {
+    // block y = l, block x = slice of samples; 256 threads stride over (b, d)
+    __shared__ float red[8];
+    const int l = blockIdx.y;
+    const long long per = (B + gridDim.x - 1) / gridDim.x, b0 = (long long)blockIdx.x * per;
+    const long long b1 = b0 + per < B ? b0 + per : B;
+    float acc = 0.f;
+    for (long long i = b0 * D + threadIdx.x; i < b1 * D; i += 256) {
+        const long long b = i / D;
+        acc += __ldg(gp + (b * L + l) * D + (i - b * D));
+    }
+    for (int o = 16; o > 0; o >>= 1) acc += __shfl_xor_sync(0xffffffffu, acc, o);
+    if ((threadIdx.x & 31) == 0) red[threadIdx.x >> 5] = acc;
+    __syncthreads();
+    if (threadIdx.x == 0) { float s = 0.f; for (int w = 0; w < 8; ++w) s += red[w]; part[(size_t)blockIdx.x * L + l] = s; }
+}
+__global__ void cin_db_final_kernel(const float* __restrict__ part, int n, int L, float* __restrict__ gb) {
+    const int l = blockIdx.x * blockDim.x + threadIdx.x;
+    if (l >= L) return;
+    float acc = 0.f;
+    for (int s = 0; s < n; ++s) acc += part[(size_t)s * L + l];
+    gb[l] = acc;
+}
+
+}  // namespace tc
+
+static int dw_tc_slices(long long M, int n_ktiles) {
+    long long want = ceil_div(2LL * sm_count(), n_ktiles);
+    long long max_s = ceil_div(M, 4096);
+    if (want > max_s) want = max_s;
+    if (want < 1) want = 1;
+    return (int)want;
+}
+
+size_t cin_tc_dw_scratch_floats(long long B, int F, int D, int Hmax, int Lmax) {
+    const int FP = cin_tc_fp(F);
+    if (!FP) return 0;
+    const int Lp = (Lmax + 31) & ~31;
+    const int n_ktiles = (int)ceil_div((long long)Hmax * FP, 128);
+    const long long M = B * D;
+    const int ns = dw_tc_slices(M, n_ktiles);
+    return (size_t)Lp * M + (size_t)ns * n_ktiles * 128 * Lp + 64 * (size_t)Lmax + 256;
+}
+
+// dW and db of one CIN layer on tcgen05
+int cin_layer_dw_tc(const float* g_pre, const float* x0, long long x_bs, const float* hid, long long h_bs, float* gw,
+                    float* gb, long long B, int F, int H, int D, int L, float* scratch, cudaStream_t st) {
+    using namespace tc;
+    const int FP = cin_tc_fp(F);
+    DFM_REQUIRE(FP > 0 && L <= 256 && D % 4 == 0, DFM_ERR_UNSUPPORTED, "cin tcgen05 dW: F=%d L=%d D=%d outside the instantiated tiles", F, L, D);
+    const int Lp = (L + 31) & ~31;
+    const long long M = B * D;
+    const int n_ktiles = (int)ceil_div((long long)H * FP, 128), Kt = n_ktiles * 128;
+    const int ns = dw_tc_slices(M, n_ktiles);
+    const long long slice_rows = ceil_div(ceil_div(M, ns), 32) * 32;
+    const int real_slices = (int)ceil_div(M, slice_rows);
+    float* gLM = scratch;
+    float* part = scratch + (((size_t)Lp * M + 63) & ~(size_t)63);
+    float* dbp = part + (size_t)ns * Kt * Lp;
+    long long gb_ = ceil_div((long long)Lp * M, 256);
+    if (gb_ > 16LL * sm_count()) gb_ = 16LL * sm_count();
+    cin_gpre_lm_kernel<<<(unsigned)gb_, 256, 0, st>>>(g_pre, B, L, D, Lp, M, gLM);
+    DFM_CHECK_LAUNCH();
+    CUtensorMap gmap;
+    int rc = make_tmap_2d(&gmap, gLM, Lp, M, Lp);
+    if (rc) return rc;
+    DwTcArgs a;
+    a.x0 = x0; a.x_bs = x_bs; a.hid = hid; a.h_bs = h_bs; a.part = part; a.M = M; a.slice_rows = slice_rows;
+    a.F = F; a.FP = FP; a.H = H; a.D = D; a.Lp = Lp; a.Kt = Kt;
+    const int nh_max = 127 / FP + 2;
+    const size_t smem = (size_t)DW_NSTAGE * ((Lp * 128 + 1023) & ~1023) + (size_t)2 * (nh_max + F) * SLAB * 4 + 256 + 1024;
+    DFM_REQUIRE(smem <= 227 * 1024, DFM_ERR_UNSUPPORTED, "cin tcgen05 dW: %zu B shared memory", smem);
+    DFM_CHECK_CUDA(cudaFuncSetAttribute(cin_tc_dw_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
+    cin_tc_dw_kernel<<<dim3(n_ktiles, real_slices), DW_THREADS, smem, st>>>(a, gmap);
+    cin_dw_reduce_kernel<<<(unsigned)ceil_div((long long)L * H * F, 256), 256, 0, st>>>(part, real_slices, Kt, Lp, L, H, F, FP, gw);
+    const int dbs = 64;
+    cin_db_partial_kernel<<<dim3(dbs, L), 256, 0, st>>>(g_pre, B, L, D, dbp);
+    cin_db_final_kernel<<<(unsigned)ceil_div(L, 128), 128, 0, st>>>(dbp, dbs, L, gb);
+    DFM_CHECK_LAUNCH();
+    return DFM_OK;
+}
+
+}  // namespace dfm
