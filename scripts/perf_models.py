@@ -36,6 +36,6 @@ def run(name, B, cin_sizes=None, precision="fp32", prof=False):
         print(p.key_averages().table(sort_by="cuda_time_total", row_limit=8, max_name_column_width=60))
 
 run("deepfm", 4096); run("deepfm", 65536)
-run("xdeepfm", 4096); run("xdeepfm", 65536); run("xdeepfm", 65536, precision="tf32")
-run("xdeepfm", 65536, [128, 128, 64]); run("xdeepfm", 65536, [128, 128, 64], "tf32", prof=True)
+run("xdeepfm", 4096); run("xdeepfm", 65536, precision="tf32")
+run("xdeepfm", 65536, [128, 128, 64], "tf32", prof=True)
 run("attention_deepfm", 4096); run("attention_deepfm", 65536, prof=True)
