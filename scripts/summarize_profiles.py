@@ -45,6 +45,22 @@ with open(os.path.join(dst, f"{tag}_ncu_full_kernels.csv"), "w") as fh:
     fh.write(",".join(f"{w} [{units[i]}]" for w, i in idx) + "\n")
     for r in rows[2:]:
         fh.write(",".join('"' + r[i].replace('"', "'")[:80] + '"' if w == "Kernel Name" else r[i].replace(",", "") for w, i in idx) + "\n")
+# 3. the tcgen05 CIN kernels (forward, backward-data, dW)
+rep2 = os.path.join(src, f"prof_{tag}_cin.ncu-rep")
+if os.path.exists(rep2):
+    raw = subprocess.run(["ncu", "-i", rep2, "--page", "raw", "--csv"], capture_output=True, text=True).stdout
+    rows = list(csv.reader(raw.splitlines()))
+    hdr, units = rows[0], rows[1]
+    want2 = want + ["sm__pipe_tensor_cycles_active.avg.pct_of_peak_sustained_elapsed",
+                    "sm__pipe_tensor_subpipe_hmma_cycles_active.avg.pct_of_peak_sustained_active",
+                    "smsp__inst_executed_pipe_tmem.sum", "l1tex__data_bank_conflicts_pipe_lsu_mem_shared.sum"]
+    idx = [(w, hdr.index(w)) for w in want2 if w in hdr]
+    with open(os.path.join(dst, f"{tag}_ncu_full_cin_tcgen05.csv"), "w") as fh:
+        fh.write("# ncu --set full --clock-control none --import-source on -k regex:cin_tc : python scripts/ncu_cin.py 8192 (F=39, D=64, CIN [128,128], TF32)\n")
+        fh.write(",".join(f"{w} [{units[i]}]" for w, i in idx) + "\n")
+        for r in rows[2:]:
+            fh.write(",".join('"' + r[i].replace('"', "'")[:70] + '"' if w == "Kernel Name" else r[i].replace(",", "") for w, i in idx) + "\n")
+    print(open(os.path.join(dst, f"{tag}_ncu_full_cin_tcgen05.csv")).read())
 for name in (f"bench_{tag}.json",):
     if os.path.exists(os.path.join(src, name)):
         shutil.copy(os.path.join(src, name), os.path.join(dst, name))
