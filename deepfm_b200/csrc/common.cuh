@@ -71,6 +71,14 @@ __device__ __forceinline__ VecF<1> vload<1>(const float* p) {
     return r;
 }
 
+template <>
+__device__ __forceinline__ VecF<2> vload<2>(const float* p) {
+    float2 t = __ldg(reinterpret_cast<const float2*>(p));
+    VecF<2> r;
+    r.v[0] = t.x; r.v[1] = t.y;
+    return r;
+}
+
 template <int V>
 __device__ __forceinline__ VecF<V> vload_stream(const float* p);  // touched once: evict-first
 template <>
@@ -96,6 +104,10 @@ __device__ __forceinline__ void vstore<4>(float* p, const VecF<4>& x) {
 template <>
 __device__ __forceinline__ void vstore<1>(float* p, const VecF<1>& x) {
     *p = x.v[0];
+}
+template <>
+__device__ __forceinline__ void vstore<2>(float* p, const VecF<2>& x) {
+    *reinterpret_cast<float2*>(p) = make_float2(x.v[0], x.v[1]);
 }
 
 template <int V>

@@ -3,11 +3,15 @@
 // base.py:78-83; ATen embedding_dense_backward / _embedding_bag_dense_backward / mm).
 //
 //   sort      stable LSB radix sort of (key = global row, payload = b*S + slot), PAD keys last
-//   segreduce one lane group per chunk of CHUNK sorted positions; the upstream gradient of a slot
+//   segreduce one lane group per chunk of sorted positions; the upstream gradient of a slot
 //             g_raw = g_flat + P^T (g_field + g_fm (fm_sum - e)) is rebuilt on the fly, so the
 //             FM gradient never exists in HBM; segments inside a chunk are written directly
-//             (+ 2*l2*w[row]); the open head/tail partial sums go to a side buffer
-//   stitch    one lane group per segment that spans chunks adds the partials in chunk order
+//             (+ 2*l2*w[row]); the open head/tail partial sums go to a side buffer.
+//             Two kernels: segreduce_staged_kernel (plain SPARSE tables, no g_field: every gradient /
+//             fm_sum / table row of a unit is staged in shared memory with cp.async, so the random
+//             256-byte row reads are all in flight at once) and segreduce_kernel (everything else).
+//   stitch    one block per segment that spans units: lane groups add the units' partials in a fixed
+//             strided order, then one group folds them (owners are listed by segreduce)
 //   pgrads    DENSE-field Linear and projection gradients: per-slice partial sums in shared
 //             memory, then a fixed-order reduction over slices (+ 2*l2*p)
 // No float atomics anywhere: every output element has exactly one writer and a fixed summation
@@ -49,6 +53,10 @@ struct BwdArgs {
     int row_stride;                       // direct mode: floats per row = max_tdim + 4 ([g, g_first, g_fm, 0, 0])
     int slot_bits;                        // payload = (b << slot_bits) | slot
     unsigned long long* counters;  // {n_valid, n_unique}
+    unsigned* open_count;          // number of units that own a segment leaving the unit
+    unsigned* open_list;           // those units (order irrelevant: one writer per segment)
+    unsigned* long_count;          // segments spanning more than LONG_SPAN units: (owner unit, last unit) pairs
+    unsigned* long_list;
 };
 
 // payload of key position i = b*S + slot:  (b << bits) | slot   (decoded with a shift and a mask)
@@ -567,7 +575,10 @@ segreduce_kernel(const __grid_constant__ DevPlan P, const __grid_constant__ DevG
             if (j == 0) {
                 (is_tail ? a.tail1 : a.head1)[blockIdx.x] = acc1;
                 (is_tail ? a.tailg : a.headg)[blockIdx.x] = gs;
-                if (is_tail) { a.tail_start[blockIdx.x] = seg_start; a.tail_field[blockIdx.x] = f; }
+                if (is_tail) {
+                    a.tail_start[blockIdx.x] = seg_start; a.tail_field[blockIdx.x] = f;
+                    a.open_list[atomicAdd(a.open_count, 1u)] = blockIdx.x;
+                }
             }
         }
     }
@@ -581,9 +592,271 @@ segreduce_kernel(const __grid_constant__ DevPlan P, const __grid_constant__ DevG
         atomicAdd(a.counters + threadIdx.x, (unsigned long long)s_cnt[threadIdx.x]);
 }
 
-// One lane group per unit (= the positions one segreduce block covered); only the unit in which a
-// multi-unit segment STARTS does work: the lanes first find where the segment ends (one unit per
-// lane), then the later units' head partials are added in unit order.
+// ---- staged fast path ------------------------------------------------------------------------
+// One WARP walks a contiguous range of R sorted positions front to back: lane l owns dims [l*VL, (l+1)*VL) of
+// the row (VL = tdim / 32), the running segment sum lives in registers and is carried from position to
+// position, so there is no stitching inside a range at all -- only the first / last segment of a range can be
+// open, and those go to the unit-level side buffers (unit = R) exactly as in segreduce_kernel.
+// The warp is fed by its own three-deep cp.async pipeline in shared memory (no block barriers, only
+// __syncwarp), in steps of WS_POS positions:
+//     K(k+2)  sorted keys / payloads two steps ahead                     -> key ring (3 slots)
+//     R(k+1)  decode the next step (lane = position: pointers of its gradient row, its sample's fm_sum row and,
+//             for positions that start a segment, its table row) and issue every 16-byte piece of those rows
+//             plus the per-position scalars as cp.async                  -> row buffer (2 slots)
+//     C(k)    the sequential segmented sum over the step, out of shared memory.
+// Every row read of a step (random 256-byte rows) is in flight while the previous step is being summed, and no
+// register holds staged data.
+constexpr int WS_POS = 16;      // positions per warp step
+constexpr int WS_WARPS = 4;     // warps per block (each with a private ~26 KB pipeline at D = 64)
+
+__device__ __forceinline__ void cp_async16(void* smem, const void* gmem) {
+    asm volatile("cp.async.cg.shared.global [%0], [%1], 16;\n" ::"r"((unsigned)__cvta_generic_to_shared(smem)), "l"(gmem));
+}
+__device__ __forceinline__ void cp_async4(void* smem, const void* gmem) {
+    asm volatile("cp.async.ca.shared.global [%0], [%1], 4;\n" ::"r"((unsigned)__cvta_generic_to_shared(smem)), "l"(gmem));
+}
+__device__ __forceinline__ void cp_async_commit() { asm volatile("cp.async.commit_group;\n" ::: "memory"); }
+template <int N>
+__device__ __forceinline__ void cp_async_wait() { asm volatile("cp.async.wait_group %0;\n" ::"n"(N) : "memory"); }
+
+template <int VL>
+__device__ __forceinline__ VecF<VL> lds_vec(const float* p) {   // one LDS.32 / LDS.64 / LDS.128
+    VecF<VL> r;
+    if constexpr (VL == 4) { const float4 t = *reinterpret_cast<const float4*>(p); r.v[0] = t.x; r.v[1] = t.y; r.v[2] = t.z; r.v[3] = t.w; }
+    else if constexpr (VL == 2) { const float2 t = *reinterpret_cast<const float2*>(p); r.v[0] = t.x; r.v[1] = t.y; }
+    else r.v[0] = *p;
+    return r;
+}
+
+struct WarpLayout {   // byte offsets inside one warp's private region
+    size_t rows, row_buf, ptrs, keys, pays, meta, meta_buf, total;
+};
+__host__ __device__ inline WarpLayout warp_layout(int tdim, bool has_fm) {
+    WarpLayout L;
+    size_t o = 0;
+    L.rows = o; L.row_buf = (size_t)WS_POS * tdim * 4 * (has_fm ? 3 : 2); o += 2 * L.row_buf;   // [2][s_g | s_w | s_s]
+    L.ptrs = o; o += (size_t)WS_POS * 8 * 3;                                                      // gptr, sptr, wptr
+    L.keys = o; o += 3 * (size_t)WS_POS * 4;
+    L.pays = o; o += 3 * (size_t)WS_POS * 4;
+    L.meta = o; L.meta_buf = (size_t)WS_POS * (4 * 3 + 2 + 2); o += 2 * L.meta_buf;               // [2][m | o | w1 | f | head]
+    L.total = (o + 15) & ~(size_t)15;
+    return L;
+}
+__host__ __device__ inline size_t warp_kernel_smem(int tdim, int S, int F, bool has_fm) {
+    size_t o = (size_t)WS_WARPS * warp_layout(tdim, has_fm).total;
+    o += (size_t)((S + 7) & ~7) * 2;
+    return o + (size_t)F * sizeof(FieldB);
+}
+
+template <bool HAS_FM, int VL>
+__global__ void __launch_bounds__(WS_WARPS * 32)
+segreduce_warp_kernel(const __grid_constant__ DevPlan P, const __grid_constant__ DevGrads GR,
+                      const __grid_constant__ BwdArgs a, long long R) {
+    extern __shared__ __align__(16) unsigned char sm_raw[];
+    const int lane = threadIdx.x & 31, wib = threadIdx.x >> 5;
+    const int tdim = P.max_tdim, S = P.S;
+    const int G = tdim >> 2, lgG = __ffs(G) - 1;       // 16-byte pieces per row
+    const WarpLayout L = warp_layout(tdim, HAS_FM);
+    unsigned char* wbase = sm_raw + (size_t)wib * L.total;
+    unsigned short* s_slotf = reinterpret_cast<unsigned short*>(sm_raw + (size_t)WS_WARPS * L.total);
+    FieldB* t_field = reinterpret_cast<FieldB*>(s_slotf + ((S + 7) & ~7));
+    const float** s_gptr = reinterpret_cast<const float**>(wbase + L.ptrs);
+    const float** s_sptr = s_gptr + WS_POS;
+    const float** s_wptr = s_sptr + WS_POS;
+    auto keys_of = [&](int k) { return reinterpret_cast<uint32_t*>(wbase + L.keys) + (k % 3) * WS_POS; };
+    auto pays_of = [&](int k) { return reinterpret_cast<uint32_t*>(wbase + L.pays) + (k % 3) * WS_POS; };
+    auto rows_of = [&](int k) { return reinterpret_cast<float*>(wbase + L.rows + (size_t)(k & 1) * L.row_buf); };
+    auto meta_of = [&](int k) { return reinterpret_cast<float*>(wbase + L.meta + (size_t)(k & 1) * L.meta_buf); };
+
+    for (int t = threadIdx.x; t < S; t += blockDim.x) s_slotf[t] = P.slot_field[t];
+    stage_fields(P, t_field);
+    __syncthreads();                                   // the only block barrier
+
+    const uint32_t PAD = P.pad_key;
+    const int bits = a.slot_bits;
+    const uint32_t smask = (1u << bits) - 1u;
+    const float coef = a.l2x2 * (a.l2_gscale ? __ldg(a.l2_gscale) : 1.f);
+    const bool need_w = HAS_FM || coef != 0.f || a.direct;
+    const bool need_w1 = coef != 0.f;
+    const long long unit_id = (long long)blockIdx.x * WS_WARPS + wib;
+    const long long r0 = unit_id * R;
+    if (r0 >= a.N) return;
+    const long long r1 = (r0 + R < a.N) ? r0 + R : a.N;
+    const int nsteps = (int)((r1 - r0 + WS_POS - 1) / WS_POS);
+    const uint32_t prev_key = r0 > 0 ? __ldg(a.skeys + r0 - 1) : PAD;
+
+    auto issue_keys = [&](int k) {
+        if (k < nsteps && lane < WS_POS) {
+            const long long p = r0 + (long long)k * WS_POS + lane;
+            if (p < r1) { cp_async4(keys_of(k) + lane, a.skeys + p); cp_async4(pays_of(k) + lane, a.spay + p); }
+            else keys_of(k)[lane] = PAD;
+        }
+        cp_async_commit();
+    };
+    auto issue_rows = [&](int k) {
+        if (k < nsteps) {
+            const uint32_t* ks = keys_of(k);
+            const uint32_t* ps = pays_of(k);
+            float* s_g = rows_of(k);
+            float* s_w = s_g + WS_POS * tdim;
+            float* s_s = s_w + WS_POS * tdim;
+            float* s_m = meta_of(k);
+            float* s_o = s_m + WS_POS;
+            float* s_w1 = s_o + WS_POS;
+            unsigned short* s_f = reinterpret_cast<unsigned short*>(s_w1 + WS_POS);
+            unsigned short* s_head = s_f + WS_POS;
+            if (lane < WS_POS) {
+                const int i = lane;
+                const uint32_t key = ks[i];
+                int head = 0;
+                if (key != PAD) {
+                    const uint32_t pay = ps[i];
+                    int f;
+                    if (a.direct) {
+                        f = field_of_key(t_field, P.n_fields, key);
+                        const float* row = a.g_flat + (size_t)pay * a.row_stride;
+                        s_gptr[i] = row;
+                        s_sptr[i] = nullptr;
+                        cp_async4(s_o + i, row + tdim);          // packed first-order gradient
+                        cp_async4(s_m + i, row + tdim + 1);      // packed g_fm (for -(sum g_fm) w)
+                    } else {
+                        const uint32_t b = pay >> bits;
+                        f = s_slotf[pay & smask];
+                        s_gptr[i] = a.g_flat + (size_t)b * P.T + t_field[f].flat_off;
+                        s_sptr[i] = HAS_FM ? a.fm_sum + (size_t)b * P.D : nullptr;
+                        if (a.g_fm) cp_async4(s_m + i, a.g_fm + b); else s_m[i] = 0.f;
+                        if (a.g_first) cp_async4(s_o + i, a.g_first + b); else s_o[i] = 0.f;
+                    }
+                    const FieldB& fb = t_field[f];
+                    s_f[i] = (unsigned short)f;
+                    s_wptr[i] = fb.w2 + (size_t)(key - fb.row_base) * fb.dim;
+                    const uint32_t before = i > 0 ? ks[i - 1] : (k > 0 ? keys_of(k - 1)[WS_POS - 1] : prev_key);
+                    head = key != before;                        // starts a segment inside this range
+                    if (need_w1 && head) cp_async4(s_w1 + i, fb.w1 + (key - fb.row_base));
+                }
+                s_head[i] = (unsigned short)head;
+            }
+            __syncwarp();
+            for (int q = lane; q < WS_POS * G; q += 32) {
+                const int i = q >> lgG, c = q & (G - 1);
+                if (ks[i] == PAD) continue;
+                cp_async16(s_g + i * tdim + c * 4, s_gptr[i] + c * 4);
+                if (HAS_FM) cp_async16(s_s + i * tdim + c * 4, s_sptr[i] + c * 4);
+                if (need_w && s_head[i]) cp_async16(s_w + i * tdim + c * 4, s_wptr[i] + c * 4);
+            }
+        }
+        cp_async_commit();
+    };
+
+    // running segment
+    uint32_t cur = PAD;
+    bool started_before = false, open = false;
+    int f = 0, n_heads = 0, n_valid = 0;
+    long long head_pos = r0;
+    VecF<VL> acc = vzero<VL>(), wreg = vzero<VL>();
+    float acc1 = 0.f, gs = 0.f, w1reg = 0.f;
+    auto close_segment = [&]() {
+        if (started_before) {   // started in an earlier range: the unit stitch pass finishes it
+            vstore<VL>(a.head2 + (size_t)unit_id * tdim + lane * VL, acc);
+            if (lane == 0) { a.head1[unit_id] = acc1; a.headg[unit_id] = gs; }
+        } else {
+            write_row<VL>(P, GR, a, coef, t_field[f], cur, f, head_pos, lane, acc, acc1, gs, true, wreg, w1reg);
+        }
+    };
+
+    issue_keys(0);
+    issue_keys(1);
+    cp_async_wait<1>();
+    __syncwarp();
+    issue_rows(0);
+    bool ended = false;
+    for (int k = 0; k < nsteps && !ended; ++k) {
+        issue_keys(k + 2);
+        cp_async_wait<2>();            // K(k+1) has landed   [pending: R(k), K(k+2)]
+        __syncwarp();
+        issue_rows(k + 1);
+        cp_async_wait<2>();            // R(k) has landed     [pending: K(k+2), R(k+1)]
+        __syncwarp();
+        const uint32_t* ks = keys_of(k);
+        const float* s_g = rows_of(k);
+        const float* s_w = s_g + WS_POS * tdim;
+        const float* s_s = s_w + WS_POS * tdim;
+        const float* s_m = meta_of(k);
+        const float* s_o = s_m + WS_POS;
+        const float* s_w1 = s_o + WS_POS;
+        const unsigned short* s_f = reinterpret_cast<const unsigned short*>(s_w1 + WS_POS);
+#pragma unroll 4
+        for (int i = 0; i < WS_POS; ++i) {
+            const uint32_t key = ks[i];
+            if (key == PAD) { ended = true; break; }
+            if (!open || key != cur) {
+                if (open) close_segment();
+                started_before = !open && key == prev_key;      // only the range's first segment can be
+                open = true;
+                cur = key; f = s_f[i];
+                head_pos = r0 + (long long)k * WS_POS + i;
+                if (!started_before) {
+                    ++n_heads;
+                    wreg = lds_vec<VL>(s_w + i * tdim + lane * VL);
+                    w1reg = s_w1[i];
+                }
+                acc = vzero<VL>(); acc1 = 0.f; gs = 0.f;
+            }
+            const VecF<VL> g = lds_vec<VL>(s_g + i * tdim + lane * VL);
+            const float m = s_m[i];
+            if (HAS_FM) {
+                const VecF<VL> sv = lds_vec<VL>(s_s + i * tdim + lane * VL);
+#pragma unroll
+                for (int v = 0; v < VL; ++v) acc.v[v] += fmaf(m, sv.v[v], g.v[v]);
+            } else {
+#pragma unroll
+                for (int v = 0; v < VL; ++v) acc.v[v] += g.v[v];
+            }
+            gs += m;
+            acc1 += s_o[i];
+            ++n_valid;
+        }
+        __syncwarp();                  // row buffer k & 1 and key slot k % 3 are free again
+    }
+    cp_async_wait<0>();
+    if (open) {
+        const bool continues = !ended && r1 < a.N && __ldg(a.skeys + r1) == cur;
+        if (started_before || !continues) {
+            close_segment();
+        } else {                       // starts here and leaves the range: this unit owns the segment
+            vstore<VL>(a.tail2 + (size_t)unit_id * tdim + lane * VL, acc);
+            if (lane == 0) {
+                a.tail1[unit_id] = acc1; a.tailg[unit_id] = gs;
+                a.tail_start[unit_id] = head_pos; a.tail_field[unit_id] = f;
+                a.open_list[atomicAdd(a.open_count, 1u)] = (unsigned)unit_id;
+            }
+        }
+    }
+    if (lane == 0 && (n_valid | n_heads)) {
+        atomicAdd(a.counters, (unsigned long long)n_valid);
+        atomicAdd(a.counters + 1, (unsigned long long)n_heads);
+    }
+}
+
+// ---- segments that leave their unit (listed by segreduce in open_list: only the unit in which the segment
+// STARTS is listed).  stitch_kernel: one lane group per listed segment finds the unit in which it ends (G units
+// per step) and, when it spans at most LONG_SPAN units, adds their head partials in unit order.  Longer
+// segments (hot rows of small tables) are queued for stitch_long_kernel: one block each, lane group g adds the
+// partials of units u+1+g, u+1+g+gpb, ... and group 0 folds tail(u) + partial(0) + partial(1) + ... -- fixed
+// orders both, whichever block or group runs them.
+constexpr int LONG_SPAN = 24;
+
+template <int V>
+__device__ __forceinline__ void stitch_write(const DevPlan& P, const DevGrads& GR, const BwdArgs& a, float coef,
+                                             long long u, uint32_t k, int j, const VecF<V>& acc, float acc1, float gs) {
+    const int f = a.tail_field[u];
+    const FieldDev& fd = P.f[f];
+    FieldB fb;
+    fb.w2 = fd.w2; fb.w1 = fd.w1; fb.row_base = (unsigned)fd.row_base; fb.dim = fd.dim;
+    fb.flat_off = fd.flat_off; fb.aux_off = fd.aux_off; fb.flags = 0;
+    write_row<V>(P, GR, a, coef, fb, k, f, a.tail_start[u], j, acc, acc1, gs);
+}
+
 template <int V>
 __global__ void __launch_bounds__(256)
 stitch_kernel(const __grid_constant__ DevPlan P, const __grid_constant__ DevGrads GR,
@@ -591,48 +864,96 @@ stitch_kernel(const __grid_constant__ DevPlan P, const __grid_constant__ DevGrad
     const int gpb = blockDim.x / G;
     const int gl = threadIdx.x / G;
     const int j = threadIdx.x - gl * G;
-    const long long u = (long long)blockIdx.x * gpb + gl;
-    const long long p0 = u * unit;
-    if (p0 >= a.N) return;
-    const long long p1 = p0 + unit;
-    if (p1 >= a.N) return;                                   // the last unit cannot continue
-    const uint32_t k = __ldg(a.skeys + p1 - 1);
-    if (k == P.pad_key || __ldg(a.skeys + p1) != k) return;  // no segment leaves this unit
-    if (__ldg(a.skeys + p0) == k && p0 > 0 && __ldg(a.skeys + p0 - 1) == k) return;  // not the owner
     const unsigned gmask = group_mask(G);
     const unsigned lane_base = (threadIdx.x & 31u) & ~(unsigned)(G - 1);
     const int tdim = P.max_tdim, nlane = tdim / V;
     const float coef = a.l2x2 * (a.l2_gscale ? __ldg(a.l2_gscale) : 1.f);
-    // last unit of the segment: the first unit after u that is not "through"
-    long long last = u + 1;
-    for (long long base = u + 1;; base += G) {
-        const long long uu = base + j;
-        const long long e = (uu + 1) * unit;
-        const bool through = e < a.N && __ldg(a.skeys + e - 1) == k && __ldg(a.skeys + e) == k;
-        unsigned stop = __ballot_sync(gmask, !through) >> lane_base;
-        if (G < 32) stop &= (1u << G) - 1u;
-        if (stop) { last = base + (__ffs(stop) - 1); break; }
-    }
-    VecF<V> acc = vzero<V>();
-    if (j < nlane) acc = vload<V>(a.tail2 + (size_t)u * tdim + j * V);
-    float acc1 = a.tail1[u], gs = a.tailg[u];
-#pragma unroll 4
-    for (long long uu = u + 1; uu <= last; ++uu) {
-        if (j < nlane) {
-            const VecF<V> h = vload<V>(a.head2 + (size_t)uu * tdim + j * V);
-#pragma unroll
-            for (int v = 0; v < V; ++v) acc.v[v] += h.v[v];
+    const unsigned n_open = *a.open_count;
+    for (unsigned it = blockIdx.x * gpb + gl; it < n_open; it += gridDim.x * gpb) {
+        const long long u = a.open_list[it];
+        const uint32_t k = __ldg(a.skeys + (u + 1) * unit - 1);
+        // last unit of the segment: the first unit after u that is not "through"
+        long long last = u + 1;
+        for (long long base = u + 1;; base += G) {
+            const long long uu = base + j;
+            const long long e = (uu + 1) * unit;
+            const bool through = e < a.N && __ldg(a.skeys + e - 1) == k && __ldg(a.skeys + e) == k;
+            unsigned stop = __ballot_sync(gmask, !through) >> lane_base;
+            if (G < 32) stop &= (1u << G) - 1u;
+            if (stop) { last = base + (__ffs(stop) - 1); break; }
         }
-        acc1 += __ldg(a.head1 + uu);
-        gs += __ldg(a.headg + uu);
+        if (last - u > LONG_SPAN) {
+            if (j == 0) {
+                const unsigned q = atomicAdd(a.long_count, 1u);
+                a.long_list[2 * q] = (unsigned)u; a.long_list[2 * q + 1] = (unsigned)last;
+            }
+            continue;
+        }
+        VecF<V> acc = vzero<V>();
+        if (j < nlane) acc = vload<V>(a.tail2 + (size_t)u * tdim + j * V);
+        float acc1 = a.tail1[u], gs = a.tailg[u];
+#pragma unroll 4
+        for (long long uu = u + 1; uu <= last; ++uu) {
+            if (j < nlane) {
+                const VecF<V> h = vload<V>(a.head2 + (size_t)uu * tdim + j * V);
+#pragma unroll
+                for (int v = 0; v < V; ++v) acc.v[v] += h.v[v];
+            }
+            acc1 += __ldg(a.head1 + uu);
+            gs += __ldg(a.headg + uu);
+        }
+        stitch_write<V>(P, GR, a, coef, u, k, j, acc, acc1, gs);
     }
-    const long long hp = a.tail_start[u];
-    const int f = a.tail_field[u];
-    const FieldDev& fd = P.f[f];
-    FieldB fb;
-    fb.w2 = fd.w2; fb.w1 = fd.w1; fb.row_base = (unsigned)fd.row_base; fb.dim = fd.dim;
-    fb.flat_off = fd.flat_off; fb.aux_off = fd.aux_off; fb.flags = 0;
-    write_row<V>(P, GR, a, coef, fb, k, f, hp, j, acc, acc1, gs);
+}
+
+template <int V>
+__global__ void __launch_bounds__(256)
+stitch_long_kernel(const __grid_constant__ DevPlan P, const __grid_constant__ DevGrads GR,
+                   const __grid_constant__ BwdArgs a, int G, long long unit) {
+    extern __shared__ __align__(16) float st_sm[];
+    const int gpb = blockDim.x / G;
+    const int gl = threadIdx.x / G;
+    const int j = threadIdx.x - gl * G;
+    const int tdim = P.max_tdim, nlane = tdim / V;
+    float* s_part = st_sm;                   // gpb x tdim
+    float* s_p1 = s_part + gpb * tdim;       // gpb
+    float* s_pg = s_p1 + gpb;                // gpb
+    const float coef = a.l2x2 * (a.l2_gscale ? __ldg(a.l2_gscale) : 1.f);
+    const unsigned n_long = *a.long_count;
+    for (unsigned it = blockIdx.x; it < n_long; it += gridDim.x) {
+        const long long u = a.long_list[2 * it], last = a.long_list[2 * it + 1];
+        const uint32_t k = __ldg(a.skeys + (u + 1) * unit - 1);
+        VecF<V> acc = vzero<V>();
+        float acc1 = 0.f, gs = 0.f;
+#pragma unroll 4
+        for (long long uu = u + 1 + gl; uu <= last; uu += gpb) {
+            if (j < nlane) {
+                const VecF<V> h = vload<V>(a.head2 + (size_t)uu * tdim + j * V);
+#pragma unroll
+                for (int v = 0; v < V; ++v) acc.v[v] += h.v[v];
+            }
+            acc1 += __ldg(a.head1 + uu);
+            gs += __ldg(a.headg + uu);
+        }
+        __syncthreads();                     // previous round's reads of s_part are done
+        if (j < nlane) vstore<V>(s_part + gl * tdim + j * V, acc);
+        if (j == 0) { s_p1[gl] = acc1; s_pg[gl] = gs; }
+        __syncthreads();
+        if (gl == 0) {
+            VecF<V> tot = vzero<V>();
+            if (j < nlane) tot = vload<V>(a.tail2 + (size_t)u * tdim + j * V);
+            float t1 = a.tail1[u], tg = a.tailg[u];
+            for (int g2 = 0; g2 < gpb; ++g2) {
+                if (j < nlane) {
+#pragma unroll
+                    for (int v = 0; v < V; ++v) tot.v[v] += s_part[g2 * tdim + j * V + v];
+                }
+                t1 += s_p1[g2];
+                tg += s_pg[g2];
+            }
+            stitch_write<V>(P, GR, a, coef, u, k, j, tot, t1, tg);
+        }
+    }
 }
 
 // ---- DENSE-field Linear grads and projection grads -------------------------------------
@@ -641,9 +962,11 @@ struct PgField {
 };
 // DENSE fields without projection are streamed (dense_stream_kernel); fields with a projection
 // go through the shared-memory tile kernel (pgrads_kernel).  pf[] lists the tile fields first.
+struct PgRun { short pf0, n; };   // streamed DENSE fields that are consecutive in the flat view
 struct PgArgs {
     PgField pf[MAX_FIELDS];
-    int n_pf, n_tile, n_slices, vals_per_slice;
+    PgRun runs[MAX_FIELDS];
+    int n_pf, n_tile, n_runs, n_slices, vals_per_slice;
     long long slice_len;
     float* partials;          // (n_slices, vals_per_slice)
 };
@@ -733,79 +1056,93 @@ pgrads_kernel(const __grid_constant__ DevPlan P, const __grid_constant__ BwdArgs
     for (int o = tid; o < pfd.nvals; o += PG_THREADS) out[o] = s_acc[o];
 }
 
-// DENSE field without projection: g_raw = g_flat + g_field + g_fm (fm_sum - e) is streamed once with
-// 128-bit loads; lane c of a sample group owns dims [cV, cV+V) and keeps sum(g_raw * x), sum(g_raw)
-// in registers; one fixed-order shared-memory reduction over the sample groups at the end.
-template <int V>
-__global__ void __launch_bounds__(PG_THREADS)
+// DENSE fields without projection: g_raw = g_flat + g_field + g_fm (fm_sum - e) is streamed once.  One block
+// owns a RUN of fields that are consecutive in the flat view and a slice of samples: thread (field u, lane c)
+// reads dims [cV, cV+V) of field u for every sample of the slice -- the whole block reads one contiguous
+// n*d*4-byte span per sample -- and keeps sum(g_raw * x), sum(g_raw) in registers, so there is no cross-thread
+// reduction at all; the slices are added in order by pgrads_finish_kernel.
+template <int V, bool HAS_FIELD>
+__global__ void __launch_bounds__(PG_THREADS, 2)
 dense_stream_kernel(const __grid_constant__ DevPlan P, const __grid_constant__ BwdArgs a,
                     const __grid_constant__ PgArgs pg, int lanes) {
-    extern __shared__ float sm[];
-    const PgField pfd = pg.pf[pg.n_tile + blockIdx.y];
+    const PgRun run = pg.runs[blockIdx.y];
+    const int u = threadIdx.x / lanes, c = threadIdx.x - u * lanes;
+    if (u >= run.n) return;
+    const PgField pfd = pg.pf[pg.n_tile + run.pf0 + u];
     const int f = pfd.f;
     const FieldDev& fd = P.f[f];
     const int D = P.D, d = fd.dim, F = P.n_fields, nch = d / V;
-    const int rows = PG_THREADS / lanes;
-    const int s = threadIdx.x / lanes, c = threadIdx.x - s * lanes;
+    if (c >= nch) return;
     const long long b_lo = (long long)blockIdx.x * pg.slice_len;
     const long long b_hi = (b_lo + pg.slice_len < a.B) ? b_lo + pg.slice_len : a.B;
     VecF<V> aw = vzero<V>(), ab = vzero<V>();
     float a1w = 0.f, a1b = 0.f;
-    if (c < nch) {
-        // e[b, f, :] = x[b] * w2 + b2 is recomputed, not re-read
-        const VecF<V> w2c = vload<V>(fd.w2 + c * V), b2c = vload<V>(fd.b2 + c * V);
-#pragma unroll 2
-        for (long long b = b_lo + s; b < b_hi; b += rows) {
-            const float x = __ldg(reinterpret_cast<const float*>(fd.in) + b);
-            VecF<V> g = vzero<V>();
-            if (a.g_flat) g = vload_stream<V>(a.g_flat + (size_t)b * P.T + fd.flat_off + c * V);
-            const size_t eoff = ((size_t)b * F + f) * D + c * V;
-            if (a.g_field) {
-                const VecF<V> t = vload_stream<V>(a.g_field + eoff);
+    // e[b, f, :] = x[b] * w2 + b2 is recomputed, not re-read
+    const VecF<V> w2c = vload<V>(fd.w2 + c * V), b2c = vload<V>(fd.b2 + c * V);
+    const float* xin = reinterpret_cast<const float*>(fd.in);
+    const float* gp = a.g_flat ? a.g_flat + fd.flat_off + c * V : nullptr;
+    const float* ep = HAS_FIELD ? a.g_field + (size_t)f * D + c * V : nullptr;
+    const float* sp = a.g_fm ? a.fm_sum + c * V : nullptr;
+    const bool first = c == 0 && a.g_first != nullptr;
+    constexpr int UB = HAS_FIELD ? 4 : 8;
+    for (long long b0 = b_lo; b0 < b_hi; b0 += UB) {
+        VecF<V> g[UB], t[HAS_FIELD ? UB : 1], sv[UB];
+        float x[UB], gfm[UB], g1[UB];
 #pragma unroll
-                for (int v = 0; v < V; ++v) g.v[v] += t.v[v];
-            }
-            if (a.g_fm) {
-                const float gfm = __ldg(a.g_fm + b);
-                const VecF<V> sv = vload<V>(a.fm_sum + (size_t)b * D + c * V);
+        for (int i = 0; i < UB; ++i) {       // every load of the batch is issued before any is consumed
+            const long long b = (b0 + i < b_hi) ? b0 + i : b_hi - 1;
+            x[i] = __ldg(xin + b);
+            g[i] = gp ? vload_stream<V>(gp + (size_t)b * P.T) : vzero<V>();
+            if (HAS_FIELD) t[i] = vload_stream<V>(ep + (size_t)b * F * D);
+            sv[i] = sp ? vload<V>(sp + (size_t)b * D) : vzero<V>();
+            gfm[i] = sp ? __ldg(a.g_fm + b) : 0.f;
+            g1[i] = first ? __ldg(a.g_first + b) : 0.f;
+        }
 #pragma unroll
-                for (int v = 0; v < V; ++v) g.v[v] = fmaf(gfm, sv.v[v] - fmaf(x, w2c.v[v], b2c.v[v]), g.v[v]);
-            }
+        for (int i = 0; i < UB; ++i) {
+            if (b0 + i >= b_hi) break;
 #pragma unroll
-            for (int v = 0; v < V; ++v) { aw.v[v] = fmaf(g.v[v], x, aw.v[v]); ab.v[v] += g.v[v]; }
-            if (c == 0 && a.g_first) {
-                const float g1 = __ldg(a.g_first + b);
-                a1w = fmaf(g1, x, a1w);
-                a1b += g1;
+            for (int v = 0; v < V; ++v) {
+                float gr = g[i].v[v];
+                if (HAS_FIELD) gr += t[i].v[v];
+                if (sp) gr = fmaf(gfm[i], sv[i].v[v] - fmaf(x[i], w2c.v[v], b2c.v[v]), gr);
+                aw.v[v] = fmaf(gr, x[i], aw.v[v]);
+                ab.v[v] += gr;
             }
+            a1w = fmaf(g1[i], x[i], a1w);
+            a1b += g1[i];
         }
     }
-    // sm[s][0..d) = aw, [d..2d) = ab, [2d] = a1w, [2d+1] = a1b
-    const int stride = 2 * d + 2;
-    if (c < nch) {
-#pragma unroll
-        for (int v = 0; v < V; ++v) { sm[s * stride + c * V + v] = aw.v[v]; sm[s * stride + d + c * V + v] = ab.v[v]; }
-        if (c == 0) { sm[s * stride + 2 * d] = a1w; sm[s * stride + 2 * d + 1] = a1b; }
-    }
-    __syncthreads();
     float* out = pg.partials + (size_t)blockIdx.x * pg.vals_per_slice + pfd.part_off;
-    for (int o = threadIdx.x; o < stride; o += PG_THREADS) {
-        float acc = 0.f;
-        for (int r = 0; r < rows; ++r) acc += sm[r * stride + o];
-        out[o] = acc;
-    }
+#pragma unroll
+    for (int v = 0; v < V; ++v) { out[c * V + v] = aw.v[v]; out[d + c * V + v] = ab.v[v]; }
+    if (c == 0) { out[2 * d] = a1w; out[2 * d + 1] = a1b; }
 }
 
-__global__ void pgrads_finish_kernel(const __grid_constant__ DevPlan P, const __grid_constant__ DevGrads GR,
-                                     const __grid_constant__ BwdArgs a, const __grid_constant__ PgArgs pg) {
+// Adds the per-slice partials in a fixed order: warp w of a block takes slices w, w + 8, ... for 32 consecutive
+// values (coalesced), then warp 0 folds the 8 sums in order and adds the L2 term.
+__global__ void __launch_bounds__(256)
+pgrads_finish_kernel(const __grid_constant__ DevPlan P, const __grid_constant__ DevGrads GR,
+                     const __grid_constant__ BwdArgs a, const __grid_constant__ PgArgs pg) {
+    __shared__ float s_acc[8][32];
     const PgField pfd = pg.pf[blockIdx.y];
     const FieldDev& fd = P.f[pfd.f];
     const GradDev& gd = GR.g[pfd.f];
-    const int o = blockIdx.x * blockDim.x + threadIdx.x;
-    if (o >= pfd.nvals) return;
-    const float coef = a.l2x2 * (a.l2_gscale ? __ldg(a.l2_gscale) : 1.f);
+    const int w = threadIdx.x >> 5, lane = threadIdx.x & 31;
+    const int o = blockIdx.x * 32 + lane;
     float acc = 0.f;
-    for (int s = 0; s < pg.n_slices; ++s) acc += pg.partials[(size_t)s * pg.vals_per_slice + pfd.part_off + o];
+    if (o < pfd.nvals) {
+        const float* src = pg.partials + pfd.part_off + o;
+#pragma unroll 8
+        for (int s = w; s < pg.n_slices; s += 8) acc += src[(size_t)s * pg.vals_per_slice];
+    }
+    s_acc[w][lane] = acc;
+    __syncthreads();
+    if (w != 0 || o >= pfd.nvals) return;
+    acc = 0.f;
+#pragma unroll
+    for (int q = 0; q < 8; ++q) acc += s_acc[q][lane];
+    const float coef = a.l2x2 * (a.l2_gscale ? __ldg(a.l2_gscale) : 1.f);
     const int d = fd.dim;
     const int n_proj = fd.proj ? P.D * d : 0;
     if (o < n_proj) { gd.gproj[o] = fmaf(coef, __ldg(fd.proj + o), acc); return; }
@@ -819,7 +1156,7 @@ __global__ void pgrads_finish_kernel(const __grid_constant__ DevPlan P, const __
 // ---- host-side workspace carving --------------------------------------------------------
 struct BwdLayout {
     size_t cub_bytes, off_cub, off_payload, off_head2, off_head1, off_tail2, off_tail1, off_tstart, off_headg, off_tailg, off_tfield, off_counters,
-        off_partials, total;
+        off_open, off_long, off_partials, total;
     long long n_chunks;
     int n_slices, vals_per_slice;
     long long slice_len;
@@ -846,11 +1183,13 @@ static int make_layout(const dfm_plan* plan, long long B, BwdLayout& L, long lon
     const long long N = direct_rows >= 0 ? direct_rows : B * plan->S;
     L.cub_bytes = 0;
     if (N > 0) { int rc = sort_temp_bytes(N, plan->key_bits, &L.cub_bytes); if (rc) return rc; }
-    L.n_chunks = ceil_div(N > 0 ? N : 1, 8 * CHUNK);   // units: >= 8 chunks per segreduce block
+    // units: >= 8 chunks of CHUNK per segreduce block, or 4 * WS_POS positions (at least) per warp range
+    const long long min_unit = 4 * WS_POS;
+    L.n_chunks = ceil_div(N > 0 ? N : 1, min_unit);
     int vals = 0, n_pf = 0;
     for (int f = 0; f < plan->n_fields; ++f) { int n = pg_count_vals(plan, f); if (n) { vals += n; ++n_pf; } }
     L.vals_per_slice = vals;
-    int want = n_pf ? (int)ceil_div(4 * sm_count(), n_pf) : 1;
+    int want = n_pf ? 4 * sm_count() : 1;
     long long max_slices = ceil_div(B > 0 ? B : 1, 2 * PG_TILE);
     if (want > max_slices) want = (int)max_slices;
     if (want < 1) want = 1;
@@ -869,6 +1208,8 @@ static int make_layout(const dfm_plan* plan, long long B, BwdLayout& L, long lon
     L.off_tailg = take((size_t)L.n_chunks * 4);
     L.off_tfield = take((size_t)L.n_chunks * 4);
     L.off_counters = take(16);
+    L.off_open = take((size_t)(L.n_chunks + 1) * 4);      // [0] = count, [1..] = owner units
+    L.off_long = take((size_t)(L.n_chunks / 16 + 2) * 8); // [0] = count, then (owner, last) pairs of long segments
     L.off_partials = take((size_t)L.n_slices * vals * 4);
     L.total = off;
     return DFM_OK;
@@ -993,6 +1334,10 @@ static int embed_bwd_impl(const dfm_plan* plan, int64_t batch, long long direct_
     a.row_stride = plan->max_tdim + 4;
     a.counters = n_valid ? reinterpret_cast<unsigned long long*>(n_valid)
                          : reinterpret_cast<unsigned long long*>(ws + L.off_counters);
+    a.open_count = reinterpret_cast<unsigned*>(ws + L.off_open);
+    a.open_list = a.open_count + 1;
+    a.long_count = reinterpret_cast<unsigned*>(ws + L.off_long);
+    a.long_list = a.long_count + 2;
     const int fill_blocks = 8 * sm_count();
 
     // 1. dense mode: every element of every table gradient starts as 2*l2*w (or 0)
@@ -1013,29 +1358,63 @@ static int embed_bwd_impl(const dfm_plan* plan, int64_t batch, long long direct_
         rc = sort_keys_impl(plan, N, payS, keys, sorted_keys, sorted_payload, ws + L.off_cub,
                             L.off_payload + (size_t)N * 4 - L.off_cub, stream);
         if (rc) return rc;
+        DFM_CHECK_CUDA(cudaMemsetAsync(a.open_count, 0, 4, st));
+        DFM_CHECK_CUDA(cudaMemsetAsync(a.long_count, 0, 4, st));
         const int gpb = 256 / G;
-        const long long unit = (long long)gpb * CHUNK;               // positions per segreduce block
-        const long long n_units = ceil_div(N, unit);
-        const unsigned blocks = (unsigned)n_units;
-        const unsigned sblocks = (unsigned)ceil_div(n_units, gpb);
-        const size_t smem = seg_smem_bytes(gpb, plan->max_tdim, (int)unit, direct ? 0 : plan->S, plan->n_fields) + 16;
         bool any_generic = false;
         for (int f = 0; f < plan->n_fields; ++f)
             any_generic = any_generic || plan->kind[f] == DFM_SEQUENCE || (plan->kind[f] == DFM_SPARSE && plan->dim[f] != plan->fm_dim);
-        if (smem > 48 * 1024) {
-            DFM_CHECK_CUDA(cudaFuncSetAttribute(segreduce_kernel<4, true>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
-            DFM_CHECK_CUDA(cudaFuncSetAttribute(segreduce_kernel<1, true>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
-            DFM_CHECK_CUDA(cudaFuncSetAttribute(segreduce_kernel<4, false>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
-            DFM_CHECK_CUDA(cudaFuncSetAttribute(segreduce_kernel<1, false>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
-        }
-        if (V == 4) {
-            if (any_generic) segreduce_kernel<4, true><<<blocks, 256, smem, st>>>(*P, *GR, a, G);
-            else segreduce_kernel<4, false><<<blocks, 256, smem, st>>>(*P, *GR, a, G);
-            stitch_kernel<4><<<sblocks, 256, 0, st>>>(*P, *GR, a, G, unit);
+        const bool has_fm = g_fm != nullptr && !direct;
+        const int tdim = plan->max_tdim;
+        const size_t st_smem = warp_kernel_smem(tdim, direct ? 0 : plan->S, plan->n_fields, has_fm);
+        const bool staged = V == 4 && lanes == G && (tdim == 32 || tdim == 64) && g_flat && !g_field && (direct || !any_generic) &&
+                            (!g_fm || direct || plan->fm_dim == tdim);
+        long long unit;
+        if (staged) {
+            // one range of R positions per warp, all warps resident (2 blocks per SM at D = 64)
+            const int per_sm = (int)((220 * 1024) / st_smem) > 0 ? (int)((220 * 1024) / st_smem) : 1;
+            long long blocks = (long long)per_sm * sm_count();
+            long long R = ceil_div(ceil_div(N, blocks * WS_WARPS), WS_POS) * WS_POS;
+            if (R < 4 * WS_POS) R = 4 * WS_POS;
+            blocks = ceil_div(ceil_div(N, R), WS_WARPS);
+            unit = R;
+#define DFM_LAUNCH_WARP(FM, VLN)                                                                                           \
+            do {                                                                                                               \
+                DFM_CHECK_CUDA(cudaFuncSetAttribute(segreduce_warp_kernel<FM, VLN>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)st_smem)); \
+                segreduce_warp_kernel<FM, VLN><<<(unsigned)blocks, WS_WARPS * 32, st_smem, st>>>(*P, *GR, a, R);            \
+            } while (0)
+            if (has_fm) { if (tdim == 64) DFM_LAUNCH_WARP(true, 2); else DFM_LAUNCH_WARP(true, 1); }
+            else { if (tdim == 64) DFM_LAUNCH_WARP(false, 2); else DFM_LAUNCH_WARP(false, 1); }
+#undef DFM_LAUNCH_WARP
         } else {
-            if (any_generic) segreduce_kernel<1, true><<<blocks, 256, smem, st>>>(*P, *GR, a, G);
-            else segreduce_kernel<1, false><<<blocks, 256, smem, st>>>(*P, *GR, a, G);
+            unit = (long long)gpb * CHUNK;               // positions per segreduce block
+            const unsigned blocks = (unsigned)ceil_div(N, unit);
+            const size_t smem = seg_smem_bytes(gpb, plan->max_tdim, (int)unit, direct ? 0 : plan->S, plan->n_fields) + 16;
+            if (smem > 48 * 1024) {
+                DFM_CHECK_CUDA(cudaFuncSetAttribute(segreduce_kernel<4, true>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
+                DFM_CHECK_CUDA(cudaFuncSetAttribute(segreduce_kernel<1, true>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
+                DFM_CHECK_CUDA(cudaFuncSetAttribute(segreduce_kernel<4, false>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
+                DFM_CHECK_CUDA(cudaFuncSetAttribute(segreduce_kernel<1, false>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
+            }
+            if (V == 4) {
+                if (any_generic) segreduce_kernel<4, true><<<blocks, 256, smem, st>>>(*P, *GR, a, G);
+                else segreduce_kernel<4, false><<<blocks, 256, smem, st>>>(*P, *GR, a, G);
+            } else {
+                if (any_generic) segreduce_kernel<1, true><<<blocks, 256, smem, st>>>(*P, *GR, a, G);
+                else segreduce_kernel<1, false><<<blocks, 256, smem, st>>>(*P, *GR, a, G);
+            }
+        }
+        const long long n_units = ceil_div(N, unit);
+        const long long want = ceil_div(n_units, gpb);
+        const unsigned sblocks = (unsigned)(want < 4LL * sm_count() ? want : 4LL * sm_count());
+        const unsigned lblocks = (unsigned)(n_units < 2LL * sm_count() ? n_units : 2LL * sm_count());
+        const size_t ssm = (size_t)gpb * (plan->max_tdim + 2) * 4;
+        if (V == 4) {
+            stitch_kernel<4><<<sblocks, 256, 0, st>>>(*P, *GR, a, G, unit);
+            stitch_long_kernel<4><<<lblocks, 256, ssm, st>>>(*P, *GR, a, G, unit);
+        } else {
             stitch_kernel<1><<<sblocks, 256, 0, st>>>(*P, *GR, a, G, unit);
+            stitch_long_kernel<1><<<lblocks, 256, ssm, st>>>(*P, *GR, a, G, unit);
         }
         DFM_CHECK_LAUNCH();
     } else if (n_valid) {
@@ -1046,10 +1425,11 @@ static int embed_bwd_impl(const dfm_plan* plan, int64_t batch, long long direct_
     PgArgs* pg = new PgArgs;
     struct G2 { PgArgs* p; ~G2() { delete p; } } g2{pg};
     memset(pg, 0, sizeof(*pg));
-    int max_smem_floats = 0, max_vals = 0, stream_smem_floats = 0, stream_lanes = 1;
+    int max_smem_floats = 0, max_vals = 0, stream_lanes = 1;
     auto streamable = [&](int f) {
         return plan->kind[f] == DFM_DENSE && plan->dim[f] == plan->fm_dim && plan->dim[f] / V <= 32;
     };
+    int last_stream_f = -2;
     for (int pass = 0; pass < 2; ++pass) {
         for (int f = 0; f < plan->n_fields; ++f) {
             const int n = pg_count_vals(plan, f);
@@ -1064,7 +1444,15 @@ static int embed_bwd_impl(const dfm_plan* plan, int64_t batch, long long direct_
                 if (fl > max_smem_floats) max_smem_floats = fl;
             } else {
                 stream_lanes = next_pow2(plan->dim[f] / V);   // every streamed field has dim == fm_dim
-                stream_smem_floats = (PG_THREADS / stream_lanes) * (2 * plan->dim[f] + 2);
+                // runs: consecutive fields (contiguous in the flat view), at most PG_THREADS / lanes per block
+                const int si = pg->n_pf - 1 - pg->n_tile;
+                if (pg->n_runs > 0 && f == last_stream_f + 1 && (pg->runs[pg->n_runs - 1].n + 1) * stream_lanes <= PG_THREADS) {
+                    pg->runs[pg->n_runs - 1].n++;
+                } else {
+                    pg->runs[pg->n_runs].pf0 = (short)si; pg->runs[pg->n_runs].n = 1;
+                    pg->n_runs++;
+                }
+                last_stream_f = f;
             }
         }
     }
@@ -1075,15 +1463,16 @@ static int embed_bwd_impl(const dfm_plan* plan, int64_t batch, long long direct_
         DFM_REQUIRE(smem <= 200 * 1024, DFM_ERR_UNSUPPORTED, "dfm_embed_bwd: projection/dense grads need %zu B shared memory", smem);
         if (smem > 48 * 1024)
             DFM_CHECK_CUDA(cudaFuncSetAttribute(pgrads_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
-        const int n_stream = pg->n_pf - pg->n_tile;
         if (batch > 0 && pg->n_tile > 0)
             pgrads_kernel<<<dim3(pg->n_slices, pg->n_tile), PG_THREADS, smem, st>>>(*P, a, *pg);
-        if (batch > 0 && n_stream > 0) {
-            const size_t ssm = (size_t)stream_smem_floats * 4;
-            if (V == 4) dense_stream_kernel<4><<<dim3(pg->n_slices, n_stream), PG_THREADS, ssm, st>>>(*P, a, *pg, stream_lanes);
-            else dense_stream_kernel<1><<<dim3(pg->n_slices, n_stream), PG_THREADS, ssm, st>>>(*P, a, *pg, stream_lanes);
+        if (batch > 0 && pg->n_runs > 0) {
+            const dim3 grid(pg->n_slices, pg->n_runs);
+            if (V == 4 && g_field) dense_stream_kernel<4, true><<<grid, PG_THREADS, 0, st>>>(*P, a, *pg, stream_lanes);
+            else if (V == 4) dense_stream_kernel<4, false><<<grid, PG_THREADS, 0, st>>>(*P, a, *pg, stream_lanes);
+            else if (g_field) dense_stream_kernel<1, true><<<grid, PG_THREADS, 0, st>>>(*P, a, *pg, stream_lanes);
+            else dense_stream_kernel<1, false><<<grid, PG_THREADS, 0, st>>>(*P, a, *pg, stream_lanes);
         }
-        pgrads_finish_kernel<<<dim3((unsigned)ceil_div(max_vals, 128), pg->n_pf), 128, 0, st>>>(*P, *GR, a, *pg);
+        pgrads_finish_kernel<<<dim3((unsigned)ceil_div(max_vals, 32), pg->n_pf), 256, 0, st>>>(*P, *GR, a, *pg);
         DFM_CHECK_LAUNCH();
     }
     return DFM_OK;

@@ -43,6 +43,37 @@ __device__ __forceinline__ VecF<V> gather_row_chunk(const FieldDev& fd, int id, 
     return vload<V>(fd.w2 + (size_t)id * fd.dim + c * V);
 }
 
+// Plain bag (SEQUENCE, dim == D, sum / mean, no projection): lane j owns dims [jV, jV+V) of the pooled
+// row.  NBAG row gathers are in flight per lane (pads are predicated off, not branched around), added in
+// bag order, so the summation order is the reference's (EmbeddingBag walks the bag front to back).
+constexpr int NBAG = 8;
+template <int V>
+__device__ __forceinline__ VecF<V> pool_plain(const float* __restrict__ w2, const int* __restrict__ ids, int L,
+                                              int rs, int j, int& cnt_out) {
+    VecF<V> acc = vzero<V>();
+    int cnt = 0;
+    for (int l0 = 0; l0 < L; l0 += NBAG) {
+        VecF<V> r[NBAG];
+        int id[NBAG];
+#pragma unroll
+        for (int i = 0; i < NBAG; ++i) {
+            id[i] = (l0 + i < L) ? ids[l0 + i] : 0;
+            r[i] = vzero<V>();
+            if (id[i]) r[i] = vload<V>(w2 + (size_t)id[i] * rs + j * V);
+        }
+#pragma unroll
+        for (int i = 0; i < NBAG; ++i) {
+            if (id[i]) {
+                ++cnt;
+#pragma unroll
+                for (int v = 0; v < V; ++v) acc.v[v] += r[i].v[v];
+            }
+        }
+    }
+    cnt_out = cnt;
+    return acc;
+}
+
 // Pool one chunk of a bag: EmbeddingBag(mode, padding_idx=0) -- pads skipped wherever they are,
 // all-pad bag -> 0, duplicates count once per occurrence, max ties keep the first.
 template <int V>
@@ -266,6 +297,46 @@ embed_fwd_kernel(const __grid_constant__ DevPlan P, long long B, int G, int smem
             }
             continue;
         }
+        if (run.cls == 3) {
+            // plain bags of dim D (sum / mean): pooled row -> flat (== field embedding)
+            for (int u = 0; u < run.n; ++u) {
+                const int f = run.f0 + u;
+                const FieldDev& fd = P.f[f];
+                const int* ids = s_ids + fd.slot_base;
+                const int L = fd.max_len;
+                const bool mean = fd.combiner == DFM_MEAN;
+                int cnt = 0;
+                if (lane_on) {
+                    VecF<V> r = pool_plain<V>(fd.w2, ids, L, rs, j, cnt);
+                    if (mean && cnt > 0) {
+                        const float fc = (float)cnt;
+#pragma unroll
+                        for (int v = 0; v < V; ++v) r.v[v] = r.v[v] / fc;   // true division like ATen
+                    }
+                    if (active) {
+                        vstore_stream<V>(flat_b + fd.flat_off + j * V, r);
+                        if (two_views) vstore_stream<V>(fe_b + (size_t)f * D + j * V, r);
+                    }
+#pragma unroll
+                    for (int v = 0; v < V; ++v) { Sacc.v[v] += r.v[v]; Qacc.v[v] += __fmul_rn(r.v[v], r.v[v]); }
+                }
+                // first-order bag: one id per lane, fixed-order group reduction
+                float w1sum = 0.f;
+                int c1 = 0;
+                for (int l = j; l < L; l += G) {
+                    const int id = ids[l];
+                    if (id) { w1sum += __ldg(fd.w1 + (size_t)id * w1s); ++c1; }
+                }
+                w1sum = group_sum(w1sum, G, gmask);
+                c1 = (int)group_sum((float)c1, G, gmask);
+                if (j == 0) {
+                    if (mean && c1 > 0) w1sum = w1sum / (float)c1;
+                    fo_acc += w1sum;
+                    if (mean && active && aux_b) aux_b[fd.aux_off] = __float_as_uint(c1 > 0 ? 1.f / (float)c1 : 0.f);
+                }
+            }
+            continue;
+        }
         // ---- generic field: sequence bags, projected fields (any kind)
         const int f = run.f0;
         const FieldDev& fd = P.f[f];
@@ -415,7 +486,8 @@ int dfm_plan::fill(DevPlan& P, const void* const* inputs, const float* const* pa
     int n_dense = 0, n_runs = 0;
     for (int f = 0; f < n_fields; ++f) {
         const bool plain = dim[f] == fm_dim;
-        const int cls = (plain && kind[f] == DFM_SPARSE) ? 0 : (plain && kind[f] == DFM_DENSE) ? 1 : 2;
+        const int cls = (plain && kind[f] == DFM_SPARSE) ? 0 : (plain && kind[f] == DFM_DENSE) ? 1
+                        : (plain && kind[f] == DFM_SEQUENCE && combiner[f] != DFM_MAX) ? 3 : 2;
         if (n_runs > 0 && P.runs[n_runs - 1].cls == cls && cls != 2) {
             P.runs[n_runs - 1].n++;
         } else {
@@ -501,8 +573,9 @@ void dfm_plan_destroy(dfm_plan* plan) { delete plan; }
 int dfm_plan_set_table_stride(dfm_plan* plan, int row_stride, int w1_stride) {
     DFM_REQUIRE(plan && row_stride >= 0 && w1_stride >= 0, DFM_ERR_INVALID, "dfm_plan_set_table_stride: bad argument");
     for (int f = 0; f < plan->n_fields; ++f)
-        DFM_REQUIRE(plan->kind[f] == DFM_DENSE || (plan->kind[f] == DFM_SPARSE && plan->dim[f] == plan->fm_dim), DFM_ERR_UNSUPPORTED,
-                    "dfm_plan_set_table_stride: only plain SPARSE fields (dim == fm_dim) may use a strided row buffer");
+        DFM_REQUIRE(plan->kind[f] == DFM_DENSE || (plan->dim[f] == plan->fm_dim &&
+                        (plan->kind[f] == DFM_SPARSE || plan->combiner[f] != DFM_MAX)), DFM_ERR_UNSUPPORTED,
+                    "dfm_plan_set_table_stride: only plain SPARSE / sum- or mean-bag fields (dim == fm_dim) may use a strided row buffer");
     DFM_REQUIRE(row_stride == 0 || row_stride >= plan->fm_dim, DFM_ERR_INVALID, "dfm_plan_set_table_stride: stride < dim");
     plan->row_stride = row_stride; plan->w1_stride = w1_stride;
     return DFM_OK;

@@ -3,8 +3,13 @@
 // side (deepfm_b200/sharded.py); these kernels are the owner-side gather of the looked-up rows
 // and the sample-side packing of the row gradients into send order.
 //
-//   shard_gather   keys (global rows, as received)  ->  vec (M, d), first-order (M), local keys (M)
-//   shard_pack     upstream grads of the three views + FM  ->  g_vec (n, d), g_fo (n) in send order
+//   shard_route    id slots -> send order (stable grouping by owner), 1-based send positions per slot
+//                  (0 = nothing sent: a padding entry of a multi-hot bag), per-owner counts
+//   shard_gather   keys (global rows, as received)  ->  packed reply rows (M, d + 4), local keys (M)
+//   shard_pack     upstream grads of the three views + FM  ->  packed gradient rows (n, d + 4) in send order
+// Multi-hot bags (SEQUENCE fields, sum / mean) are exchanged id by id: the sample's GPU pools the
+// received rows in K1 (global mean divisor = the bag's non-pad count) and the gradient of every member
+// id travels back as its own row, so the owner-side reduction is the same sorted segmented sum.
 #include <string.h>
 
 #include "plan.cuh"
@@ -19,6 +24,9 @@ struct ShardField {
     int dim;
     int flat_off;          // sample side: offset of the field inside the flat view
     int field;             // sample side: field index
+    int slot_base, max_len;// sample side: first id slot / ids per sample of the field
+    int bag;               // 0: SPARSE, 1: sum bag, 2: mean bag
+    int aux_off;           // mean bag: word of the per-sample aux record that holds 1 / count
 };
 struct ShardArgs {
     ShardField f[MAX_FIELDS];
@@ -55,15 +63,19 @@ shard_gather_kernel(const __grid_constant__ ShardArgs a, long long M, const uint
 
 struct PackArgs {
     const float *g_first, *g_field, *g_flat, *g_fm, *fe, *fm_sum;
-    const long long* pos;  // (S, B): send position of slot s of sample b
+    const uint32_t* aux;
+    const long long* pos;  // per field f: (B, max_len) block at B * slot_base[f]; 1-based send position, 0 = not sent
     long long B;
-    int S, T, F, D, dmax;
+    int S, T, F, D, dmax, A;
+    unsigned short slot_tf[MAX_SLOTS];   // id slot -> index into ShardArgs::f
 };
 
-// one lane group per (slot, sample): packed gradient row in send order
-//   [ g_flat + g_field + g_fm * fm_sum  (d) , g_first , g_fm , 0 , 0 ]
-// The owner folds -(sum g_fm) * w[row] in at the end of the segment (e == w[row] for every member), so the
-// field embeddings are not re-read here.
+// one lane group per (sample, slot): packed gradient row in send order
+//   SPARSE  [ g_flat + g_field + g_fm * fm_sum  (d) , g_first , g_fm , 0 , 0 ]
+//           The owner folds -(sum g_fm) * w[row] in at the end of the segment (e == w[row] for every member),
+//           so the field embeddings are not re-read here.
+//   bag     [ scale * (g_flat + g_field + g_fm * (fm_sum - e_bag))  (d) , scale * g_first , 0 , 0 , 0 ]
+//           scale = 1 (sum) or 1 / count (mean); e_bag is the pooled row K1 wrote.
 template <int V>
 __global__ void __launch_bounds__(256)
 shard_pack_kernel(const __grid_constant__ ShardArgs a, const __grid_constant__ PackArgs p, int G,
@@ -74,8 +86,12 @@ shard_pack_kernel(const __grid_constant__ ShardArgs a, const __grid_constant__ P
     for (long long i = (long long)blockIdx.x * gpb + gl; i < n; i += (long long)gridDim.x * gpb) {
         const long long b = i / p.S;
         const int s = (int)(i - b * p.S);
-        const ShardField& sf = a.f[s];
-        const long long q = __ldg(p.pos + (long long)s * p.B + b);
+        const ShardField& sf = a.f[p.slot_tf[s]];
+        const long long q = __ldg(p.pos + p.B * sf.slot_base + b * sf.max_len + (s - sf.slot_base)) - 1;
+        if (q < 0) continue;                                   // padding entry of a bag: nothing was sent
+        float scale = 1.f;
+        if (sf.bag == 2) scale = __uint_as_float(__ldg(p.aux + (size_t)b * p.A + sf.aux_off));
+        const float m = p.g_fm ? __ldg(p.g_fm + b) : 0.f;
         if (j < sf.dim / V) {
             VecF<V> g = vzero<V>();
             if (p.g_flat) g = vload_stream<V>(p.g_flat + (size_t)b * p.T + sf.flat_off + j * V);
@@ -86,16 +102,25 @@ shard_pack_kernel(const __grid_constant__ ShardArgs a, const __grid_constant__ P
                 for (int v = 0; v < V; ++v) g.v[v] += t.v[v];
             }
             if (p.g_fm) {
-                const float m = __ldg(p.g_fm + b);
                 const VecF<V> sv = vload<V>(p.fm_sum + (size_t)b * p.D + j * V);
+                if (sf.bag) {
+                    const VecF<V> e = vload<V>(p.fe + eoff);
 #pragma unroll
-                for (int v = 0; v < V; ++v) g.v[v] = fmaf(m, sv.v[v], g.v[v]);
+                    for (int v = 0; v < V; ++v) g.v[v] = fmaf(m, sv.v[v] - e.v[v], g.v[v]);
+                } else {
+#pragma unroll
+                    for (int v = 0; v < V; ++v) g.v[v] = fmaf(m, sv.v[v], g.v[v]);
+                }
+            }
+            if (sf.bag == 2) {
+#pragma unroll
+                for (int v = 0; v < V; ++v) g.v[v] *= scale;
             }
             vstore_stream<V>(g_vec + (size_t)q * (p.dmax + 4) + j * V, g);
         }
         if (j == 0)
             *reinterpret_cast<float4*>(g_vec + (size_t)q * (p.dmax + 4) + p.dmax) =
-                make_float4(p.g_first ? __ldg(p.g_first + b) : 0.f, p.g_fm ? __ldg(p.g_fm + b) : 0.f, 0.f, 0.f);
+                make_float4((p.g_first ? __ldg(p.g_first + b) : 0.f) * scale, sf.bag ? 0.f : m, 0.f, 0.f);
     }
 }
 
@@ -104,25 +129,45 @@ shard_pack_kernel(const __grid_constant__ ShardArgs a, const __grid_constant__ P
 constexpr int RT_TILE = 2048;     // id slots per block
 constexpr int RT_MAXW = 16;       // ranks
 
+struct RouteField {
+    const long long* ids;   // (B,) or (B, max_len) id column
+    unsigned gbase;         // global row base (key = gbase + id)
+    int slot_base, max_len;
+    int bag;                // SEQUENCE: padding entries (id 0) are not sent
+};
 struct RouteArgs {
-    const long long* ids[MAX_FIELDS];   // per id slot: the field's id column (B,)
-    unsigned gbase[MAX_FIELDS];         // per id slot: global row base
+    RouteField f[MAX_FIELDS];            // table fields only
+    unsigned short slot_tf[MAX_SLOTS];   // id slot -> index into f
     int S, world;
     long long B;
 };
 
+// owner of id slot i = b * S + s (sample-major source order), -1 if nothing is sent for it
+__device__ __forceinline__ int route_owner(const RouteArgs& a, const RouteField* t, const unsigned short* slot_tf,
+                                           long long i, long long& b, int& s, long long& id, const RouteField*& rf) {
+    b = i / a.S; s = (int)(i - b * a.S);
+    rf = t + slot_tf[s];
+    id = __ldg(rf->ids + b * rf->max_len + (s - rf->slot_base));
+    if (rf->bag && id == 0) return -1;
+    return (int)(id % a.world);
+}
+
 __global__ void __launch_bounds__(256)
 route_count_kernel(const __grid_constant__ RouteArgs a, int* __restrict__ block_counts) {
     __shared__ int hist[RT_MAXW];
+    __shared__ RouteField t[MAX_FIELDS];
+    __shared__ unsigned short slot_tf[MAX_SLOTS];
     if (threadIdx.x < RT_MAXW) hist[threadIdx.x] = 0;
+    for (int q = threadIdx.x; q < MAX_FIELDS; q += 256) t[q] = a.f[q];
+    for (int q = threadIdx.x; q < a.S; q += 256) slot_tf[q] = a.slot_tf[q];
     __syncthreads();
     const long long n = a.B * a.S, i0 = (long long)blockIdx.x * RT_TILE;
-    for (int t = threadIdx.x; t < RT_TILE; t += 256) {
-        const long long i = i0 + t;
+    for (int c = threadIdx.x; c < RT_TILE; c += 256) {
+        const long long i = i0 + c;
         if (i >= n) break;
-        const long long b = i / a.S;
-        const int s = (int)(i - b * a.S);
-        atomicAdd(&hist[(int)(__ldg(a.ids[s] + b) % a.world)], 1);
+        long long b, id; int s; const RouteField* rf;
+        const int o = route_owner(a, t, slot_tf, i, b, s, id, rf);
+        if (o >= 0) atomicAdd(&hist[o], 1);
     }
     __syncthreads();
     if (threadIdx.x < RT_MAXW) block_counts[blockIdx.x * RT_MAXW + threadIdx.x] = hist[threadIdx.x];
@@ -148,22 +193,23 @@ __global__ void route_scan_kernel(const int* __restrict__ block_counts, int nblk
 
 __global__ void __launch_bounds__(256)
 route_scatter_kernel(const __grid_constant__ RouteArgs a, const long long* __restrict__ offsets, int nblk,
-                     uint32_t* __restrict__ send_keys, long long* __restrict__ pos_sb) {
+                     uint32_t* __restrict__ send_keys, long long* __restrict__ pos) {
     __shared__ long long run[RT_MAXW];
     __shared__ int warp_cnt[8][RT_MAXW];
+    __shared__ RouteField t[MAX_FIELDS];
+    __shared__ unsigned short slot_tf[MAX_SLOTS];
     const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
     if (threadIdx.x < a.world) run[threadIdx.x] = offsets[(size_t)threadIdx.x * nblk + blockIdx.x];
+    for (int q = threadIdx.x; q < MAX_FIELDS; q += 256) t[q] = a.f[q];
+    for (int q = threadIdx.x; q < a.S; q += 256) slot_tf[q] = a.slot_tf[q];
     const long long n = a.B * a.S, i0 = (long long)blockIdx.x * RT_TILE;
     for (int c = 0; c < RT_TILE; c += 256) {
         __syncthreads();
         const long long i = i0 + c + threadIdx.x;
         int o = -1, s = 0;
         long long b = 0, id = 0;
-        if (i < n) {
-            b = i / a.S; s = (int)(i - b * a.S);
-            id = __ldg(a.ids[s] + b);
-            o = (int)(id % a.world);
-        }
+        const RouteField* rf = t;
+        if (i < n) o = route_owner(a, t, slot_tf, i, b, s, id, rf);
         int rank = 0;
         for (int w = 0; w < a.world; ++w) {
             const unsigned m = __ballot_sync(0xffffffffu, o == w);
@@ -171,11 +217,14 @@ route_scatter_kernel(const __grid_constant__ RouteArgs a, const long long* __res
             if (lane == 0) warp_cnt[warp][w] = __popc(m);
         }
         __syncthreads();
-        if (o >= 0) {
-            long long q = run[o] + rank;
-            for (int w2 = 0; w2 < warp; ++w2) q += warp_cnt[w2][o];
-            send_keys[q] = a.gbase[s] + (uint32_t)id;
-            pos_sb[(long long)s * a.B + b] = q;
+        if (i < n) {
+            long long q = -1;
+            if (o >= 0) {
+                q = run[o] + rank;
+                for (int w2 = 0; w2 < warp; ++w2) q += warp_cnt[w2][o];
+                send_keys[q] = rf->gbase + (uint32_t)id;
+            }
+            pos[a.B * rf->slot_base + b * rf->max_len + (s - rf->slot_base)] = q + 1;   // 1-based, 0 = not sent
         }
         __syncthreads();
         if (threadIdx.x < a.world) {
@@ -196,9 +245,12 @@ static int fill_shard_args(const dfm_plan* local_plan, const int64_t* global_row
     a.world = world; a.rank = rank; a.dmax = local_plan->max_tdim; a.pad_local = (unsigned)local_plan->total_rows;
     int n = 0;
     for (int f = 0; f < local_plan->n_fields; ++f) {
-        if (local_plan->kind[f] == DFM_DENSE) continue;
-        if (local_plan->kind[f] != DFM_SPARSE || local_plan->dim[f] != local_plan->fm_dim || local_plan->dim[f] % 4) {
-            set_error("sharded tables support SPARSE fields with embedding_dim == fm_embed_dim, a multiple of 4 (field %d)", f);
+        const int k = local_plan->kind[f];
+        if (k == DFM_DENSE) continue;
+        if (local_plan->dim[f] != local_plan->fm_dim || local_plan->dim[f] % 4 ||
+            (k == DFM_SEQUENCE && local_plan->combiner[f] == DFM_MAX)) {
+            set_error("sharded tables support SPARSE and sum/mean SEQUENCE fields with embedding_dim == fm_embed_dim, "
+                      "a multiple of 4 (field %d)", f);
             return DFM_ERR_UNSUPPORTED;
         }
         ShardField& sf = a.f[n++];
@@ -210,9 +262,21 @@ static int fill_shard_args(const dfm_plan* local_plan, const int64_t* global_row
         sf.dim = local_plan->dim[f];
         sf.flat_off = local_plan->flat_off[f];
         sf.field = f;
+        sf.slot_base = local_plan->slot_base[f];
+        sf.max_len = local_plan->max_len[f];
+        sf.bag = k == DFM_SEQUENCE ? (local_plan->combiner[f] == DFM_MEAN ? 2 : 1) : 0;
+        sf.aux_off = local_plan->aux_off[f];
     }
     a.n = n;
     return DFM_OK;
+}
+
+// id slot -> index among the table (non-DENSE) fields
+static void fill_slot_tf(const dfm_plan* plan, unsigned short* slot_tf) {
+    std::vector<int> tf(plan->n_fields, 0);
+    int n = 0;
+    for (int f = 0; f < plan->n_fields; ++f) if (plan->kind[f] != DFM_DENSE) tf[f] = n++;
+    for (int s = 0; s < plan->S; ++s) slot_tf[s] = (unsigned short)tf[plan->slot_field[s]];
 }
 
 extern "C" {
@@ -243,22 +307,29 @@ int dfm_shard_gather(const dfm_plan* local_plan, int world, int rank, const int6
 
 int dfm_shard_pack_grad(const dfm_plan* plan, int64_t batch, const int64_t* positions, const float* g_first,
                         const float* g_field, const float* g_flat, const float* g_fm, const float* fm_sum,
-                        float* g_vec, void* stream) {
+                        const float* field_emb, const uint32_t* aux, float* g_vec, void* stream) {
     DFM_REQUIRE(plan && batch >= 0, DFM_ERR_INVALID, "dfm_shard_pack_grad: bad argument");
     if (batch == 0 || plan->S == 0) return DFM_OK;
     DFM_REQUIRE(positions && g_vec && (!g_fm || fm_sum), DFM_ERR_INVALID, "dfm_shard_pack_grad: null tensor");
     ShardArgs* a = new ShardArgs;
-    struct Gd { ShardArgs* p; ~Gd() { delete p; } } gd{a};
+    PackArgs* pp = new PackArgs;
+    struct Gd { ShardArgs* p; PackArgs* q; ~Gd() { delete p; delete q; } } gd{a, pp};
     std::vector<int64_t> zeros(plan->n_fields + 1, 0);
     int rc = fill_shard_args(plan, zeros.data(), nullptr, 1, 0, *a, false);
     if (rc) return rc;
-    DFM_REQUIRE(a->n == plan->S, DFM_ERR_UNSUPPORTED, "dfm_shard_pack_grad: one slot per table field expected");
-    PackArgs p;
-    p.g_first = g_first; p.g_field = g_field; p.g_flat = g_flat; p.g_fm = g_fm; p.fe = nullptr; p.fm_sum = fm_sum;
+    bool any_bag = false, any_mean = false;
+    for (int i = 0; i < a->n; ++i) { any_bag = any_bag || a->f[i].bag; any_mean = any_mean || a->f[i].bag == 2; }
+    DFM_REQUIRE(!any_bag || !g_fm || field_emb, DFM_ERR_INVALID, "dfm_shard_pack_grad: bag fields need the field embeddings for the FM gradient");
+    DFM_REQUIRE(!any_mean || aux, DFM_ERR_INVALID, "dfm_shard_pack_grad: mean bags need the aux record of the forward");
+    PackArgs& p = *pp;
+    memset(&p, 0, sizeof(p));
+    p.g_first = g_first; p.g_field = g_field; p.g_flat = g_flat; p.g_fm = g_fm; p.fe = field_emb; p.fm_sum = fm_sum;
+    p.aux = aux; p.A = plan->A;
     p.pos = reinterpret_cast<const long long*>(positions); p.B = batch; p.S = plan->S; p.T = plan->T;
     p.F = plan->n_fields; p.D = plan->fm_dim; p.dmax = plan->max_tdim;
+    fill_slot_tf(plan, p.slot_tf);
     auto al16 = [](const void* q) { return (reinterpret_cast<uintptr_t>(q) & 15u) == 0; };
-    const bool v4 = plan->vec == 4 && al16(g_flat) && al16(g_field) && al16(fm_sum) && al16(g_vec);
+    const bool v4 = plan->vec == 4 && al16(g_flat) && al16(g_field) && al16(fm_sum) && al16(g_vec) && al16(field_emb);
     const int lanes = p.dmax / (v4 ? 4 : 1);
     DFM_REQUIRE(lanes <= 32, DFM_ERR_UNSUPPORTED, "dfm_shard_pack_grad: table dim %d too wide", p.dmax);
     const int G = next_pow2(lanes);
@@ -291,12 +362,17 @@ int dfm_shard_route(const dfm_plan* plan, int world, const int64_t* global_row_b
     struct Gd { RouteArgs* p; ~Gd() { delete p; } } gd{a};
     memset(a, 0, sizeof(*a));
     a->S = plan->S; a->world = world; a->B = batch;
-    for (int s = 0; s < plan->S; ++s) {
-        const int f = plan->slot_field[s];
-        DFM_REQUIRE(plan->kind[f] == DFM_SPARSE && inputs[f], DFM_ERR_INVALID, "dfm_shard_route: field %d is not a SPARSE column", f);
-        a->ids[s] = static_cast<const long long*>(inputs[f]);
-        a->gbase[s] = (unsigned)global_row_base[f];
+    int nt = 0;
+    for (int f = 0; f < plan->n_fields; ++f) {
+        if (plan->kind[f] == DFM_DENSE) continue;
+        DFM_REQUIRE(inputs[f], DFM_ERR_INVALID, "dfm_shard_route: field %d has no id column", f);
+        RouteField& rf = a->f[nt++];
+        rf.ids = static_cast<const long long*>(inputs[f]);
+        rf.gbase = (unsigned)global_row_base[f];
+        rf.slot_base = plan->slot_base[f]; rf.max_len = plan->max_len[f];
+        rf.bag = plan->kind[f] == DFM_SEQUENCE ? 1 : 0;
     }
+    fill_slot_tf(plan, a->slot_tf);
     const int nblk = (int)ceil_div(n, RT_TILE);
     int* block_counts = static_cast<int*>(workspace);
     long long* offsets = reinterpret_cast<long long*>(static_cast<char*>(workspace) + align_up((size_t)nblk * RT_MAXW * 4, 256));

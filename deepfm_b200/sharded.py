@@ -13,8 +13,11 @@ rank ``r`` owns its ``b`` samples.  One step is
               so each row's gradient is produced on exactly one GPU: no allreduce of table gradients.
 
 Dense-field Linears and everything else (DNN, CIN, attention) are replicated and data-parallel;
-``allreduce_dense`` averages their gradients in one flat bucket.  Supported here: SPARSE and DENSE
-fields with ``embedding_dim == fm_embed_dim`` (the Criteo shapes); multi-hot bags are not sharded yet.
+``allreduce_dense`` averages their gradients in one flat bucket.  Supported here: SPARSE, DENSE and
+multi-hot SEQUENCE (sum / mean) fields with ``embedding_dim == fm_embed_dim`` (the Criteo shapes).
+A bag is exchanged id by id (padding entries are not sent), pooled by K1 on the sample's GPU with the
+bag's global non-pad count as the mean divisor, and every member's gradient row travels back to the
+row's owner, so the owner-side reduction is unchanged.
 
 The phases are plain methods so that a single process can emulate ``W`` ranks (tests) and so that
 the routing logic (pure torch ops) runs on CPU tensors under gloo.
@@ -46,22 +49,45 @@ def local_rows(vocab: int, world: int, rank: int) -> int:
 class Route:
     send_keys: torch.Tensor      # (n,) int32 (u32 bits): global rows in send order (grouped by owner)
     counts: torch.Tensor         # (W,) int64: keys per destination
-    order: torch.Tensor          # (n,) int64: send position -> slot index b*S + s
-    pos_sb: torch.Tensor         # (S, b) int64: slot -> send position
+    order: Optional[torch.Tensor]  # (n,) int64: send position -> source slot index b*S + s (torch path only)
+    pos: torch.Tensor            # (b*S,) int64, field-major: field f's (b, max_len) block at b * slot_base[f];
+    #                              1-based send position of every id slot, 0 = not sent (padding id of a bag)
 
 
-def route_ids(ids: torch.Tensor, row_base: torch.Tensor, world: int) -> Route:
-    """ids (b, S) int64, row_base (S,) int64.  Stable grouping by owner = id mod W (pure torch ops:
-    works on CPU and CUDA tensors; matches oracle.shard_route bit-exactly)."""
+def field_positions(pos: torch.Tensor, b: int, lens: Sequence[int]) -> List[torch.Tensor]:
+    """Per table field: its (b,) / (b, L) block of ``Route.pos`` (views, no copy) -- K1's id columns."""
+    out, s0 = [], 0
+    for L in lens:
+        blk = pos[b * s0: b * (s0 + L)]
+        out.append(blk.view(b, L) if L > 1 else blk)
+        s0 += L
+    return out
+
+
+def route_ids(ids: torch.Tensor, row_base: torch.Tensor, world: int, lens: Optional[Sequence[int]] = None,
+              bag: Optional[Sequence[bool]] = None) -> Route:
+    """ids (b, S) int64 (the id slots of one sample side by side, bags expanded), row_base (S,) int64 per slot,
+    lens / bag per table field (sum(lens) == S).  Stable grouping of the slots, in source order b*S + s, by
+    owner = id mod W; padding entries (id 0) of bag fields are not sent.  Pure torch ops: works on CPU and CUDA
+    tensors; matches oracle.shard_route bit-exactly."""
     b, S = ids.shape
-    owner = (ids % world).reshape(-1)
+    lens = [1] * S if lens is None else list(lens)
+    bag = [False] * len(lens) if bag is None else list(bag)
+    slot_bag = torch.tensor([g for L, g in zip(lens, bag) for _ in range(L)], dtype=torch.bool, device=ids.device)
+    sent = ~(slot_bag[None, :] & (ids == 0))
+    owner = torch.where(sent, ids % world, torch.full_like(ids, world)).reshape(-1)   # unsent slots sort last
+    n = int(sent.sum())
+    order = torch.sort(owner, stable=True).indices[:n]
+    counts = torch.bincount(owner, minlength=world + 1)[:world]
+    pos_flat = torch.zeros(b * S, dtype=torch.int64, device=ids.device)
+    pos_flat[order] = torch.arange(1, n + 1, device=ids.device, dtype=torch.int64)
+    pos_bs = pos_flat.view(b, S)
+    blocks, s0 = [], 0
+    for L in lens:
+        blocks.append(pos_bs[:, s0:s0 + L].reshape(-1))
+        s0 += L
     keys = (ids + row_base[None, :]).reshape(-1)
-    order = torch.sort(owner, stable=True).indices
-    counts = torch.bincount(owner, minlength=world)
-    pos = torch.empty_like(order)
-    pos[order] = torch.arange(order.numel(), device=order.device, dtype=order.dtype)
-    return Route(send_keys=keys[order].to(torch.int32), counts=counts, order=order,
-                 pos_sb=pos.view(b, S).t().contiguous())
+    return Route(send_keys=keys[order].to(torch.int32), counts=counts, order=order, pos=torch.cat(blocks))
 
 
 class TorchDistComm:
@@ -100,8 +126,10 @@ class TorchDistComm:
         mat = host.tolist()
         return mat[self.rank], [mat[src][self.rank] for src in range(self.world)]
 
-    def all_to_all(self, send: torch.Tensor, send_counts: Sequence[int], recv_counts: Sequence[int]) -> torch.Tensor:
-        out = send.new_empty((int(sum(recv_counts)),) + tuple(send.shape[1:]))
+    def all_to_all(self, send: torch.Tensor, send_counts: Sequence[int], recv_counts: Sequence[int],
+                   out: Optional[torch.Tensor] = None) -> torch.Tensor:
+        if out is None:
+            out = send.new_empty((int(sum(recv_counts)),) + tuple(send.shape[1:]))
         self.dist.all_to_all_single(out, send.contiguous(), list(recv_counts), list(send_counts), group=self.group)
         return out
 
@@ -118,16 +146,17 @@ class _ShardedEmbedFn(torch.autograd.Function):
         else:
             route = mod.route(inputs)
             send_counts, recv_counts = comm.exchange_counts(route.counts)     # the only host sync of the step
-        recv_keys = comm.all_to_all(route.send_keys, send_counts, recv_counts)
+        recv_keys = comm.all_to_all(route.send_keys[:int(sum(send_counts))], send_counts, recv_counts)
         rows, lkeys = mod.gather(recv_keys)
-        got = comm.all_to_all(rows, recv_counts, send_counts)              # (n, D + 4): vector + first-order weight
-        first, field, flat, fm, fm_sum, fin_inputs = mod.finish(inputs, route.pos_sb, got, need_bwd)
+        got = mod.reply_buffer(int(sum(send_counts)), rows)                # (1 + n, D + 4): zero row, then the replies
+        comm.all_to_all(rows, recv_counts, send_counts, out=got[1:])       # vector + first-order weight per row
+        first, field, flat, fm, fm_sum, aux, fin_inputs = mod.finish(inputs, route.pos, got, need_bwd)
         ctx.mod, ctx.n_inputs = mod, n_inputs
         ctx.counts = (send_counts, recv_counts)
         ctx.set_materialize_grads(False)
         ctx.l2, ctx.done = None, False
         if need_bwd:
-            ctx.save_for_backward(field, flat, fm_sum, route.pos_sb, lkeys, got, *fin_inputs, *params)
+            ctx.save_for_backward(field, flat, fm_sum, route.pos, lkeys, got, aux, *fin_inputs, *params)
             mod._live_ctx = weakref.ref(ctx)
         return first, field, flat, fm
 
@@ -135,16 +164,16 @@ class _ShardedEmbedFn(torch.autograd.Function):
     def backward(ctx, g_first, g_field, g_flat, g_fm):
         mod: ShardedFeatureEmbedding = ctx.mod
         saved = ctx.saved_tensors
-        field, flat, fm_sum, pos_sb, lkeys, got = saved[:6]
+        field, flat, fm_sum, pos, lkeys, got, aux = saved[:7]
         n_f = len(mod.field_names)
-        fin_inputs = saved[6:6 + n_f]
-        params = saved[6 + n_f:]
+        fin_inputs = saved[7:7 + n_f]
+        params = saved[7 + n_f:]
         send_counts, recv_counts = ctx.counts
         lam, gscale = ctx.l2 if ctx.l2 is not None else (0.0, None)
         ctx.done = True
         cont = lambda g: None if g is None else g.contiguous()
-        g_rows, dense_grads = mod.pack_grads(fin_inputs, pos_sb, got, cont(g_first), cont(g_field), cont(g_flat),
-                                             cont(g_fm), field, flat, fm_sum, params, lam, gscale)
+        g_rows, dense_grads = mod.pack_grads(fin_inputs, pos, got, cont(g_first), cont(g_field), cont(g_flat),
+                                             cont(g_fm), field, flat, fm_sum, params, lam, gscale, aux)
         g_recv = mod.comm.all_to_all(g_rows, send_counts, recv_counts)    # (M, D + 4): gradient row + scalars
         table_grads = mod.owner_backward(lkeys, g_recv, params, lam, gscale)
         grads = [dense_grads.get(i, table_grads.get(i)) for i in range(len(params))]
@@ -160,37 +189,50 @@ class ShardedFeatureEmbedding(nn.Module):
         self.second_order_embeddings = nn.ModuleDict()
         self.first_order_embeddings = nn.ModuleDict()
         self.projections = nn.ModuleDict()            # always empty here (dims == fm_embed_dim)
-        kinds, dims, vocabs, lvocabs = [], [], [], []
+        kinds, dims, vocabs, lvocabs, lens, combiners = [], [], [], [], [], []
         for name in self.field_names:
             fs = schema.fields[name]
             kind = kind_of(fs)
-            if kind not in ("sparse", "dense") or int(fs.embedding_dim) != fm_embed_dim:
+            comb = str(getattr(fs, "combiner", "mean") or "mean")
+            if int(fs.embedding_dim) != fm_embed_dim or (kind == "sequence" and comb not in ("sum", "mean")):
                 raise NotImplementedError(
-                    f"field {name!r}: sharded tables support SPARSE/DENSE fields with embedding_dim == fm_embed_dim")
+                    f"field {name!r}: sharded tables support SPARSE / DENSE / sum- or mean-pooled SEQUENCE fields "
+                    f"with embedding_dim == fm_embed_dim")
             d = int(fs.embedding_dim)
-            if kind == "sparse":
-                rows = local_rows(int(fs.vocabulary_size), world, rank)
-                self.second_order_embeddings[name] = nn.Embedding(rows, d)
-                self.first_order_embeddings[name] = nn.Embedding(rows, 1)
-                vocabs.append(int(fs.vocabulary_size))
-                lvocabs.append(rows)
-            else:
+            if kind == "dense":
                 self.second_order_embeddings[name] = nn.Linear(1, d)
                 self.first_order_embeddings[name] = nn.Linear(1, 1)
                 vocabs.append(0)
                 lvocabs.append(0)
+            else:
+                rows = local_rows(int(fs.vocabulary_size), world, rank)
+                if kind == "sparse":
+                    self.second_order_embeddings[name] = nn.Embedding(rows, d)
+                    self.first_order_embeddings[name] = nn.Embedding(rows, 1)
+                else:
+                    self.second_order_embeddings[name] = nn.EmbeddingBag(rows, d, mode=comb)
+                    self.first_order_embeddings[name] = nn.EmbeddingBag(rows, 1, mode=comb)
+                vocabs.append(int(fs.vocabulary_size))
+                lvocabs.append(rows)
             kinds.append(_lib.KIND[kind])
             dims.append(d)
+            lens.append(int(fs.max_length) if kind == "sequence" else 1)
+            combiners.append(_lib.COMBINER[comb] if kind == "sequence" else _lib.SUM)
         self._kinds, self._dims, self._vocabs, self._lvocabs = kinds, dims, vocabs, lvocabs
+        self._max_lens, self._combiners = lens, combiners
         self._init_weights()
         self.num_fields = len(kinds)
-        self._sparse_idx = [i for i, k in enumerate(kinds) if k == _lib.SPARSE]
-        self._S = len(self._sparse_idx)
+        self._table_idx = [i for i, k in enumerate(kinds) if k != _lib.DENSE]
+        self._sparse_idx = self._table_idx                      # historical name
+        self._lens = [lens[i] for i in self._table_idx]
+        self._bag = [kinds[i] == _lib.SEQUENCE for i in self._table_idx]
+        self._S = sum(self._lens)
+        self._A = sum(1 for i in self._table_idx if kinds[i] == _lib.SEQUENCE and combiners[i] == _lib.MEAN)
         self._T = sum(dims)
         grb, lrb = [0], [0]
         for k, v, lv in zip(kinds, vocabs, lvocabs):
-            grb.append(grb[-1] + (v if k == _lib.SPARSE else 0))
-            lrb.append(lrb[-1] + (lv if k == _lib.SPARSE else 0))
+            grb.append(grb[-1] + (v if k != _lib.DENSE else 0))
+            lrb.append(lrb[-1] + (lv if k != _lib.DENSE else 0))
         if grb[-1] >= 2 ** 31:
             raise NotImplementedError("sharded tables: total rows must stay below 2^31")
         self._global_row_base, self._row_base = grb, lrb
@@ -208,7 +250,7 @@ class ShardedFeatureEmbedding(nn.Module):
         """Same family as the reference (embedding.py:66-74): xavier-uniform rows, zero padding row
         (global id 0 lives on rank 0, local row 0), xavier Linears with zero bias."""
         for name, m in list(self.second_order_embeddings.items()) + list(self.first_order_embeddings.items()):
-            if isinstance(m, nn.Embedding):
+            if isinstance(m, (nn.Embedding, nn.EmbeddingBag)):
                 nn.init.xavier_uniform_(m.weight.data)
                 if self.rank == 0:
                     m.weight.data[0].zero_()
@@ -223,7 +265,7 @@ class ShardedFeatureEmbedding(nn.Module):
         for name in self.field_names:
             for mine, theirs in ((self.second_order_embeddings[name], full.second_order_embeddings[name]),
                                  (self.first_order_embeddings[name], full.first_order_embeddings[name])):
-                if isinstance(mine, nn.Embedding):
+                if isinstance(mine, (nn.Embedding, nn.EmbeddingBag)):
                     rows = theirs.weight[self.rank::self.world]
                     mine.weight[: rows.shape[0]].copy_(rows)
                 else:
@@ -235,17 +277,16 @@ class ShardedFeatureEmbedding(nn.Module):
         if self._plans is None:
             lib = _lib.lib()
             n = self.num_fields
-            ones, sums = [1] * n, [_lib.SUM] * n
 
             def make(vocabs):
                 p = lib.dfm_plan_create(n, _lib.i32_array(self._kinds), _lib.i32_array(self._dims),
-                                        _lib.i64_array(vocabs), _lib.i32_array(ones), _lib.i32_array(sums),
-                                        int(self.fm_embed_dim))
+                                        _lib.i64_array(vocabs), _lib.i32_array(self._max_lens),
+                                        _lib.i32_array(self._combiners), int(self.fm_embed_dim))
                 if not p:
                     raise ValueError(f"dfm_plan_create: {_lib.last_error()}")
                 return C.c_void_p(p)
-            cap = min(VIRTUAL_VOCAB, (2 ** 32 - 2) // max(self._S, 1))
-            virt = [cap if k == _lib.SPARSE else 0 for k in self._kinds]
+            self._virtual_cap = min(VIRTUAL_VOCAB, (2 ** 32 - 2) // max(len(self._table_idx), 1))
+            virt = [self._virtual_cap if k != _lib.DENSE else 0 for k in self._kinds]
             sample_plan = make(virt)
             _lib.check(lib.dfm_plan_set_table_stride(sample_plan, self.fm_embed_dim + 4, self.fm_embed_dim + 4),
                        "dfm_plan_set_table_stride")
@@ -285,24 +326,39 @@ class ShardedFeatureEmbedding(nn.Module):
 
     # -- phases -------------------------------------------------------------------------------
     def route(self, inputs: Sequence[torch.Tensor]) -> Route:
-        if inputs[self._sparse_idx[0]].is_cuda:                 # product path: the routing kernels
+        if inputs[self._table_idx[0]].is_cuda:                  # product path: the routing kernels
             lib = _lib.lib()
             _, sample_plan = self._ensure_plans()
             dev = inputs[0].device
             b, S, W = inputs[0].shape[0], self._S, self.world
             send_keys = torch.empty((b * S,), device=dev, dtype=torch.int32)
-            pos_sb = torch.empty((S, b), device=dev, dtype=torch.int64)
+            pos = torch.empty((b * S,), device=dev, dtype=torch.int64)
             counts = torch.empty((W,), device=dev, dtype=torch.int64)
             ws = torch.empty((max(lib.dfm_shard_route_workspace_bytes(sample_plan, b), 16),), device=dev, dtype=torch.uint8)
             _lib.check(lib.dfm_shard_route(sample_plan, W, _lib.i64_array(self._global_row_base), b, _lib.ptr_array(inputs),
-                                           _lib.ptr(send_keys), _lib.ptr(pos_sb), _lib.ptr(counts), ws.data_ptr(), ws.numel(),
+                                           _lib.ptr(send_keys), _lib.ptr(pos), _lib.ptr(counts), ws.data_ptr(), ws.numel(),
                                            _lib.stream_ptr()), "dfm_shard_route")
-            return Route(send_keys=send_keys, counts=counts, order=None, pos_sb=pos_sb)
-        ids = torch.stack([inputs[i] for i in self._sparse_idx], dim=1)   # CPU tensors: host-logic tests (gloo)
+            return Route(send_keys=send_keys, counts=counts, order=None, pos=pos)
+        return self.route_torch(inputs)
+
+    def route_torch(self, inputs: Sequence[torch.Tensor]) -> Route:
+        """The same routing in plain torch ops (CPU tensors under gloo; the restatement the GPU tests compare with)."""
+        b = inputs[0].shape[0]
+        ids = torch.cat([inputs[i].view(b, -1) for i in self._table_idx], dim=1)
         if self._rb_dev is None or self._rb_dev.device != ids.device:
-            self._rb_dev = torch.tensor([self._global_row_base[i] for i in self._sparse_idx], dtype=torch.int64,
-                                        device=ids.device)
-        return route_ids(ids, self._rb_dev, self.world)
+            self._rb_dev = torch.tensor([self._global_row_base[i] for i, L in zip(self._table_idx, self._lens) for _ in range(L)],
+                                        dtype=torch.int64, device=ids.device)
+        return route_ids(ids, self._rb_dev, self.world, self._lens, self._bag)
+
+    def reply_buffer(self, n: int, like: torch.Tensor) -> torch.Tensor:
+        """(1 + n, D + 4) buffer K1 reads as its table: row 0 is the reserved zero row (send positions are
+        1-based), rows 1.. receive the replies in send order."""
+        cap = getattr(self, "_virtual_cap", VIRTUAL_VOCAB)
+        if n + 1 > cap:
+            raise NotImplementedError(f"sharded tables: {n} exchanged rows per step exceed the plan capacity {cap}")
+        got = like.new_empty((n + 1, self.fm_embed_dim + 4))
+        got[0].zero_()
+        return got
 
     def gather(self, recv_keys: torch.Tensor):
         lib = _lib.lib()
@@ -318,7 +374,7 @@ class ShardedFeatureEmbedding(nn.Module):
         return rows, lkeys
 
     def _virtual_ptrs(self, params, got):
-        """Sample-side plan: every SPARSE table is the received row buffer (row stride D + 4, first-order
+        """Sample-side plan: every id table is the received row buffer (row stride D + 4, first-order
         weight at column D)."""
         arr = self._ptrs(params)
         D = self.fm_embed_dim
@@ -327,17 +383,18 @@ class ShardedFeatureEmbedding(nn.Module):
             arr[5 * i + 2] = got.data_ptr() + 4 * D
         return arr
 
-    def finish(self, inputs, pos_sb, got, need_bwd: bool):
+    def finish(self, inputs, pos, got, need_bwd: bool):
         lib = _lib.lib()
         _, sample_plan = self._ensure_plans()
         params = self._ordered_params()
         dev = got.device
         b = inputs[0].shape[0]
         F, D, T = self.num_fields, self.fm_embed_dim, self._T
+        blocks = field_positions(pos, b, self._lens)
         fin_inputs, s = [], 0
         for i in range(F):
-            if self._kinds[i] == _lib.SPARSE:
-                fin_inputs.append(pos_sb[s])
+            if self._kinds[i] != _lib.DENSE:
+                fin_inputs.append(blocks[s])
                 s += 1
             else:
                 fin_inputs.append(inputs[i])
@@ -346,23 +403,24 @@ class ShardedFeatureEmbedding(nn.Module):
         first = torch.empty((b, 1), device=dev, dtype=torch.float32)
         fm = torch.empty((b, 1), device=dev, dtype=torch.float32)
         fm_sum = torch.empty((b, D), device=dev, dtype=torch.float32) if need_bwd else None
+        aux = torch.empty((b, max(self._A, 1)), device=dev, dtype=torch.int32)
         _lib.check(lib.dfm_embed_fwd(sample_plan, b, _lib.ptr_array(fin_inputs), self._virtual_ptrs(params, got),
                                      first.data_ptr(), field.data_ptr(), flat.data_ptr(), fm.data_ptr(),
-                                     _lib.ptr(fm_sum), None, None, None, _lib.stream_ptr()), "dfm_embed_fwd")
-        return first, field, flat, fm, fm_sum, fin_inputs
+                                     _lib.ptr(fm_sum), None, aux.data_ptr(), None, _lib.stream_ptr()), "dfm_embed_fwd")
+        return first, field, flat, fm, fm_sum, aux, fin_inputs
 
-    def pack_grads(self, fin_inputs, pos_sb, got, g_first, g_field, g_flat, g_fm, field, flat, fm_sum,
-                   params, lam, gscale):
+    def pack_grads(self, fin_inputs, pos, got, g_first, g_field, g_flat, g_fm, field, flat, fm_sum,
+                   params, lam, gscale, aux=None):
         lib = _lib.lib()
         _, sample_plan = self._ensure_plans()
         self._ordered_params()
         dev = flat.device
         b = flat.shape[0]
-        n = b * self._S
+        n = got.shape[0] - 1
         g_rows = torch.empty((n, self.fm_embed_dim + 4), device=dev, dtype=torch.float32)
-        _lib.check(lib.dfm_shard_pack_grad(sample_plan, b, _lib.ptr(pos_sb), _lib.ptr(g_first), _lib.ptr(g_field),
-                                           _lib.ptr(g_flat), _lib.ptr(g_fm), _lib.ptr(fm_sum), _lib.ptr(g_rows),
-                                           _lib.stream_ptr()), "dfm_shard_pack_grad")
+        _lib.check(lib.dfm_shard_pack_grad(sample_plan, b, _lib.ptr(pos), _lib.ptr(g_first), _lib.ptr(g_field),
+                                           _lib.ptr(g_flat), _lib.ptr(g_fm), _lib.ptr(fm_sum), field.data_ptr(),
+                                           _lib.ptr(aux), _lib.ptr(g_rows), _lib.stream_ptr()), "dfm_shard_pack_grad")
         # DENSE-field Linear gradients (data-parallel parameters): K2 with the table part skipped
         dense_grads: Dict[int, torch.Tensor] = {}
         grads = []
@@ -376,7 +434,7 @@ class ShardedFeatureEmbedding(nn.Module):
             _lib.check(lib.dfm_embed_bwd(
                 sample_plan, b, _lib.ptr_array(fin_inputs), self._virtual_ptrs(params, got),
                 _lib.ptr(g_first), _lib.ptr(g_field), _lib.ptr(g_flat), _lib.ptr(g_fm), field.data_ptr(), flat.data_ptr(),
-                _lib.ptr(fm_sum), None, None, float(lam), _lib.ptr(gscale), _lib.GRAD_SKIP_TABLES, self._ptrs(grads),
+                _lib.ptr(fm_sum), None, _lib.ptr(aux), float(lam), _lib.ptr(gscale), _lib.GRAD_SKIP_TABLES, self._ptrs(grads),
                 None, None, None, None, None, ws.data_ptr(), ws.numel(), _lib.stream_ptr()), "dfm_embed_bwd")
         return g_rows, dense_grads
 
@@ -434,7 +492,12 @@ class ShardedFeatureEmbedding(nn.Module):
         for i, name in enumerate(self.field_names):
             x = _lib.require_cuda(batch[name], f"batch[{name!r}]")
             x = x.float() if self._kinds[i] == _lib.DENSE else x.long()
-            out.append(x.reshape(x.shape[0]).contiguous())
+            if self._kinds[i] == _lib.SEQUENCE:
+                if x.dim() != 2 or x.shape[1] != self._max_lens[i]:
+                    raise ValueError(f"batch[{name!r}]: expected (B, {self._max_lens[i]}) ids, got {tuple(x.shape)}")
+                out.append(x.contiguous())
+            else:
+                out.append(x.reshape(x.shape[0]).contiguous())
         return out
 
     def forward_fused(self, batch):

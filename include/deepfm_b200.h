@@ -200,15 +200,22 @@ DFM_API int dfm_attn_bwd(const float* x, const float* g_out, int64_t batch, int 
  * vector gradients is issued by the host side between these calls.
  *   Exchanged rows are d_max + 4 floats wide (16-byte aligned): one collective carries the vector and
  *   its scalars.
- *   dfm_shard_route : sample side.  Stable grouping of the B*S id slots by owner: send_keys (B*S)
- *       global rows in send order, positions (S, B) send position of every slot, counts (W).
+ *   dfm_shard_route : sample side.  Stable grouping of the B*S id slots (source order b*S + s) by
+ *       owner: send_keys (<= B*S) global rows in send order, counts (W), and positions: for field f
+ *       the (B, max_len[f]) block at offset B * slot_base[f] holds the 1-based send position of every
+ *       slot (0 = nothing sent: a padding id of a multi-hot bag; the padding id of a SPARSE field IS
+ *       sent, its row 0 is returned as stored).  The blocks are K1's id columns of the sample-side plan.
  *   dfm_shard_gather : owner side.  keys = global rows (row_base[f] + id) as received; writes the
  *       reply rows [row (d), first-order weight, 0, 0, 0] and the local sort keys
  *       (local_row_base[f] + local_row, PAD for id 0) the owner-side backward consumes.
- *   dfm_plan_set_table_stride : lets K1 (dfm_embed_fwd) read every plain SPARSE table with a row
- *       stride != dim, i.e. straight out of the received reply rows (first-order at column d).
- *   dfm_shard_pack_grad : sample side.  positions (S, B) as above; writes the gradient rows
- *       [g_flat + g_field + g_fm * fm_sum (d), g_first, g_fm, 0, 0] in send order.
+ *   dfm_plan_set_table_stride : lets K1 (dfm_embed_fwd) read every plain SPARSE / sum- or mean-bag
+ *       table with a row stride != dim, i.e. straight out of the received reply rows (row 0 of that
+ *       buffer is a reserved zero row, reply i is row i + 1; first-order at column d).
+ *   dfm_shard_pack_grad : sample side.  positions as above; writes the gradient rows in send order:
+ *       SPARSE [g_flat + g_field + g_fm * fm_sum (d), g_first, g_fm, 0, 0];  bag member
+ *       [scale * (g_flat + g_field + g_fm * (fm_sum - e_bag)) (d), scale * g_first, 0, 0, 0] with
+ *       scale = 1 (sum) or 1 / non-pad count (mean, from the forward's aux record); field_emb / aux
+ *       may be null when the plan has no bag fields.
  *   dfm_rows_bwd : owner side backward = K2 on a row list: keys (n) with one packed gradient row
  *       each; same sort / segreduce / stitch kernels and modes as dfm_embed_bwd, the field is
  *       derived from the key and -(sum g_fm) w[row] + 2 l2 w[row] is folded in at the segment end.
@@ -224,7 +231,8 @@ DFM_API int dfm_shard_gather(const dfm_plan* local_plan, int world, int rank,
                              void* stream);
 DFM_API int dfm_shard_pack_grad(const dfm_plan* plan, int64_t batch, const int64_t* positions,
                                 const float* g_first, const float* g_field, const float* g_flat,
-                                const float* g_fm, const float* fm_sum, float* g_rows, void* stream);
+                                const float* g_fm, const float* fm_sum, const float* field_emb,
+                                const uint32_t* aux, float* g_rows, void* stream);
 DFM_API int dfm_plan_set_table_stride(dfm_plan* plan, int row_stride, int w1_stride);
 DFM_API size_t dfm_rows_bwd_workspace_bytes(const dfm_plan* plan, int64_t n_rows);
 DFM_API int dfm_rows_bwd(const dfm_plan* plan, int64_t n_rows, const float* const* params,

@@ -289,6 +289,24 @@ def cin_forward(x0: np.ndarray, weights: List[np.ndarray], biases: List[np.ndarr
     return (out, saved) if keep else out
 
 
+def cin_relu_margin(x0, weights, biases, split_half) -> float:
+    """Smallest |pre-activation| over all layers.  A pre-activation closer to zero than the fp32 rounding of
+    the contraction can land on the other side of the ReLU (cin.py:91) in an fp32 implementation, which changes
+    its gradient by a whole term; tests draw inputs whose margin is clear of that."""
+    B, F, D = x0.shape
+    n = len(weights)
+    direct, _, _ = cin_plan(F, [w.shape[0] for w in weights], split_half)
+    hidden, margin = x0, np.inf
+    for i in range(n):
+        H = hidden.shape[1]
+        z = (hidden[:, :, None, :] * x0[:, None, :, :]).reshape(B, H * F, D)
+        pre = np.einsum("lk,bkd->bld", weights[i], z) + biases[i][None, :, None]
+        margin = min(margin, float(np.abs(pre).min()))
+        act = np.maximum(pre, 0)
+        hidden = act[:, direct[i]:] if (split_half and i < n - 1) else act
+    return margin
+
+
 def cin_backward(x0, weights, biases, split_half, g_out):
     """Gradients of CIN.forward w.r.t. x0, every conv weight and bias.
 
@@ -467,20 +485,40 @@ def segment_heads(sorted_keys: np.ndarray):
     return k[head], np.concatenate([starts, [n_valid]])
 
 
-def shard_route(ids: np.ndarray, world: int):
+def shard_route(ids: np.ndarray, world: int, sent: Optional[np.ndarray] = None):
     """Row sharding rule: owner = id mod W, local_row = id div W  (SURVEY 8(e)).
 
-    ids: flat int64 array in source order.  Returns (owner, local_row, counts (W,),
-    offsets (W+1,), perm) where perm is the stable permutation that groups ids by owner
-    (position i of the send buffer holds ids[perm[i]]).
+    ids: flat int64 array in source order (slot index b*S + s, multi-hot bags expanded to their
+    max_length slots).  sent: optional bool mask; False marks slots that are not exchanged -- the
+    padding entries (id 0) of EmbeddingBag fields, which the reference skips wherever they occur
+    (embedding.py:41-50, padding_idx=0).  Returns (owner, local_row, counts (W,), offsets (W+1,), perm)
+    where perm is the stable permutation that groups the SENT slots by owner (position i of the send
+    buffer holds ids[perm[i]]).
     """
     owner = (ids % world).astype(np.int64)
     local = (ids // world).astype(np.int64)
-    counts = np.bincount(owner, minlength=world).astype(np.int64)
+    if sent is None:
+        sent = np.ones(ids.shape, dtype=bool)
+    key = np.where(sent, owner, world)
+    counts = np.bincount(key, minlength=world + 1).astype(np.int64)[:world]
     offsets = np.zeros(world + 1, dtype=np.int64)
     np.cumsum(counts, out=offsets[1:])
-    perm = np.argsort(owner, kind="stable").astype(np.int64)
+    perm = np.argsort(key, kind="stable").astype(np.int64)[: int(sent.sum())]
     return owner, local, counts, offsets, perm
+
+
+def shard_positions(perm: np.ndarray, b: int, lens: Sequence[int]) -> np.ndarray:
+    """1-based send position of every id slot in the field-major layout the kernels use: field f's
+    (b, L_f) block starts at b * slot_base[f]; 0 = not sent."""
+    S = int(sum(lens))
+    pos = np.zeros(b * S, dtype=np.int64)
+    pos[perm] = np.arange(1, perm.size + 1)
+    pos = pos.reshape(b, S)
+    out, s0 = [], 0
+    for L in lens:
+        out.append(pos[:, s0:s0 + L].reshape(-1))
+        s0 += L
+    return np.concatenate(out)
 
 
 # --------------------------------------------------------------------------------------

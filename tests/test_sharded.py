@@ -12,7 +12,7 @@ import torch
 import torch.multiprocessing as mp
 
 from deepfm_b200.schema import DatasetSchema, FeatureType, FieldSchema
-from deepfm_b200.sharded import Route, local_rows, route_ids
+from deepfm_b200.sharded import Route, field_positions, local_rows, route_ids
 from oracle import deepfm_oracle as O
 from tests.helpers import assert_close_rel
 
@@ -29,12 +29,45 @@ def test_route_ids_matches_oracle_shard_route():
     assert r.order.tolist() == perm.tolist()
     keys = (ids + row_base[None, :]).reshape(-1)
     assert r.send_keys.tolist() == keys[perm].tolist()
-    pos = r.pos_sb.t().reshape(-1).numpy()                       # slot index -> send position
-    assert np.array_equal(perm[pos], np.arange(b * S))
+    pos = r.pos.view(S, b).t().reshape(-1).numpy()               # slot index -> 1-based send position
+    assert np.array_equal(perm[pos - 1], np.arange(b * S))
+    assert np.array_equal(r.pos.numpy(), O.shard_positions(perm, b, [1] * S))
     for w in range(W):                                            # every key of bucket w is owned by w
         seg = perm[offsets[w]:offsets[w + 1]]
         assert np.all(ids.reshape(-1)[seg] % W == w)
     assert local_rows(10, 4, 0) == 3 and local_rows(10, 4, 1) == 3 and local_rows(10, 4, 2) == 2 and local_rows(2, 4, 3) == 1
+
+
+def test_route_ids_multihot_skips_bag_padding():
+    """Bags are exchanged id by id; their padding entries (id 0, anywhere in the bag) are not sent, while the
+    padding id of a SPARSE field is (its row 0 is returned as stored, embedding.py:35-40)."""
+    rng = np.random.default_rng(1)
+    b, W = 41, 3
+    lens, bag, vocab = [1, 4, 1, 6], [False, True, False, True], [30, 17, 5, 200]
+    cols = []
+    for L, g, v in zip(lens, bag, vocab):
+        x = rng.integers(0, v, (b, L))
+        if g:
+            x = x * (rng.random((b, L)) < 0.6)             # pads in the middle of the bag too
+            x[3] = 0                                       # an all-pad bag
+        cols.append(x)
+    ids = np.concatenate(cols, axis=1).astype(np.int64)
+    S = ids.shape[1]
+    fbase = np.concatenate([[0], np.cumsum(vocab)[:-1]])
+    row_base = np.repeat(fbase, lens).astype(np.int64)
+    slot_bag = np.repeat(bag, lens)
+    sent = ~(slot_bag[None, :] & (ids == 0))
+    r = route_ids(torch.from_numpy(ids), torch.from_numpy(row_base), W, lens, bag)
+    owner, local, counts, offsets, perm = O.shard_route(ids.reshape(-1), W, sent.reshape(-1))
+    assert r.counts.tolist() == counts.tolist() and int(counts.sum()) == int(sent.sum())
+    assert r.order.tolist() == perm.tolist()
+    keys = (ids + row_base[None, :]).reshape(-1)
+    assert r.send_keys.tolist() == keys[perm].tolist()
+    assert np.array_equal(r.pos.numpy(), O.shard_positions(perm, b, lens))
+    blocks = field_positions(r.pos, b, lens)
+    assert [tuple(t.shape) for t in blocks] == [(b,), (b, 4), (b,), (b, 6)]
+    assert torch.equal(blocks[1] == 0, torch.from_numpy(cols[1] == 0))      # exactly the pads are unsent
+    assert bool((blocks[0] > 0).all())                                       # SPARSE id 0 still travels
 
 
 def _gloo_worker(rank, world, port, out):
@@ -58,7 +91,7 @@ def _gloo_worker(rank, world, port, out):
     # reply with a function of the key; the sender must get it back in send order
     reply = comm.all_to_all((k * 3 + 1).float()[:, None].repeat(1, 2), recv_counts, send_counts)
     ok_reply = bool(torch.equal(reply[:, 0], r.send_keys.float() * 3 + 1))
-    back = reply[:, 0][r.pos_sb.t().reshape(-1)]                  # slot order
+    back = reply[:, 0][r.pos.view(3, 20).t().reshape(-1) - 1]     # slot order
     ok_slot = bool(torch.equal(back, ((ids + row_base[None, :]).reshape(-1) * 3 + 1).float()))
     out.put((rank, ok_owner, ok_reply, ok_slot, sum(recv_counts)))
     dist.destroy_process_group()
@@ -81,12 +114,16 @@ def test_all_to_all_plumbing_gloo_world2():
 
 # ------------------------------------------------------------------------------------------ GPU
 
-def _schema(D):
+def _schema(D, multihot=False):
     fields = {}
     for i in range(3):
         fields[f"d{i}"] = FieldSchema(f"d{i}", FeatureType.DENSE, embedding_dim=D)
     for i, v in enumerate((50, 2000, 7, 301, 11)):
         fields[f"s{i}"] = FieldSchema(f"s{i}", FeatureType.SPARSE, vocabulary_size=v, embedding_dim=D)
+    if multihot:
+        for i, (v, L, comb) in enumerate(((40, 5, "mean"), (3000, 16, "sum"), (9, 3, "mean"))):
+            fields[f"q{i}"] = FieldSchema(f"q{i}", FeatureType.SEQUENCE, vocabulary_size=v, embedding_dim=D,
+                                          max_length=L, combiner=comb)
     return DatasetSchema(fields=fields)
 
 
@@ -107,15 +144,15 @@ def _exchange(bufs, counts, reverse=False):
 
 
 @pytest.mark.gpu
-@pytest.mark.parametrize("W,D", [(2, 16), (3, 64)])
-def test_sharded_equals_unsharded_emulated_ranks(W, D):
+@pytest.mark.parametrize("W,D,multihot", [(2, 16, False), (3, 64, False), (2, 64, True), (4, 16, True)])
+def test_sharded_equals_unsharded_emulated_ranks(W, D, multihot):
     from deepfm_b200.layers.embedding import FeatureEmbedding
     from deepfm_b200.layers.fm import FMInteraction
     from deepfm_b200.layers.l2 import l2_penalty
     from deepfm_b200.sharded import ShardedFeatureEmbedding
     torch.manual_seed(0)
     rng = np.random.default_rng(W * D)
-    schema = _schema(D)
+    schema = _schema(D, multihot)
     b, lam = 301, 1e-3
     full = FeatureEmbedding(schema, D).cuda()
     with torch.no_grad():
@@ -127,6 +164,11 @@ def test_sharded_equals_unsharded_emulated_ranks(W, D):
         for n, f in schema.fields.items():
             if f.feature_type == FeatureType.DENSE:
                 bt[n] = torch.from_numpy(rng.uniform(-1, 1, b).astype(np.float32)).cuda()
+            elif f.feature_type == FeatureType.SEQUENCE:
+                x = (rng.zipf(1.3, (b, f.max_length)) - 1) % f.vocabulary_size
+                x = x * (rng.random((b, f.max_length)) < 0.6)      # pads anywhere in the bag
+                x[5] = 0                                           # an all-pad bag
+                bt[n] = torch.from_numpy(x.astype(np.int64)).cuda()
             else:
                 bt[n] = torch.from_numpy(((rng.zipf(1.3, b) - 1) % f.vocabulary_size).astype(np.int64)).cuda()
         batches.append(bt)
@@ -148,13 +190,18 @@ def test_sharded_equals_unsharded_emulated_ranks(W, D):
     counts = [r.counts.tolist() for r in routes]
     recv_keys = _exchange([r.send_keys for r in routes], counts)
     for m, x, r in zip(mods, ins, routes):          # routing kernels == the torch restatement, bit-exactly
-        ref = route_ids(torch.stack([x[i] for i in m._sparse_idx], dim=1),
-                        torch.tensor([m._global_row_base[i] for i in m._sparse_idx], device="cuda"), W)
-        assert torch.equal(r.send_keys, ref.send_keys) and torch.equal(r.pos_sb, ref.pos_sb)
+        ref = m.route_torch(x)
+        n_sent = int(ref.counts.sum())
         assert torch.equal(r.counts, ref.counts)
+        assert torch.equal(r.send_keys[:n_sent], ref.send_keys) and torch.equal(r.pos, ref.pos)
+        r.send_keys = r.send_keys[:n_sent]
     gathered = [m.gather(k) for m, k in zip(mods, recv_keys)]
     got = _exchange([g[0] for g in gathered], counts, reverse=True)
-    outs = [m.finish(x, r.pos_sb, v, True) for m, x, r, v in zip(mods, ins, routes, got)]
+    for i, (m, v) in enumerate(zip(mods, got)):     # row 0 of the reply buffer is the reserved zero row
+        buf = m.reply_buffer(v.shape[0], v)
+        buf[1:] = v
+        got[i] = buf
+    outs = [m.finish(x, r.pos, v, True) for m, x, r, v in zip(mods, ins, routes, got)]
     assert torch.equal(torch.cat([o[0] for o in outs]), fo.detach())      # same rows, same order: bit-identical
     assert torch.equal(torch.cat([o[2] for o in outs]), fl.detach())
     assert torch.equal(torch.cat([o[3] for o in outs]), fm.detach())
@@ -164,8 +211,9 @@ def test_sharded_equals_unsharded_emulated_ranks(W, D):
     for r, (m, o) in enumerate(zip(mods, outs)):
         sl = slice(r * b, (r + 1) * b)
         params = m._ordered_params()
-        packed.append(m.pack_grads(o[5], routes[r].pos_sb, got[r], g_first[sl].contiguous(), None,
-                                   g_flat[sl].contiguous(), g_fm[sl].contiguous(), o[1], o[2], o[4], params, lam / W, gscale))
+        packed.append(m.pack_grads(o[6], routes[r].pos, got[r], g_first[sl].contiguous(), None,
+                                   g_flat[sl].contiguous(), g_fm[sl].contiguous(), o[1], o[2], o[4], params, lam / W, gscale,
+                                   o[5]))
     g_recv = _exchange([p[0] for p in packed], counts)
     for r, m in enumerate(mods):
         params = m._ordered_params()
