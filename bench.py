@@ -12,7 +12,11 @@ A step is the reference trainer's forward + loss + backward (trainer.py:219-229)
 `e2e`    : the same step through the public module API with the batch in pinned HOST memory, the
            host->device copies and the loss.item() read inside the timed region.
 `roofline`: the fused embedding+FM forward kernel (K1), algorithmic bytes / CUDA-event time of the
-           C-ABI call, against MEASURED_PEAKS.json.
+           C-ABI call, against MEASURED_PEAKS.json.  `roofline_bwd`: the backward (K2) the same way; its
+           algorithmic bytes use the number of UNIQUE rows the batch touched (counted by the kernel), the
+           all-rows-unique bound of SURVEY 8(d) is given next to it.
+`--workload`: the other BASELINE.json configs as secondary lines (same JSON shape, `config.workload` names
+           them): xdeepfm_criteo_multihot (config 5; tables sized 125 M rows per GPU), xdeepfm_ml, attention_ml.
 `cpu_baseline` / `--impl reference`: the reference's own PyTorch-CPU code path (oracle/torch_port.py:
            the same ATen ops in the same order; the reference package itself cannot travel to the
            GPU box) on a bounded sample of the same workload, all host cores.
@@ -42,11 +46,35 @@ CPU_SAMPLE_BATCH = 8192
 CPU_SAMPLE_MAX_VOCAB = 1_000_000
 
 
-def bench_config():
+WORKLOADS = {
+    # name: (model, description)
+    "deepfm_criteo": ("deepfm", WORKLOAD),
+    "xdeepfm_criteo_multihot": ("xdeepfm", "xdeepfm_criteo_13dense_26multihot_avg8_d64_cin128x128_b{B}_per_gpu"),
+    "xdeepfm_ml": ("xdeepfm", "xdeepfm_ml100k_shape_cin128x128x64_b65536"),
+    "attention_ml": ("attention_deepfm", "attention_deepfm_ml100k_shape_4heads_a64_b65536"),
+}
+MULTIHOT_ROWS_PER_GPU = 125_000_000     # config 5: 1 B rows over 8 GPUs (32 GB of tables per GPU)
+MULTIHOT_BATCH = 16384                  # per GPU: CIN [128,128] at F = 39, D = 64 is 197 MFLOP per sample
+
+
+def bench_config(workload: str = "deepfm_criteo"):
     from deepfm_b200.config import ExperimentConfig
     cfg = ExperimentConfig()
-    cfg.feature.fm_embed_dim = EMBED_DIM
+    if workload in ("deepfm_criteo", "xdeepfm_criteo_multihot"):
+        cfg.feature.fm_embed_dim = EMBED_DIM
+    if workload == "xdeepfm_ml":
+        cfg.cin.layer_sizes = [128, 128, 64]          # configs/xdeepfm_movielens_cin_tuned.yaml
     return cfg
+
+
+def workload_schema(workload: str, n_gpus: int):
+    from deepfm_b200 import workloads as W
+    if workload == "deepfm_criteo":
+        return W.criteo_schema(EMBED_DIM), BATCH
+    if workload == "xdeepfm_criteo_multihot":
+        scale = MULTIHOT_ROWS_PER_GPU * n_gpus / float(sum(W.CRITEO_VOCAB))
+        return W.criteo_multihot_schema(EMBED_DIM, max_length=16, vocab_scale=scale), MULTIHOT_BATCH
+    return W.ml100k_schema(), BATCH
 
 
 def base_line(args, n_gpus):
@@ -159,9 +187,12 @@ def run_ours(args, rank: int, local_rank: int, n_gpus: int):
     if n_gpus > 1:
         dist.init_process_group("nccl", device_id=dev)
     torch.manual_seed(1234)                      # identical replicas of the dense parameters
-    schema = W.criteo_schema(EMBED_DIM)
-    cfg = bench_config()
-    if n_gpus > 1:
+    wl = args.workload
+    model_name = WORKLOADS[wl][0]
+    schema, BATCH = workload_schema(wl, n_gpus)
+    cfg = bench_config(wl)
+    sharded = n_gpus > 1 and wl in ("deepfm_criteo", "xdeepfm_criteo_multihot")
+    if sharded:
         # tables row-sharded over the ranks (all-to-all of looked-up vectors and their gradients),
         # everything else replicated and data-parallel (one flat NCCL allreduce)
         from deepfm_b200 import models as M
@@ -170,9 +201,11 @@ def run_ours(args, rank: int, local_rank: int, n_gpus: int):
         M.BaseCTRModel.embedding_factory = staticmethod(
             lambda schema, fm_embed_dim: ShardedFeatureEmbedding(schema, fm_embed_dim, n_gpus, rank, comm))
     with torch.device(dev):
-        model = create_model("deepfm", schema, cfg)
+        model = create_model(model_name, schema, cfg)
     model.train()
     model.embedding.grad_mode = "row_sparse"
+    if model_name == "xdeepfm" and args.cin_precision:
+        model.cin.precision = args.cin_precision
     emb = model.embedding
     ordered = emb._ordered_params()
     table_ids = {id(p) for p, is_table in zip(ordered, emb._param_is_table) if is_table}
@@ -199,7 +232,7 @@ def run_ours(args, rank: int, local_rank: int, n_gpus: int):
         loss = bce(logits, labels) + model.get_l2_reg_loss()
         loss.backward()
         allreduce_dense()
-        if next_batch is not None and n_gpus > 1:
+        if next_batch is not None and sharded:
             model.embedding.prefetch(next_batch)      # input pipeline: route the next batch behind this step
         return loss
 
@@ -276,9 +309,28 @@ def run_ours(args, rank: int, local_rank: int, n_gpus: int):
         pass
     hbm_peak = float(peaks.get("hbm_gbs", 6650.0))
     peak_src = "measured (MEASURED_PEAKS.json)" if "hbm_gbs" in peaks else "fallback 6650 GB/s"
-    k2_bytes = 33_500 * BATCH                                     # SURVEY 8(d) upper bound, all rows unique
+    # K2 algorithmic bytes with the MEASURED unique-row count U of the last batch:
+    #   g_flat read once 4T B/sample, sorted key + payload read by the reduction 8 B/slot, per unique row one
+    #   table-row read (FM fold + L2) and one gradient-row write (4d each) + the two first-order scalars;
+    #   the radix sort's own passes (CUB, 4 x (read + write) of 8 B/slot) are reported separately.
+    n_slots, n_unique = BATCH * 26, None
+    rg = getattr(model.embedding, "row_grads", None)
+    if rg is not None:
+        n_slots, n_unique = [int(v) for v in rg.counts.tolist()]
+    T_ = schema.total_embedding_dim
+    k2_bytes_bound = 33_500 * BATCH                               # all rows unique
+    k2_bytes = BATCH * 4 * T_ + n_slots * 8 + (n_unique if n_unique is not None else n_slots) * (8 * EMBED_DIM + 8)
+    k2_sort_bytes = n_slots * 8 * 2 * 4
     ms_step = total_ms / K_
     line = base_line(args, n_gpus)
+    if wl != "deepfm_criteo":
+        line["config"] = {"workload": WORKLOADS[wl][1].format(B=BATCH), "model": model_name, "batch_per_gpu": BATCH,
+                          "global_batch": BATCH * n_gpus, "embed_dim": cfg.feature.fm_embed_dim,
+                          "table_rows": int(sum(f.vocabulary_size for f in schema.fields.values())),
+                          "cin": getattr(model, "cin", None) and model.cin.layer_sizes,
+                          "cin_precision": getattr(model, "cin", None) and model.cin.precision,
+                          "parallelism": line["config"]["parallelism"] if sharded else f"dp{n_gpus}",
+                          "note": "secondary line: not the workload BASELINE.json's metric is quoted on"}
     line.update({
         "value": BATCH * n_gpus / (ms_step * 1e-3), "ms_per_step": ms_step, "warmup": W_,
         "clocks": clocks,
@@ -286,7 +338,7 @@ def run_ours(args, rank: int, local_rank: int, n_gpus: int):
                 "h2d_bytes_per_step": h2d, "d2h_bytes_per_step": 4},
         "gpu_launches": (launches or 0) * K_,
     })
-    if k1_ms:
+    if k1_ms and wl == "deepfm_criteo":
         k1_gbs = K1_BYTES_PER_SAMPLE * BATCH / (k1_ms * 1e-3) / 1e9
         line["roofline"] = {"kernel": "dfm::embed_fwd_kernel<4> (K1: gather+pool+FM forward)", "bound": "hbm",
                             "achieved": k1_gbs, "peak": hbm_peak, "unit": "GB/s", "frac": k1_gbs / hbm_peak,
@@ -296,11 +348,16 @@ def run_ours(args, rank: int, local_rank: int, n_gpus: int):
         line["roofline_bwd"] = {"kernel": "K2 = sort + segreduce + stitch + dense_stream (dfm_embed_bwd)", "bound": "hbm",
                                 "achieved": k2_bytes / (k2_ms * 1e-3) / 1e9, "peak": hbm_peak, "unit": "GB/s",
                                 "frac": k2_bytes / (k2_ms * 1e-3) / 1e9 / hbm_peak, "ms": k2_ms,
-                                "algorithmic_bytes": k2_bytes}
+                                "algorithmic_bytes": k2_bytes, "id_slots": n_slots, "unique_rows": n_unique,
+                                "sort_bytes_not_counted": k2_sort_bytes,
+                                "all_rows_unique_bound": {"algorithmic_bytes": k2_bytes_bound,
+                                                          "frac": k2_bytes_bound / (k2_ms * 1e-3) / 1e9 / hbm_peak}}
     else:
         line["roofline"] = {"bound": "hbm", "achieved": None, "peak": hbm_peak, "unit": "GB/s", "frac": None,
                             "traffic": None, "note": "per-kernel roofline is reported by the N=1 run (unsharded K1)"}
-    if n_gpus == 1 and not args.no_cpu_baseline:
+        if k1_ms:
+            line["roofline"]["k1_ms"], line["roofline"]["k2_ms"] = k1_ms, k2_ms
+    if n_gpus == 1 and not args.no_cpu_baseline and wl == "deepfm_criteo":
         r = cpu_reference_run(steps=3, warmup=1, budget_s=60.0)
         line["cpu_baseline"] = {"value": r["value"], "unit": UNIT, "cores": r["cores"], "kind": "port", "sample": r["sample"]}
     print(json.dumps(line), flush=True)
@@ -315,6 +372,9 @@ def main():
     ap.add_argument("--warmup", type=int, default=5)
     ap.add_argument("--impl", default="ours", choices=["ours", "reference"])
     ap.add_argument("--no-cpu-baseline", action="store_true")
+    ap.add_argument("--workload", default="deepfm_criteo", choices=sorted(WORKLOADS))
+    ap.add_argument("--cin-precision", default="tf32", choices=["fp32", "tf32"],
+                    help="xDeepFM workloads: CIN contraction on tcgen05 (tf32) or CUDA cores (fp32)")
     args = ap.parse_args()
     rank = int(os.environ.get("RANK", "0"))
     local_rank = int(os.environ.get("LOCAL_RANK", "0"))
@@ -324,7 +384,8 @@ def main():
         # launched without torchrun: re-exec under it (the driver normally does this itself)
         cmd = [sys.executable, "-m", "torch.distributed.run", "--nnodes=1", f"--nproc-per-node={args.gpus}",
                "--master-addr", "127.0.0.1", "--master-port", os.environ.get("MASTER_PORT", "29533"), __file__,
-               "--gpus", str(args.gpus), "--steps", str(args.steps), "--warmup", str(args.warmup), "--impl", args.impl]
+               "--gpus", str(args.gpus), "--steps", str(args.steps), "--warmup", str(args.warmup), "--impl", args.impl,
+               "--workload", args.workload, "--cin-precision", args.cin_precision]
         sys.exit(subprocess.call(cmd))
     if args.impl == "reference":
         run_reference(args, rank, n_gpus)

@@ -6,12 +6,10 @@
 //   segreduce one lane group per chunk of sorted positions; the upstream gradient of a slot
 //             g_raw = g_flat + P^T (g_field + g_fm (fm_sum - e)) is rebuilt on the fly, so the
 //             FM gradient never exists in HBM; segments inside a chunk are written directly
-//             (+ 2*l2*w[row]); the open head/tail partial sums go to a side buffer.
-//             Two kernels: segreduce_staged_kernel (plain SPARSE tables, no g_field: every gradient /
-//             fm_sum / table row of a unit is staged in shared memory with cp.async, so the random
-//             256-byte row reads are all in flight at once) and segreduce_kernel (everything else).
-//   stitch    one block per segment that spans units: lane groups add the units' partials in a fixed
-//             strided order, then one group folds them (owners are listed by segreduce)
+//             (+ 2*l2*w[row]); the open head/tail partial sums go to a side buffer
+//   stitch    segments that span units (their owner units are listed by segreduce): one lane group each
+//             adds the units' partials in unit order; hot rows that span many units go to a second
+//             kernel, one block each, with a fixed strided order
 //   pgrads    DENSE-field Linear and projection gradients: per-slice partial sums in shared
 //             memory, then a fixed-order reduction over slices (+ 2*l2*p)
 // No float atomics anywhere: every output element has exactly one writer and a fixed summation
@@ -592,252 +590,6 @@ segreduce_kernel(const __grid_constant__ DevPlan P, const __grid_constant__ DevG
         atomicAdd(a.counters + threadIdx.x, (unsigned long long)s_cnt[threadIdx.x]);
 }
 
-// ---- staged fast path ------------------------------------------------------------------------
-// One WARP walks a contiguous range of R sorted positions front to back: lane l owns dims [l*VL, (l+1)*VL) of
-// the row (VL = tdim / 32), the running segment sum lives in registers and is carried from position to
-// position, so there is no stitching inside a range at all -- only the first / last segment of a range can be
-// open, and those go to the unit-level side buffers (unit = R) exactly as in segreduce_kernel.
-// The warp is fed by its own three-deep cp.async pipeline in shared memory (no block barriers, only
-// __syncwarp), in steps of WS_POS positions:
-//     K(k+2)  sorted keys / payloads two steps ahead                     -> key ring (3 slots)
-//     R(k+1)  decode the next step (lane = position: pointers of its gradient row, its sample's fm_sum row and,
-//             for positions that start a segment, its table row) and issue every 16-byte piece of those rows
-//             plus the per-position scalars as cp.async                  -> row buffer (2 slots)
-//     C(k)    the sequential segmented sum over the step, out of shared memory.
-// Every row read of a step (random 256-byte rows) is in flight while the previous step is being summed, and no
-// register holds staged data.
-constexpr int WS_POS = 16;      // positions per warp step
-constexpr int WS_WARPS = 4;     // warps per block (each with a private ~26 KB pipeline at D = 64)
-
-__device__ __forceinline__ void cp_async16(void* smem, const void* gmem) {
-    asm volatile("cp.async.cg.shared.global [%0], [%1], 16;\n" ::"r"((unsigned)__cvta_generic_to_shared(smem)), "l"(gmem));
-}
-__device__ __forceinline__ void cp_async4(void* smem, const void* gmem) {
-    asm volatile("cp.async.ca.shared.global [%0], [%1], 4;\n" ::"r"((unsigned)__cvta_generic_to_shared(smem)), "l"(gmem));
-}
-__device__ __forceinline__ void cp_async_commit() { asm volatile("cp.async.commit_group;\n" ::: "memory"); }
-template <int N>
-__device__ __forceinline__ void cp_async_wait() { asm volatile("cp.async.wait_group %0;\n" ::"n"(N) : "memory"); }
-
-template <int VL>
-__device__ __forceinline__ VecF<VL> lds_vec(const float* p) {   // one LDS.32 / LDS.64 / LDS.128
-    VecF<VL> r;
-    if constexpr (VL == 4) { const float4 t = *reinterpret_cast<const float4*>(p); r.v[0] = t.x; r.v[1] = t.y; r.v[2] = t.z; r.v[3] = t.w; }
-    else if constexpr (VL == 2) { const float2 t = *reinterpret_cast<const float2*>(p); r.v[0] = t.x; r.v[1] = t.y; }
-    else r.v[0] = *p;
-    return r;
-}
-
-struct WarpLayout {   // byte offsets inside one warp's private region
-    size_t rows, row_buf, ptrs, keys, pays, meta, meta_buf, total;
-};
-__host__ __device__ inline WarpLayout warp_layout(int tdim, bool has_fm) {
-    WarpLayout L;
-    size_t o = 0;
-    L.rows = o; L.row_buf = (size_t)WS_POS * tdim * 4 * (has_fm ? 3 : 2); o += 2 * L.row_buf;   // [2][s_g | s_w | s_s]
-    L.ptrs = o; o += (size_t)WS_POS * 8 * 3;                                                      // gptr, sptr, wptr
-    L.keys = o; o += 3 * (size_t)WS_POS * 4;
-    L.pays = o; o += 3 * (size_t)WS_POS * 4;
-    L.meta = o; L.meta_buf = (size_t)WS_POS * (4 * 3 + 2 + 2); o += 2 * L.meta_buf;               // [2][m | o | w1 | f | head]
-    L.total = (o + 15) & ~(size_t)15;
-    return L;
-}
-__host__ __device__ inline size_t warp_kernel_smem(int tdim, int S, int F, bool has_fm) {
-    size_t o = (size_t)WS_WARPS * warp_layout(tdim, has_fm).total;
-    o += (size_t)((S + 7) & ~7) * 2;
-    return o + (size_t)F * sizeof(FieldB);
-}
-
-template <bool HAS_FM, int VL>
-__global__ void __launch_bounds__(WS_WARPS * 32)
-segreduce_warp_kernel(const __grid_constant__ DevPlan P, const __grid_constant__ DevGrads GR,
-                      const __grid_constant__ BwdArgs a, long long R) {
-    extern __shared__ __align__(16) unsigned char sm_raw[];
-    const int lane = threadIdx.x & 31, wib = threadIdx.x >> 5;
-    const int tdim = P.max_tdim, S = P.S;
-    const int G = tdim >> 2, lgG = __ffs(G) - 1;       // 16-byte pieces per row
-    const WarpLayout L = warp_layout(tdim, HAS_FM);
-    unsigned char* wbase = sm_raw + (size_t)wib * L.total;
-    unsigned short* s_slotf = reinterpret_cast<unsigned short*>(sm_raw + (size_t)WS_WARPS * L.total);
-    FieldB* t_field = reinterpret_cast<FieldB*>(s_slotf + ((S + 7) & ~7));
-    const float** s_gptr = reinterpret_cast<const float**>(wbase + L.ptrs);
-    const float** s_sptr = s_gptr + WS_POS;
-    const float** s_wptr = s_sptr + WS_POS;
-    auto keys_of = [&](int k) { return reinterpret_cast<uint32_t*>(wbase + L.keys) + (k % 3) * WS_POS; };
-    auto pays_of = [&](int k) { return reinterpret_cast<uint32_t*>(wbase + L.pays) + (k % 3) * WS_POS; };
-    auto rows_of = [&](int k) { return reinterpret_cast<float*>(wbase + L.rows + (size_t)(k & 1) * L.row_buf); };
-    auto meta_of = [&](int k) { return reinterpret_cast<float*>(wbase + L.meta + (size_t)(k & 1) * L.meta_buf); };
-
-    for (int t = threadIdx.x; t < S; t += blockDim.x) s_slotf[t] = P.slot_field[t];
-    stage_fields(P, t_field);
-    __syncthreads();                                   // the only block barrier
-
-    const uint32_t PAD = P.pad_key;
-    const int bits = a.slot_bits;
-    const uint32_t smask = (1u << bits) - 1u;
-    const float coef = a.l2x2 * (a.l2_gscale ? __ldg(a.l2_gscale) : 1.f);
-    const bool need_w = HAS_FM || coef != 0.f || a.direct;
-    const bool need_w1 = coef != 0.f;
-    const long long unit_id = (long long)blockIdx.x * WS_WARPS + wib;
-    const long long r0 = unit_id * R;
-    if (r0 >= a.N) return;
-    const long long r1 = (r0 + R < a.N) ? r0 + R : a.N;
-    const int nsteps = (int)((r1 - r0 + WS_POS - 1) / WS_POS);
-    const uint32_t prev_key = r0 > 0 ? __ldg(a.skeys + r0 - 1) : PAD;
-
-    auto issue_keys = [&](int k) {
-        if (k < nsteps && lane < WS_POS) {
-            const long long p = r0 + (long long)k * WS_POS + lane;
-            if (p < r1) { cp_async4(keys_of(k) + lane, a.skeys + p); cp_async4(pays_of(k) + lane, a.spay + p); }
-            else keys_of(k)[lane] = PAD;
-        }
-        cp_async_commit();
-    };
-    auto issue_rows = [&](int k) {
-        if (k < nsteps) {
-            const uint32_t* ks = keys_of(k);
-            const uint32_t* ps = pays_of(k);
-            float* s_g = rows_of(k);
-            float* s_w = s_g + WS_POS * tdim;
-            float* s_s = s_w + WS_POS * tdim;
-            float* s_m = meta_of(k);
-            float* s_o = s_m + WS_POS;
-            float* s_w1 = s_o + WS_POS;
-            unsigned short* s_f = reinterpret_cast<unsigned short*>(s_w1 + WS_POS);
-            unsigned short* s_head = s_f + WS_POS;
-            if (lane < WS_POS) {
-                const int i = lane;
-                const uint32_t key = ks[i];
-                int head = 0;
-                if (key != PAD) {
-                    const uint32_t pay = ps[i];
-                    int f;
-                    if (a.direct) {
-                        f = field_of_key(t_field, P.n_fields, key);
-                        const float* row = a.g_flat + (size_t)pay * a.row_stride;
-                        s_gptr[i] = row;
-                        s_sptr[i] = nullptr;
-                        cp_async4(s_o + i, row + tdim);          // packed first-order gradient
-                        cp_async4(s_m + i, row + tdim + 1);      // packed g_fm (for -(sum g_fm) w)
-                    } else {
-                        const uint32_t b = pay >> bits;
-                        f = s_slotf[pay & smask];
-                        s_gptr[i] = a.g_flat + (size_t)b * P.T + t_field[f].flat_off;
-                        s_sptr[i] = HAS_FM ? a.fm_sum + (size_t)b * P.D : nullptr;
-                        if (a.g_fm) cp_async4(s_m + i, a.g_fm + b); else s_m[i] = 0.f;
-                        if (a.g_first) cp_async4(s_o + i, a.g_first + b); else s_o[i] = 0.f;
-                    }
-                    const FieldB& fb = t_field[f];
-                    s_f[i] = (unsigned short)f;
-                    s_wptr[i] = fb.w2 + (size_t)(key - fb.row_base) * fb.dim;
-                    const uint32_t before = i > 0 ? ks[i - 1] : (k > 0 ? keys_of(k - 1)[WS_POS - 1] : prev_key);
-                    head = key != before;                        // starts a segment inside this range
-                    if (need_w1 && head) cp_async4(s_w1 + i, fb.w1 + (key - fb.row_base));
-                }
-                s_head[i] = (unsigned short)head;
-            }
-            __syncwarp();
-            for (int q = lane; q < WS_POS * G; q += 32) {
-                const int i = q >> lgG, c = q & (G - 1);
-                if (ks[i] == PAD) continue;
-                cp_async16(s_g + i * tdim + c * 4, s_gptr[i] + c * 4);
-                if (HAS_FM) cp_async16(s_s + i * tdim + c * 4, s_sptr[i] + c * 4);
-                if (need_w && s_head[i]) cp_async16(s_w + i * tdim + c * 4, s_wptr[i] + c * 4);
-            }
-        }
-        cp_async_commit();
-    };
-
-    // running segment
-    uint32_t cur = PAD;
-    bool started_before = false, open = false;
-    int f = 0, n_heads = 0, n_valid = 0;
-    long long head_pos = r0;
-    VecF<VL> acc = vzero<VL>(), wreg = vzero<VL>();
-    float acc1 = 0.f, gs = 0.f, w1reg = 0.f;
-    auto close_segment = [&]() {
-        if (started_before) {   // started in an earlier range: the unit stitch pass finishes it
-            vstore<VL>(a.head2 + (size_t)unit_id * tdim + lane * VL, acc);
-            if (lane == 0) { a.head1[unit_id] = acc1; a.headg[unit_id] = gs; }
-        } else {
-            write_row<VL>(P, GR, a, coef, t_field[f], cur, f, head_pos, lane, acc, acc1, gs, true, wreg, w1reg);
-        }
-    };
-
-    issue_keys(0);
-    issue_keys(1);
-    cp_async_wait<1>();
-    __syncwarp();
-    issue_rows(0);
-    bool ended = false;
-    for (int k = 0; k < nsteps && !ended; ++k) {
-        issue_keys(k + 2);
-        cp_async_wait<2>();            // K(k+1) has landed   [pending: R(k), K(k+2)]
-        __syncwarp();
-        issue_rows(k + 1);
-        cp_async_wait<2>();            // R(k) has landed     [pending: K(k+2), R(k+1)]
-        __syncwarp();
-        const uint32_t* ks = keys_of(k);
-        const float* s_g = rows_of(k);
-        const float* s_w = s_g + WS_POS * tdim;
-        const float* s_s = s_w + WS_POS * tdim;
-        const float* s_m = meta_of(k);
-        const float* s_o = s_m + WS_POS;
-        const float* s_w1 = s_o + WS_POS;
-        const unsigned short* s_f = reinterpret_cast<const unsigned short*>(s_w1 + WS_POS);
-#pragma unroll 4
-        for (int i = 0; i < WS_POS; ++i) {
-            const uint32_t key = ks[i];
-            if (key == PAD) { ended = true; break; }
-            if (!open || key != cur) {
-                if (open) close_segment();
-                started_before = !open && key == prev_key;      // only the range's first segment can be
-                open = true;
-                cur = key; f = s_f[i];
-                head_pos = r0 + (long long)k * WS_POS + i;
-                if (!started_before) {
-                    ++n_heads;
-                    wreg = lds_vec<VL>(s_w + i * tdim + lane * VL);
-                    w1reg = s_w1[i];
-                }
-                acc = vzero<VL>(); acc1 = 0.f; gs = 0.f;
-            }
-            const VecF<VL> g = lds_vec<VL>(s_g + i * tdim + lane * VL);
-            const float m = s_m[i];
-            if (HAS_FM) {
-                const VecF<VL> sv = lds_vec<VL>(s_s + i * tdim + lane * VL);
-#pragma unroll
-                for (int v = 0; v < VL; ++v) acc.v[v] += fmaf(m, sv.v[v], g.v[v]);
-            } else {
-#pragma unroll
-                for (int v = 0; v < VL; ++v) acc.v[v] += g.v[v];
-            }
-            gs += m;
-            acc1 += s_o[i];
-            ++n_valid;
-        }
-        __syncwarp();                  // row buffer k & 1 and key slot k % 3 are free again
-    }
-    cp_async_wait<0>();
-    if (open) {
-        const bool continues = !ended && r1 < a.N && __ldg(a.skeys + r1) == cur;
-        if (started_before || !continues) {
-            close_segment();
-        } else {                       // starts here and leaves the range: this unit owns the segment
-            vstore<VL>(a.tail2 + (size_t)unit_id * tdim + lane * VL, acc);
-            if (lane == 0) {
-                a.tail1[unit_id] = acc1; a.tailg[unit_id] = gs;
-                a.tail_start[unit_id] = head_pos; a.tail_field[unit_id] = f;
-                a.open_list[atomicAdd(a.open_count, 1u)] = (unsigned)unit_id;
-            }
-        }
-    }
-    if (lane == 0 && (n_valid | n_heads)) {
-        atomicAdd(a.counters, (unsigned long long)n_valid);
-        atomicAdd(a.counters + 1, (unsigned long long)n_heads);
-    }
-}
-
 // ---- segments that leave their unit (listed by segreduce in open_list: only the unit in which the segment
 // STARTS is listed).  stitch_kernel: one lane group per listed segment finds the unit in which it ends (G units
 // per step) and, when it spans at most LONG_SPAN units, adds their head partials in unit order.  Longer
@@ -1183,9 +935,7 @@ static int make_layout(const dfm_plan* plan, long long B, BwdLayout& L, long lon
     const long long N = direct_rows >= 0 ? direct_rows : B * plan->S;
     L.cub_bytes = 0;
     if (N > 0) { int rc = sort_temp_bytes(N, plan->key_bits, &L.cub_bytes); if (rc) return rc; }
-    // units: >= 8 chunks of CHUNK per segreduce block, or 4 * WS_POS positions (at least) per warp range
-    const long long min_unit = 4 * WS_POS;
-    L.n_chunks = ceil_div(N > 0 ? N : 1, min_unit);
+    L.n_chunks = ceil_div(N > 0 ? N : 1, 8 * CHUNK);   // units: >= 8 chunks per segreduce block
     int vals = 0, n_pf = 0;
     for (int f = 0; f < plan->n_fields; ++f) { int n = pg_count_vals(plan, f); if (n) { vals += n; ++n_pf; } }
     L.vals_per_slice = vals;
@@ -1364,29 +1114,8 @@ static int embed_bwd_impl(const dfm_plan* plan, int64_t batch, long long direct_
         bool any_generic = false;
         for (int f = 0; f < plan->n_fields; ++f)
             any_generic = any_generic || plan->kind[f] == DFM_SEQUENCE || (plan->kind[f] == DFM_SPARSE && plan->dim[f] != plan->fm_dim);
-        const bool has_fm = g_fm != nullptr && !direct;
-        const int tdim = plan->max_tdim;
-        const size_t st_smem = warp_kernel_smem(tdim, direct ? 0 : plan->S, plan->n_fields, has_fm);
-        const bool staged = V == 4 && lanes == G && (tdim == 32 || tdim == 64) && g_flat && !g_field && (direct || !any_generic) &&
-                            (!g_fm || direct || plan->fm_dim == tdim);
         long long unit;
-        if (staged) {
-            // one range of R positions per warp, all warps resident (2 blocks per SM at D = 64)
-            const int per_sm = (int)((220 * 1024) / st_smem) > 0 ? (int)((220 * 1024) / st_smem) : 1;
-            long long blocks = (long long)per_sm * sm_count();
-            long long R = ceil_div(ceil_div(N, blocks * WS_WARPS), WS_POS) * WS_POS;
-            if (R < 4 * WS_POS) R = 4 * WS_POS;
-            blocks = ceil_div(ceil_div(N, R), WS_WARPS);
-            unit = R;
-#define DFM_LAUNCH_WARP(FM, VLN)                                                                                           \
-            do {                                                                                                               \
-                DFM_CHECK_CUDA(cudaFuncSetAttribute(segreduce_warp_kernel<FM, VLN>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)st_smem)); \
-                segreduce_warp_kernel<FM, VLN><<<(unsigned)blocks, WS_WARPS * 32, st_smem, st>>>(*P, *GR, a, R);            \
-            } while (0)
-            if (has_fm) { if (tdim == 64) DFM_LAUNCH_WARP(true, 2); else DFM_LAUNCH_WARP(true, 1); }
-            else { if (tdim == 64) DFM_LAUNCH_WARP(false, 2); else DFM_LAUNCH_WARP(false, 1); }
-#undef DFM_LAUNCH_WARP
-        } else {
+        {
             unit = (long long)gpb * CHUNK;               // positions per segreduce block
             const unsigned blocks = (unsigned)ceil_div(N, unit);
             const size_t smem = seg_smem_bytes(gpb, plan->max_tdim, (int)unit, direct ? 0 : plan->S, plan->n_fields) + 16;
