@@ -221,10 +221,17 @@ def run_ours(args, rank: int, local_rank: int, n_gpus: int):
     devy = [y.to(dev) for y in host_y]
     bce = torch.nn.BCEWithLogitsLoss()
 
+    reducer = None
+    if n_gpus > 1:
+        from deepfm_b200.sharded import DenseGradReducer
+        emb_ids = {id(p) for p in emb.parameters()}
+        early = [p for p in dense_params if id(p) not in emb_ids]
+        late = [p for p in dense_params if id(p) in emb_ids]
+        reducer = DenseGradReducer(early, late, n_gpus)    # allreduce of the DNN grads overlaps the table backward
+
     def allreduce_dense():
-        if n_gpus > 1:
-            from deepfm_b200.sharded import allreduce_dense as ar
-            ar(dense_params, n_gpus)
+        if reducer is not None:
+            reducer.finish()
 
     def step(batch, labels, next_batch=None):
         model.zero_grad(set_to_none=True)

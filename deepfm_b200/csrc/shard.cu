@@ -1,5 +1,6 @@
-// Row-sharded embedding tables across W GPUs:  owner(id) = id mod W,
-// local_row = id div W, per field.  The exchange itself is an NCCL all-to-all issued by the host
+// Row-sharded embedding tables across W GPUs:  owner(f, id) = (id + f) mod W,
+// local_row = id div W, per field f (the rotation by the field index spreads the hot ids 1, 2, ... of the
+// tables over the ranks).  The exchange itself is an NCCL all-to-all issued by the host
 // side (deepfm_b200/sharded.py); these kernels are the owner-side gather of the looked-up rows
 // and the sample-side packing of the row gradients into send order.
 //
@@ -15,6 +16,8 @@
 #include "plan.cuh"
 
 namespace dfm {
+
+constexpr int RT_MAXW_ = 16;      // ranks (== RT_MAXW below)
 
 struct ShardField {
     const float* w2;       // local shard (rows_local, d)
@@ -35,10 +38,28 @@ struct ShardArgs {
     unsigned pad_local;    // local PAD key (= total local rows)
 };
 
+// Fused exchange over peer memory (NVLink P2P stores): row i of a rank's send order belongs to the peer whose
+// segment [start[p], start[p + 1]) contains i and is written straight into that peer's buffer at
+// base[p] + (i - start[p]) * row_stride -- the collective IS the kernel's store stream, there is no staging
+// buffer and no separate all-to-all.  n == 0: plain local output.
+struct PeerDst {
+    long long start[RT_MAXW_ + 1];
+    float* base[RT_MAXW_];
+    int n;
+};
+
+__device__ __forceinline__ float* peer_row(const PeerDst& pd, float* local, long long i, int row_stride) {
+    if (pd.n == 0) return local + (size_t)i * row_stride;
+    int p = 0;
+#pragma unroll 1
+    for (int q = 1; q < pd.n; ++q) if (i >= pd.start[q]) p = q;
+    return pd.base[p] + (size_t)(i - pd.start[p]) * row_stride;
+}
+
 template <int V>
 __global__ void __launch_bounds__(256)
 shard_gather_kernel(const __grid_constant__ ShardArgs a, long long M, const uint32_t* __restrict__ keys, int G,
-                    float* __restrict__ vec, uint32_t* __restrict__ lkeys) {
+                    float* __restrict__ vec, uint32_t* __restrict__ lkeys, const __grid_constant__ PeerDst pd) {
     __shared__ ShardField t[MAX_FIELDS];
     for (int i = threadIdx.x; i < a.n; i += blockDim.x) t[i] = a.f[i];
     __syncthreads();
@@ -50,12 +71,13 @@ shard_gather_kernel(const __grid_constant__ ShardArgs a, long long M, const uint
         for (int q = 1; q < a.n; ++q) if (key >= t[q].gbase) fi = q;
         const ShardField& sf = t[fi];
         const uint32_t id = key - sf.gbase;
-        const uint32_t lrow = id / (uint32_t)a.world;         // id mod world == rank by construction
+        const uint32_t lrow = id / (uint32_t)a.world;         // (id + field) mod world == rank by construction
         // packed reply row: [row (d), first-order weight, 0, 0, 0]
+        float* dst = peer_row(pd, vec, i, a.dmax + 4);
         if (j < sf.dim / V)
-            vstore_stream<V>(vec + (size_t)i * (a.dmax + 4) + j * V, vload<V>(sf.w2 + (size_t)lrow * sf.dim + j * V));
+            vstore_stream<V>(dst + j * V, vload<V>(sf.w2 + (size_t)lrow * sf.dim + j * V));
         if (j == 0) {
-            *reinterpret_cast<float4*>(vec + (size_t)i * (a.dmax + 4) + a.dmax) = make_float4(__ldg(sf.w1 + lrow), 0.f, 0.f, 0.f);
+            *reinterpret_cast<float4*>(dst + a.dmax) = make_float4(__ldg(sf.w1 + lrow), 0.f, 0.f, 0.f);
             lkeys[i] = id ? sf.lbase + lrow : a.pad_local;    // id 0 is the padding row: no gradient
         }
     }
@@ -79,7 +101,7 @@ struct PackArgs {
 template <int V>
 __global__ void __launch_bounds__(256)
 shard_pack_kernel(const __grid_constant__ ShardArgs a, const __grid_constant__ PackArgs p, int G,
-                  float* __restrict__ g_vec) {
+                  float* __restrict__ g_vec, const __grid_constant__ PeerDst pd) {
     const int gpb = blockDim.x / G;
     const int gl = threadIdx.x / G, j = threadIdx.x - gl * G;
     const long long n = p.B * p.S;
@@ -92,6 +114,7 @@ shard_pack_kernel(const __grid_constant__ ShardArgs a, const __grid_constant__ P
         float scale = 1.f;
         if (sf.bag == 2) scale = __uint_as_float(__ldg(p.aux + (size_t)b * p.A + sf.aux_off));
         const float m = p.g_fm ? __ldg(p.g_fm + b) : 0.f;
+        float* dst = peer_row(pd, g_vec, q, p.dmax + 4);
         if (j < sf.dim / V) {
             VecF<V> g = vzero<V>();
             if (p.g_flat) g = vload_stream<V>(p.g_flat + (size_t)b * p.T + sf.flat_off + j * V);
@@ -116,10 +139,10 @@ shard_pack_kernel(const __grid_constant__ ShardArgs a, const __grid_constant__ P
 #pragma unroll
                 for (int v = 0; v < V; ++v) g.v[v] *= scale;
             }
-            vstore_stream<V>(g_vec + (size_t)q * (p.dmax + 4) + j * V, g);
+            vstore_stream<V>(dst + j * V, g);
         }
         if (j == 0)
-            *reinterpret_cast<float4*>(g_vec + (size_t)q * (p.dmax + 4) + p.dmax) =
+            *reinterpret_cast<float4*>(dst + p.dmax) =
                 make_float4((p.g_first ? __ldg(p.g_first + b) : 0.f) * scale, sf.bag ? 0.f : m, 0.f, 0.f);
     }
 }
@@ -127,13 +150,14 @@ shard_pack_kernel(const __grid_constant__ ShardArgs a, const __grid_constant__ P
 // ---- routing: stable grouping of the id slots by owner = id mod W (oracle.shard_route) --------
 // count (per-block owner histogram) -> scan (one block) -> scatter (stable inside and across blocks).
 constexpr int RT_TILE = 2048;     // id slots per block
-constexpr int RT_MAXW = 16;       // ranks
+constexpr int RT_MAXW = RT_MAXW_;  // ranks
 
 struct RouteField {
     const long long* ids;   // (B,) or (B, max_len) id column
     unsigned gbase;         // global row base (key = gbase + id)
     int slot_base, max_len;
     int bag;                // SEQUENCE: padding entries (id 0) are not sent
+    int rot;                // owner = (id + rot) mod W, rot = schema index of the field
 };
 struct RouteArgs {
     RouteField f[MAX_FIELDS];            // table fields only
@@ -149,7 +173,7 @@ __device__ __forceinline__ int route_owner(const RouteArgs& a, const RouteField*
     rf = t + slot_tf[s];
     id = __ldg(rf->ids + b * rf->max_len + (s - rf->slot_base));
     if (rf->bag && id == 0) return -1;
-    return (int)(id % a.world);
+    return (int)((id + rf->rot) % a.world);
 }
 
 __global__ void __launch_bounds__(256)
@@ -279,19 +303,44 @@ static void fill_slot_tf(const dfm_plan* plan, unsigned short* slot_tf) {
     for (int s = 0; s < plan->S; ++s) slot_tf[s] = (unsigned short)tf[plan->slot_field[s]];
 }
 
+static int fill_peer(PeerDst& pd, int n_peers, const int64_t* peer_start, float* const* peer_rows, const char* who) {
+    memset(&pd, 0, sizeof(pd));
+    if (n_peers == 0) return DFM_OK;
+    if (n_peers < 0 || n_peers > RT_MAXW_ || !peer_start || !peer_rows) {
+        set_error("%s: need 1..%d peers with segment starts and row pointers", who, RT_MAXW_);
+        return DFM_ERR_INVALID;
+    }
+    for (int q = 0; q < n_peers; ++q) {
+        if (!peer_rows[q] || (reinterpret_cast<uintptr_t>(peer_rows[q]) & 15u) || peer_start[q] > peer_start[q + 1]) {
+            set_error("%s: peer %d has a null / unaligned row pointer or a negative segment", who, q);
+            return DFM_ERR_INVALID;
+        }
+        pd.start[q] = peer_start[q]; pd.base[q] = peer_rows[q];
+    }
+    pd.start[n_peers] = peer_start[n_peers];
+    pd.n = n_peers;
+    return DFM_OK;
+}
+
 extern "C" {
 
-int dfm_shard_gather(const dfm_plan* local_plan, int world, int rank, const int64_t* global_row_base,
-                     int64_t n_keys, const uint32_t* keys, const float* const* params, float* vec,
-                     uint32_t* local_keys, void* stream) {
+static int shard_gather_impl(const dfm_plan* local_plan, int world, int rank, const int64_t* global_row_base,
+                             int64_t n_keys, const uint32_t* keys, const float* const* params, float* vec,
+                             uint32_t* local_keys, int n_peers, const int64_t* peer_start, float* const* peer_rows,
+                             void* stream) {
     DFM_REQUIRE(local_plan && global_row_base && params && world > 0 && rank >= 0 && rank < world, DFM_ERR_INVALID,
                 "dfm_shard_gather: bad argument");
     if (n_keys <= 0) return DFM_OK;
-    DFM_REQUIRE(keys && vec && local_keys, DFM_ERR_INVALID, "dfm_shard_gather: null tensor");
+    DFM_REQUIRE(keys && (vec || n_peers > 0) && local_keys, DFM_ERR_INVALID, "dfm_shard_gather: null tensor");
     ShardArgs* a = new ShardArgs;
-    struct Gd { ShardArgs* p; ~Gd() { delete p; } } gd{a};
+    PeerDst* pd = new PeerDst;
+    struct Gd { ShardArgs* p; PeerDst* q; ~Gd() { delete p; delete q; } } gd{a, pd};
     int rc = fill_shard_args(local_plan, global_row_base, params, world, rank, *a, true);
     if (rc) return rc;
+    rc = fill_peer(*pd, n_peers, peer_start, peer_rows, "dfm_shard_gather_p2p");
+    if (rc) return rc;
+    DFM_REQUIRE(n_peers == 0 || peer_start[n_peers] - peer_start[0] == n_keys, DFM_ERR_INVALID,
+                "dfm_shard_gather_p2p: the peer segments must cover the %lld keys", (long long)n_keys);
     const bool v4 = local_plan->vec == 4 && (reinterpret_cast<uintptr_t>(vec) & 15u) == 0;
     const int lanes = a->dmax / (v4 ? 4 : 1);
     DFM_REQUIRE(lanes <= 32, DFM_ERR_UNSUPPORTED, "dfm_shard_gather: table dim %d too wide", a->dmax);
@@ -299,23 +348,42 @@ int dfm_shard_gather(const dfm_plan* local_plan, int world, int rank, const int6
     long long blocks = ceil_div(n_keys, 256 / G);
     if (blocks > 8LL * sm_count()) blocks = 8LL * sm_count();
     cudaStream_t st = static_cast<cudaStream_t>(stream);
-    if (v4) shard_gather_kernel<4><<<(unsigned)blocks, 256, 0, st>>>(*a, n_keys, keys, G, vec, local_keys);
-    else shard_gather_kernel<1><<<(unsigned)blocks, 256, 0, st>>>(*a, n_keys, keys, G, vec, local_keys);
+    if (v4) shard_gather_kernel<4><<<(unsigned)blocks, 256, 0, st>>>(*a, n_keys, keys, G, vec, local_keys, *pd);
+    else shard_gather_kernel<1><<<(unsigned)blocks, 256, 0, st>>>(*a, n_keys, keys, G, vec, local_keys, *pd);
     DFM_CHECK_LAUNCH();
     return DFM_OK;
 }
 
-int dfm_shard_pack_grad(const dfm_plan* plan, int64_t batch, const int64_t* positions, const float* g_first,
-                        const float* g_field, const float* g_flat, const float* g_fm, const float* fm_sum,
-                        const float* field_emb, const uint32_t* aux, float* g_vec, void* stream) {
+int dfm_shard_gather(const dfm_plan* local_plan, int world, int rank, const int64_t* global_row_base,
+                     int64_t n_keys, const uint32_t* keys, const float* const* params, float* vec,
+                     uint32_t* local_keys, void* stream) {
+    return shard_gather_impl(local_plan, world, rank, global_row_base, n_keys, keys, params, vec, local_keys, 0, nullptr,
+                             nullptr, stream);
+}
+
+int dfm_shard_gather_p2p(const dfm_plan* local_plan, int world, int rank, const int64_t* global_row_base,
+                         int64_t n_keys, const uint32_t* keys, const float* const* params, int n_peers,
+                         const int64_t* peer_start, float* const* peer_rows, uint32_t* local_keys, void* stream) {
+    DFM_REQUIRE(n_peers > 0, DFM_ERR_INVALID, "dfm_shard_gather_p2p: no peers");
+    return shard_gather_impl(local_plan, world, rank, global_row_base, n_keys, keys, params, nullptr, local_keys, n_peers,
+                             peer_start, peer_rows, stream);
+}
+
+static int shard_pack_impl(const dfm_plan* plan, int64_t batch, const int64_t* positions, const float* g_first,
+                           const float* g_field, const float* g_flat, const float* g_fm, const float* fm_sum,
+                           const float* field_emb, const uint32_t* aux, float* g_vec, int n_peers,
+                           const int64_t* peer_start, float* const* peer_rows, void* stream) {
     DFM_REQUIRE(plan && batch >= 0, DFM_ERR_INVALID, "dfm_shard_pack_grad: bad argument");
     if (batch == 0 || plan->S == 0) return DFM_OK;
-    DFM_REQUIRE(positions && g_vec && (!g_fm || fm_sum), DFM_ERR_INVALID, "dfm_shard_pack_grad: null tensor");
+    DFM_REQUIRE(positions && (g_vec || n_peers > 0) && (!g_fm || fm_sum), DFM_ERR_INVALID, "dfm_shard_pack_grad: null tensor");
     ShardArgs* a = new ShardArgs;
     PackArgs* pp = new PackArgs;
-    struct Gd { ShardArgs* p; PackArgs* q; ~Gd() { delete p; delete q; } } gd{a, pp};
+    PeerDst* pd = new PeerDst;
+    struct Gd { ShardArgs* p; PackArgs* q; PeerDst* r; ~Gd() { delete p; delete q; delete r; } } gd{a, pp, pd};
     std::vector<int64_t> zeros(plan->n_fields + 1, 0);
     int rc = fill_shard_args(plan, zeros.data(), nullptr, 1, 0, *a, false);
+    if (rc) return rc;
+    rc = fill_peer(*pd, n_peers, peer_start, peer_rows, "dfm_shard_pack_grad_p2p");
     if (rc) return rc;
     bool any_bag = false, any_mean = false;
     for (int i = 0; i < a->n; ++i) { any_bag = any_bag || a->f[i].bag; any_mean = any_mean || a->f[i].bag == 2; }
@@ -336,10 +404,26 @@ int dfm_shard_pack_grad(const dfm_plan* plan, int64_t batch, const int64_t* posi
     long long blocks = ceil_div(batch * plan->S, 256 / G);
     if (blocks > 8LL * sm_count()) blocks = 8LL * sm_count();
     cudaStream_t st = static_cast<cudaStream_t>(stream);
-    if (v4) shard_pack_kernel<4><<<(unsigned)blocks, 256, 0, st>>>(*a, p, G, g_vec);
-    else shard_pack_kernel<1><<<(unsigned)blocks, 256, 0, st>>>(*a, p, G, g_vec);
+    if (v4) shard_pack_kernel<4><<<(unsigned)blocks, 256, 0, st>>>(*a, p, G, g_vec, *pd);
+    else shard_pack_kernel<1><<<(unsigned)blocks, 256, 0, st>>>(*a, p, G, g_vec, *pd);
     DFM_CHECK_LAUNCH();
     return DFM_OK;
+}
+
+int dfm_shard_pack_grad(const dfm_plan* plan, int64_t batch, const int64_t* positions, const float* g_first,
+                        const float* g_field, const float* g_flat, const float* g_fm, const float* fm_sum,
+                        const float* field_emb, const uint32_t* aux, float* g_vec, void* stream) {
+    return shard_pack_impl(plan, batch, positions, g_first, g_field, g_flat, g_fm, fm_sum, field_emb, aux, g_vec, 0, nullptr,
+                           nullptr, stream);
+}
+
+int dfm_shard_pack_grad_p2p(const dfm_plan* plan, int64_t batch, const int64_t* positions, const float* g_first,
+                            const float* g_field, const float* g_flat, const float* g_fm, const float* fm_sum,
+                            const float* field_emb, const uint32_t* aux, int n_peers, const int64_t* peer_start,
+                            float* const* peer_rows, void* stream) {
+    DFM_REQUIRE(n_peers > 0, DFM_ERR_INVALID, "dfm_shard_pack_grad_p2p: no peers");
+    return shard_pack_impl(plan, batch, positions, g_first, g_field, g_flat, g_fm, fm_sum, field_emb, aux, nullptr, n_peers,
+                           peer_start, peer_rows, stream);
 }
 
 size_t dfm_shard_route_workspace_bytes(const dfm_plan* plan, int64_t batch) {
@@ -371,6 +455,7 @@ int dfm_shard_route(const dfm_plan* plan, int world, const int64_t* global_row_b
         rf.gbase = (unsigned)global_row_base[f];
         rf.slot_base = plan->slot_base[f]; rf.max_len = plan->max_len[f];
         rf.bag = plan->kind[f] == DFM_SEQUENCE ? 1 : 0;
+        rf.rot = f % world;
     }
     fill_slot_tf(plan, a->slot_tf);
     const int nblk = (int)ceil_div(n, RT_TILE);

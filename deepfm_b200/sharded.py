@@ -1,8 +1,9 @@
 """Row-sharded ``FeatureEmbedding`` for one 8xB200 box (the reference is single-device).
 
 Every embedding table (second- and first-order) is sharded by row over the ``W`` ranks of a
-``torch.distributed`` NCCL group: ``owner(id) = id mod W``, ``local_row = id div W`` (uniform load
-under skewed ids; bit-exact contract: ``oracle.shard_route``).  Samples stay data-parallel:
+``torch.distributed`` NCCL group: ``owner(f, id) = (id + f) mod W`` with ``f`` the schema index of the field,
+``local_row = id div W`` (the rotation spreads the hot ids 1, 2, ... of the 26 tables over the ranks instead of
+piling them on ranks 1, 2, ...; bit-exact contract: ``oracle.shard_route``).  Samples stay data-parallel:
 rank ``r`` owns its ``b`` samples.  One step is
 
     forward   route ids by owner -> all-to-all(keys) -> owners gather rows (dfm_shard_gather)
@@ -40,9 +41,10 @@ from .schema import kind_of
 VIRTUAL_VOCAB = 1 << 26     # capacity of the "received rows" pseudo table of the sample-side plan
 
 
-def local_rows(vocab: int, world: int, rank: int) -> int:
-    """Number of ids in [0, vocab) owned by ``rank`` (id mod world == rank); at least 1 row is kept."""
-    return max((vocab - rank + world - 1) // world, 1)
+def local_rows(vocab: int, world: int, rank: int, field: int = 0) -> int:
+    """Number of ids in [0, vocab) owned by ``rank`` ((id + field) mod world == rank); at least 1 row is kept."""
+    first = (rank - field) % world          # smallest id this rank owns in the field's table
+    return max((vocab - first + world - 1) // world, 1)
 
 
 @dataclass
@@ -65,17 +67,20 @@ def field_positions(pos: torch.Tensor, b: int, lens: Sequence[int]) -> List[torc
 
 
 def route_ids(ids: torch.Tensor, row_base: torch.Tensor, world: int, lens: Optional[Sequence[int]] = None,
-              bag: Optional[Sequence[bool]] = None) -> Route:
+              bag: Optional[Sequence[bool]] = None, rot: Optional[Sequence[int]] = None) -> Route:
     """ids (b, S) int64 (the id slots of one sample side by side, bags expanded), row_base (S,) int64 per slot,
     lens / bag per table field (sum(lens) == S).  Stable grouping of the slots, in source order b*S + s, by
-    owner = id mod W; padding entries (id 0) of bag fields are not sent.  Pure torch ops: works on CPU and CUDA
+    owner = (id + rot[field]) mod W (rot: schema index per table field, default 0); padding entries (id 0) of
+    bag fields are not sent.  Pure torch ops: works on CPU and CUDA
     tensors; matches oracle.shard_route bit-exactly."""
     b, S = ids.shape
     lens = [1] * S if lens is None else list(lens)
     bag = [False] * len(lens) if bag is None else list(bag)
     slot_bag = torch.tensor([g for L, g in zip(lens, bag) for _ in range(L)], dtype=torch.bool, device=ids.device)
     sent = ~(slot_bag[None, :] & (ids == 0))
-    owner = torch.where(sent, ids % world, torch.full_like(ids, world)).reshape(-1)   # unsent slots sort last
+    rot = [0] * len(lens) if rot is None else list(rot)
+    slot_rot = torch.tensor([r for L, r in zip(lens, rot) for _ in range(L)], dtype=ids.dtype, device=ids.device)
+    owner = torch.where(sent, (ids + slot_rot[None, :]) % world, torch.full_like(ids, world)).reshape(-1)   # unsent last
     n = int(sent.sum())
     order = torch.sort(owner, stable=True).indices[:n]
     counts = torch.bincount(owner, minlength=world + 1)[:world]
@@ -104,6 +109,7 @@ class TorchDistComm:
         rows = [torch.empty_like(counts) for _ in range(self.world)]
         self.dist.all_gather(rows, counts.contiguous(), group=self.group)
         host = torch.stack(rows).tolist()
+        self.last_matrix = host
         return host[self.rank], [host[src][self.rank] for src in range(self.world)]
 
     def exchange_counts_async(self, counts: torch.Tensor):
@@ -124,6 +130,7 @@ class TorchDistComm:
         if ev is not None:
             ev.synchronize()
         mat = host.tolist()
+        self.last_matrix = mat            # mat[s][r]: rows rank s sends to rank r
         return mat[self.rank], [mat[src][self.rank] for src in range(self.world)]
 
     def all_to_all(self, send: torch.Tensor, send_counts: Sequence[int], recv_counts: Sequence[int],
@@ -132,6 +139,50 @@ class TorchDistComm:
             out = send.new_empty((int(sum(recv_counts)),) + tuple(send.shape[1:]))
         self.dist.all_to_all_single(out, send.contiguous(), list(recv_counts), list(send_counts), group=self.group)
         return out
+
+
+class PeerExchange:
+    """The two vector exchanges of a step as peer-memory writes (compute fused with its collective).
+
+    Every rank owns two symmetric-memory buffers per direction (``torch.distributed._symmetric_memory``: CUDA VMM
+    allocations mapped into every peer over NVLink/NVSwitch).  The owner-side gather kernel stores each reply row
+    straight into the requesting GPU's ``got`` buffer, the sample-side packing kernel stores each gradient row
+    straight into the owning GPU's ``g_recv`` buffer: no staging buffer, no NCCL all-to-all; one device-side
+    barrier separates the writes from their consumer.  Buffers alternate between steps, so that barrier is the
+    only synchronisation needed (a peer can be at most one exchange ahead)."""
+
+    def __init__(self, comm: "TorchDistComm", row_floats: int, capacity_rows: int, device):
+        import torch.distributed._symmetric_memory as symm
+        self.comm, self.world, self.rank = comm, comm.world, comm.rank
+        self.row_floats, self.cap = row_floats, int(capacity_rows)
+        group = comm.group if comm.group is not None else comm.dist.group.WORLD
+        n = 4 * self.cap * row_floats                        # [got 0 | got 1 | g_recv 0 | g_recv 1]
+        self.buf = symm.empty((n,), dtype=torch.float32, device=device)
+        self.hdl = symm.rendezvous(self.buf, group.group_name)
+        self.buf.zero_()                                     # row 0 of both got buffers is the reserved zero row
+        self.peer_base = [int(p) for p in self.hdl.buffer_ptrs]
+        self.step = 0
+        torch.cuda.synchronize(device)
+        self.hdl.barrier(channel=0)
+
+    def region(self, kind: int, parity: int, rank: Optional[int] = None) -> int:
+        """Device address of buffer (kind 0: got, 1: g_recv; parity) on ``rank`` (default: this rank)."""
+        base = self.peer_base[self.rank if rank is None else rank]
+        return base + (2 * kind + parity) * self.cap * self.row_floats * 4
+
+    def view(self, kind: int, parity: int, rows: int) -> torch.Tensor:
+        off = (2 * kind + parity) * self.cap * self.row_floats
+        return self.buf[off: off + rows * self.row_floats].view(rows, self.row_floats)
+
+    def fits(self, matrix) -> bool:
+        """Same answer on every rank (all of them hold the full W x W count matrix)."""
+        W = self.world
+        sent = max(sum(matrix[s]) for s in range(W))
+        recv = max(sum(matrix[s][r] for s in range(W)) for r in range(W))
+        return sent + 1 <= self.cap and recv <= self.cap
+
+    def barrier(self, channel: int) -> None:
+        self.hdl.barrier(channel=channel)
 
 
 class _ShardedEmbedFn(torch.autograd.Function):
@@ -147,12 +198,25 @@ class _ShardedEmbedFn(torch.autograd.Function):
             route = mod.route(inputs)
             send_counts, recv_counts = comm.exchange_counts(route.counts)     # the only host sync of the step
         recv_keys = comm.all_to_all(route.send_keys[:int(sum(send_counts))], send_counts, recv_counts)
-        rows, lkeys = mod.gather(recv_keys)
-        got = mod.reply_buffer(int(sum(send_counts)), rows)                # (1 + n, D + 4): zero row, then the replies
-        comm.all_to_all(rows, recv_counts, send_counts, out=got[1:])       # vector + first-order weight per row
+        px = mod.peer_exchange(inputs[0].device)
+        matrix = getattr(comm, "last_matrix", None)
+        use_p2p = px is not None and matrix is not None and px.fits(matrix)
+        parity = 0
+        if use_p2p:
+            # owners store every reply row straight into the requester's got buffer (NVLink P2P), then one barrier
+            parity = px.step & 1
+            px.step += 1
+            lkeys = mod.gather_p2p(recv_keys, px, matrix, parity)
+            px.barrier(0)
+            got = px.view(0, parity, int(sum(send_counts)) + 1)
+        else:
+            rows, lkeys = mod.gather(recv_keys)
+            got = mod.reply_buffer(int(sum(send_counts)), rows)            # (1 + n, D + 4): zero row, then the replies
+            comm.all_to_all(rows, recv_counts, send_counts, out=got[1:])   # vector + first-order weight per row
         first, field, flat, fm, fm_sum, aux, fin_inputs = mod.finish(inputs, route.pos, got, need_bwd)
         ctx.mod, ctx.n_inputs = mod, n_inputs
         ctx.counts = (send_counts, recv_counts)
+        ctx.p2p = (px, matrix, parity) if use_p2p else None
         ctx.set_materialize_grads(False)
         ctx.l2, ctx.done = None, False
         if need_bwd:
@@ -173,8 +237,13 @@ class _ShardedEmbedFn(torch.autograd.Function):
         ctx.done = True
         cont = lambda g: None if g is None else g.contiguous()
         g_rows, dense_grads = mod.pack_grads(fin_inputs, pos, got, cont(g_first), cont(g_field), cont(g_flat),
-                                             cont(g_fm), field, flat, fm_sum, params, lam, gscale, aux)
-        g_recv = mod.comm.all_to_all(g_rows, send_counts, recv_counts)    # (M, D + 4): gradient row + scalars
+                                             cont(g_fm), field, flat, fm_sum, params, lam, gscale, aux, p2p=ctx.p2p)
+        if ctx.p2p is not None:           # the gradient rows were stored straight into the owners' buffers
+            px, matrix, parity = ctx.p2p
+            px.barrier(1)
+            g_recv = px.view(1, parity, int(sum(recv_counts)))
+        else:
+            g_recv = mod.comm.all_to_all(g_rows, send_counts, recv_counts)    # (M, D + 4): gradient row + scalars
         table_grads = mod.owner_backward(lkeys, g_recv, params, lam, gscale)
         grads = [dense_grads.get(i, table_grads.get(i)) for i in range(len(params))]
         return (None, None, None) + (None,) * ctx.n_inputs + tuple(grads)
@@ -205,7 +274,7 @@ class ShardedFeatureEmbedding(nn.Module):
                 vocabs.append(0)
                 lvocabs.append(0)
             else:
-                rows = local_rows(int(fs.vocabulary_size), world, rank)
+                rows = local_rows(int(fs.vocabulary_size), world, rank, len(kinds))
                 if kind == "sparse":
                     self.second_order_embeddings[name] = nn.Embedding(rows, d)
                     self.first_order_embeddings[name] = nn.Embedding(rows, 1)
@@ -245,14 +314,17 @@ class ShardedFeatureEmbedding(nn.Module):
         self._param_is_table: List[bool] = []
         self._slot_of_param: List[int] = []
         self._rb_dev = None
+        self._px = None                   # PeerExchange (None: not created yet, False: unavailable)
+        self.p2p_capacity_rows = 0        # rows per exchange buffer; 0: sized by the first forward (2 x b x slots)
 
     def _init_weights(self) -> None:
         """Same family as the reference (embedding.py:66-74): xavier-uniform rows, zero padding row
-        (global id 0 lives on rank 0, local row 0), xavier Linears with zero bias."""
+        (global id 0 of field f lives on rank f mod W, local row 0), xavier Linears with zero bias."""
+        index = {name: f for f, name in enumerate(self.field_names)}
         for name, m in list(self.second_order_embeddings.items()) + list(self.first_order_embeddings.items()):
             if isinstance(m, (nn.Embedding, nn.EmbeddingBag)):
                 nn.init.xavier_uniform_(m.weight.data)
-                if self.rank == 0:
+                if self.rank == index[name] % self.world:
                     m.weight.data[0].zero_()
             else:
                 nn.init.xavier_uniform_(m.weight.data)
@@ -260,13 +332,13 @@ class ShardedFeatureEmbedding(nn.Module):
 
     @torch.no_grad()
     def load_from_full(self, full) -> None:
-        """Take this rank's rows (id = rank + W * local_row) and the replicated Linears from an
+        """Take this rank's rows (id = (rank - f) mod W + W * local_row) and the replicated Linears from an
         unsharded FeatureEmbedding."""
-        for name in self.field_names:
+        for f, name in enumerate(self.field_names):
             for mine, theirs in ((self.second_order_embeddings[name], full.second_order_embeddings[name]),
                                  (self.first_order_embeddings[name], full.first_order_embeddings[name])):
                 if isinstance(mine, (nn.Embedding, nn.EmbeddingBag)):
-                    rows = theirs.weight[self.rank::self.world]
+                    rows = theirs.weight[(self.rank - f) % self.world::self.world]
                     mine.weight[: rows.shape[0]].copy_(rows)
                 else:
                     mine.weight.copy_(theirs.weight)
@@ -348,7 +420,7 @@ class ShardedFeatureEmbedding(nn.Module):
         if self._rb_dev is None or self._rb_dev.device != ids.device:
             self._rb_dev = torch.tensor([self._global_row_base[i] for i, L in zip(self._table_idx, self._lens) for _ in range(L)],
                                         dtype=torch.int64, device=ids.device)
-        return route_ids(ids, self._rb_dev, self.world, self._lens, self._bag)
+        return route_ids(ids, self._rb_dev, self.world, self._lens, self._bag, [i % self.world for i in self._table_idx])
 
     def reply_buffer(self, n: int, like: torch.Tensor) -> torch.Tensor:
         """(1 + n, D + 4) buffer K1 reads as its table: row 0 is the reserved zero row (send positions are
@@ -372,6 +444,43 @@ class ShardedFeatureEmbedding(nn.Module):
                                         _lib.ptr(recv_keys), self._ptrs(params), _lib.ptr(rows), _lib.ptr(lkeys),
                                         _lib.stream_ptr()), "dfm_shard_gather")
         return rows, lkeys
+
+    def peer_exchange(self, device):
+        """The symmetric-memory exchange buffers (created on first use; None when peer memory is unavailable or
+        disabled with DFM_SHARD_P2P=0 -- the NCCL all-to-all path is used then)."""
+        import os
+        if self._px is False or self.comm is None or self.world == 1 or os.environ.get("DFM_SHARD_P2P", "1") == "0":
+            return None
+        if self._px is None:
+            try:
+                cap = int(getattr(self, "p2p_capacity_rows", 0)) or None
+                if cap is None:
+                    return None           # sized by the first forward (needs the batch size)
+                self._px = PeerExchange(self.comm, self.fm_embed_dim + 4, cap, device)
+            except Exception as e:        # no P2P / symmetric memory on this box: keep the NCCL path
+                import warnings
+                warnings.warn(f"peer-memory exchange unavailable ({e}); using NCCL all-to-all")
+                self._px = False
+                return None
+        return self._px
+
+    def gather_p2p(self, recv_keys: torch.Tensor, px: "PeerExchange", matrix, parity: int):
+        lib = _lib.lib()
+        local_plan, _ = self._ensure_plans()
+        params = self._ordered_params()
+        M, W, me = recv_keys.numel(), self.world, self.rank
+        lkeys = torch.empty((M,), device=recv_keys.device, dtype=torch.int32)
+        stride_b = (self.fm_embed_dim + 4) * 4
+        starts, bases, acc = [0], [], 0
+        for s_ in range(W):                                   # received keys are grouped by source rank
+            acc += matrix[s_][me]
+            starts.append(acc)
+            send_off = sum(matrix[s_][:me])                   # where rank me's segment starts in s_'s send order
+            bases.append(px.region(0, parity, s_) + (1 + send_off) * stride_b)
+        _lib.check(lib.dfm_shard_gather_p2p(local_plan, W, me, _lib.i64_array(self._global_row_base), M,
+                                            _lib.ptr(recv_keys), self._ptrs(params), W, _lib.i64_array(starts),
+                                            _lib.ptr_array(bases), _lib.ptr(lkeys), _lib.stream_ptr()), "dfm_shard_gather_p2p")
+        return lkeys
 
     def _virtual_ptrs(self, params, got):
         """Sample-side plan: every id table is the received row buffer (row stride D + 4, first-order
@@ -410,17 +519,33 @@ class ShardedFeatureEmbedding(nn.Module):
         return first, field, flat, fm, fm_sum, aux, fin_inputs
 
     def pack_grads(self, fin_inputs, pos, got, g_first, g_field, g_flat, g_fm, field, flat, fm_sum,
-                   params, lam, gscale, aux=None):
+                   params, lam, gscale, aux=None, p2p=None):
         lib = _lib.lib()
         _, sample_plan = self._ensure_plans()
         self._ordered_params()
         dev = flat.device
         b = flat.shape[0]
         n = got.shape[0] - 1
-        g_rows = torch.empty((n, self.fm_embed_dim + 4), device=dev, dtype=torch.float32)
-        _lib.check(lib.dfm_shard_pack_grad(sample_plan, b, _lib.ptr(pos), _lib.ptr(g_first), _lib.ptr(g_field),
-                                           _lib.ptr(g_flat), _lib.ptr(g_fm), _lib.ptr(fm_sum), field.data_ptr(),
-                                           _lib.ptr(aux), _lib.ptr(g_rows), _lib.stream_ptr()), "dfm_shard_pack_grad")
+        if p2p is not None:
+            px, matrix, parity = p2p
+            W, me = self.world, self.rank
+            stride_b = (self.fm_embed_dim + 4) * 4
+            starts, bases, acc = [0], [], 0
+            for r_ in range(W):                               # my send order is grouped by owner rank
+                acc += matrix[me][r_]
+                starts.append(acc)
+                recv_off = sum(matrix[s_][r_] for s_ in range(me))   # where my segment starts in r_'s receive order
+                bases.append(px.region(1, parity, r_) + recv_off * stride_b)
+            g_rows = None
+            _lib.check(lib.dfm_shard_pack_grad_p2p(sample_plan, b, _lib.ptr(pos), _lib.ptr(g_first), _lib.ptr(g_field),
+                                                   _lib.ptr(g_flat), _lib.ptr(g_fm), _lib.ptr(fm_sum), field.data_ptr(),
+                                                   _lib.ptr(aux), W, _lib.i64_array(starts), _lib.ptr_array(bases),
+                                                   _lib.stream_ptr()), "dfm_shard_pack_grad_p2p")
+        else:
+            g_rows = torch.empty((n, self.fm_embed_dim + 4), device=dev, dtype=torch.float32)
+            _lib.check(lib.dfm_shard_pack_grad(sample_plan, b, _lib.ptr(pos), _lib.ptr(g_first), _lib.ptr(g_field),
+                                               _lib.ptr(g_flat), _lib.ptr(g_fm), _lib.ptr(fm_sum), field.data_ptr(),
+                                               _lib.ptr(aux), _lib.ptr(g_rows), _lib.stream_ptr()), "dfm_shard_pack_grad")
         # DENSE-field Linear gradients (data-parallel parameters): K2 with the table part skipped
         dense_grads: Dict[int, torch.Tensor] = {}
         grads = []
@@ -506,6 +631,8 @@ class ShardedFeatureEmbedding(nn.Module):
         self._ensure_plans()
         params = self._ordered_params()
         inputs = self._prepare(batch)
+        if not self.p2p_capacity_rows:    # every rank derives the same capacity (same batch size and schema)
+            self.p2p_capacity_rows = 2 * inputs[0].shape[0] * max(self._S, 1) + 16
         need_bwd = torch.is_grad_enabled() and any(p.requires_grad for p in params)
         first, field, flat, fm = _ShardedEmbedFn.apply(self, len(inputs), need_bwd, *inputs, *params)
         field._dfm_fm = (fm, field._version)
@@ -517,6 +644,61 @@ class ShardedFeatureEmbedding(nn.Module):
 
     def table_parameters(self):
         return [p for p, t in zip(self._ordered_params(), self._param_is_table) if t]
+
+
+class DenseGradReducer:
+    """Data-parallel averaging of the replicated parameters' gradients, overlapped with the table backward.
+
+    ``early`` parameters (DNN / CIN / attention / head Linears) have their gradients before the embedding
+    backward starts: as soon as the last of them is accumulated (post-accumulate-grad hooks, the order the
+    autograd engine guarantees on every rank) ONE flat NCCL allreduce is launched asynchronously, so it runs on
+    NCCL's stream underneath the gradient exchange and the owner-side reduction.  ``late`` parameters (the
+    DENSE-field Linears inside the embedding) follow in a second, tiny allreduce in ``finish()``."""
+
+    def __init__(self, early, late, world: int, group=None):
+        import torch.distributed as dist
+        self.dist, self.group, self.world = dist, group, world
+        self.early = [p for p in early if p.requires_grad]
+        self.late = [p for p in late if p.requires_grad]
+        self._pending, self._work, self._flat = 0, None, None
+        if world > 1:
+            for p in self.early:
+                p.register_post_accumulate_grad_hook(self._hook)
+
+    def _hook(self, _param) -> None:
+        self._pending += 1
+        if self._pending == len(self.early):
+            self._flat = torch.cat([p.grad.reshape(-1) for p in self.early])
+            self._work = self.dist.all_reduce(self._flat, group=self.group, async_op=True)
+
+    @staticmethod
+    def _scatter(flat, params, world):
+        flat.div_(world)
+        off = 0
+        for p in params:
+            n = p.grad.numel()
+            p.grad.copy_(flat[off:off + n].view_as(p.grad))
+            off += n
+
+    def finish(self) -> None:
+        """Call after ``backward()``: waits for the early bucket, reduces the late one, writes both back."""
+        if self.world == 1:
+            return
+        if self._work is None:            # a parameter got no gradient this step: reduce what there is, now
+            got = [p for p in self.early if p.grad is not None]
+            if got:
+                flat = torch.cat([p.grad.reshape(-1) for p in got])
+                self.dist.all_reduce(flat, group=self.group)
+                self._scatter(flat, got, self.world)
+        else:
+            self._work.wait()
+            self._scatter(self._flat, self.early, self.world)
+        late = [p for p in self.late if p.grad is not None]
+        if late:
+            flat = torch.cat([p.grad.reshape(-1) for p in late])
+            self.dist.all_reduce(flat, group=self.group)
+            self._scatter(flat, late, self.world)
+        self._pending, self._work, self._flat = 0, None, None
 
 
 def allreduce_dense(params, world: int, group=None) -> None:

@@ -195,7 +195,8 @@ DFM_API int dfm_attn_bwd(const float* x, const float* g_out, int64_t batch, int 
                          void* workspace, size_t workspace_bytes, void* stream);
 
 /* ------------------------------------------------------------------------------------------
- * Row-sharded tables over W GPUs (new; the reference is single-device).  owner(id) = id mod W,
+ * Row-sharded tables over W GPUs (new; the reference is single-device).  owner(f, id) = (id + f) mod W
+ * (f = schema index of the field: spreads the hot small ids of the tables over the ranks),
  * local_row = id div W, per field (oracle: shard_route).  The NCCL all-to-all of keys / vectors /
  * vector gradients is issued by the host side between these calls.
  *   Exchanged rows are d_max + 4 floats wide (16-byte aligned): one collective carries the vector and
@@ -233,6 +234,21 @@ DFM_API int dfm_shard_pack_grad(const dfm_plan* plan, int64_t batch, const int64
                                 const float* g_first, const float* g_field, const float* g_flat,
                                 const float* g_fm, const float* fm_sum, const float* field_emb,
                                 const uint32_t* aux, float* g_rows, void* stream);
+/* Fused exchange over peer memory (NVLink P2P stores; peer buffers come from CUDA IPC / torch symmetric
+ * memory): the same two kernels write every row straight into the destination GPU's buffer instead of a
+ * local staging buffer followed by an all-to-all.  Rows [peer_start[p], peer_start[p+1]) of this rank's send
+ * order (dfm_shard_gather_p2p: of the received keys, which are grouped by source) go to
+ * peer_rows[p] + (i - peer_start[p]) * (d_max + 4).  The caller separates the writes from the consumer with
+ * a cross-GPU barrier. */
+DFM_API int dfm_shard_gather_p2p(const dfm_plan* local_plan, int world, int rank,
+                                 const int64_t* global_row_base, int64_t n_keys, const uint32_t* keys,
+                                 const float* const* params, int n_peers, const int64_t* peer_start,
+                                 float* const* peer_rows, uint32_t* local_keys, void* stream);
+DFM_API int dfm_shard_pack_grad_p2p(const dfm_plan* plan, int64_t batch, const int64_t* positions,
+                                    const float* g_first, const float* g_field, const float* g_flat,
+                                    const float* g_fm, const float* fm_sum, const float* field_emb,
+                                    const uint32_t* aux, int n_peers, const int64_t* peer_start,
+                                    float* const* peer_rows, void* stream);
 DFM_API int dfm_plan_set_table_stride(dfm_plan* plan, int row_stride, int w1_stride);
 DFM_API size_t dfm_rows_bwd_workspace_bytes(const dfm_plan* plan, int64_t n_rows);
 DFM_API int dfm_rows_bwd(const dfm_plan* plan, int64_t n_rows, const float* const* params,

@@ -485,8 +485,12 @@ def segment_heads(sorted_keys: np.ndarray):
     return k[head], np.concatenate([starts, [n_valid]])
 
 
-def shard_route(ids: np.ndarray, world: int, sent: Optional[np.ndarray] = None):
-    """Row sharding rule: owner = id mod W, local_row = id div W  (SURVEY 8(e)).
+def shard_route(ids: np.ndarray, world: int, sent: Optional[np.ndarray] = None, rot: Optional[np.ndarray] = None):
+    """Row sharding rule: owner = (id + rot) mod W, local_row = id div W  (SURVEY 8(e)), where rot is the
+    schema index of the slot's field (0 when not given): a plain ``id mod W`` would put the hottest ids
+    (1, 2, ... under Zipf-like skew) of EVERY table on the same ranks; rotating by the field index spreads
+    them, and ``id div W`` stays a dense local row index because the ids a rank owns in one table are
+    still one residue class.
 
     ids: flat int64 array in source order (slot index b*S + s, multi-hot bags expanded to their
     max_length slots).  sent: optional bool mask; False marks slots that are not exchanged -- the
@@ -495,7 +499,7 @@ def shard_route(ids: np.ndarray, world: int, sent: Optional[np.ndarray] = None):
     where perm is the stable permutation that groups the SENT slots by owner (position i of the send
     buffer holds ids[perm[i]]).
     """
-    owner = (ids % world).astype(np.int64)
+    owner = ((ids + (0 if rot is None else rot)) % world).astype(np.int64)
     local = (ids // world).astype(np.int64)
     if sent is None:
         sent = np.ones(ids.shape, dtype=bool)

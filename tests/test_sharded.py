@@ -36,6 +36,9 @@ def test_route_ids_matches_oracle_shard_route():
         seg = perm[offsets[w]:offsets[w + 1]]
         assert np.all(ids.reshape(-1)[seg] % W == w)
     assert local_rows(10, 4, 0) == 3 and local_rows(10, 4, 1) == 3 and local_rows(10, 4, 2) == 2 and local_rows(2, 4, 3) == 1
+    # rotated rule: field 1 puts id 0 on rank 1, so rank 0 owns ids 3 and 7 of a 10-row table
+    assert local_rows(10, 4, 0, field=1) == 2 and local_rows(10, 4, 1, field=1) == 3
+    assert sum(local_rows(1000, 8, r, field=5) for r in range(8)) == 1000
 
 
 def test_route_ids_multihot_skips_bag_padding():
@@ -57,8 +60,11 @@ def test_route_ids_multihot_skips_bag_padding():
     row_base = np.repeat(fbase, lens).astype(np.int64)
     slot_bag = np.repeat(bag, lens)
     sent = ~(slot_bag[None, :] & (ids == 0))
-    r = route_ids(torch.from_numpy(ids), torch.from_numpy(row_base), W, lens, bag)
-    owner, local, counts, offsets, perm = O.shard_route(ids.reshape(-1), W, sent.reshape(-1))
+    rot = [2, 0, 1, 2]                                     # owner = (id + rot[field]) mod W
+    slot_rot = np.repeat(rot, lens)
+    r = route_ids(torch.from_numpy(ids), torch.from_numpy(row_base), W, lens, bag, rot)
+    owner, local, counts, offsets, perm = O.shard_route(ids.reshape(-1), W, sent.reshape(-1), np.tile(slot_rot, b))
+    assert np.array_equal(owner, (ids + slot_rot[None, :]).reshape(-1) % W)
     assert r.counts.tolist() == counts.tolist() and int(counts.sum()) == int(sent.sum())
     assert r.order.tolist() == perm.tolist()
     keys = (ids + row_base[None, :]).reshape(-1)
@@ -110,6 +116,46 @@ def test_all_to_all_plumbing_gloo_world2():
         assert p.exitcode == 0
     assert all(r[1] and r[2] and r[3] for r in res), res
     assert sum(r[4] for r in res) == 2 * 20 * 3                   # every key arrived somewhere
+
+
+def _reducer_worker(rank, world, port, out):
+    import torch.distributed as dist
+    os.environ.update(MASTER_ADDR="127.0.0.1", MASTER_PORT=str(port))
+    dist.init_process_group("gloo", rank=rank, world_size=world)
+    from deepfm_b200.sharded import DenseGradReducer
+    torch.manual_seed(0)                                   # identical replicas
+    early = torch.nn.Sequential(torch.nn.Linear(6, 5), torch.nn.ReLU(), torch.nn.Linear(5, 1))
+    late = torch.nn.Linear(3, 6)                           # plays the embedding's DENSE-field Linears
+    red = DenseGradReducer(list(early.parameters()), list(late.parameters()), world)
+    ok = True
+    for step in range(2):                                  # twice: the hook counters must reset
+        gen = torch.Generator().manual_seed(10 * step + rank)
+        x = torch.randn(7, 3, generator=gen)
+        for p in list(early.parameters()) + list(late.parameters()):
+            p.grad = None
+        early(late(x)).sum().backward()
+        mine = [p.grad.clone() for p in list(early.parameters()) + list(late.parameters())]
+        red.finish()
+        for p, g in zip(list(early.parameters()) + list(late.parameters()), mine):
+            parts = [torch.empty_like(g) for _ in range(world)]
+            dist.all_gather(parts, g)
+            ok = ok and torch.allclose(p.grad, sum(parts) / world, atol=1e-6)
+    out.put((rank, ok))
+    dist.destroy_process_group()
+
+
+def test_dense_grad_reducer_gloo_world2():
+    ctx = mp.get_context("spawn")
+    q = ctx.Queue()
+    port = 31000 + os.getpid() % 2000
+    procs = [ctx.Process(target=_reducer_worker, args=(r, 2, port, q)) for r in range(2)]
+    for p in procs:
+        p.start()
+    res = [q.get(timeout=120) for _ in procs]
+    for p in procs:
+        p.join(timeout=60)
+        assert p.exitcode == 0
+    assert all(r[1] for r in res), res
 
 
 # ------------------------------------------------------------------------------------------ GPU
@@ -222,7 +268,7 @@ def test_sharded_equals_unsharded_emulated_ranks(W, D, multihot):
             slot = m._slot_of_param[i]
             name = m.field_names[slot // 5]
             ref = (full.second_order_embeddings if slot % 5 == 0 else full.first_order_embeddings)[name].weight.grad
-            ref = ref[r::W]
+            ref = ref[(r - slot // 5) % W::W]
             assert_close_rel(g[: ref.shape[0]].cpu(), ref.cpu(), 2e-5, f"rank {r} {name} slot {slot % 5}")
     # replicated DENSE-field Linears: the sum over ranks of the per-rank gradients is the full gradient
     for i, tab in enumerate(mods[0]._param_is_table):
