@@ -86,7 +86,9 @@ def base_line(args, n_gpus):
                    "dnn": [256, 128, 64], "table_grad": "row_sparse (sorted unique rows), L2 value exact",
                    "cache": "working set >> L2: 8.6 GB tables, 654 MB embeddings written per step, 4 rotating batches",
                    "parallelism": f"dp{n_gpus}" if n_gpus == 1 else
-                   f"dp{n_gpus} dense params (NCCL allreduce) + tables row-sharded over {n_gpus} ranks (NCCL all-to-all)"},
+                   f"dp{n_gpus} dense params + tables <= 4096 rows replicated (NCCL allreduce, overlapped) + large tables "
+                   f"row-sharded over {n_gpus} ranks (ids by NCCL all-to-all, vectors and gradients as NVLink peer-memory "
+                   f"stores fused into the gather / pack kernels)"},
     }
 
 

@@ -159,7 +159,7 @@ __device__ __forceinline__ void stage_fields(const DevPlan& P, FieldB* t) {
         FieldB e;
         e.w2 = fd.w2; e.w1 = fd.w1; e.row_base = (unsigned)fd.row_base; e.dim = fd.dim;
         e.flat_off = fd.flat_off; e.aux_off = fd.aux_off;
-        e.flags = fd.kind | (fd.combiner << 4) | ((fd.kind == DFM_SPARSE && fd.proj == nullptr) ? 0x100 : 0);
+        e.flags = fd.kind | (fd.combiner << 4) | ((fd.kind == DFM_SPARSE && fd.proj == nullptr) ? 0x100 : 0) | (fd.foreign ? 0x200 : 0);
         t[f] = e;
     }
 }
@@ -448,7 +448,7 @@ __device__ __forceinline__ void process_chunk_fast(const DevPlan& P, const DevGr
 __device__ __forceinline__ int field_of_key(const FieldB* t, int n_fields, uint32_t key) {
     int f = 0;
     for (int i = 0; i < n_fields; ++i)
-        if (t[i].dim > 0 && (t[i].flags & 0xf) != DFM_DENSE && key >= t[i].row_base) f = i;
+        if (t[i].dim > 0 && (t[i].flags & 0xf) != DFM_DENSE && !(t[i].flags & 0x200) && key >= t[i].row_base) f = i;
     return f;
 }
 
@@ -1054,12 +1054,12 @@ static int embed_bwd_impl(const dfm_plan* plan, int64_t batch, long long direct_
         GradDev& g = GR->g[f];
         g.gw2 = grads[5 * f + 0]; g.gb2 = grads[5 * f + 1]; g.gw1 = grads[5 * f + 2];
         g.gb1 = grads[5 * f + 3]; g.gproj = grads[5 * f + 4];
-        const bool table = plan->kind[f] != DFM_DENSE;
+        const bool table = plan->kind[f] != DFM_DENSE && !plan->foreign[f];
         if (table && mode == DFM_GRAD_DENSE) {
             DFM_REQUIRE(g.gw2 && g.gw1, DFM_ERR_INVALID, "dfm_embed_bwd: dense mode needs table grads for field %d", f);
             aligned = aligned && al16(g.gw2);
         }
-        if (!table && !direct) DFM_REQUIRE(g.gw2 && g.gb2 && g.gw1 && g.gb1, DFM_ERR_INVALID, "dfm_embed_bwd: DENSE field %d grads missing", f);
+        if (plan->kind[f] == DFM_DENSE && !direct) DFM_REQUIRE(g.gw2 && g.gb2 && g.gw1 && g.gb1, DFM_ERR_INVALID, "dfm_embed_bwd: DENSE field %d grads missing", f);
         if (plan->dim[f] != plan->fm_dim && !direct) DFM_REQUIRE(g.gproj, DFM_ERR_INVALID, "dfm_embed_bwd: projection grad of field %d missing", f);
     }
     if (!aligned) V = 1;
@@ -1093,7 +1093,7 @@ static int embed_bwd_impl(const dfm_plan* plan, int64_t batch, long long direct_
     // 1. dense mode: every element of every table gradient starts as 2*l2*w (or 0)
     if (mode == DFM_GRAD_DENSE) {
         for (int f = 0; f < plan->n_fields; ++f) {
-            if (plan->kind[f] == DFM_DENSE) continue;
+            if (plan->kind[f] == DFM_DENSE || plan->foreign[f]) continue;
             const long long n2 = plan->vocab[f] * plan->dim[f], n1 = plan->vocab[f];
             int b2 = (int)(ceil_div(n2, 1024) < fill_blocks ? ceil_div(n2, 1024) : fill_blocks);
             int b1 = (int)(ceil_div(n1, 1024) < fill_blocks ? ceil_div(n1, 1024) : fill_blocks);

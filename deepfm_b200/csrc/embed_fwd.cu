@@ -129,11 +129,13 @@ struct SlotS {              // one id slot
     unsigned row_base;      // key = row_base + id
     int vocab;
     int stride_pos;         // (ids per sample << 16) | position in the bag
-    int sparse;             // 1: SPARSE (first-order term taken in phase 1)
+    int sparse;             // 1: SPARSE (first-order term taken in phase 1); bit 1: foreign (no sort key)
+    int w1s;                // floats between consecutive first-order weights
 };
 struct FieldS {             // one field, what the plain runs need
     const float* w2;
     const float* b2;
+    int rs;                 // floats between consecutive table rows
 };
 struct DenseS {             // one DENSE field
     const float* in;
@@ -163,10 +165,12 @@ embed_fwd_kernel(const __grid_constant__ DevPlan P, long long B, int G, int smem
         SlotS e;
         e.in = reinterpret_cast<const long long*>(fd.in); e.w1 = fd.w1;
         e.row_base = (unsigned)fd.row_base; e.vocab = fd.vocab;
-        e.stride_pos = (fd.max_len << 16) | P.slot_pos[s]; e.sparse = fd.kind == DFM_SPARSE;
+        e.stride_pos = (fd.max_len << 16) | P.slot_pos[s];
+        e.sparse = (fd.kind == DFM_SPARSE ? 1 : 0) | (fd.foreign ? 2 : 0);
+        e.w1s = fd.w1_stride;
         t_slot[s] = e;
     }
-    for (int f = threadIdx.x; f < F; f += blockDim.x) { t_field[f].w2 = P.f[f].w2; t_field[f].b2 = P.f[f].b2; }
+    for (int f = threadIdx.x; f < F; f += blockDim.x) { t_field[f].w2 = P.f[f].w2; t_field[f].b2 = P.f[f].b2; t_field[f].rs = P.f[f].row_stride; }
     for (int i = threadIdx.x; i < ND; i += blockDim.x) {
         const FieldDev& fd = P.f[P.dense_field[i]];
         t_dense[i].in = reinterpret_cast<const float*>(fd.in); t_dense[i].w1 = fd.w1; t_dense[i].b1 = fd.b1;
@@ -181,8 +185,6 @@ embed_fwd_kernel(const __grid_constant__ DevPlan P, long long B, int G, int smem
     float* s_x = reinterpret_cast<float*>(s_ids + S);
     float* s_raw = s_x + ND;
     const int nch_e = D / V;
-    const int rs = P.row_stride ? P.row_stride : D;      // table row stride of the plain SPARSE runs
-    const int w1s = P.w1_stride ? P.w1_stride : 1;
     const long long n_tiles = (B + gpb - 1) / gpb;
     // persistent blocks: the tables above are staged once, then the block walks sample tiles
     for (long long tile = blockIdx.x; tile < n_tiles; tile += gridDim.x) {
@@ -201,8 +203,8 @@ embed_fwd_kernel(const __grid_constant__ DevPlan P, long long B, int G, int smem
             id = 0;
         }
         s_ids[s] = (int)id;
-        if (keys && active) keys[b * S + s] = id ? e.row_base + (unsigned)id : P.pad_key;
-        if (e.sparse) fo_acc += __ldg(e.w1 + (size_t)id * w1s);        // row 0 returned as stored
+        if (keys && active) keys[b * S + s] = (id && !(e.sparse & 2)) ? e.row_base + (unsigned)id : P.pad_key;
+        if (e.sparse & 1) fo_acc += __ldg(e.w1 + (size_t)id * e.w1s);  // row 0 returned as stored
     }
     for (int i = j; i < ND; i += G) {
         const DenseS e = t_dense[i];
@@ -235,13 +237,13 @@ embed_fwd_kernel(const __grid_constant__ DevPlan P, long long B, int G, int smem
                 VecF<V> r[4], nx[4];
                 if (run.n >= 4) {
 #pragma unroll
-                    for (int i = 0; i < 4; ++i) r[i] = vload<V>(tf[i].w2 + (size_t)ids[i] * rs + j * V);
+                    for (int i = 0; i < 4; ++i) r[i] = vload<V>(tf[i].w2 + (size_t)ids[i] * tf[i].rs + j * V);
                 }
                 for (; u + 4 <= run.n; u += 4) {
                     const bool more = u + 8 <= run.n;
                     if (more) {
 #pragma unroll
-                        for (int i = 0; i < 4; ++i) nx[i] = vload<V>(tf[u + 4 + i].w2 + (size_t)ids[u + 4 + i] * rs + j * V);
+                        for (int i = 0; i < 4; ++i) nx[i] = vload<V>(tf[u + 4 + i].w2 + (size_t)ids[u + 4 + i] * tf[u + 4 + i].rs + j * V);
                     }
                     if (active) {
 #pragma unroll
@@ -263,7 +265,7 @@ embed_fwd_kernel(const __grid_constant__ DevPlan P, long long B, int G, int smem
                     }
                 }
                 for (; u < run.n; ++u) {
-                    const VecF<V> r = vload<V>(tf[u].w2 + (size_t)ids[u] * rs + j * V);
+                    const VecF<V> r = vload<V>(tf[u].w2 + (size_t)ids[u] * tf[u].rs + j * V);
                     if (active) {
                         vstore_stream<V>(dst + u * D, r);
                         if (two_views) vstore_stream<V>(dst2 + u * D, r);
@@ -307,7 +309,7 @@ embed_fwd_kernel(const __grid_constant__ DevPlan P, long long B, int G, int smem
                 const bool mean = fd.combiner == DFM_MEAN;
                 int cnt = 0;
                 if (lane_on) {
-                    VecF<V> r = pool_plain<V>(fd.w2, ids, L, rs, j, cnt);
+                    VecF<V> r = pool_plain<V>(fd.w2, ids, L, fd.row_stride, j, cnt);
                     if (mean && cnt > 0) {
                         const float fc = (float)cnt;
 #pragma unroll
@@ -325,7 +327,7 @@ embed_fwd_kernel(const __grid_constant__ DevPlan P, long long B, int G, int smem
                 int c1 = 0;
                 for (int l = j; l < L; l += G) {
                     const int id = ids[l];
-                    if (id) { w1sum += __ldg(fd.w1 + (size_t)id * w1s); ++c1; }
+                    if (id) { w1sum += __ldg(fd.w1 + (size_t)id * fd.w1_stride); ++c1; }
                 }
                 w1sum = group_sum(w1sum, G, gmask);
                 c1 = (int)group_sum((float)c1, G, gmask);
@@ -451,7 +453,7 @@ __global__ void emit_keys_kernel(const __grid_constant__ DevPlan P, long long B,
         const FieldDev& fd = P.f[P.slot_field[s]];
         long long id = __ldg(reinterpret_cast<const long long*>(fd.in) + b * fd.max_len + P.slot_pos[s]);
         if (id < 0 || id >= fd.vocab) id = 0;
-        keys[i] = id ? (uint32_t)(fd.row_base + id) : P.pad_key;
+        keys[i] = (id && !fd.foreign) ? (uint32_t)(fd.row_base + id) : P.pad_key;
     }
 }
 
@@ -477,7 +479,10 @@ int dfm_plan::fill(DevPlan& P, const void* const* inputs, const float* const* pa
         fd.kind = kind[f]; fd.dim = dim[f]; fd.flat_off = flat_off[f]; fd.max_len = max_len[f];
         fd.combiner = combiner[f]; fd.slot_base = slot_base[f]; fd.aux_off = aux_off[f];
         fd.vocab = (int)vocab[f];
-        if (kind[f] != DFM_DENSE) aligned = aligned && al16(fd.w2);
+        fd.row_stride = row_stride[f] ? row_stride[f] : dim[f];
+        fd.w1_stride = w1_stride[f] ? w1_stride[f] : 1;
+        fd.foreign = foreign[f];
+        if (kind[f] != DFM_DENSE) aligned = aligned && al16(fd.w2) && fd.row_stride % 4 == 0;
     }
     for (int s = 0; s < S; ++s) {
         P.slot_field[s] = (unsigned short)slot_field[s];
@@ -498,7 +503,6 @@ int dfm_plan::fill(DevPlan& P, const void* const* inputs, const float* const* pa
         if (kind[f] == DFM_DENSE) P.dense_field[n_dense++] = (unsigned short)f;
     }
     P.n_runs = n_runs; P.n_dense = n_dense;
-    P.row_stride = row_stride; P.w1_stride = w1_stride;
     return (vec == 4 && aligned) ? 4 : 1;
 }
 
@@ -542,6 +546,7 @@ dfm_plan* dfm_plan_create(int n_fields, const int32_t* kind, const int32_t* dim,
         p->vocab.push_back(k == DFM_DENSE ? 0 : vocab[f]);
         p->flat_off.push_back(T); p->slot_base.push_back(S); p->aux_off.push_back(A);
         p->row_base.push_back(rows);
+        p->row_stride.push_back(0); p->w1_stride.push_back(0); p->foreign.push_back(0);
         T += d;
         if (k != DFM_DENSE) {
             for (int l = 0; l < L; ++l) { p->slot_field.push_back(f); p->slot_pos.push_back(l); }
@@ -570,14 +575,28 @@ dfm_plan* dfm_plan_create(int n_fields, const int32_t* kind, const int32_t* dim,
 
 void dfm_plan_destroy(dfm_plan* plan) { delete plan; }
 
+int dfm_plan_set_field_source(dfm_plan* plan, int field, int row_stride, int w1_stride, int foreign) {
+    DFM_REQUIRE(plan && field >= 0 && field < plan->n_fields && row_stride >= 0 && w1_stride >= 0, DFM_ERR_INVALID,
+                "dfm_plan_set_field_source: bad argument");
+    const int f = field;
+    DFM_REQUIRE(plan->kind[f] != DFM_DENSE, DFM_ERR_INVALID, "dfm_plan_set_field_source: field %d has no id table", f);
+    if (row_stride || w1_stride)
+        DFM_REQUIRE(plan->dim[f] == plan->fm_dim && (plan->kind[f] == DFM_SPARSE || plan->combiner[f] != DFM_MAX), DFM_ERR_UNSUPPORTED,
+                    "dfm_plan_set_field_source: only plain SPARSE / sum- or mean-bag fields (dim == fm_dim) may use a strided row buffer");
+    DFM_REQUIRE(row_stride == 0 || row_stride >= plan->dim[f], DFM_ERR_INVALID, "dfm_plan_set_field_source: stride < dim");
+    plan->row_stride[f] = row_stride; plan->w1_stride[f] = w1_stride; plan->foreign[f] = foreign ? 1 : 0;
+    plan->recompute_rows();
+    if (plan->total_rows >= 0xffffffffLL) { set_error("dfm_plan_set_field_source: %lld rows (max 2^32-2)", plan->total_rows); return DFM_ERR_UNSUPPORTED; }
+    return DFM_OK;
+}
+
 int dfm_plan_set_table_stride(dfm_plan* plan, int row_stride, int w1_stride) {
-    DFM_REQUIRE(plan && row_stride >= 0 && w1_stride >= 0, DFM_ERR_INVALID, "dfm_plan_set_table_stride: bad argument");
-    for (int f = 0; f < plan->n_fields; ++f)
-        DFM_REQUIRE(plan->kind[f] == DFM_DENSE || (plan->dim[f] == plan->fm_dim &&
-                        (plan->kind[f] == DFM_SPARSE || plan->combiner[f] != DFM_MAX)), DFM_ERR_UNSUPPORTED,
-                    "dfm_plan_set_table_stride: only plain SPARSE / sum- or mean-bag fields (dim == fm_dim) may use a strided row buffer");
-    DFM_REQUIRE(row_stride == 0 || row_stride >= plan->fm_dim, DFM_ERR_INVALID, "dfm_plan_set_table_stride: stride < dim");
-    plan->row_stride = row_stride; plan->w1_stride = w1_stride;
+    DFM_REQUIRE(plan, DFM_ERR_INVALID, "dfm_plan_set_table_stride: null plan");
+    for (int f = 0; f < plan->n_fields; ++f) {
+        if (plan->kind[f] == DFM_DENSE) continue;
+        int rc = dfm_plan_set_field_source(plan, f, row_stride, w1_stride, plan->foreign[f]);
+        if (rc) return rc;
+    }
     return DFM_OK;
 }
 

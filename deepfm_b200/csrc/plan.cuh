@@ -19,6 +19,8 @@ struct FieldDev {
     const float* proj;  // (D, d) or nullptr
     long long row_base; // first global row of this field's table
     int kind, dim, flat_off, max_len, combiner, slot_base, aux_off, vocab;
+    int row_stride, w1_stride;   // floats between consecutive rows of the id table / first-order table
+    int foreign;                 // 1: the table's gradient is produced elsewhere (no sort key, no table grad here)
 };
 
 struct GradDev {
@@ -35,7 +37,6 @@ struct DevPlan {
     int n_fields, D, T, S, A, aliased, max_tdim;
     unsigned pad_key;
     int n_runs, n_dense;
-    int row_stride, w1_stride;   // floats between consecutive rows of every id table (0: dim / 1)
     FieldDev f[MAX_FIELDS];
     FieldRun runs[MAX_FIELDS];
     unsigned short slot_field[MAX_SLOTS];
@@ -57,7 +58,21 @@ struct dfm_plan {
     int T = 0, S = 0, A = 0, aliasable = 0, max_tdim = 0, key_bits = 0, vec = 1;
     long long total_rows = 0;
     int n_proj_expected = 0;
-    int row_stride = 0, w1_stride = 0;   // see dfm_plan_set_table_stride
+    std::vector<int> row_stride, w1_stride, foreign;   // per field, see dfm_plan_set_field_source
+
+    // row_base / total_rows / key_bits over the fields whose gradient is produced here (foreign fields own no keys)
+    void recompute_rows() {
+        long long rows = 0;
+        for (int f = 0; f < n_fields; ++f) {
+            row_base[f] = rows;
+            if (kind[f] != DFM_DENSE && !foreign[f]) rows += vocab[f];
+        }
+        row_base[n_fields] = rows;
+        total_rows = rows;
+        int bits = 1;
+        while ((1ULL << bits) <= (unsigned long long)rows) ++bits;   // PAD key == rows must sort last
+        key_bits = bits;
+    }
 
     // Fill the per-call device image.  Returns the vector width usable for this call
     // (4 only if every dimension is a multiple of 4 and every pointer is 16-byte aligned).

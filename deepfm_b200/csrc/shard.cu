@@ -108,6 +108,7 @@ shard_pack_kernel(const __grid_constant__ ShardArgs a, const __grid_constant__ P
     for (long long i = (long long)blockIdx.x * gpb + gl; i < n; i += (long long)gridDim.x * gpb) {
         const long long b = i / p.S;
         const int s = (int)(i - b * p.S);
+        if (p.slot_tf[s] == 0xffff) continue;                  // replicated table: its gradient is local
         const ShardField& sf = a.f[p.slot_tf[s]];
         const long long q = __ldg(p.pos + p.B * sf.slot_base + b * sf.max_len + (s - sf.slot_base)) - 1;
         if (q < 0) continue;                                   // padding entry of a bag: nothing was sent
@@ -170,6 +171,7 @@ struct RouteArgs {
 __device__ __forceinline__ int route_owner(const RouteArgs& a, const RouteField* t, const unsigned short* slot_tf,
                                            long long i, long long& b, int& s, long long& id, const RouteField*& rf) {
     b = i / a.S; s = (int)(i - b * a.S);
+    if (slot_tf[s] == 0xffff) { rf = nullptr; id = 0; return -1; }      // replicated table: looked up locally
     rf = t + slot_tf[s];
     id = __ldg(rf->ids + b * rf->max_len + (s - rf->slot_base));
     if (rf->bag && id == 0) return -1;
@@ -241,7 +243,7 @@ route_scatter_kernel(const __grid_constant__ RouteArgs a, const long long* __res
             if (lane == 0) warp_cnt[warp][w] = __popc(m);
         }
         __syncthreads();
-        if (i < n) {
+        if (i < n && rf) {
             long long q = -1;
             if (o >= 0) {
                 q = run[o] + rank;
@@ -263,6 +265,12 @@ route_scatter_kernel(const __grid_constant__ RouteArgs a, const long long* __res
 
 using namespace dfm;
 
+// Table fields of the plan that take part in the exchange: on the owner side (need_params) the fields whose
+// gradient is produced here, on the sample side the FOREIGN fields (their tables live on the owners).
+static bool shard_field(const dfm_plan* plan, int f, bool owner_side) {
+    return plan->kind[f] != DFM_DENSE && (owner_side ? !plan->foreign[f] : plan->foreign[f] != 0);
+}
+
 static int fill_shard_args(const dfm_plan* local_plan, const int64_t* global_row_base, const float* const* params,
                            int world, int rank, ShardArgs& a, bool need_params) {
     memset(&a, 0, sizeof(a));
@@ -270,7 +278,7 @@ static int fill_shard_args(const dfm_plan* local_plan, const int64_t* global_row
     int n = 0;
     for (int f = 0; f < local_plan->n_fields; ++f) {
         const int k = local_plan->kind[f];
-        if (k == DFM_DENSE) continue;
+        if (!shard_field(local_plan, f, need_params)) continue;
         if (local_plan->dim[f] != local_plan->fm_dim || local_plan->dim[f] % 4 ||
             (k == DFM_SEQUENCE && local_plan->combiner[f] == DFM_MAX)) {
             set_error("sharded tables support SPARSE and sum/mean SEQUENCE fields with embedding_dim == fm_embed_dim, "
@@ -295,11 +303,11 @@ static int fill_shard_args(const dfm_plan* local_plan, const int64_t* global_row
     return DFM_OK;
 }
 
-// id slot -> index among the table (non-DENSE) fields
+// id slot -> index among the exchanged (sample side: foreign) table fields, 0xffff for the other slots
 static void fill_slot_tf(const dfm_plan* plan, unsigned short* slot_tf) {
-    std::vector<int> tf(plan->n_fields, 0);
+    std::vector<int> tf(plan->n_fields, 0xffff);
     int n = 0;
-    for (int f = 0; f < plan->n_fields; ++f) if (plan->kind[f] != DFM_DENSE) tf[f] = n++;
+    for (int f = 0; f < plan->n_fields; ++f) if (shard_field(plan, f, false)) tf[f] = n++;
     for (int s = 0; s < plan->S; ++s) slot_tf[s] = (unsigned short)tf[plan->slot_field[s]];
 }
 
@@ -448,7 +456,7 @@ int dfm_shard_route(const dfm_plan* plan, int world, const int64_t* global_row_b
     a->S = plan->S; a->world = world; a->B = batch;
     int nt = 0;
     for (int f = 0; f < plan->n_fields; ++f) {
-        if (plan->kind[f] == DFM_DENSE) continue;
+        if (!shard_field(plan, f, false)) continue;
         DFM_REQUIRE(inputs[f], DFM_ERR_INVALID, "dfm_shard_route: field %d has no id column", f);
         RouteField& rf = a->f[nt++];
         rf.ids = static_cast<const long long*>(inputs[f]);

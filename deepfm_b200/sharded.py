@@ -20,6 +20,12 @@ A bag is exchanged id by id (padding entries are not sent), pooled by K1 on the 
 bag's global non-pad count as the mean divisor, and every member's gradient row travels back to the
 row's owner, so the owner-side reduction is unchanged.
 
+Small tables (``vocabulary_size <= replicate_below``, default 4096 rows = 1 MB at D = 64) are REPLICATED, not
+sharded (sharding them is pure overhead): every rank looks them up locally inside the same K1
+launch, produces their dense gradient with the local sort/segment-reduce, and the reducer averages it with the
+other data-parallel parameters.  On the Criteo shape that takes 14 of the 26 tables -- and the hottest ids of
+the batch -- out of the exchange.
+
 The phases are plain methods so that a single process can emulate ``W`` ranks (tests) and so that
 the routing logic (pure torch ops) runs on CPU tensors under gloo.
 """
@@ -213,7 +219,7 @@ class _ShardedEmbedFn(torch.autograd.Function):
             rows, lkeys = mod.gather(recv_keys)
             got = mod.reply_buffer(int(sum(send_counts)), rows)            # (1 + n, D + 4): zero row, then the replies
             comm.all_to_all(rows, recv_counts, send_counts, out=got[1:])   # vector + first-order weight per row
-        first, field, flat, fm, fm_sum, aux, fin_inputs = mod.finish(inputs, route.pos, got, need_bwd)
+        first, field, flat, fm, fm_sum, aux, fin_inputs, keys = mod.finish(inputs, route.pos, got, need_bwd)
         ctx.mod, ctx.n_inputs = mod, n_inputs
         ctx.counts = (send_counts, recv_counts)
         ctx.p2p = (px, matrix, parity) if use_p2p else None
@@ -221,6 +227,7 @@ class _ShardedEmbedFn(torch.autograd.Function):
         ctx.l2, ctx.done = None, False
         if need_bwd:
             ctx.save_for_backward(field, flat, fm_sum, route.pos, lkeys, got, aux, *fin_inputs, *params)
+            ctx.keys = keys
             mod._live_ctx = weakref.ref(ctx)
         return first, field, flat, fm
 
@@ -237,7 +244,8 @@ class _ShardedEmbedFn(torch.autograd.Function):
         ctx.done = True
         cont = lambda g: None if g is None else g.contiguous()
         g_rows, dense_grads = mod.pack_grads(fin_inputs, pos, got, cont(g_first), cont(g_field), cont(g_flat),
-                                             cont(g_fm), field, flat, fm_sum, params, lam, gscale, aux, p2p=ctx.p2p)
+                                             cont(g_fm), field, flat, fm_sum, params, lam, gscale, aux, p2p=ctx.p2p,
+                                             keys=ctx.keys)
         if ctx.p2p is not None:           # the gradient rows were stored straight into the owners' buffers
             px, matrix, parity = ctx.p2p
             px.barrier(1)
@@ -250,9 +258,11 @@ class _ShardedEmbedFn(torch.autograd.Function):
 
 
 class ShardedFeatureEmbedding(nn.Module):
-    def __init__(self, schema, fm_embed_dim: int = 16, world: int = 1, rank: int = 0, comm=None) -> None:
+    def __init__(self, schema, fm_embed_dim: int = 16, world: int = 1, rank: int = 0, comm=None,
+                 replicate_below: int = 4096) -> None:
         super().__init__()
         self.schema, self.fm_embed_dim = schema, fm_embed_dim
+        self.replicate_below = int(replicate_below)
         self.world, self.rank, self.comm = world, rank, comm
         self.field_names = list(schema.fields.keys())
         self.second_order_embeddings = nn.ModuleDict()
@@ -274,7 +284,8 @@ class ShardedFeatureEmbedding(nn.Module):
                 vocabs.append(0)
                 lvocabs.append(0)
             else:
-                rows = local_rows(int(fs.vocabulary_size), world, rank, len(kinds))
+                replicated = int(fs.vocabulary_size) <= self.replicate_below
+                rows = int(fs.vocabulary_size) if replicated else local_rows(int(fs.vocabulary_size), world, rank, len(kinds))
                 if kind == "sparse":
                     self.second_order_embeddings[name] = nn.Embedding(rows, d)
                     self.first_order_embeddings[name] = nn.Embedding(rows, 1)
@@ -289,19 +300,23 @@ class ShardedFeatureEmbedding(nn.Module):
             combiners.append(_lib.COMBINER[comb] if kind == "sequence" else _lib.SUM)
         self._kinds, self._dims, self._vocabs, self._lvocabs = kinds, dims, vocabs, lvocabs
         self._max_lens, self._combiners = lens, combiners
-        self._init_weights()
         self.num_fields = len(kinds)
-        self._table_idx = [i for i, k in enumerate(kinds) if k != _lib.DENSE]
+        self._repl_idx = [i for i, k in enumerate(kinds) if k != _lib.DENSE and vocabs[i] <= self.replicate_below]
+        repl = set(self._repl_idx)
+        self._table_idx = [i for i, k in enumerate(kinds) if k != _lib.DENSE and i not in repl]   # the SHARDED tables
         self._sparse_idx = self._table_idx                      # historical name
+        self._all_tables = [i for i, k in enumerate(kinds) if k != _lib.DENSE]
+        self._all_lens = [lens[i] for i in self._all_tables]
+        self._all_S = sum(self._all_lens)                                                          # id slots of the plan
         self._lens = [lens[i] for i in self._table_idx]
         self._bag = [kinds[i] == _lib.SEQUENCE for i in self._table_idx]
         self._S = sum(self._lens)
-        self._A = sum(1 for i in self._table_idx if kinds[i] == _lib.SEQUENCE and combiners[i] == _lib.MEAN)
+        self._A = sum(1 for i in range(len(kinds)) if kinds[i] == _lib.SEQUENCE and combiners[i] == _lib.MEAN)   # aux words / sample
         self._T = sum(dims)
         grb, lrb = [0], [0]
-        for k, v, lv in zip(kinds, vocabs, lvocabs):
+        for i, (k, v, lv) in enumerate(zip(kinds, vocabs, lvocabs)):
             grb.append(grb[-1] + (v if k != _lib.DENSE else 0))
-            lrb.append(lrb[-1] + (lv if k != _lib.DENSE else 0))
+            lrb.append(lrb[-1] + (lv if (k != _lib.DENSE and i not in repl) else 0))    # owner-side keys: sharded tables only
         if grb[-1] >= 2 ** 31:
             raise NotImplementedError("sharded tables: total rows must stay below 2^31")
         self._global_row_base, self._row_base = grb, lrb
@@ -316,6 +331,7 @@ class ShardedFeatureEmbedding(nn.Module):
         self._rb_dev = None
         self._px = None                   # PeerExchange (None: not created yet, False: unavailable)
         self.p2p_capacity_rows = 0        # rows per exchange buffer; 0: sized by the first forward (2 x b x slots)
+        self._init_weights()
 
     def _init_weights(self) -> None:
         """Same family as the reference (embedding.py:66-74): xavier-uniform rows, zero padding row
@@ -324,7 +340,7 @@ class ShardedFeatureEmbedding(nn.Module):
         for name, m in list(self.second_order_embeddings.items()) + list(self.first_order_embeddings.items()):
             if isinstance(m, (nn.Embedding, nn.EmbeddingBag)):
                 nn.init.xavier_uniform_(m.weight.data)
-                if self.rank == index[name] % self.world:
+                if self.rank == index[name] % self.world or index[name] in self._repl_idx:
                     m.weight.data[0].zero_()
             else:
                 nn.init.xavier_uniform_(m.weight.data)
@@ -337,7 +353,9 @@ class ShardedFeatureEmbedding(nn.Module):
         for f, name in enumerate(self.field_names):
             for mine, theirs in ((self.second_order_embeddings[name], full.second_order_embeddings[name]),
                                  (self.first_order_embeddings[name], full.first_order_embeddings[name])):
-                if isinstance(mine, (nn.Embedding, nn.EmbeddingBag)):
+                if isinstance(mine, (nn.Embedding, nn.EmbeddingBag)) and f in self._repl_idx:
+                    mine.weight.copy_(theirs.weight)
+                elif isinstance(mine, (nn.Embedding, nn.EmbeddingBag)):
                     rows = theirs.weight[(self.rank - f) % self.world::self.world]
                     mine.weight[: rows.shape[0]].copy_(rows)
                 else:
@@ -358,11 +376,16 @@ class ShardedFeatureEmbedding(nn.Module):
                     raise ValueError(f"dfm_plan_create: {_lib.last_error()}")
                 return C.c_void_p(p)
             self._virtual_cap = min(VIRTUAL_VOCAB, (2 ** 32 - 2) // max(len(self._table_idx), 1))
-            virt = [self._virtual_cap if k != _lib.DENSE else 0 for k in self._kinds]
+            shard = set(self._table_idx)
+            virt = [self._virtual_cap if i in shard else v for i, v in enumerate(self._vocabs)]
             sample_plan = make(virt)
-            _lib.check(lib.dfm_plan_set_table_stride(sample_plan, self.fm_embed_dim + 4, self.fm_embed_dim + 4),
-                       "dfm_plan_set_table_stride")
-            self._plans = (make(self._lvocabs), sample_plan)
+            D4 = self.fm_embed_dim + 4
+            for i in self._table_idx:     # sample side: sharded tables = the received reply rows, gradient made by the owner
+                _lib.check(lib.dfm_plan_set_field_source(sample_plan, i, D4, D4, 1), "dfm_plan_set_field_source")
+            local_plan = make(self._lvocabs)
+            for i in self._repl_idx:      # owner side: replicated tables are none of its business
+                _lib.check(lib.dfm_plan_set_field_source(local_plan, i, 0, 0, 1), "dfm_plan_set_field_source")
+            self._plans = (local_plan, sample_plan)
         return self._plans
 
     def __del__(self):
@@ -379,8 +402,9 @@ class ShardedFeatureEmbedding(nn.Module):
         for f, name in enumerate(self.field_names):
             second, first = self.second_order_embeddings[name], self.first_order_embeddings[name]
             dense = self._kinds[f] == _lib.DENSE
-            entries = [(0, second.weight, not dense)] + ([(1, second.bias, False)] if dense else []) + \
-                      [(2, first.weight, not dense)] + ([(3, first.bias, False)] if dense else [])
+            shard = not dense and f not in self._repl_idx      # replicated tables are data-parallel parameters
+            entries = [(0, second.weight, shard)] + ([(1, second.bias, False)] if dense else []) + \
+                      [(2, first.weight, shard)] + ([(3, first.bias, False)] if dense else [])
             for k, p, tab in entries:
                 out.append(p)
                 is_table.append(tab)
@@ -402,8 +426,8 @@ class ShardedFeatureEmbedding(nn.Module):
             lib = _lib.lib()
             _, sample_plan = self._ensure_plans()
             dev = inputs[0].device
-            b, S, W = inputs[0].shape[0], self._S, self.world
-            send_keys = torch.empty((b * S,), device=dev, dtype=torch.int32)
+            b, S, W = inputs[0].shape[0], self._all_S, self.world
+            send_keys = torch.empty((b * max(self._S, 1),), device=dev, dtype=torch.int32)
             pos = torch.empty((b * S,), device=dev, dtype=torch.int64)
             counts = torch.empty((W,), device=dev, dtype=torch.int64)
             ws = torch.empty((max(lib.dfm_shard_route_workspace_bytes(sample_plan, b), 16),), device=dev, dtype=torch.uint8)
@@ -420,7 +444,20 @@ class ShardedFeatureEmbedding(nn.Module):
         if self._rb_dev is None or self._rb_dev.device != ids.device:
             self._rb_dev = torch.tensor([self._global_row_base[i] for i, L in zip(self._table_idx, self._lens) for _ in range(L)],
                                         dtype=torch.int64, device=ids.device)
-        return route_ids(ids, self._rb_dev, self.world, self._lens, self._bag, [i % self.world for i in self._table_idx])
+        r = route_ids(ids, self._rb_dev, self.world, self._lens, self._bag, [i % self.world for i in self._table_idx])
+        # positions in the plan's layout: one block per table field (replicated tables: zeros, nothing is sent)
+        full = torch.zeros(b * self._all_S, dtype=torch.int64, device=ids.device)
+        mine = dict(zip(self._table_idx, field_positions(r.pos, b, self._lens)))
+        for i, blk in zip(self._all_tables, field_positions(full, b, self._all_lens)):
+            if i in mine:
+                blk.copy_(mine[i])
+        r.pos = full
+        return r
+
+    def sharded_positions(self, pos: torch.Tensor, b: int) -> List[torch.Tensor]:
+        """The position blocks of the SHARDED table fields (views of ``Route.pos``), in field order."""
+        shard = set(self._table_idx)
+        return [blk for i, blk in zip(self._all_tables, field_positions(pos, b, self._all_lens)) if i in shard]
 
     def reply_buffer(self, n: int, like: torch.Tensor) -> torch.Tensor:
         """(1 + n, D + 4) buffer K1 reads as its table: row 0 is the reserved zero row (send positions are
@@ -499,27 +536,23 @@ class ShardedFeatureEmbedding(nn.Module):
         dev = got.device
         b = inputs[0].shape[0]
         F, D, T = self.num_fields, self.fm_embed_dim, self._T
-        blocks = field_positions(pos, b, self._lens)
-        fin_inputs, s = [], 0
-        for i in range(F):
-            if self._kinds[i] != _lib.DENSE:
-                fin_inputs.append(blocks[s])
-                s += 1
-            else:
-                fin_inputs.append(inputs[i])
+        blocks = dict(zip(self._table_idx, self.sharded_positions(pos, b)))
+        fin_inputs = [blocks.get(i, inputs[i]) for i in range(F)]     # sharded: send positions; replicated / DENSE: the input
         flat = torch.empty((b, T), device=dev, dtype=torch.float32)
         field = flat.view(b, F, D)
         first = torch.empty((b, 1), device=dev, dtype=torch.float32)
         fm = torch.empty((b, 1), device=dev, dtype=torch.float32)
         fm_sum = torch.empty((b, D), device=dev, dtype=torch.float32) if need_bwd else None
         aux = torch.empty((b, max(self._A, 1)), device=dev, dtype=torch.int32)
+        # sort keys of the replicated tables' ids (sharded slots get the PAD key): their backward is local
+        keys = torch.empty((b * self._all_S,), device=dev, dtype=torch.int32) if (need_bwd and self._repl_idx) else None
         _lib.check(lib.dfm_embed_fwd(sample_plan, b, _lib.ptr_array(fin_inputs), self._virtual_ptrs(params, got),
                                      first.data_ptr(), field.data_ptr(), flat.data_ptr(), fm.data_ptr(),
-                                     _lib.ptr(fm_sum), None, aux.data_ptr(), None, _lib.stream_ptr()), "dfm_embed_fwd")
-        return first, field, flat, fm, fm_sum, aux, fin_inputs
+                                     _lib.ptr(fm_sum), _lib.ptr(keys), aux.data_ptr(), None, _lib.stream_ptr()), "dfm_embed_fwd")
+        return first, field, flat, fm, fm_sum, aux, fin_inputs, keys
 
     def pack_grads(self, fin_inputs, pos, got, g_first, g_field, g_flat, g_fm, field, flat, fm_sum,
-                   params, lam, gscale, aux=None, p2p=None):
+                   params, lam, gscale, aux=None, p2p=None, keys=None):
         lib = _lib.lib()
         _, sample_plan = self._ensure_plans()
         self._ordered_params()
@@ -546,7 +579,9 @@ class ShardedFeatureEmbedding(nn.Module):
             _lib.check(lib.dfm_shard_pack_grad(sample_plan, b, _lib.ptr(pos), _lib.ptr(g_first), _lib.ptr(g_field),
                                                _lib.ptr(g_flat), _lib.ptr(g_fm), _lib.ptr(fm_sum), field.data_ptr(),
                                                _lib.ptr(aux), _lib.ptr(g_rows), _lib.stream_ptr()), "dfm_shard_pack_grad")
-        # DENSE-field Linear gradients (data-parallel parameters): K2 with the table part skipped
+        # Data-parallel parameters of the embedding: DENSE-field Linears and the replicated (small) tables.
+        # K2 on the sample-side plan; the sharded tables are foreign there, so only the replicated ones are
+        # sorted / segment-reduced (dense (V, d) gradients, 2*l2*w on every row like the reference).
         dense_grads: Dict[int, torch.Tensor] = {}
         grads = []
         for i, (p, tab) in enumerate(zip(params, self._param_is_table)):
@@ -555,12 +590,18 @@ class ShardedFeatureEmbedding(nn.Module):
             if g is not None:
                 dense_grads[i] = g
         if dense_grads:
+            keys = keys if self._repl_idx else None
+            mode = _lib.GRAD_DENSE if keys is not None else _lib.GRAD_SKIP_TABLES
             ws = torch.empty((max(lib.dfm_embed_bwd_workspace_bytes(sample_plan, b), 16),), device=dev, dtype=torch.uint8)
+            skeys = spay = None
+            if keys is not None:
+                skeys = torch.empty_like(keys)
+                spay = torch.empty_like(keys)
             _lib.check(lib.dfm_embed_bwd(
                 sample_plan, b, _lib.ptr_array(fin_inputs), self._virtual_ptrs(params, got),
                 _lib.ptr(g_first), _lib.ptr(g_field), _lib.ptr(g_flat), _lib.ptr(g_fm), field.data_ptr(), flat.data_ptr(),
-                _lib.ptr(fm_sum), None, _lib.ptr(aux), float(lam), _lib.ptr(gscale), _lib.GRAD_SKIP_TABLES, self._ptrs(grads),
-                None, None, None, None, None, ws.data_ptr(), ws.numel(), _lib.stream_ptr()), "dfm_embed_bwd")
+                _lib.ptr(fm_sum), _lib.ptr(keys), _lib.ptr(aux), float(lam), _lib.ptr(gscale), mode, self._ptrs(grads),
+                _lib.ptr(skeys), _lib.ptr(spay), None, None, None, ws.data_ptr(), ws.numel(), _lib.stream_ptr()), "dfm_embed_bwd")
         return g_rows, dense_grads
 
     def owner_backward(self, lkeys, g_recv, params, lam, gscale):

@@ -249,6 +249,13 @@ DFM_API int dfm_shard_pack_grad_p2p(const dfm_plan* plan, int64_t batch, const i
                                     const float* g_fm, const float* fm_sum, const float* field_emb,
                                     const uint32_t* aux, int n_peers, const int64_t* peer_start,
                                     float* const* peer_rows, void* stream);
+/* Per-field table source of a plan: row_stride / w1_stride (floats, 0 = dim / 1) let K1 read the field's rows
+ * out of a strided buffer (the received reply rows); foreign = 1 marks a table whose gradient is produced
+ * elsewhere: K1 emits no sort key for its ids and dfm_embed_bwd / dfm_rows_bwd ignore it.  On the sample-side
+ * plan of the sharded path the SHARDED tables are foreign (the exchange kernels act on exactly those fields),
+ * on the owner-side plan the REPLICATED (small) tables are.  dfm_plan_set_table_stride applies one stride
+ * pair to every id table. */
+DFM_API int dfm_plan_set_field_source(dfm_plan* plan, int field, int row_stride, int w1_stride, int foreign);
 DFM_API int dfm_plan_set_table_stride(dfm_plan* plan, int row_stride, int w1_stride);
 DFM_API size_t dfm_rows_bwd_workspace_bytes(const dfm_plan* plan, int64_t n_rows);
 DFM_API int dfm_rows_bwd(const dfm_plan* plan, int64_t n_rows, const float* const* params,

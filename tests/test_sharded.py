@@ -118,6 +118,50 @@ def test_all_to_all_plumbing_gloo_world2():
     assert sum(r[4] for r in res) == 2 * 20 * 3                   # every key arrived somewhere
 
 
+def test_sharded_module_bookkeeping_cpu():
+    """Host logic of ShardedFeatureEmbedding (no kernels): which tables are sharded / replicated, local table
+    sizes under the rotated owner rule, load_from_full, and the torch routing in the plan's position layout."""
+    from deepfm_b200.sharded import ShardedFeatureEmbedding
+    schema = _schema(8, multihot=True)
+    W = 3
+    names = list(schema.fields)
+    mods = [ShardedFeatureEmbedding(schema, 8, W, r, replicate_below=60) for r in range(W)]
+    m = mods[1]
+    small = {n for n, f in schema.fields.items() if f.feature_type != FeatureType.DENSE and f.vocabulary_size <= 60}
+    assert {names[i] for i in m._repl_idx} == small and small            # s0 (50), s2 (7), s4 (11), q0 (40), q2 (9)
+    for i in m._repl_idx:                                                 # replicated: full table on every rank
+        assert m.second_order_embeddings[names[i]].weight.shape[0] == schema.fields[names[i]].vocabulary_size
+    for i in m._table_idx:                                                # sharded: the ranks' shards partition the ids
+        V = schema.fields[names[i]].vocabulary_size
+        if V >= W:
+            assert sum(mm.second_order_embeddings[names[i]].weight.shape[0] for mm in mods) == V
+    assert [p.shape[0] > 0 for p in m.table_parameters()] and len(m.table_parameters()) == 2 * len(m._table_idx)
+    # routing restatement: replicated fields send nothing, sharded fields follow (id + field) mod W
+    rng = np.random.default_rng(3)
+    b = 29
+    ins = []
+    for n, f in schema.fields.items():
+        if f.feature_type == FeatureType.DENSE:
+            ins.append(torch.zeros(b))
+        elif f.feature_type == FeatureType.SEQUENCE:
+            ins.append(torch.from_numpy(rng.integers(0, f.vocabulary_size, (b, f.max_length))))
+        else:
+            ins.append(torch.from_numpy(rng.integers(0, f.vocabulary_size, b)))
+    r = m.route_torch(ins)
+    assert r.pos.numel() == b * m._all_S
+    for i, blk in zip(m._all_tables, field_positions(r.pos, b, m._all_lens)):
+        if i in m._repl_idx:
+            assert int(blk.abs().sum()) == 0
+        else:
+            sent = ins[i].reshape(blk.shape) != 0 if schema.fields[names[i]].feature_type == FeatureType.SEQUENCE \
+                else torch.ones_like(blk, dtype=torch.bool)
+            assert torch.equal(blk > 0, sent)
+            owner = (ins[i].reshape(blk.shape) + i) % W
+            bounds = torch.cumsum(r.counts, 0)
+            got_owner = torch.bucketize(blk - 1, bounds, right=True)
+            assert torch.equal(got_owner[sent], owner[sent])
+
+
 def _reducer_worker(rank, world, port, out):
     import torch.distributed as dist
     os.environ.update(MASTER_ADDR="127.0.0.1", MASTER_PORT=str(port))
@@ -190,8 +234,10 @@ def _exchange(bufs, counts, reverse=False):
 
 
 @pytest.mark.gpu
-@pytest.mark.parametrize("W,D,multihot", [(2, 16, False), (3, 64, False), (2, 64, True), (4, 16, True)])
-def test_sharded_equals_unsharded_emulated_ranks(W, D, multihot):
+@pytest.mark.parametrize("W,D,multihot,repl", [(2, 16, False, 0), (3, 64, False, 0), (2, 64, True, 0), (4, 16, True, 0),
+                                                 (3, 64, False, 60), (2, 16, True, 60)])
+def test_sharded_equals_unsharded_emulated_ranks(W, D, multihot, repl):
+    """repl: tables of at most that many rows are replicated (looked up and differentiated locally)."""
     from deepfm_b200.layers.embedding import FeatureEmbedding
     from deepfm_b200.layers.fm import FMInteraction
     from deepfm_b200.layers.l2 import l2_penalty
@@ -227,7 +273,7 @@ def test_sharded_equals_unsharded_emulated_ranks(W, D, multihot):
     fm = FMInteraction()(fe)
     ((fo * g_first).sum() + (fl * g_flat).sum() + (fm * g_fm).sum() + l2_penalty(full, lam)).backward()
 
-    mods = [ShardedFeatureEmbedding(schema, D, W, r).cuda() for r in range(W)]
+    mods = [ShardedFeatureEmbedding(schema, D, W, r, replicate_below=repl).cuda() for r in range(W)]
     for m in mods:
         m.load_from_full(full)
         m.grad_mode = "dense"
@@ -239,7 +285,9 @@ def test_sharded_equals_unsharded_emulated_ranks(W, D, multihot):
         ref = m.route_torch(x)
         n_sent = int(ref.counts.sum())
         assert torch.equal(r.counts, ref.counts)
-        assert torch.equal(r.send_keys[:n_sent], ref.send_keys) and torch.equal(r.pos, ref.pos)
+        assert torch.equal(r.send_keys[:n_sent], ref.send_keys)
+        for mine, theirs in zip(m.sharded_positions(r.pos, b), m.sharded_positions(ref.pos, b)):
+            assert torch.equal(mine, theirs)
         r.send_keys = r.send_keys[:n_sent]
     gathered = [m.gather(k) for m, k in zip(mods, recv_keys)]
     got = _exchange([g[0] for g in gathered], counts, reverse=True)
@@ -259,7 +307,7 @@ def test_sharded_equals_unsharded_emulated_ranks(W, D, multihot):
         params = m._ordered_params()
         packed.append(m.pack_grads(o[6], routes[r].pos, got[r], g_first[sl].contiguous(), None,
                                    g_flat[sl].contiguous(), g_fm[sl].contiguous(), o[1], o[2], o[4], params, lam / W, gscale,
-                                   o[5]))
+                                   o[5], keys=o[7]))
     g_recv = _exchange([p[0] for p in packed], counts)
     for r, m in enumerate(mods):
         params = m._ordered_params()
@@ -267,10 +315,12 @@ def test_sharded_equals_unsharded_emulated_ranks(W, D, multihot):
         for i, g in tg.items():
             slot = m._slot_of_param[i]
             name = m.field_names[slot // 5]
+            assert slot // 5 not in m._repl_idx
             ref = (full.second_order_embeddings if slot % 5 == 0 else full.first_order_embeddings)[name].weight.grad
             ref = ref[(r - slot // 5) % W::W]
             assert_close_rel(g[: ref.shape[0]].cpu(), ref.cpu(), 2e-5, f"rank {r} {name} slot {slot % 5}")
-    # replicated DENSE-field Linears: the sum over ranks of the per-rank gradients is the full gradient
+    # replicated parameters (DENSE-field Linears, small tables): the sum over ranks of the per-rank gradients is the
+    # full gradient (each rank was given l2 / W)
     for i, tab in enumerate(mods[0]._param_is_table):
         if tab:
             continue
