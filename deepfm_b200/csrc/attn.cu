@@ -465,6 +465,15 @@ static void attn_fill(AttnArgs& a, const float* x, const float* g_out, float* ou
     a.gamma = residual ? p[8] : nullptr; a.beta = residual ? p[9] : nullptr; a.partials = nullptr; a.acc_global = 0; a.nat = 0;
 }
 
+// attn16.cu: warp-per-sample kernels for D = 16, head dim 16, F <= 16 (BASELINE config 3)
+bool attn16_supported(int F, int D, int A, int heads);
+size_t attn16_workspace_bytes(int64_t B, int F, int A);
+int attn16_fwd(const float* x, int64_t B, int F, int A, int heads, int residual, const float* const* params, float* out,
+               cudaStream_t st);
+int attn16_bwd(const float* x, const float* g_out, int64_t B, int F, int A, int heads, int residual,
+               const float* const* params, float* g_x, float* const* g_params, void* workspace, size_t workspace_bytes,
+               cudaStream_t st);
+
 }  // namespace dfm
 
 using namespace dfm;
@@ -475,7 +484,12 @@ size_t dfm_attn_workspace_bytes(int64_t batch, int n_fields, int dim, int attent
     int spb, grid; size_t smem;
     int ag = 0, nt_ = 1;
     if (attn_config(batch, n_fields, dim, attention_dim, heads, true, spb, smem, grid, &ag, &nt_) != DFM_OK) return 0;
-    return (size_t)grid * attn_np(dim, attention_dim) * 4 + 256;
+    size_t bytes = (size_t)grid * attn_np(dim, attention_dim) * 4 + 256;
+    if (attn16_supported(n_fields, dim, attention_dim, heads)) {
+        const size_t b16 = attn16_workspace_bytes(batch, n_fields, attention_dim);
+        if (b16 > bytes) bytes = b16;
+    }
+    return bytes;
 }
 
 int dfm_attn_fwd(const float* x, int64_t batch, int n_fields, int dim, int attention_dim, int heads,
@@ -487,6 +501,8 @@ int dfm_attn_fwd(const float* x, int64_t batch, int n_fields, int dim, int atten
     if (rc) return rc;
     if (batch == 0) return DFM_OK;
     DFM_REQUIRE(x && out, DFM_ERR_INVALID, "dfm_attn_fwd: null tensor");
+    if (attn16_supported(n_fields, dim, attention_dim, heads) && ((reinterpret_cast<uintptr_t>(x) | reinterpret_cast<uintptr_t>(out)) & 15u) == 0)
+        return attn16_fwd(x, batch, n_fields, attention_dim, heads, use_residual, params, out, static_cast<cudaStream_t>(stream));
     AttnArgs a;
     attn_fill(a, x, nullptr, out, batch, n_fields, dim, attention_dim, heads, use_residual, params, spb);
     if (smem > 48 * 1024) DFM_CHECK_CUDA(cudaFuncSetAttribute(attn_fwd_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
@@ -507,6 +523,10 @@ int dfm_attn_bwd(const float* x, const float* g_out, int64_t batch, int n_fields
     if (rc) return rc;
     const int D = dim, A = attention_dim, NP = attn_np(D, A);
     cudaStream_t st = static_cast<cudaStream_t>(stream);
+    if (batch > 0 && attn16_supported(n_fields, dim, attention_dim, heads) && x && g_out && g_x &&
+        ((reinterpret_cast<uintptr_t>(x) | reinterpret_cast<uintptr_t>(g_out) | reinterpret_cast<uintptr_t>(g_x)) & 15u) == 0)
+        return attn16_bwd(x, g_out, batch, n_fields, attention_dim, heads, use_residual, params, g_x, g_params, workspace,
+                          workspace_bytes, st);
     AttnGradPtrs gp;
     const int sizes[10] = {A * D, A, A * D, A, A * D, A, D * A, D, D, D};
     for (int i = 0; i < 10; ++i) { gp.n[i] = sizes[i]; gp.p[i] = (i < 8 || use_residual) ? g_params[i] : nullptr; }

@@ -101,7 +101,10 @@ def test_attention_golden(tag):
             assert_close_rel(p.grad.cpu(), ref[k], 1e-4, k)
 
 
-@pytest.mark.parametrize("B,F,D,A,H,res", [(1000, 16, 16, 64, 4, True), (77, 39, 64, 64, 4, True), (33, 5, 6, 12, 3, False)])
+# (1000,16,16,64,4), (257,11,16,32,2), (70,16,16,128,8), (5,1,16,16,1): the warp-per-sample kernels (D = 16, head dim 16,
+# F <= 16; F = 11 and F = 1 exercise the masked rows); the others: the general shared-memory kernels
+@pytest.mark.parametrize("B,F,D,A,H,res", [(1000, 16, 16, 64, 4, True), (77, 39, 64, 64, 4, True), (33, 5, 6, 12, 3, False),
+                                            (257, 11, 16, 32, 2, False), (70, 16, 16, 128, 8, True), (5, 1, 16, 16, 1, True)])
 def test_attention_vs_oracle_larger(B, F, D, A, H, res):
     rng = np.random.default_rng(B + F)
     att = MultiHeadSelfAttention(D, H, A, 1, res).cuda()
