@@ -332,6 +332,11 @@ def run_ours(args, rank: int, local_rank: int, n_gpus: int):
     k2_sort_bytes = n_slots * 8 * 2 * 4
     ms_step = total_ms / K_
     line = base_line(args, n_gpus)
+    from deepfm_b200 import fp32_emulation
+    line["config"]["dnn_gemm"] = (f"library (out of scope): {fp32_emulation.status()}, cuBLAS {fp32_emulation.cublas_version()}; "
+                                  "fp32 in / fp32 out, max-norm rel err vs fp64 4.4e-7 (native SIMT sgemm: 1.8e-6)") \
+        if fp32_emulation._state["enabled"] else f"library (out of scope): torch-bundled cuBLAS {fp32_emulation.cublas_version()} SIMT sgemm"
+    dnn_note = line["config"]["dnn_gemm"]
     if wl != "deepfm_criteo":
         line["config"] = {"workload": WORKLOADS[wl][1].format(B=BATCH), "model": model_name, "batch_per_gpu": BATCH,
                           "global_batch": BATCH * n_gpus, "embed_dim": cfg.feature.fm_embed_dim,
@@ -339,6 +344,7 @@ def run_ours(args, rank: int, local_rank: int, n_gpus: int):
                           "cin": getattr(model, "cin", None) and model.cin.layer_sizes,
                           "cin_precision": getattr(model, "cin", None) and model.cin.precision,
                           "parallelism": line["config"]["parallelism"] if sharded else f"dp{n_gpus}",
+                          "dnn_gemm": dnn_note,
                           "note": "secondary line: not the workload BASELINE.json's metric is quoted on"}
     line.update({
         "value": BATCH * n_gpus / (ms_step * 1e-3), "ms_per_step": ms_step, "warmup": W_,
@@ -382,6 +388,9 @@ def main():
     ap.add_argument("--impl", default="ours", choices=["ours", "reference"])
     ap.add_argument("--no-cpu-baseline", action="store_true")
     ap.add_argument("--workload", default="deepfm_criteo", choices=sorted(WORKLOADS))
+    ap.add_argument("--dnn-gemm", default="emulated", choices=["emulated", "native"],
+                    help="library GEMMs of the (out-of-scope) DNN tower: cuBLAS 12.9 FP32 emulation on the BF16 tensor "
+                         "cores (fp32-accurate) or torch's bundled cuBLAS 12.8 SIMT sgemm")
     ap.add_argument("--cin-precision", default="tf32", choices=["fp32", "tf32"],
                     help="xDeepFM workloads: CIN contraction on tcgen05 (tf32) or CUDA cores (fp32)")
     args = ap.parse_args()
@@ -394,8 +403,11 @@ def main():
         cmd = [sys.executable, "-m", "torch.distributed.run", "--nnodes=1", f"--nproc-per-node={args.gpus}",
                "--master-addr", "127.0.0.1", "--master-port", os.environ.get("MASTER_PORT", "29533"), __file__,
                "--gpus", str(args.gpus), "--steps", str(args.steps), "--warmup", str(args.warmup), "--impl", args.impl,
-               "--workload", args.workload, "--cin-precision", args.cin_precision]
+               "--workload", args.workload, "--cin-precision", args.cin_precision, "--dnn-gemm", args.dnn_gemm]
         sys.exit(subprocess.call(cmd))
+    if args.impl != "reference" and args.dnn_gemm == "emulated":
+        from deepfm_b200 import fp32_emulation          # before anything imports torch
+        fp32_emulation.enable()
     if args.impl == "reference":
         run_reference(args, rank, n_gpus)
     else:

@@ -60,3 +60,26 @@ def test_train_step_changes_weights_like_reference_trainer():
         opt.step()
     changed = [k for k, v in model.state_dict().items() if v.dtype.is_floating_point and not torch.equal(v, before[k])]
     assert any(k.startswith("embedding.second_order") for k in changed) and any(k.startswith("dnn") for k in changed)
+
+
+def test_model_parity_holds_under_cublas_fp32_emulation():
+    """bench.py runs the (library) DNN GEMMs on cuBLAS 12.9's FP32 emulation (BF16x9 on the tensor cores, see
+    deepfm_b200/fp32_emulation.py).  The swap has to happen before torch is imported, so the whole-model golden
+    tests are re-run in a fresh interpreter with it enabled: same fixtures, same tolerances."""
+    import os
+    import subprocess
+    import sys
+    root = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
+    code = ("import sys\n"
+            "from deepfm_b200 import fp32_emulation as E\n"
+            "if not E.enable():\n"
+            "    print('EMULATION-UNAVAILABLE', E.status()); sys.exit(0)\n"
+            "import pytest\n"
+            "rc = pytest.main(['-q', '-x', 'tests/test_models_gpu.py', '-m', 'gpu', '-k', 'logits_loss_and_grads'])\n"
+            "print('CUBLAS', E.cublas_version())\n"
+            "sys.exit(int(rc))\n")
+    r = subprocess.run([sys.executable, "-c", code], cwd=root, capture_output=True, text=True, timeout=900)
+    if "EMULATION-UNAVAILABLE" in r.stdout:
+        pytest.skip(r.stdout.strip())
+    assert r.returncode == 0, r.stdout[-3000:] + r.stderr[-2000:]
+    assert "CUBLAS 12.9" in r.stdout or "CUBLAS 12.1" in r.stdout or "CUBLAS 13" in r.stdout, r.stdout[-500:]
