@@ -60,6 +60,9 @@ SIGNATURES = {
     "dfm_rows_bwd_workspace_bytes": (_sz, [_vp, _i64]),
     "dfm_rows_bwd": (C.c_int, [_vp, _i64, _pp, _vp, _vp, _f32, _vp, C.c_int, _pp, _vp, _vp, _vp, _vp, _vp,
                                _vp, _sz, _vp]),
+    "dfm_adam_rows": (C.c_int, [_vp, _i64, _vp, _vp, _vp, _pp, _pp, _pp, _f32, _f32, _f32, _f32, _i64, _vp, _vp]),
+    "dfm_rows_sumsq_workspace_bytes": (_sz, []),
+    "dfm_rows_sumsq": (C.c_int, [_vp, _i64, _vp, _vp, _vp, _vp, _vp, _sz, _vp]),
     "dfm_attn_workspace_bytes": (_sz, [_i64, C.c_int, C.c_int, C.c_int, C.c_int]),
     "dfm_attn_fwd": (C.c_int, [_vp, _i64, C.c_int, C.c_int, C.c_int, C.c_int, C.c_int, _pp, _vp, _vp]),
     "dfm_attn_bwd": (C.c_int, [_vp, _vp, _i64, C.c_int, C.c_int, C.c_int, C.c_int, C.c_int, _pp, _vp, _pp,

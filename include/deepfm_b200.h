@@ -264,6 +264,26 @@ DFM_API int dfm_rows_bwd(const dfm_plan* plan, int64_t n_rows, const float* cons
                          uint32_t* sorted_payload, float* row_grad2, float* row_grad1, int64_t* n_valid,
                          void* workspace, size_t workspace_bytes, void* stream);
 
+/* ------------------------------------------------------------------------------------------
+ * Row-sparse optimizer step on the id tables (reference trainer.py:232-237 +
+ * trainer.py:67-78: clip_grad_norm_(1.0), torch.optim.Adam(lr 1e-3)).  Consumes dfm_embed_bwd's /
+ * dfm_rows_bwd's row-sparse output in place (sorted keys + the summed gradient at the first position of
+ * every segment): torch.optim.Adam's update restricted to the touched rows ("lazy" moments -- documented
+ * deviation from the dense reference; oracle: adam_rows).  params / exp_avg / exp_avg_sq: 5 slots per field
+ * like everywhere, only the two table slots are read.  clip_scale: device scalar multiplying every gradient
+ * (min(1, max_norm / (norm + 1e-6)) of the global-norm clip), or NULL.
+ *   dfm_rows_sumsq: sum of squares of the touched rows' gradients (the table part of that norm),
+ *   deterministic fixed-order reduction into out[0].
+ * ---------------------------------------------------------------------------------------- */
+DFM_API int dfm_adam_rows(const dfm_plan* plan, int64_t n_sorted, const uint32_t* sorted_keys,
+                          const float* row_grad2, const float* row_grad1, float* const* params,
+                          float* const* exp_avg, float* const* exp_avg_sq, float lr, float beta1, float beta2,
+                          float eps, int64_t step, const float* clip_scale, void* stream);
+DFM_API size_t dfm_rows_sumsq_workspace_bytes(void);
+DFM_API int dfm_rows_sumsq(const dfm_plan* plan, int64_t n_sorted, const uint32_t* sorted_keys,
+                           const float* row_grad2, const float* row_grad1, float* out, void* workspace,
+                           size_t workspace_bytes, void* stream);
+
 #ifdef __cplusplus
 }
 #endif

@@ -224,3 +224,24 @@ def test_shard_route():
     assert counts.tolist() == [3, 3, 1, 1] and offsets.tolist() == [0, 3, 6, 7, 8]
     assert perm.tolist() == [1, 3, 7, 0, 2, 4, 5, 6]
     assert np.all(local * 4 + owner == ids)
+
+
+def test_adam_rows_equals_torch_adam_when_every_row_is_touched():
+    """Pins oracle.adam_rows (the optimiser row) to torch.optim.Adam (trainer.py:67-78 defaults):
+    with every row touched at every step the row-restricted update IS dense Adam."""
+    import torch
+    rng = np.random.default_rng(5)
+    w = rng.standard_normal((7, 4)).astype(np.float32)
+    p = torch.nn.Parameter(torch.from_numpy(w.copy()))
+    opt = torch.optim.Adam([p], lr=1e-3)
+    m, v = np.zeros_like(w), np.zeros_like(w)
+    rows = np.arange(7)
+    for step in (1, 2, 3, 4):
+        g = rng.standard_normal((7, 4)).astype(np.float32)
+        p.grad = torch.from_numpy(g.copy())
+        opt.step()
+        w, m, v = O.adam_rows(w, m, v, rows, g, step)
+        np.testing.assert_allclose(w, p.detach().numpy(), rtol=2e-6, atol=1e-7)
+    # lazy semantics: a row that is not touched keeps weight and moments
+    w2, m2, v2 = O.adam_rows(w, m, v, np.array([1, 3]), g[[1, 3]], 5)
+    assert np.array_equal(w2[[0, 2, 4, 5, 6]], w[[0, 2, 4, 5, 6]]) and np.array_equal(m2[0], m[0])
