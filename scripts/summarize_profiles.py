@@ -66,3 +66,18 @@ for name in (f"bench_{tag}.json",):
         shutil.copy(os.path.join(src, name), os.path.join(dst, name))
 print(open(os.path.join(dst, f"{tag}_launches_summary.csv")).read()[:3000])
 print(open(os.path.join(dst, f"{tag}_ncu_full_kernels.csv")).read())
+
+# 4. the warp-per-sample attention kernels (config 3) and their tall-skinny parameter-gradient GEMMs
+rep3 = os.path.join(src, f"prof_{tag}_attn.ncu-rep")
+if os.path.exists(rep3):
+    raw = subprocess.run(["ncu", "-i", rep3, "--page", "raw", "--csv"], capture_output=True, text=True).stdout
+    rows = list(csv.reader(raw.splitlines()))
+    hdr, units = rows[0], rows[1]
+    want3 = want + ["sm__inst_executed_pipe_fma.avg.pct_of_peak_sustained_active", "sm__pipe_fma_cycles_active.avg.pct_of_peak_sustained_active",
+                    "l1tex__data_bank_conflicts_pipe_lsu_mem_shared.sum", "launch__occupancy_limit_shared_mem", "launch__occupancy_limit_registers"]
+    idx = [(w, hdr.index(w)) for w in want3 if w in hdr]
+    with open(os.path.join(dst, f"{tag}_ncu_full_attention.csv"), "w") as fh:
+        fh.write("# ncu --set full --clock-control none --import-source on -k regex:attn16|tsgemm : python scripts/ncu_attn.py (B=65536, F=16, D=16, 4 heads, A=64)\n")
+        fh.write(",".join(f"{w} [{units[i]}]" for w, i in idx) + "\n")
+        for r in rows[2:]:
+            fh.write(",".join('"' + r[i].replace('"', "'")[:80] + '"' if w == "Kernel Name" else r[i].replace(",", "") for w, i in idx) + "\n")
