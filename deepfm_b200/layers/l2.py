@@ -5,6 +5,12 @@ Value: one deterministic multi-tensor reduction (``dfm_sumsq``) instead of a Pyt
 ``FeatureEmbedding`` forward of the same step, the ``2*lambda*p`` term is folded into the
 embedding backward kernel K2 (no extra pass over the tables); in every other situation the
 node produces it itself with ``dfm_axpy``.
+
+The value is an HBM-bound pass over every table (1.35 ms for the 8.6 GB of the Criteo shape) that nothing in the
+step depends on except the final scalar add, so ``prefetch_l2`` lets the model start it on a side stream at the top
+of ``forward`` (once a previous step has shown that the penalty is really used), where it overlaps the tensor-bound
+DNN; ``l2_penalty`` then only waits for the event.  The prefetched value is used only if the parameters are the very
+same tensors at the very same versions.
 """
 
 from __future__ import annotations
@@ -14,15 +20,55 @@ import torch
 from .. import _lib
 
 
+def _launch_sumsq(params, lam: float):
+    lib = _lib.lib()
+    dev = params[0].device
+    out = torch.empty((), device=dev, dtype=torch.float32)
+    ws = torch.empty((4096,), device=dev, dtype=torch.float32)
+    _lib.check(lib.dfm_sumsq(len(params), _lib.ptr_array(params), _lib.i64_array([p.numel() for p in params]),
+                             float(lam), out.data_ptr(), ws.data_ptr(), _lib.stream_ptr()), "dfm_sumsq")
+    return out, ws
+
+
+def _param_key(params, lam: float):
+    return (float(lam),) + tuple((p.data_ptr(), p._version) for p in params)
+
+
+def prefetch_l2(emb, lam: float) -> None:
+    """Start ``lam * sum ||p||^2`` on the embedding's side stream (no-op until a step has used the penalty)."""
+    if lam <= 0 or not getattr(emb, "_l2_wanted", False):
+        emb._l2_prefetched = None
+        return
+    if getattr(emb, "_l2_prefetched", None) is not None:      # the previous prefetch was never consumed: stop speculating
+        emb._l2_prefetched, emb._l2_wanted = None, False
+        return
+    params = [p for p in emb.parameters()]
+    if not params or any((not p.is_cuda) or (not p.is_contiguous()) for p in params):
+        return
+    side = getattr(emb, "_l2_stream", None)
+    if side is None:
+        side = emb._l2_stream = torch.cuda.Stream(device=params[0].device)
+    side.wait_stream(torch.cuda.current_stream(params[0].device))     # the weights are final for this step
+    with torch.cuda.stream(side):
+        out, ws = _launch_sumsq(params, lam)
+        ev = torch.cuda.Event()
+        ev.record(side)
+    emb._l2_prefetched = (_param_key(params, lam), out, ws, ev)
+
+
 class _L2PenaltyFn(torch.autograd.Function):
     @staticmethod
     def forward(ctx, emb, lam: float, *params):
-        lib = _lib.lib()
-        dev = params[0].device
-        out = torch.empty((), device=dev, dtype=torch.float32)
-        ws = torch.empty((4096,), device=dev, dtype=torch.float32)
-        _lib.check(lib.dfm_sumsq(len(params), _lib.ptr_array(params), _lib.i64_array([p.numel() for p in params]),
-                                 float(lam), out.data_ptr(), ws.data_ptr(), _lib.stream_ptr()), "dfm_sumsq")
+        emb._l2_wanted = True
+        pre, emb._l2_prefetched = getattr(emb, "_l2_prefetched", None), None
+        if pre is not None and pre[0] == _param_key(params, lam):
+            _, out, ws, ev = pre
+            cur = torch.cuda.current_stream(out.device)
+            cur.wait_event(ev)
+            out.record_stream(cur)
+            ws.record_stream(cur)
+        else:
+            out, _ = _launch_sumsq(params, lam)
         ctx.emb, ctx.lam = emb, float(lam)
         ctx.save_for_backward(*params)
         return out

@@ -18,7 +18,7 @@ import torch.nn as nn
 from .layers.dnn import DNN
 from .layers.embedding import FeatureEmbedding
 from .layers.fm import FMInteraction
-from .layers.l2 import l2_penalty
+from .layers.l2 import l2_penalty, prefetch_l2
 
 
 class BaseCTRModel(nn.Module, ABC):
@@ -45,6 +45,10 @@ class BaseCTRModel(nn.Module, ABC):
 
     def forward(self, batch: Dict[str, torch.Tensor]) -> torch.Tensor:
         first_order, field_embeddings, flat_embeddings = self.embedding(batch)
+        if self.training and torch.is_grad_enabled():
+            # the L2 value of get_l2_reg_loss() starts now, on a side stream, underneath the interaction / DNN
+            # forward (after the HBM-bound embedding kernel, which it would only slow down)
+            prefetch_l2(self.embedding, float(self.config.feature.embedding_l2_reg))
         return self._forward_components(first_order, field_embeddings, flat_embeddings)
 
     def predict(self, batch: Dict[str, torch.Tensor]) -> torch.Tensor:

@@ -77,3 +77,6 @@ class RowSparseAdam:
                                      rg.row_grad1.data_ptr(), self._slots(self._params), self._slots(self.exp_avg),
                                      self._slots(self.exp_avg_sq), self.lr, self.betas[0], self.betas[1], self.eps,
                                      self.step_count, _lib.ptr(clip_scale), _lib.stream_ptr()), "dfm_adam_rows")
+        for p, t in zip(self._params, self._is_table):      # the kernel wrote through raw pointers
+            if t:
+                torch._C._increment_version(p)

@@ -83,3 +83,31 @@ def test_model_parity_holds_under_cublas_fp32_emulation():
         pytest.skip(r.stdout.strip())
     assert r.returncode == 0, r.stdout[-3000:] + r.stderr[-2000:]
     assert "CUBLAS 12.9" in r.stdout or "CUBLAS 12.1" in r.stdout or "CUBLAS 13" in r.stdout, r.stdout[-500:]
+
+
+def test_l2_value_prefetched_on_side_stream_is_the_same_value():
+    """From the second training step on, BaseCTRModel.forward starts the L2 reduction on a side stream
+    (layers/l2.py prefetch_l2); the value and the gradients must be exactly those of the in-line reduction, and a
+    parameter update between two steps must be seen."""
+    _, model = _model("deepfm")
+    batch = to_dev(spec.golden_batch())
+    labels = torch.from_numpy(spec.golden_labels()).cuda()
+    model.train()
+    vals, grads = [], []
+    for step in range(3):
+        model.zero_grad(set_to_none=True)
+        torch.manual_seed(7)                                  # same dropout mask every step
+        logits = model(batch)
+        used_prefetch = getattr(model.embedding, "_l2_prefetched", None) is not None
+        l2 = model.get_l2_reg_loss()
+        (torch.nn.BCEWithLogitsLoss()(logits.squeeze(1), labels) + l2).backward()
+        vals.append(l2.item())
+        grads.append(model.embedding.second_order_embeddings["u"].weight.grad.clone())
+        assert used_prefetch == (step > 0)
+    assert vals[0] == vals[1] == vals[2]
+    assert torch.equal(grads[0], grads[1]) and torch.equal(grads[0], grads[2])
+    with torch.no_grad():
+        model.embedding.second_order_embeddings["u"].weight.mul_(2.0)
+    model.zero_grad(set_to_none=True)
+    model(batch)
+    assert model.get_l2_reg_loss().item() > vals[0]
