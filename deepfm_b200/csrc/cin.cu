@@ -293,6 +293,9 @@ int cin_layer_fwd_tc(const float* x0, long long x_bs, const float* hid, long lon
                      const float* bias, float* act, long long B, int F, int H, int D, int L, float* wpad,
                      cudaStream_t st);
 size_t cin_tc_wpad_floats(int F, int Hmax, int Lmax);
+bool cin_tc_bwd_supported(long long B, int F, int H, int D, int L);
+int cin_gpre_fused(const float* act, const float* g_out, const float* g_hnext, long long B, int L, int D, int direct,
+                   int out_dim, int col_off, int next_off, int next_n, float* bwd_scratch, float* dw_scratch, cudaStream_t st);
 size_t cin_tc_bwd_scratch_floats(long long B, int F, int D, int Hmax, int Lmax);
 size_t cin_tc_dw_scratch_floats(long long B, int F, int D, int Hmax, int Lmax);
 int cin_layer_dw_tc(const float* g_pre, const float* x0, long long x_bs, const float* hid, long long h_bs, float* gw,
@@ -414,9 +417,18 @@ int dfm_cin_bwd(const float* x0, const float* g_out, int64_t batch, int n_fields
         const long long tot = batch * L * D;
         long long gb = ceil_div(tot, 256);
         if (gb > 16LL * sm_count()) gb = 16LL * sm_count();
-        cin_gpre_kernel<<<(unsigned)gb, 256, 0, st>>>(act, g_out, g_hnext, batch, L, D, c.direct[i], c.out_dim,
-                                                      c.col_off[i], next_off, next_n, g_pre);
-        DFM_CHECK_LAUNCH();
+        // tensor-core path: g_pre is produced once, directly in the two layouts its GEMMs read
+        const bool fused = precision == 1 && cin_tc_bwd_supported(batch, F, H, D, L);
+        if (fused) {
+            rc = cin_gpre_fused(act, g_out, g_hnext, batch, L, D, c.direct[i], c.out_dim, c.col_off[i], next_off, next_n,
+                                tc_scratch, dw_scratch, st);
+            if (rc) return rc;
+        } else {
+            cin_gpre_kernel<<<(unsigned)gb, 256, 0, st>>>(act, g_out, g_hnext, batch, L, D, c.direct[i], c.out_dim,
+                                                          c.col_off[i], next_off, next_n, g_pre);
+            DFM_CHECK_LAUNCH();
+        }
+        const float* g_pre_in = fused ? nullptr : g_pre;
         // hidden input of this layer
         const float* hid = x0;
         long long h_bs = (long long)F * D;
@@ -428,9 +440,9 @@ int dfm_cin_bwd(const float* x0, const float* g_out, int64_t batch, int n_fields
         // weight / bias gradients
         bool dw_done = false;
         if (precision == 1) {
-            rc = cin_layer_dw_tc(g_pre, x0, (long long)F * D, hid, h_bs, g_weights[i], g_biases[i], batch, F, H, D, L, dw_scratch, st);
+            rc = cin_layer_dw_tc(g_pre_in, x0, (long long)F * D, hid, h_bs, g_weights[i], g_biases[i], batch, F, H, D, L, dw_scratch, st);
             if (rc == DFM_OK) dw_done = true;
-            else if (rc != DFM_ERR_UNSUPPORTED) return rc;
+            else if (rc != DFM_ERR_UNSUPPORTED || fused) return rc;
         }
         if (!dw_done) {
         DwArgs d;
@@ -449,11 +461,11 @@ int dfm_cin_bwd(const float* x0, const float* g_out, int64_t batch, int n_fields
         }
         float* gh = g_hid[i & 1];
         if (precision == 1) {   // tensor cores: gz = g_pre W stays in TMEM, contracted per row in the epilogue
-            rc = cin_layer_bwd_data_tc(g_pre, x0, (long long)F * D, hid, h_bs, weights[i], i == 0 ? g_x0 : gh,
+            rc = cin_layer_bwd_data_tc(g_pre_in, x0, (long long)F * D, hid, h_bs, weights[i], i == 0 ? g_x0 : gh,
                                        i == 0 ? (long long)F * D : (long long)H * D, i == 0 ? 1 : 0, g_x0, batch, F, H, D, L,
                                        tc_scratch, st);
             if (rc == DFM_OK) { g_hnext = gh; continue; }
-            if (rc != DFM_ERR_UNSUPPORTED) return rc;       // unsupported tile shape: fp32 CUDA-core path below
+            if (rc != DFM_ERR_UNSUPPORTED || fused) return rc;   // unsupported tile shape: fp32 CUDA-core path below
         }
         // d/d hidden  (layer 0: the hidden input is x0 itself -> accumulate into g_x0)
         OpGemmArgs a;

@@ -260,9 +260,11 @@ int cin_layer_bwd_data_tc(const float* g_pre, const float* x0, long long x_bs, c
     float* wt = scratch + (((size_t)M * Lp + 31) & ~(size_t)31);
     const size_t tile_smem = (size_t)L * (D + 1) * 4;
     DFM_REQUIRE(tile_smem <= 200 * 1024, DFM_ERR_UNSUPPORTED, "cin tcgen05 backward: L*D too large for the transpose tile");
-    if (tile_smem > 48 * 1024)
-        DFM_CHECK_CUDA(cudaFuncSetAttribute(cin_gpre_transpose_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)tile_smem));
-    cin_gpre_transpose_kernel<<<(unsigned)B, 256, tile_smem, st>>>(g_pre, B, L, D, Lp, gT);
+    if (g_pre) {      // nullptr: g_pre^T is already in the scratch (cin_gpre_fused)
+        if (tile_smem > 48 * 1024)
+            DFM_CHECK_CUDA(cudaFuncSetAttribute(cin_gpre_transpose_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)tile_smem));
+        cin_gpre_transpose_kernel<<<(unsigned)B, 256, tile_smem, st>>>(g_pre, B, L, D, Lp, gT);
+    }
     long long pb = ceil_div((long long)Hp * FP * Lp, 256);
     if (pb > 4LL * sm_count()) pb = 4LL * sm_count();
     cin_wt_pad_kernel<<<(unsigned)pb, 256, 0, st>>>(w, L, H, F, FP, Hp, Lp, wt);
@@ -506,6 +508,84 @@ cin_db_partial_kernel(const float* __restrict__ gp, long long B, int L, int D, f
     __syncthreads();
     if (threadIdx.x == 0) { float s = 0.f; for (int w = 0; w < 8; ++w) s += red[w]; part[(size_t)blockIdx.x * L + l] = s; }
 }
+// the same partial sums from the (Lp, M) layout: row l is contiguous
+__global__ void __launch_bounds__(256)
+cin_db_rows_kernel(const float* __restrict__ gLM, long long M, int L, float* __restrict__ part) {
+    __shared__ float red[8];
+    const int l = blockIdx.y;
+    const long long per = (M + gridDim.x - 1) / gridDim.x, r0 = (long long)blockIdx.x * per;
+    const long long r1 = r0 + per < M ? r0 + per : M;
+    const float* row = gLM + (size_t)l * M;
+    float acc = 0.f;
+    for (long long i = r0 + threadIdx.x; i < r1; i += 256) acc += __ldg(row + i);
+    for (int o = 16; o > 0; o >>= 1) acc += __shfl_xor_sync(0xffffffffu, acc, o);
+    if ((threadIdx.x & 31) == 0) red[threadIdx.x >> 5] = acc;
+    __syncthreads();
+    if (threadIdx.x == 0) { float s = 0.f; for (int w = 0; w < 8; ++w) s += red[w]; part[(size_t)blockIdx.x * L + l] = s; }
+}
+
+// g_pre = (act > 0) * ([l < direct] g_out[b, col_off + l] + [l in next range] g_hnext[b, l - next_off, d])  (cin.py:91-102
+// backward) written ONCE, straight into the two layouts the tensor-core kernels read: g_pre^T (B*D, Lp) for the
+// data-gradient GEMM and (Lp, B*D) for the weight-gradient GEMM (both zero padded to Lp) -- the (B, L, D) copy, its two
+// re-layout passes and their re-reads never happen.  One block per group of `spb` samples, through a shared-memory tile.
+// index split without integer division when the divisor is a power of two (lg >= 0)
+__device__ __forceinline__ void split(int i, int n, int lg, int& q, int& r) {
+    if (lg >= 0) { q = i >> lg; r = i & (n - 1); } else { q = i / n; r = i - q * n; }
+}
+
+__global__ void __launch_bounds__(256)
+cin_gpre_fused_kernel(const float* __restrict__ act, const float* __restrict__ g_out, const float* __restrict__ g_hnext,
+                      long long B, int L, int D, int Lp, int direct, int out_dim, int col_off, int next_off, int next_n,
+                      int spb, int lgD4, int lgLp4, float* __restrict__ gT, float* __restrict__ gLM) {
+    extern __shared__ float tile[];                      // [spb][L][D + 1]
+    const long long b0 = (long long)blockIdx.x * spb;
+    const int ns = (int)((B - b0 < spb) ? B - b0 : spb);
+    const int LD = L * D, D1 = D + 1, D4 = D >> 2, Lp4 = Lp >> 2;
+    const long long M = B * D;
+    // 1. g_pre of ns samples -> tile; 128-bit reads of the activation (d is contiguous)
+    for (int s = 0; s < ns; ++s) {
+        const long long b = b0 + s;
+        const float4* a4 = reinterpret_cast<const float4*>(act + b * LD);
+        float* ts = tile + (size_t)s * L * D1;
+        for (int i = threadIdx.x; i < (LD >> 2); i += 256) {
+            int l, c;
+            split(i, D4, lgD4, l, c);
+            const float4 a = __ldcs(a4 + i);
+            float gd = 0.f;
+            if (l < direct) gd = __ldg(g_out + b * out_dim + col_off + l);
+            float4 gh = make_float4(0.f, 0.f, 0.f, 0.f);
+            if (g_hnext && l >= next_off && l < next_off + next_n)
+                gh = __ldcs(reinterpret_cast<const float4*>(g_hnext + (b * next_n + (l - next_off)) * D) + c);
+            float* t = ts + l * D1 + (c << 2);
+            t[0] = a.x > 0.f ? gd + gh.x : 0.f; t[1] = a.y > 0.f ? gd + gh.y : 0.f;
+            t[2] = a.z > 0.f ? gd + gh.z : 0.f; t[3] = a.w > 0.f ? gd + gh.w : 0.f;
+        }
+    }
+    __syncthreads();
+    // 2. g_pre^T (B*D, Lp): rows (b, d), 128-bit stores along l
+    for (int i = threadIdx.x; i < ns * D * Lp4; i += 256) {
+        int sd, l4;
+        split(i, Lp4, lgLp4, sd, l4);
+        int s, d;
+        split(sd, D, lgD4 >= 0 ? lgD4 + 2 : -1, s, d);
+        const int l = l4 << 2;
+        const float* t = tile + ((size_t)s * L + l) * D1 + d;
+        float4 v;
+        v.x = l < L ? t[0] : 0.f; v.y = l + 1 < L ? t[D1] : 0.f; v.z = l + 2 < L ? t[2 * D1] : 0.f; v.w = l + 3 < L ? t[3 * D1] : 0.f;
+        __stcs(reinterpret_cast<float4*>(gT + ((b0 * D + sd) * Lp)) + l4, v);
+    }
+    // 3. (Lp, M): for every l the ns * D values of this sample group are contiguous, 128-bit stores along (s, d)
+    const int span4 = ns * D4;
+    for (int i = threadIdx.x; i < Lp * span4; i += 256) {
+        const int l = i / span4, c = i - l * span4;
+        int s, c4;
+        split(c, D4, lgD4, s, c4);
+        float4 v = make_float4(0.f, 0.f, 0.f, 0.f);
+        if (l < L) { const float* t = tile + ((size_t)s * L + l) * D1 + (c4 << 2); v = make_float4(t[0], t[1], t[2], t[3]); }
+        __stcs(reinterpret_cast<float4*>(gLM + (size_t)l * M + b0 * D) + c, v);
+    }
+}
+
 __global__ void cin_db_final_kernel(const float* __restrict__ part, int n, int L, float* __restrict__ gb) {
     const int l = blockIdx.x * blockDim.x + threadIdx.x;
     if (l >= L) return;
@@ -534,6 +614,38 @@ size_t cin_tc_dw_scratch_floats(long long B, int F, int D, int Hmax, int Lmax) {
     return (size_t)Lp * M + (size_t)ns * n_ktiles * 128 * Lp + 64 * (size_t)Lmax + 256;
 }
 
+// Can both tensor-core backward kernels take this layer (same conditions as their own checks)?
+bool cin_tc_bwd_supported(long long B, int F, int H, int D, int L) {
+    const int FP = cin_tc_fp(F);
+    if (!(FP > 0 && L <= 256 && D % 4 == 0)) return false;
+    const int HT = 256 / FP, NT = HT * FP, Lp = (L + 31) & ~31;
+    const size_t a_bytes = (size_t)(Lp / 32) * 128 * 128, b_stage = ((size_t)NT * 128 + 1023) & ~(size_t)1023;
+    if (a_bytes + b_stage + 256 + 1024 > 227 * 1024) return false;
+    const int nh_max = 127 / FP + 2;
+    const size_t smem = (size_t)tc::DW_NSTAGE * ((Lp * 128 + 1023) & ~1023) + (size_t)2 * (nh_max + F) * tc::SLAB * 4 + 256 + 1024;
+    return smem <= 227 * 1024 && (size_t)L * (D + 1) * 4 <= 64 * 1024;
+}
+
+// g_pre of one layer straight into the scratch layouts of cin_layer_bwd_data_tc (gT) and cin_layer_dw_tc (gLM)
+int cin_gpre_fused(const float* act, const float* g_out, const float* g_hnext, long long B, int L, int D, int direct,
+                   int out_dim, int col_off, int next_off, int next_n, float* bwd_scratch, float* dw_scratch, cudaStream_t st) {
+    using namespace tc;
+    const int Lp = (L + 31) & ~31;
+    const size_t per = (size_t)L * (D + 1) * 4;
+    int spb = (int)((64 * 1024) / per);
+    if (spb < 1) spb = 1;
+    if (spb > 8) spb = 8;
+    const size_t smem = per * spb;
+    if (smem > 48 * 1024)
+        DFM_CHECK_CUDA(cudaFuncSetAttribute(cin_gpre_fused_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
+    auto lg = [](int n) { int b = 0; while ((1 << b) < n) ++b; return (1 << b) == n ? b : -1; };
+    cin_gpre_fused_kernel<<<(unsigned)ceil_div(B, spb), 256, smem, st>>>(act, g_out, g_hnext, B, L, D, Lp, direct, out_dim, col_off,
+                                                                          next_off, next_n, spb, lg(D / 4), lg(Lp / 4), bwd_scratch,
+                                                                          dw_scratch);
+    DFM_CHECK_LAUNCH();
+    return DFM_OK;
+}
+
 // dW and db of one CIN layer on tcgen05
 int cin_layer_dw_tc(const float* g_pre, const float* x0, long long x_bs, const float* hid, long long h_bs, float* gw,
                     float* gb, long long B, int F, int H, int D, int L, float* scratch, cudaStream_t st) {
@@ -551,7 +663,7 @@ int cin_layer_dw_tc(const float* g_pre, const float* x0, long long x_bs, const f
     float* dbp = part + (size_t)ns * Kt * Lp;
     long long gb_ = ceil_div((long long)Lp * M, 256);
     if (gb_ > 16LL * sm_count()) gb_ = 16LL * sm_count();
-    cin_gpre_lm_kernel<<<(unsigned)gb_, 256, 0, st>>>(g_pre, B, L, D, Lp, M, gLM);
+    if (g_pre) cin_gpre_lm_kernel<<<(unsigned)gb_, 256, 0, st>>>(g_pre, B, L, D, Lp, M, gLM);   // nullptr: already there
     DFM_CHECK_LAUNCH();
     CUtensorMap gmap;
     int rc = make_tmap_2d(&gmap, gLM, Lp, M, Lp);
@@ -566,7 +678,8 @@ int cin_layer_dw_tc(const float* g_pre, const float* x0, long long x_bs, const f
     cin_tc_dw_kernel<<<dim3(n_ktiles, real_slices), DW_THREADS, smem, st>>>(a, gmap);
     cin_dw_reduce_kernel<<<(unsigned)ceil_div((long long)L * H * F, 256), 256, 0, st>>>(part, real_slices, Kt, Lp, L, H, F, FP, gw);
     const int dbs = 64;
-    cin_db_partial_kernel<<<dim3(dbs, L), 256, 0, st>>>(g_pre, B, L, D, dbp);
+    if (g_pre) cin_db_partial_kernel<<<dim3(dbs, L), 256, 0, st>>>(g_pre, B, L, D, dbp);
+    else cin_db_rows_kernel<<<dim3(dbs, L), 256, 0, st>>>(gLM, M, L, dbp);
     cin_db_final_kernel<<<(unsigned)ceil_div(L, 128), 128, 0, st>>>(dbp, dbs, L, gb);
     DFM_CHECK_LAUNCH();
     return DFM_OK;
