@@ -42,7 +42,7 @@ BATCH = 65536
 EMBED_DIM = 64
 WORKLOAD = "deepfm_criteo_13dense_26sparse_d64_b65536_per_gpu"
 K1_BYTES_PER_SAMPLE = 26 * (8 + 4 * EMBED_DIM + 4) + 13 * 4 + 4 * 39 * EMBED_DIM + 8   # 17012
-K1_DRAM_TRAFFIC = 752_747_520          # bytes per launch, ncu --set full (profiles/r1_ncu_full_kernels.csv)
+K1_DRAM_TRAFFIC = 741_201_408          # bytes per launch, ncu --set full (profiles/r1_ncu_full_kernels.csv: 112.9 MB read + 628.3 MB written)
 CPU_SAMPLE_BATCH = 8192
 CPU_SAMPLE_MAX_VOCAB = 1_000_000
 
@@ -184,6 +184,8 @@ def run_ours(args, rank: int, local_rank: int, n_gpus: int):
 
     if not torch.cuda.is_available():
         raise RuntimeError("bench.py needs a CUDA device: the deepfm_b200 kernels have no CPU fallback")
+    if os.environ.get("NCCL_DEBUG", "").upper() == "VERSION":
+        os.environ["NCCL_DEBUG"] = "WARN"        # NCCL prints its version banner on STDOUT: keep stdout to the one JSON line
     _lib.lib()
     torch.cuda.set_device(local_rank)
     dev = torch.device("cuda", local_rank)
