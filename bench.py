@@ -58,6 +58,19 @@ MULTIHOT_ROWS_PER_GPU = 125_000_000     # config 5: 1 B rows over 8 GPUs (32 GB 
 MULTIHOT_BATCH = 16384                  # per GPU: CIN [128,128] at F = 39, D = 64 is 197 MFLOP per sample
 
 
+_RESULT_FD = None      # the real stdout; fd 1 is pointed at stderr while the bench runs (see main)
+
+
+def emit(line: dict) -> None:
+    """The ONE JSON line of the contract, on the real stdout."""
+    data = (json.dumps(line) + "\n").encode()
+    if _RESULT_FD is None:
+        sys.stdout.write(data.decode())
+        sys.stdout.flush()
+    else:
+        os.write(_RESULT_FD, data)
+
+
 def bench_config(workload: str = "deepfm_criteo"):
     from deepfm_b200.config import ExperimentConfig
     cfg = ExperimentConfig()
@@ -172,7 +185,7 @@ def run_reference(args, rank: int, n_gpus: int):
                  "cpu_baseline": {"value": r["value"], "unit": UNIT, "cores": r["cores"], "kind": "port", "sample": r["sample"]},
                  "e2e": {"value": r["value"], "unit": UNIT, "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0},
                  "gpu_launches": 0, "dtype": "f32"})
-    print(json.dumps(line), flush=True)
+    emit(line)
 
 
 # ------------------------------------------------------------------------------------ GPU arm
@@ -396,7 +409,7 @@ def run_ours(args, rank: int, local_rank: int, n_gpus: int):
     if n_gpus == 1 and not args.no_cpu_baseline and wl == "deepfm_criteo":
         r = cpu_reference_run(steps=3, warmup=1, budget_s=60.0)
         line["cpu_baseline"] = {"value": r["value"], "unit": UNIT, "cores": r["cores"], "kind": "port", "sample": r["sample"]}
-    print(json.dumps(line), flush=True)
+    emit(line)
     if n_gpus > 1:
         dist.destroy_process_group()
 
@@ -426,6 +439,12 @@ def main():
                "--gpus", str(args.gpus), "--steps", str(args.steps), "--warmup", str(args.warmup), "--impl", args.impl,
                "--workload", args.workload, "--cin-precision", args.cin_precision, "--dnn-gemm", args.dnn_gemm]
         sys.exit(subprocess.call(cmd))
+    # Libraries (NCCL's version banner, for one) write to fd 1: point it at stderr for the whole run and keep the
+    # real stdout for the single JSON line.
+    global _RESULT_FD
+    sys.stdout.flush()
+    _RESULT_FD = os.dup(1)
+    os.dup2(2, 1)
     if args.impl != "reference" and args.dnn_gemm == "emulated":
         from deepfm_b200 import fp32_emulation          # before anything imports torch
         fp32_emulation.enable()
