@@ -319,8 +319,9 @@ def run_ours(args, rank: int, local_rank: int, n_gpus: int):
     def e2e_step(i):
         batch, labels, ev = pending.pop()
         main_stream.wait_event(ev)
-        pending.append(issue_copy(i + 1))
-        return step(batch, labels).item()
+        loss = step(batch, labels)                 # every kernel of step i is enqueued ...
+        pending.append(issue_copy(i + 1))          # ... then the host issues the copies of step i + 1 (they overlap step i)
+        return loss.item()
 
     for i in range(2):
         e2e_step(i)

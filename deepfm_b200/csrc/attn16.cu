@@ -345,6 +345,7 @@ attn16_bwd_kernel(const __grid_constant__ Attn16Args a) {
 // C[n][m] = sum_rows L[row][n] * R[row][m]  and  csum[n] = sum_rows L[row][n], for a slice of rows per block:
 // partials[slice] = [C (N*M) | csum (N)].  N, M multiples of 4; thread tiles of 4 x 4, RC rows per smem chunk.
 constexpr int TS_RC = 32;
+template <int TS_LV, int TS_RV>   // float4 of L / of R per thread and chunk: N <= 32 * TS_LV, M <= 32 * TS_RV
 __global__ void __launch_bounds__(256)
 tsgemm_kernel(const float* __restrict__ L, int ldl, int N, const float* __restrict__ R, int ldr, int M,
               long long rows, long long slice_rows, float* __restrict__ partials) {
@@ -363,22 +364,45 @@ tsgemm_kernel(const float* __restrict__ L, int ldl, int N, const float* __restri
     const bool on0 = t0 < n_tiles, on1 = t1 < n_tiles;
     const long long r_lo = (long long)blockIdx.x * slice_rows;
     const long long r_hi = r_lo + slice_rows < rows ? r_lo + slice_rows : rows;
-    for (long long rc = r_lo; rc < r_hi; rc += TS_RC) {
+    // register double buffer: the next chunk's global loads are in flight while the current chunk is multiplied
+    const int nl4 = N >> 2, n_l = TS_RC * nl4, n_r = TS_RC * tm;
+    float4 lbuf[TS_LV], rbuf[TS_RV];
+    auto fetch = [&](long long rc) {
         const int nr = (int)(r_hi - rc < TS_RC ? r_hi - rc : TS_RC);
-        __syncthreads();
-        for (int i = tid; i < TS_RC * (N >> 2); i += 256) {
-            const int rr = i / (N >> 2), c = (i - rr * (N >> 2)) << 2;
-            float4 v = make_float4(0.f, 0.f, 0.f, 0.f);
-            if (rr < nr) v = __ldcs(reinterpret_cast<const float4*>(L + (size_t)(rc + rr) * ldl + c));
-            *reinterpret_cast<float4*>(Ls + rr * N + c) = v;
+#pragma unroll
+        for (int q = 0; q < TS_LV; ++q) {
+            const int i = tid + q * 256;
+            lbuf[q] = make_float4(0.f, 0.f, 0.f, 0.f);
+            if (i < n_l) {
+                const int rr = i / nl4, c = (i - rr * nl4) << 2;
+                if (rr < nr) lbuf[q] = __ldcs(reinterpret_cast<const float4*>(L + (size_t)(rc + rr) * ldl + c));
+            }
         }
-        for (int i = tid; i < TS_RC * tm; i += 256) {
-            const int rr = i / tm, c = (i - rr * tm) << 2;
-            float4 v = make_float4(0.f, 0.f, 0.f, 0.f);
-            if (rr < nr) v = __ldcs(reinterpret_cast<const float4*>(R + (size_t)(rc + rr) * ldr + c));
-            *reinterpret_cast<float4*>(Rs + rr * M + c) = v;
+#pragma unroll
+        for (int q = 0; q < TS_RV; ++q) {
+            const int i = tid + q * 256;
+            rbuf[q] = make_float4(0.f, 0.f, 0.f, 0.f);
+            if (i < n_r) {
+                const int rr = i / tm, c = (i - rr * tm) << 2;
+                if (rr < nr) rbuf[q] = __ldcs(reinterpret_cast<const float4*>(R + (size_t)(rc + rr) * ldr + c));
+            }
+        }
+    };
+    if (r_lo < r_hi) fetch(r_lo);
+    for (long long rc = r_lo; rc < r_hi; rc += TS_RC) {
+        __syncthreads();
+#pragma unroll
+        for (int q = 0; q < TS_LV; ++q) {
+            const int i = tid + q * 256;
+            if (i < n_l) { const int rr = i / nl4, c = (i - rr * nl4) << 2; *reinterpret_cast<float4*>(Ls + rr * N + c) = lbuf[q]; }
+        }
+#pragma unroll
+        for (int q = 0; q < TS_RV; ++q) {
+            const int i = tid + q * 256;
+            if (i < n_r) { const int rr = i / tm, c = (i - rr * tm) << 2; *reinterpret_cast<float4*>(Rs + rr * M + c) = rbuf[q]; }
         }
         __syncthreads();
+        if (rc + TS_RC < r_hi) fetch(rc + TS_RC);
         if (on0) {
 #pragma unroll 4
             for (int rr = 0; rr < TS_RC; ++rr) {
@@ -517,9 +541,14 @@ int attn16_bwd(const float* x, const float* g_out, int64_t B, int F, int A, int 
     const long long rows = (long long)B * F;
     // [dWq | dWk | dWv] (3A x 16) = [gQ | gK | gV]^T x  (+ column sums = the bias gradients);  dWo (16 x A) = g_r^T O
     const size_t sm1 = (size_t)TS_RC * (3 * A + 16) * 4, sm2 = (size_t)TS_RC * (16 + A) * 4;
-    DFM_CHECK_CUDA(cudaFuncSetAttribute(tsgemm_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)(sm1 > sm2 ? sm1 : sm2)));
-    tsgemm_kernel<<<L.slices, 256, sm1, st>>>(a.G, 3 * A, 3 * A, x, 16, 16, rows, L.slice_rows, p1);
-    tsgemm_kernel<<<L.slices, 256, sm2, st>>>(a.GR, 16, 16, a.O, A, A, rows, L.slice_rows, p2);
+    if (3 * A <= 256) {
+        DFM_CHECK_CUDA(cudaFuncSetAttribute(tsgemm_kernel<8, 1>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)sm1));
+        tsgemm_kernel<8, 1><<<L.slices, 256, sm1, st>>>(a.G, 3 * A, 3 * A, x, 16, 16, rows, L.slice_rows, p1);
+    } else {
+        DFM_CHECK_CUDA(cudaFuncSetAttribute(tsgemm_kernel<12, 1>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)sm1));
+        tsgemm_kernel<12, 1><<<L.slices, 256, sm1, st>>>(a.G, 3 * A, 3 * A, x, 16, 16, rows, L.slice_rows, p1);
+    }
+    tsgemm_kernel<1, 4><<<L.slices, 256, sm2, st>>>(a.GR, 16, 16, a.O, A, A, rows, L.slice_rows, p2);   // A <= 128
     SegOut s1, s2, s3;
     memset(&s1, 0, sizeof(s1)); memset(&s2, 0, sizeof(s2)); memset(&s3, 0, sizeof(s3));
     const int AD = A * 16;

@@ -8,11 +8,26 @@ B = int(sys.argv[1]) if len(sys.argv) > 1 else 65536
 att = MultiHeadSelfAttention(16, 4, 64, 1, True).cuda()
 x = torch.randn(B, 16, 16, device="cuda", requires_grad=True)
 g = torch.randn(B, 16, 16, device="cuda")
-for _ in range(3):
+def one():
     att.zero_grad(set_to_none=True); x.grad = None
-    att(x).backward(g)
+    y = att(x)
+    y.backward(g)
+
+for _ in range(5):
+    one()
 torch.cuda.synchronize()
-a, b, c = (torch.cuda.Event(enable_timing=True) for _ in range(3))
-a.record(); y = att(x); b.record(); y.backward(g); c.record(); torch.cuda.synchronize()
+n = 10
+a, b = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+a.record()
+for _ in range(n):
+    with torch.no_grad():
+        att(x)
+b.record(); torch.cuda.synchronize()
+fwd = a.elapsed_time(b) / n
+a.record()
+for _ in range(n):
+    one()
+b.record(); torch.cuda.synchronize()
+both = a.elapsed_time(b) / n
 flops = B * (2 * 16 * 16 * 3 * 64 + 4 * 4 * 16 * 16 * 16 + 2 * 16 * 64 * 16)
-print(f"attention B={B}: fwd {a.elapsed_time(b):.3f} ms ({flops / a.elapsed_time(b) / 1e9:.1f} TFLOP/s), bwd {b.elapsed_time(c):.3f} ms")
+print(f"attention B={B}: fwd {fwd:.3f} ms ({flops / fwd / 1e9:.1f} TFLOP/s), fwd+bwd {both:.3f} ms")
