@@ -362,6 +362,41 @@ class ShardedFeatureEmbedding(nn.Module):
                     mine.weight.copy_(theirs.weight)
                     mine.bias.copy_(theirs.bias)
 
+    @torch.no_grad()
+    def full_state_dict(self, group=None) -> Dict[str, torch.Tensor]:
+        """Collective: the embedding's parameters in the REFERENCE layout (``FeatureEmbedding.state_dict`` keys and
+        shapes: ``second_order_embeddings.<f>.weight (V, d)`` ...), every rank's rows interleaved back to
+        ``id = (rank - f) mod W + W * local_row`` -- the inverse of ``load_from_full``.  Returned on every rank (CPU
+        tensors), so rank 0 can ``torch.save`` a checkpoint the unsharded module / the reference loads
+        (checkpoint interop for sharded tables)."""
+        import torch.distributed as dist
+        W = self.world
+        out: Dict[str, torch.Tensor] = {}
+        for f, name in enumerate(self.field_names):
+            for prefix, mod in (("second_order_embeddings", self.second_order_embeddings[name]),
+                                ("first_order_embeddings", self.first_order_embeddings[name])):
+                if not isinstance(mod, (nn.Embedding, nn.EmbeddingBag)) or f in self._repl_idx:
+                    for k, v in mod.state_dict().items():        # replicated: rank-local copy is the parameter
+                        out[f"{prefix}.{name}.{k}"] = v.detach().cpu().clone()
+                    continue
+                V = self._vocabs[f]
+                mine = mod.weight.detach()
+                rows_max = (V + W - 1) // W                       # shards differ by at most one row: pad, gather, trim
+                pad = torch.zeros((rows_max, mine.shape[1]), dtype=mine.dtype, device=mine.device)
+                pad[: min(mine.shape[0], rows_max)] = mine[:rows_max]
+                if W > 1:
+                    parts = [torch.empty_like(pad) for _ in range(W)]
+                    dist.all_gather(parts, pad, group=group)
+                else:
+                    parts = [pad]
+                full = torch.empty((V, mine.shape[1]), dtype=mine.dtype)
+                for r in range(W):
+                    first = (r - f) % W                           # smallest id rank r owns in this table
+                    n = len(range(first, V, W))
+                    full[first::W] = parts[r][:n].cpu()
+                out[f"{prefix}.{name}.weight"] = full
+        return out
+
     # -- plans --------------------------------------------------------------------------------
     def _ensure_plans(self):
         if self._plans is None:

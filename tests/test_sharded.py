@@ -162,6 +162,44 @@ def test_sharded_module_bookkeeping_cpu():
             assert torch.equal(got_owner[sent], owner[sent])
 
 
+def _ckpt_worker(rank, world, port, out):
+    import torch.distributed as dist
+    os.environ.update(MASTER_ADDR="127.0.0.1", MASTER_PORT=str(port))
+    dist.init_process_group("gloo", rank=rank, world_size=world)
+    from deepfm_b200.layers.embedding import FeatureEmbedding
+    from deepfm_b200.sharded import ShardedFeatureEmbedding
+    torch.manual_seed(0)                                   # the same "checkpoint" on every rank
+    schema = _schema(8, multihot=True)
+    full = FeatureEmbedding(schema, 8)
+    with torch.no_grad():
+        for p in full.parameters():
+            p.add_(0.1 * torch.randn_like(p))
+    shard = ShardedFeatureEmbedding(schema, 8, world, rank, replicate_below=60)
+    shard.load_from_full(full)
+    sd = shard.full_state_dict()                           # collective: shards -> reference layout
+    ref = full.state_dict()
+    ok = set(sd) == set(ref) and all(sd[k].shape == ref[k].shape and torch.equal(sd[k], ref[k]) for k in ref)
+    again = FeatureEmbedding(schema, 8)
+    again.load_state_dict(sd)                              # the unsharded module (reference keys) loads it
+    out.put((rank, ok))
+    dist.destroy_process_group()
+
+
+def test_sharded_checkpoint_round_trip_gloo_world2():
+    """load_from_full -> full_state_dict is the identity on the reference-layout state_dict."""
+    ctx = mp.get_context("spawn")
+    q = ctx.Queue()
+    port = 33000 + os.getpid() % 2000
+    procs = [ctx.Process(target=_ckpt_worker, args=(r, 2, port, q)) for r in range(2)]
+    for p in procs:
+        p.start()
+    res = [q.get(timeout=180) for _ in procs]
+    for p in procs:
+        p.join(timeout=60)
+        assert p.exitcode == 0
+    assert all(r[1] for r in res), res
+
+
 def _reducer_worker(rank, world, port, out):
     import torch.distributed as dist
     os.environ.update(MASTER_ADDR="127.0.0.1", MASTER_PORT=str(port))
