@@ -50,11 +50,11 @@ SIGNATURES = {
     "dfm_cin_bwd": (C.c_int, [_vp, _vp, _i64, C.c_int, C.c_int, C.c_int, _pi32, C.c_int, _pp, C.c_int,
                               _vp, _vp, _pp, _pp, _vp, _sz, _vp]),
     "dfm_shard_route_workspace_bytes": (_sz, [_vp, _i64]),
-    "dfm_shard_route": (C.c_int, [_vp, C.c_int, _pi64, _i64, _pp, _vp, _vp, _vp, _vp, _sz, _vp]),
+    "dfm_shard_route": (C.c_int, [_vp, C.c_int, _pi64, _i64, _pp, _vp, _vp, _vp, _vp, _vp, _sz, _vp]),
     "dfm_shard_gather": (C.c_int, [_vp, C.c_int, C.c_int, _pi64, _i64, _vp, _pp, _vp, _vp, _vp]),
     "dfm_shard_pack_grad": (C.c_int, [_vp, _i64, _vp, _vp, _vp, _vp, _vp, _vp, _vp, _vp, _vp, _vp]),
     "dfm_shard_gather_p2p": (C.c_int, [_vp, C.c_int, C.c_int, _pi64, _i64, _vp, _pp, C.c_int, _pi64, _pp, _vp, _vp]),
-    "dfm_shard_pack_grad_p2p": (C.c_int, [_vp, _i64, _vp, _vp, _vp, _vp, _vp, _vp, _vp, _vp, C.c_int, _pi64, _pp, _vp]),
+    "dfm_shard_pack_grad_p2p": (C.c_int, [_vp, _i64, _vp, _vp, _vp, _vp, _vp, _vp, _vp, _vp, C.c_int, _pi64, _pp, _vp, _vp]),
     "dfm_plan_set_table_stride": (C.c_int, [_vp, C.c_int, C.c_int]),
     "dfm_plan_set_field_source": (C.c_int, [_vp, C.c_int, C.c_int, C.c_int, C.c_int]),
     "dfm_rows_bwd_workspace_bytes": (_sz, [_vp, _i64]),

@@ -89,6 +89,8 @@ struct PackArgs {
     const long long* pos;  // per field f: (B, max_len) block at B * slot_base[f]; 1-based send position, 0 = not sent
     long long B;
     int S, T, F, D, dmax, A;
+    const uint32_t* send_slots;   // optional: send position -> id slot index b * S + s (the inverse of pos)
+    long long n_sent;
     unsigned short slot_tf[MAX_SLOTS];   // id slot -> index into ShardArgs::f
 };
 
@@ -104,13 +106,17 @@ shard_pack_kernel(const __grid_constant__ ShardArgs a, const __grid_constant__ P
                   float* __restrict__ g_vec, const __grid_constant__ PeerDst pd) {
     const int gpb = blockDim.x / G;
     const int gl = threadIdx.x / G, j = threadIdx.x - gl * G;
-    const long long n = p.B * p.S;
-    for (long long i = (long long)blockIdx.x * gpb + gl; i < n; i += (long long)gridDim.x * gpb) {
+    // With send_slots the groups walk the SEND order: consecutive groups write consecutive rows of the same peer's
+    // buffer (long sequential NVLink store streams; the random access moves to the local gradient reads).
+    // Without it they walk the id slots and look the send position up.
+    const long long n = p.send_slots ? p.n_sent : p.B * p.S;
+    for (long long t = (long long)blockIdx.x * gpb + gl; t < n; t += (long long)gridDim.x * gpb) {
+        const long long i = p.send_slots ? (long long)__ldg(p.send_slots + t) : t;
         const long long b = i / p.S;
         const int s = (int)(i - b * p.S);
         if (p.slot_tf[s] == 0xffff) continue;                  // replicated table: its gradient is local
         const ShardField& sf = a.f[p.slot_tf[s]];
-        const long long q = __ldg(p.pos + p.B * sf.slot_base + b * sf.max_len + (s - sf.slot_base)) - 1;
+        const long long q = p.send_slots ? t : __ldg(p.pos + p.B * sf.slot_base + b * sf.max_len + (s - sf.slot_base)) - 1;
         if (q < 0) continue;                                   // padding entry of a bag: nothing was sent
         float scale = 1.f;
         if (sf.bag == 2) scale = __uint_as_float(__ldg(p.aux + (size_t)b * p.A + sf.aux_off));
@@ -219,7 +225,7 @@ __global__ void route_scan_kernel(const int* __restrict__ block_counts, int nblk
 
 __global__ void __launch_bounds__(256)
 route_scatter_kernel(const __grid_constant__ RouteArgs a, const long long* __restrict__ offsets, int nblk,
-                     uint32_t* __restrict__ send_keys, long long* __restrict__ pos) {
+                     uint32_t* __restrict__ send_keys, long long* __restrict__ pos, uint32_t* __restrict__ send_slots) {
     __shared__ long long run[RT_MAXW];
     __shared__ int warp_cnt[8][RT_MAXW];
     __shared__ RouteField t[MAX_FIELDS];
@@ -249,6 +255,7 @@ route_scatter_kernel(const __grid_constant__ RouteArgs a, const long long* __res
                 q = run[o] + rank;
                 for (int w2 = 0; w2 < warp; ++w2) q += warp_cnt[w2][o];
                 send_keys[q] = rf->gbase + (uint32_t)id;
+                if (send_slots) send_slots[q] = (uint32_t)i;
             }
             pos[a.B * rf->slot_base + b * rf->max_len + (s - rf->slot_base)] = q + 1;   // 1-based, 0 = not sent
         }
@@ -380,7 +387,8 @@ int dfm_shard_gather_p2p(const dfm_plan* local_plan, int world, int rank, const 
 static int shard_pack_impl(const dfm_plan* plan, int64_t batch, const int64_t* positions, const float* g_first,
                            const float* g_field, const float* g_flat, const float* g_fm, const float* fm_sum,
                            const float* field_emb, const uint32_t* aux, float* g_vec, int n_peers,
-                           const int64_t* peer_start, float* const* peer_rows, void* stream) {
+                           const int64_t* peer_start, float* const* peer_rows, const uint32_t* send_slots, int64_t n_sent,
+                           void* stream) {
     DFM_REQUIRE(plan && batch >= 0, DFM_ERR_INVALID, "dfm_shard_pack_grad: bad argument");
     if (batch == 0 || plan->S == 0) return DFM_OK;
     DFM_REQUIRE(positions && (g_vec || n_peers > 0) && (!g_fm || fm_sum), DFM_ERR_INVALID, "dfm_shard_pack_grad: null tensor");
@@ -403,13 +411,15 @@ static int shard_pack_impl(const dfm_plan* plan, int64_t batch, const int64_t* p
     p.aux = aux; p.A = plan->A;
     p.pos = reinterpret_cast<const long long*>(positions); p.B = batch; p.S = plan->S; p.T = plan->T;
     p.F = plan->n_fields; p.D = plan->fm_dim; p.dmax = plan->max_tdim;
+    p.send_slots = send_slots; p.n_sent = n_sent;
+    if (send_slots && n_sent <= 0) return DFM_OK;
     fill_slot_tf(plan, p.slot_tf);
     auto al16 = [](const void* q) { return (reinterpret_cast<uintptr_t>(q) & 15u) == 0; };
     const bool v4 = plan->vec == 4 && al16(g_flat) && al16(g_field) && al16(fm_sum) && al16(g_vec) && al16(field_emb);
     const int lanes = p.dmax / (v4 ? 4 : 1);
     DFM_REQUIRE(lanes <= 32, DFM_ERR_UNSUPPORTED, "dfm_shard_pack_grad: table dim %d too wide", p.dmax);
     const int G = next_pow2(lanes);
-    long long blocks = ceil_div(batch * plan->S, 256 / G);
+    long long blocks = ceil_div(send_slots ? n_sent : batch * plan->S, 256 / G);
     if (blocks > 8LL * sm_count()) blocks = 8LL * sm_count();
     cudaStream_t st = static_cast<cudaStream_t>(stream);
     if (v4) shard_pack_kernel<4><<<(unsigned)blocks, 256, 0, st>>>(*a, p, G, g_vec, *pd);
@@ -422,16 +432,16 @@ int dfm_shard_pack_grad(const dfm_plan* plan, int64_t batch, const int64_t* posi
                         const float* g_field, const float* g_flat, const float* g_fm, const float* fm_sum,
                         const float* field_emb, const uint32_t* aux, float* g_vec, void* stream) {
     return shard_pack_impl(plan, batch, positions, g_first, g_field, g_flat, g_fm, fm_sum, field_emb, aux, g_vec, 0, nullptr,
-                           nullptr, stream);
+                           nullptr, nullptr, 0, stream);
 }
 
 int dfm_shard_pack_grad_p2p(const dfm_plan* plan, int64_t batch, const int64_t* positions, const float* g_first,
                             const float* g_field, const float* g_flat, const float* g_fm, const float* fm_sum,
                             const float* field_emb, const uint32_t* aux, int n_peers, const int64_t* peer_start,
-                            float* const* peer_rows, void* stream) {
+                            float* const* peer_rows, const uint32_t* send_slots, void* stream) {
     DFM_REQUIRE(n_peers > 0, DFM_ERR_INVALID, "dfm_shard_pack_grad_p2p: no peers");
     return shard_pack_impl(plan, batch, positions, g_first, g_field, g_flat, g_fm, fm_sum, field_emb, aux, nullptr, n_peers,
-                           peer_start, peer_rows, stream);
+                           peer_start, peer_rows, send_slots, send_slots ? peer_start[n_peers] - peer_start[0] : 0, stream);
 }
 
 size_t dfm_shard_route_workspace_bytes(const dfm_plan* plan, int64_t batch) {
@@ -442,7 +452,7 @@ size_t dfm_shard_route_workspace_bytes(const dfm_plan* plan, int64_t batch) {
 
 int dfm_shard_route(const dfm_plan* plan, int world, const int64_t* global_row_base, int64_t batch,
                     const void* const* inputs, uint32_t* send_keys, int64_t* positions, int64_t* counts,
-                    void* workspace, size_t workspace_bytes, void* stream) {
+                    uint32_t* send_slots, void* workspace, size_t workspace_bytes, void* stream) {
     DFM_REQUIRE(plan && global_row_base && inputs && counts && world > 0 && world <= RT_MAXW && batch >= 0, DFM_ERR_INVALID,
                 "dfm_shard_route: bad argument (world must be 1..%d)", RT_MAXW);
     cudaStream_t st = static_cast<cudaStream_t>(stream);
@@ -471,7 +481,7 @@ int dfm_shard_route(const dfm_plan* plan, int world, const int64_t* global_row_b
     long long* offsets = reinterpret_cast<long long*>(static_cast<char*>(workspace) + align_up((size_t)nblk * RT_MAXW * 4, 256));
     route_count_kernel<<<nblk, 256, 0, st>>>(*a, block_counts);
     route_scan_kernel<<<1, 32, 0, st>>>(block_counts, nblk, world, offsets, reinterpret_cast<long long*>(counts));
-    route_scatter_kernel<<<nblk, 256, 0, st>>>(*a, offsets, nblk, send_keys, reinterpret_cast<long long*>(positions));
+    route_scatter_kernel<<<nblk, 256, 0, st>>>(*a, offsets, nblk, send_keys, reinterpret_cast<long long*>(positions), send_slots);
     DFM_CHECK_LAUNCH();
     return DFM_OK;
 }

@@ -60,6 +60,7 @@ class Route:
     order: Optional[torch.Tensor]  # (n,) int64: send position -> source slot index b*S + s (torch path only)
     pos: torch.Tensor            # (b*S,) int64, field-major: field f's (b, max_len) block at b * slot_base[f];
     #                              1-based send position of every id slot, 0 = not sent (padding id of a bag)
+    send_slots: Optional[torch.Tensor] = None   # (n,) int32: send position -> id slot index b*S + s (kernel path)
 
 
 def field_positions(pos: torch.Tensor, b: int, lens: Sequence[int]) -> List[torch.Tensor]:
@@ -222,7 +223,7 @@ class _ShardedEmbedFn(torch.autograd.Function):
         first, field, flat, fm, fm_sum, aux, fin_inputs, keys = mod.finish(inputs, route.pos, got, need_bwd)
         ctx.mod, ctx.n_inputs = mod, n_inputs
         ctx.counts = (send_counts, recv_counts)
-        ctx.p2p = (px, matrix, parity) if use_p2p else None
+        ctx.p2p = (px, matrix, parity, route.send_slots) if use_p2p else None
         ctx.set_materialize_grads(False)
         ctx.l2, ctx.done = None, False
         if need_bwd:
@@ -247,7 +248,7 @@ class _ShardedEmbedFn(torch.autograd.Function):
                                              cont(g_fm), field, flat, fm_sum, params, lam, gscale, aux, p2p=ctx.p2p,
                                              keys=ctx.keys)
         if ctx.p2p is not None:           # the gradient rows were stored straight into the owners' buffers
-            px, matrix, parity = ctx.p2p
+            px, matrix, parity, _ = ctx.p2p
             px.barrier(1)
             g_recv = px.view(1, parity, int(sum(recv_counts)))
         else:
@@ -465,11 +466,12 @@ class ShardedFeatureEmbedding(nn.Module):
             send_keys = torch.empty((b * max(self._S, 1),), device=dev, dtype=torch.int32)
             pos = torch.empty((b * S,), device=dev, dtype=torch.int64)
             counts = torch.empty((W,), device=dev, dtype=torch.int64)
+            send_slots = torch.empty_like(send_keys)
             ws = torch.empty((max(lib.dfm_shard_route_workspace_bytes(sample_plan, b), 16),), device=dev, dtype=torch.uint8)
             _lib.check(lib.dfm_shard_route(sample_plan, W, _lib.i64_array(self._global_row_base), b, _lib.ptr_array(inputs),
-                                           _lib.ptr(send_keys), _lib.ptr(pos), _lib.ptr(counts), ws.data_ptr(), ws.numel(),
-                                           _lib.stream_ptr()), "dfm_shard_route")
-            return Route(send_keys=send_keys, counts=counts, order=None, pos=pos)
+                                           _lib.ptr(send_keys), _lib.ptr(pos), _lib.ptr(counts), _lib.ptr(send_slots),
+                                           ws.data_ptr(), ws.numel(), _lib.stream_ptr()), "dfm_shard_route")
+            return Route(send_keys=send_keys, counts=counts, order=None, pos=pos, send_slots=send_slots)
         return self.route_torch(inputs)
 
     def route_torch(self, inputs: Sequence[torch.Tensor]) -> Route:
@@ -595,7 +597,7 @@ class ShardedFeatureEmbedding(nn.Module):
         b = flat.shape[0]
         n = got.shape[0] - 1
         if p2p is not None:
-            px, matrix, parity = p2p
+            px, matrix, parity, send_slots = p2p
             W, me = self.world, self.rank
             stride_b = (self.fm_embed_dim + 4) * 4
             starts, bases, acc = [0], [], 0
@@ -608,7 +610,7 @@ class ShardedFeatureEmbedding(nn.Module):
             _lib.check(lib.dfm_shard_pack_grad_p2p(sample_plan, b, _lib.ptr(pos), _lib.ptr(g_first), _lib.ptr(g_field),
                                                    _lib.ptr(g_flat), _lib.ptr(g_fm), _lib.ptr(fm_sum), field.data_ptr(),
                                                    _lib.ptr(aux), W, _lib.i64_array(starts), _lib.ptr_array(bases),
-                                                   _lib.stream_ptr()), "dfm_shard_pack_grad_p2p")
+                                                   _lib.ptr(send_slots), _lib.stream_ptr()), "dfm_shard_pack_grad_p2p")
         else:
             g_rows = torch.empty((n, self.fm_embed_dim + 4), device=dev, dtype=torch.float32)
             _lib.check(lib.dfm_shard_pack_grad(sample_plan, b, _lib.ptr(pos), _lib.ptr(g_first), _lib.ptr(g_field),

@@ -206,6 +206,8 @@ DFM_API int dfm_attn_bwd(const float* x, const float* g_out, int64_t batch, int 
  *       the (B, max_len[f]) block at offset B * slot_base[f] holds the 1-based send position of every
  *       slot (0 = nothing sent: a padding id of a multi-hot bag; the padding id of a SPARSE field IS
  *       sent, its row 0 is returned as stored).  The blocks are K1's id columns of the sample-side plan.
+ *       send_slots (optional, <= B*S): the inverse map, send position -> id slot index b*S + s; with it
+ *       dfm_shard_pack_grad_p2p walks the send order, so every peer receives one sequential store stream.
  *   dfm_shard_gather : owner side.  keys = global rows (row_base[f] + id) as received; writes the
  *       reply rows [row (d), first-order weight, 0, 0, 0] and the local sort keys
  *       (local_row_base[f] + local_row, PAD for id 0) the owner-side backward consumes.
@@ -224,7 +226,7 @@ DFM_API int dfm_attn_bwd(const float* x, const float* g_out, int64_t batch, int 
 DFM_API size_t dfm_shard_route_workspace_bytes(const dfm_plan* plan, int64_t batch);
 DFM_API int dfm_shard_route(const dfm_plan* plan, int world, const int64_t* global_row_base,
                             int64_t batch, const void* const* inputs, uint32_t* send_keys,
-                            int64_t* positions, int64_t* counts, void* workspace,
+                            int64_t* positions, int64_t* counts, uint32_t* send_slots, void* workspace,
                             size_t workspace_bytes, void* stream);
 DFM_API int dfm_shard_gather(const dfm_plan* local_plan, int world, int rank,
                              const int64_t* global_row_base, int64_t n_keys, const uint32_t* keys,
@@ -248,7 +250,7 @@ DFM_API int dfm_shard_pack_grad_p2p(const dfm_plan* plan, int64_t batch, const i
                                     const float* g_first, const float* g_field, const float* g_flat,
                                     const float* g_fm, const float* fm_sum, const float* field_emb,
                                     const uint32_t* aux, int n_peers, const int64_t* peer_start,
-                                    float* const* peer_rows, void* stream);
+                                    float* const* peer_rows, const uint32_t* send_slots, void* stream);
 /* Per-field table source of a plan: row_stride / w1_stride (floats, 0 = dim / 1) let K1 read the field's rows
  * out of a strided buffer (the received reply rows); foreign = 1 marks a table whose gradient is produced
  * elsewhere: K1 emits no sort key for its ids and dfm_embed_bwd / dfm_rows_bwd ignore it.  On the sample-side
