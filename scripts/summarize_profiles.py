@@ -61,8 +61,6 @@ if os.path.exists(rep2):
         for r in rows[2:]:
             fh.write(",".join('"' + r[i].replace('"', "'")[:70] + '"' if w == "Kernel Name" else r[i].replace(",", "") for w, i in idx) + "\n")
     print(open(os.path.join(dst, f"{tag}_ncu_full_cin_tcgen05.csv")).read())
-    if os.path.exists(os.path.join(src, name)):
-        shutil.copy(os.path.join(src, name), os.path.join(dst, name))
 print(open(os.path.join(dst, f"{tag}_launches_summary.csv")).read()[:3000])
 print(open(os.path.join(dst, f"{tag}_ncu_full_kernels.csv")).read())
 
