@@ -306,6 +306,10 @@ class ShardedFeatureEmbedding(nn.Module):
         repl = set(self._repl_idx)
         self._table_idx = [i for i, k in enumerate(kinds) if k != _lib.DENSE and i not in repl]   # the SHARDED tables
         self._sparse_idx = self._table_idx                      # historical name
+        if not self._table_idx:
+            raise NotImplementedError(
+                f"no table has more than replicate_below={self.replicate_below} rows: nothing to shard -- use the plain "
+                f"FeatureEmbedding on every rank and average all gradients (DenseGradReducer)")
         self._all_tables = [i for i, k in enumerate(kinds) if k != _lib.DENSE]
         self._all_lens = [lens[i] for i in self._all_tables]
         self._all_S = sum(self._all_lens)                                                          # id slots of the plan

@@ -162,6 +162,27 @@ def test_sharded_module_bookkeeping_cpu():
             assert torch.equal(got_owner[sent], owner[sent])
 
 
+def test_peer_exchange_layout_and_capacity_logic():
+    """Host arithmetic of PeerExchange (no GPU): buffer regions, and the collective-safe capacity decision."""
+    from deepfm_b200.sharded import PeerExchange
+    px = PeerExchange.__new__(PeerExchange)                 # the constructor needs symmetric memory; the logic does not
+    px.world, px.rank, px.row_floats, px.cap = 3, 1, 68, 1000
+    px.peer_base = [1 << 30, 2 << 30, 3 << 30]
+    stride = 1000 * 68 * 4
+    assert px.region(0, 0) == (2 << 30) and px.region(0, 1) == (2 << 30) + stride
+    assert px.region(1, 0, rank=2) == (3 << 30) + 2 * stride and px.region(1, 1, rank=0) == (1 << 30) + 3 * stride
+    ok = [[100, 200, 300], [50, 60, 70], [400, 100, 100]]   # matrix[s][r]: rows s sends to r
+    assert px.fits(ok)                                       # max sent 600 (+ the zero row), max received 550
+    assert not px.fits([[500, 499, 1], [0, 0, 0], [0, 0, 0]])   # 1000 sent + the zero row > capacity
+    assert not px.fits([[400, 0, 0], [400, 0, 0], [400, 0, 0]])  # rank 0 would receive 1200 rows
+
+
+def test_sharding_needs_a_table_to_shard():
+    from deepfm_b200.sharded import ShardedFeatureEmbedding
+    with pytest.raises(NotImplementedError, match="nothing to shard"):
+        ShardedFeatureEmbedding(_schema(8), 8, 2, 0, replicate_below=10 ** 6)
+
+
 def _ckpt_worker(rank, world, port, out):
     import torch.distributed as dist
     os.environ.update(MASTER_ADDR="127.0.0.1", MASTER_PORT=str(port))
