@@ -18,6 +18,7 @@ OK, ERR_INVALID, ERR_UNSUPPORTED, ERR_CUDA, ERR_WORKSPACE = 0, -1, -2, -3, -4
 SPARSE, SEQUENCE, DENSE = 0, 1, 2
 SUM, MEAN, MAX = 0, 1, 2
 GRAD_DENSE, GRAD_ROWSPARSE, GRAD_SKIP_TABLES = 0, 1, 2
+GRAD_PRESORTED = 0x100
 KIND = {"sparse": SPARSE, "sequence": SEQUENCE, "dense": DENSE}
 COMBINER = {"sum": SUM, "mean": MEAN, "max": MAX}
 
@@ -39,10 +40,13 @@ SIGNATURES = {
     "dfm_embed_bwd": (C.c_int, [_vp, _i64, _pp, _pp, _vp, _vp, _vp, _vp, _vp, _vp, _vp, _vp, _vp,
                                 _f32, _vp, C.c_int, _pp, _vp, _vp, _vp, _vp, _vp, _vp, _sz, _vp]),
     "dfm_emit_keys": (C.c_int, [_vp, _i64, _pp, _vp, _vp]),
+    "dfm_sort_keys_workspace_bytes": (_sz, [_vp, _i64]),
     "dfm_sort_keys": (C.c_int, [_vp, _i64, _vp, _vp, _vp, _vp, _sz, _vp]),
     "dfm_fm_fwd": (C.c_int, [_vp, _i64, C.c_int, C.c_int, _vp, _vp]),
     "dfm_fm_bwd": (C.c_int, [_vp, _vp, _i64, C.c_int, C.c_int, _vp, _vp]),
     "dfm_sumsq": (C.c_int, [C.c_int, _pp, _pi64, _f32, _vp, _vp, _vp]),
+    "dfm_sumsq_acc": (C.c_int, [C.c_int, _pp, _pi64, _vp, _vp, _vp]),
+    "dfm_l2_combine": (C.c_int, [_vp, _vp, _f32, _vp, _vp]),
     "dfm_axpy": (C.c_int, [_vp, _i64, _f32, _vp, _vp, C.c_int, _vp]),
     "dfm_cin_sizes": (C.c_int, [C.c_int, C.c_int, C.c_int, _pi32, C.c_int, _i64, _pi64]),
     "dfm_cin_fwd": (C.c_int, [_vp, _i64, C.c_int, C.c_int, C.c_int, _pi32, C.c_int, _pp, _pp, C.c_int,
@@ -50,17 +54,18 @@ SIGNATURES = {
     "dfm_cin_bwd": (C.c_int, [_vp, _vp, _i64, C.c_int, C.c_int, C.c_int, _pi32, C.c_int, _pp, C.c_int,
                               _vp, _vp, _pp, _pp, _vp, _sz, _vp]),
     "dfm_shard_route_workspace_bytes": (_sz, [_vp, _i64]),
-    "dfm_shard_route": (C.c_int, [_vp, C.c_int, _pi64, _i64, _pp, _vp, _vp, _vp, _vp, _vp, _sz, _vp]),
+    "dfm_shard_route": (C.c_int, [_vp, C.c_int, _pi64, _i64, _pp, _vp, _vp, _vp, _vp, _vp, _vp, _sz, _vp]),
     "dfm_shard_gather": (C.c_int, [_vp, C.c_int, C.c_int, _pi64, _i64, _vp, _pp, _vp, _vp, _vp]),
-    "dfm_shard_pack_grad": (C.c_int, [_vp, _i64, _vp, _vp, _vp, _vp, _vp, _vp, _vp, _vp, _vp, _vp]),
+    "dfm_shard_pack_grad": (C.c_int, [_vp, _i64, _vp, _vp, _vp, _vp, _vp, _vp, _vp, _vp, _vp, _f32, _vp]),
     "dfm_shard_gather_p2p": (C.c_int, [_vp, C.c_int, C.c_int, _pi64, _i64, _vp, _pp, C.c_int, _pi64, _pp, _vp, _vp]),
-    "dfm_shard_pack_grad_p2p": (C.c_int, [_vp, _i64, _vp, _vp, _vp, _vp, _vp, _vp, _vp, _vp, C.c_int, _pi64, _pp, _vp, _vp]),
+    "dfm_shard_pack_grad_p2p": (C.c_int, [_vp, _i64, _vp, _vp, _vp, _vp, _vp, _vp, _vp, _vp, C.c_int, _pi64, _pp, _vp, _f32, _vp]),
     "dfm_plan_set_table_stride": (C.c_int, [_vp, C.c_int, C.c_int]),
     "dfm_plan_set_field_source": (C.c_int, [_vp, C.c_int, C.c_int, C.c_int, C.c_int]),
     "dfm_rows_bwd_workspace_bytes": (_sz, [_vp, _i64]),
     "dfm_rows_bwd": (C.c_int, [_vp, _i64, _pp, _vp, _vp, _f32, _vp, C.c_int, _pp, _vp, _vp, _vp, _vp, _vp,
                                _vp, _sz, _vp]),
-    "dfm_adam_rows": (C.c_int, [_vp, _i64, _vp, _vp, _vp, _pp, _pp, _pp, _f32, _f32, _f32, _f32, _i64, _vp, _vp]),
+    "dfm_adam_rows": (C.c_int, [_vp, _i64, _vp, _vp, _vp, _pp, _pp, _pp, _f32, _f32, _f32, _f32, _i64, _vp, _vp, _vp, _sz, _vp]),
+    "dfm_adam_rows_workspace_bytes": (_sz, []),
     "dfm_rows_sumsq_workspace_bytes": (_sz, []),
     "dfm_rows_sumsq": (C.c_int, [_vp, _i64, _vp, _vp, _vp, _vp, _vp, _sz, _vp]),
     "dfm_attn_workspace_bytes": (_sz, [_i64, C.c_int, C.c_int, C.c_int, C.c_int]),

@@ -14,6 +14,8 @@
 //             memory, then a fixed-order reduction over slices (+ 2*l2*p)
 // No float atomics anywhere: every output element has exactly one writer and a fixed summation
 // order, so the gradients are bit-reproducible run to run.
+#include <stdlib.h>
+
 #include <cub/device/device_radix_sort.cuh>
 
 #include "plan.cuh"
@@ -708,6 +710,259 @@ stitch_long_kernel(const __grid_constant__ DevPlan P, const __grid_constant__ De
     }
 }
 
+// ---- seg2: warp-sequential segmented reduction (the fast path of the plain shapes) ---------------------------
+// Eligible plans (host check in embed_bwd_impl): every field has dim == fm_dim == D in {32, 64, 128}, id fields are
+// plain SPARSE or sum / mean bags (the Criteo shapes, and the owner side of the sharded path).
+// One WARP owns a span of `unit` consecutive sorted positions and walks it front to back; a lane owns VW = D / 32
+// floats of the row, so every 128-, 256- or 512-byte gradient row is one coalesced warp load and the running
+// segment sum lives in VW registers per lane.  Per tile of 32 positions each lane decodes ONE position (key, payload
+// -> row offset, g_fm[b], first-order gradient, bag scale) and the warp then consumes the 32 positions in order with
+// warp-uniform control flow: the decoded scalars travel by shuffle, NB positions' row loads are issued before the
+// first is consumed, segment heads come from one ballot.  The table row of a segment (for -(sum g_fm) w + 2 l2 w) is
+// requested when the segment starts and used when it ends.  No shared-memory staging, no block barrier in the loop,
+// ~18 warp instructions per position (the lane-group kernel above: ~100).  Segments that cross span boundaries use
+// the same head / tail carry records as segreduce_kernel, so stitch_kernel / stitch_long_kernel finish them
+// unchanged.  Summation order inside a segment is the sorted (= batch) order: deterministic.
+template <int VW> struct LaneVec;
+template <> struct LaneVec<1> { using T = float; };
+template <> struct LaneVec<2> { using T = float2; };
+template <> struct LaneVec<4> { using T = float4; };
+
+template <int VW>
+__device__ __forceinline__ void lv_load_stream(float (&r)[VW], const float* p) {
+    using T = typename LaneVec<VW>::T;
+    const T t = __ldcs(reinterpret_cast<const T*>(p));
+    const float* q = reinterpret_cast<const float*>(&t);
+#pragma unroll
+    for (int v = 0; v < VW; ++v) r[v] = q[v];
+}
+template <int VW>
+__device__ __forceinline__ void lv_load(float (&r)[VW], const float* p) {
+    using T = typename LaneVec<VW>::T;
+    const T t = __ldg(reinterpret_cast<const T*>(p));
+    const float* q = reinterpret_cast<const float*>(&t);
+#pragma unroll
+    for (int v = 0; v < VW; ++v) r[v] = q[v];
+}
+template <int VW>
+__device__ __forceinline__ void lv_store(float* p, const float (&r)[VW]) {
+    using T = typename LaneVec<VW>::T;
+    T t;
+    float* q = reinterpret_cast<float*>(&t);
+#pragma unroll
+    for (int v = 0; v < VW; ++v) q[v] = r[v];
+    *reinterpret_cast<T*>(p) = t;
+}
+
+template <int VW>
+struct Seg2State {
+    uint32_t cur;          // key of the running segment
+    int seg_start;         // sorted position of its first member
+    int f;                 // its field
+    bool lead;             // it started before this span: its sum goes to the head carry, not to a row
+    float acc[VW], w[VW];  // running sum (this lane's floats); table row of the segment (requested at its head)
+    float a1, gs, w1;
+};
+
+template <int VW>
+__device__ __forceinline__ void seg2_close(const DevPlan& P, const DevGrads& GR, const BwdArgs& a, const FieldB* t_field,
+                                           float coef, bool need_w, int lane, long long unit_idx, const Seg2State<VW>& st) {
+    const int tdim = P.max_tdim;
+    if (st.lead) {         // partial sum of a segment that started in an earlier span
+        lv_store<VW>(a.head2 + (size_t)unit_idx * tdim + lane * VW, st.acc);
+        if (lane == 0) { a.head1[unit_idx] = st.a1; a.headg[unit_idx] = st.gs; }
+        return;
+    }
+    const FieldB& fb = t_field[st.f];
+    const size_t row = (size_t)(st.cur - fb.row_base);
+    float out[VW];
+    const float cw = coef - st.gs;
+#pragma unroll
+    for (int v = 0; v < VW; ++v) out[v] = need_w ? fmaf(cw, st.w[v], st.acc[v]) : st.acc[v];
+    float* dst = a.mode == DFM_GRAD_DENSE ? GR.g[st.f].gw2 + row * tdim : a.row_grad2 + (size_t)st.seg_start * tdim;
+    lv_store<VW>(dst + lane * VW, out);
+    if (lane == 0) {
+        const float o1 = coef != 0.f ? fmaf(coef, st.w1, st.a1) : st.a1;
+        if (a.mode == DFM_GRAD_DENSE) GR.g[st.f].gw1[row] = o1;
+        else a.row_grad1[st.seg_start] = o1;
+    }
+}
+
+template <int VW, bool HAS_FM, bool HAS_FIELD, bool HAS_BAG, bool DIRECT>
+__global__ void __launch_bounds__(256, 4)
+seg2_kernel(const __grid_constant__ DevPlan P, const __grid_constant__ DevGrads GR,
+            const __grid_constant__ BwdArgs a, long long unit) {
+    __shared__ FieldB t_field[MAX_FIELDS];
+    __shared__ unsigned short s_slotf[MAX_SLOTS];
+    __shared__ int s_cnt[2];
+    stage_fields(P, t_field);
+    for (int s = threadIdx.x; s < P.S; s += blockDim.x) s_slotf[s] = P.slot_field[s];
+    if (threadIdx.x < 2) s_cnt[threadIdx.x] = 0;
+    __syncthreads();
+    // positions whose row loads are in flight together: ~24 floats of load registers per lane
+    constexpr int STREAMS = 1 + ((HAS_FM && !DIRECT) ? 1 : 0) + (HAS_FIELD ? 1 : 0) + (HAS_BAG ? 1 : 0);
+    constexpr int NBQ = 24 / (VW * STREAMS);
+    constexpr int NB = NBQ >= 8 ? 8 : NBQ >= 4 ? 4 : 2;
+    const int lane = threadIdx.x & 31;
+    const long long unit_idx = (long long)blockIdx.x * (blockDim.x >> 5) + (threadIdx.x >> 5);
+    const long long p_lo = unit_idx * unit;
+    const long long p_hi = (p_lo + unit < a.N) ? p_lo + unit : a.N;
+    const uint32_t PAD = P.pad_key;
+    const int bits = a.slot_bits;
+    const uint32_t smask = (1u << bits) - 1u;
+    const float coef = a.l2x2 * (a.l2_gscale ? __ldg(a.l2_gscale) : 1.f);
+    const bool fm_rt = HAS_FM && !DIRECT && a.g_fm != nullptr;   // bag variants are compiled with HAS_FM and decide here
+    const bool fm_on = DIRECT || fm_rt;
+    const bool need_w = fm_on || coef != 0.f;
+    const int tdim = P.max_tdim, D = P.D, T = P.T;
+    int n_valid = 0, n_heads = 0;
+
+    if (p_lo < a.N) {
+        Seg2State<VW> st;
+        st.cur = PAD; st.seg_start = (int)p_lo; st.f = 0; st.lead = false; st.a1 = 0.f; st.gs = 0.f; st.w1 = 0.f;
+#pragma unroll
+        for (int v = 0; v < VW; ++v) { st.acc[v] = 0.f; st.w[v] = 0.f; }
+        const uint32_t key0 = __ldg(a.skeys + p_lo);
+        if (p_lo > 0 && key0 != PAD && __ldg(a.skeys + p_lo - 1) == key0) {     // the span opens inside a segment
+            st.cur = key0; st.lead = true;
+        }
+        bool ended = false;
+        for (long long p = p_lo; p < p_hi && !ended; p += 32) {
+            // ---- decode: one position per lane
+            const long long q = p + lane;
+            const bool valid = q < p_hi;
+            const uint32_t key = valid ? __ldg(a.skeys + q) : PAD;
+            const uint32_t pay = valid ? __ldg(a.spay + q) : 0u;
+            unsigned goff = 0, bofs = 0;     // float offsets of the position's gradient row / its sample's fm_sum row
+            int fl = 0, bag = 0;
+            float m = 0.f, o = 0.f, c = 1.f;
+            if (key != PAD) {
+                if (DIRECT) {
+                    fl = field_of_key(t_field, P.n_fields, key);
+                    goff = pay * (unsigned)a.row_stride;
+                    o = __ldg(a.g_flat + goff + tdim);          // packed first-order gradient
+                    m = __ldg(a.g_flat + goff + tdim + 1);      // packed g_fm (for -(sum g_fm) w)
+                } else {
+                    const uint32_t b = pay >> bits;
+                    fl = s_slotf[pay & smask];
+                    const FieldB& fb = t_field[fl];
+                    goff = b * (unsigned)T + (unsigned)fb.flat_off;
+                    bofs = b * (unsigned)D;
+                    if (HAS_FM && a.g_fm) m = __ldg(a.g_fm + b);
+                    if (a.g_first) o = __ldg(a.g_first + b);
+                    if (HAS_BAG && (fb.flags & 0xf) == DFM_SEQUENCE) {
+                        bag = 1;
+                        if (((fb.flags >> 4) & 0xf) == DFM_MEAN) c = __uint_as_float(__ldg(a.aux + (size_t)b * P.A + fb.aux_off));
+                        o *= c;
+                    }
+                }
+            }
+            const uint32_t prevk = __shfl_up_sync(0xffffffffu, key, 1);
+            const unsigned headmask = __ballot_sync(0xffffffffu, key != (lane == 0 ? st.cur : prevk));
+            const unsigned padmask = __ballot_sync(0xffffffffu, key == PAD);
+            const int n_live = padmask ? __ffs(padmask) - 1 : 32;       // PAD keys sort last: everything after is PAD
+            if (n_live < 32) ended = true;
+            // ---- consume the tile in sorted order, NB positions per batch
+            for (int r0 = 0; r0 < n_live; r0 += NB) {
+                float gA[NB][VW], gB[HAS_FIELD ? NB : 1][VW], sv[HAS_FM ? NB : 1][VW], eB[HAS_BAG ? NB : 1][VW];
+#pragma unroll
+                for (int i = 0; i < NB; ++i) {
+                    const int r = (r0 + i) & 31;                       // positions >= n_live are loaded (valid memory) but not consumed
+                    const unsigned go = __shfl_sync(0xffffffffu, goff, r);
+                    lv_load_stream<VW>(gA[i], a.g_flat + go + lane * VW);
+                    if (HAS_FIELD) lv_load_stream<VW>(gB[i], a.g_field + go + lane * VW);
+                    if (HAS_FM && !DIRECT) {
+                        const unsigned bo = __shfl_sync(0xffffffffu, bofs, r);
+                        if (fm_rt) lv_load<VW>(sv[i], a.fm_sum + bo + lane * VW);
+                        else {
+#pragma unroll
+                            for (int v = 0; v < VW; ++v) sv[i][v] = 0.f;
+                        }
+                    }
+                    if (HAS_BAG) {                                      // pooled embedding of the bag (aliased layout: same offset)
+                        const int bg = __shfl_sync(0xffffffffu, bag, r);
+                        if (bg && fm_rt) lv_load<VW>(eB[i], a.fe + go + lane * VW);
+                        else {
+#pragma unroll
+                            for (int v = 0; v < VW; ++v) eB[i][v] = 0.f;
+                        }
+                    }
+                }
+#pragma unroll
+                for (int i = 0; i < NB; ++i) {
+                    const int r = r0 + i;
+                    if (r >= n_live) break;
+                    if ((headmask >> r) & 1u) {
+                        if (st.cur != PAD) seg2_close<VW>(P, GR, a, t_field, coef, need_w, lane, unit_idx, st);
+                        st.cur = __shfl_sync(0xffffffffu, key, r);
+                        st.f = __shfl_sync(0xffffffffu, fl, r);
+                        st.seg_start = (int)(p + r); st.lead = false; st.a1 = 0.f; st.gs = 0.f;
+#pragma unroll
+                        for (int v = 0; v < VW; ++v) st.acc[v] = 0.f;
+                        ++n_heads;
+                        if (need_w) {                                   // requested now, used when the segment ends
+                            const FieldB& fb = t_field[st.f];
+                            const size_t row = (size_t)(st.cur - fb.row_base);
+                            lv_load<VW>(st.w, fb.w2 + row * tdim + lane * VW);
+                            if (coef != 0.f) st.w1 = __ldg(fb.w1 + row);
+                        }
+                    }
+                    const float mr = (HAS_FM || DIRECT) ? __shfl_sync(0xffffffffu, m, r) : 0.f;
+                    const float orr = __shfl_sync(0xffffffffu, o, r);
+                    float cr = 1.f;
+                    int bg = 0;
+                    if (HAS_BAG) { cr = __shfl_sync(0xffffffffu, c, r); bg = __shfl_sync(0xffffffffu, bag, r); }
+#pragma unroll
+                    for (int v = 0; v < VW; ++v) {
+                        float t = gA[i][v];
+                        if (HAS_FIELD) t += gB[i][v];
+                        if (HAS_FM && !DIRECT) t = fmaf(mr, HAS_BAG ? sv[i][v] - eB[i][v] : sv[i][v], t);
+                        if (HAS_BAG) t *= cr;
+                        st.acc[v] += t;
+                    }
+                    if (!HAS_BAG || !bg) st.gs += mr;                   // bag members carry their e term themselves
+                    st.a1 += orr;
+                    ++n_valid;
+                }
+            }
+        }
+        // ---- the span's last segment: finished here, or handed to the stitch pass
+        if (st.cur != PAD) {
+            const bool continues = !ended && p_hi < a.N && __ldg(a.skeys + p_hi) == st.cur;
+            if (st.lead || !continues) {
+                seg2_close<VW>(P, GR, a, t_field, coef, need_w, lane, unit_idx, st);
+            } else {
+                lv_store<VW>(a.tail2 + (size_t)unit_idx * tdim + lane * VW, st.acc);
+                if (lane == 0) {
+                    a.tail1[unit_idx] = st.a1; a.tailg[unit_idx] = st.gs;
+                    a.tail_start[unit_idx] = st.seg_start; a.tail_field[unit_idx] = st.f;
+                    a.open_list[atomicAdd(a.open_count, 1u)] = (unsigned)unit_idx;
+                }
+            }
+        }
+    }
+    // counters: one pair of integer atomics per block (order-independent, so still deterministic)
+    if (lane == 0 && (n_valid | n_heads)) { atomicAdd(&s_cnt[0], n_valid); atomicAdd(&s_cnt[1], n_heads); }
+    __syncthreads();
+    if (threadIdx.x < 2 && s_cnt[threadIdx.x])
+        atomicAdd(a.counters + threadIdx.x, (unsigned long long)s_cnt[threadIdx.x]);
+}
+
+template <int VW>
+static void launch_seg2(bool direct, bool has_fm, bool has_field, bool has_bag, unsigned blocks, cudaStream_t st,
+                        const DevPlan& P, const DevGrads& GR, const BwdArgs& a, long long unit) {
+    if (direct) { seg2_kernel<VW, false, false, false, true><<<blocks, 256, 0, st>>>(P, GR, a, unit); return; }
+    if (has_bag) {
+        if (has_field) seg2_kernel<VW, true, true, true, false><<<blocks, 256, 0, st>>>(P, GR, a, unit);
+        else seg2_kernel<VW, true, false, true, false><<<blocks, 256, 0, st>>>(P, GR, a, unit);
+        return;
+    }
+    if (has_fm && has_field) seg2_kernel<VW, true, true, false, false><<<blocks, 256, 0, st>>>(P, GR, a, unit);
+    else if (has_fm) seg2_kernel<VW, true, false, false, false><<<blocks, 256, 0, st>>>(P, GR, a, unit);
+    else if (has_field) seg2_kernel<VW, false, true, false, false><<<blocks, 256, 0, st>>>(P, GR, a, unit);
+    else seg2_kernel<VW, false, false, false, false><<<blocks, 256, 0, st>>>(P, GR, a, unit);
+}
+
 // ---- DENSE-field Linear grads and projection grads -------------------------------------
 struct PgField {
     int f, nvals, part_off;   // part_off: offset (floats) of this field inside one slice's partials
@@ -981,6 +1236,13 @@ size_t dfm_embed_bwd_workspace_bytes(const dfm_plan* plan, int64_t batch) {
 static int sort_keys_impl(const dfm_plan* plan, int64_t n, int S, const uint32_t* keys, uint32_t* sorted_keys,
                           uint32_t* sorted_payload, void* workspace, size_t workspace_bytes, void* stream);
 
+size_t dfm_sort_keys_workspace_bytes(const dfm_plan* plan, int64_t n) {
+    if (!plan || n <= 0) return 16;
+    size_t cub_bytes = 0;
+    if (sort_temp_bytes(n, plan->key_bits, &cub_bytes) != DFM_OK) return 0;
+    return align_up(cub_bytes, 256) + (size_t)n * 4;
+}
+
 int dfm_sort_keys(const dfm_plan* plan, int64_t n, const uint32_t* keys, uint32_t* sorted_keys,
                   uint32_t* sorted_payload, void* workspace, size_t workspace_bytes, void* stream) {
     DFM_REQUIRE(plan, DFM_ERR_INVALID, "dfm_sort_keys: null argument");
@@ -1019,6 +1281,8 @@ static int embed_bwd_impl(const dfm_plan* plan, int64_t batch, long long direct_
                   float* row_grad2, float* row_grad1, int64_t* n_valid, void* workspace,
                   size_t workspace_bytes, void* stream) {
     const bool direct = direct_rows >= 0;
+    const bool presorted = (mode & DFM_GRAD_PRESORTED) != 0;   // sorted_keys / sorted_payload already hold dfm_sort_keys' result
+    mode &= ~DFM_GRAD_PRESORTED;
     const bool skip_tables = mode == DFM_GRAD_SKIP_TABLES;
     DFM_REQUIRE(plan && params && grads && workspace && (inputs || direct), DFM_ERR_INVALID, "dfm_embed_bwd: null argument");
     DFM_REQUIRE(batch >= 0, DFM_ERR_INVALID, "dfm_embed_bwd: negative batch");
@@ -1026,7 +1290,7 @@ static int embed_bwd_impl(const dfm_plan* plan, int64_t batch, long long direct_
                 "dfm_embed_bwd: unknown mode %d", mode);
     DFM_REQUIRE(!g_fm || (fm_sum && field_emb), DFM_ERR_INVALID, "dfm_embed_bwd: g_fm needs fm_sum and field_emb");
     DFM_REQUIRE(batch == 0 || plan->A == 0 || aux, DFM_ERR_INVALID, "dfm_embed_bwd: aux required");
-    DFM_REQUIRE(batch == 0 || plan->S == 0 || skip_tables || (sorted_keys && sorted_payload && keys), DFM_ERR_INVALID, "dfm_embed_bwd: key buffers required");
+    DFM_REQUIRE(batch == 0 || plan->S == 0 || skip_tables || (sorted_keys && sorted_payload && (keys || presorted)), DFM_ERR_INVALID, "dfm_embed_bwd: key buffers required");
     DFM_REQUIRE(batch == 0 || mode != DFM_GRAD_ROWSPARSE || plan->S == 0 || (row_grad2 && row_grad1 && n_valid), DFM_ERR_INVALID,
                 "dfm_embed_bwd: row-sparse outputs required");
     DFM_REQUIRE(batch == 0 || plan->n_proj_expected == 0 || flat, DFM_ERR_INVALID, "dfm_embed_bwd: flat needed for projection grads");
@@ -1105,17 +1369,39 @@ static int embed_bwd_impl(const dfm_plan* plan, int64_t batch, long long direct_
     // 2. sort + segmented reduction of the id slots
     if (N > 0 && (batch > 0 || direct) && !skip_tables) {
         DFM_CHECK_CUDA(cudaMemsetAsync(a.counters, 0, 16, st));
-        rc = sort_keys_impl(plan, N, payS, keys, sorted_keys, sorted_payload, ws + L.off_cub,
-                            L.off_payload + (size_t)N * 4 - L.off_cub, stream);
-        if (rc) return rc;
+        if (!presorted) {
+            rc = sort_keys_impl(plan, N, payS, keys, sorted_keys, sorted_payload, ws + L.off_cub,
+                                L.off_payload + (size_t)N * 4 - L.off_cub, stream);
+            if (rc) return rc;
+        }
         DFM_CHECK_CUDA(cudaMemsetAsync(a.open_count, 0, 4, st));
         DFM_CHECK_CUDA(cudaMemsetAsync(a.long_count, 0, 4, st));
         const int gpb = 256 / G;
-        bool any_generic = false;
-        for (int f = 0; f < plan->n_fields; ++f)
+        bool any_generic = false, any_generic_proj = false, any_bag = false;
+        for (int f = 0; f < plan->n_fields; ++f) {
             any_generic = any_generic || plan->kind[f] == DFM_SEQUENCE || (plan->kind[f] == DFM_SPARSE && plan->dim[f] != plan->fm_dim);
+            // what seg2 cannot do: a field (any kind) whose dim differs from fm_dim, a max-pooled bag
+            any_generic_proj = any_generic_proj || plan->dim[f] != plan->fm_dim ||
+                               (plan->kind[f] == DFM_SEQUENCE && plan->combiner[f] == DFM_MAX && !plan->foreign[f]);
+            any_bag = any_bag || (plan->kind[f] == DFM_SEQUENCE && !plan->foreign[f]);
+        }
         long long unit;
-        {
+        // fast path (seg2): every field dim == fm_dim in {32, 64, 128}, id fields plain SPARSE or sum / mean bags
+        bool fast = V == 4 && !any_generic_proj && plan->max_tdim == plan->fm_dim &&
+                    (plan->fm_dim == 32 || plan->fm_dim == 64 || plan->fm_dim == 128) && (direct || (g_flat && plan->aliasable)) &&
+                    (direct ? N * (long long)a.row_stride : (long long)batch * plan->T) < 0x7fffffffLL &&
+                    getenv("DFM_K2_LEGACY") == nullptr;
+        if (fast) {
+            const int vw = plan->fm_dim / 32;
+            const long long warps_max = 32LL * sm_count();            // 4 blocks of 8 warps per SM
+            unit = ceil_div(ceil_div(N, warps_max), 32) * 32;
+            if (unit < 256) unit = 256;                               // carry records are sized for spans >= 256 (make_layout)
+            const unsigned blocks = (unsigned)ceil_div(ceil_div(N, unit), 8);
+            const bool hf = g_fm != nullptr, hg = g_field != nullptr;
+            if (vw == 1) launch_seg2<1>(direct, hf, hg, any_bag, blocks, st, *P, *GR, a, unit);
+            else if (vw == 2) launch_seg2<2>(direct, hf, hg, any_bag, blocks, st, *P, *GR, a, unit);
+            else launch_seg2<4>(direct, hf, hg, any_bag, blocks, st, *P, *GR, a, unit);
+        } else {
             unit = (long long)gpb * CHUNK;               // positions per segreduce block
             const unsigned blocks = (unsigned)ceil_div(N, unit);
             const size_t smem = seg_smem_bytes(gpb, plan->max_tdim, (int)unit, direct ? 0 : plan->S, plan->n_fields) + 16;

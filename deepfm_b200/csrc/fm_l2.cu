@@ -96,6 +96,28 @@ sumsq_final_kernel(const float* __restrict__ partial, int n, float scale, float*
     }
 }
 
+// double-precision variant of the final stage: acc[0] = sum of the per-block partials (no scale), the exact
+// starting point of the incrementally maintained ||W||^2 (dfm_adam_rows adds sum(new^2 - old^2) of touched rows)
+__global__ void __launch_bounds__(256)
+sumsq_final_f64_kernel(const float* __restrict__ partial, int n, double* __restrict__ acc) {
+    __shared__ double red[8];
+    double a = 0.0;
+    for (int i = threadIdx.x; i < n; i += blockDim.x) a += (double)partial[i];
+    for (int o = 16; o > 0; o >>= 1) a += __shfl_xor_sync(0xffffffffu, a, o);
+    if ((threadIdx.x & 31) == 0) red[threadIdx.x >> 5] = a;
+    __syncthreads();
+    if (threadIdx.x == 0) {
+        double s = 0.0;
+        for (int w = 0; w < 8; ++w) s += red[w];
+        acc[0] = s;
+    }
+}
+
+__global__ void l2_combine_kernel(const double* __restrict__ a, const double* __restrict__ b, float lam,
+                                  float* __restrict__ out) {
+    if (threadIdx.x == 0 && blockIdx.x == 0) out[0] = (float)((double)lam * (a[0] + (b ? b[0] : 0.0)));
+}
+
 __global__ void axpy_kernel(const float* __restrict__ p, long long n, float coef,
                             const float* __restrict__ scale_dev, float* __restrict__ g, int accumulate) {
     const float c = coef * (scale_dev ? __ldg(scale_dev) : 1.f);
@@ -128,10 +150,9 @@ int dfm_fm_bwd(const float* e, const float* g_out, int64_t batch, int n_fields, 
 }
 
 int dfm_sumsq(int n_tensors, const float* const* ptrs, const int64_t* numel, float scale, float* out,
-              float* workspace, void* stream) {
-    DFM_REQUIRE(n_tensors >= 0 && out && workspace && (n_tensors == 0 || (ptrs && numel)), DFM_ERR_INVALID,
-                "dfm_sumsq: null argument");
-    cudaStream_t st = static_cast<cudaStream_t>(stream);
+              float* workspace, void* stream);
+
+static int sumsq_partials(int n_tensors, const float* const* ptrs, const int64_t* numel, float* workspace, cudaStream_t st) {
     SumsqArgs a;
     int done = 0, launches = 0;
     while (done < n_tensors || launches == 0) {
@@ -143,7 +164,36 @@ int dfm_sumsq(int n_tensors, const float* const* ptrs, const int64_t* numel, flo
         sumsq_partial_kernel<<<SS_BLOCKS, 256, 0, st>>>(a, workspace, launches > 0);
         ++launches;
     }
+    return DFM_OK;
+}
+
+int dfm_sumsq_acc(int n_tensors, const float* const* ptrs, const int64_t* numel, double* acc,
+                  float* workspace, void* stream) {
+    DFM_REQUIRE(n_tensors >= 0 && acc && workspace && (n_tensors == 0 || (ptrs && numel)), DFM_ERR_INVALID,
+                "dfm_sumsq_acc: null argument");
+    cudaStream_t st = static_cast<cudaStream_t>(stream);
+    int rc = sumsq_partials(n_tensors, ptrs, numel, workspace, st);
+    if (rc) return rc;
+    sumsq_final_f64_kernel<<<1, 256, 0, st>>>(workspace, SS_BLOCKS, acc);
+    DFM_CHECK_LAUNCH();
+    return DFM_OK;
+}
+
+int dfm_sumsq(int n_tensors, const float* const* ptrs, const int64_t* numel, float scale, float* out,
+              float* workspace, void* stream) {
+    DFM_REQUIRE(n_tensors >= 0 && out && workspace && (n_tensors == 0 || (ptrs && numel)), DFM_ERR_INVALID,
+                "dfm_sumsq: null argument");
+    cudaStream_t st = static_cast<cudaStream_t>(stream);
+    int rc = sumsq_partials(n_tensors, ptrs, numel, workspace, st);
+    if (rc) return rc;
     sumsq_final_kernel<<<1, 256, 0, st>>>(workspace, SS_BLOCKS, scale, out);
+    DFM_CHECK_LAUNCH();
+    return DFM_OK;
+}
+
+int dfm_l2_combine(const double* acc_a, const double* acc_b, float lam, float* out, void* stream) {
+    DFM_REQUIRE(acc_a && out, DFM_ERR_INVALID, "dfm_l2_combine: null argument");
+    l2_combine_kernel<<<1, 32, 0, static_cast<cudaStream_t>(stream)>>>(acc_a, acc_b, lam, out);
     DFM_CHECK_LAUNCH();
     return DFM_OK;
 }

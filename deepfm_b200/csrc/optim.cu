@@ -46,8 +46,10 @@ __device__ __forceinline__ float adam_update(float g, float& m, float& v, float 
 template <int V>
 __global__ void __launch_bounds__(256)
 adam_rows_kernel(const __grid_constant__ AdamArgs a, long long N, const uint32_t* __restrict__ skeys,
-                 const float* __restrict__ rg2, const float* __restrict__ rg1, int G) {
+                 const float* __restrict__ rg2, const float* __restrict__ rg1, int G, double* __restrict__ ssq_partial) {
     __shared__ AdamField t[MAX_FIELDS];
+    __shared__ double s_red[8];
+    double dsq = 0.0;      // sum over this thread's elements of w_new^2 - w_old^2 (incremental ||W||^2)
     for (int i = threadIdx.x; i < a.n; i += blockDim.x) t[i] = a.f[i];
     __syncthreads();
     const int gpb = blockDim.x / G, gl = threadIdx.x / G, j = threadIdx.x - gl * G;
@@ -63,20 +65,51 @@ adam_rows_kernel(const __grid_constant__ AdamArgs a, long long N, const uint32_t
             VecF<V> g = vload<V>(rg2 + (size_t)p * a.tdim + j * V);
             VecF<V> w = vload<V>(fd.w2 + o), m = vload<V>(fd.m2 + o), v = vload<V>(fd.v2 + o);
 #pragma unroll
-            for (int q = 0; q < V; ++q) w.v[q] = adam_update(g.v[q] * clip, m.v[q], v.v[q], w.v[q], a);
+            for (int q = 0; q < V; ++q) {
+                const float wo = w.v[q];
+                w.v[q] = adam_update(g.v[q] * clip, m.v[q], v.v[q], wo, a);
+                if (ssq_partial) dsq += (double)w.v[q] * (double)w.v[q] - (double)wo * (double)wo;
+            }
             vstore<V>(fd.w2 + o, w); vstore<V>(fd.m2 + o, m); vstore<V>(fd.v2 + o, v);
         }
         if (j == 0) {
             float m = fd.m1[row], v = fd.v1[row];
-            fd.w1[row] = adam_update(__ldg(rg1 + p) * clip, m, v, fd.w1[row], a);
+            const float wo = fd.w1[row];
+            const float wn = adam_update(__ldg(rg1 + p) * clip, m, v, wo, a);
+            fd.w1[row] = wn;
             fd.m1[row] = m; fd.v1[row] = v;
+            if (ssq_partial) dsq += (double)wn * (double)wn - (double)wo * (double)wo;
+        }
+    }
+    if (ssq_partial) {      // per-block partial, fixed order inside the block; blocks are added in block order
+        for (int o = 16; o > 0; o >>= 1) dsq += __shfl_xor_sync(0xffffffffu, dsq, o);
+        if ((threadIdx.x & 31) == 0) s_red[threadIdx.x >> 5] = dsq;
+        __syncthreads();
+        if (threadIdx.x == 0) {
+            double s = 0.0;
+            for (int w = 0; w < 8; ++w) s += s_red[w];
+            ssq_partial[blockIdx.x] = s;
         }
     }
 }
 
+__global__ void ssq_apply_kernel(const double* __restrict__ partial, int n, double* __restrict__ acc) {
+    if (threadIdx.x == 0 && blockIdx.x == 0) {
+        double s = 0.0;
+        for (int i = 0; i < n; ++i) s += partial[i];
+        acc[0] += s;
+    }
+}
+
+struct RowDims {            // table fields in key order: only dim[f] floats of a row_grad2 row are defined
+    unsigned row_base[MAX_FIELDS];
+    int dim[MAX_FIELDS];
+    int n;
+};
+
 __global__ void __launch_bounds__(256)
 rows_sumsq_kernel(long long N, const uint32_t* __restrict__ skeys, unsigned pad, const float* __restrict__ rg2,
-                  const float* __restrict__ rg1, int tdim, float* __restrict__ partial) {
+                  const float* __restrict__ rg1, int tdim, float* __restrict__ partial, const __grid_constant__ RowDims rd) {
     __shared__ float red[8];
     float acc = 0.f;
     const long long per = (N + gridDim.x - 1) / gridDim.x;        // contiguous positions per block
@@ -85,7 +118,10 @@ rows_sumsq_kernel(long long N, const uint32_t* __restrict__ skeys, unsigned pad,
     for (long long p = lo + warp; p < hi; p += 8) {               // one warp per position, lanes over the row
         const uint32_t key = __ldg(skeys + p);
         if (key == pad || (p > 0 && __ldg(skeys + p - 1) == key)) continue;
-        for (int c = lane; c < tdim; c += 32) { const float g = __ldg(rg2 + (size_t)p * tdim + c); acc = fmaf(g, g, acc); }
+        int fi = 0;
+        for (int q = 1; q < rd.n; ++q) if (key >= rd.row_base[q]) fi = q;
+        const int dimf = rd.dim[fi];                              // K2 writes dim[f] floats of the row, the tail is undefined
+        for (int c = lane; c < dimf; c += 32) { const float g = __ldg(rg2 + (size_t)p * tdim + c); acc = fmaf(g, g, acc); }
         if (lane == 0) { const float g = __ldg(rg1 + p); acc = fmaf(g, g, acc); }
     }
     for (int o = 16; o > 0; o >>= 1) acc += __shfl_xor_sync(0xffffffffu, acc, o);
@@ -112,10 +148,15 @@ using namespace dfm;
 
 extern "C" {
 
+size_t dfm_adam_rows_workspace_bytes(void) { return (size_t)8 * 8 * 256 * sizeof(double); }   /* >= 8 * SMs blocks */
+
 int dfm_adam_rows(const dfm_plan* plan, int64_t n_sorted, const uint32_t* sorted_keys, const float* row_grad2,
                   const float* row_grad1, float* const* params, float* const* exp_avg, float* const* exp_avg_sq,
-                  float lr, float beta1, float beta2, float eps, int64_t step, const float* clip_scale, void* stream) {
+                  float lr, float beta1, float beta2, float eps, int64_t step, const float* clip_scale,
+                  double* ssq_acc, void* ssq_workspace, size_t ssq_workspace_bytes, void* stream) {
     DFM_REQUIRE(plan && params && exp_avg && exp_avg_sq && step >= 1, DFM_ERR_INVALID, "dfm_adam_rows: bad argument");
+    DFM_REQUIRE(!ssq_acc || (ssq_workspace && ssq_workspace_bytes >= dfm_adam_rows_workspace_bytes()), DFM_ERR_WORKSPACE,
+                "dfm_adam_rows: ssq_acc needs a workspace of dfm_adam_rows_workspace_bytes()");
     if (n_sorted <= 0 || plan->S == 0) return DFM_OK;
     DFM_REQUIRE(sorted_keys && row_grad2 && row_grad1, DFM_ERR_INVALID, "dfm_adam_rows: null tensor");
     AdamArgs* a = new AdamArgs;
@@ -143,9 +184,12 @@ int dfm_adam_rows(const dfm_plan* plan, int64_t n_sorted, const uint32_t* sorted
     const int G = next_pow2(lanes);
     long long blocks = ceil_div(n_sorted, 256 / G);
     if (blocks > 8LL * sm_count()) blocks = 8LL * sm_count();
+    if (blocks > 8 * 256) blocks = 8 * 256;                      // dfm_adam_rows_workspace_bytes() partial slots
     cudaStream_t st = static_cast<cudaStream_t>(stream);
-    if (V == 4) adam_rows_kernel<4><<<(unsigned)blocks, 256, 0, st>>>(*a, n_sorted, sorted_keys, row_grad2, row_grad1, G);
-    else adam_rows_kernel<1><<<(unsigned)blocks, 256, 0, st>>>(*a, n_sorted, sorted_keys, row_grad2, row_grad1, G);
+    double* part = ssq_acc ? static_cast<double*>(ssq_workspace) : nullptr;
+    if (V == 4) adam_rows_kernel<4><<<(unsigned)blocks, 256, 0, st>>>(*a, n_sorted, sorted_keys, row_grad2, row_grad1, G, part);
+    else adam_rows_kernel<1><<<(unsigned)blocks, 256, 0, st>>>(*a, n_sorted, sorted_keys, row_grad2, row_grad1, G, part);
+    if (ssq_acc) ssq_apply_kernel<<<1, 32, 0, st>>>(part, (int)blocks, ssq_acc);
     DFM_CHECK_LAUNCH();
     return DFM_OK;
 }
@@ -161,8 +205,14 @@ int dfm_rows_sumsq(const dfm_plan* plan, int64_t n_sorted, const uint32_t* sorte
     if (n_sorted > 0 && plan->S > 0) {
         DFM_REQUIRE(sorted_keys && row_grad2 && row_grad1, DFM_ERR_INVALID, "dfm_rows_sumsq: null tensor");
         blocks = (int)(ceil_div(n_sorted, 64) < 1024 ? ceil_div(n_sorted, 64) : 1024);
+        RowDims rd;
+        memset(&rd, 0, sizeof(rd));
+        for (int f = 0; f < plan->n_fields; ++f) {
+            if (plan->kind[f] == DFM_DENSE || plan->foreign[f]) continue;
+            rd.row_base[rd.n] = (unsigned)plan->row_base[f]; rd.dim[rd.n] = plan->dim[f]; ++rd.n;
+        }
         rows_sumsq_kernel<<<blocks, 256, 0, st>>>(n_sorted, sorted_keys, (unsigned)plan->total_rows, row_grad2, row_grad1,
-                                                  plan->max_tdim, partial);
+                                                  plan->max_tdim, partial, rd);
     }
     rows_sumsq_final_kernel<<<1, 32, 0, st>>>(partial, blocks, out);
     DFM_CHECK_LAUNCH();

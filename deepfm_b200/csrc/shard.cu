@@ -91,6 +91,7 @@ struct PackArgs {
     int S, T, F, D, dmax, A;
     const uint32_t* send_slots;   // optional: send position -> id slot index b * S + s (the inverse of pos)
     long long n_sent;
+    float grad_scale;             // multiplies every exchanged gradient row (1 / world: the global-mean-loss convention)
     unsigned short slot_tf[MAX_SLOTS];   // id slot -> index into ShardArgs::f
 };
 
@@ -121,6 +122,7 @@ shard_pack_kernel(const __grid_constant__ ShardArgs a, const __grid_constant__ P
         float scale = 1.f;
         if (sf.bag == 2) scale = __uint_as_float(__ldg(p.aux + (size_t)b * p.A + sf.aux_off));
         const float m = p.g_fm ? __ldg(p.g_fm + b) : 0.f;
+        const float gsc = p.grad_scale;
         float* dst = peer_row(pd, g_vec, q, p.dmax + 4);
         if (j < sf.dim / V) {
             VecF<V> g = vzero<V>();
@@ -142,15 +144,16 @@ shard_pack_kernel(const __grid_constant__ ShardArgs a, const __grid_constant__ P
                     for (int v = 0; v < V; ++v) g.v[v] = fmaf(m, sv.v[v], g.v[v]);
                 }
             }
-            if (sf.bag == 2) {
+            if (sf.bag == 2 || gsc != 1.f) {
+                const float sc = scale * gsc;
 #pragma unroll
-                for (int v = 0; v < V; ++v) g.v[v] *= scale;
+                for (int v = 0; v < V; ++v) g.v[v] *= sc;
             }
             vstore_stream<V>(dst + j * V, g);
         }
         if (j == 0)
             *reinterpret_cast<float4*>(dst + p.dmax) =
-                make_float4((p.g_first ? __ldg(p.g_first + b) : 0.f) * scale, sf.bag ? 0.f : m, 0.f, 0.f);
+                make_float4((p.g_first ? __ldg(p.g_first + b) : 0.f) * scale * gsc, sf.bag ? 0.f : m * gsc, 0.f, 0.f);
     }
 }
 
@@ -165,12 +168,14 @@ struct RouteField {
     int slot_base, max_len;
     int bag;                // SEQUENCE: padding entries (id 0) are not sent
     int rot;                // owner = (id + rot) mod W, rot = schema index of the field
+    long long vocab;        // ids outside [0, vocab) are clamped to the padding id 0 and flagged (reference: IndexError)
 };
 struct RouteArgs {
     RouteField f[MAX_FIELDS];            // table fields only
     unsigned short slot_tf[MAX_SLOTS];   // id slot -> index into f
     int S, world;
     long long B;
+    int* status;            // optional device word, set to 1 when an id is out of range
 };
 
 // owner of id slot i = b * S + s (sample-major source order), -1 if nothing is sent for it
@@ -180,6 +185,10 @@ __device__ __forceinline__ int route_owner(const RouteArgs& a, const RouteField*
     if (slot_tf[s] == 0xffff) { rf = nullptr; id = 0; return -1; }      // replicated table: looked up locally
     rf = t + slot_tf[s];
     id = __ldg(rf->ids + b * rf->max_len + (s - rf->slot_base));
+    if ((unsigned long long)id >= (unsigned long long)rf->vocab) {     // also catches id < 0
+        if (a.status) *a.status = 1;
+        id = 0;
+    }
     if (rf->bag && id == 0) return -1;
     return (int)((id + rf->rot) % a.world);
 }
@@ -388,7 +397,7 @@ static int shard_pack_impl(const dfm_plan* plan, int64_t batch, const int64_t* p
                            const float* g_field, const float* g_flat, const float* g_fm, const float* fm_sum,
                            const float* field_emb, const uint32_t* aux, float* g_vec, int n_peers,
                            const int64_t* peer_start, float* const* peer_rows, const uint32_t* send_slots, int64_t n_sent,
-                           void* stream) {
+                           float grad_scale, void* stream) {
     DFM_REQUIRE(plan && batch >= 0, DFM_ERR_INVALID, "dfm_shard_pack_grad: bad argument");
     if (batch == 0 || plan->S == 0) return DFM_OK;
     DFM_REQUIRE(positions && (g_vec || n_peers > 0) && (!g_fm || fm_sum), DFM_ERR_INVALID, "dfm_shard_pack_grad: null tensor");
@@ -411,7 +420,7 @@ static int shard_pack_impl(const dfm_plan* plan, int64_t batch, const int64_t* p
     p.aux = aux; p.A = plan->A;
     p.pos = reinterpret_cast<const long long*>(positions); p.B = batch; p.S = plan->S; p.T = plan->T;
     p.F = plan->n_fields; p.D = plan->fm_dim; p.dmax = plan->max_tdim;
-    p.send_slots = send_slots; p.n_sent = n_sent;
+    p.send_slots = send_slots; p.n_sent = n_sent; p.grad_scale = grad_scale;
     if (send_slots && n_sent <= 0) return DFM_OK;
     fill_slot_tf(plan, p.slot_tf);
     auto al16 = [](const void* q) { return (reinterpret_cast<uintptr_t>(q) & 15u) == 0; };
@@ -430,18 +439,19 @@ static int shard_pack_impl(const dfm_plan* plan, int64_t batch, const int64_t* p
 
 int dfm_shard_pack_grad(const dfm_plan* plan, int64_t batch, const int64_t* positions, const float* g_first,
                         const float* g_field, const float* g_flat, const float* g_fm, const float* fm_sum,
-                        const float* field_emb, const uint32_t* aux, float* g_vec, void* stream) {
+                        const float* field_emb, const uint32_t* aux, float* g_vec, float grad_scale, void* stream) {
     return shard_pack_impl(plan, batch, positions, g_first, g_field, g_flat, g_fm, fm_sum, field_emb, aux, g_vec, 0, nullptr,
-                           nullptr, nullptr, 0, stream);
+                           nullptr, nullptr, 0, grad_scale, stream);
 }
 
 int dfm_shard_pack_grad_p2p(const dfm_plan* plan, int64_t batch, const int64_t* positions, const float* g_first,
                             const float* g_field, const float* g_flat, const float* g_fm, const float* fm_sum,
                             const float* field_emb, const uint32_t* aux, int n_peers, const int64_t* peer_start,
-                            float* const* peer_rows, const uint32_t* send_slots, void* stream) {
+                            float* const* peer_rows, const uint32_t* send_slots, float grad_scale, void* stream) {
     DFM_REQUIRE(n_peers > 0, DFM_ERR_INVALID, "dfm_shard_pack_grad_p2p: no peers");
     return shard_pack_impl(plan, batch, positions, g_first, g_field, g_flat, g_fm, fm_sum, field_emb, aux, nullptr, n_peers,
-                           peer_start, peer_rows, send_slots, send_slots ? peer_start[n_peers] - peer_start[0] : 0, stream);
+                           peer_start, peer_rows, send_slots, send_slots ? peer_start[n_peers] - peer_start[0] : 0, grad_scale,
+                           stream);
 }
 
 size_t dfm_shard_route_workspace_bytes(const dfm_plan* plan, int64_t batch) {
@@ -452,7 +462,7 @@ size_t dfm_shard_route_workspace_bytes(const dfm_plan* plan, int64_t batch) {
 
 int dfm_shard_route(const dfm_plan* plan, int world, const int64_t* global_row_base, int64_t batch,
                     const void* const* inputs, uint32_t* send_keys, int64_t* positions, int64_t* counts,
-                    uint32_t* send_slots, void* workspace, size_t workspace_bytes, void* stream) {
+                    uint32_t* send_slots, int32_t* status, void* workspace, size_t workspace_bytes, void* stream) {
     DFM_REQUIRE(plan && global_row_base && inputs && counts && world > 0 && world <= RT_MAXW && batch >= 0, DFM_ERR_INVALID,
                 "dfm_shard_route: bad argument (world must be 1..%d)", RT_MAXW);
     cudaStream_t st = static_cast<cudaStream_t>(stream);
@@ -463,7 +473,7 @@ int dfm_shard_route(const dfm_plan* plan, int world, const int64_t* global_row_b
     RouteArgs* a = new RouteArgs;
     struct Gd { RouteArgs* p; ~Gd() { delete p; } } gd{a};
     memset(a, 0, sizeof(*a));
-    a->S = plan->S; a->world = world; a->B = batch;
+    a->S = plan->S; a->world = world; a->B = batch; a->status = status;
     int nt = 0;
     for (int f = 0; f < plan->n_fields; ++f) {
         if (!shard_field(plan, f, false)) continue;
@@ -474,6 +484,7 @@ int dfm_shard_route(const dfm_plan* plan, int world, const int64_t* global_row_b
         rf.slot_base = plan->slot_base[f]; rf.max_len = plan->max_len[f];
         rf.bag = plan->kind[f] == DFM_SEQUENCE ? 1 : 0;
         rf.rot = f % world;
+        rf.vocab = global_row_base[f + 1] - global_row_base[f];
     }
     fill_slot_tf(plan, a->slot_tf);
     const int nblk = (int)ceil_div(n, RT_TILE);

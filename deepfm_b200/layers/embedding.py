@@ -27,6 +27,7 @@ import torch.nn as nn
 
 from .. import _lib
 from ..schema import kind_of
+from ._status import IndexStatusMixin
 
 
 class RowSparseGrads:
@@ -84,11 +85,10 @@ class _EmbedFn(torch.autograd.Function):
         first = torch.empty((B, 1), device=dev, dtype=torch.float32)
         fm_out = torch.empty((B, 1), device=dev, dtype=torch.float32)
         fm_sum = torch.empty((B, D), device=dev, dtype=torch.float32) if need_bwd else None
-        keys = torch.empty((B * S,), device=dev, dtype=torch.int32) if (need_bwd and S) else None
+        prep = mod._take_prepared(inputs) if (need_bwd and S) else None     # keys sorted ahead of the step (prepare())
+        keys = torch.empty((B * S,), device=dev, dtype=torch.int32) if (need_bwd and S and prep is None) else None
         aux = torch.empty((B, A), device=dev, dtype=torch.int32) if A else None
-        status = mod._status if mod.check_indices else None
-        if status is not None:
-            status.zero_()
+        status = mod._status_word(dev)
         in_arr = _lib.ptr_array(inputs)
         par_arr = mod._param_ptrs(params)
         ev = mod._event_pair("fwd")
@@ -97,13 +97,13 @@ class _EmbedFn(torch.autograd.Function):
                                      _lib.ptr(aux), _lib.ptr(status), _lib.stream_ptr()), "dfm_embed_fwd")
         if ev is not None:
             ev[1].record()
-        if status is not None and int(status.item()) != 0:
-            raise IndexError("index out of range in FeatureEmbedding (an id is outside [0, vocabulary_size))")
+        if status is not None:
+            mod._post_status()
         ctx.mod = mod
         ctx.n_inputs = n_inputs
         ctx.set_materialize_grads(False)
-        ctx.l2 = None            # (lambda, upstream-grad tensor) set by the L2 penalty node
-        ctx.done = False
+        ctx.l2 = None            # (lambda, upstream-grad tensor) set by the L2 penalty node, consumed by backward
+        ctx.prep = prep
         if need_bwd:
             ctx.save_for_backward(field, flat, fm_sum, keys, aux, *inputs, *params)
             mod._live_ctx = weakref.ref(ctx)
@@ -112,6 +112,7 @@ class _EmbedFn(torch.autograd.Function):
     @staticmethod
     def backward(ctx, g_first, g_field, g_flat, g_fm):
         mod: FeatureEmbedding = ctx.mod
+        mod.raise_if_bad_index(block=False)   # lazy check of the forward's status word (the reference raises IndexError)
         lib = _lib.lib()
         saved = ctx.saved_tensors
         field, flat, fm_sum, keys, aux = saved[:5]
@@ -130,11 +131,20 @@ class _EmbedFn(torch.autograd.Function):
         lam, gscale = (0.0, None)
         if ctx.l2 is not None:
             lam, gscale = ctx.l2
-        ctx.done = True
+            ctx.l2 = None         # consumed: a second backward over a retained graph gets its own fold (or none)
         ws_bytes = lib.dfm_embed_bwd_workspace_bytes(mod._plan, B)
         ws = torch.empty((max(ws_bytes, 16),), device=dev, dtype=torch.uint8)
-        skeys = torch.empty((max(N, 1),), device=dev, dtype=torch.int32)
-        spay = torch.empty((max(N, 1),), device=dev, dtype=torch.int32)
+        prep = ctx.prep
+        flags = 0
+        if prep is not None:          # sorted by the input pipeline on its own stream: nothing to sort here
+            skeys, spay, ev_sorted = prep
+            torch.cuda.current_stream(dev).wait_event(ev_sorted)
+            skeys.record_stream(torch.cuda.current_stream(dev))
+            spay.record_stream(torch.cuda.current_stream(dev))
+            flags = _lib.GRAD_PRESORTED
+        else:
+            skeys = torch.empty((max(N, 1),), device=dev, dtype=torch.int32)
+            spay = torch.empty((max(N, 1),), device=dev, dtype=torch.int32)
         counts = torch.zeros((2,), device=dev, dtype=torch.int64)
         rg2 = rg1 = None
         if rowsparse:
@@ -145,7 +155,7 @@ class _EmbedFn(torch.autograd.Function):
             mod._plan, B, _lib.ptr_array(inputs), mod._param_ptrs(params),
             _lib.ptr(g_first), _lib.ptr(g_field), _lib.ptr(g_flat), _lib.ptr(g_fm),
             field.data_ptr(), flat.data_ptr(), _lib.ptr(fm_sum), _lib.ptr(keys), _lib.ptr(aux),
-            float(lam), _lib.ptr(gscale), _lib.GRAD_ROWSPARSE if rowsparse else _lib.GRAD_DENSE,
+            float(lam), _lib.ptr(gscale), (_lib.GRAD_ROWSPARSE if rowsparse else _lib.GRAD_DENSE) | flags,
             mod._param_ptrs(grads), skeys.data_ptr(), spay.data_ptr(), _lib.ptr(rg2), _lib.ptr(rg1),
             counts.data_ptr(), ws.data_ptr(), ws.numel(), _lib.stream_ptr()), "dfm_embed_bwd")
         if ev is not None:
@@ -158,7 +168,7 @@ class _EmbedFn(torch.autograd.Function):
         return (None, None, None) + (None,) * ctx.n_inputs + tuple(grads)
 
 
-class FeatureEmbedding(nn.Module):
+class FeatureEmbedding(IndexStatusMixin, nn.Module):
     """Three views from one fused pass: ``first_order (B,1)``, ``field_embeddings (B,F,D)``,
     ``flat_embeddings (B,T)``  (reference: embedding.py:14-126)."""
 
@@ -202,11 +212,11 @@ class FeatureEmbedding(nn.Module):
         # extras
         self.grad_mode = "dense"
         self.profile_events = None      # set to {} to collect (start, end) CUDA events per call
-        self.check_indices = False
+        self._init_status()             # out-of-range ids raise IndexError lazily (layers/_status.py)
+        self._live_anchor = None
         self.row_grads: Optional[RowSparseGrads] = None
         self.last_counts = None
         self._live_ctx = None
-        self._status = None
         self._plan = None
         self._plan_args = (kinds, dims, vocabs, lens, combs)
         self.num_fields = len(self.field_names)
@@ -316,14 +326,71 @@ class FeatureEmbedding(nn.Module):
                 raise ValueError(f"batch[{name!r}] must have shape (B,), got {tuple(x.shape)}")
         return x.contiguous()
 
+    # -- device-side input pipeline hook ------------------------------------
+    def prepare(self, batch: Dict[str, torch.Tensor], stream: Optional["torch.cuda.Stream"] = None) -> None:
+        """Sort a FUTURE batch's row keys now.  The backward's sort depends on the ids only, not on weights or
+        gradients, so the input pipeline runs it (dfm_emit_keys + dfm_sort_keys) on a side stream while the current
+        step computes; the forward of that batch then skips the key emission and its backward starts at the
+        segmented reduction (DFM_GRAD_PRESORTED).  Matching is by the id tensors' storage: pass the same tensors to
+        ``forward``.  Calling it is optional -- without it K1 emits the keys and K2 sorts them itself."""
+        if self._S == 0:
+            return
+        self._ensure_plan()
+        lib = _lib.lib()
+        inputs = [self._prepare_input(n, f, batch[n]) for f, n in enumerate(self.field_names)]
+        dev = inputs[0].device
+        B = inputs[0].shape[0]
+        N = B * self._S
+        if N == 0:
+            return
+        side = stream
+        if side is None:
+            side = getattr(self, "_prep_stream", None)
+            if side is None or side.device != dev:
+                side = self._prep_stream = torch.cuda.Stream(device=dev)
+        cur = torch.cuda.current_stream(dev)
+        side.wait_stream(cur)                      # the id tensors are ready on the caller's stream
+        with torch.cuda.stream(side):
+            keys = torch.empty((N,), device=dev, dtype=torch.int32)
+            skeys = torch.empty((N,), device=dev, dtype=torch.int32)
+            spay = torch.empty((N,), device=dev, dtype=torch.int32)
+            ws = torch.empty((max(lib.dfm_sort_keys_workspace_bytes(self._plan, N), 16),), device=dev, dtype=torch.uint8)
+            store = getattr(self, "profile_events", None)
+            t0 = t1 = None
+            if store is not None:
+                t0, t1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+                t0.record(side)
+            _lib.check(lib.dfm_emit_keys(self._plan, B, _lib.ptr_array(inputs), keys.data_ptr(), side.cuda_stream), "dfm_emit_keys")
+            _lib.check(lib.dfm_sort_keys(self._plan, N, keys.data_ptr(), skeys.data_ptr(), spay.data_ptr(), ws.data_ptr(),
+                                         ws.numel(), side.cuda_stream), "dfm_sort_keys")
+            if store is not None:
+                t1.record(side)
+                store.setdefault("sort", []).append((t0, t1))
+            ev = torch.cuda.Event()
+            ev.record(side)
+        for t in inputs:
+            t.record_stream(side)
+        sig = tuple(t.data_ptr() for t, k in zip(inputs, self._kinds) if k != _lib.DENSE) + (B,)
+        self._prepared = (sig, (skeys, spay, ev))
+
+    def _take_prepared(self, inputs):
+        pref = getattr(self, "_prepared", None)
+        if pref is None:
+            return None
+        sig = tuple(t.data_ptr() for t, k in zip(inputs, self._kinds) if k != _lib.DENSE) + (inputs[0].shape[0],)
+        if pref[0] != sig:
+            return None
+        self._prepared = None
+        return pref[1]
+
     def forward_fused(self, batch: Dict[str, torch.Tensor]):
         """(first_order, field_embeddings, flat, fm_value) -- the FM term comes for free."""
         self._ensure_plan()
+        if self._status_pending and self.check_indices:
+            self.raise_if_bad_index(block=True, keep=1)
         params = self._ordered_params()
         for p in params:
             _lib.require_cuda(p, "FeatureEmbedding parameter")
-        if self.check_indices and (self._status is None or self._status.device != params[0].device):
-            self._status = torch.zeros(1, dtype=torch.int32, device=params[0].device)
         inputs = [self._prepare_input(n, f, batch[n]) for f, n in enumerate(self.field_names)]
         B = inputs[0].shape[0]
         for n, x in zip(self.field_names, inputs):
@@ -331,6 +398,7 @@ class FeatureEmbedding(nn.Module):
                 raise ValueError(f"batch[{n!r}] has {x.shape[0]} rows, expected {B}")
         need_bwd = torch.is_grad_enabled() and any(p.requires_grad for p in params)
         first, field, flat, fm = _EmbedFn.apply(self, len(inputs), need_bwd, *inputs, *params)
+        self._live_anchor = weakref.ref(first) if need_bwd else None     # the L2 node hangs itself below this node
         field._dfm_fm = (fm, field._version)     # picked up by FMInteraction (same tensor object)
         return first, field, flat, fm
 

@@ -1,75 +1,122 @@
-"""The embedding L2 penalty ``lambda * sum_p ||p||^2`` (reference: base.py:78-83) as one node.
+"""The embedding L2 penalty ``lambda * sum_p ||p||^2`` (reference: base.py:78-83) as one autograd node.
 
-Value: one deterministic multi-tensor reduction (``dfm_sumsq``) instead of a Python loop of
-``norm().pow()``.  Gradient: if the penalty is added to a loss that also flows through the
-``FeatureEmbedding`` forward of the same step, the ``2*lambda*p`` term is folded into the
-embedding backward kernel K2 (no extra pass over the tables); in every other situation the
-node produces it itself with ``dfm_axpy``.
+Value.  The reference re-reads every parameter every step (a Python loop of ``norm().pow()``); at the Criteo shape that
+is an 8.6 GB pass for a scalar that only changes on the rows the optimizer touched (SURVEY hard part 2).  Here the
+id tables' share ``sum ||w||^2`` is kept in a device fp64 scalar (``TableNormCache``):
+  * computed once by the exact fixed-order reduction ``dfm_sumsq_acc`` (the audited slow path),
+  * reused for as long as the table tensors are the same storage at the same ``_version`` (nobody wrote to them),
+  * updated in place by ``RowSparseAdam.step`` -- ``dfm_adam_rows`` adds ``sum(w_new^2 - w_old^2)`` of the rows it
+    touches -- so a training loop never pays the dense pass again;
+  * any other writer (a dense torch optimizer, ``load_state_dict`` ...) bumps ``_version`` and the next call falls
+    back to the exact reduction.
+The small parameters (DENSE-field Linears, projections) are reduced every call (a few KB).
 
-The value is an HBM-bound pass over every table (1.35 ms for the 8.6 GB of the Criteo shape) that nothing in the
-step depends on except the final scalar add, so ``prefetch_l2`` lets the model start it on a side stream at the top
-of ``forward`` (once a previous step has shown that the penalty is really used), where it overlaps the tensor-bound
-DNN; ``l2_penalty`` then only waits for the event.  The prefetched value is used only if the parameters are the very
-same tensors at the very same versions.
+Gradient.  If the penalty is added to a loss that also flows through the ``FeatureEmbedding`` forward of the same
+step, the ``2*lambda*p`` term is folded into the embedding backward kernel K2 (no extra pass over the tables).  The
+node takes the embedding's ``first_order`` output as an (otherwise unused) input, so the autograd graph itself
+guarantees that the embedding's backward runs after this node in every backward pass that reaches it -- no engine
+callbacks, no private API.  In every other situation the node produces ``2*lambda*p`` itself with ``dfm_axpy``.
 """
 
 from __future__ import annotations
+
+from typing import List, Optional
 
 import torch
 
 from .. import _lib
 
 
-def _launch_sumsq(params, lam: float):
+class TableNormCache:
+    """Device fp64 ``sum ||w||^2`` over a fixed list of table tensors, valid for one (storage, version) key."""
+
+    def __init__(self) -> None:
+        self.key = None
+        self.acc: Optional[torch.Tensor] = None      # (1,) float64 on the tables' device
+        self.refreshes = 0                           # number of exact (dense) reductions so far
+
+    @staticmethod
+    def key_of(tables) -> tuple:
+        return tuple((p.data_ptr(), p._version, p.numel()) for p in tables)
+
+    def valid_for(self, tables) -> bool:
+        return self.acc is not None and self.key == self.key_of(tables)
+
+    def refresh(self, tables) -> torch.Tensor:
+        """Exact reduction (one pass over the tables) on the current stream."""
+        lib = _lib.lib()
+        dev = tables[0].device
+        if self.acc is None or self.acc.device != dev:
+            self.acc = torch.zeros((1,), device=dev, dtype=torch.float64)
+        ws = torch.empty((4096,), device=dev, dtype=torch.float32)
+        _lib.check(lib.dfm_sumsq_acc(len(tables), _lib.ptr_array(tables), _lib.i64_array([p.numel() for p in tables]),
+                                     self.acc.data_ptr(), ws.data_ptr(), _lib.stream_ptr()), "dfm_sumsq_acc")
+        self.key = self.key_of(tables)
+        self.refreshes += 1
+        return self.acc
+
+    def rekey(self, tables) -> None:
+        """The caller updated ``acc`` itself while writing to the tables (RowSparseAdam): adopt the new versions."""
+        self.key = self.key_of(tables)
+
+    def invalidate(self) -> None:
+        self.key = None
+
+
+def _split_params(emb):
+    """(tables, small): the id tables (cached) and everything else (reduced every call)."""
+    params = [p for p in emb.parameters()]
+    table_ids = set()
+    ordered = getattr(emb, "_ordered_params", None)
+    if ordered is not None:      # exactly the tensors RowSparseAdam steps (sharded module: the sharded tables only)
+        op = ordered()
+        table_ids = {id(p) for p, is_table in zip(op, emb._param_is_table) if is_table}
+    tables = [p for p in params if id(p) in table_ids]
+    small = [p for p in params if id(p) not in table_ids]
+    return tables, small
+
+
+def table_norm_cache(emb) -> TableNormCache:
+    cache = getattr(emb, "_l2_cache", None)
+    if cache is None:
+        cache = emb._l2_cache = TableNormCache()
+    return cache
+
+
+def _l2_value(emb, params, lam: float) -> torch.Tensor:
     lib = _lib.lib()
     dev = params[0].device
+    tables, small = _split_params(emb)
     out = torch.empty((), device=dev, dtype=torch.float32)
-    ws = torch.empty((4096,), device=dev, dtype=torch.float32)
-    _lib.check(lib.dfm_sumsq(len(params), _lib.ptr_array(params), _lib.i64_array([p.numel() for p in params]),
-                             float(lam), out.data_ptr(), ws.data_ptr(), _lib.stream_ptr()), "dfm_sumsq")
-    return out, ws
-
-
-def _param_key(params, lam: float):
-    return (float(lam),) + tuple((p.data_ptr(), p._version) for p in params)
+    acc_t = None
+    if tables:
+        cache = table_norm_cache(emb)
+        acc_t = cache.acc if cache.valid_for(tables) else cache.refresh(tables)
+    acc_s = None
+    if small:
+        acc_s = torch.empty((1,), device=dev, dtype=torch.float64)
+        ws = torch.empty((4096,), device=dev, dtype=torch.float32)
+        _lib.check(lib.dfm_sumsq_acc(len(small), _lib.ptr_array(small), _lib.i64_array([p.numel() for p in small]),
+                                     acc_s.data_ptr(), ws.data_ptr(), _lib.stream_ptr()), "dfm_sumsq_acc")
+    a, b = (acc_t, acc_s) if acc_t is not None else (acc_s, None)
+    _lib.check(lib.dfm_l2_combine(a.data_ptr(), _lib.ptr(b), float(lam), out.data_ptr(), _lib.stream_ptr()), "dfm_l2_combine")
+    return out
 
 
 def prefetch_l2(emb, lam: float) -> None:
-    """Start ``lam * sum ||p||^2`` on the embedding's side stream (no-op until a step has used the penalty)."""
-    if lam <= 0 or not getattr(emb, "_l2_wanted", False):
-        emb._l2_prefetched = None
-        return
-    if getattr(emb, "_l2_prefetched", None) is not None:      # the previous prefetch was never consumed: stop speculating
-        emb._l2_prefetched, emb._l2_wanted = None, False
-        return
-    params = [p for p in emb.parameters()]
-    if not params or any((not p.is_cuda) or (not p.is_contiguous()) for p in params):
-        return
-    side = getattr(emb, "_l2_stream", None)
-    if side is None:
-        side = emb._l2_stream = torch.cuda.Stream(device=params[0].device)
-    side.wait_stream(torch.cuda.current_stream(params[0].device))     # the weights are final for this step
-    with torch.cuda.stream(side):
-        out, ws = _launch_sumsq(params, lam)
-        ev = torch.cuda.Event()
-        ev.record(side)
-    emb._l2_prefetched = (_param_key(params, lam), out, ws, ev)
+    """Kept for API compatibility: the table norm is cached / maintained incrementally now, nothing to prefetch."""
+    return None
 
 
 class _L2PenaltyFn(torch.autograd.Function):
     @staticmethod
-    def forward(ctx, emb, lam: float, *params):
-        emb._l2_wanted = True
-        pre, emb._l2_prefetched = getattr(emb, "_l2_prefetched", None), None
-        if pre is not None and pre[0] == _param_key(params, lam):
-            _, out, ws, ev = pre
-            cur = torch.cuda.current_stream(out.device)
-            cur.wait_event(ev)
-            out.record_stream(cur)
-            ws.record_stream(cur)
-        else:
-            out, _ = _launch_sumsq(params, lam)
+    def forward(ctx, emb, lam: float, anchor, *params):
+        out = _l2_value(emb, params, lam)
         ctx.emb, ctx.lam = emb, float(lam)
+        # `anchor` is an output of the embedding's autograd node of this step (or None): with it as an input, that
+        # node is an ancestor of this one and is guaranteed to run later in the same backward pass.
+        live = emb._live_ctx() if getattr(emb, "_live_ctx", None) is not None else None
+        ctx.live = live if anchor is not None else None
         ctx.save_for_backward(*params)
         return out
 
@@ -78,16 +125,10 @@ class _L2PenaltyFn(torch.autograd.Function):
         params = ctx.saved_tensors
         emb, lam = ctx.emb, ctx.lam
         g = g.contiguous().float()
-        live = emb._live_ctx() if emb._live_ctx is not None else None
-        if live is not None and not live.done and live.l2 is None:
-            live.l2 = (lam, g)       # K2 adds 2*lam*g*p to every gradient it writes
-
-            def verify():            # runs when the whole backward pass is over
-                if not live.done:    # the embedding node was not part of this graph after all
-                    live.l2 = None
-                    _apply_direct(emb, params, lam, g)
-            torch.autograd.Variable._execution_engine.queue_callback(verify)
-            return (None, None) + (None,) * len(params)
+        live = ctx.live
+        if live is not None and live.l2 is None:
+            live.l2 = (lam, g)       # K2 adds 2*lam*g*p to every gradient it writes; consumed (cleared) there
+            return (None, None, None) + (None,) * len(params)
         grads = []
         lib = _lib.lib()
         for p in params:
@@ -95,23 +136,18 @@ class _L2PenaltyFn(torch.autograd.Function):
             _lib.check(lib.dfm_axpy(p.data_ptr(), p.numel(), 2.0 * lam, g.data_ptr(), gp.data_ptr(), 0,
                                     _lib.stream_ptr()), "dfm_axpy")
             grads.append(gp)
-        return (None, None) + tuple(grads)
-
-
-def _apply_direct(emb, params, lam, g):
-    lib = _lib.lib()
-    with torch.no_grad():
-        for p in params:
-            if not p.requires_grad:
-                continue
-            if p.grad is None:
-                p.grad = torch.zeros_like(p)
-            _lib.check(lib.dfm_axpy(p.data_ptr(), p.numel(), 2.0 * lam, g.data_ptr(), p.grad.data_ptr(), 1,
-                                    _lib.stream_ptr()), "dfm_axpy")
+        return (None, None, None) + tuple(grads)
 
 
 def l2_penalty(emb, lam: float) -> torch.Tensor:
-    params = [p.contiguous() for p in emb.parameters()]
+    params: List[torch.Tensor] = [p.contiguous() for p in emb.parameters()]
     for p in params:
         _lib.require_cuda(p, "FeatureEmbedding parameter")
-    return _L2PenaltyFn.apply(emb, lam, *params)
+    anchor = None
+    ref = getattr(emb, "_live_anchor", None)
+    live = emb._live_ctx() if getattr(emb, "_live_ctx", None) is not None else None
+    if ref is not None and live is not None and torch.is_grad_enabled():
+        anchor = ref()
+        if anchor is not None and not anchor.requires_grad:
+            anchor = None
+    return _L2PenaltyFn.apply(emb, lam, anchor, *params)

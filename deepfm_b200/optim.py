@@ -32,6 +32,7 @@ class RowSparseAdam:
                 _lib.require_cuda(p, "embedding table")
         self.exp_avg = [torch.zeros_like(p) if t else None for p, t in zip(self._params, self._is_table)]
         self.exp_avg_sq = [torch.zeros_like(p) if t else None for p, t in zip(self._params, self._is_table)]
+        self._ssq_ws = None
 
     def _plan(self):
         if hasattr(self.emb, "_ensure_plans"):          # sharded: the owner-side plan
@@ -73,10 +74,25 @@ class RowSparseAdam:
                                "and backward() must have run)")
         self.step_count += 1
         lib = _lib.lib()
+        # incrementally maintained ||W||^2 (layers/l2.py): if the cached value describes the tables as they are now,
+        # the kernel adds sum(w_new^2 - w_old^2) of the rows it touches and the cache follows the new versions;
+        # otherwise the next get_l2_reg_loss() falls back to the exact reduction.
+        tables = self.table_parameters()
+        cache = getattr(self.emb, "_l2_cache", None)
+        live = cache is not None and cache.valid_for(tables)
+        acc = ws = None
+        if live:
+            acc = cache.acc
+            if self._ssq_ws is None or self._ssq_ws.device != acc.device:
+                self._ssq_ws = torch.empty((lib.dfm_adam_rows_workspace_bytes(),), device=acc.device, dtype=torch.uint8)
+            ws = self._ssq_ws
         _lib.check(lib.dfm_adam_rows(self._plan(), rg.sorted_keys.numel(), rg.sorted_keys.data_ptr(), rg.row_grad2.data_ptr(),
                                      rg.row_grad1.data_ptr(), self._slots(self._params), self._slots(self.exp_avg),
                                      self._slots(self.exp_avg_sq), self.lr, self.betas[0], self.betas[1], self.eps,
-                                     self.step_count, _lib.ptr(clip_scale), _lib.stream_ptr()), "dfm_adam_rows")
+                                     self.step_count, _lib.ptr(clip_scale), _lib.ptr(acc), _lib.ptr(ws),
+                                     ws.numel() if ws is not None else 0, _lib.stream_ptr()), "dfm_adam_rows")
         for p, t in zip(self._params, self._is_table):      # the kernel wrote through raw pointers
             if t:
-                torch._C._increment_version(p)
+                torch.autograd.graph.increment_version(p)
+        if live:
+            cache.rekey(tables)

@@ -41,6 +41,7 @@ import torch
 import torch.nn as nn
 
 from . import _lib
+from .layers._status import IndexStatusMixin
 from .layers.embedding import RowSparseGrads
 from .schema import kind_of
 
@@ -225,7 +226,7 @@ class _ShardedEmbedFn(torch.autograd.Function):
         ctx.counts = (send_counts, recv_counts)
         ctx.p2p = (px, matrix, parity, route.send_slots) if use_p2p else None
         ctx.set_materialize_grads(False)
-        ctx.l2, ctx.done = None, False
+        ctx.l2 = None
         if need_bwd:
             ctx.save_for_backward(field, flat, fm_sum, route.pos, lkeys, got, aux, *fin_inputs, *params)
             ctx.keys = keys
@@ -242,7 +243,8 @@ class _ShardedEmbedFn(torch.autograd.Function):
         params = saved[7 + n_f:]
         send_counts, recv_counts = ctx.counts
         lam, gscale = ctx.l2 if ctx.l2 is not None else (0.0, None)
-        ctx.done = True
+        ctx.l2 = None                     # consumed (see layers/l2.py)
+        mod.raise_if_bad_index(block=False)
         cont = lambda g: None if g is None else g.contiguous()
         g_rows, dense_grads = mod.pack_grads(fin_inputs, pos, got, cont(g_first), cont(g_field), cont(g_flat),
                                              cont(g_fm), field, flat, fm_sum, params, lam, gscale, aux, p2p=ctx.p2p,
@@ -258,10 +260,19 @@ class _ShardedEmbedFn(torch.autograd.Function):
         return (None, None, None) + (None,) * ctx.n_inputs + tuple(grads)
 
 
-class ShardedFeatureEmbedding(nn.Module):
+class ShardedFeatureEmbedding(IndexStatusMixin, nn.Module):
+    """``grad_scale`` (default 1 / world): factor applied to every exchanged table-gradient row.  Each rank
+    back-propagates the mean loss of ITS ``b`` samples; the data-parallel parameters' gradients are averaged over the
+    ranks (``DenseGradReducer``), i.e. they are gradients of the GLOBAL-mean loss.  A sharded row's gradient is the SUM
+    over the ranks of what their samples contribute, so it is scaled by 1 / world to be on that same scale (the global
+    clip norm and the optimizer then see one consistent loss); the L2 term ``2*l2*w`` is added once by the owner,
+    unscaled.  Set ``grad_scale = 1.0`` for sum semantics."""
+
     def __init__(self, schema, fm_embed_dim: int = 16, world: int = 1, rank: int = 0, comm=None,
-                 replicate_below: int = 4096) -> None:
+                 replicate_below: int = 4096, grad_scale: Optional[float] = None) -> None:
         super().__init__()
+        self._init_status()
+        self.grad_scale = (1.0 / world) if grad_scale is None else float(grad_scale)
         self.schema, self.fm_embed_dim = schema, fm_embed_dim
         self.replicate_below = int(replicate_below)
         self.world, self.rank, self.comm = world, rank, comm
@@ -330,6 +341,7 @@ class ShardedFeatureEmbedding(nn.Module):
         self.row_grads: Optional[RowSparseGrads] = None
         self.last_counts = None
         self._live_ctx = None
+        self._live_anchor = None
         self._plans = None
         self._param_is_table: List[bool] = []
         self._slot_of_param: List[int] = []
@@ -474,7 +486,9 @@ class ShardedFeatureEmbedding(nn.Module):
             ws = torch.empty((max(lib.dfm_shard_route_workspace_bytes(sample_plan, b), 16),), device=dev, dtype=torch.uint8)
             _lib.check(lib.dfm_shard_route(sample_plan, W, _lib.i64_array(self._global_row_base), b, _lib.ptr_array(inputs),
                                            _lib.ptr(send_keys), _lib.ptr(pos), _lib.ptr(counts), _lib.ptr(send_slots),
-                                           ws.data_ptr(), ws.numel(), _lib.stream_ptr()), "dfm_shard_route")
+                                           _lib.ptr(self._status_word(dev)), ws.data_ptr(), ws.numel(), _lib.stream_ptr()),
+                       "dfm_shard_route")
+            self._post_status()
             return Route(send_keys=send_keys, counts=counts, order=None, pos=pos, send_slots=send_slots)
         return self.route_torch(inputs)
 
@@ -614,12 +628,14 @@ class ShardedFeatureEmbedding(nn.Module):
             _lib.check(lib.dfm_shard_pack_grad_p2p(sample_plan, b, _lib.ptr(pos), _lib.ptr(g_first), _lib.ptr(g_field),
                                                    _lib.ptr(g_flat), _lib.ptr(g_fm), _lib.ptr(fm_sum), field.data_ptr(),
                                                    _lib.ptr(aux), W, _lib.i64_array(starts), _lib.ptr_array(bases),
-                                                   _lib.ptr(send_slots), _lib.stream_ptr()), "dfm_shard_pack_grad_p2p")
+                                                   _lib.ptr(send_slots), float(self.grad_scale), _lib.stream_ptr()),
+                       "dfm_shard_pack_grad_p2p")
         else:
             g_rows = torch.empty((n, self.fm_embed_dim + 4), device=dev, dtype=torch.float32)
             _lib.check(lib.dfm_shard_pack_grad(sample_plan, b, _lib.ptr(pos), _lib.ptr(g_first), _lib.ptr(g_field),
                                                _lib.ptr(g_flat), _lib.ptr(g_fm), _lib.ptr(fm_sum), field.data_ptr(),
-                                               _lib.ptr(aux), _lib.ptr(g_rows), _lib.stream_ptr()), "dfm_shard_pack_grad")
+                                               _lib.ptr(aux), _lib.ptr(g_rows), float(self.grad_scale), _lib.stream_ptr()),
+                       "dfm_shard_pack_grad")
         # Data-parallel parameters of the embedding: DENSE-field Linears and the replicated (small) tables.
         # K2 on the sample-side plan; the sharded tables are foreign there, so only the replicated ones are
         # sorted / segment-reduced (dense (V, d) gradients, 2*l2*w on every row like the reference).
@@ -716,7 +732,10 @@ class ShardedFeatureEmbedding(nn.Module):
         if not self.p2p_capacity_rows:    # every rank derives the same capacity (same batch size and schema)
             self.p2p_capacity_rows = 2 * inputs[0].shape[0] * max(self._S, 1) + 16
         need_bwd = torch.is_grad_enabled() and any(p.requires_grad for p in params)
+        if self._status_pending and self.check_indices:
+            self.raise_if_bad_index(block=True, keep=2)
         first, field, flat, fm = _ShardedEmbedFn.apply(self, len(inputs), need_bwd, *inputs, *params)
+        self._live_anchor = weakref.ref(first) if need_bwd else None
         field._dfm_fm = (fm, field._version)
         return first, field, flat, fm
 

@@ -45,7 +45,10 @@ typedef enum dfm_status {
 enum { DFM_SPARSE = 0, DFM_SEQUENCE = 1, DFM_DENSE = 2 };
 enum { DFM_SUM = 0, DFM_MEAN = 1, DFM_MAX = 2 };
 /* Gradient layout of the embedding tables produced by dfm_embed_bwd. */
-enum { DFM_GRAD_DENSE = 0, DFM_GRAD_ROWSPARSE = 1, DFM_GRAD_SKIP_TABLES = 2 /* only DENSE-field / projection grads */ };
+enum { DFM_GRAD_DENSE = 0, DFM_GRAD_ROWSPARSE = 1, DFM_GRAD_SKIP_TABLES = 2 /* only DENSE-field / projection grads */,
+       /* flag, OR-ed into the mode of dfm_embed_bwd / dfm_rows_bwd: sorted_keys / sorted_payload already hold the
+        * result of dfm_sort_keys for this batch (the device-side input pipeline sorts ahead of the step) */
+       DFM_GRAD_PRESORTED = 0x100 };
 
 DFM_API const char* dfm_last_error(void);
 DFM_API int dfm_version(void);
@@ -136,6 +139,7 @@ DFM_API int dfm_embed_bwd(const dfm_plan* plan, int64_t batch, const void* const
  * against the oracle (emit_keys / sort_pairs / segment_heads). */
 DFM_API int dfm_emit_keys(const dfm_plan* plan, int64_t batch, const void* const* inputs,
                   uint32_t* keys, void* stream);
+DFM_API size_t dfm_sort_keys_workspace_bytes(const dfm_plan* plan, int64_t n);
 DFM_API int dfm_sort_keys(const dfm_plan* plan, int64_t n, const uint32_t* keys, uint32_t* sorted_keys,
                   uint32_t* sorted_payload, void* workspace, size_t workspace_bytes,
                   void* stream);
@@ -153,6 +157,14 @@ DFM_API int dfm_fm_bwd(const float* e, const float* g_out, int64_t batch, int n_
  * ---------------------------------------------------------------------------------------- */
 DFM_API int dfm_sumsq(int n_tensors, const float* const* ptrs, const int64_t* numel, float scale,
               float* out, float* workspace, void* stream);
+/* Incrementally maintained ||W||^2 (SURVEY hard part 2: the reference re-reads every table every step):
+ * dfm_sumsq_acc writes the exact sum of squares of the tensor list into the device double acc[0] (the audited slow
+ * path, same reduction as dfm_sumsq); dfm_adam_rows then adds sum(w_new^2 - w_old^2) of the rows it touches, so the
+ * value stays current without another pass over the tables; dfm_l2_combine forms out[0] = lam * (a[0] + b[0])
+ * (b may be NULL) -- the scalar get_l2_reg_loss returns. */
+DFM_API int dfm_sumsq_acc(int n_tensors, const float* const* ptrs, const int64_t* numel, double* acc,
+                          float* workspace, void* stream);
+DFM_API int dfm_l2_combine(const double* acc_a, const double* acc_b, float lam, float* out, void* stream);
 /* g[i] (+)= coef * scale_dev[0] * p[i]  (the dense L2 gradient when K2 is not in the graph). */
 DFM_API int dfm_axpy(const float* p, int64_t numel, float coef, const float* scale_dev, float* g,
              int accumulate, void* stream);
@@ -208,6 +220,8 @@ DFM_API int dfm_attn_bwd(const float* x, const float* g_out, int64_t batch, int 
  *       sent, its row 0 is returned as stored).  The blocks are K1's id columns of the sample-side plan.
  *       send_slots (optional, <= B*S): the inverse map, send position -> id slot index b*S + s; with it
  *       dfm_shard_pack_grad_p2p walks the send order, so every peer receives one sequential store stream.
+ *       An id outside [0, vocabulary_size) (global_row_base[f+1] - global_row_base[f]) is routed as the padding
+ *       id 0 and sets *status = 1 (optional device word; the reference raises IndexError).
  *   dfm_shard_gather : owner side.  keys = global rows (row_base[f] + id) as received; writes the
  *       reply rows [row (d), first-order weight, 0, 0, 0] and the local sort keys
  *       (local_row_base[f] + local_row, PAD for id 0) the owner-side backward consumes.
@@ -218,7 +232,9 @@ DFM_API int dfm_attn_bwd(const float* x, const float* g_out, int64_t batch, int 
  *       SPARSE [g_flat + g_field + g_fm * fm_sum (d), g_first, g_fm, 0, 0];  bag member
  *       [scale * (g_flat + g_field + g_fm * (fm_sum - e_bag)) (d), scale * g_first, 0, 0, 0] with
  *       scale = 1 (sum) or 1 / non-pad count (mean, from the forward's aux record); field_emb / aux
- *       may be null when the plan has no bag fields.
+ *       may be null when the plan has no bag fields.  grad_scale multiplies every packed value: 1 / world makes
+ *       the owner's summed table gradient the gradient of the GLOBAL-mean loss, the scale the averaged
+ *       data-parallel parameters have (the L2 term 2 l2 w is added once, by the owner, unscaled).
  *   dfm_rows_bwd : owner side backward = K2 on a row list: keys (n) with one packed gradient row
  *       each; same sort / segreduce / stitch kernels and modes as dfm_embed_bwd, the field is
  *       derived from the key and -(sum g_fm) w[row] + 2 l2 w[row] is folded in at the segment end.
@@ -226,8 +242,8 @@ DFM_API int dfm_attn_bwd(const float* x, const float* g_out, int64_t batch, int 
 DFM_API size_t dfm_shard_route_workspace_bytes(const dfm_plan* plan, int64_t batch);
 DFM_API int dfm_shard_route(const dfm_plan* plan, int world, const int64_t* global_row_base,
                             int64_t batch, const void* const* inputs, uint32_t* send_keys,
-                            int64_t* positions, int64_t* counts, uint32_t* send_slots, void* workspace,
-                            size_t workspace_bytes, void* stream);
+                            int64_t* positions, int64_t* counts, uint32_t* send_slots, int32_t* status,
+                            void* workspace, size_t workspace_bytes, void* stream);
 DFM_API int dfm_shard_gather(const dfm_plan* local_plan, int world, int rank,
                              const int64_t* global_row_base, int64_t n_keys, const uint32_t* keys,
                              const float* const* params, float* rows, uint32_t* local_keys,
@@ -235,7 +251,7 @@ DFM_API int dfm_shard_gather(const dfm_plan* local_plan, int world, int rank,
 DFM_API int dfm_shard_pack_grad(const dfm_plan* plan, int64_t batch, const int64_t* positions,
                                 const float* g_first, const float* g_field, const float* g_flat,
                                 const float* g_fm, const float* fm_sum, const float* field_emb,
-                                const uint32_t* aux, float* g_rows, void* stream);
+                                const uint32_t* aux, float* g_rows, float grad_scale, void* stream);
 /* Fused exchange over peer memory (NVLink P2P stores; peer buffers come from CUDA IPC / torch symmetric
  * memory): the same two kernels write every row straight into the destination GPU's buffer instead of a
  * local staging buffer followed by an all-to-all.  Rows [peer_start[p], peer_start[p+1]) of this rank's send
@@ -250,7 +266,8 @@ DFM_API int dfm_shard_pack_grad_p2p(const dfm_plan* plan, int64_t batch, const i
                                     const float* g_first, const float* g_field, const float* g_flat,
                                     const float* g_fm, const float* fm_sum, const float* field_emb,
                                     const uint32_t* aux, int n_peers, const int64_t* peer_start,
-                                    float* const* peer_rows, const uint32_t* send_slots, void* stream);
+                                    float* const* peer_rows, const uint32_t* send_slots, float grad_scale,
+                                    void* stream);
 /* Per-field table source of a plan: row_stride / w1_stride (floats, 0 = dim / 1) let K1 read the field's rows
  * out of a strided buffer (the received reply rows); foreign = 1 marks a table whose gradient is produced
  * elsewhere: K1 emits no sort key for its ids and dfm_embed_bwd / dfm_rows_bwd ignore it.  On the sample-side
@@ -274,13 +291,18 @@ DFM_API int dfm_rows_bwd(const dfm_plan* plan, int64_t n_rows, const float* cons
  * deviation from the dense reference; oracle: adam_rows).  params / exp_avg / exp_avg_sq: 5 slots per field
  * like everywhere, only the two table slots are read.  clip_scale: device scalar multiplying every gradient
  * (min(1, max_norm / (norm + 1e-6)) of the global-norm clip), or NULL.
- *   dfm_rows_sumsq: sum of squares of the touched rows' gradients (the table part of that norm),
- *   deterministic fixed-order reduction into out[0].
+ *   ssq_acc (optional): device double holding sum ||w||^2 over the tables (dfm_sumsq_acc); the kernel adds
+ *   sum(w_new^2 - w_old^2) of the touched elements (fp64, per-block partials added in block order) so the L2
+ *   value needs no pass over the tables; ssq_workspace >= dfm_adam_rows_workspace_bytes() then.
+ *   dfm_rows_sumsq: sum of squares of the touched rows' gradients (the table part of that norm; only the
+ *   dim[f] defined floats of each row), deterministic fixed-order reduction into out[0].
  * ---------------------------------------------------------------------------------------- */
 DFM_API int dfm_adam_rows(const dfm_plan* plan, int64_t n_sorted, const uint32_t* sorted_keys,
                           const float* row_grad2, const float* row_grad1, float* const* params,
                           float* const* exp_avg, float* const* exp_avg_sq, float lr, float beta1, float beta2,
-                          float eps, int64_t step, const float* clip_scale, void* stream);
+                          float eps, int64_t step, const float* clip_scale, double* ssq_acc,
+                          void* ssq_workspace, size_t ssq_workspace_bytes, void* stream);
+DFM_API size_t dfm_adam_rows_workspace_bytes(void);
 DFM_API size_t dfm_rows_sumsq_workspace_bytes(void);
 DFM_API int dfm_rows_sumsq(const dfm_plan* plan, int64_t n_sorted, const uint32_t* sorted_keys,
                            const float* row_grad2, const float* row_grad1, float* out, void* workspace,

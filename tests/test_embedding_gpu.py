@@ -125,12 +125,32 @@ def test_empty_batch():
 
 def test_out_of_range_index_raises_like_reference():
     g, emb = golden_embedding()
-    emb.check_indices = True
+    emb.check_indices = "sync"            # check inside forward (one host sync per call)
     batch = to_dev(split_prefixed(g, "batch/"))
     batch["u"] = batch["u"].clone()
     batch["u"][2] = 11                    # vocabulary_size == 11
     with pytest.raises(IndexError):
         emb(batch)
+
+
+def test_out_of_range_index_raises_lazily_by_default():
+    """Default: no host sync on the hot path; the status word travels asynchronously and the error surfaces at
+    raise_if_bad_index() / a later forward (never silently)."""
+    g, emb = golden_embedding()
+    assert emb.check_indices is True
+    good = to_dev(split_prefixed(g, "batch/"))
+    bad = dict(good)
+    bad["u"] = good["u"].clone()
+    bad["u"][2] = -3
+    emb(bad)                              # clamped to the padding row, flagged
+    with pytest.raises(IndexError):
+        emb.raise_if_bad_index()
+    emb(good)
+    emb.raise_if_bad_index()              # the flag was cleared, a clean batch stays clean
+    emb(bad)
+    torch.cuda.synchronize()
+    with pytest.raises(IndexError):
+        emb(good)                         # surfaces at the next forward at the latest once it has arrived
 
 
 # ----------------------------------------------------------------- integer artefacts (bit-exact)

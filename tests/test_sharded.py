@@ -332,7 +332,7 @@ def test_sharded_equals_unsharded_emulated_ranks(W, D, multihot, repl):
     fm = FMInteraction()(fe)
     ((fo * g_first).sum() + (fl * g_flat).sum() + (fm * g_fm).sum() + l2_penalty(full, lam)).backward()
 
-    mods = [ShardedFeatureEmbedding(schema, D, W, r, replicate_below=repl).cuda() for r in range(W)]
+    mods = [ShardedFeatureEmbedding(schema, D, W, r, replicate_below=repl, grad_scale=1.0).cuda() for r in range(W)]   # sum semantics
     for m in mods:
         m.load_from_full(full)
         m.grad_mode = "dense"
