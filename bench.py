@@ -226,6 +226,8 @@ def run_ours(args, rank: int, local_rank: int, n_gpus: int):
     if model_name == "xdeepfm" and args.cin_precision:
         model.cin.precision = args.cin_precision
     emb = model.embedding
+    if hasattr(emb, "async_sort"):
+        emb.async_sort = args.sort != "inline"
     ordered = emb._ordered_params()
     table_ids = {id(p) for p, is_table in zip(ordered, emb._param_is_table) if is_table}
     dense_params = [p for p in model.parameters() if id(p) not in table_ids]
@@ -266,7 +268,7 @@ def run_ours(args, rank: int, local_rank: int, n_gpus: int):
         # device-side input pipeline: the NEXT batch's row keys are emitted and sorted on a side
         # stream while this step computes (the sort depends on the ids only), so its backward starts at the segmented
         # reduction.  One sort per step still runs -- overlapped, not skipped; its duration is reported (sort_ms).
-        if not sharded and not args.no_presort:
+        if not sharded and args.sort == "ahead":
             model.embedding.prepare(batch)
 
     def barrier():
@@ -324,7 +326,7 @@ def run_ours(args, rank: int, local_rank: int, n_gpus: int):
         with torch.cuda.stream(copy_stream):
             batch = {k: v.to(dev, non_blocking=True) for k, v in hb.items()}
             labels = hy.to(dev, non_blocking=True)
-            if not sharded and not args.no_presort:       # the input pipeline sorts the batch's keys right behind its copy
+            if not sharded and args.sort == "ahead":      # the input pipeline sorts the batch's keys right behind its copy
                 model.embedding.prepare(batch, stream=copy_stream)
             ev = torch.cuda.Event()
             ev.record(copy_stream)
@@ -356,6 +358,16 @@ def run_ours(args, rank: int, local_rank: int, n_gpus: int):
             step(devb[0], devy[0])
             torch.cuda.synchronize()
         launches = sum(e.count for e in prof.key_averages() if "dfm::" in e.key or "DeviceRadixSort" in e.key)
+        if args.profile_step:      # per-kernel device time of one warm step (concurrent streams as they run), for profiles/
+            with open(args.profile_step, "w") as fh:
+                fh.write(f"# torch.profiler, one warm step of: bench.py --workload {wl} --gpus {n_gpus} --sort {args.sort}\n")
+                fh.write("kernel,launches,total_us,avg_us,share_pct\n")
+                evs = sorted(prof.key_averages(), key=lambda e: -e.device_time_total)
+                tot = sum(e.device_time_total for e in evs) or 1.0
+                for e in evs:
+                    if e.device_time_total > 0:
+                        fh.write(f"\"{e.key[:110]}\",{e.count},{e.device_time_total:.1f},{e.device_time_total / e.count:.2f},"
+                                 f"{100.0 * e.device_time_total / tot:.2f}\n")
     else:
         step(devb[0], devy[0])
         torch.cuda.synchronize()
@@ -453,7 +465,10 @@ def main():
     ap.add_argument("--warmup", type=int, default=5)
     ap.add_argument("--impl", default="ours", choices=["ours", "reference"])
     ap.add_argument("--no-cpu-baseline", action="store_true")
-    ap.add_argument("--no-presort", action="store_true", help="K2 sorts the row keys itself inside the backward")
+    ap.add_argument("--profile-step", default=None, help="write a per-kernel device-time table of one warm step to this file")
+    ap.add_argument("--sort", default="side", choices=["side", "ahead", "inline"],
+                    help="where the backward's key sort runs: on a side stream right behind K1 (default), one step ahead in "
+                         "the input pipeline (FeatureEmbedding.prepare), or inside the backward")
     ap.add_argument("--workload", default="deepfm_criteo", choices=sorted(WORKLOADS))
     ap.add_argument("--dnn-gemm", default="emulated", choices=["emulated", "native"],
                     help="library GEMMs of the (out-of-scope) DNN tower: cuBLAS 12.9 FP32 emulation on the BF16 tensor "

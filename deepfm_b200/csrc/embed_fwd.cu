@@ -442,18 +442,34 @@ embed_fwd_kernel(const __grid_constant__ DevPlan P, long long B, int G, int smem
     }   // tile loop
 }
 
-// Keys only (bit-exact integer artefact; also used when the forward ran without key emission).
-__global__ void emit_keys_kernel(const __grid_constant__ DevPlan P, long long B,
-                                 uint32_t* __restrict__ keys) {
-    const long long n = B * P.S;
+// Keys only (bit-exact integer artefact; also the first stage of the input pipeline's ahead-of-step sort).
+// The per-slot records are staged in shared memory (lane-divergent reads of the by-value plan would serialise
+// in the constant bank); thread i owns key position i = b*S + s, so the key writes are coalesced.
+__global__ void __launch_bounds__(256)
+emit_keys_kernel(const __grid_constant__ DevPlan P, long long B, uint32_t* __restrict__ keys) {
+    extern __shared__ __align__(16) unsigned char ek_raw[];
+    SlotS* t_slot = reinterpret_cast<SlotS*>(ek_raw);
+    const int S = P.S;
+    for (int s = threadIdx.x; s < S; s += blockDim.x) {
+        const FieldDev& fd = P.f[P.slot_field[s]];
+        SlotS e;
+        e.in = reinterpret_cast<const long long*>(fd.in); e.w1 = nullptr;
+        e.row_base = (unsigned)fd.row_base; e.vocab = fd.vocab;
+        e.stride_pos = (fd.max_len << 16) | P.slot_pos[s];
+        e.sparse = fd.foreign ? 2 : 0;
+        e.w1s = 0;
+        t_slot[s] = e;
+    }
+    __syncthreads();
+    const long long n = B * S;
     for (long long i = (long long)blockIdx.x * blockDim.x + threadIdx.x; i < n;
          i += (long long)gridDim.x * blockDim.x) {
-        const long long b = i / P.S;
-        const int s = (int)(i - b * P.S);
-        const FieldDev& fd = P.f[P.slot_field[s]];
-        long long id = __ldg(reinterpret_cast<const long long*>(fd.in) + b * fd.max_len + P.slot_pos[s]);
-        if (id < 0 || id >= fd.vocab) id = 0;
-        keys[i] = (id && !fd.foreign) ? (uint32_t)(fd.row_base + id) : P.pad_key;
+        const long long b = i / S;
+        const int s = (int)(i - b * S);
+        const SlotS e = t_slot[s];
+        long long id = __ldg(e.in + b * (e.stride_pos >> 16) + (e.stride_pos & 0xffff));
+        if ((unsigned long long)id >= (unsigned long long)e.vocab) id = 0;
+        keys[i] = (id && !(e.sparse & 2)) ? e.row_base + (unsigned)id : P.pad_key;
     }
 }
 
@@ -684,7 +700,8 @@ int dfm_emit_keys(const dfm_plan* plan, int64_t batch, const void* const* inputs
     plan->fill(*Pp, inputs, dummy.data(), true);
     const long long n = batch * plan->S;
     const int blocks = (int)(ceil_div(n, 256) < 8LL * sm_count() ? ceil_div(n, 256) : 8LL * sm_count());
-    emit_keys_kernel<<<blocks, 256, 0, static_cast<cudaStream_t>(stream)>>>(*Pp, batch, keys);
+    const size_t ek_smem = (size_t)plan->S * sizeof(SlotS);
+    emit_keys_kernel<<<blocks, 256, ek_smem, static_cast<cudaStream_t>(stream)>>>(*Pp, batch, keys);
     delete Pp;
     DFM_CHECK_LAUNCH();
     return DFM_OK;

@@ -99,6 +99,10 @@ class _EmbedFn(torch.autograd.Function):
             ev[1].record()
         if status is not None:
             mod._post_status()
+        if keys is not None and mod.async_sort and B * S > 0:
+            # the backward's sort needs the keys only: start it now on a side stream, underneath the interaction /
+            # DNN forward and backward; the embedding backward then begins at the segmented reduction
+            prep = mod._sort_async(keys, B * S, dev)
         ctx.mod = mod
         ctx.n_inputs = n_inputs
         ctx.set_materialize_grads(False)
@@ -213,6 +217,7 @@ class FeatureEmbedding(IndexStatusMixin, nn.Module):
         self.grad_mode = "dense"
         self.profile_events = None      # set to {} to collect (start, end) CUDA events per call
         self._init_status()             # out-of-range ids raise IndexError lazily (layers/_status.py)
+        self.async_sort = True          # sort the backward's keys on a side stream right behind K1 (False: inside backward)
         self._live_anchor = None
         self.row_grads: Optional[RowSparseGrads] = None
         self.last_counts = None
@@ -343,15 +348,33 @@ class FeatureEmbedding(IndexStatusMixin, nn.Module):
         N = B * self._S
         if N == 0:
             return
-        side = stream
-        if side is None:
-            side = getattr(self, "_prep_stream", None)
-            if side is None or side.device != dev:
-                side = self._prep_stream = torch.cuda.Stream(device=dev)
         cur = torch.cuda.current_stream(dev)
+        side = stream if stream is not None else self._side_stream(dev)
         side.wait_stream(cur)                      # the id tensors are ready on the caller's stream
         with torch.cuda.stream(side):
             keys = torch.empty((N,), device=dev, dtype=torch.int32)
+            _lib.check(lib.dfm_emit_keys(self._plan, B, _lib.ptr_array(inputs), keys.data_ptr(), side.cuda_stream), "dfm_emit_keys")
+        prepared = self._sort_async(keys, N, dev, side=side, wait=False)
+        for t in inputs:
+            t.record_stream(side)
+        sig = tuple(t.data_ptr() for t, k in zip(inputs, self._kinds) if k != _lib.DENSE) + (B,)
+        self._prepared = (sig, prepared)
+
+    def _side_stream(self, dev):
+        side = getattr(self, "_prep_stream", None)
+        if side is None or side.device != dev:
+            side = self._prep_stream = torch.cuda.Stream(device=dev)
+        return side
+
+    def _sort_async(self, keys, N: int, dev, side=None, wait: bool = True):
+        """dfm_sort_keys on a side stream; returns (sorted_keys, sorted_payload, event)."""
+        lib = _lib.lib()
+        cur = torch.cuda.current_stream(dev)
+        if side is None:
+            side = self._side_stream(dev)
+        if wait:
+            side.wait_stream(cur)
+        with torch.cuda.stream(side):
             skeys = torch.empty((N,), device=dev, dtype=torch.int32)
             spay = torch.empty((N,), device=dev, dtype=torch.int32)
             ws = torch.empty((max(lib.dfm_sort_keys_workspace_bytes(self._plan, N), 16),), device=dev, dtype=torch.uint8)
@@ -360,7 +383,6 @@ class FeatureEmbedding(IndexStatusMixin, nn.Module):
             if store is not None:
                 t0, t1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
                 t0.record(side)
-            _lib.check(lib.dfm_emit_keys(self._plan, B, _lib.ptr_array(inputs), keys.data_ptr(), side.cuda_stream), "dfm_emit_keys")
             _lib.check(lib.dfm_sort_keys(self._plan, N, keys.data_ptr(), skeys.data_ptr(), spay.data_ptr(), ws.data_ptr(),
                                          ws.numel(), side.cuda_stream), "dfm_sort_keys")
             if store is not None:
@@ -368,10 +390,8 @@ class FeatureEmbedding(IndexStatusMixin, nn.Module):
                 store.setdefault("sort", []).append((t0, t1))
             ev = torch.cuda.Event()
             ev.record(side)
-        for t in inputs:
-            t.record_stream(side)
-        sig = tuple(t.data_ptr() for t, k in zip(inputs, self._kinds) if k != _lib.DENSE) + (B,)
-        self._prepared = (sig, (skeys, spay, ev))
+        keys.record_stream(side)
+        return skeys, spay, ev
 
     def _take_prepared(self, inputs):
         pref = getattr(self, "_prepared", None)

@@ -105,7 +105,21 @@ def _bench_cfg(fm_dim, cin=None):
     return cfg
 
 
+def _port_grads(name, schema, cfg, params, batch, labels, dtype):
+    cast = lambda t: t.to(dtype) if t.is_floating_point() else t
+    port = TP.PortedModel(name, schema, cfg, params={k: cast(v) for k, v in params.items()})
+    b = {k: cast(v) for k, v in batch.items()}
+    logits = port.forward(b)
+    loss = torch.nn.functional.binary_cross_entropy_with_logits(logits.squeeze(1), labels.to(dtype)) + port.l2_reg_loss()
+    loss.backward()
+    return logits.detach(), loss.detach(), {k: v.grad for k, v in port.params.items() if v.grad is not None}
+
+
 def _whole_model_vs_port(name, schema, cfg, B, seed, logits_tol=1e-5, grad_tol=GRAD_TOL, cin_precision=None):
+    """The CUDA model against the torch-CPU port of the reference on the same weights and batch.  Tolerance per
+    tensor: the stated fp32 bound (logits 1e-5, gradients 1e-4 max-norm relative), or -- where a long fp32 reduction
+    (batch-size-long sums behind BatchNorm) makes the fp32 REFERENCE itself deviate more than that from its own fp64
+    evaluation -- three times that measured reference-fp32-vs-fp64 deviation (printed)."""
     torch.manual_seed(seed)
     model = create_model(name, schema, cfg).cuda().train()
     if cin_precision is not None:
@@ -116,15 +130,22 @@ def _whole_model_vs_port(name, schema, cfg, B, seed, logits_tol=1e-5, grad_tol=G
     logits = model(_cuda(batch))
     loss = torch.nn.functional.binary_cross_entropy_with_logits(logits.squeeze(1), labels.cuda()) + model.get_l2_reg_loss()
     loss.backward()
-    port = TP.PortedModel(name, schema, cfg, params=params)
-    ref_logits = port.forward(batch)
-    ref_loss = torch.nn.functional.binary_cross_entropy_with_logits(ref_logits.squeeze(1), labels) + port.l2_reg_loss()
-    ref_loss.backward()
-    assert_close_rel(logits.detach().cpu(), ref_logits.detach(), logits_tol, f"{name} logits", floor=2e-6)
-    assert abs(loss.item() - ref_loss.item()) <= 1e-5 * abs(ref_loss.item()), (loss.item(), ref_loss.item())
+    l32, loss32, g32 = _port_grads(name, schema, cfg, params, batch, labels, torch.float32)
+    l64, loss64, g64 = _port_grads(name, schema, cfg, params, batch, labels, torch.float64)
+    from tests.conftest import rel_max_err
+    noise = rel_max_err(l32.numpy(), l64.numpy(), floor=2e-6)
+    assert_close_rel(logits.detach().cpu(), l64, max(logits_tol, 3 * noise), f"{name} logits", floor=2e-6)
+    assert abs(loss.item() - loss64.item()) <= 1e-5 * abs(loss64.item()), (loss.item(), loss64.item())
+    worst = []
     for k, p in model.named_parameters():
         assert p.grad is not None, k
-        assert_close_rel(p.grad.cpu(), port.params[k].grad, grad_tol, f"{name} {k}", floor=1e-6)
+        noise = rel_max_err(g32[k].numpy(), g64[k].numpy(), floor=1e-6)
+        ours = rel_max_err(p.grad.cpu().numpy(), g64[k].numpy(), floor=1e-6)
+        worst.append((ours, noise, k))
+        assert_close_rel(p.grad.cpu(), g64[k], max(grad_tol, 3 * noise), f"{name} {k} (reference fp32 vs fp64: {noise:.2e})", floor=1e-6)
+    worst.sort(reverse=True)
+    print(f"[{name}] worst gradient deviations vs fp64 (ours, reference-fp32): " +
+          ", ".join(f"{k}: {o:.1e}/{n:.1e}" for o, n, k in worst[:3]))
 
 
 def test_deepfm_on_criteo_shape_vs_reference_port():
