@@ -53,6 +53,9 @@ WORKLOADS = {
     "deepfm_criteo": ("deepfm", WORKLOAD),
     "xdeepfm_criteo_multihot": ("xdeepfm", "xdeepfm_criteo_13dense_26multihot_avg8_d64_cin128x128_b{B}_per_gpu"),
     "xdeepfm_ml": ("xdeepfm", "xdeepfm_ml100k_shape_cin128x128x64_b65536"),
+    "xdeepfm_ml_yaml": ("xdeepfm", "xdeepfm_ml100k_shape_cin64_b65536 (configs/xdeepfm_movielens.yaml, batch raised to fill the GPU)"),
+    "xdeepfm_ml_yaml_b4096": ("xdeepfm", "xdeepfm_ml100k_shape_cin64_b4096 (configs/xdeepfm_movielens.yaml as written)"),
+    "deepfm_ml_b4096": ("deepfm", "deepfm_ml100k_shape_b4096 (configs/deepfm_movielens.yaml: BASELINE config 1, the reference's CPU case)"),
     "attention_ml": ("attention_deepfm", "attention_deepfm_ml100k_shape_4heads_a64_b65536"),
 }
 MULTIHOT_ROWS_PER_GPU = 125_000_000     # config 5: 1 B rows over 8 GPUs (32 GB of tables per GPU)
@@ -79,6 +82,8 @@ def bench_config(workload: str = "deepfm_criteo"):
         cfg.feature.fm_embed_dim = EMBED_DIM
     if workload == "xdeepfm_ml":
         cfg.cin.layer_sizes = [128, 128, 64]          # configs/xdeepfm_movielens_cin_tuned.yaml
+    if workload.startswith("xdeepfm_ml_yaml"):
+        cfg.cin.layer_sizes = [64]                    # configs/xdeepfm_movielens.yaml:22-24
     return cfg
 
 
@@ -89,7 +94,7 @@ def workload_schema(workload: str, n_gpus: int):
     if workload == "xdeepfm_criteo_multihot":
         scale = MULTIHOT_ROWS_PER_GPU * n_gpus / float(sum(W.CRITEO_VOCAB))
         return W.criteo_multihot_schema(EMBED_DIM, max_length=16, vocab_scale=scale), MULTIHOT_BATCH
-    return W.ml100k_schema(), BATCH
+    return W.ml100k_schema(), cfg_batch(workload)
 
 
 def base_line(args, n_gpus):
@@ -145,26 +150,93 @@ class ClockSampler:
 
 
 # ------------------------------------------------------------------------------------ CPU arm
-def cpu_reference_run(steps: int, warmup: int, budget_s: float = 240.0):
-    """Reference PyTorch-CPU path (torch-CPU port of the reference modules) on a bounded sample."""
+def _import_reference():
+    """The UNMODIFIED reference package from baseline/_ref (see baseline/README.md), or None."""
+    ref_dir = os.path.join(ROOT, "baseline", "_ref")
+    if not os.path.isdir(os.path.join(ref_dir, "deepfm")):
+        return None
+    for p in (os.path.join(ROOT, "baseline"), ref_dir):       # baseline/dacite.py: stand-in for the absent `dacite`
+        if p not in sys.path:
+            sys.path.insert(0, p)
+    try:
+        import deepfm                                          # noqa: F401
+        from deepfm import config as rcfg, models as rmodels
+        from deepfm.data import schema as rschema
+        return rcfg, rmodels, rschema
+    except Exception as e:                                     # pragma: no cover - depends on the box
+        print(f"[bench] reference import failed ({e}); using the torch-CPU port", file=sys.stderr)
+        return None
+
+
+def _ref_schema(rschema, schema):
+    """Our DatasetSchema -> the reference's own dataclasses (same fields, same order)."""
+    fields = {}
+    for name, f in schema.fields.items():
+        kind = f.feature_type.value if hasattr(f.feature_type, "value") else str(f.feature_type)
+        fields[name] = rschema.FieldSchema(name, rschema.FeatureType(kind), vocabulary_size=f.vocabulary_size,
+                                           embedding_dim=f.embedding_dim, max_length=f.max_length, combiner=f.combiner)
+    return rschema.DatasetSchema(fields=fields, label_field="label")
+
+
+def cpu_reference_run(steps: int, warmup: int, budget_s: float = 240.0, workload: str = "deepfm_criteo"):
+    """The reference's own PyTorch-CPU code path on a bounded sample of the workload, all host cores: the unmodified
+    modules from baseline/_ref when they are there (kind "reference"), else the torch-CPU port (kind "port")."""
+    import psutil
     import torch
     from deepfm_b200 import workloads as W
-    from oracle import torch_port as TP
     cores = os.cpu_count() or 1
     torch.set_num_threads(cores)
-    schema = W.criteo_schema(EMBED_DIM, max_vocab=CPU_SAMPLE_MAX_VOCAB)
-    cfg = bench_config()
-    model = TP.PortedModel("deepfm", schema, cfg, seed=0)
-    batch = W.synthetic_batch(schema, CPU_SAMPLE_BATCH, seed=0)
-    labels = W.synthetic_labels(CPU_SAMPLE_BATCH, seed=0)
+    model_name = WORKLOADS[workload][0]
+    cfg = bench_config(workload)
+    free_gb = psutil.virtual_memory().available / 2 ** 30
+    note = ""
+    if workload == "deepfm_criteo":
+        # full size = 8.6 GB of tables + the same again of dense autograd gradients (+ zeros): needs ~40 GB of host RAM
+        full = free_gb >= 48 and not os.environ.get("DFM_BENCH_CPU_SMALL")
+        schema = W.criteo_schema(EMBED_DIM) if full else W.criteo_schema(EMBED_DIM, max_vocab=CPU_SAMPLE_MAX_VOCAB)
+        B = BATCH if full else CPU_SAMPLE_BATCH
+        note = ("full 33.76 M-row tables, the bench batch" if full else
+                f"tables capped at {CPU_SAMPLE_MAX_VOCAB} rows each (host has {free_gb:.0f} GB free)")
+    elif workload == "xdeepfm_criteo_multihot":
+        schema = W.criteo_multihot_schema(EMBED_DIM, max_length=16, vocab_scale=CPU_SAMPLE_MAX_VOCAB / 10131227.0)
+        B = 512           # the reference materialises a (B, 39*39, 64) outer product per CIN layer
+        note = "tables scaled to <= 1 M rows, batch bounded by the unfused CIN outer product"
+    else:
+        schema = W.ml100k_schema()      # fits the host at full size
+        B = cfg_batch(workload)
+        note = "full ML-100K-shaped schema"
+    batch = W.synthetic_batch(schema, B, seed=0)
+    labels = W.synthetic_labels(B, seed=0)
+    ref = None if os.environ.get("DFM_BENCH_CPU_PORT") else _import_reference()
+    if ref is not None:
+        rcfg, rmodels, rschema = ref
+        rc = rcfg.ExperimentConfig()
+        rc.feature.fm_embed_dim = cfg.feature.fm_embed_dim
+        rc.cin.layer_sizes = list(cfg.cin.layer_sizes)
+        torch.manual_seed(0)
+        model = rmodels.create_model(model_name, _ref_schema(rschema, schema), rc)
+        model.train()
+        bce = torch.nn.BCEWithLogitsLoss()
+
+        def one_step():
+            model.zero_grad(set_to_none=True)
+            loss = bce(model(batch).squeeze(1), labels) + model.get_l2_reg_loss()     # trainer.py:219-229
+            loss.backward()
+        kind = "reference"
+    else:
+        from oracle import torch_port as TP
+        model = TP.PortedModel(model_name, schema, cfg, seed=0)
+
+        def one_step():
+            for p in model.trainable():
+                p.grad = None
+            model.loss(batch, labels).backward()
+        kind = "port"
     times = []
     t_start = time.perf_counter()
     for i in range(warmup + steps):
-        for p in model.trainable():
-            p.grad = None
         t0 = time.perf_counter()
-        loss = model.loss(batch, labels)
-        loss.backward()
+        one_step()
         dt = time.perf_counter() - t0
         if i >= warmup:
             times.append(dt)
@@ -172,20 +244,27 @@ def cpu_reference_run(steps: int, warmup: int, budget_s: float = 240.0):
             break
     ms = 1e3 * sum(times) / len(times)
     rows = sum(f.vocabulary_size for f in schema.fields.values())
-    return {"value": CPU_SAMPLE_BATCH / (ms / 1e3), "ms_per_step": ms, "cores": cores, "steps": len(times),
-            "sample": f"batch {CPU_SAMPLE_BATCH}, tables capped at {CPU_SAMPLE_MAX_VOCAB} rows each ({rows} rows), "
-                      f"{len(times)} timed steps of fwd+loss+L2+backward, torch {torch.__version__} CPU"}
+    return {"value": B / (ms / 1e3), "ms_per_step": ms, "cores": cores, "steps": len(times), "kind": kind,
+            "sample": f"batch {B}, {note} ({rows} rows), {len(times)} timed steps of fwd+loss+L2+backward, "
+                      f"{'unmodified reference modules (baseline/_ref)' if kind == 'reference' else 'torch-CPU port of the reference'}, "
+                      f"torch {torch.__version__} CPU, {cores} threads"}
+
+
+def cfg_batch(workload: str) -> int:
+    return 4096 if workload.endswith("_b4096") else BATCH
 
 
 def run_reference(args, rank: int, n_gpus: int):
     if rank != 0:
         return
-    r = cpu_reference_run(args.steps, args.warmup)
+    r = cpu_reference_run(args.steps, args.warmup, workload=args.workload)
     line = base_line(args, n_gpus)
     line.update({"impl": "reference", "value": r["value"], "ms_per_step": r["ms_per_step"], "steps": r["steps"],
-                 "cpu_baseline": {"value": r["value"], "unit": UNIT, "cores": r["cores"], "kind": "port", "sample": r["sample"]},
+                 "cpu_baseline": {"value": r["value"], "unit": UNIT, "cores": r["cores"], "kind": r["kind"], "sample": r["sample"]},
                  "e2e": {"value": r["value"], "unit": UNIT, "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0},
                  "gpu_launches": 0, "dtype": "f32"})
+    if args.workload != "deepfm_criteo":
+        line["config"] = {"workload": WORKLOADS[args.workload][1].format(B=cfg_batch(args.workload)), "model": WORKLOADS[args.workload][0]}
     emit(line)
 
 
@@ -450,9 +529,9 @@ def run_ours(args, rank: int, local_rank: int, n_gpus: int):
                             "traffic": None, "note": "per-kernel roofline is reported by the N=1 run (unsharded K1)"}
         if k1_ms:
             line["roofline"]["k1_ms"], line["roofline"]["k2_ms"] = k1_ms, k2_ms
-    if n_gpus == 1 and not args.no_cpu_baseline and wl == "deepfm_criteo":
-        r = cpu_reference_run(steps=3, warmup=1, budget_s=60.0)
-        line["cpu_baseline"] = {"value": r["value"], "unit": UNIT, "cores": r["cores"], "kind": "port", "sample": r["sample"]}
+    if n_gpus == 1 and not args.no_cpu_baseline:
+        r = cpu_reference_run(steps=3, warmup=1, budget_s=60.0, workload=wl)
+        line["cpu_baseline"] = {"value": r["value"], "unit": UNIT, "cores": r["cores"], "kind": r["kind"], "sample": r["sample"]}
     emit(line)
     if n_gpus > 1:
         dist.destroy_process_group()

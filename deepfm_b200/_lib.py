@@ -68,6 +68,15 @@ SIGNATURES = {
     "dfm_adam_rows_workspace_bytes": (_sz, []),
     "dfm_rows_sumsq_workspace_bytes": (_sz, []),
     "dfm_rows_sumsq": (C.c_int, [_vp, _i64, _vp, _vp, _vp, _vp, _vp, _sz, _vp]),
+    "dfm_gemm3_workspace_bytes": (_sz, [C.c_int, _i64, _i64, _i64]),
+    "dfm_gemm3": (C.c_int, [C.c_int, _vp, _vp, _vp, _vp, _i64, _i64, _i64, _vp, _sz, _vp]),
+    "dfm_tower_workspace_bytes": (_sz, [_i64, C.c_int]),
+    "dfm_bn_stats": (C.c_int, [_vp, _i64, C.c_int, _f32, _vp, _vp, _vp, _vp, _f32, _vp, _sz, _vp]),
+    "dfm_bn_act_fwd": (C.c_int, [_vp, _i64, C.c_int, C.c_int, C.c_int, _vp, _vp, _vp, _vp, _f32, C.c_uint64, _vp, _vp]),
+    "dfm_bn_act_bwd": (C.c_int, [_vp, _vp, _i64, C.c_int, C.c_int, C.c_int, _vp, _vp, _vp, _vp, _f32, C.c_uint64,
+                                 _vp, _vp, _vp, _vp, _vp, _sz, _vp]),
+    "dfm_head_fwd": (C.c_int, [_vp, _vp, _vp, _i64, C.c_int, _vp, _vp]),
+    "dfm_head_bwd": (C.c_int, [_vp, _vp, _vp, _i64, C.c_int, _vp, _vp, _vp, _vp, _sz, _vp]),
     "dfm_attn_workspace_bytes": (_sz, [_i64, C.c_int, C.c_int, C.c_int, C.c_int]),
     "dfm_attn_fwd": (C.c_int, [_vp, _i64, C.c_int, C.c_int, C.c_int, C.c_int, C.c_int, _pp, _vp, _vp]),
     "dfm_attn_bwd": (C.c_int, [_vp, _vp, _i64, C.c_int, C.c_int, C.c_int, C.c_int, C.c_int, _pp, _vp, _pp,

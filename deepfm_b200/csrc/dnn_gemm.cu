@@ -1,0 +1,366 @@
+// fp32-accurate GEMMs of the DNN tower on the 5th-generation tensor cores (reference:
+// deepfm/models/layers/dnn.py:45-59 -- nn.Linear forward and its two autograd products, ATen mm / addmm).
+//
+// One persistent, warp-specialised tcgen05 kernel computes D[M][N] = sum_k A(m,k) * B(n,k) in "3xTF32": every fp32
+// operand x is split into x_hi (its top 19 bits, a valid tf32 number) and x_lo = x - x_hi (exact in fp32), and
+//     D += A_hi * B_hi + A_hi * B_lo + A_lo * B_hi          (fp32 accumulation in tensor memory)
+// so the dropped term is ~2^-22 relative: the accuracy class of an fp32 SIMT sgemm at 3 tensor-core passes.
+// Operand layouts (no transposed copies anywhere):
+//     mode 0  NT   A [M][K]   B [N][K]     Y  = X  W^T (+ bias)    both K-major
+//     mode 1  NN   A [M][K]   B [K][N]     dX = dY W               A K-major, B MN-major
+//     mode 2  TN   A [K][M]   B [K][N]     dW = dY^T X             both MN-major, split-K with a fixed-order reduce
+// Pipeline per k-block of 32:  warp 0 issues the TMA loads (128-byte-swizzled boxes, mbarrier complete_tx);  warps
+// 2-5 split the landed tiles IN PLACE (raw -> hi), write B_lo to a second shared-memory tile and A_lo straight
+// into tensor memory (tcgen05.st: the A_lo * B_hi product runs in the TS form, which halves its shared-memory
+// reads);  one elected thread of warp 1 issues 12 `tcgen05.mma.cta_group::1.kind::tf32` (M = 128, N = tile, K = 8)
+// and recycles the stage with tcgen05.commit;  warps 6-9 drain one of two TMEM accumulators (tcgen05.ld) into
+// global memory while the next tile's MMAs fill the other.
+#include "tc_common.cuh"
+
+namespace dfm {
+namespace g3 {
+
+constexpr int TM = 128;          // rows of D per tile (UMMA M)
+constexpr int KB = 32;           // reduction elements per stage: 32 tf32 = one 128-byte swizzle row
+constexpr int MAXST = 6;
+constexpr int THREADS = 320;     // warp 0: TMA, warp 1: MMA, warps 2-5: split, warps 6-9: epilogue
+constexpr int A_BYTES = TM * 128;
+
+struct Args {
+    float* D; long long ldd;             // output (or split-K partial base), row stride in floats
+    const float* bias;                   // (N) or null
+    long long M, N, K;
+    int tn;                              // N tile: multiple of 32, <= 192
+    int n_mt, n_nt, n_split;
+    long long k_per_split;               // multiple of KB
+    long long split_stride;              // floats between the partial outputs of consecutive splits
+    int a_mn, b_mn;                      // 1: the operand is MN-major ([K][MN] in memory)
+    int nstage;
+    uint32_t tmem_cols;
+};
+
+// MN-major, 128-byte swizzle (cute::UMMA canonical layout ((8,n),(8,k)):((1,LBO),(8,SBO)) in 16-byte units):
+// 32 MN elements are contiguous (128 B), 8 k-rows of 128 B form one 1024-byte atom, the next 32 MN elements
+// start LBO = 32 k-rows * 128 B = 4096 B further (one TMA box {32 mn, 32 k} per MN atom).
+__device__ __forceinline__ uint64_t make_desc_mn(uint32_t smem_addr) {
+    uint64_t d = 0;
+    d |= (uint64_t)((smem_addr & 0x3FFFFu) >> 4);
+    d |= (uint64_t)(4096 >> 4) << 16;       // leading byte offset: next MN atom
+    d |= (uint64_t)(1024 >> 4) << 32;       // stride byte offset: next group of 8 k
+    d |= (uint64_t)1 << 46;                 // descriptor version (Blackwell)
+    d |= (uint64_t)2 << 61;                 // SWIZZLE_128B
+    return d;
+}
+
+__device__ __forceinline__ float tf32_hi(float x) { return __uint_as_float(__float_as_uint(x) & 0xffffe000u); }
+
+__global__ void __launch_bounds__(THREADS, 1)
+gemm3_kernel(const __grid_constant__ Args a, const __grid_constant__ CUtensorMap mapA, const __grid_constant__ CUtensorMap mapB) {
+    using namespace tc;
+    extern __shared__ unsigned char smem_raw[];
+    unsigned char* smem = smem_raw + ((1024u - (smem_u32(smem_raw) & 1023u)) & 1023u);
+    const int b_bytes = a.tn * 128;
+    const int stage_bytes = A_BYTES + 2 * b_bytes;          // [A raw -> hi][B raw -> hi][B lo]
+    uint64_t* bars = reinterpret_cast<uint64_t*>(smem + (size_t)a.nstage * stage_bytes);
+    uint64_t* full_raw = bars;                 // TMA landed
+    uint64_t* full_split = bars + MAXST;       // hi / lo tiles ready
+    uint64_t* empty = bars + 2 * MAXST;        // MMAs of the stage retired
+    uint64_t* acc_full = bars + 3 * MAXST;     // [2]
+    uint64_t* acc_empty = acc_full + 2;        // [2]
+    uint32_t* tmem_slot = reinterpret_cast<uint32_t*>(acc_empty + 2);
+
+    const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
+    if (threadIdx.x == 0) {
+        for (int s = 0; s < MAXST; ++s) { mbar_init(full_raw + s, 1); mbar_init(full_split + s, 4); mbar_init(empty + s, 1); }
+        for (int i = 0; i < 2; ++i) { mbar_init(acc_full + i, 1); mbar_init(acc_empty + i, 4); }
+        asm volatile("prefetch.tensormap [%0];" ::"l"(reinterpret_cast<uint64_t>(&mapA)) : "memory");
+        asm volatile("prefetch.tensormap [%0];" ::"l"(reinterpret_cast<uint64_t>(&mapB)) : "memory");
+        asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
+    }
+    if (warp == 1) tmem_alloc(tmem_slot, a.tmem_cols);
+    tc_fence_before();
+    __syncthreads();
+    tc_fence_after();
+    const uint32_t tmem_base = *tmem_slot;
+    const uint32_t alo_col0 = (uint32_t)(2 * a.tn);          // TMEM columns of the A_lo ring (32 per stage)
+    const long long n_units = (long long)a.n_mt * a.n_nt * a.n_split;
+
+    auto unit_of = [&](long long u, int& mt, int& nt, int& sp) {
+        nt = (int)(u % a.n_nt);
+        const long long rest = u / a.n_nt;
+        mt = (int)(rest % a.n_mt);
+        sp = (int)(rest / a.n_mt);
+    };
+    auto kblocks = [&](int sp, long long& k0) {
+        k0 = (long long)sp * a.k_per_split;
+        long long k1 = k0 + a.k_per_split;
+        if (k1 > a.K) k1 = a.K;
+        return (int)((k1 - k0 + KB - 1) / KB);
+    };
+
+    if (warp == 0) {
+        // ------------------------------------------------------------------ TMA producer
+        if (lane == 0) {
+            uint32_t s = 0, ph = 0;
+            const uint32_t tx = (uint32_t)(A_BYTES + b_bytes);
+            for (long long u = blockIdx.x; u < n_units; u += gridDim.x) {
+                int mt, nt, sp;
+                unit_of(u, mt, nt, sp);
+                long long k0;
+                const int nkb = kblocks(sp, k0);
+                for (int kb = 0; kb < nkb; ++kb) {
+                    mbar_wait(empty + s, ph ^ 1u);
+                    mbar_arrive_expect_tx(full_raw + s, tx);
+                    unsigned char* sa = smem + (size_t)s * stage_bytes;
+                    unsigned char* sb = sa + A_BYTES;
+                    const int kk = (int)(k0 + (long long)kb * KB);
+                    if (!a.a_mn) tma_load_2d(sa, &mapA, kk, mt * TM, full_raw + s);                   // box {32 k, 128 rows}
+                    else for (int j = 0; j < TM / 32; ++j) tma_load_2d(sa + j * 4096, &mapA, mt * TM + j * 32, kk, full_raw + s);
+                    if (!a.b_mn) tma_load_2d(sb, &mapB, kk, nt * a.tn, full_raw + s);                 // box {32 k, tn rows}
+                    else for (int j = 0; j < a.tn / 32; ++j) tma_load_2d(sb + j * 4096, &mapB, nt * a.tn + j * 32, kk, full_raw + s);
+                    if (++s == (uint32_t)a.nstage) { s = 0; ph ^= 1u; }
+                }
+            }
+        }
+    } else if (warp == 1) {
+        // ------------------------------------------------------------------ MMA issuer (one thread)
+        if (lane == 0) {
+            uint32_t s = 0, ph = 0;
+            const uint32_t idesc = (1u << 4) | (2u << 7) | (2u << 10) | ((uint32_t)(a.tn >> 3) << 17) | ((128u >> 4) << 24);
+            const uint32_t idesc_ss = idesc | ((uint32_t)a.a_mn << 15) | ((uint32_t)a.b_mn << 16);
+            const uint32_t idesc_ts = idesc | ((uint32_t)a.b_mn << 16);
+            const uint64_t adv_a = a.a_mn ? (1024 >> 4) : (32 >> 4);     // descriptor step per K = 8
+            const uint64_t adv_b = a.b_mn ? (1024 >> 4) : (32 >> 4);
+            long long it = 0;
+            for (long long u = blockIdx.x; u < n_units; u += gridDim.x, ++it) {
+                int mt, nt, sp;
+                unit_of(u, mt, nt, sp);
+                long long k0;
+                const int nkb = kblocks(sp, k0);
+                const uint32_t acc = (uint32_t)(it & 1), acc_ph = (uint32_t)((it >> 1) & 1);
+                mbar_wait(acc_empty + acc, acc_ph ^ 1u);                 // the epilogue drained this accumulator
+                tc_fence_after();
+                const uint32_t tacc = tmem_base + acc * (uint32_t)a.tn;
+                for (int kb = 0; kb < nkb; ++kb) {
+                    mbar_wait(full_raw + s, ph);
+                    mbar_wait(full_split + s, ph);
+                    tc_fence_after();
+                    const uint32_t sa = smem_u32(smem + (size_t)s * stage_bytes);
+                    const uint64_t da = a.a_mn ? make_desc_mn(sa) : make_desc(sa);
+                    const uint64_t db = a.b_mn ? make_desc_mn(sa + A_BYTES) : make_desc(sa + A_BYTES);
+                    const uint64_t dbl = a.b_mn ? make_desc_mn(sa + A_BYTES + b_bytes) : make_desc(sa + A_BYTES + b_bytes);
+                    const uint32_t talo = tmem_base + alo_col0 + s * 32;
+#pragma unroll
+                    for (int k = 0; k < KB / 8; ++k) {
+                        umma_tf32(tacc, da + adv_a * k, db + adv_b * k, idesc_ss, (kb | k) ? 1u : 0u);      // hi * hi
+                        umma_tf32(tacc, da + adv_a * k, dbl + adv_b * k, idesc_ss, 1u);                     // hi * lo
+                        umma_tf32_ts(tacc, talo + k * 8, db + adv_b * k, idesc_ts, 1u);                     // lo * hi
+                    }
+                    umma_commit(empty + s);
+                    if (++s == (uint32_t)a.nstage) { s = 0; ph ^= 1u; }
+                }
+                umma_commit(acc_full + acc);
+            }
+        }
+    } else if (warp < 6) {
+        // ------------------------------------------------------------------ splitters: raw -> hi (in place), lo
+        const int q = warp & 3;                         // TMEM lane quarter this warp may access
+        const int r = q * 32 + lane;                    // A row (= TMEM lane)
+        const int tid = threadIdx.x - 64;
+        uint32_t s = 0, ph = 0;
+        for (long long u = blockIdx.x; u < n_units; u += gridDim.x) {
+            int mt, nt, sp;
+            unit_of(u, mt, nt, sp);
+            long long k0;
+            const int nkb = kblocks(sp, k0);
+            for (int kb = 0; kb < nkb; ++kb) {
+                mbar_wait(full_raw + s, ph);
+                unsigned char* sa = smem + (size_t)s * stage_bytes;
+                float lo[32];
+                if (!a.a_mn) {                           // row r: 8 chunks of 4 k, chunk c at ((c ^ (r & 7)) << 4)
+                    unsigned char* rowp = sa + r * 128;
+#pragma unroll
+                    for (int c = 0; c < 8; ++c) {
+                        float4* p = reinterpret_cast<float4*>(rowp + ((c ^ (r & 7)) << 4));
+                        const float4 v = *p;
+                        const float4 h = make_float4(tf32_hi(v.x), tf32_hi(v.y), tf32_hi(v.z), tf32_hi(v.w));
+                        *p = h;
+                        lo[4 * c] = v.x - h.x; lo[4 * c + 1] = v.y - h.y; lo[4 * c + 2] = v.z - h.z; lo[4 * c + 3] = v.w - h.w;
+                    }
+                } else {                                 // element (k, mn = r): atom r / 32, row k, chunk ((r % 32) / 4) ^ (k & 7)
+                    unsigned char* atom = sa + (r >> 5) * 4096 + (r & 3) * 4;
+                    const int ch = (r & 31) >> 2;
+#pragma unroll
+                    for (int k = 0; k < 32; ++k) {
+                        float* p = reinterpret_cast<float*>(atom + k * 128 + ((ch ^ (k & 7)) << 4));
+                        const float v = *p;
+                        const float h = tf32_hi(v);
+                        *p = h;
+                        lo[k] = v - h;
+                    }
+                }
+                tmem_st32(tmem_base + ((uint32_t)(q * 32) << 16) + alo_col0 + s * 32, lo);
+                float4* bh = reinterpret_cast<float4*>(sa + A_BYTES);
+                float4* bl = reinterpret_cast<float4*>(sa + A_BYTES + b_bytes);
+                const int nchunk = b_bytes >> 4;
+                for (int i = tid; i < nchunk; i += 128) {
+                    const float4 v = bh[i];
+                    const float4 h = make_float4(tf32_hi(v.x), tf32_hi(v.y), tf32_hi(v.z), tf32_hi(v.w));
+                    bh[i] = h;
+                    bl[i] = make_float4(v.x - h.x, v.y - h.y, v.z - h.z, v.w - h.w);
+                }
+                fence_proxy_async();                     // generic-proxy writes -> async proxy (UMMA reads)
+                tc_fence_before();                       // tcgen05.st (already waited) ordered before the arrive
+                __syncwarp();
+                if (lane == 0) mbar_arrive(full_split + s);
+                if (++s == (uint32_t)a.nstage) { s = 0; ph ^= 1u; }
+            }
+        }
+    } else {
+        // ------------------------------------------------------------------ epilogue: TMEM -> global
+        const int q = warp & 3;
+        const int r = q * 32 + lane;
+        long long it = 0;
+        const bool vec_ok = (a.ldd & 3) == 0 && (reinterpret_cast<uintptr_t>(a.D) & 15u) == 0 && (a.split_stride & 3) == 0;
+        for (long long u = blockIdx.x; u < n_units; u += gridDim.x, ++it) {
+            int mt, nt, sp;
+            unit_of(u, mt, nt, sp);
+            const uint32_t acc = (uint32_t)(it & 1), acc_ph = (uint32_t)((it >> 1) & 1);
+            mbar_wait(acc_full + acc, acc_ph);
+            tc_fence_after();
+            const long long row = (long long)mt * TM + r;
+            float* out = a.D + (size_t)sp * a.split_stride + (size_t)row * a.ldd;
+            const uint32_t taddr = tmem_base + ((uint32_t)(q * 32) << 16) + acc * (uint32_t)a.tn;
+            for (int c0 = 0; c0 < a.tn; c0 += 32) {
+                float v[32];
+                tmem_ld32(taddr + c0, v);
+                const long long col0 = (long long)nt * a.tn + c0;
+                if (row < a.M && col0 < a.N) {
+                    if (a.bias) {
+#pragma unroll
+                        for (int i = 0; i < 32; ++i) if (col0 + i < a.N) v[i] += __ldg(a.bias + col0 + i);
+                    }
+                    if (vec_ok && col0 + 32 <= a.N) {
+#pragma unroll
+                        for (int i = 0; i < 8; ++i)
+                            *reinterpret_cast<float4*>(out + col0 + 4 * i) = make_float4(v[4 * i], v[4 * i + 1], v[4 * i + 2], v[4 * i + 3]);
+                    } else {
+#pragma unroll
+                        for (int i = 0; i < 32; ++i) if (col0 + i < a.N) out[col0 + i] = v[i];
+                    }
+                }
+            }
+            tc_fence_before();
+            __syncwarp();
+            if (lane == 0) mbar_arrive(acc_empty + acc);
+        }
+    }
+    __syncthreads();
+    if (warp == 1) tmem_dealloc(tmem_base, a.tmem_cols);
+}
+
+// out[i] = sum_s partial[s][i] in split order (+ bias): the deterministic end of a split-K product
+__global__ void __launch_bounds__(256)
+splitk_reduce_kernel(const float* __restrict__ partial, int n_split, long long stride, float* __restrict__ out, long long n) {
+    for (long long i = (long long)blockIdx.x * blockDim.x + threadIdx.x; i < n; i += (long long)gridDim.x * blockDim.x) {
+        float acc = 0.f;
+        for (int s = 0; s < n_split; ++s) acc += __ldcs(partial + (size_t)s * stride + i);
+        out[i] = acc;
+    }
+}
+
+struct Plan {
+    int tn, n_mt, n_nt, n_split, nstage;
+    long long k_per_split;
+    size_t smem, ws_bytes;
+    uint32_t tmem_cols;
+};
+
+static int make_plan(int mode, long long M, long long N, long long K, Plan& p) {
+    DFM_REQUIRE(mode >= 0 && mode <= 2 && M > 0 && N > 0 && K > 0, DFM_ERR_INVALID, "dfm_gemm3: bad mode / shape");
+    DFM_REQUIRE(M < (1LL << 31) && N < (1LL << 31) && K < (1LL << 31), DFM_ERR_UNSUPPORTED, "dfm_gemm3: dimension too large");
+    // TMA needs 16-byte global strides: the contiguous extent of each operand must be a multiple of 4 floats
+    const long long a_inner = mode == 2 ? M : K, b_inner = mode == 0 ? K : N;
+    DFM_REQUIRE(a_inner % 4 == 0 && b_inner % 4 == 0, DFM_ERR_UNSUPPORTED,
+                "dfm_gemm3: contiguous extents (%lld, %lld) must be multiples of 4", a_inner, b_inner);
+    p.n_nt = (int)ceil_div(N, 192);
+    p.tn = (int)(ceil_div(ceil_div(N, p.n_nt), 32) * 32);
+    p.n_mt = (int)ceil_div(M, TM);
+    p.n_split = 1;
+    if (mode == 2) {
+        const long long base = (long long)p.n_mt * p.n_nt;
+        long long want = ceil_div(2LL * sm_count(), base);
+        const long long max_split = ceil_div(K, 8LL * KB);            // at least 8 k-blocks per split
+        if (want > max_split) want = max_split;
+        if (want < 1) want = 1;
+        p.n_split = (int)want;
+    }
+    p.k_per_split = ceil_div(ceil_div(K, p.n_split), KB) * KB;
+    p.n_split = (int)ceil_div(K, p.k_per_split);
+    const int stage_bytes = A_BYTES + 2 * p.tn * 128;
+    const size_t fixed = (3 * MAXST + 4) * 8 + 16 + 1024;
+    p.nstage = MAXST;
+    while (p.nstage > 2 && ((size_t)p.nstage * stage_bytes + fixed > 227 * 1024 || 2 * p.tn + p.nstage * 32 > 512)) --p.nstage;
+    p.smem = (size_t)p.nstage * stage_bytes + fixed;
+    uint32_t cols = 32;
+    while (cols < (uint32_t)(2 * p.tn + p.nstage * 32)) cols <<= 1;
+    p.tmem_cols = cols;
+    p.ws_bytes = p.n_split > 1 ? (size_t)p.n_split * M * N * 4 : 0;
+    return DFM_OK;
+}
+
+}  // namespace g3
+}  // namespace dfm
+
+using namespace dfm;
+
+extern "C" {
+
+size_t dfm_gemm3_workspace_bytes(int mode, int64_t M, int64_t N, int64_t K) {
+    g3::Plan p;
+    if (g3::make_plan(mode, M, N, K, p) != DFM_OK) return 0;
+    return p.ws_bytes + 256;
+}
+
+int dfm_gemm3(int mode, const float* A, const float* B, float* D, const float* bias, int64_t M, int64_t N, int64_t K,
+              void* workspace, size_t workspace_bytes, void* stream) {
+    using namespace g3;
+    DFM_REQUIRE(A && B && D, DFM_ERR_INVALID, "dfm_gemm3: null operand");
+    Plan p;
+    int rc = make_plan(mode, M, N, K, p);
+    if (rc) return rc;
+    DFM_REQUIRE(((reinterpret_cast<uintptr_t>(A) | reinterpret_cast<uintptr_t>(B)) & 15u) == 0, DFM_ERR_UNSUPPORTED,
+                "dfm_gemm3: operands must be 16-byte aligned");
+    DFM_REQUIRE(p.n_split == 1 || (workspace && workspace_bytes >= p.ws_bytes), DFM_ERR_WORKSPACE,
+                "dfm_gemm3: workspace %zu < %zu", workspace_bytes, p.ws_bytes);
+    DFM_REQUIRE(p.n_split == 1 || !bias, DFM_ERR_UNSUPPORTED, "dfm_gemm3: bias with split-K is not supported");
+    cudaStream_t st = static_cast<cudaStream_t>(stream);
+    Args a;
+    memset(&a, 0, sizeof(a));
+    a.M = M; a.N = N; a.K = K; a.tn = p.tn; a.n_mt = p.n_mt; a.n_nt = p.n_nt; a.n_split = p.n_split;
+    a.k_per_split = p.k_per_split; a.nstage = p.nstage; a.tmem_cols = p.tmem_cols;
+    a.a_mn = mode == 2 ? 1 : 0; a.b_mn = mode == 0 ? 0 : 1;
+    a.bias = bias;
+    if (p.n_split > 1) { a.D = static_cast<float*>(workspace); a.ldd = N; a.split_stride = M * N; }
+    else { a.D = D; a.ldd = N; a.split_stride = 0; }
+    CUtensorMap mapA, mapB;
+    // K-major operand [rows][K]: box {32 k, rows};  MN-major operand [K][MN]: box {32 mn, 32 k}
+    rc = a.a_mn ? tc::make_tmap_2d(&mapA, A, K, M, 32) : tc::make_tmap_2d(&mapA, A, M, K, TM);
+    if (rc) return rc;
+    rc = a.b_mn ? tc::make_tmap_2d(&mapB, B, K, N, 32) : tc::make_tmap_2d(&mapB, B, N, K, p.tn);
+    if (rc) return rc;
+    DFM_CHECK_CUDA(cudaFuncSetAttribute(gemm3_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)p.smem));
+    long long grid = (long long)p.n_mt * p.n_nt * p.n_split;
+    if (grid > sm_count()) grid = sm_count();
+    gemm3_kernel<<<(unsigned)grid, THREADS, p.smem, st>>>(a, mapA, mapB);
+    if (p.n_split > 1) {
+        const long long n = M * N;
+        long long blocks = ceil_div(n, 256);
+        if (blocks > 4LL * sm_count()) blocks = 4LL * sm_count();
+        splitk_reduce_kernel<<<(unsigned)blocks, 256, 0, st>>>(static_cast<const float*>(workspace), p.n_split, M * N, D, n);
+    }
+    DFM_CHECK_LAUNCH();
+    return DFM_OK;
+}
+
+}  // extern "C"

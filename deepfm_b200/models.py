@@ -15,7 +15,7 @@ from typing import Dict, Type
 import torch
 import torch.nn as nn
 
-from .layers.dnn import DNN
+from .layers.dnn import DNN, linear_head
 from .layers.embedding import FeatureEmbedding
 from .layers.fm import FMInteraction
 from .layers.l2 import l2_penalty, prefetch_l2
@@ -73,7 +73,7 @@ class DeepFM(BaseCTRModel):
         self.output_linear = nn.Linear(self.dnn.output_dim, 1)
 
     def _forward_components(self, first_order, field_embeddings, flat_embeddings):
-        return first_order + self.fm(field_embeddings) + self.output_linear(self.dnn(flat_embeddings))
+        return first_order + self.fm(field_embeddings) + linear_head(self.output_linear, self.dnn(flat_embeddings))
 
 
 class xDeepFM(BaseCTRModel):
@@ -88,8 +88,8 @@ class xDeepFM(BaseCTRModel):
         self.dnn_linear = nn.Linear(self.dnn.output_dim, 1)
 
     def _forward_components(self, first_order, field_embeddings, flat_embeddings):
-        return (first_order + self.cin_linear(self.cin(field_embeddings))
-                + self.dnn_linear(self.dnn(flat_embeddings)))
+        return (first_order + linear_head(self.cin_linear, self.cin(field_embeddings))
+                + linear_head(self.dnn_linear, self.dnn(flat_embeddings)))
 
 
 class AttentionDeepFM(BaseCTRModel):
@@ -110,7 +110,7 @@ class AttentionDeepFM(BaseCTRModel):
         fm_out = self.fm(field_embeddings)
         refined = self.attention(field_embeddings)
         tower_in = torch.cat([refined.reshape(refined.size(0), -1), flat_embeddings], dim=1)
-        return first_order + fm_out + self.output_linear(self.dnn(tower_in))
+        return first_order + fm_out + linear_head(self.output_linear, self.dnn(tower_in))
 
 
 MODEL_REGISTRY: Dict[str, Type[BaseCTRModel]] = {

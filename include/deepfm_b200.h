@@ -308,6 +308,43 @@ DFM_API int dfm_rows_sumsq(const dfm_plan* plan, int64_t n_sorted, const uint32_
                            const float* row_grad2, const float* row_grad1, float* out, void* workspace,
                            size_t workspace_bytes, void* stream);
 
+/* ------------------------------------------------------------------------------------------
+ * DNN tower (reference deepfm/models/layers/dnn.py:45-59: Linear -> BatchNorm1d ->
+ * activation -> Dropout, and the head nn.Linear(., 1) of deepfm.py:36-42 / xdeepfm.py:42-48).
+ *   dfm_gemm3: fp32-accurate GEMM on tcgen05 ("3xTF32": hi*hi + hi*lo + lo*hi of the tf32 split of both
+ *       operands, fp32 accumulation in tensor memory; operands by TMA, no transposed copies):
+ *         mode 0  D[M][N] = A[M][K] * B[N][K]^T (+ bias[N])     nn.Linear forward       (ATen addmm)
+ *         mode 1  D[M][N] = A[M][K] * B[K][N]                   grad wrt the input       (ATen mm)
+ *         mode 2  D[M][N] = A[K][M]^T * B[K][N]                 grad wrt the weight      (ATen mm), split-K with a
+ *                 fixed-order reduction: workspace >= dfm_gemm3_workspace_bytes().
+ *       The contiguous extent of each operand must be a multiple of 4 floats and 16-byte aligned
+ *       (DFM_ERR_UNSUPPORTED otherwise).
+ *   dfm_bn_stats: training-mode BatchNorm1d statistics of y (M, C): mean, rstd = 1/sqrt(biased var + eps);
+ *       running_mean / running_var (optional) get the momentum update with the unbiased variance.
+ *   dfm_bn_act_fwd: out = dropout(act(gamma * (y - mean) * rstd + beta)); bn 0 = none, 1 = batch statistics,
+ *       2 = fixed (running) statistics; act 0 relu, 1 leaky_relu(0.01), 2 gelu (erf), 3 tanh (dnn.py:20-25);
+ *       the dropout mask is a counter-based function of (seed, element index), regenerated by the backward.
+ *   dfm_bn_act_bwd: dy from da (z, xhat and the mask recomputed from y); dgamma, dbeta (BatchNorm affine grads),
+ *       dbias (optional: column sums of dy, the Linear bias gradient).  workspace >= dfm_tower_workspace_bytes(M, C).
+ *   dfm_head_fwd / dfm_head_bwd: out[m] = a[m, :] . w + b;  da (optional), dw (C), db (1).
+ * All reductions are fixed-order with fp64 partials: deterministic.
+ * ---------------------------------------------------------------------------------------- */
+DFM_API size_t dfm_gemm3_workspace_bytes(int mode, int64_t M, int64_t N, int64_t K);
+DFM_API int dfm_gemm3(int mode, const float* A, const float* B, float* D, const float* bias, int64_t M, int64_t N,
+                      int64_t K, void* workspace, size_t workspace_bytes, void* stream);
+DFM_API size_t dfm_tower_workspace_bytes(int64_t M, int C);
+DFM_API int dfm_bn_stats(const float* y, int64_t M, int C, float eps, float* mean, float* rstd, float* running_mean,
+                         float* running_var, float momentum, void* workspace, size_t workspace_bytes, void* stream);
+DFM_API int dfm_bn_act_fwd(const float* y, int64_t M, int C, int bn, int act, const float* mean, const float* rstd,
+                           const float* gamma, const float* beta, float drop_p, uint64_t seed, float* out, void* stream);
+DFM_API int dfm_bn_act_bwd(const float* da, const float* y, int64_t M, int C, int bn, int act, const float* mean,
+                           const float* rstd, const float* gamma, const float* beta, float drop_p, uint64_t seed,
+                           float* dy, float* dgamma, float* dbeta, float* dbias, void* workspace,
+                           size_t workspace_bytes, void* stream);
+DFM_API int dfm_head_fwd(const float* a, const float* w, const float* b, int64_t M, int C, float* out, void* stream);
+DFM_API int dfm_head_bwd(const float* a, const float* w, const float* g, int64_t M, int C, float* da, float* dw, float* db,
+                         void* workspace, size_t workspace_bytes, void* stream);
+
 #ifdef __cplusplus
 }
 #endif

@@ -1,0 +1,8 @@
+#!/bin/bash
+# usage: scripts/gpurun_retry.sh <timeout> [--gpus N] -- '<command>'   (retries while the pod answers "busy")
+for i in $(seq 1 30); do
+  out=$(/usr/local/graft/bin/gpurun --timeout "$@" 2>&1)
+  if echo "$out" | grep -q "status=transient"; then sleep 90; continue; fi
+  echo "$out"; exit 0
+done
+echo "$out"; echo "gave up after 30 tries"
