@@ -62,8 +62,16 @@ SIGNATURES = {
     "dfm_plan_set_table_stride": (C.c_int, [_vp, C.c_int, C.c_int]),
     "dfm_plan_set_field_source": (C.c_int, [_vp, C.c_int, C.c_int, C.c_int, C.c_int]),
     "dfm_rows_bwd_workspace_bytes": (_sz, [_vp, _i64]),
-    "dfm_rows_bwd": (C.c_int, [_vp, _i64, _pp, _vp, _vp, _f32, _vp, C.c_int, _pp, _vp, _vp, _vp, _vp, _vp,
+    "dfm_rows_bwd": (C.c_int, [_vp, _i64, _pp, _vp, _vp, _vp, _f32, _vp, C.c_int, _pp, _vp, _vp, _vp, _vp, _vp,
                                _vp, _sz, _vp]),
+    "dfm_shard_ukeys": (C.c_int, [_vp, C.c_int, _pi64, _pi64, C.c_int, _i64, _pp, _vp, _vp, _vp, _vp, _vp]),
+    "dfm_sort_pairs_workspace_bytes": (_sz, [_i64, C.c_int]),
+    "dfm_sort_pairs": (C.c_int, [_i64, C.c_int, _vp, _vp, _vp, _vp, _vp, _sz, _vp]),
+    "dfm_shard_unique_workspace_bytes": (_sz, [_i64]),
+    "dfm_shard_unique": (C.c_int, [_vp, C.c_int, C.c_int, _i64, _i64, _vp, _vp, _vp, _vp, _vp, _vp, _vp, _sz, _vp]),
+    "dfm_shard_gather2": (C.c_int, [_vp, C.c_int, C.c_int, _i64, _vp, _pp, C.c_int, _pi64, _pp, _pp, _vp, _vp]),
+    "dfm_shard_bwd_peer": (C.c_int, [_vp, _i64, _vp, _vp, _vp, _vp, _vp, _vp, _vp, _vp, _vp, _vp, _i64, C.c_uint32, C.c_int,
+                                     _pi64, _pp, _pp, _f32, _vp, _sz, _vp]),
     "dfm_adam_rows": (C.c_int, [_vp, _i64, _vp, _vp, _vp, _pp, _pp, _pp, _f32, _f32, _f32, _f32, _i64, _vp, _vp, _vp, _sz, _vp]),
     "dfm_adam_rows_workspace_bytes": (_sz, []),
     "dfm_rows_sumsq_workspace_bytes": (_sz, []),

@@ -57,7 +57,30 @@ struct BwdArgs {
     unsigned* open_list;           // those units (order irrelevant: one writer per segment)
     unsigned* long_count;          // segments spanning more than LONG_SPAN units: (owner unit, last unit) pairs
     unsigned* long_list;
+    const float* g_sc;             // direct mode, split layout: g_flat = (M, tdim) vectors, g_sc = (M, 4) [g_first, g_fm, 0, 0]
+    unsigned pad_key;              // PAD key of the sorted stream (normally the plan's; owner-major keys have their own)
+    // peer output (row-sharded tables, sample side): the finished segment sums are not table gradients but rows of the
+    // gradient EXCHANGE -- segment u (its ordinal among the segment heads, uidx[head position]) belongs to the owner
+    // whose range [peer_start[o], peer_start[o + 1]) contains u and is stored straight into that GPU's buffers
+    // (NVLink peer stores): vector at peer_vec[o] + (u - start) * tdim, scalars [sum g_first, sum g_fm, 0, 0] at
+    // peer_sc[o] + (u - start) * 4, everything times peer_scale.  No table row is read, no L2 term added (the owner does).
+    int peer_n;
+    long long peer_start[17];
+    float* peer_vec[16];
+    float* peer_sc[16];
+    const uint32_t* uidx;
+    float peer_scale;
 };
+
+// destination of exchange row u (peer output mode)
+__device__ __forceinline__ void peer_dst(const BwdArgs& a, long long u, int tdim, float*& vec, float*& sc) {
+    int o = 0;
+#pragma unroll 1
+    for (int q = 1; q < a.peer_n; ++q) if (u >= a.peer_start[q]) o = q;
+    const long long r = u - a.peer_start[o];
+    vec = a.peer_vec[o] + (size_t)r * tdim;
+    sc = a.peer_sc[o] + (size_t)r * 4;
+}
 
 // payload of key position i = b*S + slot:  (b << bits) | slot   (decoded with a shift and a mask)
 __global__ void payload_kernel(uint32_t* p, long long n, int S, int bits) {
@@ -176,6 +199,18 @@ __device__ __forceinline__ void write_row(const DevPlan& P, const DevGrads& GR, 
                                           const FieldB& fb, uint32_t key, int f, long long head_pos, int j,
                                           const VecF<V>& acc, float acc1, float gs,
                                           bool have_pre = false, VecF<V> wpre = VecF<V>(), float w1pre = 0.f) {
+    if (a.peer_n > 0) {     // exchange row instead of a table gradient (see BwdArgs)
+        float *pv, *ps;
+        peer_dst(a, (long long)__ldg(a.uidx + head_pos), P.max_tdim, pv, ps);
+        if (j < P.max_tdim / V) {
+            VecF<V> out = acc;
+#pragma unroll
+            for (int v = 0; v < V; ++v) out.v[v] *= a.peer_scale;
+            vstore<V>(pv + j * V, out);
+        }
+        if (j == 0) *reinterpret_cast<float4*>(ps) = make_float4(acc1 * a.peer_scale, gs * a.peer_scale, 0.f, 0.f);
+        return;
+    }
     const long long row = (long long)(key - fb.row_base);
     if (j < fb.dim / V) {   // table dims are <= G * V (checked on the host)
         VecF<V> out = acc;
@@ -773,6 +808,16 @@ __device__ __forceinline__ void seg2_close(const DevPlan& P, const DevGrads& GR,
         if (lane == 0) { a.head1[unit_idx] = st.a1; a.headg[unit_idx] = st.gs; }
         return;
     }
+    if (a.peer_n > 0) {
+        float *pv, *ps;
+        peer_dst(a, (long long)__ldg(a.uidx + st.seg_start), tdim, pv, ps);
+        float o[VW];
+#pragma unroll
+        for (int v = 0; v < VW; ++v) o[v] = st.acc[v] * a.peer_scale;
+        lv_store<VW>(pv + lane * VW, o);
+        if (lane == 0) *reinterpret_cast<float4*>(ps) = make_float4(st.a1 * a.peer_scale, st.gs * a.peer_scale, 0.f, 0.f);
+        return;
+    }
     const FieldB& fb = t_field[st.f];
     const size_t row = (size_t)(st.cur - fb.row_base);
     float out[VW];
@@ -807,13 +852,13 @@ seg2_kernel(const __grid_constant__ DevPlan P, const __grid_constant__ DevGrads 
     const long long unit_idx = (long long)blockIdx.x * (blockDim.x >> 5) + (threadIdx.x >> 5);
     const long long p_lo = unit_idx * unit;
     const long long p_hi = (p_lo + unit < a.N) ? p_lo + unit : a.N;
-    const uint32_t PAD = P.pad_key;
+    const uint32_t PAD = a.pad_key;
     const int bits = a.slot_bits;
     const uint32_t smask = (1u << bits) - 1u;
-    const float coef = a.l2x2 * (a.l2_gscale ? __ldg(a.l2_gscale) : 1.f);
+    const float coef = a.peer_n > 0 ? 0.f : a.l2x2 * (a.l2_gscale ? __ldg(a.l2_gscale) : 1.f);
     const bool fm_rt = HAS_FM && !DIRECT && a.g_fm != nullptr;   // bag variants are compiled with HAS_FM and decide here
     const bool fm_on = DIRECT || fm_rt;
-    const bool need_w = fm_on || coef != 0.f;
+    const bool need_w = a.peer_n == 0 && (fm_on || coef != 0.f);
     const int tdim = P.max_tdim, D = P.D, T = P.T;
     int n_valid = 0, n_heads = 0;
 
@@ -839,9 +884,15 @@ seg2_kernel(const __grid_constant__ DevPlan P, const __grid_constant__ DevGrads 
             if (key != PAD) {
                 if (DIRECT) {
                     fl = field_of_key(t_field, P.n_fields, key);
-                    goff = pay * (unsigned)a.row_stride;
-                    o = __ldg(a.g_flat + goff + tdim);          // packed first-order gradient
-                    m = __ldg(a.g_flat + goff + tdim + 1);      // packed g_fm (for -(sum g_fm) w)
+                    if (a.g_sc) {                               // split layout: (M, tdim) vectors + (M, 4) scalars
+                        goff = pay * (unsigned)tdim;
+                        const float2 sc = __ldg(reinterpret_cast<const float2*>(a.g_sc) + 2 * (size_t)pay);
+                        o = sc.x; m = sc.y;
+                    } else {
+                        goff = pay * (unsigned)a.row_stride;
+                        o = __ldg(a.g_flat + goff + tdim);      // packed first-order gradient
+                        m = __ldg(a.g_flat + goff + tdim + 1);  // packed g_fm (for -(sum g_fm) w)
+                    }
                 } else {
                     const uint32_t b = pay >> bits;
                     fl = s_slotf[pay & smask];
@@ -1346,6 +1397,8 @@ static int embed_bwd_impl(const dfm_plan* plan, int64_t batch, long long direct_
     a.tail_field = reinterpret_cast<int*>(ws + L.off_tfield);
     a.direct = direct ? 1 : 0;
     a.row_stride = plan->max_tdim + 4;
+    a.pad_key = (unsigned)plan->total_rows;
+    if (direct && g_first) { a.g_sc = g_first; a.g_first = nullptr; }    // split layout of the exchanged rows (dfm_rows_bwd)
     a.counters = n_valid ? reinterpret_cast<unsigned long long*>(n_valid)
                          : reinterpret_cast<unsigned long long*>(ws + L.off_counters);
     a.open_count = reinterpret_cast<unsigned*>(ws + L.off_open);
@@ -1391,6 +1444,8 @@ static int embed_bwd_impl(const dfm_plan* plan, int64_t batch, long long direct_
                     (plan->fm_dim == 32 || plan->fm_dim == 64 || plan->fm_dim == 128) && (direct || (g_flat && plan->aliasable)) &&
                     (direct ? N * (long long)a.row_stride : (long long)batch * plan->T) < 0x7fffffffLL &&
                     getenv("DFM_K2_LEGACY") == nullptr;
+        DFM_REQUIRE(fast || !(direct && a.g_sc), DFM_ERR_UNSUPPORTED,
+                    "dfm_rows_bwd: the split (vector, scalar) row layout needs embedding_dim == fm_embed_dim in {32, 64, 128}");
         if (fast) {
             const int vw = plan->fm_dim / 32;
             const long long warps_max = 32LL * sm_count();            // 4 blocks of 8 warps per SM
@@ -1506,6 +1561,28 @@ int dfm_embed_bwd(const dfm_plan* plan, int64_t batch, const void* const* inputs
                           workspace, workspace_bytes, stream);
 }
 
+size_t dfm_sort_pairs_workspace_bytes(int64_t n, int bits) {
+    if (n <= 0) return 16;
+    size_t bytes = 0;
+    if (sort_temp_bytes(n, bits, &bytes) != DFM_OK) return 0;
+    return align_up(bytes, 256);
+}
+
+// stable LSB radix sort of (key, payload) pairs on the low `bits` bits of the key (CUB DeviceRadixSort)
+int dfm_sort_pairs(int64_t n, int bits, const uint32_t* keys, const uint32_t* payload, uint32_t* sorted_keys,
+                   uint32_t* sorted_payload, void* workspace, size_t workspace_bytes, void* stream) {
+    DFM_REQUIRE(n >= 0 && bits >= 1 && bits <= 32, DFM_ERR_INVALID, "dfm_sort_pairs: bad argument");
+    if (n == 0) return DFM_OK;
+    DFM_REQUIRE(keys && payload && sorted_keys && sorted_payload && workspace && n < 0x7fffffffLL, DFM_ERR_INVALID, "dfm_sort_pairs: null tensor");
+    size_t bytes = 0;
+    int rc = sort_temp_bytes(n, bits, &bytes);
+    if (rc) return rc;
+    DFM_REQUIRE(workspace_bytes >= bytes, DFM_ERR_WORKSPACE, "dfm_sort_pairs: workspace %zu < %zu", workspace_bytes, bytes);
+    DFM_CHECK_CUDA(cub::DeviceRadixSort::SortPairs(workspace, bytes, keys, sorted_keys, payload, sorted_payload, (int)n, 0, bits,
+                                                   static_cast<cudaStream_t>(stream)));
+    return DFM_OK;
+}
+
 size_t dfm_rows_bwd_workspace_bytes(const dfm_plan* plan, int64_t n_rows) {
     if (!plan || n_rows < 0) return 0;
     BwdLayout L;
@@ -1514,14 +1591,104 @@ size_t dfm_rows_bwd_workspace_bytes(const dfm_plan* plan, int64_t n_rows) {
 }
 
 int dfm_rows_bwd(const dfm_plan* plan, int64_t n_rows, const float* const* params, const uint32_t* keys,
-                 const float* g_rows, float l2, const float* l2_gscale, int mode,
+                 const float* g_rows, const float* g_scalars, float l2, const float* l2_gscale, int mode,
                  float* const* grads, uint32_t* sorted_keys, uint32_t* sorted_payload, float* row_grad2,
                  float* row_grad1, int64_t* n_valid, void* workspace, size_t workspace_bytes, void* stream) {
     DFM_REQUIRE(n_rows >= 0, DFM_ERR_INVALID, "dfm_rows_bwd: negative row count");
-    DFM_REQUIRE(n_rows == 0 || (keys && g_rows), DFM_ERR_INVALID, "dfm_rows_bwd: null argument");
-    return embed_bwd_impl(plan, 0, n_rows, nullptr, params, nullptr, nullptr, g_rows, nullptr, nullptr, nullptr, nullptr, keys,
+    DFM_REQUIRE(n_rows == 0 || ((keys || (mode & DFM_GRAD_PRESORTED)) && g_rows), DFM_ERR_INVALID, "dfm_rows_bwd: null argument");
+    // split layout (g_scalars != NULL): g_rows is (n, tdim) and g_scalars (n, 4); it is carried in the g_first slot
+    return embed_bwd_impl(plan, 0, n_rows, nullptr, params, g_scalars, nullptr, g_rows, nullptr, nullptr, nullptr, nullptr, keys,
                           nullptr, l2, l2_gscale, mode, grads, sorted_keys, sorted_payload, row_grad2, row_grad1, n_valid,
                           workspace, workspace_bytes, stream);
+}
+
+// Sample side of the row-sharded backward: segmented reduction of the batch's gradient rows per UNIQUE (owner, row)
+// key, in the fixed sorted order, with the finished sums stored straight into the owners' exchange buffers.
+int dfm_shard_bwd_peer(const dfm_plan* plan, int64_t batch, const float* g_first, const float* g_field, const float* g_flat,
+                       const float* g_fm, const float* field_emb, const float* fm_sum, const uint32_t* aux,
+                       const uint32_t* sorted_keys, const uint32_t* sorted_payload, const uint32_t* uidx, int64_t n_sorted,
+                       uint32_t pad_key, int n_peers, const int64_t* peer_start, float* const* peer_vec, float* const* peer_sc,
+                       float grad_scale, void* workspace, size_t workspace_bytes, void* stream) {
+    DFM_REQUIRE(plan && batch >= 0 && n_sorted >= 0, DFM_ERR_INVALID, "dfm_shard_bwd_peer: bad argument");
+    if (batch == 0 || n_sorted == 0) return DFM_OK;
+    DFM_REQUIRE(g_flat && sorted_keys && sorted_payload && uidx && workspace && peer_start && peer_vec && peer_sc, DFM_ERR_INVALID,
+                "dfm_shard_bwd_peer: null tensor");
+    DFM_REQUIRE(n_peers >= 1 && n_peers <= 16, DFM_ERR_INVALID, "dfm_shard_bwd_peer: 1..16 peers");
+    DFM_REQUIRE(!g_fm || (fm_sum && field_emb), DFM_ERR_INVALID, "dfm_shard_bwd_peer: g_fm needs fm_sum and field_emb");
+    const int D = plan->fm_dim;
+    bool ok = plan->aliasable && plan->max_tdim == D && (D == 32 || D == 64 || D == 128) && plan->vec == 4;
+    bool any_bag = false;
+    for (int f = 0; f < plan->n_fields; ++f) {
+        ok = ok && plan->dim[f] == D;
+        if (plan->kind[f] == DFM_SEQUENCE && plan->foreign[f]) {
+            ok = ok && plan->combiner[f] != DFM_MAX;
+            any_bag = true;
+        }
+    }
+    DFM_REQUIRE(ok, DFM_ERR_UNSUPPORTED, "dfm_shard_bwd_peer: needs every embedding_dim == fm_embed_dim in {32, 64, 128} and sum / mean bags");
+    DFM_REQUIRE((long long)batch * plan->T < 0x7fffffffLL && n_sorted < 0x7fffffffLL, DFM_ERR_UNSUPPORTED, "dfm_shard_bwd_peer: batch too large");
+    DFM_REQUIRE(!any_bag || !g_fm || field_emb, DFM_ERR_INVALID, "dfm_shard_bwd_peer: bag fields need the field embeddings");
+    DFM_REQUIRE(plan->A == 0 || aux, DFM_ERR_INVALID, "dfm_shard_bwd_peer: aux record required");
+    auto al16 = [](const void* q) { return (reinterpret_cast<uintptr_t>(q) & 15u) == 0; };
+    DFM_REQUIRE(al16(g_flat) && al16(g_field) && al16(fm_sum) && al16(field_emb), DFM_ERR_UNSUPPORTED, "dfm_shard_bwd_peer: unaligned tensor");
+    BwdLayout L;
+    int rc = make_layout(plan, 0, L, n_sorted);
+    if (rc) return rc;
+    DFM_REQUIRE(workspace_bytes >= L.total, DFM_ERR_WORKSPACE, "dfm_shard_bwd_peer: workspace %zu < %zu", workspace_bytes, L.total);
+    cudaStream_t st = static_cast<cudaStream_t>(stream);
+    char* ws = static_cast<char*>(workspace);
+    DevPlan* P = new DevPlan;
+    DevGrads* GR = new DevGrads;
+    struct Guard { DevPlan* p; DevGrads* g; ~Guard() { delete p; delete g; } } guard{P, GR};
+    std::vector<const float*> dummy(5 * plan->n_fields, nullptr);
+    plan->fill(*P, nullptr, dummy.data(), false);
+    P->aliased = 1;
+    memset(GR, 0, sizeof(*GR));
+    BwdArgs a;
+    memset(&a, 0, sizeof(a));
+    a.g_first = g_first; a.g_field = g_field; a.g_flat = g_flat; a.g_fm = g_fm; a.fe = field_emb; a.fm_sum = fm_sum; a.aux = aux;
+    a.mode = DFM_GRAD_ROWSPARSE; a.B = batch; a.N = n_sorted;
+    a.skeys = sorted_keys; a.spay = sorted_payload;
+    a.head2 = reinterpret_cast<float*>(ws + L.off_head2); a.head1 = reinterpret_cast<float*>(ws + L.off_head1);
+    a.tail2 = reinterpret_cast<float*>(ws + L.off_tail2); a.tail1 = reinterpret_cast<float*>(ws + L.off_tail1);
+    a.tail_start = reinterpret_cast<long long*>(ws + L.off_tstart);
+    a.headg = reinterpret_cast<float*>(ws + L.off_headg); a.tailg = reinterpret_cast<float*>(ws + L.off_tailg);
+    a.tail_field = reinterpret_cast<int*>(ws + L.off_tfield);
+    a.slot_bits = slot_bits_of(plan->S);
+    a.counters = reinterpret_cast<unsigned long long*>(ws + L.off_counters);
+    a.open_count = reinterpret_cast<unsigned*>(ws + L.off_open); a.open_list = a.open_count + 1;
+    a.long_count = reinterpret_cast<unsigned*>(ws + L.off_long); a.long_list = a.long_count + 2;
+    a.pad_key = pad_key;
+    a.peer_n = n_peers; a.uidx = uidx; a.peer_scale = grad_scale;
+    for (int q = 0; q < n_peers; ++q) {
+        DFM_REQUIRE(peer_vec[q] && peer_sc[q] && al16(peer_vec[q]) && al16(peer_sc[q]) && peer_start[q] <= peer_start[q + 1], DFM_ERR_INVALID,
+                    "dfm_shard_bwd_peer: peer %d has a null / unaligned buffer or a negative range", q);
+        a.peer_start[q] = peer_start[q]; a.peer_vec[q] = peer_vec[q]; a.peer_sc[q] = peer_sc[q];
+    }
+    a.peer_start[n_peers] = peer_start[n_peers];
+    DFM_CHECK_CUDA(cudaMemsetAsync(a.counters, 0, 16, st));
+    DFM_CHECK_CUDA(cudaMemsetAsync(a.open_count, 0, 4, st));
+    DFM_CHECK_CUDA(cudaMemsetAsync(a.long_count, 0, 4, st));
+    const long long N = n_sorted;
+    const long long warps_max = 32LL * sm_count();
+    long long unit = ceil_div(ceil_div(N, warps_max), 32) * 32;
+    if (unit < 256) unit = 256;
+    const unsigned blocks = (unsigned)ceil_div(ceil_div(N, unit), 8);
+    const bool hf = g_fm != nullptr, hg = g_field != nullptr;
+    const int vw = D / 32;
+    if (vw == 1) launch_seg2<1>(false, hf, hg, any_bag, blocks, st, *P, *GR, a, unit);
+    else if (vw == 2) launch_seg2<2>(false, hf, hg, any_bag, blocks, st, *P, *GR, a, unit);
+    else launch_seg2<4>(false, hf, hg, any_bag, blocks, st, *P, *GR, a, unit);
+    const int G = next_pow2(D / 4), gpb = 256 / G;
+    const long long n_units = ceil_div(N, unit);
+    const long long want = ceil_div(n_units, gpb);
+    const unsigned sblocks = (unsigned)(want < 4LL * sm_count() ? want : 4LL * sm_count());
+    const unsigned lblocks = (unsigned)(n_units < 2LL * sm_count() ? n_units : 2LL * sm_count());
+    const size_t ssm = (size_t)gpb * (D + 2) * 4;
+    stitch_kernel<4><<<sblocks, 256, 0, st>>>(*P, *GR, a, G, unit);
+    stitch_long_kernel<4><<<lblocks, 256, ssm, st>>>(*P, *GR, a, G, unit);
+    DFM_CHECK_LAUNCH();
+    return DFM_OK;
 }
 
 }  // extern "C"

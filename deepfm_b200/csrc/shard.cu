@@ -277,6 +277,185 @@ route_scatter_kernel(const __grid_constant__ RouteArgs a, const long long* __res
     }
 }
 
+
+// =================================================================================================================
+// v2 exchange: UNIQUE rows per owner.  Under CTR-like skew most id slots of a batch repeat a row that the same GPU
+// already asked the same owner for, so the sample side sorts its sharded id slots by the owner-major key
+//     key = owner << lbits | (vbase[f] + id div W)           (the low part IS the owner's local sort key)
+// and sends every distinct key once: send order = sorted unique keys (grouped by owner, ascending inside),
+// positions[slot] = 1 + index of the slot's key in that order (0: nothing sent), and in the backward the gradient
+// rows of all slots that share a key are pre-reduced on the sender in the same sorted order (dfm_shard_bwd_peer)
+// before ONE row per unique key crosses NVLink.
+//   shard_ukeys    id slots -> (key, payload = b << pbits | plan slot); unsent slots get the PAD key; positions = 0
+//   shard_unique   sorted keys -> unique keys in send order, per-owner counts, unique index per sorted position,
+//                  positions (count -> scan -> emit, stable, no float anywhere)
+//   shard_gather2  owner side: unique local keys -> vector rows + [w1, 0, 0, 0] scalars, stored into the requester's
+//                  buffers (peer stores), and the backward keys (PAD for the padding row id 0)
+struct UKeyField {
+    const long long* ids;
+    unsigned vbase;            // local key base of the field (sum of ceil(V / W) of the sharded fields before it)
+    int slot_base, max_len, bag, rot;
+    long long vocab;
+};
+struct UKeyArgs {
+    UKeyField f[MAX_FIELDS];             // sharded table fields
+    unsigned short ts_field[MAX_SLOTS];  // compact sharded slot -> index into f
+    unsigned short ts_pos[MAX_SLOTS];    // compact sharded slot -> position inside the bag
+    int S_sh, world, lbits, pbits;
+    unsigned pad;
+    long long B;
+    int* status;
+};
+
+__global__ void __launch_bounds__(256)
+shard_ukeys_kernel(const __grid_constant__ UKeyArgs a, uint32_t* __restrict__ keys, uint32_t* __restrict__ payload,
+                   long long* __restrict__ pos) {
+    __shared__ UKeyField t[MAX_FIELDS];
+    __shared__ unsigned short tf[MAX_SLOTS], tp[MAX_SLOTS];
+    for (int q = threadIdx.x; q < MAX_FIELDS; q += 256) t[q] = a.f[q];
+    for (int q = threadIdx.x; q < a.S_sh; q += 256) { tf[q] = a.ts_field[q]; tp[q] = a.ts_pos[q]; }
+    __syncthreads();
+    const long long n = a.B * a.S_sh;
+    for (long long j = (long long)blockIdx.x * blockDim.x + threadIdx.x; j < n; j += (long long)gridDim.x * blockDim.x) {
+        const long long b = j / a.S_sh;
+        const int ts = (int)(j - b * a.S_sh);
+        const UKeyField& fd = t[tf[ts]];
+        const int l = tp[ts];
+        long long id = __ldg(fd.ids + b * fd.max_len + l);
+        if ((unsigned long long)id >= (unsigned long long)fd.vocab) {     // also catches id < 0
+            if (a.status) *a.status = 1;
+            id = 0;
+        }
+        const bool sent = !(fd.bag && id == 0);
+        const unsigned owner = (unsigned)((id + fd.rot) % a.world);
+        keys[j] = sent ? (owner << a.lbits) | (fd.vbase + (unsigned)(id / a.world)) : a.pad;
+        payload[j] = ((uint32_t)b << a.pbits) | (uint32_t)(fd.slot_base + l);
+        pos[a.B * fd.slot_base + b * fd.max_len + l] = 0;
+    }
+}
+
+constexpr int UQ_TILE = 2048;
+
+__global__ void __launch_bounds__(256)
+uniq_count_kernel(const uint32_t* __restrict__ sk, long long n, unsigned pad, int lbits, int* __restrict__ blk_heads,
+                  int* __restrict__ blk_owner) {
+    __shared__ int hist[RT_MAXW + 1];
+    if (threadIdx.x <= RT_MAXW) hist[threadIdx.x] = 0;
+    __syncthreads();
+    const long long i0 = (long long)blockIdx.x * UQ_TILE;
+    for (int c = threadIdx.x; c < UQ_TILE; c += 256) {
+        const long long p = i0 + c;
+        if (p >= n) break;
+        const uint32_t k = __ldg(sk + p);
+        if (k == pad) continue;
+        if (p == 0 || __ldg(sk + p - 1) != k) { atomicAdd(&hist[RT_MAXW], 1); atomicAdd(&hist[k >> lbits], 1); }
+    }
+    __syncthreads();
+    if (threadIdx.x < RT_MAXW) blk_owner[blockIdx.x * RT_MAXW + threadIdx.x] = hist[threadIdx.x];
+    if (threadIdx.x == 0) blk_heads[blockIdx.x] = hist[RT_MAXW];
+}
+
+__global__ void uniq_scan_kernel(const int* __restrict__ blk_heads, const int* __restrict__ blk_owner, int nblk, int world,
+                                 long long* __restrict__ blk_base, long long* __restrict__ counts) {
+    if (threadIdx.x == 0) {
+        long long run = 0;
+        for (int b = 0; b < nblk; ++b) { blk_base[b] = run; run += blk_heads[b]; }
+    }
+    if (threadIdx.x < world) {
+        long long c = 0;
+        for (int b = 0; b < nblk; ++b) c += blk_owner[b * RT_MAXW + threadIdx.x];
+        counts[threadIdx.x] = c;
+    }
+}
+
+struct UniqArgs {
+    unsigned short slot_sb[MAX_SLOTS];   // plan slot -> slot_base of its field
+    unsigned short slot_ml[MAX_SLOTS];   // plan slot -> max_len of its field
+    long long B;
+    int pbits;
+    unsigned pad, lmask;
+};
+
+__global__ void __launch_bounds__(256)
+uniq_emit_kernel(const __grid_constant__ UniqArgs a, const uint32_t* __restrict__ sk, const uint32_t* __restrict__ sp,
+                 long long n, const long long* __restrict__ blk_base, uint32_t* __restrict__ ukeys,
+                 uint32_t* __restrict__ uidx, long long* __restrict__ pos) {
+    __shared__ int warp_cnt[8];
+    __shared__ long long run;
+    const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
+    if (threadIdx.x == 0) run = blk_base[blockIdx.x];
+    const long long i0 = (long long)blockIdx.x * UQ_TILE;
+    const uint32_t pmask = (1u << a.pbits) - 1u;
+    for (int c = 0; c < UQ_TILE; c += 256) {
+        __syncthreads();
+        const long long p = i0 + c + threadIdx.x;
+        uint32_t k = a.pad;
+        bool head = false;
+        if (p < n) {
+            k = __ldg(sk + p);
+            head = k != a.pad && (p == 0 || __ldg(sk + p - 1) != k);
+        }
+        const unsigned m = __ballot_sync(0xffffffffu, head);
+        const int incl = __popc(m & (0xffffffffu >> (31 - lane)));      // heads at lanes <= this one
+        if (lane == 0) warp_cnt[warp] = __popc(m);
+        __syncthreads();
+        int before = 0;
+        for (int w2 = 0; w2 < warp; ++w2) before += warp_cnt[w2];
+        if (k != a.pad) {
+            const long long u = run + before + incl - 1;     // ordinal of this position's segment among all heads
+            if (head) ukeys[u] = k & a.lmask;
+            uidx[p] = (uint32_t)u;
+            const uint32_t pay = __ldg(sp + p);
+            const long long b = pay >> a.pbits;
+            const int s = (int)(pay & pmask);
+            pos[a.B * a.slot_sb[s] + b * a.slot_ml[s] + (s - a.slot_sb[s])] = u + 1;      // 1-based, 0 = not sent
+        }
+        __syncthreads();
+        if (threadIdx.x == 0) {
+            int add = 0;
+            for (int w2 = 0; w2 < 8; ++w2) add += warp_cnt[w2];
+            run += add;
+        }
+    }
+}
+
+struct PeerDst2 {
+    long long start[RT_MAXW_ + 1];
+    float* vec[RT_MAXW_];
+    float* sc[RT_MAXW_];
+    int n;
+};
+
+template <int V>
+__global__ void __launch_bounds__(256)
+shard_gather2_kernel(const __grid_constant__ ShardArgs a, long long M, const uint32_t* __restrict__ lk, int G,
+                     uint32_t* __restrict__ bkeys, const __grid_constant__ PeerDst2 pd) {
+    __shared__ ShardField t[MAX_FIELDS];
+    for (int i = threadIdx.x; i < a.n; i += blockDim.x) t[i] = a.f[i];
+    __syncthreads();
+    const int gpb = blockDim.x / G;
+    const int gl = threadIdx.x / G, j = threadIdx.x - gl * G;
+    for (long long i = (long long)blockIdx.x * gpb + gl; i < M; i += (long long)gridDim.x * gpb) {
+        const uint32_t key = __ldg(lk + i);
+        int fi = 0;
+        for (int q = 1; q < a.n; ++q) if (key >= t[q].lbase) fi = q;
+        const ShardField& sf = t[fi];
+        const uint32_t lrow = key - sf.lbase;
+        int p = 0;
+#pragma unroll 1
+        for (int q = 1; q < pd.n; ++q) if (i >= pd.start[q]) p = q;
+        const long long r = i - pd.start[p];
+        if (j < sf.dim / V)
+            vstore_stream<V>(pd.vec[p] + (size_t)r * a.dmax + j * V, vload<V>(sf.w2 + (size_t)lrow * sf.dim + j * V));
+        if (j == 0) {
+            *reinterpret_cast<float4*>(pd.sc[p] + (size_t)r * 4) = make_float4(__ldg(sf.w1 + lrow), 0.f, 0.f, 0.f);
+            // global id 0 (the padding row: local row 0 on rank f mod W) takes no gradient
+            const bool id0 = lrow == 0 && ((a.rank - sf.field) % a.world + a.world) % a.world == 0;
+            bkeys[i] = id0 ? a.pad_local : key;
+        }
+    }
+}
+
 }  // namespace dfm
 
 using namespace dfm;
@@ -493,6 +672,115 @@ int dfm_shard_route(const dfm_plan* plan, int world, const int64_t* global_row_b
     route_count_kernel<<<nblk, 256, 0, st>>>(*a, block_counts);
     route_scan_kernel<<<1, 32, 0, st>>>(block_counts, nblk, world, offsets, reinterpret_cast<long long*>(counts));
     route_scatter_kernel<<<nblk, 256, 0, st>>>(*a, offsets, nblk, send_keys, reinterpret_cast<long long*>(positions), send_slots);
+    DFM_CHECK_LAUNCH();
+    return DFM_OK;
+}
+
+size_t dfm_shard_unique_workspace_bytes(int64_t n) {
+    const long long nblk = ceil_div(n > 0 ? n : 1, UQ_TILE) + 1;
+    return (size_t)nblk * 4 + (size_t)nblk * RT_MAXW * 4 + (size_t)nblk * 8 + 1024;
+}
+
+int dfm_shard_ukeys(const dfm_plan* plan, int world, const int64_t* vbase, const int64_t* vocab, int lbits, int64_t batch,
+                    const void* const* inputs, uint32_t* keys, uint32_t* payload, int64_t* positions, int32_t* status,
+                    void* stream) {
+    DFM_REQUIRE(plan && vbase && vocab && inputs && world > 0 && world <= RT_MAXW && batch >= 0 && lbits > 0 && lbits < 31,
+                DFM_ERR_INVALID, "dfm_shard_ukeys: bad argument (world must be 1..%d)", RT_MAXW);
+    if (batch == 0) return DFM_OK;
+    DFM_REQUIRE(keys && payload && positions, DFM_ERR_INVALID, "dfm_shard_ukeys: null tensor");
+    UKeyArgs* a = new UKeyArgs;
+    struct Gd { UKeyArgs* p; ~Gd() { delete p; } } gd{a};
+    memset(a, 0, sizeof(*a));
+    int nt = 0, ts = 0, pbits = 0;
+    while ((1 << pbits) < plan->S) ++pbits;
+    for (int f = 0; f < plan->n_fields; ++f) {
+        if (!shard_field(plan, f, false)) continue;
+        DFM_REQUIRE(inputs[f], DFM_ERR_INVALID, "dfm_shard_ukeys: field %d has no id column", f);
+        UKeyField& kf = a->f[nt];
+        kf.ids = static_cast<const long long*>(inputs[f]);
+        kf.vbase = (unsigned)vbase[f];
+        kf.slot_base = plan->slot_base[f]; kf.max_len = plan->max_len[f];
+        kf.bag = plan->kind[f] == DFM_SEQUENCE ? 1 : 0;
+        kf.rot = f % world;
+        kf.vocab = vocab[f];
+        for (int l = 0; l < plan->max_len[f]; ++l) { a->ts_field[ts] = (unsigned short)nt; a->ts_pos[ts] = (unsigned short)l; ++ts; }
+        ++nt;
+    }
+    DFM_REQUIRE(ts > 0, DFM_ERR_INVALID, "dfm_shard_ukeys: the plan has no sharded (foreign) table");
+    DFM_REQUIRE(((long long)batch << pbits) < 0xffffffffLL, DFM_ERR_UNSUPPORTED, "dfm_shard_ukeys: batch * slots must fit 32 bits");
+    a->S_sh = ts; a->world = world; a->lbits = lbits; a->pbits = pbits; a->B = batch; a->status = status;
+    a->pad = (unsigned)world << lbits;
+    const long long n = (long long)batch * ts;
+    long long blocks = ceil_div(n, 256);
+    if (blocks > 8LL * sm_count()) blocks = 8LL * sm_count();
+    shard_ukeys_kernel<<<(unsigned)blocks, 256, 0, static_cast<cudaStream_t>(stream)>>>(*a, keys, payload, reinterpret_cast<long long*>(positions));
+    DFM_CHECK_LAUNCH();
+    return DFM_OK;
+}
+
+int dfm_shard_unique(const dfm_plan* plan, int world, int lbits, int64_t batch, int64_t n, const uint32_t* sorted_keys,
+                     const uint32_t* sorted_payload, uint32_t* unique_keys, uint32_t* unique_index, int64_t* positions,
+                     int64_t* counts, void* workspace, size_t workspace_bytes, void* stream) {
+    DFM_REQUIRE(plan && counts && world > 0 && world <= RT_MAXW && n >= 0, DFM_ERR_INVALID, "dfm_shard_unique: bad argument");
+    cudaStream_t st = static_cast<cudaStream_t>(stream);
+    if (n == 0) { DFM_CHECK_CUDA(cudaMemsetAsync(counts, 0, (size_t)world * 8, st)); return DFM_OK; }
+    DFM_REQUIRE(sorted_keys && sorted_payload && unique_keys && unique_index && positions && workspace, DFM_ERR_INVALID, "dfm_shard_unique: null tensor");
+    DFM_REQUIRE(workspace_bytes >= dfm_shard_unique_workspace_bytes(n), DFM_ERR_WORKSPACE, "dfm_shard_unique: workspace too small");
+    UniqArgs* a = new UniqArgs;
+    struct Gd { UniqArgs* p; ~Gd() { delete p; } } gd{a};
+    memset(a, 0, sizeof(*a));
+    for (int s = 0; s < plan->S; ++s) {
+        const int f = plan->slot_field[s];
+        a->slot_sb[s] = (unsigned short)plan->slot_base[f];
+        a->slot_ml[s] = (unsigned short)plan->max_len[f];
+    }
+    int pbits = 0;
+    while ((1 << pbits) < plan->S) ++pbits;
+    a->B = batch; a->pbits = pbits; a->pad = (unsigned)world << lbits; a->lmask = (1u << lbits) - 1u;
+    const int nblk = (int)ceil_div(n, UQ_TILE);
+    char* ws = static_cast<char*>(workspace);
+    int* blk_heads = reinterpret_cast<int*>(ws);
+    int* blk_owner = reinterpret_cast<int*>(ws + align_up((size_t)nblk * 4, 256));
+    long long* blk_base = reinterpret_cast<long long*>(ws + align_up((size_t)nblk * 4, 256) + align_up((size_t)nblk * RT_MAXW * 4, 256));
+    uniq_count_kernel<<<nblk, 256, 0, st>>>(sorted_keys, n, a->pad, lbits, blk_heads, blk_owner);
+    uniq_scan_kernel<<<1, 32, 0, st>>>(blk_heads, blk_owner, nblk, world, blk_base, reinterpret_cast<long long*>(counts));
+    uniq_emit_kernel<<<nblk, 256, 0, st>>>(*a, sorted_keys, sorted_payload, n, blk_base, unique_keys, unique_index,
+                                           reinterpret_cast<long long*>(positions));
+    DFM_CHECK_LAUNCH();
+    return DFM_OK;
+}
+
+int dfm_shard_gather2(const dfm_plan* local_plan, int world, int rank, int64_t n_keys, const uint32_t* local_keys,
+                      const float* const* params, int n_peers, const int64_t* peer_start, float* const* peer_vec,
+                      float* const* peer_sc, uint32_t* backward_keys, void* stream) {
+    DFM_REQUIRE(local_plan && params && world > 0 && rank >= 0 && rank < world, DFM_ERR_INVALID, "dfm_shard_gather2: bad argument");
+    if (n_keys <= 0) return DFM_OK;
+    DFM_REQUIRE(local_keys && backward_keys && n_peers >= 1 && n_peers <= RT_MAXW_ && peer_start && peer_vec && peer_sc, DFM_ERR_INVALID,
+                "dfm_shard_gather2: null tensor / 1..%d peers", RT_MAXW_);
+    DFM_REQUIRE(peer_start[n_peers] - peer_start[0] == n_keys, DFM_ERR_INVALID, "dfm_shard_gather2: the peer segments must cover the %lld keys", (long long)n_keys);
+    ShardArgs* a = new ShardArgs;
+    PeerDst2* pd = new PeerDst2;
+    struct Gd { ShardArgs* p; PeerDst2* q; ~Gd() { delete p; delete q; } } gd{a, pd};
+    std::vector<int64_t> zeros(local_plan->n_fields + 1, 0);
+    int rc = fill_shard_args(local_plan, zeros.data(), params, world, rank, *a, true);
+    if (rc) return rc;
+    memset(pd, 0, sizeof(*pd));
+    for (int q = 0; q < n_peers; ++q) {
+        DFM_REQUIRE(peer_vec[q] && peer_sc[q] && ((reinterpret_cast<uintptr_t>(peer_vec[q]) | reinterpret_cast<uintptr_t>(peer_sc[q])) & 15u) == 0 &&
+                    peer_start[q] <= peer_start[q + 1], DFM_ERR_INVALID, "dfm_shard_gather2: peer %d has a null / unaligned buffer or a negative segment", q);
+        pd->start[q] = peer_start[q]; pd->vec[q] = peer_vec[q]; pd->sc[q] = peer_sc[q];
+    }
+    pd->start[n_peers] = peer_start[n_peers];
+    pd->n = n_peers;
+    const bool v4 = local_plan->vec == 4;
+    const int lanes = a->dmax / (v4 ? 4 : 1);
+    DFM_REQUIRE(lanes <= 32, DFM_ERR_UNSUPPORTED, "dfm_shard_gather2: table dim %d too wide", a->dmax);
+    const int G = next_pow2(lanes);
+    long long blocks = ceil_div(n_keys, 256 / G);
+    if (blocks > 8LL * sm_count()) blocks = 8LL * sm_count();
+    cudaStream_t st = static_cast<cudaStream_t>(stream);
+    if (v4) shard_gather2_kernel<4><<<(unsigned)blocks, 256, 0, st>>>(*a, n_keys, local_keys, G, backward_keys, *pd);
+    else shard_gather2_kernel<1><<<(unsigned)blocks, 256, 0, st>>>(*a, n_keys, local_keys, G, backward_keys, *pd);
     DFM_CHECK_LAUNCH();
     return DFM_OK;
 }

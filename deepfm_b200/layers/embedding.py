@@ -111,11 +111,15 @@ class _EmbedFn(torch.autograd.Function):
         if need_bwd:
             ctx.save_for_backward(field, flat, fm_sum, keys, aux, *inputs, *params)
             mod._live_ctx = weakref.ref(ctx)
-        return first, field, flat, fm_out
+        # 5th output: a scalar that exists only to be an input of the L2 penalty node (layers/l2.py), which makes this
+        # node an ancestor of that one -- the module keeps it alive, the three views may be dropped by the caller
+        anchor = torch.zeros((), device=dev, dtype=torch.float32)
+        return first, field, flat, fm_out, anchor
 
     @staticmethod
-    def backward(ctx, g_first, g_field, g_flat, g_fm):
+    def backward(ctx, g_first, g_field, g_flat, g_fm, _g_anchor=None):
         mod: FeatureEmbedding = ctx.mod
+        mod._live_anchor = None           # a penalty node created from now on cannot hang below this (spent) node
         mod.raise_if_bad_index(block=False)   # lazy check of the forward's status word (the reference raises IndexError)
         lib = _lib.lib()
         saved = ctx.saved_tensors
@@ -417,8 +421,8 @@ class FeatureEmbedding(IndexStatusMixin, nn.Module):
             if x.shape[0] != B:
                 raise ValueError(f"batch[{n!r}] has {x.shape[0]} rows, expected {B}")
         need_bwd = torch.is_grad_enabled() and any(p.requires_grad for p in params)
-        first, field, flat, fm = _EmbedFn.apply(self, len(inputs), need_bwd, *inputs, *params)
-        self._live_anchor = weakref.ref(first) if need_bwd else None     # the L2 node hangs itself below this node
+        first, field, flat, fm, anchor = _EmbedFn.apply(self, len(inputs), need_bwd, *inputs, *params)
+        self._live_anchor = anchor if (need_bwd and anchor.requires_grad) else None   # the L2 node hangs itself below this node
         field._dfm_fm = (fm, field._version)     # picked up by FMInteraction (same tensor object)
         return first, field, flat, fm
 

@@ -13,9 +13,10 @@ The small parameters (DENSE-field Linears, projections) are reduced every call (
 
 Gradient.  If the penalty is added to a loss that also flows through the ``FeatureEmbedding`` forward of the same
 step, the ``2*lambda*p`` term is folded into the embedding backward kernel K2 (no extra pass over the tables).  The
-node takes the embedding's ``first_order`` output as an (otherwise unused) input, so the autograd graph itself
+node takes a scalar output of the embedding's autograd node as an (otherwise unused) input, so the autograd graph itself
 guarantees that the embedding's backward runs after this node in every backward pass that reaches it -- no engine
-callbacks, no private API.  In every other situation the node produces ``2*lambda*p`` itself with ``dfm_axpy``.
+callbacks, no private API.  (The anchor is a dedicated scalar output of the embedding node that the module holds on
+to: the three views themselves may be dropped by the model as soon as it has combined them.)  In every other situation the node produces ``2*lambda*p`` itself with ``dfm_axpy``.
 """
 
 from __future__ import annotations
@@ -143,11 +144,8 @@ def l2_penalty(emb, lam: float) -> torch.Tensor:
     params: List[torch.Tensor] = [p.contiguous() for p in emb.parameters()]
     for p in params:
         _lib.require_cuda(p, "FeatureEmbedding parameter")
-    anchor = None
-    ref = getattr(emb, "_live_anchor", None)
+    anchor = getattr(emb, "_live_anchor", None)
     live = emb._live_ctx() if getattr(emb, "_live_ctx", None) is not None else None
-    if ref is not None and live is not None and torch.is_grad_enabled():
-        anchor = ref()
-        if anchor is not None and not anchor.requires_grad:
-            anchor = None
+    if anchor is not None and (live is None or not torch.is_grad_enabled() or not anchor.requires_grad):
+        anchor = None
     return _L2PenaltyFn.apply(emb, lam, anchor, *params)

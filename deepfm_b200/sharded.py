@@ -48,20 +48,30 @@ from .schema import kind_of
 VIRTUAL_VOCAB = 1 << 26     # capacity of the "received rows" pseudo table of the sample-side plan
 
 
-def local_rows(vocab: int, world: int, rank: int, field: int = 0) -> int:
-    """Number of ids in [0, vocab) owned by ``rank`` ((id + field) mod world == rank); at least 1 row is kept."""
-    first = (rank - field) % world          # smallest id this rank owns in the field's table
-    return max((vocab - first + world - 1) // world, 1)
+def local_rows(vocab: int, world: int, rank: int = 0, field: int = 0) -> int:
+    """Rows of a sharded table on EVERY rank: ceil(vocab / world).  The ids a rank owns in one table are one residue
+    class, (id + field) mod world == rank, with local_row = id div world; sizing every shard to the largest class
+    (at most one unused row) makes a row's local sort key the same number on every rank."""
+    return max((vocab + world - 1) // world, 1)
+
+
+def owned_rows(vocab: int, world: int, rank: int, field: int = 0) -> int:
+    """Number of ids in [0, vocab) that ``rank`` owns in the table of schema field ``field``."""
+    first = (rank - field) % world
+    return max((vocab - first + world - 1) // world, 0)
 
 
 @dataclass
 class Route:
-    send_keys: torch.Tensor      # (n,) int32 (u32 bits): global rows in send order (grouped by owner)
-    counts: torch.Tensor         # (W,) int64: keys per destination
-    order: Optional[torch.Tensor]  # (n,) int64: send position -> source slot index b*S + s (torch path only)
-    pos: torch.Tensor            # (b*S,) int64, field-major: field f's (b, max_len) block at b * slot_base[f];
-    #                              1-based send position of every id slot, 0 = not sent (padding id of a bag)
-    send_slots: Optional[torch.Tensor] = None   # (n,) int32: send position -> id slot index b*S + s (kernel path)
+    """One batch routed for the unique-row exchange (see ShardedFeatureEmbedding)."""
+    send_keys: torch.Tensor      # (>= n_unique,) int32: owner-local keys (vbase[f] + id div W) in send order
+    counts: torch.Tensor         # (W,) int64: unique keys per destination
+    pos: torch.Tensor            # (b * S_all,) int64, the plan's field-major blocks: 1 + index of the slot's key in the
+    #                              send order, 0 = nothing sent (padding id of a bag, replicated table)
+    skeys: Optional[torch.Tensor] = None   # kernel path: the sorted (owner << lbits | key, payload) stream and the
+    spay: Optional[torch.Tensor] = None    # unique index of every sorted position -- the backward's segments
+    uidx: Optional[torch.Tensor] = None
+    n_sorted: int = 0
 
 
 def field_positions(pos: torch.Tensor, b: int, lens: Sequence[int]) -> List[torch.Tensor]:
@@ -74,33 +84,32 @@ def field_positions(pos: torch.Tensor, b: int, lens: Sequence[int]) -> List[torc
     return out
 
 
-def route_ids(ids: torch.Tensor, row_base: torch.Tensor, world: int, lens: Optional[Sequence[int]] = None,
-              bag: Optional[Sequence[bool]] = None, rot: Optional[Sequence[int]] = None) -> Route:
-    """ids (b, S) int64 (the id slots of one sample side by side, bags expanded), row_base (S,) int64 per slot,
-    lens / bag per table field (sum(lens) == S).  Stable grouping of the slots, in source order b*S + s, by
-    owner = (id + rot[field]) mod W (rot: schema index per table field, default 0); padding entries (id 0) of
-    bag fields are not sent.  Pure torch ops: works on CPU and CUDA
-    tensors; matches oracle.shard_route bit-exactly."""
+def route_unique(ids: torch.Tensor, vbase: torch.Tensor, world: int, lens: Optional[Sequence[int]] = None,
+                 bag: Optional[Sequence[bool]] = None, rot: Optional[Sequence[int]] = None, lbits: int = 24) -> Route:
+    """Torch restatement of the routing kernels (CPU and CUDA tensors; bit-exact contract: oracle.shard_route_unique).
+    ids (b, S) int64 (the sharded id slots of one sample side by side, bags expanded), vbase (S,) int64 per slot,
+    lens / bag / rot per table field.  key = owner << lbits | (vbase + id div W) with owner = (id + rot) mod W;
+    padding entries (id 0) of bag fields are not sent; the send order is the sorted set of distinct keys."""
     b, S = ids.shape
     lens = [1] * S if lens is None else list(lens)
     bag = [False] * len(lens) if bag is None else list(bag)
-    slot_bag = torch.tensor([g for L, g in zip(lens, bag) for _ in range(L)], dtype=torch.bool, device=ids.device)
-    sent = ~(slot_bag[None, :] & (ids == 0))
     rot = [0] * len(lens) if rot is None else list(rot)
+    slot_bag = torch.tensor([g for L, g in zip(lens, bag) for _ in range(L)], dtype=torch.bool, device=ids.device)
     slot_rot = torch.tensor([r for L, r in zip(lens, rot) for _ in range(L)], dtype=ids.dtype, device=ids.device)
-    owner = torch.where(sent, (ids + slot_rot[None, :]) % world, torch.full_like(ids, world)).reshape(-1)   # unsent last
-    n = int(sent.sum())
-    order = torch.sort(owner, stable=True).indices[:n]
-    counts = torch.bincount(owner, minlength=world + 1)[:world]
+    sent = ~(slot_bag[None, :] & (ids == 0))
+    owner = (ids + slot_rot[None, :]) % world
+    comp = (owner << lbits) | (vbase[None, :] + ids // world)
+    flat, sent_f = comp.reshape(-1), sent.reshape(-1)
+    uniq, inverse = torch.unique(flat[sent_f], sorted=True, return_inverse=True)
+    counts = torch.bincount(uniq >> lbits, minlength=world)[:world]
     pos_flat = torch.zeros(b * S, dtype=torch.int64, device=ids.device)
-    pos_flat[order] = torch.arange(1, n + 1, device=ids.device, dtype=torch.int64)
+    pos_flat[sent_f] = inverse + 1
     pos_bs = pos_flat.view(b, S)
     blocks, s0 = [], 0
     for L in lens:
         blocks.append(pos_bs[:, s0:s0 + L].reshape(-1))
         s0 += L
-    keys = (ids + row_base[None, :]).reshape(-1)
-    return Route(send_keys=keys[order].to(torch.int32), counts=counts, order=order, pos=torch.cat(blocks))
+    return Route(send_keys=(uniq & ((1 << lbits) - 1)).to(torch.int32), counts=counts, pos=torch.cat(blocks))
 
 
 class TorchDistComm:
@@ -152,35 +161,43 @@ class TorchDistComm:
 class PeerExchange:
     """The two vector exchanges of a step as peer-memory writes (compute fused with its collective).
 
-    Every rank owns two symmetric-memory buffers per direction (``torch.distributed._symmetric_memory``: CUDA VMM
-    allocations mapped into every peer over NVLink/NVSwitch).  The owner-side gather kernel stores each reply row
-    straight into the requesting GPU's ``got`` buffer, the sample-side packing kernel stores each gradient row
-    straight into the owning GPU's ``g_recv`` buffer: no staging buffer, no NCCL all-to-all; one device-side
-    barrier separates the writes from their consumer.  Buffers alternate between steps, so that barrier is the
-    only synchronisation needed (a peer can be at most one exchange ahead)."""
+    Every rank owns one symmetric-memory allocation (``deepfm_b200._peer``: CUDA VMM memory mapped into every peer
+    over NVLink / NVSwitch) holding, for each direction (0: looked-up rows "got", 1: gradient rows "g_recv") and each
+    step parity, a (cap, D) vector buffer followed by a (cap, 4) scalar buffer -- 256-byte rows that start on a
+    256-byte boundary and 16-byte scalar records, so every peer store is a whole number of aligned sectors.  The
+    owner-side gather kernel stores each reply row straight into the requesting GPU's ``got`` buffers, the sample-side
+    segmented reduction stores each unique row's gradient straight into the owning GPU's ``g_recv`` buffers: no staging
+    buffer, no NCCL all-to-all; one device-side barrier separates the writes from their consumer.  Buffers alternate
+    between steps (a peer can be at most one exchange ahead)."""
 
-    def __init__(self, comm: "TorchDistComm", row_floats: int, capacity_rows: int, device):
-        import torch.distributed._symmetric_memory as symm
+    def __init__(self, comm: "TorchDistComm", dim: int, capacity_rows: int, device):
+        from . import _peer
         self.comm, self.world, self.rank = comm, comm.world, comm.rank
-        self.row_floats, self.cap = row_floats, int(capacity_rows)
+        self.dim, self.cap = int(dim), (int(capacity_rows) + 63) // 64 * 64      # every block starts on a 256-byte boundary
         group = comm.group if comm.group is not None else comm.dist.group.WORLD
-        n = 4 * self.cap * row_floats                        # [got 0 | got 1 | g_recv 0 | g_recv 1]
-        self.buf = symm.empty((n,), dtype=torch.float32, device=device)
-        self.hdl = symm.rendezvous(self.buf, group.group_name)
+        n = 4 * self.cap * (self.dim + 4)
+        self.buf, self.hdl = _peer.symmetric_empty(n, device, group)
         self.buf.zero_()                                     # row 0 of both got buffers is the reserved zero row
         self.peer_base = [int(p) for p in self.hdl.buffer_ptrs]
         self.step = 0
         torch.cuda.synchronize(device)
         self.hdl.barrier(channel=0)
 
-    def region(self, kind: int, parity: int, rank: Optional[int] = None) -> int:
-        """Device address of buffer (kind 0: got, 1: g_recv; parity) on ``rank`` (default: this rank)."""
-        base = self.peer_base[self.rank if rank is None else rank]
-        return base + (2 * kind + parity) * self.cap * self.row_floats * 4
+    def _offsets(self, kind: int, parity: int):
+        """Float offsets of the (vector, scalar) buffers of (kind, parity) inside a rank's allocation."""
+        base = (2 * kind + parity) * self.cap * (self.dim + 4)
+        return base, base + self.cap * self.dim
 
-    def view(self, kind: int, parity: int, rows: int) -> torch.Tensor:
-        off = (2 * kind + parity) * self.cap * self.row_floats
-        return self.buf[off: off + rows * self.row_floats].view(rows, self.row_floats)
+    def region(self, kind: int, parity: int, rank: Optional[int] = None):
+        """Device addresses (vector buffer, scalar buffer) of (kind 0: got, 1: g_recv; parity) on ``rank``."""
+        b = self.peer_base[self.rank if rank is None else rank]
+        ov, os_ = self._offsets(kind, parity)
+        return b + 4 * ov, b + 4 * os_
+
+    def views(self, kind: int, parity: int, rows: int):
+        ov, os_ = self._offsets(kind, parity)
+        return (self.buf[ov: ov + rows * self.dim].view(rows, self.dim),
+                self.buf[os_: os_ + rows * 4].view(rows, 4))
 
     def fits(self, matrix) -> bool:
         """Same answer on every rank (all of them hold the full W x W count matrix)."""
@@ -205,57 +222,71 @@ class _ShardedEmbedFn(torch.autograd.Function):
         else:
             route = mod.route(inputs)
             send_counts, recv_counts = comm.exchange_counts(route.counts)     # the only host sync of the step
-        recv_keys = comm.all_to_all(route.send_keys[:int(sum(send_counts))], send_counts, recv_counts)
+        n_send, n_recv = int(sum(send_counts)), int(sum(recv_counts))
+        recv_keys = comm.all_to_all(route.send_keys[:n_send], send_counts, recv_counts)
         px = mod.peer_exchange(inputs[0].device)
         matrix = getattr(comm, "last_matrix", None)
         use_p2p = px is not None and matrix is not None and px.fits(matrix)
         parity = 0
         if use_p2p:
-            # owners store every reply row straight into the requester's got buffer (NVLink P2P), then one barrier
+            # owners store every reply row straight into the requester's got buffers (NVLink P2P), then one barrier
             parity = px.step & 1
             px.step += 1
-            lkeys = mod.gather_p2p(recv_keys, px, matrix, parity)
+            bkeys = mod.gather(recv_keys, p2p=(px, matrix, parity))
             px.barrier(0)
-            got = px.view(0, parity, int(sum(send_counts)) + 1)
+            got_vec, got_sc = px.views(0, parity, n_send + 1)
         else:
-            rows, lkeys = mod.gather(recv_keys)
-            got = mod.reply_buffer(int(sum(send_counts)), rows)            # (1 + n, D + 4): zero row, then the replies
-            comm.all_to_all(rows, recv_counts, send_counts, out=got[1:])   # vector + first-order weight per row
-        first, field, flat, fm, fm_sum, aux, fin_inputs, keys = mod.finish(inputs, route.pos, got, need_bwd)
+            vec, sc, bkeys = mod.gather(recv_keys)
+            got_vec, got_sc = mod.reply_buffers(n_send, vec)                  # row 0: the reserved zero row
+            comm.all_to_all(vec, recv_counts, send_counts, out=got_vec[1:])
+            comm.all_to_all(sc, recv_counts, send_counts, out=got_sc[1:])
+        bsorted = mod.sort_owner_keys(bkeys) if need_bwd else None            # side stream: the owner-side backward's sort
+        first, field, flat, fm, fm_sum, aux, fin_inputs, keys = mod.finish(inputs, route.pos, got_vec, got_sc, need_bwd)
         ctx.mod, ctx.n_inputs = mod, n_inputs
         ctx.counts = (send_counts, recv_counts)
-        ctx.p2p = (px, matrix, parity, route.send_slots) if use_p2p else None
+        ctx.p2p = (px, matrix, parity) if use_p2p else None
+        ctx.route = route if need_bwd else None
+        ctx.bsorted = bsorted
         ctx.set_materialize_grads(False)
         ctx.l2 = None
         if need_bwd:
-            ctx.save_for_backward(field, flat, fm_sum, route.pos, lkeys, got, aux, *fin_inputs, *params)
+            ctx.save_for_backward(field, flat, fm_sum, got_vec, got_sc, aux, *fin_inputs, *params)
             ctx.keys = keys
             mod._live_ctx = weakref.ref(ctx)
-        return first, field, flat, fm
+        anchor = torch.zeros((), device=first.device, dtype=torch.float32)     # see layers/l2.py
+        return first, field, flat, fm, anchor
 
     @staticmethod
-    def backward(ctx, g_first, g_field, g_flat, g_fm):
+    def backward(ctx, g_first, g_field, g_flat, g_fm, _g_anchor=None):
         mod: ShardedFeatureEmbedding = ctx.mod
+        mod._live_anchor = None
         saved = ctx.saved_tensors
-        field, flat, fm_sum, pos, lkeys, got, aux = saved[:7]
+        field, flat, fm_sum, got_vec, got_sc, aux = saved[:6]
         n_f = len(mod.field_names)
-        fin_inputs = saved[7:7 + n_f]
-        params = saved[7 + n_f:]
+        fin_inputs = saved[6:6 + n_f]
+        params = saved[6 + n_f:]
         send_counts, recv_counts = ctx.counts
         lam, gscale = ctx.l2 if ctx.l2 is not None else (0.0, None)
         ctx.l2 = None                     # consumed (see layers/l2.py)
         mod.raise_if_bad_index(block=False)
         cont = lambda g: None if g is None else g.contiguous()
-        g_rows, dense_grads = mod.pack_grads(fin_inputs, pos, got, cont(g_first), cont(g_field), cont(g_flat),
-                                             cont(g_fm), field, flat, fm_sum, params, lam, gscale, aux, p2p=ctx.p2p,
-                                             keys=ctx.keys)
-        if ctx.p2p is not None:           # the gradient rows were stored straight into the owners' buffers
-            px, matrix, parity, _ = ctx.p2p
+        g_first, g_field, g_flat, g_fm = cont(g_first), cont(g_field), cont(g_flat), cont(g_fm)
+        n_recv = int(sum(recv_counts))
+        if ctx.p2p is not None:           # the unique rows' gradients are stored straight into the owners' buffers
+            px, matrix, parity = ctx.p2p
+            mod.reduce_grads(ctx.route, g_first, g_field, g_flat, g_fm, field, fm_sum, aux, p2p=ctx.p2p)
+            dense_grads = mod.local_grads(fin_inputs, got_vec, got_sc, g_first, g_field, g_flat, g_fm, field, flat, fm_sum,
+                                          params, lam, gscale, aux, ctx.keys)
             px.barrier(1)
-            g_recv = px.view(1, parity, int(sum(recv_counts)))
+            g_vec, g_sc = px.views(1, parity, n_recv)
         else:
-            g_recv = mod.comm.all_to_all(g_rows, send_counts, recv_counts)    # (M, D + 4): gradient row + scalars
-        table_grads = mod.owner_backward(lkeys, g_recv, params, lam, gscale)
+            sv, ss = mod.reduce_grads(ctx.route, g_first, g_field, g_flat, g_fm, field, fm_sum, aux)
+            dense_grads = mod.local_grads(fin_inputs, got_vec, got_sc, g_first, g_field, g_flat, g_fm, field, flat, fm_sum,
+                                          params, lam, gscale, aux, ctx.keys)
+            n_send = int(sum(send_counts))
+            g_vec = mod.comm.all_to_all(sv[:n_send], send_counts, recv_counts)
+            g_sc = mod.comm.all_to_all(ss[:n_send], send_counts, recv_counts)
+        table_grads = mod.owner_backward(ctx.bsorted, g_vec, g_sc, params, lam, gscale)
         grads = [dense_grads.get(i, table_grads.get(i)) for i in range(len(params))]
         return (None, None, None) + (None,) * ctx.n_inputs + tuple(grads)
 
@@ -297,7 +328,7 @@ class ShardedFeatureEmbedding(IndexStatusMixin, nn.Module):
                 lvocabs.append(0)
             else:
                 replicated = int(fs.vocabulary_size) <= self.replicate_below
-                rows = int(fs.vocabulary_size) if replicated else local_rows(int(fs.vocabulary_size), world, rank, len(kinds))
+                rows = int(fs.vocabulary_size) if replicated else local_rows(int(fs.vocabulary_size), world)
                 if kind == "sparse":
                     self.second_order_embeddings[name] = nn.Embedding(rows, d)
                     self.first_order_embeddings[name] = nn.Embedding(rows, 1)
@@ -316,11 +347,11 @@ class ShardedFeatureEmbedding(IndexStatusMixin, nn.Module):
         self._repl_idx = [i for i, k in enumerate(kinds) if k != _lib.DENSE and vocabs[i] <= self.replicate_below]
         repl = set(self._repl_idx)
         self._table_idx = [i for i, k in enumerate(kinds) if k != _lib.DENSE and i not in repl]   # the SHARDED tables
-        self._sparse_idx = self._table_idx                      # historical name
         if not self._table_idx:
             raise NotImplementedError(
                 f"no table has more than replicate_below={self.replicate_below} rows: nothing to shard -- use the plain "
                 f"FeatureEmbedding on every rank and average all gradients (DenseGradReducer)")
+        # (the exchange kernels need fm_embed_dim in {32, 64, 128} -- one warp load per row -- and say so when called)
         self._all_tables = [i for i, k in enumerate(kinds) if k != _lib.DENSE]
         self._all_lens = [lens[i] for i in self._all_tables]
         self._all_S = sum(self._all_lens)                                                          # id slots of the plan
@@ -329,14 +360,22 @@ class ShardedFeatureEmbedding(IndexStatusMixin, nn.Module):
         self._S = sum(self._lens)
         self._A = sum(1 for i in range(len(kinds)) if kinds[i] == _lib.SEQUENCE and combiners[i] == _lib.MEAN)   # aux words / sample
         self._T = sum(dims)
-        grb, lrb = [0], [0]
-        for i, (k, v, lv) in enumerate(zip(kinds, vocabs, lvocabs)):
-            grb.append(grb[-1] + (v if k != _lib.DENSE else 0))
-            lrb.append(lrb[-1] + (lv if (k != _lib.DENSE and i not in repl) else 0))    # owner-side keys: sharded tables only
-        if grb[-1] >= 2 ** 31:
+        # owner-local key space: vbase[f] = rows of the sharded tables before field f (identical on every rank)
+        vb, acc = [], 0
+        for i in range(len(kinds)):
+            vb.append(acc)
+            if i in set(self._table_idx):
+                acc += lvocabs[i]
+        vb.append(acc)
+        if acc >= 2 ** 31 or sum(vocabs) >= 2 ** 31:
             raise NotImplementedError("sharded tables: total rows must stay below 2^31")
-        self._global_row_base, self._row_base = grb, lrb
-        self._max_tdim = fm_embed_dim if self._S else 0
+        self._vbase, self._row_base = vb, vb                 # the owner-side plan's row_base is exactly this
+        self._lbits = max(int(acc).bit_length(), 1)          # PAD of the local key space == acc must fit too
+        self._kbits = self._lbits + int(world).bit_length()  # sort bits of owner << lbits | key (PAD = world << lbits)
+        if self._kbits > 32:
+            raise NotImplementedError("sharded tables: owner-major keys need more than 32 bits")
+        self._pad_key = world << self._lbits
+        self._max_tdim = fm_embed_dim
         self.grad_mode = "row_sparse"
         self.row_grads: Optional[RowSparseGrads] = None
         self.last_counts = None
@@ -345,9 +384,9 @@ class ShardedFeatureEmbedding(IndexStatusMixin, nn.Module):
         self._plans = None
         self._param_is_table: List[bool] = []
         self._slot_of_param: List[int] = []
-        self._rb_dev = None
         self._px = None                   # PeerExchange (None: not created yet, False: unavailable)
-        self.p2p_capacity_rows = 0        # rows per exchange buffer; 0: sized by the first forward (2 x b x slots)
+        self.p2p_capacity_rows = 0        # rows per exchange buffer; 0: sized by the first forward (b x slots + 16)
+        self._side = None
         self._init_weights()
 
     def _init_weights(self) -> None:
@@ -375,6 +414,7 @@ class ShardedFeatureEmbedding(IndexStatusMixin, nn.Module):
                 elif isinstance(mine, (nn.Embedding, nn.EmbeddingBag)):
                     rows = theirs.weight[(self.rank - f) % self.world::self.world]
                     mine.weight[: rows.shape[0]].copy_(rows)
+                    mine.weight[rows.shape[0]:].zero_()           # the (at most one) row no id maps to
                 else:
                     mine.weight.copy_(theirs.weight)
                     mine.bias.copy_(theirs.bias)
@@ -397,15 +437,12 @@ class ShardedFeatureEmbedding(IndexStatusMixin, nn.Module):
                         out[f"{prefix}.{name}.{k}"] = v.detach().cpu().clone()
                     continue
                 V = self._vocabs[f]
-                mine = mod.weight.detach()
-                rows_max = (V + W - 1) // W                       # shards differ by at most one row: pad, gather, trim
-                pad = torch.zeros((rows_max, mine.shape[1]), dtype=mine.dtype, device=mine.device)
-                pad[: min(mine.shape[0], rows_max)] = mine[:rows_max]
+                mine = mod.weight.detach()                        # (ceil(V / W), d) on every rank
                 if W > 1:
-                    parts = [torch.empty_like(pad) for _ in range(W)]
-                    dist.all_gather(parts, pad, group=group)
+                    parts = [torch.empty_like(mine) for _ in range(W)]
+                    dist.all_gather(parts, mine.contiguous(), group=group)
                 else:
-                    parts = [pad]
+                    parts = [mine]
                 full = torch.empty((V, mine.shape[1]), dtype=mine.dtype)
                 for r in range(W):
                     first = (r - f) % W                           # smallest id rank r owns in this table
@@ -431,9 +468,9 @@ class ShardedFeatureEmbedding(IndexStatusMixin, nn.Module):
             shard = set(self._table_idx)
             virt = [self._virtual_cap if i in shard else v for i, v in enumerate(self._vocabs)]
             sample_plan = make(virt)
-            D4 = self.fm_embed_dim + 4
-            for i in self._table_idx:     # sample side: sharded tables = the received reply rows, gradient made by the owner
-                _lib.check(lib.dfm_plan_set_field_source(sample_plan, i, D4, D4, 1), "dfm_plan_set_field_source")
+            for i in self._table_idx:     # sample side: a sharded table = the received reply rows ((n, D) vectors, (n, 4)
+                # scalars with the first-order weight in column 0); its gradient is made by the owner
+                _lib.check(lib.dfm_plan_set_field_source(sample_plan, i, self.fm_embed_dim, 4, 1), "dfm_plan_set_field_source")
             local_plan = make(self._lvocabs)
             for i in self._repl_idx:      # owner side: replicated tables are none of its business
                 _lib.check(lib.dfm_plan_set_field_source(local_plan, i, 0, 0, 1), "dfm_plan_set_field_source")
@@ -472,34 +509,48 @@ class ShardedFeatureEmbedding(IndexStatusMixin, nn.Module):
             arr[slot] = t.data_ptr()
         return arr
 
+    def _side_stream(self, dev):
+        if self._side is None or self._side.device != dev:
+            self._side = torch.cuda.Stream(device=dev)
+        return self._side
+
     # -- phases -------------------------------------------------------------------------------
     def route(self, inputs: Sequence[torch.Tensor]) -> Route:
-        if inputs[self._table_idx[0]].is_cuda:                  # product path: the routing kernels
-            lib = _lib.lib()
-            _, sample_plan = self._ensure_plans()
-            dev = inputs[0].device
-            b, S, W = inputs[0].shape[0], self._all_S, self.world
-            send_keys = torch.empty((b * max(self._S, 1),), device=dev, dtype=torch.int32)
-            pos = torch.empty((b * S,), device=dev, dtype=torch.int64)
-            counts = torch.empty((W,), device=dev, dtype=torch.int64)
-            send_slots = torch.empty_like(send_keys)
-            ws = torch.empty((max(lib.dfm_shard_route_workspace_bytes(sample_plan, b), 16),), device=dev, dtype=torch.uint8)
-            _lib.check(lib.dfm_shard_route(sample_plan, W, _lib.i64_array(self._global_row_base), b, _lib.ptr_array(inputs),
-                                           _lib.ptr(send_keys), _lib.ptr(pos), _lib.ptr(counts), _lib.ptr(send_slots),
-                                           _lib.ptr(self._status_word(dev)), ws.data_ptr(), ws.numel(), _lib.stream_ptr()),
-                       "dfm_shard_route")
-            self._post_status()
-            return Route(send_keys=send_keys, counts=counts, order=None, pos=pos, send_slots=send_slots)
-        return self.route_torch(inputs)
+        """Sample side, ids only: owner-major keys -> sort -> unique keys in send order, per-owner counts, the slots'
+        positions in that order, and the sorted stream the backward reduces over."""
+        if not inputs[self._table_idx[0]].is_cuda:
+            return self.route_torch(inputs)
+        lib = _lib.lib()
+        _, sample_plan = self._ensure_plans()
+        dev = inputs[0].device
+        b, W = inputs[0].shape[0], self.world
+        n = b * self._S
+        keys = torch.empty((max(n, 1),), device=dev, dtype=torch.int32)
+        pay = torch.empty((max(n, 1),), device=dev, dtype=torch.int32)
+        pos = torch.zeros((b * self._all_S,), device=dev, dtype=torch.int64)       # replicated tables' blocks stay 0
+        counts = torch.empty((W,), device=dev, dtype=torch.int64)
+        _lib.check(lib.dfm_shard_ukeys(sample_plan, W, _lib.i64_array(self._vbase), _lib.i64_array(self._vocabs), self._lbits,
+                                       b, _lib.ptr_array(inputs), _lib.ptr(keys), _lib.ptr(pay), _lib.ptr(pos),
+                                       _lib.ptr(self._status_word(dev)), _lib.stream_ptr()), "dfm_shard_ukeys")
+        self._post_status()
+        skeys, spay = torch.empty_like(keys), torch.empty_like(pay)
+        ws = torch.empty((max(lib.dfm_sort_pairs_workspace_bytes(n, self._kbits), lib.dfm_shard_unique_workspace_bytes(n), 16),),
+                         device=dev, dtype=torch.uint8)
+        _lib.check(lib.dfm_sort_pairs(n, self._kbits, _lib.ptr(keys), _lib.ptr(pay), _lib.ptr(skeys), _lib.ptr(spay),
+                                      ws.data_ptr(), ws.numel(), _lib.stream_ptr()), "dfm_sort_pairs")
+        ukeys, uidx = torch.empty_like(keys), torch.empty_like(keys)
+        _lib.check(lib.dfm_shard_unique(sample_plan, W, self._lbits, b, n, _lib.ptr(skeys), _lib.ptr(spay), _lib.ptr(ukeys),
+                                        _lib.ptr(uidx), _lib.ptr(pos), _lib.ptr(counts), ws.data_ptr(), ws.numel(),
+                                        _lib.stream_ptr()), "dfm_shard_unique")
+        return Route(send_keys=ukeys, counts=counts, pos=pos, skeys=skeys, spay=spay, uidx=uidx, n_sorted=n)
 
     def route_torch(self, inputs: Sequence[torch.Tensor]) -> Route:
         """The same routing in plain torch ops (CPU tensors under gloo; the restatement the GPU tests compare with)."""
         b = inputs[0].shape[0]
         ids = torch.cat([inputs[i].view(b, -1) for i in self._table_idx], dim=1)
-        if self._rb_dev is None or self._rb_dev.device != ids.device:
-            self._rb_dev = torch.tensor([self._global_row_base[i] for i, L in zip(self._table_idx, self._lens) for _ in range(L)],
-                                        dtype=torch.int64, device=ids.device)
-        r = route_ids(ids, self._rb_dev, self.world, self._lens, self._bag, [i % self.world for i in self._table_idx])
+        vb = torch.tensor([self._vbase[i] for i, L in zip(self._table_idx, self._lens) for _ in range(L)],
+                          dtype=torch.int64, device=ids.device)
+        r = route_unique(ids, vb, self.world, self._lens, self._bag, [i % self.world for i in self._table_idx], self._lbits)
         # positions in the plan's layout: one block per table field (replicated tables: zeros, nothing is sent)
         full = torch.zeros(b * self._all_S, dtype=torch.int64, device=ids.device)
         mine = dict(zip(self._table_idx, field_positions(r.pos, b, self._lens)))
@@ -514,28 +565,17 @@ class ShardedFeatureEmbedding(IndexStatusMixin, nn.Module):
         shard = set(self._table_idx)
         return [blk for i, blk in zip(self._all_tables, field_positions(pos, b, self._all_lens)) if i in shard]
 
-    def reply_buffer(self, n: int, like: torch.Tensor) -> torch.Tensor:
-        """(1 + n, D + 4) buffer K1 reads as its table: row 0 is the reserved zero row (send positions are
-        1-based), rows 1.. receive the replies in send order."""
+    def reply_buffers(self, n: int, like: torch.Tensor):
+        """((1 + n, D) vectors, (1 + n, 4) scalars) K1 reads as its table: row 0 is the reserved zero row (positions
+        are 1-based), rows 1.. receive the replies in send order."""
         cap = getattr(self, "_virtual_cap", VIRTUAL_VOCAB)
         if n + 1 > cap:
             raise NotImplementedError(f"sharded tables: {n} exchanged rows per step exceed the plan capacity {cap}")
-        got = like.new_empty((n + 1, self.fm_embed_dim + 4))
-        got[0].zero_()
-        return got
-
-    def gather(self, recv_keys: torch.Tensor):
-        lib = _lib.lib()
-        local_plan, _ = self._ensure_plans()
-        params = self._ordered_params()
-        M = recv_keys.numel()
-        dev = params[0].device
-        rows = torch.empty((M, self.fm_embed_dim + 4), device=dev, dtype=torch.float32)
-        lkeys = torch.empty((M,), device=dev, dtype=torch.int32)
-        _lib.check(lib.dfm_shard_gather(local_plan, self.world, self.rank, _lib.i64_array(self._global_row_base), M,
-                                        _lib.ptr(recv_keys), self._ptrs(params), _lib.ptr(rows), _lib.ptr(lkeys),
-                                        _lib.stream_ptr()), "dfm_shard_gather")
-        return rows, lkeys
+        vec = like.new_empty((n + 1, self.fm_embed_dim))
+        sc = like.new_empty((n + 1, 4))
+        vec[0].zero_()
+        sc[0].zero_()
+        return vec, sc
 
     def peer_exchange(self, device):
         """The symmetric-memory exchange buffers (created on first use; None when peer memory is unavailable or
@@ -548,7 +588,7 @@ class ShardedFeatureEmbedding(IndexStatusMixin, nn.Module):
                 cap = int(getattr(self, "p2p_capacity_rows", 0)) or None
                 if cap is None:
                     return None           # sized by the first forward (needs the batch size)
-                self._px = PeerExchange(self.comm, self.fm_embed_dim + 4, cap, device)
+                self._px = PeerExchange(self.comm, self.fm_embed_dim, cap, device)
             except Exception as e:        # no P2P / symmetric memory on this box: keep the NCCL path
                 import warnings
                 warnings.warn(f"peer-memory exchange unavailable ({e}); using NCCL all-to-all")
@@ -556,43 +596,78 @@ class ShardedFeatureEmbedding(IndexStatusMixin, nn.Module):
                 return None
         return self._px
 
-    def gather_p2p(self, recv_keys: torch.Tensor, px: "PeerExchange", matrix, parity: int):
+    def gather(self, recv_keys: torch.Tensor, p2p=None):
+        """Owner side: the received unique keys -> rows.  Without ``p2p``: returns staging (vectors (M, D), scalars
+        (M, 4), backward keys (M,)); with ``p2p = (px, matrix, parity)`` every row is stored straight into the requesting
+        GPU's got buffers and only the backward keys are returned."""
         lib = _lib.lib()
         local_plan, _ = self._ensure_plans()
         params = self._ordered_params()
         M, W, me = recv_keys.numel(), self.world, self.rank
-        lkeys = torch.empty((M,), device=recv_keys.device, dtype=torch.int32)
-        stride_b = (self.fm_embed_dim + 4) * 4
-        starts, bases, acc = [0], [], 0
-        for s_ in range(W):                                   # received keys are grouped by source rank
-            acc += matrix[s_][me]
-            starts.append(acc)
-            send_off = sum(matrix[s_][:me])                   # where rank me's segment starts in s_'s send order
-            bases.append(px.region(0, parity, s_) + (1 + send_off) * stride_b)
-        _lib.check(lib.dfm_shard_gather_p2p(local_plan, W, me, _lib.i64_array(self._global_row_base), M,
-                                            _lib.ptr(recv_keys), self._ptrs(params), W, _lib.i64_array(starts),
-                                            _lib.ptr_array(bases), _lib.ptr(lkeys), _lib.stream_ptr()), "dfm_shard_gather_p2p")
-        return lkeys
+        dev = params[0].device
+        bkeys = torch.empty((max(M, 1),), device=dev, dtype=torch.int32)
+        if p2p is None:
+            vec = torch.empty((M, self.fm_embed_dim), device=dev, dtype=torch.float32)
+            sc = torch.empty((M, 4), device=dev, dtype=torch.float32)
+            starts, vecs, scs = [0, M], [vec.data_ptr()], [sc.data_ptr()]
+        else:
+            px, matrix, parity = p2p
+            starts, vecs, scs, acc = [0], [], [], 0
+            for s_ in range(W):                                   # received keys are grouped by source rank
+                acc += matrix[s_][me]
+                starts.append(acc)
+                send_off = sum(matrix[s_][:me])                   # where rank me's segment starts in s_'s send order
+                v, c = px.region(0, parity, s_)
+                vecs.append(v + (1 + send_off) * self.fm_embed_dim * 4)
+                scs.append(c + (1 + send_off) * 16)
+        if M > 0:
+            _lib.check(lib.dfm_shard_gather2(local_plan, W, me, M, _lib.ptr(recv_keys), self._ptrs(params), len(vecs),
+                                             _lib.i64_array(starts), _lib.ptr_array(vecs), _lib.ptr_array(scs),
+                                             _lib.ptr(bkeys), _lib.stream_ptr()), "dfm_shard_gather2")
+        bkeys = bkeys[:M]
+        return bkeys if p2p is not None else (vec, sc, bkeys)
 
-    def _virtual_ptrs(self, params, got):
-        """Sample-side plan: every id table is the received row buffer (row stride D + 4, first-order
-        weight at column D)."""
+    def sort_owner_keys(self, bkeys: torch.Tensor):
+        """Owner side: sort the backward keys NOW on a side stream (they depend on the ids only); the owner-side
+        backward then starts at the segmented reduction.  Returns (sorted_keys, sorted_payload, event, M)."""
+        lib = _lib.lib()
+        local_plan, _ = self._ensure_plans()
+        M = bkeys.numel()
+        dev = bkeys.device
+        if M == 0:
+            return None
+        cur = torch.cuda.current_stream(dev)
+        side = self._side_stream(dev)
+        side.wait_stream(cur)
+        with torch.cuda.stream(side):
+            skeys = torch.empty((M,), device=dev, dtype=torch.int32)
+            spay = torch.empty((M,), device=dev, dtype=torch.int32)
+            pay = torch.arange(M, device=dev, dtype=torch.int32)       # payload = row of the received buffers
+            ws = torch.empty((max(lib.dfm_sort_pairs_workspace_bytes(M, self._lbits), 16),), device=dev, dtype=torch.uint8)
+            _lib.check(lib.dfm_sort_pairs(M, self._lbits, bkeys.data_ptr(), pay.data_ptr(), skeys.data_ptr(), spay.data_ptr(),
+                                          ws.data_ptr(), ws.numel(), side.cuda_stream), "dfm_sort_pairs")
+            ev = torch.cuda.Event()
+            ev.record(side)
+        bkeys.record_stream(side)
+        return skeys, spay, ev, M
+
+    def _virtual_ptrs(self, params, got_vec, got_sc):
+        """Sample-side plan: every sharded id table is the received row buffers."""
         arr = self._ptrs(params)
-        D = self.fm_embed_dim
-        for i in self._sparse_idx:
-            arr[5 * i + 0] = got.data_ptr()
-            arr[5 * i + 2] = got.data_ptr() + 4 * D
+        for i in self._table_idx:
+            arr[5 * i + 0] = got_vec.data_ptr()
+            arr[5 * i + 2] = got_sc.data_ptr()
         return arr
 
-    def finish(self, inputs, pos, got, need_bwd: bool):
+    def finish(self, inputs, pos, got_vec, got_sc, need_bwd: bool):
         lib = _lib.lib()
         _, sample_plan = self._ensure_plans()
         params = self._ordered_params()
-        dev = got.device
+        dev = got_vec.device
         b = inputs[0].shape[0]
         F, D, T = self.num_fields, self.fm_embed_dim, self._T
         blocks = dict(zip(self._table_idx, self.sharded_positions(pos, b)))
-        fin_inputs = [blocks.get(i, inputs[i]) for i in range(F)]     # sharded: send positions; replicated / DENSE: the input
+        fin_inputs = [blocks.get(i, inputs[i]) for i in range(F)]     # sharded: reply positions; replicated / DENSE: the input
         flat = torch.empty((b, T), device=dev, dtype=torch.float32)
         field = flat.view(b, F, D)
         first = torch.empty((b, 1), device=dev, dtype=torch.float32)
@@ -601,44 +676,56 @@ class ShardedFeatureEmbedding(IndexStatusMixin, nn.Module):
         aux = torch.empty((b, max(self._A, 1)), device=dev, dtype=torch.int32)
         # sort keys of the replicated tables' ids (sharded slots get the PAD key): their backward is local
         keys = torch.empty((b * self._all_S,), device=dev, dtype=torch.int32) if (need_bwd and self._repl_idx) else None
-        _lib.check(lib.dfm_embed_fwd(sample_plan, b, _lib.ptr_array(fin_inputs), self._virtual_ptrs(params, got),
+        _lib.check(lib.dfm_embed_fwd(sample_plan, b, _lib.ptr_array(fin_inputs), self._virtual_ptrs(params, got_vec, got_sc),
                                      first.data_ptr(), field.data_ptr(), flat.data_ptr(), fm.data_ptr(),
                                      _lib.ptr(fm_sum), _lib.ptr(keys), aux.data_ptr(), None, _lib.stream_ptr()), "dfm_embed_fwd")
         return first, field, flat, fm, fm_sum, aux, fin_inputs, keys
 
-    def pack_grads(self, fin_inputs, pos, got, g_first, g_field, g_flat, g_fm, field, flat, fm_sum,
-                   params, lam, gscale, aux=None, p2p=None, keys=None):
+    def reduce_grads(self, route: Route, g_first, g_field, g_flat, g_fm, field, fm_sum, aux, p2p=None):
+        """Sample side backward of the sharded tables: the gradient rows of all slots that share a key are summed (in
+        the sorted order of ``route``) and one row per unique key goes to its owner -- straight into the owner's
+        g_recv buffers with ``p2p = (px, matrix, parity)``, else into staging (vectors, scalars) in send order."""
+        lib = _lib.lib()
+        _, sample_plan = self._ensure_plans()
+        dev = field.device
+        b = field.shape[0]
+        W, me = self.world, self.rank
+        n = route.n_sorted
+        if p2p is None:
+            sv = torch.empty((max(n, 1), self.fm_embed_dim), device=dev, dtype=torch.float32)
+            ss = torch.empty((max(n, 1), 4), device=dev, dtype=torch.float32)
+            starts, vecs, scs = [0, n], [sv.data_ptr()], [ss.data_ptr()]
+        else:
+            px, matrix, parity = p2p
+            sv = ss = None
+            starts, vecs, scs, acc = [0], [], [], 0
+            for r_ in range(W):                               # my send order is grouped by owner rank
+                acc += matrix[me][r_]
+                starts.append(acc)
+                recv_off = sum(matrix[s_][r_] for s_ in range(me))   # where my segment starts in r_'s receive order
+                v, c = px.region(1, parity, r_)
+                vecs.append(v + recv_off * self.fm_embed_dim * 4)
+                scs.append(c + recv_off * 16)
+        if n > 0 and b > 0:
+            ws = torch.empty((max(lib.dfm_rows_bwd_workspace_bytes(sample_plan, n), 16),), device=dev, dtype=torch.uint8)
+            _lib.check(lib.dfm_shard_bwd_peer(sample_plan, b, _lib.ptr(g_first), _lib.ptr(g_field), _lib.ptr(g_flat),
+                                              _lib.ptr(g_fm), field.data_ptr(), _lib.ptr(fm_sum), _lib.ptr(aux),
+                                              _lib.ptr(route.skeys), _lib.ptr(route.spay), _lib.ptr(route.uidx), n,
+                                              self._pad_key, len(vecs), _lib.i64_array(starts), _lib.ptr_array(vecs),
+                                              _lib.ptr_array(scs), float(self.grad_scale), ws.data_ptr(), ws.numel(),
+                                              _lib.stream_ptr()), "dfm_shard_bwd_peer")
+        return sv, ss
+
+    def local_grads(self, fin_inputs, got_vec, got_sc, g_first, g_field, g_flat, g_fm, field, flat, fm_sum,
+                    params, lam, gscale, aux=None, keys=None):
+        """Data-parallel parameters of the embedding: DENSE-field Linears and the replicated (small) tables.
+        K2 on the sample-side plan; the sharded tables are foreign there, so only the replicated ones are
+        sorted / segment-reduced (dense (V, d) gradients, 2*l2*w on every row like the reference)."""
         lib = _lib.lib()
         _, sample_plan = self._ensure_plans()
         self._ordered_params()
         dev = flat.device
         b = flat.shape[0]
-        n = got.shape[0] - 1
-        if p2p is not None:
-            px, matrix, parity, send_slots = p2p
-            W, me = self.world, self.rank
-            stride_b = (self.fm_embed_dim + 4) * 4
-            starts, bases, acc = [0], [], 0
-            for r_ in range(W):                               # my send order is grouped by owner rank
-                acc += matrix[me][r_]
-                starts.append(acc)
-                recv_off = sum(matrix[s_][r_] for s_ in range(me))   # where my segment starts in r_'s receive order
-                bases.append(px.region(1, parity, r_) + recv_off * stride_b)
-            g_rows = None
-            _lib.check(lib.dfm_shard_pack_grad_p2p(sample_plan, b, _lib.ptr(pos), _lib.ptr(g_first), _lib.ptr(g_field),
-                                                   _lib.ptr(g_flat), _lib.ptr(g_fm), _lib.ptr(fm_sum), field.data_ptr(),
-                                                   _lib.ptr(aux), W, _lib.i64_array(starts), _lib.ptr_array(bases),
-                                                   _lib.ptr(send_slots), float(self.grad_scale), _lib.stream_ptr()),
-                       "dfm_shard_pack_grad_p2p")
-        else:
-            g_rows = torch.empty((n, self.fm_embed_dim + 4), device=dev, dtype=torch.float32)
-            _lib.check(lib.dfm_shard_pack_grad(sample_plan, b, _lib.ptr(pos), _lib.ptr(g_first), _lib.ptr(g_field),
-                                               _lib.ptr(g_flat), _lib.ptr(g_fm), _lib.ptr(fm_sum), field.data_ptr(),
-                                               _lib.ptr(aux), _lib.ptr(g_rows), float(self.grad_scale), _lib.stream_ptr()),
-                       "dfm_shard_pack_grad")
-        # Data-parallel parameters of the embedding: DENSE-field Linears and the replicated (small) tables.
-        # K2 on the sample-side plan; the sharded tables are foreign there, so only the replicated ones are
-        # sorted / segment-reduced (dense (V, d) gradients, 2*l2*w on every row like the reference).
         dense_grads: Dict[int, torch.Tensor] = {}
         grads = []
         for i, (p, tab) in enumerate(zip(params, self._param_is_table)):
@@ -655,18 +742,19 @@ class ShardedFeatureEmbedding(IndexStatusMixin, nn.Module):
                 skeys = torch.empty_like(keys)
                 spay = torch.empty_like(keys)
             _lib.check(lib.dfm_embed_bwd(
-                sample_plan, b, _lib.ptr_array(fin_inputs), self._virtual_ptrs(params, got),
+                sample_plan, b, _lib.ptr_array(fin_inputs), self._virtual_ptrs(params, got_vec, got_sc),
                 _lib.ptr(g_first), _lib.ptr(g_field), _lib.ptr(g_flat), _lib.ptr(g_fm), field.data_ptr(), flat.data_ptr(),
                 _lib.ptr(fm_sum), _lib.ptr(keys), _lib.ptr(aux), float(lam), _lib.ptr(gscale), mode, self._ptrs(grads),
                 _lib.ptr(skeys), _lib.ptr(spay), None, None, None, ws.data_ptr(), ws.numel(), _lib.stream_ptr()), "dfm_embed_bwd")
-        return g_rows, dense_grads
+        return dense_grads
 
-    def owner_backward(self, lkeys, g_recv, params, lam, gscale):
+    def owner_backward(self, bsorted, g_vec, g_sc, params, lam, gscale):
+        """Owner side: K2 on the received unique rows (keys sorted ahead by ``sort_owner_keys``); every row's gradient
+        is produced on exactly one GPU."""
         lib = _lib.lib()
         local_plan, _ = self._ensure_plans()
         self._ordered_params()
-        dev = g_recv.device
-        M = lkeys.numel()
+        dev = g_vec.device
         rowsparse = self.grad_mode == "row_sparse"
         grads, table_grads = [], {}
         for i, (p, tab) in enumerate(zip(params, self._param_is_table)):
@@ -674,18 +762,29 @@ class ShardedFeatureEmbedding(IndexStatusMixin, nn.Module):
             grads.append(g)
             if g is not None:
                 table_grads[i] = g
-        ws = torch.empty((max(lib.dfm_rows_bwd_workspace_bytes(local_plan, M), 16),), device=dev, dtype=torch.uint8)
-        skeys = torch.empty((max(M, 1),), device=dev, dtype=torch.int32)
-        spay = torch.empty((max(M, 1),), device=dev, dtype=torch.int32)
+        M = 0 if bsorted is None else bsorted[3]
         counts = torch.zeros((2,), device=dev, dtype=torch.int64)
+        if M == 0:
+            for g in table_grads.values():
+                g.zero_()
+            self.row_grads = None
+            self.last_counts = counts
+            return table_grads
+        skeys, spay, ev, _ = bsorted
+        cur = torch.cuda.current_stream(dev)
+        cur.wait_event(ev)
+        skeys.record_stream(cur)
+        spay.record_stream(cur)
+        ws = torch.empty((max(lib.dfm_rows_bwd_workspace_bytes(local_plan, M), 16),), device=dev, dtype=torch.uint8)
         rg2 = rg1 = None
         if rowsparse:
-            rg2 = torch.empty((max(M, 1), self.fm_embed_dim), device=dev, dtype=torch.float32)
-            rg1 = torch.empty((max(M, 1),), device=dev, dtype=torch.float32)
-        _lib.check(lib.dfm_rows_bwd(local_plan, M, self._ptrs(params), _lib.ptr(lkeys), _lib.ptr(g_recv),
-                                    float(lam), _lib.ptr(gscale), _lib.GRAD_ROWSPARSE if rowsparse else _lib.GRAD_DENSE,
-                                    self._ptrs(grads), skeys.data_ptr(), spay.data_ptr(), _lib.ptr(rg2), _lib.ptr(rg1),
-                                    counts.data_ptr(), ws.data_ptr(), ws.numel(), _lib.stream_ptr()), "dfm_rows_bwd")
+            rg2 = torch.empty((M, self.fm_embed_dim), device=dev, dtype=torch.float32)
+            rg1 = torch.empty((M,), device=dev, dtype=torch.float32)
+        mode = (_lib.GRAD_ROWSPARSE if rowsparse else _lib.GRAD_DENSE) | _lib.GRAD_PRESORTED
+        _lib.check(lib.dfm_rows_bwd(local_plan, M, self._ptrs(params), None, _lib.ptr(g_vec), _lib.ptr(g_sc),
+                                    float(lam), _lib.ptr(gscale), mode, self._ptrs(grads), skeys.data_ptr(), spay.data_ptr(),
+                                    _lib.ptr(rg2), _lib.ptr(rg1), counts.data_ptr(), ws.data_ptr(), ws.numel(),
+                                    _lib.stream_ptr()), "dfm_rows_bwd")
         self.row_grads = RowSparseGrads(skeys, spay, rg2, rg1, counts, self._row_base, self._dims, self.field_names) \
             if rowsparse else None
         self.last_counts = counts
@@ -730,12 +829,12 @@ class ShardedFeatureEmbedding(IndexStatusMixin, nn.Module):
         params = self._ordered_params()
         inputs = self._prepare(batch)
         if not self.p2p_capacity_rows:    # every rank derives the same capacity (same batch size and schema)
-            self.p2p_capacity_rows = 2 * inputs[0].shape[0] * max(self._S, 1) + 16
+            self.p2p_capacity_rows = inputs[0].shape[0] * max(self._S, 1) + 16
         need_bwd = torch.is_grad_enabled() and any(p.requires_grad for p in params)
         if self._status_pending and self.check_indices:
             self.raise_if_bad_index(block=True, keep=2)
-        first, field, flat, fm = _ShardedEmbedFn.apply(self, len(inputs), need_bwd, *inputs, *params)
-        self._live_anchor = weakref.ref(first) if need_bwd else None
+        first, field, flat, fm, anchor = _ShardedEmbedFn.apply(self, len(inputs), need_bwd, *inputs, *params)
+        self._live_anchor = anchor if (need_bwd and anchor.requires_grad) else None
         field._dfm_fm = (fm, field._version)
         return first, field, flat, fm
 

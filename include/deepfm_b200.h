@@ -268,6 +268,47 @@ DFM_API int dfm_shard_pack_grad_p2p(const dfm_plan* plan, int64_t batch, const i
                                     const uint32_t* aux, int n_peers, const int64_t* peer_start,
                                     float* const* peer_rows, const uint32_t* send_slots, float grad_scale,
                                     void* stream);
+/* Exchange of UNIQUE rows (v2; what ShardedFeatureEmbedding uses).  Under CTR-like skew most id slots of a batch
+ * repeat a row the same GPU already asked the same owner for, so every distinct (owner, row) travels once per step
+ * and direction.  Local tables are sized ceil(V / W) rows on every rank, so the owner's sort key of a row,
+ * lkey = vbase[f] + id div W (vbase = exclusive prefix sum of ceil(V / W) over the sharded fields), is the same number
+ * on every rank.
+ *   dfm_shard_ukeys  : sample side.  Per sharded id slot (compact index j = b * S_sh + ts): key = owner << lbits | lkey
+ *       (PAD = world << lbits for an unsent bag padding entry), payload = b << pbits | plan slot (the layout K2 decodes);
+ *       positions (the plan's (B, max_len) blocks, see dfm_shard_route) are zeroed; out-of-range ids -> id 0 + *status.
+ *   dfm_sort_pairs   : stable radix sort of (key, payload) on the low `bits` bits (CUB).
+ *   dfm_shard_unique : sorted keys -> unique_keys (lkeys in send order: grouped by owner, ascending), counts (W),
+ *       unique_index[p] = ordinal of position p's key, positions[slot] = 1 + that ordinal (row of the reply buffer).
+ *   dfm_shard_gather2: owner side.  local_keys (lkeys as received, grouped by source) -> vector rows (d floats) and
+ *       scalar rows [first-order weight, 0, 0, 0] stored into the requesters' buffers: row i of source segment
+ *       [peer_start[p], peer_start[p+1]) goes to peer_vec[p] + (i - start) * d / peer_sc[p] + (i - start) * 4 (peer
+ *       memory, or a local staging buffer with n_peers = 1); backward_keys = lkey, PAD for the padding row id 0.
+ *   dfm_shard_bwd_peer: sample side backward.  K2's segmented reduction over the sample-side sorted (key, payload)
+ *       stream: the gradient rows of all slots that share a key are summed in sorted order and ONE row per unique
+ *       key -- [sum scale * (g_flat + g_field + g_fm * (fm_sum [- e_bag]))] and [sum g_first, sum g_fm, 0, 0], times
+ *       grad_scale -- is stored into the owner's buffers at the key's position in the send order.
+ *   dfm_rows_bwd with g_scalars != NULL consumes that split layout on the owner ((n, d) vectors + (n, 4) scalars). */
+DFM_API int dfm_shard_ukeys(const dfm_plan* plan, int world, const int64_t* vbase, const int64_t* vocab, int lbits,
+                            int64_t batch, const void* const* inputs, uint32_t* keys, uint32_t* payload,
+                            int64_t* positions, int32_t* status, void* stream);
+DFM_API size_t dfm_sort_pairs_workspace_bytes(int64_t n, int bits);
+DFM_API int dfm_sort_pairs(int64_t n, int bits, const uint32_t* keys, const uint32_t* payload, uint32_t* sorted_keys,
+                           uint32_t* sorted_payload, void* workspace, size_t workspace_bytes, void* stream);
+DFM_API size_t dfm_shard_unique_workspace_bytes(int64_t n);
+DFM_API int dfm_shard_unique(const dfm_plan* plan, int world, int lbits, int64_t batch, int64_t n,
+                             const uint32_t* sorted_keys, const uint32_t* sorted_payload, uint32_t* unique_keys,
+                             uint32_t* unique_index, int64_t* positions, int64_t* counts, void* workspace,
+                             size_t workspace_bytes, void* stream);
+DFM_API int dfm_shard_gather2(const dfm_plan* local_plan, int world, int rank, int64_t n_keys,
+                              const uint32_t* local_keys, const float* const* params, int n_peers,
+                              const int64_t* peer_start, float* const* peer_vec, float* const* peer_sc,
+                              uint32_t* backward_keys, void* stream);
+DFM_API int dfm_shard_bwd_peer(const dfm_plan* plan, int64_t batch, const float* g_first, const float* g_field,
+                               const float* g_flat, const float* g_fm, const float* field_emb, const float* fm_sum,
+                               const uint32_t* aux, const uint32_t* sorted_keys, const uint32_t* sorted_payload,
+                               const uint32_t* unique_index, int64_t n_sorted, uint32_t pad_key, int n_peers,
+                               const int64_t* peer_start, float* const* peer_vec, float* const* peer_sc,
+                               float grad_scale, void* workspace, size_t workspace_bytes, void* stream);
 /* Per-field table source of a plan: row_stride / w1_stride (floats, 0 = dim / 1) let K1 read the field's rows
  * out of a strided buffer (the received reply rows); foreign = 1 marks a table whose gradient is produced
  * elsewhere: K1 emits no sort key for its ids and dfm_embed_bwd / dfm_rows_bwd ignore it.  On the sample-side
@@ -278,7 +319,7 @@ DFM_API int dfm_plan_set_field_source(dfm_plan* plan, int field, int row_stride,
 DFM_API int dfm_plan_set_table_stride(dfm_plan* plan, int row_stride, int w1_stride);
 DFM_API size_t dfm_rows_bwd_workspace_bytes(const dfm_plan* plan, int64_t n_rows);
 DFM_API int dfm_rows_bwd(const dfm_plan* plan, int64_t n_rows, const float* const* params,
-                         const uint32_t* keys, const float* g_rows, float l2,
+                         const uint32_t* keys, const float* g_rows, const float* g_scalars, float l2,
                          const float* l2_gscale, int mode, float* const* grads, uint32_t* sorted_keys,
                          uint32_t* sorted_payload, float* row_grad2, float* row_grad1, int64_t* n_valid,
                          void* workspace, size_t workspace_bytes, void* stream);

@@ -511,6 +511,27 @@ def shard_route(ids: np.ndarray, world: int, sent: Optional[np.ndarray] = None, 
     return owner, local, counts, offsets, perm
 
 
+def shard_route_unique(ids: np.ndarray, vbase: np.ndarray, world: int, lbits: int, sent: Optional[np.ndarray] = None,
+                       rot: Optional[np.ndarray] = None):
+    """Unique-row exchange (the routing ShardedFeatureEmbedding uses): every DISTINCT (owner, row) of the batch travels
+    once.  ids / vbase / rot / sent: flat arrays in source order (slot index b*S + s).  owner = (id + rot) mod W,
+    owner-local key = vbase + id div W (vbase: rows of the sharded tables before the slot's field, every shard sized
+    ceil(V / W), so the key is the same number on every rank), composite = owner << lbits | key.  The send order is the
+    ascending list of distinct composites of the SENT slots (hence grouped by owner).
+    Returns (send_keys (U,) = key part in send order, counts (W,), position (n,) = 1 + index of the slot's composite in
+    the send order, 0 for unsent slots, composite (n,))."""
+    ids = ids.astype(np.int64)
+    owner = (ids + (0 if rot is None else rot)) % world
+    comp = (owner << lbits) | (vbase.astype(np.int64) + ids // world)
+    if sent is None:
+        sent = np.ones(ids.shape, dtype=bool)
+    uniq = np.unique(comp[sent])
+    counts = np.bincount(uniq >> lbits, minlength=world).astype(np.int64)[:world]
+    pos = np.zeros(ids.shape, dtype=np.int64)
+    pos[sent] = np.searchsorted(uniq, comp[sent]) + 1
+    return (uniq & ((1 << lbits) - 1)).astype(np.int64), counts, pos, comp
+
+
 def shard_positions(perm: np.ndarray, b: int, lens: Sequence[int]) -> np.ndarray:
     """1-based send position of every id slot in the field-major layout the kernels use: field f's
     (b, L_f) block starts at b * slot_base[f]; 0 = not sent."""
@@ -518,6 +539,17 @@ def shard_positions(perm: np.ndarray, b: int, lens: Sequence[int]) -> np.ndarray
     pos = np.zeros(b * S, dtype=np.int64)
     pos[perm] = np.arange(1, perm.size + 1)
     pos = pos.reshape(b, S)
+    out, s0 = [], 0
+    for L in lens:
+        out.append(pos[:, s0:s0 + L].reshape(-1))
+        s0 += L
+    return np.concatenate(out)
+
+
+def shard_positions_from(pos_flat: np.ndarray, b: int, lens: Sequence[int]) -> np.ndarray:
+    """Per-slot values in source order (b*S + s) -> the field-major layout the kernels use (see shard_positions)."""
+    S = int(sum(lens))
+    pos = np.asarray(pos_flat).reshape(b, S)
     out, s0 = [], 0
     for L in lens:
         out.append(pos[:, s0:s0 + L].reshape(-1))

@@ -12,40 +12,40 @@ import torch
 import torch.multiprocessing as mp
 
 from deepfm_b200.schema import DatasetSchema, FeatureType, FieldSchema
-from deepfm_b200.sharded import Route, field_positions, local_rows, route_ids
+from deepfm_b200.sharded import Route, field_positions, local_rows, owned_rows, route_unique
 from oracle import deepfm_oracle as O
 from tests.helpers import assert_close_rel
 
 
-def test_route_ids_matches_oracle_shard_route():
+def test_route_unique_matches_oracle():
     rng = np.random.default_rng(0)
-    b, S, W = 57, 5, 4
+    b, S, W, lbits = 57, 5, 4, 12
     vocab = [11, 300, 7, 1000, 50]
-    ids = np.stack([rng.integers(0, v, b) for v in vocab], axis=1).astype(np.int64)
-    row_base = np.concatenate([[0], np.cumsum(vocab)[:-1]]).astype(np.int64)
-    r = route_ids(torch.from_numpy(ids), torch.from_numpy(row_base), W)
-    owner, local, counts, offsets, perm = O.shard_route(ids.reshape(-1), W)
-    assert r.counts.tolist() == counts.tolist()
-    assert r.order.tolist() == perm.tolist()
-    keys = (ids + row_base[None, :]).reshape(-1)
-    assert r.send_keys.tolist() == keys[perm].tolist()
-    pos = r.pos.view(S, b).t().reshape(-1).numpy()               # slot index -> 1-based send position
-    assert np.array_equal(perm[pos - 1], np.arange(b * S))
-    assert np.array_equal(r.pos.numpy(), O.shard_positions(perm, b, [1] * S))
-    for w in range(W):                                            # every key of bucket w is owned by w
-        seg = perm[offsets[w]:offsets[w + 1]]
-        assert np.all(ids.reshape(-1)[seg] % W == w)
-    assert local_rows(10, 4, 0) == 3 and local_rows(10, 4, 1) == 3 and local_rows(10, 4, 2) == 2 and local_rows(2, 4, 3) == 1
+    ids = np.stack([((rng.zipf(1.3, b) - 1) % v) for v in vocab], axis=1).astype(np.int64)      # repeats: the point of dedup
+    lv = [local_rows(v, W) for v in vocab]
+    vbase = np.concatenate([[0], np.cumsum(lv)[:-1]]).astype(np.int64)
+    rot = np.arange(S) % W
+    r = route_unique(torch.from_numpy(ids), torch.from_numpy(vbase), W, rot=list(rot), lbits=lbits)
+    send, counts, pos, comp = O.shard_route_unique(ids.reshape(-1), np.tile(vbase, b), W, lbits, rot=np.tile(rot, b))
+    assert r.counts.tolist() == counts.tolist() and r.send_keys.tolist() == send.tolist()
+    assert np.array_equal(r.pos.numpy(), O.shard_positions_from(pos, b, [1] * S))
+    assert len(send) < b * S                                   # duplicates travel once
+    # every slot finds ITS row: the key at its position, owned by its owner
+    offs = np.concatenate([[0], np.cumsum(counts)])
+    owner_of_pos = np.searchsorted(offs, pos - 1, side="right") - 1
+    assert np.array_equal(owner_of_pos, (ids.reshape(-1) + np.tile(rot, b)) % W)
+    assert np.array_equal(send[pos - 1], np.tile(vbase, b) + ids.reshape(-1) // W)
+    assert local_rows(10, 4) == 3 and local_rows(2, 4) == 1 and local_rows(1000, 8) == 125
     # rotated rule: field 1 puts id 0 on rank 1, so rank 0 owns ids 3 and 7 of a 10-row table
-    assert local_rows(10, 4, 0, field=1) == 2 and local_rows(10, 4, 1, field=1) == 3
-    assert sum(local_rows(1000, 8, r, field=5) for r in range(8)) == 1000
+    assert owned_rows(10, 4, 0, field=1) == 2 and owned_rows(10, 4, 1, field=1) == 3
+    assert sum(owned_rows(1000, 8, r, field=5) for r in range(8)) == 1000
 
 
-def test_route_ids_multihot_skips_bag_padding():
+def test_route_unique_multihot_skips_bag_padding():
     """Bags are exchanged id by id; their padding entries (id 0, anywhere in the bag) are not sent, while the
     padding id of a SPARSE field is (its row 0 is returned as stored, embedding.py:35-40)."""
     rng = np.random.default_rng(1)
-    b, W = 41, 3
+    b, W, lbits = 41, 3, 10
     lens, bag, vocab = [1, 4, 1, 6], [False, True, False, True], [30, 17, 5, 200]
     cols = []
     for L, g, v in zip(lens, bag, vocab):
@@ -55,21 +55,17 @@ def test_route_ids_multihot_skips_bag_padding():
             x[3] = 0                                       # an all-pad bag
         cols.append(x)
     ids = np.concatenate(cols, axis=1).astype(np.int64)
-    S = ids.shape[1]
-    fbase = np.concatenate([[0], np.cumsum(vocab)[:-1]])
-    row_base = np.repeat(fbase, lens).astype(np.int64)
+    lv = [local_rows(v, W) for v in vocab]
+    fbase = np.concatenate([[0], np.cumsum(lv)[:-1]])
+    vbase = np.repeat(fbase, lens).astype(np.int64)
     slot_bag = np.repeat(bag, lens)
     sent = ~(slot_bag[None, :] & (ids == 0))
     rot = [2, 0, 1, 2]                                     # owner = (id + rot[field]) mod W
     slot_rot = np.repeat(rot, lens)
-    r = route_ids(torch.from_numpy(ids), torch.from_numpy(row_base), W, lens, bag, rot)
-    owner, local, counts, offsets, perm = O.shard_route(ids.reshape(-1), W, sent.reshape(-1), np.tile(slot_rot, b))
-    assert np.array_equal(owner, (ids + slot_rot[None, :]).reshape(-1) % W)
-    assert r.counts.tolist() == counts.tolist() and int(counts.sum()) == int(sent.sum())
-    assert r.order.tolist() == perm.tolist()
-    keys = (ids + row_base[None, :]).reshape(-1)
-    assert r.send_keys.tolist() == keys[perm].tolist()
-    assert np.array_equal(r.pos.numpy(), O.shard_positions(perm, b, lens))
+    r = route_unique(torch.from_numpy(ids), torch.from_numpy(vbase), W, lens, bag, rot, lbits)
+    send, counts, pos, comp = O.shard_route_unique(ids.reshape(-1), np.tile(vbase, b), W, lbits, sent.reshape(-1), np.tile(slot_rot, b))
+    assert r.counts.tolist() == counts.tolist() and r.send_keys.tolist() == send.tolist()
+    assert np.array_equal(r.pos.numpy(), O.shard_positions_from(pos, b, lens))
     blocks = field_positions(r.pos, b, lens)
     assert [tuple(t.shape) for t in blocks] == [(b,), (b, 4), (b,), (b, 6)]
     assert torch.equal(blocks[1] == 0, torch.from_numpy(cols[1] == 0))      # exactly the pads are unsent
@@ -84,22 +80,27 @@ def _gloo_worker(rank, world, port, out):
     comm = TorchDistComm()
     gen = torch.Generator().manual_seed(100 + rank)
     vocab = [13, 40, 9]
+    lbits = 8
     ids = torch.stack([torch.randint(0, v, (20,), generator=gen) for v in vocab], dim=1)
-    row_base = torch.tensor([0, 13, 53])
-    r = route_ids(ids, row_base, world)
+    lv = [local_rows(v, world) for v in vocab]
+    vbase = torch.tensor([0, lv[0], lv[0] + lv[1]])
+    r = route_unique(ids, vbase, world, lbits=lbits)
     send_counts, recv_counts = comm.exchange_counts(r.counts)
     assert send_counts == r.counts.tolist()
     recv_keys = comm.all_to_all(r.send_keys, send_counts, recv_counts)
-    # owner check: (key - row_base[field]) mod W == rank
+    # owner check: a received key names a row of a table this rank owns: row < ceil(V / W) of its field
     k = recv_keys.long()
-    field = (k[:, None] >= row_base[None, :]).sum(1) - 1
-    ok_owner = bool(torch.all((k - row_base[field]) % world == rank))
-    # reply with a function of the key; the sender must get it back in send order
-    reply = comm.all_to_all((k * 3 + 1).float()[:, None].repeat(1, 2), recv_counts, send_counts)
-    ok_reply = bool(torch.equal(reply[:, 0], r.send_keys.float() * 3 + 1))
+    field = (k[:, None] >= vbase[None, :]).sum(1) - 1
+    ok_owner = bool(torch.all(k - vbase[field] < torch.tensor(lv)[field]))
+    # reply with a function of (rank, key); the sender must get it back in send order
+    reply = comm.all_to_all((k * 3 + 1 + 1000 * rank).float()[:, None].repeat(1, 2), recv_counts, send_counts)
+    owner_of_send = torch.repeat_interleave(torch.arange(world), torch.tensor(send_counts))
+    ok_reply = bool(torch.equal(reply[:, 0], r.send_keys.float() * 3 + 1 + 1000 * owner_of_send))
+    # every slot reads ITS row out of the reply buffer through its position
     back = reply[:, 0][r.pos.view(3, 20).t().reshape(-1) - 1]     # slot order
-    ok_slot = bool(torch.equal(back, ((ids + row_base[None, :]).reshape(-1) * 3 + 1).float()))
-    out.put((rank, ok_owner, ok_reply, ok_slot, sum(recv_counts)))
+    want = ((vbase[None, :] + ids // world) * 3 + 1 + 1000 * (ids % world)).reshape(-1).float()
+    ok_slot = bool(torch.equal(back, want))
+    out.put((rank, ok_owner, ok_reply, ok_slot, sum(recv_counts), int(r.counts.sum())))
     dist.destroy_process_group()
 
 
@@ -115,7 +116,7 @@ def test_all_to_all_plumbing_gloo_world2():
         p.join(timeout=60)
         assert p.exitcode == 0
     assert all(r[1] and r[2] and r[3] for r in res), res
-    assert sum(r[4] for r in res) == 2 * 20 * 3                   # every key arrived somewhere
+    assert sum(r[4] for r in res) == sum(r[5] for r in res) <= 2 * 20 * 3     # every unique key arrived somewhere, once
 
 
 def test_sharded_module_bookkeeping_cpu():
@@ -133,8 +134,9 @@ def test_sharded_module_bookkeeping_cpu():
         assert m.second_order_embeddings[names[i]].weight.shape[0] == schema.fields[names[i]].vocabulary_size
     for i in m._table_idx:                                                # sharded: the ranks' shards partition the ids
         V = schema.fields[names[i]].vocabulary_size
-        if V >= W:
-            assert sum(mm.second_order_embeddings[names[i]].weight.shape[0] for mm in mods) == V
+        # every shard is sized ceil(V / W) (a row's local key is then the same number on every rank) ...
+        assert all(mm.second_order_embeddings[names[i]].weight.shape[0] == local_rows(V, W) for mm in mods)
+        assert sum(owned_rows(V, W, r, field=i) for r in range(W)) == V      # ... and the owned ids partition the table
     assert [p.shape[0] > 0 for p in m.table_parameters()] and len(m.table_parameters()) == 2 * len(m._table_idx)
     # routing restatement: replicated fields send nothing, sharded fields follow (id + field) mod W
     rng = np.random.default_rng(3)
@@ -160,21 +162,35 @@ def test_sharded_module_bookkeeping_cpu():
             bounds = torch.cumsum(r.counts, 0)
             got_owner = torch.bucketize(blk - 1, bounds, right=True)
             assert torch.equal(got_owner[sent], owner[sent])
+            key = m._vbase[i] + ins[i].reshape(blk.shape) // W                # the slot's position names ITS row
+            assert torch.equal(r.send_keys.long()[(blk - 1).clamp_min(0)][sent], key[sent])
 
 
 def test_peer_exchange_layout_and_capacity_logic():
     """Host arithmetic of PeerExchange (no GPU): buffer regions, and the collective-safe capacity decision."""
     from deepfm_b200.sharded import PeerExchange
     px = PeerExchange.__new__(PeerExchange)                 # the constructor needs symmetric memory; the logic does not
-    px.world, px.rank, px.row_floats, px.cap = 3, 1, 68, 1000
+    px.world, px.rank, px.dim, px.cap = 3, 1, 64, 1024
     px.peer_base = [1 << 30, 2 << 30, 3 << 30]
-    stride = 1000 * 68 * 4
-    assert px.region(0, 0) == (2 << 30) and px.region(0, 1) == (2 << 30) + stride
-    assert px.region(1, 0, rank=2) == (3 << 30) + 2 * stride and px.region(1, 1, rank=0) == (1 << 30) + 3 * stride
+    stride = 1024 * 68 * 4                                   # one (kind, parity) block: (cap, 64) vectors + (cap, 4) scalars
+    assert px.region(0, 0) == (2 << 30, (2 << 30) + 1024 * 64 * 4)
+    assert px.region(0, 1) == ((2 << 30) + stride, (2 << 30) + stride + 1024 * 64 * 4)
+    assert px.region(1, 0, rank=2)[0] == (3 << 30) + 2 * stride and px.region(1, 1, rank=0)[0] == (1 << 30) + 3 * stride
+    assert all(a % 256 == 0 for a in px.region(1, 1, rank=0))    # 256-byte rows start on 256-byte boundaries
     ok = [[100, 200, 300], [50, 60, 70], [400, 100, 100]]   # matrix[s][r]: rows s sends to r
     assert px.fits(ok)                                       # max sent 600 (+ the zero row), max received 550
-    assert not px.fits([[500, 499, 1], [0, 0, 0], [0, 0, 0]])   # 1000 sent + the zero row > capacity
+    assert not px.fits([[524, 499, 1], [0, 0, 0], [0, 0, 0]])   # 1024 sent + the zero row > capacity
     assert not px.fits([[400, 0, 0], [400, 0, 0], [400, 0, 0]])  # rank 0 would receive 1200 rows
+
+
+def test_peer_memory_shim_matches_installed_torch():
+    """deepfm_b200/_peer.py is the only user of torch's private symmetric-memory module: the names it relies on exist."""
+    from deepfm_b200 import _peer
+    import importlib
+    if not _peer.available():
+        pytest.skip("this torch build has no torch.distributed._symmetric_memory")
+    symm = importlib.import_module("torch.distributed._symmetric_memory")
+    assert callable(symm.empty) and callable(symm.rendezvous)
 
 
 def test_sharding_needs_a_table_to_shard():
@@ -293,10 +309,12 @@ def _exchange(bufs, counts, reverse=False):
 
 
 @pytest.mark.gpu
-@pytest.mark.parametrize("W,D,multihot,repl", [(2, 16, False, 0), (3, 64, False, 0), (2, 64, True, 0), (4, 16, True, 0),
-                                                 (3, 64, False, 60), (2, 16, True, 60)])
+@pytest.mark.parametrize("W,D,multihot,repl", [(2, 32, False, 0), (3, 64, False, 0), (2, 64, True, 0), (4, 32, True, 0),
+                                                 (3, 64, False, 60), (2, 32, True, 60)])
 def test_sharded_equals_unsharded_emulated_ranks(W, D, multihot, repl):
-    """repl: tables of at most that many rows are replicated (looked up and differentiated locally)."""
+    """W ranks emulated in one process (the exchange is done by slicing staging buffers): the routing kernels against
+    the torch restatement bit for bit, forward views bit-identical to the unsharded module on the concatenated batch,
+    every gradient within 2e-5.  repl: tables of at most that many rows are replicated."""
     from deepfm_b200.layers.embedding import FeatureEmbedding
     from deepfm_b200.layers.fm import FMInteraction
     from deepfm_b200.layers.l2 import l2_penalty
@@ -339,38 +357,46 @@ def test_sharded_equals_unsharded_emulated_ranks(W, D, multihot, repl):
     ins = [m._prepare(bt) for m, bt in zip(mods, batches)]
     routes = [m.route(x) for m, x in zip(mods, ins)]
     counts = [r.counts.tolist() for r in routes]
-    recv_keys = _exchange([r.send_keys for r in routes], counts)
     for m, x, r in zip(mods, ins, routes):          # routing kernels == the torch restatement, bit-exactly
         ref = m.route_torch(x)
-        n_sent = int(ref.counts.sum())
+        n_u = int(ref.counts.sum())
         assert torch.equal(r.counts, ref.counts)
-        assert torch.equal(r.send_keys[:n_sent], ref.send_keys)
-        for mine, theirs in zip(m.sharded_positions(r.pos, b), m.sharded_positions(ref.pos, b)):
-            assert torch.equal(mine, theirs)
-        r.send_keys = r.send_keys[:n_sent]
-    gathered = [m.gather(k) for m, k in zip(mods, recv_keys)]
-    got = _exchange([g[0] for g in gathered], counts, reverse=True)
-    for i, (m, v) in enumerate(zip(mods, got)):     # row 0 of the reply buffer is the reserved zero row
-        buf = m.reply_buffer(v.shape[0], v)
-        buf[1:] = v
-        got[i] = buf
-    outs = [m.finish(x, r.pos, v, True) for m, x, r, v in zip(mods, ins, routes, got)]
+        assert torch.equal(r.send_keys[:n_u], ref.send_keys)
+        assert torch.equal(r.pos, ref.pos)
+        assert n_u < b * m._S                         # Zipf ids: repeats travel once
+        r.send_keys = r.send_keys[:n_u]
+    recv_keys = _exchange([r.send_keys for r in routes], counts)
+    gathered = [m.gather(k) for m, k in zip(mods, recv_keys)]              # (vec, sc, bkeys) staging
+    got_v = _exchange([g[0] for g in gathered], counts, reverse=True)
+    got_s = _exchange([g[1] for g in gathered], counts, reverse=True)
+    got = []
+    for m, v, c in zip(mods, got_v, got_s):         # row 0 of the reply buffers is the reserved zero row
+        bv, bs = m.reply_buffers(v.shape[0], v)
+        bv[1:] = v
+        bs[1:] = c
+        got.append((bv, bs))
+    outs = [m.finish(x, r.pos, g[0], g[1], True) for m, x, r, g in zip(mods, ins, routes, got)]
     assert torch.equal(torch.cat([o[0] for o in outs]), fo.detach())      # same rows, same order: bit-identical
     assert torch.equal(torch.cat([o[2] for o in outs]), fl.detach())
     assert torch.equal(torch.cat([o[3] for o in outs]), fm.detach())
     # backward
     gscale = torch.ones((), device="cuda")
-    packed = []
+    staged, dense = [], []
     for r, (m, o) in enumerate(zip(mods, outs)):
         sl = slice(r * b, (r + 1) * b)
         params = m._ordered_params()
-        packed.append(m.pack_grads(o[6], routes[r].pos, got[r], g_first[sl].contiguous(), None,
-                                   g_flat[sl].contiguous(), g_fm[sl].contiguous(), o[1], o[2], o[4], params, lam / W, gscale,
+        gf, gl, gm = g_first[sl].contiguous(), g_flat[sl].contiguous(), g_fm[sl].contiguous()
+        sv, ss = m.reduce_grads(routes[r], gf, None, gl, gm, o[1], o[4], o[5])
+        n_u = routes[r].send_keys.numel()
+        staged.append((sv[:n_u], ss[:n_u]))
+        dense.append(m.local_grads(o[6], got[r][0], got[r][1], gf, None, gl, gm, o[1], o[2], o[4], params, lam / W, gscale,
                                    o[5], keys=o[7]))
-    g_recv = _exchange([p[0] for p in packed], counts)
+    g_vec = _exchange([p[0] for p in staged], counts)
+    g_sc = _exchange([p[1] for p in staged], counts)
     for r, m in enumerate(mods):
         params = m._ordered_params()
-        tg = m.owner_backward(gathered[r][1], g_recv[r], params, lam, gscale)
+        bs = m.sort_owner_keys(gathered[r][2])
+        tg = m.owner_backward(bs, g_vec[r], g_sc[r], params, lam, gscale)
         for i, g in tg.items():
             slot = m._slot_of_param[i]
             name = m.field_names[slot // 5]
@@ -387,5 +413,5 @@ def test_sharded_equals_unsharded_emulated_ranks(W, D, multihot, repl):
         name = mods[0].field_names[slot // 5]
         mod = (full.second_order_embeddings if slot % 5 < 2 else full.first_order_embeddings)[name]
         ref = (mod.weight if slot % 5 in (0, 2) else mod.bias).grad
-        got_g = sum(p[1][i] for p in packed)
+        got_g = sum(p[i] for p in dense)
         assert_close_rel(got_g.cpu(), ref.cpu(), 2e-5, f"dense {name} slot {slot % 5}")
