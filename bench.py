@@ -280,6 +280,8 @@ def run_ours(args, rank: int, local_rank: int, n_gpus: int):
     if os.environ.get("NCCL_DEBUG", "").upper() == "VERSION":
         os.environ["NCCL_DEBUG"] = "WARN"        # NCCL prints its version banner on STDOUT: keep stdout to the one JSON line
     _lib.lib()
+    from deepfm_b200.layers.dnn import DNN as _DNN
+    _DNN.fused = args.dnn_gemm == "own"
     torch.cuda.set_device(local_rank)
     dev = torch.device("cuda", local_rank)
     if n_gpus > 1:
@@ -298,6 +300,21 @@ def run_ours(args, rank: int, local_rank: int, n_gpus: int):
         comm = TorchDistComm()
         M.BaseCTRModel.embedding_factory = staticmethod(
             lambda schema, fm_embed_dim: ShardedFeatureEmbedding(schema, fm_embed_dim, n_gpus, rank, comm))
+    parity = None
+    if sharded and (args.check or os.environ.get("DFM_BENCH_CHECK")):
+        # parity of the product multi-rank path (routing kernels, peer-memory exchange, owner-side backward, reducer)
+        # against the unsharded model, on the same schema with the vocabularies scaled down so that every rank can
+        # also hold the full model; per-rank batch 8192
+        from deepfm_b200.sharded import TorchDistComm as _Comm
+        from deepfm_b200.sharded_check import check_against_unsharded
+        cschema = (W.criteo_schema(EMBED_DIM, vocab_scale=0.02) if wl == "deepfm_criteo"
+                   else W.criteo_multihot_schema(EMBED_DIM, max_length=16, vocab_scale=0.002))
+        cb = 8192 if wl == "deepfm_criteo" else 1024
+        parity = check_against_unsharded(model_name, cschema, cfg, W.synthetic_batch(cschema, cb, seed=7 + rank, device=dev),
+                                         W.synthetic_labels(cb, seed=7 + rank, device=dev), _Comm(),
+                                         replicate_below=4096 if wl == "deepfm_criteo" else 60)
+        parity["what"] = (f"sharded product path vs unsharded model, {wl} schema at reduced vocabularies, {cb} samples/rank: "
+                          "logits bit-identical, gradients max-norm relative error")
     with torch.device(dev):
         model = create_model(model_name, schema, cfg)
     model.train()
@@ -477,9 +494,14 @@ def run_ours(args, rank: int, local_rank: int, n_gpus: int):
     ms_step = total_ms / K_
     line = base_line(args, n_gpus)
     from deepfm_b200 import fp32_emulation
-    line["config"]["dnn_gemm"] = (f"library (out of scope): {fp32_emulation.status()}, cuBLAS {fp32_emulation.cublas_version()}; "
-                                  "fp32 in / fp32 out, max-norm rel err vs fp64 4.4e-7 (native SIMT sgemm: 1.8e-6)") \
-        if fp32_emulation._state["enabled"] else f"library (out of scope): torch-bundled cuBLAS {fp32_emulation.cublas_version()} SIMT sgemm"
+    if args.dnn_gemm == "own":
+        line["config"]["dnn_gemm"] = ("own kernels: dfm_gemm3 (tcgen05.mma kind::tf32, 3xTF32 split, fp32 in / fp32 out, TMA operands, "
+                                      "TMEM accumulators promoted to fp32 registers every 128 k) + fused BatchNorm/ReLU/dropout passes")
+    elif fp32_emulation._state["enabled"]:
+        line["config"]["dnn_gemm"] = (f"library: {fp32_emulation.status()}, cuBLAS {fp32_emulation.cublas_version()}; "
+                                      "fp32 in / fp32 out, max-norm rel err vs fp64 4.4e-7 (native SIMT sgemm: 1.8e-6)")
+    else:
+        line["config"]["dnn_gemm"] = f"library: torch-bundled cuBLAS {fp32_emulation.cublas_version()} SIMT sgemm"
     dnn_note = line["config"]["dnn_gemm"]
     if wl != "deepfm_criteo":
         line["config"] = {"workload": WORKLOADS[wl][1].format(B=BATCH), "model": model_name, "batch_per_gpu": BATCH,
@@ -529,6 +551,8 @@ def run_ours(args, rank: int, local_rank: int, n_gpus: int):
                             "traffic": None, "note": "per-kernel roofline is reported by the N=1 run (unsharded K1)"}
         if k1_ms:
             line["roofline"]["k1_ms"], line["roofline"]["k2_ms"] = k1_ms, k2_ms
+    if parity is not None:
+        line["parity"] = parity
     if n_gpus == 1 and not args.no_cpu_baseline:
         r = cpu_reference_run(steps=3, warmup=1, budget_s=60.0, workload=wl)
         line["cpu_baseline"] = {"value": r["value"], "unit": UNIT, "cores": r["cores"], "kind": r["kind"], "sample": r["sample"]}
@@ -544,14 +568,18 @@ def main():
     ap.add_argument("--warmup", type=int, default=5)
     ap.add_argument("--impl", default="ours", choices=["ours", "reference"])
     ap.add_argument("--no-cpu-baseline", action="store_true")
+    ap.add_argument("--check", action="store_true",
+                    help="N > 1: before timing, run the real sharded path against the unsharded model on a reduced copy of "
+                         "the workload (deepfm_b200/sharded_check.py) and report it as `parity` in the JSON line")
     ap.add_argument("--profile-step", default=None, help="write a per-kernel device-time table of one warm step to this file")
     ap.add_argument("--sort", default="side", choices=["side", "ahead", "inline"],
                     help="where the backward's key sort runs: on a side stream right behind K1 (default), one step ahead in "
                          "the input pipeline (FeatureEmbedding.prepare), or inside the backward")
     ap.add_argument("--workload", default="deepfm_criteo", choices=sorted(WORKLOADS))
-    ap.add_argument("--dnn-gemm", default="emulated", choices=["emulated", "native"],
-                    help="library GEMMs of the (out-of-scope) DNN tower: cuBLAS 12.9 FP32 emulation on the BF16 tensor "
-                         "cores (fp32-accurate) or torch's bundled cuBLAS 12.8 SIMT sgemm")
+    ap.add_argument("--dnn-gemm", default="own", choices=["own", "emulated", "native"],
+                    help="DNN tower: the repo's own kernels (tcgen05 3xTF32 GEMMs + fused BatchNorm/activation/dropout, "
+                         "default), or the library routes kept for comparison: cuBLAS 12.9 FP32 emulation (BF16x9) / "
+                         "torch's bundled cuBLAS SIMT sgemm")
     ap.add_argument("--cin-precision", default="tf32", choices=["fp32", "tf32"],
                     help="xDeepFM workloads: CIN contraction on tcgen05 (tf32) or CUDA cores (fp32)")
     args = ap.parse_args()
@@ -564,7 +592,8 @@ def main():
         cmd = [sys.executable, "-m", "torch.distributed.run", "--nnodes=1", f"--nproc-per-node={args.gpus}",
                "--master-addr", "127.0.0.1", "--master-port", os.environ.get("MASTER_PORT", "29533"), __file__,
                "--gpus", str(args.gpus), "--steps", str(args.steps), "--warmup", str(args.warmup), "--impl", args.impl,
-               "--workload", args.workload, "--cin-precision", args.cin_precision, "--dnn-gemm", args.dnn_gemm]
+               "--workload", args.workload, "--cin-precision", args.cin_precision, "--dnn-gemm", args.dnn_gemm,
+               "--sort", args.sort] + (["--check"] if args.check else [])
         sys.exit(subprocess.call(cmd))
     # Libraries (NCCL's version banner, for one) write to fd 1: point it at stderr for the whole run and keep the
     # real stdout for the single JSON line.

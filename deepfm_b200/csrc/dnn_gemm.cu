@@ -13,8 +13,16 @@
 // 2-5 split the landed tiles IN PLACE (raw -> hi), write B_lo to a second shared-memory tile and A_lo straight
 // into tensor memory (tcgen05.st: the A_lo * B_hi product runs in the TS form, which halves its shared-memory
 // reads);  one elected thread of warp 1 issues 12 `tcgen05.mma.cta_group::1.kind::tf32` (M = 128, N = tile, K = 8)
-// and recycles the stage with tcgen05.commit;  warps 6-9 drain one of two TMEM accumulators (tcgen05.ld) into
-// global memory while the next tile's MMAs fill the other.
+// and recycles the stage with tcgen05.commit;  warps 6-9 are the PROMOTERS: the tensor core's fp32 accumulation
+// rounds toward zero, so a long chain of accumulating MMAs drifts (measured 2e-5 relative at K = 2496); the MMAs
+// therefore accumulate only CH k-blocks (K = 128) into one of two TMEM accumulators, and the promoter warps add
+// each finished chunk (tcgen05.ld) into round-to-nearest fp32 master accumulators held in registers while the
+// next chunk's MMAs fill the other TMEM buffer; the masters go to global memory at the end of the tile.
+// MN-major 32-bit operands must use the 32-byte-atom 128-byte swizzle (TMA SWIZZLE_128B_ATOM_32B ==
+// UMMA SWIZZLE_128B_BASE32B: 32-byte chunks XOR-ed with the row index mod 4).
+#include <stdlib.h>
+#include <string.h>
+
 #include "tc_common.cuh"
 
 namespace dfm {
@@ -23,6 +31,8 @@ namespace g3 {
 constexpr int TM = 128;          // rows of D per tile (UMMA M)
 constexpr int KB = 32;           // reduction elements per stage: 32 tf32 = one 128-byte swizzle row
 constexpr int MAXST = 6;
+constexpr int CH = 4;            // k-blocks per TMEM accumulation chunk (K = 128: 48 accumulating MMAs)
+constexpr int TN_MAX = 128;      // N tile: the promoters keep one master accumulator per column in registers
 constexpr int THREADS = 320;     // warp 0: TMA, warp 1: MMA, warps 2-5: split, warps 6-9: epilogue
 constexpr int A_BYTES = TM * 128;
 
@@ -30,25 +40,27 @@ struct Args {
     float* D; long long ldd;             // output (or split-K partial base), row stride in floats
     const float* bias;                   // (N) or null
     long long M, N, K;
-    int tn;                              // N tile: multiple of 32, <= 192
+    int tn;                              // N tile: multiple of 32, <= TN_MAX
     int n_mt, n_nt, n_split;
     long long k_per_split;               // multiple of KB
     long long split_stride;              // floats between the partial outputs of consecutive splits
     int a_mn, b_mn;                      // 1: the operand is MN-major ([K][MN] in memory)
     int nstage;
+    int mask_hi;                         // 1: write x_hi back over the raw tile (0: rely on the MMA ignoring the low 13 bits)
     uint32_t tmem_cols;
 };
 
-// MN-major, 128-byte swizzle (cute::UMMA canonical layout ((8,n),(8,k)):((1,LBO),(8,SBO)) in 16-byte units):
-// 32 MN elements are contiguous (128 B), 8 k-rows of 128 B form one 1024-byte atom, the next 32 MN elements
-// start LBO = 32 k-rows * 128 B = 4096 B further (one TMA box {32 mn, 32 k} per MN atom).
+// MN-major 32-bit operand: cute::UMMA::LayoutType::SWIZZLE_128B_BASE32B (canonical layout ((8,n),(4,k)):((1,LBO),(8,SBO))
+// in 16-byte units): 32 MN elements are contiguous (128 B), 4 k-rows of 128 B form one 512-byte swizzle atom (32-byte
+// chunks XOR-ed with the row index mod 4), the next 4 k-rows follow SBO = 512 B later, the next 32 MN elements start
+// LBO = 32 k-rows * 128 B = 4096 B further (one TMA box {32 mn, 32 k}, SWIZZLE_128B_ATOM_32B, per MN atom).
 __device__ __forceinline__ uint64_t make_desc_mn(uint32_t smem_addr) {
     uint64_t d = 0;
     d |= (uint64_t)((smem_addr & 0x3FFFFu) >> 4);
     d |= (uint64_t)(4096 >> 4) << 16;       // leading byte offset: next MN atom
-    d |= (uint64_t)(1024 >> 4) << 32;       // stride byte offset: next group of 8 k
+    d |= (uint64_t)(512 >> 4) << 32;        // stride byte offset: next group of 4 k
     d |= (uint64_t)1 << 46;                 // descriptor version (Blackwell)
-    d |= (uint64_t)2 << 61;                 // SWIZZLE_128B
+    d |= (uint64_t)1 << 61;                 // SWIZZLE_128B_BASE32B
     return d;
 }
 
@@ -131,17 +143,20 @@ gemm3_kernel(const __grid_constant__ Args a, const __grid_constant__ CUtensorMap
             const uint32_t idesc_ts = idesc | ((uint32_t)a.b_mn << 16);
             const uint64_t adv_a = a.a_mn ? (1024 >> 4) : (32 >> 4);     // descriptor step per K = 8
             const uint64_t adv_b = a.b_mn ? (1024 >> 4) : (32 >> 4);
-            long long it = 0;
-            for (long long u = blockIdx.x; u < n_units; u += gridDim.x, ++it) {
+            long long it = 0;                                        // accumulation chunks issued so far (both TMEM buffers)
+            for (long long u = blockIdx.x; u < n_units; u += gridDim.x) {
                 int mt, nt, sp;
                 unit_of(u, mt, nt, sp);
                 long long k0;
                 const int nkb = kblocks(sp, k0);
-                const uint32_t acc = (uint32_t)(it & 1), acc_ph = (uint32_t)((it >> 1) & 1);
-                mbar_wait(acc_empty + acc, acc_ph ^ 1u);                 // the epilogue drained this accumulator
-                tc_fence_after();
-                const uint32_t tacc = tmem_base + acc * (uint32_t)a.tn;
+                uint32_t tacc = 0, acc = 0;
                 for (int kb = 0; kb < nkb; ++kb) {
+                    if (kb % CH == 0) {                              // a new chunk starts in the other accumulator
+                        acc = (uint32_t)(it & 1);
+                        mbar_wait(acc_empty + acc, (uint32_t)((it >> 1) & 1) ^ 1u);     // the promoters drained it
+                        tc_fence_after();
+                        tacc = tmem_base + acc * (uint32_t)a.tn;
+                    }
                     mbar_wait(full_raw + s, ph);
                     mbar_wait(full_split + s, ph);
                     tc_fence_after();
@@ -152,14 +167,14 @@ gemm3_kernel(const __grid_constant__ Args a, const __grid_constant__ CUtensorMap
                     const uint32_t talo = tmem_base + alo_col0 + s * 32;
 #pragma unroll
                     for (int k = 0; k < KB / 8; ++k) {
-                        umma_tf32(tacc, da + adv_a * k, db + adv_b * k, idesc_ss, (kb | k) ? 1u : 0u);      // hi * hi
-                        umma_tf32(tacc, da + adv_a * k, dbl + adv_b * k, idesc_ss, 1u);                     // hi * lo
-                        umma_tf32_ts(tacc, talo + k * 8, db + adv_b * k, idesc_ts, 1u);                     // lo * hi
+                        umma_tf32(tacc, da + adv_a * k, db + adv_b * k, idesc_ss, ((kb % CH) | k) ? 1u : 0u);   // hi * hi
+                        umma_tf32(tacc, da + adv_a * k, dbl + adv_b * k, idesc_ss, 1u);                         // hi * lo
+                        umma_tf32_ts(tacc, talo + k * 8, db + adv_b * k, idesc_ts, 1u);                         // lo * hi
                     }
                     umma_commit(empty + s);
                     if (++s == (uint32_t)a.nstage) { s = 0; ph ^= 1u; }
+                    if (kb % CH == CH - 1 || kb == nkb - 1) { umma_commit(acc_full + acc); ++it; }
                 }
-                umma_commit(acc_full + acc);
             }
         }
     } else if (warp < 6) {
@@ -184,18 +199,18 @@ gemm3_kernel(const __grid_constant__ Args a, const __grid_constant__ CUtensorMap
                         float4* p = reinterpret_cast<float4*>(rowp + ((c ^ (r & 7)) << 4));
                         const float4 v = *p;
                         const float4 h = make_float4(tf32_hi(v.x), tf32_hi(v.y), tf32_hi(v.z), tf32_hi(v.w));
-                        *p = h;
+                        if (a.mask_hi) *p = h;
                         lo[4 * c] = v.x - h.x; lo[4 * c + 1] = v.y - h.y; lo[4 * c + 2] = v.z - h.z; lo[4 * c + 3] = v.w - h.w;
                     }
-                } else {                                 // element (k, mn = r): atom r / 32, row k, chunk ((r % 32) / 4) ^ (k & 7)
-                    unsigned char* atom = sa + (r >> 5) * 4096 + (r & 3) * 4;
-                    const int ch = (r & 31) >> 2;
+                } else {                                 // element (k, mn = r): box r / 32, row k, 32-byte chunk ((r % 32) / 8) ^ (k & 3)
+                    unsigned char* atom = sa + (r >> 5) * 4096 + (r & 7) * 4;
+                    const int ch = (r & 31) >> 3;
 #pragma unroll
                     for (int k = 0; k < 32; ++k) {
-                        float* p = reinterpret_cast<float*>(atom + k * 128 + ((ch ^ (k & 7)) << 4));
+                        float* p = reinterpret_cast<float*>(atom + k * 128 + ((ch ^ (k & 3)) << 5));
                         const float v = *p;
                         const float h = tf32_hi(v);
-                        *p = h;
+                        if (a.mask_hi) *p = h;
                         lo[k] = v - h;
                     }
                 }
@@ -206,7 +221,7 @@ gemm3_kernel(const __grid_constant__ Args a, const __grid_constant__ CUtensorMap
                 for (int i = tid; i < nchunk; i += 128) {
                     const float4 v = bh[i];
                     const float4 h = make_float4(tf32_hi(v.x), tf32_hi(v.y), tf32_hi(v.z), tf32_hi(v.w));
-                    bh[i] = h;
+                    if (a.mask_hi) bh[i] = h;
                     bl[i] = make_float4(v.x - h.x, v.y - h.y, v.z - h.z, v.w - h.w);
                 }
                 fence_proxy_async();                     // generic-proxy writes -> async proxy (UMMA reads)
@@ -217,42 +232,59 @@ gemm3_kernel(const __grid_constant__ Args a, const __grid_constant__ CUtensorMap
             }
         }
     } else {
-        // ------------------------------------------------------------------ epilogue: TMEM -> global
+        // ------------------------------------------------------------------ promoters: TMEM chunks -> fp32 masters -> global
         const int q = warp & 3;
         const int r = q * 32 + lane;
         long long it = 0;
         const bool vec_ok = (a.ldd & 3) == 0 && (reinterpret_cast<uintptr_t>(a.D) & 15u) == 0 && (a.split_stride & 3) == 0;
-        for (long long u = blockIdx.x; u < n_units; u += gridDim.x, ++it) {
+        for (long long u = blockIdx.x; u < n_units; u += gridDim.x) {
             int mt, nt, sp;
             unit_of(u, mt, nt, sp);
-            const uint32_t acc = (uint32_t)(it & 1), acc_ph = (uint32_t)((it >> 1) & 1);
-            mbar_wait(acc_full + acc, acc_ph);
-            tc_fence_after();
+            long long k0;
+            const int nkb = kblocks(sp, k0);
+            const int n_chunks = (nkb + CH - 1) / CH;
+            float macc[TN_MAX];
+#pragma unroll
+            for (int i = 0; i < TN_MAX; ++i) macc[i] = 0.f;
+            for (int ch = 0; ch < n_chunks; ++ch, ++it) {
+                const uint32_t acc = (uint32_t)(it & 1), acc_ph = (uint32_t)((it >> 1) & 1);
+                mbar_wait(acc_full + acc, acc_ph);
+                tc_fence_after();
+                const uint32_t taddr = tmem_base + ((uint32_t)(q * 32) << 16) + acc * (uint32_t)a.tn;
+#pragma unroll
+                for (int c = 0; c < TN_MAX / 32; ++c) {
+                    if (c * 32 < a.tn) {
+                        float v[32];
+                        tmem_ld32(taddr + c * 32, v);
+#pragma unroll
+                        for (int i = 0; i < 32; ++i) macc[c * 32 + i] += v[i];
+                    }
+                }
+                tc_fence_before();
+                __syncwarp();
+                if (lane == 0) mbar_arrive(acc_empty + acc);
+            }
             const long long row = (long long)mt * TM + r;
             float* out = a.D + (size_t)sp * a.split_stride + (size_t)row * a.ldd;
-            const uint32_t taddr = tmem_base + ((uint32_t)(q * 32) << 16) + acc * (uint32_t)a.tn;
-            for (int c0 = 0; c0 < a.tn; c0 += 32) {
-                float v[32];
-                tmem_ld32(taddr + c0, v);
-                const long long col0 = (long long)nt * a.tn + c0;
-                if (row < a.M && col0 < a.N) {
+#pragma unroll
+            for (int c = 0; c < TN_MAX / 32; ++c) {
+                const long long col0 = (long long)nt * a.tn + c * 32;
+                if (c * 32 < a.tn && row < a.M && col0 < a.N) {
                     if (a.bias) {
 #pragma unroll
-                        for (int i = 0; i < 32; ++i) if (col0 + i < a.N) v[i] += __ldg(a.bias + col0 + i);
+                        for (int i = 0; i < 32; ++i) if (col0 + i < a.N) macc[c * 32 + i] += __ldg(a.bias + col0 + i);
                     }
                     if (vec_ok && col0 + 32 <= a.N) {
 #pragma unroll
                         for (int i = 0; i < 8; ++i)
-                            *reinterpret_cast<float4*>(out + col0 + 4 * i) = make_float4(v[4 * i], v[4 * i + 1], v[4 * i + 2], v[4 * i + 3]);
+                            *reinterpret_cast<float4*>(out + col0 + 4 * i) =
+                                make_float4(macc[c * 32 + 4 * i], macc[c * 32 + 4 * i + 1], macc[c * 32 + 4 * i + 2], macc[c * 32 + 4 * i + 3]);
                     } else {
 #pragma unroll
-                        for (int i = 0; i < 32; ++i) if (col0 + i < a.N) out[col0 + i] = v[i];
+                        for (int i = 0; i < 32; ++i) if (col0 + i < a.N) out[col0 + i] = macc[c * 32 + i];
                     }
                 }
             }
-            tc_fence_before();
-            __syncwarp();
-            if (lane == 0) mbar_arrive(acc_empty + acc);
         }
     }
     __syncthreads();
@@ -283,7 +315,7 @@ static int make_plan(int mode, long long M, long long N, long long K, Plan& p) {
     const long long a_inner = mode == 2 ? M : K, b_inner = mode == 0 ? K : N;
     DFM_REQUIRE(a_inner % 4 == 0 && b_inner % 4 == 0, DFM_ERR_UNSUPPORTED,
                 "dfm_gemm3: contiguous extents (%lld, %lld) must be multiples of 4", a_inner, b_inner);
-    p.n_nt = (int)ceil_div(N, 192);
+    p.n_nt = (int)ceil_div(N, TN_MAX);
     p.tn = (int)(ceil_div(ceil_div(N, p.n_nt), 32) * 32);
     p.n_mt = (int)ceil_div(M, TM);
     p.n_split = 1;
@@ -340,14 +372,15 @@ int dfm_gemm3(int mode, const float* A, const float* B, float* D, const float* b
     a.M = M; a.N = N; a.K = K; a.tn = p.tn; a.n_mt = p.n_mt; a.n_nt = p.n_nt; a.n_split = p.n_split;
     a.k_per_split = p.k_per_split; a.nstage = p.nstage; a.tmem_cols = p.tmem_cols;
     a.a_mn = mode == 2 ? 1 : 0; a.b_mn = mode == 0 ? 0 : 1;
+    a.mask_hi = getenv("DFM_G3_NOMASK") ? 0 : 1;
     a.bias = bias;
     if (p.n_split > 1) { a.D = static_cast<float*>(workspace); a.ldd = N; a.split_stride = M * N; }
     else { a.D = D; a.ldd = N; a.split_stride = 0; }
     CUtensorMap mapA, mapB;
     // K-major operand [rows][K]: box {32 k, rows};  MN-major operand [K][MN]: box {32 mn, 32 k}
-    rc = a.a_mn ? tc::make_tmap_2d(&mapA, A, K, M, 32) : tc::make_tmap_2d(&mapA, A, M, K, TM);
+    rc = a.a_mn ? tc::make_tmap_2d(&mapA, A, K, M, 32, true) : tc::make_tmap_2d(&mapA, A, M, K, TM);
     if (rc) return rc;
-    rc = a.b_mn ? tc::make_tmap_2d(&mapB, B, K, N, 32) : tc::make_tmap_2d(&mapB, B, N, K, p.tn);
+    rc = a.b_mn ? tc::make_tmap_2d(&mapB, B, K, N, 32, true) : tc::make_tmap_2d(&mapB, B, N, K, p.tn);
     if (rc) return rc;
     DFM_CHECK_CUDA(cudaFuncSetAttribute(gemm3_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)p.smem));
     long long grid = (long long)p.n_mt * p.n_nt * p.n_split;

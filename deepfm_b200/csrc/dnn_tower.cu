@@ -21,7 +21,7 @@ namespace tw {
 enum { ACT_RELU = 0, ACT_LEAKY = 1, ACT_GELU = 2, ACT_TANH = 3 };
 enum { BN_NONE = 0, BN_BATCH = 1, BN_FIXED = 2 };
 
-constexpr int SLAB_ROWS = 512;       // rows per partial
+constexpr int SLAB_ROWS = 256;       // rows per partial
 constexpr int CT = 32, RT = 8;       // block = 32 columns x 8 row lanes
 
 __device__ __forceinline__ float act_f(float z, int act) {
@@ -69,51 +69,105 @@ __device__ __forceinline__ float pre_act(const Ew& e, float y, int c, float& xha
 
 // ---- column sums: partial[slab][k][c] (double), k = 0, 1
 // OP 0: (sum y, sum y^2);  OP 1: (sum dz * xhat, sum dz) with dz recomputed;  OP 2: (sum x, -)
+// A block owns SLAB_ROWS rows x (32 * VC) columns: thread (tx, ty) walks rows ty, ty + RT, ... of VC consecutive
+// columns (one 128-bit load when VC = 4), UR rows in flight; fp32 terms, fp64 running sums.
 template <int OP>
+__device__ __forceinline__ void colsum_term(const Ew& e, float y, float d, size_t i, int c, double& a0, double& a1) {
+    if (OP == 0) {
+        a0 += (double)y; a1 += (double)y * (double)y;
+    } else if (OP == 1) {
+        float xhat;
+        const float z = pre_act(e, y, c, xhat);
+        float g = d * act_df(z, e.act);
+        if (e.p > 0.f) g = u01(e.seed, i) >= e.p ? g * e.keep_scale : 0.f;
+        a0 += (double)g * (double)xhat; a1 += (double)g;
+    } else {
+        a0 += (double)d;
+    }
+}
+
+template <int OP, int VC>
 __global__ void __launch_bounds__(CT * RT)
 colsum_partial_kernel(const __grid_constant__ Ew e, const float* __restrict__ da, double* __restrict__ partial) {
-    __shared__ double s0[RT][CT], s1[RT][CT];
+    __shared__ double s0[RT][CT * VC], s1[RT][CT * VC];
+    constexpr int UR = 4;
     const int tx = threadIdx.x % CT, ty = threadIdx.x / CT;
-    const int c = blockIdx.y * CT + tx;
+    const int c0 = (blockIdx.y * CT + tx) * VC;
     const long long r0 = (long long)blockIdx.x * SLAB_ROWS;
     const long long r1 = r0 + SLAB_ROWS < e.M ? r0 + SLAB_ROWS : e.M;
-    double a0 = 0.0, a1 = 0.0;
-    if (c < e.C) {
-        for (long long r = r0 + ty; r < r1; r += RT) {
-            const size_t i = (size_t)r * e.C + c;
-            if (OP == 0) {
-                const float y = __ldg(e.y + i);
-                a0 += (double)y; a1 += (double)y * (double)y;
-            } else if (OP == 1) {
-                float xhat;
-                const float z = pre_act(e, __ldg(e.y + i), c, xhat);
-                float g = __ldg(da + i) * act_df(z, e.act);
-                if (e.p > 0.f) g = u01(e.seed, i) >= e.p ? g * e.keep_scale : 0.f;
-                a0 += (double)g * (double)xhat; a1 += (double)g;
-            } else {
-                a0 += (double)__ldg(da + i);
+    double a0[VC], a1[VC];
+#pragma unroll
+    for (int v = 0; v < VC; ++v) { a0[v] = 0.0; a1[v] = 0.0; }
+    if (c0 < e.C) {
+        for (long long r = r0 + ty; r < r1; r += RT * UR) {
+            float yv[UR][VC], dv[UR][VC];
+#pragma unroll
+            for (int u = 0; u < UR; ++u) {
+                const long long rr = r + (long long)u * RT;
+                const size_t i = (size_t)(rr < r1 ? rr : r) * e.C + c0;
+                if (VC == 4) {
+                    if (OP != 2) { const float4 t = __ldg(reinterpret_cast<const float4*>(e.y + i)); yv[u][0] = t.x; yv[u][1] = t.y; yv[u][2] = t.z; yv[u][3] = t.w; }
+                    if (OP != 0) { const float4 t = __ldg(reinterpret_cast<const float4*>(da + i)); dv[u][0] = t.x; dv[u][1] = t.y; dv[u][2] = t.z; dv[u][3] = t.w; }
+                } else {
+                    if (OP != 2) yv[u][0] = __ldg(e.y + i);
+                    if (OP != 0) dv[u][0] = __ldg(da + i);
+                }
+            }
+#pragma unroll
+            for (int u = 0; u < UR; ++u) {
+                const long long rr = r + (long long)u * RT;
+                if (rr >= r1) break;
+#pragma unroll
+                for (int v = 0; v < VC; ++v)
+                    colsum_term<OP>(e, OP != 2 ? yv[u][v] : 0.f, OP != 0 ? dv[u][v] : 0.f, (size_t)rr * e.C + c0 + v, c0 + v, a0[v], a1[v]);
             }
         }
     }
-    s0[ty][tx] = a0; s1[ty][tx] = a1;
+#pragma unroll
+    for (int v = 0; v < VC; ++v) { s0[ty][tx * VC + v] = a0[v]; s1[ty][tx * VC + v] = a1[v]; }
     __syncthreads();
-    if (ty == 0 && c < e.C) {
+    for (int o = threadIdx.x; o < CT * VC; o += CT * RT) {
+        const int c = blockIdx.y * CT * VC + o;
+        if (c >= e.C) continue;
         double t0 = 0.0, t1 = 0.0;
 #pragma unroll
-        for (int q = 0; q < RT; ++q) { t0 += s0[q][tx]; t1 += s1[q][tx]; }
+        for (int q = 0; q < RT; ++q) { t0 += s0[q][o]; t1 += s1[q][o]; }
         partial[((size_t)blockIdx.x * 2 + 0) * e.C + c] = t0;
         partial[((size_t)blockIdx.x * 2 + 1) * e.C + c] = t1;
     }
 }
 
+// second stage: (s, q)[c] = sum over slabs in slab order; a block owns 32 columns, 8 lanes stride over the slabs
+__device__ __forceinline__ void colsum_second_stage(const double* __restrict__ partial, int n_slab, int C, int stride_c,
+                                                    double& s, double& q, bool& owner, int& c) {
+    __shared__ double f0[RT][CT], f1[RT][CT];
+    const int tx = threadIdx.x % CT, ty = threadIdx.x / CT;
+    c = blockIdx.x * CT + tx;
+    double a = 0.0, b = 0.0;
+    if (c < C) {
+        for (int sl = ty; sl < n_slab; sl += RT) {
+            a += partial[((size_t)sl * 2) * stride_c + c];
+            b += partial[((size_t)sl * 2 + 1) * stride_c + c];
+        }
+    }
+    f0[ty][tx] = a; f1[ty][tx] = b;
+    __syncthreads();
+    owner = ty == 0 && c < C;
+    s = 0.0; q = 0.0;
+    if (owner) {
+#pragma unroll
+        for (int k = 0; k < RT; ++k) { s += f0[k][tx]; q += f1[k][tx]; }
+    }
+}
+
 // finalize OP 0: mean, rstd (+ running statistics, momentum update with the unbiased variance)
-__global__ void bn_stats_final_kernel(const double* __restrict__ partial, int n_slab, long long M, int C, float eps,
-                                      float* __restrict__ mean, float* __restrict__ rstd,
-                                      float* __restrict__ run_mean, float* __restrict__ run_var, float momentum) {
-    const int c = blockIdx.x * blockDim.x + threadIdx.x;
-    if (c >= C) return;
-    double s = 0.0, q = 0.0;
-    for (int b = 0; b < n_slab; ++b) { s += partial[((size_t)b * 2) * C + c]; q += partial[((size_t)b * 2 + 1) * C + c]; }
+__global__ void __launch_bounds__(CT * RT)
+bn_stats_final_kernel(const double* __restrict__ partial, int n_slab, long long M, int C, float eps,
+                      float* __restrict__ mean, float* __restrict__ rstd,
+                      float* __restrict__ run_mean, float* __restrict__ run_var, float momentum) {
+    double s, q; bool owner; int c;
+    colsum_second_stage(partial, n_slab, C, C, s, q, owner, c);
+    if (!owner) return;
     const double mu = s / (double)M;
     double var = q / (double)M - mu * mu;
     if (var < 0.0) var = 0.0;
@@ -127,46 +181,66 @@ __global__ void bn_stats_final_kernel(const double* __restrict__ partial, int n_
 }
 
 // finalize OP 1 / 2: two float vectors (second optional)
-__global__ void colsum_final_kernel(const double* __restrict__ partial, int n_slab, int C, float* __restrict__ out0,
-                                    float* __restrict__ out1) {
-    const int c = blockIdx.x * blockDim.x + threadIdx.x;
-    if (c >= C) return;
-    double s = 0.0, q = 0.0;
-    for (int b = 0; b < n_slab; ++b) { s += partial[((size_t)b * 2) * C + c]; q += partial[((size_t)b * 2 + 1) * C + c]; }
+__global__ void __launch_bounds__(CT * RT)
+colsum_final_kernel(const double* __restrict__ partial, int n_slab, int C, float* __restrict__ out0, float* __restrict__ out1) {
+    double s, q; bool owner; int c;
+    colsum_second_stage(partial, n_slab, C, C, s, q, owner, c);
+    if (!owner) return;
     if (out0) out0[c] = (float)s;
     if (out1) out1[c] = (float)q;
 }
 
+// element-wise passes: VE consecutive elements per thread (one 128-bit access when the width is a multiple of 4)
+template <int VE>
 __global__ void __launch_bounds__(256)
 bn_act_fwd_kernel(const __grid_constant__ Ew e, float* __restrict__ out) {
-    const long long n = e.M * e.C;
-    for (long long i = (long long)blockIdx.x * blockDim.x + threadIdx.x; i < n; i += (long long)gridDim.x * blockDim.x) {
+    const long long n = e.M * e.C / VE;
+    for (long long iv = (long long)blockIdx.x * blockDim.x + threadIdx.x; iv < n; iv += (long long)gridDim.x * blockDim.x) {
+        const long long i = iv * VE;
         const int c = (int)(i % e.C);
-        float xhat;
-        float a = act_f(pre_act(e, __ldg(e.y + i), c, xhat), e.act);
-        if (e.p > 0.f) a = u01(e.seed, (unsigned long long)i) >= e.p ? a * e.keep_scale : 0.f;
-        out[i] = a;
+        float y[VE], a[VE];
+        if (VE == 4) { const float4 t = __ldcs(reinterpret_cast<const float4*>(e.y + i)); y[0] = t.x; y[1] = t.y; y[2] = t.z; y[3] = t.w; }
+        else y[0] = __ldcs(e.y + i);
+#pragma unroll
+        for (int v = 0; v < VE; ++v) {
+            float xhat;
+            a[v] = act_f(pre_act(e, y[v], c + v, xhat), e.act);
+            if (e.p > 0.f) a[v] = u01(e.seed, (unsigned long long)(i + v)) >= e.p ? a[v] * e.keep_scale : 0.f;
+        }
+        if (VE == 4) *reinterpret_cast<float4*>(out + i) = make_float4(a[0], a[1], a[2], a[3]);
+        else out[i] = a[0];
     }
 }
 
 // dy = gamma * rstd * (dz - dbeta / M - xhat * dgamma / M)      (BN_BATCH)
 //    = gamma * rstd * dz                                        (BN_FIXED)      = dz (BN_NONE)
+template <int VE>
 __global__ void __launch_bounds__(256)
 bn_act_bwd_apply_kernel(const __grid_constant__ Ew e, const float* __restrict__ da, const float* __restrict__ dgamma,
                         const float* __restrict__ dbeta, float* __restrict__ dy) {
-    const long long n = e.M * e.C;
+    const long long n = e.M * e.C / VE;
     const float inv_m = 1.f / (float)e.M;
-    for (long long i = (long long)blockIdx.x * blockDim.x + threadIdx.x; i < n; i += (long long)gridDim.x * blockDim.x) {
+    for (long long iv = (long long)blockIdx.x * blockDim.x + threadIdx.x; iv < n; iv += (long long)gridDim.x * blockDim.x) {
+        const long long i = iv * VE;
         const int c = (int)(i % e.C);
-        float xhat;
-        const float z = pre_act(e, __ldg(e.y + i), c, xhat);
-        float g = __ldg(da + i) * act_df(z, e.act);
-        if (e.p > 0.f) g = u01(e.seed, (unsigned long long)i) >= e.p ? g * e.keep_scale : 0.f;
-        if (e.bn == BN_BATCH)
-            g = __ldg(e.gamma + c) * __ldg(e.rstd + c) * (g - __ldg(dbeta + c) * inv_m - xhat * __ldg(dgamma + c) * inv_m);
-        else if (e.bn == BN_FIXED)
-            g = __ldg(e.gamma + c) * __ldg(e.rstd + c) * g;
-        dy[i] = g;
+        float y[VE], d[VE], g[VE];
+        if (VE == 4) {
+            const float4 t = __ldcs(reinterpret_cast<const float4*>(e.y + i)); y[0] = t.x; y[1] = t.y; y[2] = t.z; y[3] = t.w;
+            const float4 u = __ldcs(reinterpret_cast<const float4*>(da + i)); d[0] = u.x; d[1] = u.y; d[2] = u.z; d[3] = u.w;
+        } else { y[0] = __ldcs(e.y + i); d[0] = __ldcs(da + i); }
+#pragma unroll
+        for (int v = 0; v < VE; ++v) {
+            float xhat;
+            const float z = pre_act(e, y[v], c + v, xhat);
+            g[v] = d[v] * act_df(z, e.act);
+            if (e.p > 0.f) g[v] = u01(e.seed, (unsigned long long)(i + v)) >= e.p ? g[v] * e.keep_scale : 0.f;
+            if (e.bn == BN_BATCH)
+                g[v] = __ldg(e.gamma + c + v) * __ldg(e.rstd + c + v) * (g[v] - __ldg(dbeta + c + v) * inv_m - xhat * __ldg(dgamma + c + v) * inv_m);
+            else if (e.bn == BN_FIXED)
+                g[v] = __ldg(e.gamma + c + v) * __ldg(e.rstd + c + v) * g[v];
+        }
+        if (VE == 4) *reinterpret_cast<float4*>(dy + i) = make_float4(g[0], g[1], g[2], g[3]);
+        else dy[i] = g[0];
     }
 }
 
@@ -216,12 +290,11 @@ head_bwd_kernel(const float* __restrict__ a, const float* __restrict__ w, const 
     }
 }
 
-__global__ void head_final_kernel(const double* __restrict__ partial, int n_slab, int C, float* __restrict__ dw,
-                                  float* __restrict__ db) {
-    const int c = blockIdx.x * blockDim.x + threadIdx.x;
-    if (c > C) return;
-    double s = 0.0;
-    for (int b = 0; b < n_slab; ++b) s += partial[((size_t)b * 2) * (C + 1) + c];
+__global__ void __launch_bounds__(CT * RT)
+head_final_kernel(const double* __restrict__ partial, int n_slab, int C, float* __restrict__ dw, float* __restrict__ db) {
+    double s, q; bool owner; int c;
+    colsum_second_stage(partial, n_slab, C + 1, C + 1, s, q, owner, c);
+    if (!owner) return;
     if (c < C) dw[c] = (float)s;
     else if (db) db[0] = (float)s;
 }
@@ -239,6 +312,8 @@ static int fill_ew(Ew& e, const float* y, long long M, int C, int bn, int act, c
     e.p = p; e.keep_scale = 1.f / (1.f - p); e.seed = seed;
     return DFM_OK;
 }
+
+static inline bool vec4(int C, const void* p) { return C % 4 == 0 && (reinterpret_cast<uintptr_t>(p) & 15u) == 0; }
 
 static inline unsigned ew_blocks(long long n) {
     long long b = ceil_div(n > 0 ? n : 1, 256 * 4);
@@ -269,8 +344,9 @@ int dfm_bn_stats(const float* y, int64_t M, int C, float eps, float* mean, float
     e.y = y; e.M = M; e.C = C;
     const int ns = n_slabs(M);
     double* partial = static_cast<double*>(workspace);
-    colsum_partial_kernel<0><<<dim3(ns, (unsigned)ceil_div(C, CT)), CT * RT, 0, st>>>(e, nullptr, partial);
-    bn_stats_final_kernel<<<(unsigned)ceil_div(C, 128), 128, 0, st>>>(partial, ns, M, C, eps, mean, rstd, running_mean, running_var, momentum);
+    if (vec4(C, y)) colsum_partial_kernel<0, 4><<<dim3(ns, (unsigned)ceil_div(C, CT * 4)), CT * RT, 0, st>>>(e, nullptr, partial);
+    else colsum_partial_kernel<0, 1><<<dim3(ns, (unsigned)ceil_div(C, CT)), CT * RT, 0, st>>>(e, nullptr, partial);
+    bn_stats_final_kernel<<<(unsigned)ceil_div(C, CT), CT * RT, 0, st>>>(partial, ns, M, C, eps, mean, rstd, running_mean, running_var, momentum);
     DFM_CHECK_LAUNCH();
     return DFM_OK;
 }
@@ -282,7 +358,8 @@ int dfm_bn_act_fwd(const float* y, int64_t M, int C, int bn, int act, const floa
     if (rc) return rc;
     DFM_REQUIRE(out, DFM_ERR_INVALID, "dfm_bn_act_fwd: null output");
     if (M == 0) return DFM_OK;
-    bn_act_fwd_kernel<<<ew_blocks(M * C), 256, 0, static_cast<cudaStream_t>(stream)>>>(e, out);
+    if (vec4(C, y) && vec4(C, out)) bn_act_fwd_kernel<4><<<ew_blocks(M * C / 4), 256, 0, static_cast<cudaStream_t>(stream)>>>(e, out);
+    else bn_act_fwd_kernel<1><<<ew_blocks(M * C), 256, 0, static_cast<cudaStream_t>(stream)>>>(e, out);
     DFM_CHECK_LAUNCH();
     return DFM_OK;
 }
@@ -300,18 +377,22 @@ int dfm_bn_act_bwd(const float* da, const float* y, int64_t M, int C, int bn, in
     cudaStream_t st = static_cast<cudaStream_t>(stream);
     const int ns = n_slabs(M);
     double* partial = static_cast<double*>(workspace);
-    const dim3 grid(ns, (unsigned)ceil_div(C, CT));
+    const bool v4 = vec4(C, y) && vec4(C, da) && vec4(C, dy);
+    const dim3 grid(ns, (unsigned)ceil_div(C, v4 ? CT * 4 : CT));
     if (bn != BN_NONE) {
-        colsum_partial_kernel<1><<<grid, CT * RT, 0, st>>>(e, da, partial);
-        colsum_final_kernel<<<(unsigned)ceil_div(C, 128), 128, 0, st>>>(partial, ns, C, dgamma, dbeta);
+        if (v4) colsum_partial_kernel<1, 4><<<grid, CT * RT, 0, st>>>(e, da, partial);
+        else colsum_partial_kernel<1, 1><<<grid, CT * RT, 0, st>>>(e, da, partial);
+        colsum_final_kernel<<<(unsigned)ceil_div(C, CT), CT * RT, 0, st>>>(partial, ns, C, dgamma, dbeta);
     }
-    bn_act_bwd_apply_kernel<<<ew_blocks(M * C), 256, 0, st>>>(e, da, dgamma, dbeta, dy);
+    if (v4) bn_act_bwd_apply_kernel<4><<<ew_blocks(M * C / 4), 256, 0, st>>>(e, da, dgamma, dbeta, dy);
+    else bn_act_bwd_apply_kernel<1><<<ew_blocks(M * C), 256, 0, st>>>(e, da, dgamma, dbeta, dy);
     if (dbias) {     // Linear bias gradient: column sums of dy (analytically zero behind a training-mode BatchNorm)
         Ew e2;
         memset(&e2, 0, sizeof(e2));
         e2.M = M; e2.C = C;
-        colsum_partial_kernel<2><<<grid, CT * RT, 0, st>>>(e2, dy, partial);
-        colsum_final_kernel<<<(unsigned)ceil_div(C, 128), 128, 0, st>>>(partial, ns, C, dbias, nullptr);
+        if (v4) colsum_partial_kernel<2, 4><<<grid, CT * RT, 0, st>>>(e2, dy, partial);
+        else colsum_partial_kernel<2, 1><<<grid, CT * RT, 0, st>>>(e2, dy, partial);
+        colsum_final_kernel<<<(unsigned)ceil_div(C, CT), CT * RT, 0, st>>>(partial, ns, C, dbias, nullptr);
     }
     DFM_CHECK_LAUNCH();
     return DFM_OK;
@@ -334,7 +415,7 @@ int dfm_head_bwd(const float* a, const float* w, const float* g, int64_t M, int 
     double* partial = static_cast<double*>(workspace);
     head_bwd_kernel<<<dim3(ns, (unsigned)ceil_div(C + 1, CT)), CT * RT, 0, st>>>(a, w, g, M, C, da, partial);
     // dw = columns [0, C), db = column C of the (C + 1)-wide partials
-    head_final_kernel<<<(unsigned)ceil_div(C + 1, 128), 128, 0, st>>>(partial, ns, C, dw, db);
+    head_final_kernel<<<(unsigned)ceil_div(C + 1, CT), CT * RT, 0, st>>>(partial, ns, C, dw, db);
     DFM_CHECK_LAUNCH();
     return DFM_OK;
 }

@@ -833,8 +833,19 @@ __device__ __forceinline__ void seg2_close(const DevPlan& P, const DevGrads& GR,
     }
 }
 
+// One batch of NB positions whose loads are in flight together (register double buffer of seg2_kernel).
+template <int VW, int NB, bool HAS_FM, bool HAS_FIELD, bool HAS_BAG, bool DIRECT>
+struct Seg2Batch {
+    float gA[NB][VW];
+    float gB[HAS_FIELD ? NB : 1][VW];
+    float sv[(HAS_FM && !DIRECT) ? NB : 1][VW];
+    float eB[HAS_BAG ? NB : 1][VW];
+    float w[NB][VW];          // table row of a position that starts a segment (for -(sum g_fm) w + 2 l2 w at its end)
+    float w1[NB];
+};
+
 template <int VW, bool HAS_FM, bool HAS_FIELD, bool HAS_BAG, bool DIRECT>
-__global__ void __launch_bounds__(256, 4)
+__global__ void __launch_bounds__(256, 3)
 seg2_kernel(const __grid_constant__ DevPlan P, const __grid_constant__ DevGrads GR,
             const __grid_constant__ BwdArgs a, long long unit) {
     __shared__ FieldB t_field[MAX_FIELDS];
@@ -844,12 +855,15 @@ seg2_kernel(const __grid_constant__ DevPlan P, const __grid_constant__ DevGrads 
     for (int s = threadIdx.x; s < P.S; s += blockDim.x) s_slotf[s] = P.slot_field[s];
     if (threadIdx.x < 2) s_cnt[threadIdx.x] = 0;
     __syncthreads();
-    // positions whose row loads are in flight together: ~24 floats of load registers per lane
-    constexpr int STREAMS = 1 + ((HAS_FM && !DIRECT) ? 1 : 0) + (HAS_FIELD ? 1 : 0) + (HAS_BAG ? 1 : 0);
+    // two batches of NB positions are in flight per warp (~48 load registers per lane)
+    constexpr int STREAMS = 2 + ((HAS_FM && !DIRECT) ? 1 : 0) + (HAS_FIELD ? 1 : 0) + (HAS_BAG ? 1 : 0);   // incl. the w rows
     constexpr int NBQ = 24 / (VW * STREAMS);
-    constexpr int NB = NBQ >= 8 ? 8 : NBQ >= 4 ? 4 : 2;
+    constexpr int NB = NBQ >= 4 ? 4 : 2;
+    using Batch = Seg2Batch<VW, NB, HAS_FM, HAS_FIELD, HAS_BAG, DIRECT>;
     const int lane = threadIdx.x & 31;
-    const long long unit_idx = (long long)blockIdx.x * (blockDim.x >> 5) + (threadIdx.x >> 5);
+    // spans are dealt to the warps round-robin over the blocks: the sorted order groups the positions by table (hot
+    // L2-resident small tables first, cold big tables last), so a block's eight warps take spans that are far apart
+    const long long unit_idx = (long long)(threadIdx.x >> 5) * gridDim.x + blockIdx.x;
     const long long p_lo = unit_idx * unit;
     const long long p_hi = (p_lo + unit < a.N) ? p_lo + unit : a.N;
     const uint32_t PAD = a.pad_key;
@@ -859,7 +873,15 @@ seg2_kernel(const __grid_constant__ DevPlan P, const __grid_constant__ DevGrads 
     const bool fm_rt = HAS_FM && !DIRECT && a.g_fm != nullptr;   // bag variants are compiled with HAS_FM and decide here
     const bool fm_on = DIRECT || fm_rt;
     const bool need_w = a.peer_n == 0 && (fm_on || coef != 0.f);
+    const bool need_w1 = a.peer_n == 0 && coef != 0.f;
     const int tdim = P.max_tdim, D = P.D, T = P.T;
+    // kernel parameters used inside the hot loop, in registers (the by-value structs live in the constant bank)
+    const float* __restrict__ gflat = a.g_flat;
+    const float* __restrict__ gfield = a.g_field;
+    const float* __restrict__ fmsum = a.fm_sum;
+    const float* __restrict__ fe = a.fe;
+    const uint32_t* __restrict__ skeys = a.skeys;
+    const uint32_t* __restrict__ spay = a.spay;
     int n_valid = 0, n_heads = 0;
 
     if (p_lo < a.N) {
@@ -867,8 +889,8 @@ seg2_kernel(const __grid_constant__ DevPlan P, const __grid_constant__ DevGrads 
         st.cur = PAD; st.seg_start = (int)p_lo; st.f = 0; st.lead = false; st.a1 = 0.f; st.gs = 0.f; st.w1 = 0.f;
 #pragma unroll
         for (int v = 0; v < VW; ++v) { st.acc[v] = 0.f; st.w[v] = 0.f; }
-        const uint32_t key0 = __ldg(a.skeys + p_lo);
-        if (p_lo > 0 && key0 != PAD && __ldg(a.skeys + p_lo - 1) == key0) {     // the span opens inside a segment
+        const uint32_t key0 = __ldg(skeys + p_lo);
+        if (p_lo > 0 && key0 != PAD && __ldg(skeys + p_lo - 1) == key0) {     // the span opens inside a segment
             st.cur = key0; st.lead = true;
         }
         bool ended = false;
@@ -876,9 +898,10 @@ seg2_kernel(const __grid_constant__ DevPlan P, const __grid_constant__ DevGrads 
             // ---- decode: one position per lane
             const long long q = p + lane;
             const bool valid = q < p_hi;
-            const uint32_t key = valid ? __ldg(a.skeys + q) : PAD;
-            const uint32_t pay = valid ? __ldg(a.spay + q) : 0u;
+            const uint32_t key = valid ? __ldg(skeys + q) : PAD;
+            const uint32_t pay = valid ? __ldg(spay + q) : 0u;
             unsigned goff = 0, bofs = 0;     // float offsets of the position's gradient row / its sample's fm_sum row
+            unsigned long long wofs = 0;     // float offset of the position's table row inside its table
             int fl = 0, bag = 0;
             float m = 0.f, o = 0.f, c = 1.f;
             if (key != PAD) {
@@ -890,8 +913,8 @@ seg2_kernel(const __grid_constant__ DevPlan P, const __grid_constant__ DevGrads 
                         o = sc.x; m = sc.y;
                     } else {
                         goff = pay * (unsigned)a.row_stride;
-                        o = __ldg(a.g_flat + goff + tdim);      // packed first-order gradient
-                        m = __ldg(a.g_flat + goff + tdim + 1);  // packed g_fm (for -(sum g_fm) w)
+                        o = __ldg(gflat + goff + tdim);      // packed first-order gradient
+                        m = __ldg(gflat + goff + tdim + 1);  // packed g_fm (for -(sum g_fm) w)
                     }
                 } else {
                     const uint32_t b = pay >> bits;
@@ -907,38 +930,47 @@ seg2_kernel(const __grid_constant__ DevPlan P, const __grid_constant__ DevGrads 
                         o *= c;
                     }
                 }
+                if (need_w) wofs = (unsigned long long)(key - t_field[fl].row_base) * (unsigned)tdim;
             }
             const uint32_t prevk = __shfl_up_sync(0xffffffffu, key, 1);
             const unsigned headmask = __ballot_sync(0xffffffffu, key != (lane == 0 ? st.cur : prevk));
             const unsigned padmask = __ballot_sync(0xffffffffu, key == PAD);
             const int n_live = padmask ? __ffs(padmask) - 1 : 32;       // PAD keys sort last: everything after is PAD
             if (n_live < 32) ended = true;
-            // ---- consume the tile in sorted order, NB positions per batch
-            for (int r0 = 0; r0 < n_live; r0 += NB) {
-                float gA[NB][VW], gB[HAS_FIELD ? NB : 1][VW], sv[HAS_FM ? NB : 1][VW], eB[HAS_BAG ? NB : 1][VW];
+
+            // loads of the NB positions starting at r0 (positions >= n_live read valid memory and are not consumed)
+            auto load_batch = [&](Batch& B, int r0) {
 #pragma unroll
                 for (int i = 0; i < NB; ++i) {
-                    const int r = (r0 + i) & 31;                       // positions >= n_live are loaded (valid memory) but not consumed
+                    const int r = (r0 + i) & 31;
                     const unsigned go = __shfl_sync(0xffffffffu, goff, r);
-                    lv_load_stream<VW>(gA[i], a.g_flat + go + lane * VW);
-                    if (HAS_FIELD) lv_load_stream<VW>(gB[i], a.g_field + go + lane * VW);
+                    lv_load_stream<VW>(B.gA[i], gflat + go + lane * VW);
+                    if (HAS_FIELD) lv_load_stream<VW>(B.gB[i], gfield + go + lane * VW);
                     if (HAS_FM && !DIRECT) {
                         const unsigned bo = __shfl_sync(0xffffffffu, bofs, r);
-                        if (fm_rt) lv_load<VW>(sv[i], a.fm_sum + bo + lane * VW);
+                        if (fm_rt) lv_load<VW>(B.sv[i], fmsum + bo + lane * VW);
                         else {
 #pragma unroll
-                            for (int v = 0; v < VW; ++v) sv[i][v] = 0.f;
+                            for (int v = 0; v < VW; ++v) B.sv[i][v] = 0.f;
                         }
                     }
                     if (HAS_BAG) {                                      // pooled embedding of the bag (aliased layout: same offset)
                         const int bg = __shfl_sync(0xffffffffu, bag, r);
-                        if (bg && fm_rt) lv_load<VW>(eB[i], a.fe + go + lane * VW);
+                        if (bg && fm_rt) lv_load<VW>(B.eB[i], fe + go + lane * VW);
                         else {
 #pragma unroll
-                            for (int v = 0; v < VW; ++v) eB[i][v] = 0.f;
+                            for (int v = 0; v < VW; ++v) B.eB[i][v] = 0.f;
                         }
                     }
+                    if (need_w && ((headmask >> r) & 1u) && r0 + i < n_live) {   // the table row of a segment head
+                        const int f = __shfl_sync(0xffffffffu, fl, r);
+                        const unsigned long long wo = __shfl_sync(0xffffffffu, wofs, r);
+                        lv_load<VW>(B.w[i], t_field[f].w2 + wo + lane * VW);
+                        if (need_w1) B.w1[i] = __ldg(t_field[f].w1 + wo / (unsigned)tdim);
+                    }
                 }
+            };
+            auto consume_batch = [&](const Batch& B, int r0) {
 #pragma unroll
                 for (int i = 0; i < NB; ++i) {
                     const int r = r0 + i;
@@ -949,14 +981,9 @@ seg2_kernel(const __grid_constant__ DevPlan P, const __grid_constant__ DevGrads 
                         st.f = __shfl_sync(0xffffffffu, fl, r);
                         st.seg_start = (int)(p + r); st.lead = false; st.a1 = 0.f; st.gs = 0.f;
 #pragma unroll
-                        for (int v = 0; v < VW; ++v) st.acc[v] = 0.f;
+                        for (int v = 0; v < VW; ++v) { st.acc[v] = 0.f; st.w[v] = B.w[i][v]; }
+                        st.w1 = B.w1[i];
                         ++n_heads;
-                        if (need_w) {                                   // requested now, used when the segment ends
-                            const FieldB& fb = t_field[st.f];
-                            const size_t row = (size_t)(st.cur - fb.row_base);
-                            lv_load<VW>(st.w, fb.w2 + row * tdim + lane * VW);
-                            if (coef != 0.f) st.w1 = __ldg(fb.w1 + row);
-                        }
                     }
                     const float mr = (HAS_FM || DIRECT) ? __shfl_sync(0xffffffffu, m, r) : 0.f;
                     const float orr = __shfl_sync(0xffffffffu, o, r);
@@ -965,9 +992,9 @@ seg2_kernel(const __grid_constant__ DevPlan P, const __grid_constant__ DevGrads 
                     if (HAS_BAG) { cr = __shfl_sync(0xffffffffu, c, r); bg = __shfl_sync(0xffffffffu, bag, r); }
 #pragma unroll
                     for (int v = 0; v < VW; ++v) {
-                        float t = gA[i][v];
-                        if (HAS_FIELD) t += gB[i][v];
-                        if (HAS_FM && !DIRECT) t = fmaf(mr, HAS_BAG ? sv[i][v] - eB[i][v] : sv[i][v], t);
+                        float t = B.gA[i][v];
+                        if (HAS_FIELD) t += B.gB[i][v];
+                        if (HAS_FM && !DIRECT) t = fmaf(mr, HAS_BAG ? B.sv[i][v] - B.eB[i][v] : B.sv[i][v], t);
                         if (HAS_BAG) t *= cr;
                         st.acc[v] += t;
                     }
@@ -975,11 +1002,20 @@ seg2_kernel(const __grid_constant__ DevPlan P, const __grid_constant__ DevGrads 
                     st.a1 += orr;
                     ++n_valid;
                 }
+            };
+            // ---- consume the tile in sorted order, two batches in flight
+            Batch B0, B1;
+            if (n_live > 0) load_batch(B0, 0);
+            for (int r0 = 0; r0 < n_live; r0 += 2 * NB) {
+                if (r0 + NB < n_live) load_batch(B1, r0 + NB);
+                consume_batch(B0, r0);
+                if (r0 + 2 * NB < n_live) load_batch(B0, r0 + 2 * NB);
+                if (r0 + NB < n_live) consume_batch(B1, r0 + NB);
             }
         }
         // ---- the span's last segment: finished here, or handed to the stitch pass
         if (st.cur != PAD) {
-            const bool continues = !ended && p_hi < a.N && __ldg(a.skeys + p_hi) == st.cur;
+            const bool continues = !ended && p_hi < a.N && __ldg(skeys + p_hi) == st.cur;
             if (st.lead || !continues) {
                 seg2_close<VW>(P, GR, a, t_field, coef, need_w, lane, unit_idx, st);
             } else {

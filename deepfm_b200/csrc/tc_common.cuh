@@ -109,8 +109,10 @@ typedef CUresult (*EncodeTiledFn)(CUtensorMap*, CUtensorMapDataType, cuuint32_t,
                                   const cuuint32_t*, const cuuint32_t*, CUtensorMapInterleave, CUtensorMapSwizzle,
                                   CUtensorMapL2promotion, CUtensorMapFloatOOBfill);
 
-// 2-D fp32 tensor map, box = (32 floats = one 128-byte swizzle row) x box_rows, SWIZZLE_128B
-inline int make_tmap_2d(CUtensorMap* map, const float* base, long long rows, long long cols, int box_rows) {
+// 2-D fp32 tensor map, box = (32 floats = one 128-byte swizzle row) x box_rows, SWIZZLE_128B (16-byte chunks; K-major
+// UMMA operands) or, atom32 = true, SWIZZLE_128B_ATOM_32B (32-byte chunks: the only layout tcgen05 accepts for
+// MN-major 32-bit operands, cute::UMMA::LayoutType::SWIZZLE_128B_BASE32B)
+inline int make_tmap_2d(CUtensorMap* map, const float* base, long long rows, long long cols, int box_rows, bool atom32 = false) {
     static EncodeTiledFn encode = nullptr;
     if (!encode) {
         void* fn = nullptr;
@@ -127,7 +129,8 @@ inline int make_tmap_2d(CUtensorMap* map, const float* base, long long rows, lon
     const cuuint32_t box[2] = {32u, (cuuint32_t)box_rows};
     const cuuint32_t estr[2] = {1, 1};
     CUresult cr = encode(map, CU_TENSOR_MAP_DATA_TYPE_FLOAT32, 2, const_cast<float*>(base), dims, strides, box, estr,
-                         CU_TENSOR_MAP_INTERLEAVE_NONE, CU_TENSOR_MAP_SWIZZLE_128B, CU_TENSOR_MAP_L2_PROMOTION_L2_256B,
+                         CU_TENSOR_MAP_INTERLEAVE_NONE, atom32 ? CU_TENSOR_MAP_SWIZZLE_128B_ATOM_32B : CU_TENSOR_MAP_SWIZZLE_128B,
+                         CU_TENSOR_MAP_L2_PROMOTION_L2_256B,
                          CU_TENSOR_MAP_FLOAT_OOB_FILL_NONE);
     if (cr != CUDA_SUCCESS) { set_error("cuTensorMapEncodeTiled failed (%d)", (int)cr); return DFM_ERR_CUDA; }
     return DFM_OK;

@@ -16,24 +16,29 @@ def report(tag, got, A, B):     # A (M,K), B (N,K) logical
           f"vs hh+lh {rel(got, hh + Al @ Bh.t()):.2e} | vs 3-term {rel(got, hh + Ah @ Bl.t() + Al @ Bh.t()):.2e}", flush=True)
 
 torch.manual_seed(0)
-for (M, N, K) in [(128, 32, 32), (128, 64, 64), (256, 128, 256), (4096, 256, 2496), (1000, 2496, 256)]:
-    x = torch.randn(M, K, device="cuda"); w = torch.randn(N, K, device="cuda")
-    try:
-        y = _gemm3(0, x, w, torch.zeros(M, N, device="cuda"), None, M, N, K); torch.cuda.synchronize()
-        report(f"mode0 NT M{M} N{N} K{K}", y, x, w)
-    except Exception as e:
-        print("mode0 failed", M, N, K, e)
-    dy = torch.randn(M, N, device="cuda")
-    try:
-        dx = _gemm3(1, dy, w, torch.zeros(M, K, device="cuda"), None, M, K, N); torch.cuda.synchronize()
-        report(f"mode1 NN M{M} N{K} K{N}", dx, dy, w.t().contiguous())
-    except Exception as e:
-        print("mode1 failed", M, N, K, e)
-    try:
-        dw = _gemm3(2, dy, x, torch.zeros(N, K, device="cuda"), None, N, K, M); torch.cuda.synchronize()
-        report(f"mode2 TN M{N} N{K} K{M}", dw, dy.t().contiguous(), x.t().contiguous())
-    except Exception as e:
-        print("mode2 failed", M, N, K, e)
+for nomask in ("", "1"):
+  if nomask: os.environ["DFM_G3_NOMASK"] = "1"
+  else: os.environ.pop("DFM_G3_NOMASK", None)
+  print("==== DFM_G3_NOMASK =", repr(nomask), flush=True)
+  for (M, N, K) in [(128, 32, 32), (128, 64, 64), (256, 128, 256), (4096, 256, 2496), (1000, 2496, 256)]:
+      x = torch.randn(M, K, device="cuda"); w = torch.randn(N, K, device="cuda")
+      try:
+          y = _gemm3(0, x, w, torch.zeros(M, N, device="cuda"), None, M, N, K); torch.cuda.synchronize()
+          report(f"mode0 NT M{M} N{N} K{K}", y, x, w)
+      except Exception as e:
+          print("mode0 failed", M, N, K, e)
+      dy = torch.randn(M, N, device="cuda")
+      try:
+          dx = _gemm3(1, dy, w, torch.zeros(M, K, device="cuda"), None, M, K, N); torch.cuda.synchronize()
+          report(f"mode1 NN M{M} N{K} K{N}", dx, dy, w.t().contiguous())
+      except Exception as e:
+          print("mode1 failed", M, N, K, e)
+      try:
+          dw = _gemm3(2, dy, x, torch.zeros(N, K, device="cuda"), None, N, K, M); torch.cuda.synchronize()
+          report(f"mode2 TN M{N} N{K} K{M}", dw, dy.t().contiguous(), x.t().contiguous())
+      except Exception as e:
+          print("mode2 failed", M, N, K, e)
+os.environ.pop("DFM_G3_NOMASK", None)
 # layout probe: A = shifted identity, B[n][k] = 100 n + k  ->  D[m][n] = B[n][m]
 M, N, K = 128, 32, 32
 A = torch.zeros(M, K, device="cuda"); A[torch.arange(K), torch.arange(K)] = 1.0

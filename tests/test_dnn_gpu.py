@@ -1,6 +1,6 @@
 """DNN tower on the repo's own kernels against torch in fp64.
 
-dfm_gemm3 (tcgen05, 3xTF32) in its three operand layouts: max-norm relative error <= 2e-6 vs the fp64 product (the
+dfm_gemm3 (tcgen05, 3xTF32) in its three operand layouts: max-norm relative error <= 3e-6 vs the fp64 product (the
 error class of an fp32 SIMT sgemm; a single TF32 pass would be ~1e-3).  The fused Linear -> BatchNorm1d -> act ->
 Dropout block and the head Linear against the eager nn.Sequential of the same module evaluated in fp64: forward 1e-5,
 gradients 1e-4 (reference: deepfm/models/layers/dnn.py:45-59)."""
@@ -24,12 +24,12 @@ def test_gemm3_nt_nn_tn_vs_fp64(M, N, K):
     b = torch.randn(N, device="cuda")
     y = _gemm3(0, x, w, torch.empty(M, N, device="cuda"), b, M, N, K)
     ref = x.double() @ w.double().t() + b.double()
-    assert_close_rel(y.cpu(), ref.cpu(), 2e-6, "NT (Linear forward)")
+    assert_close_rel(y.cpu(), ref.cpu(), 3e-6, "NT (Linear forward)")
     dy = torch.randn(M, N, device="cuda")
     dx = _gemm3(1, dy, w, torch.empty(M, K, device="cuda"), None, M, K, N)
-    assert_close_rel(dx.cpu(), (dy.double() @ w.double()).cpu(), 2e-6, "NN (grad input)")
+    assert_close_rel(dx.cpu(), (dy.double() @ w.double()).cpu(), 3e-6, "NN (grad input)")
     dw = _gemm3(2, dy, x, torch.empty(N, K, device="cuda"), None, N, K, M)
-    assert_close_rel(dw.cpu(), (dy.double().t() @ x.double()).cpu(), 2e-6, "TN (grad weight)")
+    assert_close_rel(dw.cpu(), (dy.double().t() @ x.double()).cpu(), 3e-6, "TN (grad weight)")
     dw2 = _gemm3(2, dy, x, torch.empty(N, K, device="cuda"), None, N, K, M)
     assert torch.equal(dw, dw2)                                   # split-K with a fixed-order reduce: deterministic
 
