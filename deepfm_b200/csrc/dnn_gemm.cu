@@ -46,7 +46,9 @@ struct Args {
     long long split_stride;              // floats between the partial outputs of consecutive splits
     int a_mn, b_mn;                      // 1: the operand is MN-major ([K][MN] in memory)
     int nstage;
-    int mask_hi;                         // 1: write x_hi back over the raw tile (0: rely on the MMA ignoring the low 13 bits)
+    int mask_hi;                         // 1: write x_hi back over the raw tile (0, default: kind::tf32 ignores the low 13
+                                         // mantissa bits of its operands -- measured: identical results -- so raw IS hi)
+    int b_lo_tma;                        // 1: B_lo was precomputed in global memory (weights) and arrives by TMA (mapBlo)
     uint32_t tmem_cols;
 };
 
@@ -67,7 +69,8 @@ __device__ __forceinline__ uint64_t make_desc_mn(uint32_t smem_addr) {
 __device__ __forceinline__ float tf32_hi(float x) { return __uint_as_float(__float_as_uint(x) & 0xffffe000u); }
 
 __global__ void __launch_bounds__(THREADS, 1)
-gemm3_kernel(const __grid_constant__ Args a, const __grid_constant__ CUtensorMap mapA, const __grid_constant__ CUtensorMap mapB) {
+gemm3_kernel(const __grid_constant__ Args a, const __grid_constant__ CUtensorMap mapA, const __grid_constant__ CUtensorMap mapB,
+             const __grid_constant__ CUtensorMap mapBlo) {
     using namespace tc;
     extern __shared__ unsigned char smem_raw[];
     unsigned char* smem = smem_raw + ((1024u - (smem_u32(smem_raw) & 1023u)) & 1023u);
@@ -114,7 +117,7 @@ gemm3_kernel(const __grid_constant__ Args a, const __grid_constant__ CUtensorMap
         // ------------------------------------------------------------------ TMA producer
         if (lane == 0) {
             uint32_t s = 0, ph = 0;
-            const uint32_t tx = (uint32_t)(A_BYTES + b_bytes);
+            const uint32_t tx = (uint32_t)(A_BYTES + b_bytes * (a.b_lo_tma ? 2 : 1));
             for (long long u = blockIdx.x; u < n_units; u += gridDim.x) {
                 int mt, nt, sp;
                 unit_of(u, mt, nt, sp);
@@ -130,6 +133,11 @@ gemm3_kernel(const __grid_constant__ Args a, const __grid_constant__ CUtensorMap
                     else for (int j = 0; j < TM / 32; ++j) tma_load_2d(sa + j * 4096, &mapA, mt * TM + j * 32, kk, full_raw + s);
                     if (!a.b_mn) tma_load_2d(sb, &mapB, kk, nt * a.tn, full_raw + s);                 // box {32 k, tn rows}
                     else for (int j = 0; j < a.tn / 32; ++j) tma_load_2d(sb + j * 4096, &mapB, nt * a.tn + j * 32, kk, full_raw + s);
+                    if (a.b_lo_tma) {
+                        unsigned char* sl = sb + b_bytes;
+                        if (!a.b_mn) tma_load_2d(sl, &mapBlo, kk, nt * a.tn, full_raw + s);
+                        else for (int j = 0; j < a.tn / 32; ++j) tma_load_2d(sl + j * 4096, &mapBlo, nt * a.tn + j * 32, kk, full_raw + s);
+                    }
                     if (++s == (uint32_t)a.nstage) { s = 0; ph ^= 1u; }
                 }
             }
@@ -217,7 +225,7 @@ gemm3_kernel(const __grid_constant__ Args a, const __grid_constant__ CUtensorMap
                 tmem_st32(tmem_base + ((uint32_t)(q * 32) << 16) + alo_col0 + s * 32, lo);
                 float4* bh = reinterpret_cast<float4*>(sa + A_BYTES);
                 float4* bl = reinterpret_cast<float4*>(sa + A_BYTES + b_bytes);
-                const int nchunk = b_bytes >> 4;
+                const int nchunk = a.b_lo_tma ? 0 : (b_bytes >> 4);
                 for (int i = tid; i < nchunk; i += 128) {
                     const float4 v = bh[i];
                     const float4 h = make_float4(tf32_hi(v.x), tf32_hi(v.y), tf32_hi(v.z), tf32_hi(v.w));
@@ -291,6 +299,15 @@ gemm3_kernel(const __grid_constant__ Args a, const __grid_constant__ CUtensorMap
     if (warp == 1) tmem_dealloc(tmem_base, a.tmem_cols);
 }
 
+// lo[i] = x[i] - tf32_hi(x[i])   (weights: split once per call instead of once per M tile)
+__global__ void __launch_bounds__(256)
+split_lo_kernel(const float* __restrict__ x, float* __restrict__ lo, long long n) {
+    for (long long i = (long long)blockIdx.x * blockDim.x + threadIdx.x; i < n; i += (long long)gridDim.x * blockDim.x) {
+        const float v = __ldg(x + i);
+        lo[i] = v - tf32_hi(v);
+    }
+}
+
 // out[i] = sum_s partial[s][i] in split order (+ bias): the deterministic end of a split-K product
 __global__ void __launch_bounds__(256)
 splitk_reduce_kernel(const float* __restrict__ partial, int n_split, long long stride, float* __restrict__ out, long long n) {
@@ -338,6 +355,7 @@ static int make_plan(int mode, long long M, long long N, long long K, Plan& p) {
     while (cols < (uint32_t)(2 * p.tn + p.nstage * 32)) cols <<= 1;
     p.tmem_cols = cols;
     p.ws_bytes = p.n_split > 1 ? (size_t)p.n_split * M * N * 4 : 0;
+    if (mode != 2) p.ws_bytes += align_up((size_t)N * K * 4, 256);      // B_lo of the weight operand
     return DFM_OK;
 }
 
@@ -363,7 +381,7 @@ int dfm_gemm3(int mode, const float* A, const float* B, float* D, const float* b
     if (rc) return rc;
     DFM_REQUIRE(((reinterpret_cast<uintptr_t>(A) | reinterpret_cast<uintptr_t>(B)) & 15u) == 0, DFM_ERR_UNSUPPORTED,
                 "dfm_gemm3: operands must be 16-byte aligned");
-    DFM_REQUIRE(p.n_split == 1 || (workspace && workspace_bytes >= p.ws_bytes), DFM_ERR_WORKSPACE,
+    DFM_REQUIRE(p.ws_bytes == 0 || (workspace && workspace_bytes >= p.ws_bytes), DFM_ERR_WORKSPACE,
                 "dfm_gemm3: workspace %zu < %zu", workspace_bytes, p.ws_bytes);
     DFM_REQUIRE(p.n_split == 1 || !bias, DFM_ERR_UNSUPPORTED, "dfm_gemm3: bias with split-K is not supported");
     cudaStream_t st = static_cast<cudaStream_t>(stream);
@@ -372,7 +390,8 @@ int dfm_gemm3(int mode, const float* A, const float* B, float* D, const float* b
     a.M = M; a.N = N; a.K = K; a.tn = p.tn; a.n_mt = p.n_mt; a.n_nt = p.n_nt; a.n_split = p.n_split;
     a.k_per_split = p.k_per_split; a.nstage = p.nstage; a.tmem_cols = p.tmem_cols;
     a.a_mn = mode == 2 ? 1 : 0; a.b_mn = mode == 0 ? 0 : 1;
-    a.mask_hi = getenv("DFM_G3_NOMASK") ? 0 : 1;
+    a.mask_hi = getenv("DFM_G3_MASK") ? 1 : 0;
+    a.b_lo_tma = (mode != 2 && !getenv("DFM_G3_SPLIT_B_IN_KERNEL")) ? 1 : 0;
     a.bias = bias;
     if (p.n_split > 1) { a.D = static_cast<float*>(workspace); a.ldd = N; a.split_stride = M * N; }
     else { a.D = D; a.ldd = N; a.split_stride = 0; }
@@ -382,10 +401,20 @@ int dfm_gemm3(int mode, const float* A, const float* B, float* D, const float* b
     if (rc) return rc;
     rc = a.b_mn ? tc::make_tmap_2d(&mapB, B, K, N, 32, true) : tc::make_tmap_2d(&mapB, B, N, K, p.tn);
     if (rc) return rc;
+    CUtensorMap mapBlo = mapB;
+    if (a.b_lo_tma) {
+        float* blo = static_cast<float*>(workspace);      // mode 0 / 1 never split K: the workspace is all ours
+        const long long nb = N * K;
+        long long blocks = ceil_div(nb, 256 * 4);
+        if (blocks > 4LL * sm_count()) blocks = 4LL * sm_count();
+        split_lo_kernel<<<(unsigned)blocks, 256, 0, st>>>(B, blo, nb);
+        rc = a.b_mn ? tc::make_tmap_2d(&mapBlo, blo, K, N, 32, true) : tc::make_tmap_2d(&mapBlo, blo, N, K, p.tn);
+        if (rc) return rc;
+    }
     DFM_CHECK_CUDA(cudaFuncSetAttribute(gemm3_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)p.smem));
     long long grid = (long long)p.n_mt * p.n_nt * p.n_split;
     if (grid > sm_count()) grid = sm_count();
-    gemm3_kernel<<<(unsigned)grid, THREADS, p.smem, st>>>(a, mapA, mapB);
+    gemm3_kernel<<<(unsigned)grid, THREADS, p.smem, st>>>(a, mapA, mapB, mapBlo);
     if (p.n_split > 1) {
         const long long n = M * N;
         long long blocks = ceil_div(n, 256);

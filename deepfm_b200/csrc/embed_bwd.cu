@@ -70,6 +70,7 @@ struct BwdArgs {
     float* peer_sc[16];
     const uint32_t* uidx;
     float peer_scale;
+    int dbg;                       // tuning switches (env DFM_SEG2_DBG): 1 = block-contiguous spans, 2 = table row loaded at the head
 };
 
 // destination of exchange row u (peer output mode)
@@ -844,8 +845,10 @@ struct Seg2Batch {
     float w1[NB];
 };
 
+constexpr int SEG2_BLOCKS_PER_SM = 3;     // register budget of seg2_kernel (85 / thread); the host sizes the spans for ONE wave
+
 template <int VW, bool HAS_FM, bool HAS_FIELD, bool HAS_BAG, bool DIRECT>
-__global__ void __launch_bounds__(256, 3)
+__global__ void __launch_bounds__(256, SEG2_BLOCKS_PER_SM)
 seg2_kernel(const __grid_constant__ DevPlan P, const __grid_constant__ DevGrads GR,
             const __grid_constant__ BwdArgs a, long long unit) {
     __shared__ FieldB t_field[MAX_FIELDS];
@@ -863,7 +866,9 @@ seg2_kernel(const __grid_constant__ DevPlan P, const __grid_constant__ DevGrads 
     const int lane = threadIdx.x & 31;
     // spans are dealt to the warps round-robin over the blocks: the sorted order groups the positions by table (hot
     // L2-resident small tables first, cold big tables last), so a block's eight warps take spans that are far apart
-    const long long unit_idx = (long long)(threadIdx.x >> 5) * gridDim.x + blockIdx.x;
+    const long long unit_idx = (a.dbg & 1) ? (long long)blockIdx.x * (blockDim.x >> 5) + (threadIdx.x >> 5)
+                                           : (long long)(threadIdx.x >> 5) * gridDim.x + blockIdx.x;
+    const bool w_in_batch = !(a.dbg & 2);
     const long long p_lo = unit_idx * unit;
     const long long p_hi = (p_lo + unit < a.N) ? p_lo + unit : a.N;
     const uint32_t PAD = a.pad_key;
@@ -962,7 +967,7 @@ seg2_kernel(const __grid_constant__ DevPlan P, const __grid_constant__ DevGrads 
                             for (int v = 0; v < VW; ++v) B.eB[i][v] = 0.f;
                         }
                     }
-                    if (need_w && ((headmask >> r) & 1u) && r0 + i < n_live) {   // the table row of a segment head
+                    if (need_w && w_in_batch && ((headmask >> r) & 1u) && r0 + i < n_live) {   // the table row of a segment head
                         const int f = __shfl_sync(0xffffffffu, fl, r);
                         const unsigned long long wo = __shfl_sync(0xffffffffu, wofs, r);
                         lv_load<VW>(B.w[i], t_field[f].w2 + wo + lane * VW);
@@ -983,6 +988,12 @@ seg2_kernel(const __grid_constant__ DevPlan P, const __grid_constant__ DevGrads 
 #pragma unroll
                         for (int v = 0; v < VW; ++v) { st.acc[v] = 0.f; st.w[v] = B.w[i][v]; }
                         st.w1 = B.w1[i];
+                        if (need_w && !w_in_batch) {
+                            const FieldB& fb = t_field[st.f];
+                            const size_t row = (size_t)(st.cur - fb.row_base);
+                            lv_load<VW>(st.w, fb.w2 + row * tdim + lane * VW);
+                            if (need_w1) st.w1 = __ldg(fb.w1 + row);
+                        }
                         ++n_heads;
                     }
                     const float mr = (HAS_FM || DIRECT) ? __shfl_sync(0xffffffffu, m, r) : 0.f;
@@ -1434,6 +1445,7 @@ static int embed_bwd_impl(const dfm_plan* plan, int64_t batch, long long direct_
     a.direct = direct ? 1 : 0;
     a.row_stride = plan->max_tdim + 4;
     a.pad_key = (unsigned)plan->total_rows;
+    { const char* e = getenv("DFM_SEG2_DBG"); a.dbg = e ? atoi(e) : 0; }
     if (direct && g_first) { a.g_sc = g_first; a.g_first = nullptr; }    // split layout of the exchanged rows (dfm_rows_bwd)
     a.counters = n_valid ? reinterpret_cast<unsigned long long*>(n_valid)
                          : reinterpret_cast<unsigned long long*>(ws + L.off_counters);
@@ -1484,7 +1496,7 @@ static int embed_bwd_impl(const dfm_plan* plan, int64_t batch, long long direct_
                     "dfm_rows_bwd: the split (vector, scalar) row layout needs embedding_dim == fm_embed_dim in {32, 64, 128}");
         if (fast) {
             const int vw = plan->fm_dim / 32;
-            const long long warps_max = 32LL * sm_count();            // 4 blocks of 8 warps per SM
+            const long long warps_max = 8LL * SEG2_BLOCKS_PER_SM * sm_count();   // one wave of resident warps
             unit = ceil_div(ceil_div(N, warps_max), 32) * 32;
             if (unit < 256) unit = 256;                               // carry records are sized for spans >= 256 (make_layout)
             const unsigned blocks = (unsigned)ceil_div(ceil_div(N, unit), 8);
@@ -1695,6 +1707,7 @@ int dfm_shard_bwd_peer(const dfm_plan* plan, int64_t batch, const float* g_first
     a.open_count = reinterpret_cast<unsigned*>(ws + L.off_open); a.open_list = a.open_count + 1;
     a.long_count = reinterpret_cast<unsigned*>(ws + L.off_long); a.long_list = a.long_count + 2;
     a.pad_key = pad_key;
+    { const char* e = getenv("DFM_SEG2_DBG"); a.dbg = e ? atoi(e) : 0; }
     a.peer_n = n_peers; a.uidx = uidx; a.peer_scale = grad_scale;
     for (int q = 0; q < n_peers; ++q) {
         DFM_REQUIRE(peer_vec[q] && peer_sc[q] && al16(peer_vec[q]) && al16(peer_sc[q]) && peer_start[q] <= peer_start[q + 1], DFM_ERR_INVALID,
@@ -1706,7 +1719,7 @@ int dfm_shard_bwd_peer(const dfm_plan* plan, int64_t batch, const float* g_first
     DFM_CHECK_CUDA(cudaMemsetAsync(a.open_count, 0, 4, st));
     DFM_CHECK_CUDA(cudaMemsetAsync(a.long_count, 0, 4, st));
     const long long N = n_sorted;
-    const long long warps_max = 32LL * sm_count();
+    const long long warps_max = 8LL * SEG2_BLOCKS_PER_SM * sm_count();   // one wave of resident warps
     long long unit = ceil_div(ceil_div(N, warps_max), 32) * 32;
     if (unit < 256) unit = 256;
     const unsigned blocks = (unsigned)ceil_div(ceil_div(N, unit), 8);

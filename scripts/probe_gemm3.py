@@ -17,9 +17,9 @@ def report(tag, got, A, B):     # A (M,K), B (N,K) logical
 
 torch.manual_seed(0)
 for nomask in ("", "1"):
-  if nomask: os.environ["DFM_G3_NOMASK"] = "1"
-  else: os.environ.pop("DFM_G3_NOMASK", None)
-  print("==== DFM_G3_NOMASK =", repr(nomask), flush=True)
+  if nomask: os.environ["DFM_G3_SPLIT_B_IN_KERNEL"] = "1"
+  else: os.environ.pop("DFM_G3_SPLIT_B_IN_KERNEL", None)
+  print("==== DFM_G3_SPLIT_B_IN_KERNEL =", repr(nomask), flush=True)
   for (M, N, K) in [(128, 32, 32), (128, 64, 64), (256, 128, 256), (4096, 256, 2496), (1000, 2496, 256)]:
       x = torch.randn(M, K, device="cuda"); w = torch.randn(N, K, device="cuda")
       try:
@@ -38,7 +38,7 @@ for nomask in ("", "1"):
           report(f"mode2 TN M{N} N{K} K{M}", dw, dy.t().contiguous(), x.t().contiguous())
       except Exception as e:
           print("mode2 failed", M, N, K, e)
-os.environ.pop("DFM_G3_NOMASK", None)
+os.environ.pop("DFM_G3_SPLIT_B_IN_KERNEL", None)
 # layout probe: A = shifted identity, B[n][k] = 100 n + k  ->  D[m][n] = B[n][m]
 M, N, K = 128, 32, 32
 A = torch.zeros(M, K, device="cuda"); A[torch.arange(K), torch.arange(K)] = 1.0
@@ -46,3 +46,20 @@ B = (100 * torch.arange(N, device="cuda")[:, None] + torch.arange(K, device="cud
 D = _gemm3(0, A, B, torch.zeros(M, N, device="cuda"), None, M, N, K); torch.cuda.synchronize()
 print("layout mode0: D[0:4,0:4]=", D[0:4, 0:4].tolist(), "expected", B.t()[0:4, 0:4].tolist())
 print("rows 32..35:", D[32:36, 0:2].tolist(), " nonzero rows:", (D.abs().sum(1) > 0).nonzero().flatten().tolist()[:40])
+
+# timing of the three big products of the DNN's first layer at the bench shape
+import time
+M, N, K = 65536, 256, 2496
+x = torch.randn(M, K, device="cuda"); w = torch.randn(N, K, device="cuda") * 0.02; dy = torch.randn(M, N, device="cuda")
+outs = [torch.empty(M, N, device="cuda"), torch.empty(M, K, device="cuda"), torch.empty(N, K, device="cuda")]
+calls = [lambda: _gemm3(0, x, w, outs[0], None, M, N, K), lambda: _gemm3(1, dy, w, outs[1], None, M, K, N),
+         lambda: _gemm3(2, dy, x, outs[2], None, N, K, M)]
+for name, fn in zip(("fwd  Y=XW^T ", "dX=dY W     ", "dW=dY^T X   "), calls):
+    for _ in range(3): fn()
+    torch.cuda.synchronize()
+    a, b = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+    a.record()
+    for _ in range(10): fn()
+    b.record(); torch.cuda.synchronize()
+    ms = a.elapsed_time(b) / 10
+    print(f"{name} {ms * 1e3:8.1f} us  {3 * 2 * M * N * K / ms / 1e9:7.1f} TFLOP/s tf32-equivalent (3 products), {2 * M * N * K / ms / 1e9:7.1f} useful", flush=True)

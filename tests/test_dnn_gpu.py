@@ -66,9 +66,10 @@ def test_tower_matches_eager_fp64(act, bn, p):
     assert_close_rel(x.grad.cpu(), xd.grad.cpu(), 1e-4, "grad input")
     for (k, pm), (_, pr) in zip(list(tower.named_parameters()) + list(head.named_parameters()),
                                 list(ref.named_parameters()) + list(ref_head.named_parameters())):
-        assert_close_rel(pm.grad.cpu(), pr.grad.cpu(), 1e-4, k, floor=1e-6)
+        # (a Linear bias in front of a training-mode BatchNorm has an analytically zero gradient: rounding noise only)
+        assert_close_rel(pm.grad.cpu(), pr.grad.cpu(), 1e-4, k, floor=5e-6)
     for (k, bm), (_, br) in zip(tower.named_buffers(), ref.named_buffers()):     # running statistics, batch counter
-        assert_close_rel(bm.double().cpu(), br.cpu(), 1e-5, k)
+        assert_close_rel(bm.detach().double().cpu(), br.detach().cpu(), 1e-5, k)
     # eval mode: running statistics, no dropout
     tower.eval(); ref.eval()
     with torch.no_grad():
@@ -88,11 +89,11 @@ def test_tower_dropout_mask_is_regenerated_in_backward():
     x = torch.randn(B, 64, device="cuda", requires_grad=True)
     out = tower(x)
     zero = (out == 0).float().mean().item()
-    assert 0.6 < zero < 0.9                                      # relu zeros (~50 %) + dropped half of the rest
-    pre = torch.relu(x.detach() @ tower.mlp[0].weight.t() + tower.mlp[0].bias)
-    kept = out != 0
-    assert_close_rel(out[kept].detach().cpu(), (2.0 * pre[kept]).cpu(), 1e-5, "kept activations are scaled by 1/(1-p)")
+    assert 0.65 < zero < 0.85, zero                              # relu zeros (~50 %) + dropped half of the rest
+    pre = torch.relu(x.detach().double() @ tower.mlp[0].weight.detach().double().t() + tower.mlp[0].bias.detach().double())
+    kept = out.detach() != 0
+    assert_close_rel(out.detach()[kept].cpu(), (2.0 * pre[kept]).cpu(), 1e-5, "kept activations are scaled by 1/(1-p)")
     out.sum().backward()
     # the gradient flows exactly through the kept, positive units
-    want = (kept.float() * 2.0) @ tower.mlp[0].weight
+    want = (kept.double() * 2.0) @ tower.mlp[0].weight.detach().double()
     assert_close_rel(x.grad.cpu(), want.cpu(), 1e-5, "dropout backward uses the same mask")
