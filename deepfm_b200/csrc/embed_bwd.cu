@@ -16,6 +16,8 @@
 // order, so the gradients are bit-reproducible run to run.
 #include <stdlib.h>
 
+#include <type_traits>
+
 #include <cub/device/device_radix_sort.cuh>
 
 #include "plan.cuh"
@@ -887,6 +889,10 @@ seg2_kernel(const __grid_constant__ DevPlan P, const __grid_constant__ DevGrads 
     const float* __restrict__ fe = a.fe;
     const uint32_t* __restrict__ skeys = a.skeys;
     const uint32_t* __restrict__ spay = a.spay;
+    const float* gl = gflat + lane * VW;      // this lane's floats of row offset 0
+    const float* gfl = gfield + lane * VW;
+    const float* sl = fmsum + lane * VW;
+    const float* fel = fe + lane * VW;
     int n_valid = 0, n_heads = 0;
 
     if (p_lo < a.N) {
@@ -943,17 +949,20 @@ seg2_kernel(const __grid_constant__ DevPlan P, const __grid_constant__ DevGrads 
             const int n_live = padmask ? __ffs(padmask) - 1 : 32;       // PAD keys sort last: everything after is PAD
             if (n_live < 32) ended = true;
 
-            // loads of the NB positions starting at r0 (positions >= n_live read valid memory and are not consumed)
-            auto load_batch = [&](Batch& B, int r0) {
+            // loads of the NB positions starting at r0 (positions >= n_live read valid memory and are not consumed);
+            // FULL tiles (all 32 positions live -- every tile but the last of the data) skip the bounds checks
+            auto load_batch = [&](Batch& B, int r0, auto full_tag) {
+                constexpr bool FULL = decltype(full_tag)::value;
+                const unsigned hm = headmask >> r0;
 #pragma unroll
                 for (int i = 0; i < NB; ++i) {
-                    const int r = (r0 + i) & 31;
+                    const int r = FULL ? r0 + i : ((r0 + i) & 31);
                     const unsigned go = __shfl_sync(0xffffffffu, goff, r);
-                    lv_load_stream<VW>(B.gA[i], gflat + go + lane * VW);
-                    if (HAS_FIELD) lv_load_stream<VW>(B.gB[i], gfield + go + lane * VW);
+                    lv_load_stream<VW>(B.gA[i], gl + go);
+                    if (HAS_FIELD) lv_load_stream<VW>(B.gB[i], gfl + go);
                     if (HAS_FM && !DIRECT) {
                         const unsigned bo = __shfl_sync(0xffffffffu, bofs, r);
-                        if (fm_rt) lv_load<VW>(B.sv[i], fmsum + bo + lane * VW);
+                        if (fm_rt) lv_load<VW>(B.sv[i], sl + bo);
                         else {
 #pragma unroll
                             for (int v = 0; v < VW; ++v) B.sv[i][v] = 0.f;
@@ -961,13 +970,13 @@ seg2_kernel(const __grid_constant__ DevPlan P, const __grid_constant__ DevGrads 
                     }
                     if (HAS_BAG) {                                      // pooled embedding of the bag (aliased layout: same offset)
                         const int bg = __shfl_sync(0xffffffffu, bag, r);
-                        if (bg && fm_rt) lv_load<VW>(B.eB[i], fe + go + lane * VW);
+                        if (bg && fm_rt) lv_load<VW>(B.eB[i], fel + go);
                         else {
 #pragma unroll
                             for (int v = 0; v < VW; ++v) B.eB[i][v] = 0.f;
                         }
                     }
-                    if (need_w && w_in_batch && ((headmask >> r) & 1u) && r0 + i < n_live) {   // the table row of a segment head
+                    if (need_w && w_in_batch && ((hm >> i) & 1u) && (FULL || r0 + i < n_live)) {   // the table row of a segment head
                         const int f = __shfl_sync(0xffffffffu, fl, r);
                         const unsigned long long wo = __shfl_sync(0xffffffffu, wofs, r);
                         lv_load<VW>(B.w[i], t_field[f].w2 + wo + lane * VW);
@@ -975,12 +984,14 @@ seg2_kernel(const __grid_constant__ DevPlan P, const __grid_constant__ DevGrads 
                     }
                 }
             };
-            auto consume_batch = [&](const Batch& B, int r0) {
+            auto consume_batch = [&](const Batch& B, int r0, auto full_tag) {
+                constexpr bool FULL = decltype(full_tag)::value;
+                const unsigned hm = headmask >> r0;
 #pragma unroll
                 for (int i = 0; i < NB; ++i) {
                     const int r = r0 + i;
-                    if (r >= n_live) break;
-                    if ((headmask >> r) & 1u) {
+                    if (!FULL && r >= n_live) break;
+                    if ((hm >> i) & 1u) {
                         if (st.cur != PAD) seg2_close<VW>(P, GR, a, t_field, coef, need_w, lane, unit_idx, st);
                         st.cur = __shfl_sync(0xffffffffu, key, r);
                         st.f = __shfl_sync(0xffffffffu, fl, r);
@@ -1011,17 +1022,30 @@ seg2_kernel(const __grid_constant__ DevPlan P, const __grid_constant__ DevGrads 
                     }
                     if (!HAS_BAG || !bg) st.gs += mr;                   // bag members carry their e term themselves
                     st.a1 += orr;
-                    ++n_valid;
                 }
+                n_valid += FULL ? NB : ((n_live - r0 < NB) ? (n_live - r0 > 0 ? n_live - r0 : 0) : NB);
             };
             // ---- consume the tile in sorted order, two batches in flight
             Batch B0, B1;
-            if (n_live > 0) load_batch(B0, 0);
-            for (int r0 = 0; r0 < n_live; r0 += 2 * NB) {
-                if (r0 + NB < n_live) load_batch(B1, r0 + NB);
-                consume_batch(B0, r0);
-                if (r0 + 2 * NB < n_live) load_batch(B0, r0 + 2 * NB);
-                if (r0 + NB < n_live) consume_batch(B1, r0 + NB);
+            if (n_live == 32) {
+                const std::true_type full{};
+                load_batch(B0, 0, full);
+#pragma unroll 1
+                for (int r0 = 0; r0 < 32; r0 += 2 * NB) {
+                    load_batch(B1, r0 + NB, full);
+                    consume_batch(B0, r0, full);
+                    if (r0 + 2 * NB < 32) load_batch(B0, r0 + 2 * NB, full);
+                    consume_batch(B1, r0 + NB, full);
+                }
+            } else {
+                const std::false_type part{};
+                if (n_live > 0) load_batch(B0, 0, part);
+                for (int r0 = 0; r0 < n_live; r0 += 2 * NB) {
+                    if (r0 + NB < n_live) load_batch(B1, r0 + NB, part);
+                    consume_batch(B0, r0, part);
+                    if (r0 + 2 * NB < n_live) load_batch(B0, r0 + 2 * NB, part);
+                    if (r0 + NB < n_live) consume_batch(B1, r0 + NB, part);
+                }
             }
         }
         // ---- the span's last segment: finished here, or handed to the stitch pass

@@ -38,7 +38,7 @@ class TableNormCache:
 
     @staticmethod
     def key_of(tables) -> tuple:
-        return tuple((p.data_ptr(), p._version, p.numel()) for p in tables)
+        return tuple(sorted((p.data_ptr(), p._version, p.numel()) for p in tables))      # a set: callers list the tables in different orders
 
     def valid_for(self, tables) -> bool:
         return self.acc is not None and self.key == self.key_of(tables)
