@@ -847,10 +847,12 @@ struct Seg2Batch {
     float w1[NB];
 };
 
-constexpr int SEG2_BLOCKS_PER_SM = 3;     // register budget of seg2_kernel (85 / thread); the host sizes the spans for ONE wave
+// CFG 0: 3 blocks / SM (85 registers), 2 x 4 positions in flight per warp;  CFG 1: 2 blocks / SM (128 registers), 2 x 8.
+// The host sizes the spans for ONE wave of resident warps.
+__host__ __device__ constexpr int seg2_blocks_per_sm(int cfg) { return cfg == 1 ? 2 : 3; }
 
-template <int VW, bool HAS_FM, bool HAS_FIELD, bool HAS_BAG, bool DIRECT>
-__global__ void __launch_bounds__(256, SEG2_BLOCKS_PER_SM)
+template <int VW, bool HAS_FM, bool HAS_FIELD, bool HAS_BAG, bool DIRECT, int CFG>
+__global__ void __launch_bounds__(256, seg2_blocks_per_sm(CFG))
 seg2_kernel(const __grid_constant__ DevPlan P, const __grid_constant__ DevGrads GR,
             const __grid_constant__ BwdArgs a, long long unit) {
     __shared__ FieldB t_field[MAX_FIELDS];
@@ -862,8 +864,8 @@ seg2_kernel(const __grid_constant__ DevPlan P, const __grid_constant__ DevGrads 
     __syncthreads();
     // two batches of NB positions are in flight per warp (~48 load registers per lane)
     constexpr int STREAMS = 2 + ((HAS_FM && !DIRECT) ? 1 : 0) + (HAS_FIELD ? 1 : 0) + (HAS_BAG ? 1 : 0);   // incl. the w rows
-    constexpr int NBQ = 24 / (VW * STREAMS);
-    constexpr int NB = NBQ >= 4 ? 4 : 2;
+    constexpr int NBQ = (CFG == 1 ? 48 : 24) / (VW * STREAMS);
+    constexpr int NB = NBQ >= 8 ? 8 : NBQ >= 4 ? 4 : 2;
     using Batch = Seg2Batch<VW, NB, HAS_FM, HAS_FIELD, HAS_BAG, DIRECT>;
     const int lane = threadIdx.x & 31;
     // spans are dealt to the warps round-robin over the blocks: the sorted order groups the positions by table (hot
@@ -877,7 +879,8 @@ seg2_kernel(const __grid_constant__ DevPlan P, const __grid_constant__ DevGrads 
     const int bits = a.slot_bits;
     const uint32_t smask = (1u << bits) - 1u;
     const float coef = a.peer_n > 0 ? 0.f : a.l2x2 * (a.l2_gscale ? __ldg(a.l2_gscale) : 1.f);
-    const bool fm_rt = HAS_FM && !DIRECT && a.g_fm != nullptr;   // bag variants are compiled with HAS_FM and decide here
+    // bag variants are compiled with HAS_FM and decide at run time; for the others HAS_FM says it all
+    const bool fm_rt = HAS_FM && !DIRECT && (HAS_BAG ? a.g_fm != nullptr : true);
     const bool fm_on = DIRECT || fm_rt;
     const bool need_w = a.peer_n == 0 && (fm_on || coef != 0.f);
     const bool need_w1 = a.peer_n == 0 && coef != 0.f;
@@ -1030,8 +1033,8 @@ seg2_kernel(const __grid_constant__ DevPlan P, const __grid_constant__ DevGrads 
             if (n_live == 32) {
                 const std::true_type full{};
                 load_batch(B0, 0, full);
-#pragma unroll 1
-                for (int r0 = 0; r0 < 32; r0 += 2 * NB) {
+#pragma unroll
+                for (int r0 = 0; r0 < 32; r0 += 2 * NB) {       // fully unrolled: every shuffle lane / head bit is an immediate
                     load_batch(B1, r0 + NB, full);
                     consume_batch(B0, r0, full);
                     if (r0 + 2 * NB < 32) load_batch(B0, r0 + 2 * NB, full);
@@ -1070,19 +1073,28 @@ seg2_kernel(const __grid_constant__ DevPlan P, const __grid_constant__ DevGrads 
         atomicAdd(a.counters + threadIdx.x, (unsigned long long)s_cnt[threadIdx.x]);
 }
 
+static int seg2_cfg() { const char* e = getenv("DFM_SEG2_CFG"); return (e && atoi(e) == 1) ? 1 : 0; }
+
+template <int VW, int CFG>
+static void launch_seg2_cfg(bool direct, bool has_fm, bool has_field, bool has_bag, unsigned blocks, cudaStream_t st,
+                            const DevPlan& P, const DevGrads& GR, const BwdArgs& a, long long unit) {
+    if (direct) { seg2_kernel<VW, false, false, false, true, CFG><<<blocks, 256, 0, st>>>(P, GR, a, unit); return; }
+    if (has_bag) {
+        if (has_field) seg2_kernel<VW, true, true, true, false, CFG><<<blocks, 256, 0, st>>>(P, GR, a, unit);
+        else seg2_kernel<VW, true, false, true, false, CFG><<<blocks, 256, 0, st>>>(P, GR, a, unit);
+        return;
+    }
+    if (has_fm && has_field) seg2_kernel<VW, true, true, false, false, CFG><<<blocks, 256, 0, st>>>(P, GR, a, unit);
+    else if (has_fm) seg2_kernel<VW, true, false, false, false, CFG><<<blocks, 256, 0, st>>>(P, GR, a, unit);
+    else if (has_field) seg2_kernel<VW, false, true, false, false, CFG><<<blocks, 256, 0, st>>>(P, GR, a, unit);
+    else seg2_kernel<VW, false, false, false, false, CFG><<<blocks, 256, 0, st>>>(P, GR, a, unit);
+}
+
 template <int VW>
 static void launch_seg2(bool direct, bool has_fm, bool has_field, bool has_bag, unsigned blocks, cudaStream_t st,
                         const DevPlan& P, const DevGrads& GR, const BwdArgs& a, long long unit) {
-    if (direct) { seg2_kernel<VW, false, false, false, true><<<blocks, 256, 0, st>>>(P, GR, a, unit); return; }
-    if (has_bag) {
-        if (has_field) seg2_kernel<VW, true, true, true, false><<<blocks, 256, 0, st>>>(P, GR, a, unit);
-        else seg2_kernel<VW, true, false, true, false><<<blocks, 256, 0, st>>>(P, GR, a, unit);
-        return;
-    }
-    if (has_fm && has_field) seg2_kernel<VW, true, true, false, false><<<blocks, 256, 0, st>>>(P, GR, a, unit);
-    else if (has_fm) seg2_kernel<VW, true, false, false, false><<<blocks, 256, 0, st>>>(P, GR, a, unit);
-    else if (has_field) seg2_kernel<VW, false, true, false, false><<<blocks, 256, 0, st>>>(P, GR, a, unit);
-    else seg2_kernel<VW, false, false, false, false><<<blocks, 256, 0, st>>>(P, GR, a, unit);
+    if (seg2_cfg() == 1) launch_seg2_cfg<VW, 1>(direct, has_fm, has_field, has_bag, blocks, st, P, GR, a, unit);
+    else launch_seg2_cfg<VW, 0>(direct, has_fm, has_field, has_bag, blocks, st, P, GR, a, unit);
 }
 
 // ---- DENSE-field Linear grads and projection grads -------------------------------------
@@ -1520,7 +1532,7 @@ static int embed_bwd_impl(const dfm_plan* plan, int64_t batch, long long direct_
                     "dfm_rows_bwd: the split (vector, scalar) row layout needs embedding_dim == fm_embed_dim in {32, 64, 128}");
         if (fast) {
             const int vw = plan->fm_dim / 32;
-            const long long warps_max = 8LL * SEG2_BLOCKS_PER_SM * sm_count();   // one wave of resident warps
+            const long long warps_max = 8LL * seg2_blocks_per_sm(seg2_cfg()) * sm_count();   // one wave of resident warps
             unit = ceil_div(ceil_div(N, warps_max), 32) * 32;
             if (unit < 256) unit = 256;                               // carry records are sized for spans >= 256 (make_layout)
             const unsigned blocks = (unsigned)ceil_div(ceil_div(N, unit), 8);
@@ -1743,7 +1755,7 @@ int dfm_shard_bwd_peer(const dfm_plan* plan, int64_t batch, const float* g_first
     DFM_CHECK_CUDA(cudaMemsetAsync(a.open_count, 0, 4, st));
     DFM_CHECK_CUDA(cudaMemsetAsync(a.long_count, 0, 4, st));
     const long long N = n_sorted;
-    const long long warps_max = 8LL * SEG2_BLOCKS_PER_SM * sm_count();   // one wave of resident warps
+    const long long warps_max = 8LL * seg2_blocks_per_sm(seg2_cfg()) * sm_count();   // one wave of resident warps
     long long unit = ceil_div(ceil_div(N, warps_max), 32) * 32;
     if (unit < 256) unit = 256;
     const unsigned blocks = (unsigned)ceil_div(ceil_div(N, unit), 8);

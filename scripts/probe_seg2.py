@@ -21,12 +21,13 @@ def step(i):
     fo, fe, fl = emb(batches[i % 3])
     torch.autograd.backward([fl, fo, fm(fe)], [g_flat, torch.ones_like(fo), torch.ones_like(fo)])
 
-for dbg in ("0", "1", "2", "3"):
+for cfg, dbg in (("0", "0"), ("0", "1"), ("1", "0"), ("1", "1")):
     os.environ["DFM_SEG2_DBG"] = dbg
+    os.environ["DFM_SEG2_CFG"] = cfg
     for i in range(3): step(i)
     torch.cuda.synchronize()
     with profile(activities=[ProfilerActivity.CUDA]) as prof:
         for i in range(3): step(i)
         torch.cuda.synchronize()
     rows = [(e.key[:60], e.device_time_total / e.count) for e in prof.key_averages() if "seg2" in e.key or "stitch" in e.key or "dense_stream" in e.key or "embed_fwd" in e.key]
-    print("DFM_SEG2_DBG =", dbg, " | ".join(f"{k}: {t:.1f} us" for k, t in rows), flush=True)
+    print("DFM_SEG2_CFG =", cfg, "DFM_SEG2_DBG =", dbg, " | ".join(f"{k}: {t:.1f} us" for k, t in rows), flush=True)

@@ -66,8 +66,10 @@ def test_tower_matches_eager_fp64(act, bn, p):
     assert_close_rel(x.grad.cpu(), xd.grad.cpu(), 1e-4, "grad input")
     for (k, pm), (_, pr) in zip(list(tower.named_parameters()) + list(head.named_parameters()),
                                 list(ref.named_parameters()) + list(ref_head.named_parameters())):
-        # (a Linear bias in front of a training-mode BatchNorm has an analytically zero gradient: rounding noise only)
-        assert_close_rel(pm.grad.cpu(), pr.grad.cpu(), 1e-4, k, floor=5e-6)
+        # a Linear bias in front of a training-mode BatchNorm has an analytically zero gradient (the fp64 reference says
+        # 1e-14): what is left is the fp32 rounding noise of a 2048-term sum of +-1-sized terms
+        zero_bias = bn and k.endswith(".bias") and k.startswith("mlp.") and int(k.split(".")[1]) % 4 == 0
+        assert_close_rel(pm.grad.cpu(), pr.grad.cpu(), 1e-4, k, floor=3e-5 if zero_bias else 1e-6)
     for (k, bm), (_, br) in zip(tower.named_buffers(), ref.named_buffers()):     # running statistics, batch counter
         assert_close_rel(bm.detach().double().cpu(), br.detach().cpu(), 1e-5, k)
     # eval mode: running statistics, no dropout
