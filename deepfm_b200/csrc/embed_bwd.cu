@@ -25,6 +25,7 @@
 namespace dfm {
 
 constexpr int CHUNK = 32;      // sorted positions per lane group in segreduce
+constexpr int SEG2_UNIT = 128; // sorted positions per span of seg2_kernel (the carry records are sized for it)
 constexpr int PG_TILE = 32;    // samples per shared-memory tile in pgrads
 constexpr int PG_THREADS = 256;
 
@@ -59,6 +60,7 @@ struct BwdArgs {
     unsigned* open_list;           // those units (order irrelevant: one writer per segment)
     unsigned* long_count;          // segments spanning more than LONG_SPAN units: (owner unit, last unit) pairs
     unsigned* long_list;
+    unsigned* span_counter;        // seg2: next unclaimed span (dynamic scheduling)
     const float* g_sc;             // direct mode, split layout: g_flat = (M, tdim) vectors, g_sc = (M, 4) [g_first, g_fm, 0, 0]
     unsigned pad_key;              // PAD key of the sorted stream (normally the plan's; owner-major keys have their own)
     // peer output (row-sharded tables, sample side): the finished segment sums are not table gradients but rows of the
@@ -72,7 +74,6 @@ struct BwdArgs {
     float* peer_sc[16];
     const uint32_t* uidx;
     float peer_scale;
-    int dbg;                       // tuning switches (env DFM_SEG2_DBG): 1 = block-contiguous spans, 2 = table row loaded at the head
 };
 
 // destination of exchange row u (peer output mode)
@@ -758,7 +759,7 @@ stitch_long_kernel(const __grid_constant__ DevPlan P, const __grid_constant__ De
 // warp-uniform control flow: the decoded scalars travel by shuffle, NB positions' row loads are issued before the
 // first is consumed, segment heads come from one ballot.  The table row of a segment (for -(sum g_fm) w + 2 l2 w) is
 // requested when the segment starts and used when it ends.  No shared-memory staging, no block barrier in the loop,
-// ~18 warp instructions per position (the lane-group kernel above: ~100).  Segments that cross span boundaries use
+// ~40 warp instructions per position (the lane-group kernel above: ~100).  Segments that cross span boundaries use
 // the same head / tail carry records as segreduce_kernel, so stitch_kernel / stitch_long_kernel finish them
 // unchanged.  Summation order inside a segment is the sorted (= batch) order: deterministic.
 template <int VW> struct LaneVec;
@@ -836,23 +837,8 @@ __device__ __forceinline__ void seg2_close(const DevPlan& P, const DevGrads& GR,
     }
 }
 
-// One batch of NB positions whose loads are in flight together (register double buffer of seg2_kernel).
-template <int VW, int NB, bool HAS_FM, bool HAS_FIELD, bool HAS_BAG, bool DIRECT>
-struct Seg2Batch {
-    float gA[NB][VW];
-    float gB[HAS_FIELD ? NB : 1][VW];
-    float sv[(HAS_FM && !DIRECT) ? NB : 1][VW];
-    float eB[HAS_BAG ? NB : 1][VW];
-    float w[NB][VW];          // table row of a position that starts a segment (for -(sum g_fm) w + 2 l2 w at its end)
-    float w1[NB];
-};
-
-// CFG 0: 3 blocks / SM (85 registers), 2 x 4 positions in flight per warp;  CFG 1: 2 blocks / SM (128 registers), 2 x 8.
-// The host sizes the spans for ONE wave of resident warps.
-__host__ __device__ constexpr int seg2_blocks_per_sm(int cfg) { return cfg == 1 ? 2 : 3; }
-
-template <int VW, bool HAS_FM, bool HAS_FIELD, bool HAS_BAG, bool DIRECT, int CFG>
-__global__ void __launch_bounds__(256, seg2_blocks_per_sm(CFG))
+template <int VW, bool HAS_FM, bool HAS_FIELD, bool HAS_BAG, bool DIRECT>
+__global__ void __launch_bounds__(256, 4)
 seg2_kernel(const __grid_constant__ DevPlan P, const __grid_constant__ DevGrads GR,
             const __grid_constant__ BwdArgs a, long long unit) {
     __shared__ FieldB t_field[MAX_FIELDS];
@@ -862,19 +848,12 @@ seg2_kernel(const __grid_constant__ DevPlan P, const __grid_constant__ DevGrads 
     for (int s = threadIdx.x; s < P.S; s += blockDim.x) s_slotf[s] = P.slot_field[s];
     if (threadIdx.x < 2) s_cnt[threadIdx.x] = 0;
     __syncthreads();
-    // two batches of NB positions are in flight per warp (~48 load registers per lane)
-    constexpr int STREAMS = 2 + ((HAS_FM && !DIRECT) ? 1 : 0) + (HAS_FIELD ? 1 : 0) + (HAS_BAG ? 1 : 0);   // incl. the w rows
-    constexpr int NBQ = (CFG == 1 ? 48 : 24) / (VW * STREAMS);
+    // positions whose row loads are in flight together: ~24 floats of load registers per lane
+    constexpr int STREAMS = 1 + ((HAS_FM && !DIRECT) ? 1 : 0) + (HAS_FIELD ? 1 : 0) + (HAS_BAG ? 1 : 0);
+    constexpr int NBQ = 24 / (VW * STREAMS);
     constexpr int NB = NBQ >= 8 ? 8 : NBQ >= 4 ? 4 : 2;
-    using Batch = Seg2Batch<VW, NB, HAS_FM, HAS_FIELD, HAS_BAG, DIRECT>;
     const int lane = threadIdx.x & 31;
-    // spans are dealt to the warps round-robin over the blocks: the sorted order groups the positions by table (hot
-    // L2-resident small tables first, cold big tables last), so a block's eight warps take spans that are far apart
-    const long long unit_idx = (a.dbg & 1) ? (long long)blockIdx.x * (blockDim.x >> 5) + (threadIdx.x >> 5)
-                                           : (long long)(threadIdx.x >> 5) * gridDim.x + blockIdx.x;
-    const bool w_in_batch = !(a.dbg & 2);
-    const long long p_lo = unit_idx * unit;
-    const long long p_hi = (p_lo + unit < a.N) ? p_lo + unit : a.N;
+    const long long n_units = (a.N + unit - 1) / unit;
     const uint32_t PAD = a.pad_key;
     const int bits = a.slot_bits;
     const uint32_t smask = (1u << bits) - 1u;
@@ -883,28 +862,30 @@ seg2_kernel(const __grid_constant__ DevPlan P, const __grid_constant__ DevGrads 
     const bool fm_rt = HAS_FM && !DIRECT && (HAS_BAG ? a.g_fm != nullptr : true);
     const bool fm_on = DIRECT || fm_rt;
     const bool need_w = a.peer_n == 0 && (fm_on || coef != 0.f);
-    const bool need_w1 = a.peer_n == 0 && coef != 0.f;
     const int tdim = P.max_tdim, D = P.D, T = P.T;
-    // kernel parameters used inside the hot loop, in registers (the by-value structs live in the constant bank)
-    const float* __restrict__ gflat = a.g_flat;
-    const float* __restrict__ gfield = a.g_field;
-    const float* __restrict__ fmsum = a.fm_sum;
-    const float* __restrict__ fe = a.fe;
-    const uint32_t* __restrict__ skeys = a.skeys;
-    const uint32_t* __restrict__ spay = a.spay;
-    const float* gl = gflat + lane * VW;      // this lane's floats of row offset 0
-    const float* gfl = gfield + lane * VW;
-    const float* sl = fmsum + lane * VW;
-    const float* fel = fe + lane * VW;
+    // this lane's floats of row offset 0 of every stream (one IMAD.WIDE per row address in the loop)
+    const float* __restrict__ gl = a.g_flat + lane * VW;
+    const float* __restrict__ gfl = a.g_field + lane * VW;
+    const float* __restrict__ sl = a.fm_sum + lane * VW;
+    const float* __restrict__ fel = a.fe + lane * VW;
     int n_valid = 0, n_heads = 0;
 
-    if (p_lo < a.N) {
+    // Spans are claimed dynamically (one integer atomic per span): the sorted order groups the positions by table --
+    // hot, L2-resident rows of the small tables first, cold rows of the big ones last -- so spans differ a lot in
+    // cost; which warp takes which span does not change any result (every span has its own carry records).
+    for (;;) {
+        long long unit_idx = 0;
+        if (lane == 0) unit_idx = (long long)atomicAdd(a.span_counter, 1u);
+        unit_idx = __shfl_sync(0xffffffffu, unit_idx, 0);
+        if (unit_idx >= n_units) break;
+        const long long p_lo = unit_idx * unit;
+        const long long p_hi = (p_lo + unit < a.N) ? p_lo + unit : a.N;
         Seg2State<VW> st;
         st.cur = PAD; st.seg_start = (int)p_lo; st.f = 0; st.lead = false; st.a1 = 0.f; st.gs = 0.f; st.w1 = 0.f;
 #pragma unroll
         for (int v = 0; v < VW; ++v) { st.acc[v] = 0.f; st.w[v] = 0.f; }
-        const uint32_t key0 = __ldg(skeys + p_lo);
-        if (p_lo > 0 && key0 != PAD && __ldg(skeys + p_lo - 1) == key0) {     // the span opens inside a segment
+        const uint32_t key0 = __ldg(a.skeys + p_lo);
+        if (p_lo > 0 && key0 != PAD && __ldg(a.skeys + p_lo - 1) == key0) {     // the span opens inside a segment
             st.cur = key0; st.lead = true;
         }
         bool ended = false;
@@ -912,10 +893,9 @@ seg2_kernel(const __grid_constant__ DevPlan P, const __grid_constant__ DevGrads 
             // ---- decode: one position per lane
             const long long q = p + lane;
             const bool valid = q < p_hi;
-            const uint32_t key = valid ? __ldg(skeys + q) : PAD;
-            const uint32_t pay = valid ? __ldg(spay + q) : 0u;
+            const uint32_t key = valid ? __ldg(a.skeys + q) : PAD;
+            const uint32_t pay = valid ? __ldg(a.spay + q) : 0u;
             unsigned goff = 0, bofs = 0;     // float offsets of the position's gradient row / its sample's fm_sum row
-            unsigned long long wofs = 0;     // float offset of the position's table row inside its table
             int fl = 0, bag = 0;
             float m = 0.f, o = 0.f, c = 1.f;
             if (key != PAD) {
@@ -927,8 +907,8 @@ seg2_kernel(const __grid_constant__ DevPlan P, const __grid_constant__ DevGrads 
                         o = sc.x; m = sc.y;
                     } else {
                         goff = pay * (unsigned)a.row_stride;
-                        o = __ldg(gflat + goff + tdim);      // packed first-order gradient
-                        m = __ldg(gflat + goff + tdim + 1);  // packed g_fm (for -(sum g_fm) w)
+                        o = __ldg(a.g_flat + goff + tdim);      // packed first-order gradient
+                        m = __ldg(a.g_flat + goff + tdim + 1);  // packed g_fm (for -(sum g_fm) w)
                     }
                 } else {
                     const uint32_t b = pay >> bits;
@@ -944,71 +924,56 @@ seg2_kernel(const __grid_constant__ DevPlan P, const __grid_constant__ DevGrads 
                         o *= c;
                     }
                 }
-                if (need_w) wofs = (unsigned long long)(key - t_field[fl].row_base) * (unsigned)tdim;
             }
             const uint32_t prevk = __shfl_up_sync(0xffffffffu, key, 1);
             const unsigned headmask = __ballot_sync(0xffffffffu, key != (lane == 0 ? st.cur : prevk));
             const unsigned padmask = __ballot_sync(0xffffffffu, key == PAD);
             const int n_live = padmask ? __ffs(padmask) - 1 : 32;       // PAD keys sort last: everything after is PAD
             if (n_live < 32) ended = true;
-
-            // loads of the NB positions starting at r0 (positions >= n_live read valid memory and are not consumed);
-            // FULL tiles (all 32 positions live -- every tile but the last of the data) skip the bounds checks
-            auto load_batch = [&](Batch& B, int r0, auto full_tag) {
-                constexpr bool FULL = decltype(full_tag)::value;
-                const unsigned hm = headmask >> r0;
+            // ---- consume the tile in sorted order, NB positions per batch
+            for (int r0 = 0; r0 < n_live; r0 += NB) {
+                float gA[NB][VW], gB[HAS_FIELD ? NB : 1][VW], sv[HAS_FM ? NB : 1][VW], eB[HAS_BAG ? NB : 1][VW];
 #pragma unroll
                 for (int i = 0; i < NB; ++i) {
-                    const int r = FULL ? r0 + i : ((r0 + i) & 31);
+                    const int r = (r0 + i) & 31;                       // positions >= n_live are loaded (valid memory) but not consumed
                     const unsigned go = __shfl_sync(0xffffffffu, goff, r);
-                    lv_load_stream<VW>(B.gA[i], gl + go);
-                    if (HAS_FIELD) lv_load_stream<VW>(B.gB[i], gfl + go);
+                    lv_load_stream<VW>(gA[i], gl + go);
+                    if (HAS_FIELD) lv_load_stream<VW>(gB[i], gfl + go);
                     if (HAS_FM && !DIRECT) {
                         const unsigned bo = __shfl_sync(0xffffffffu, bofs, r);
-                        if (fm_rt) lv_load<VW>(B.sv[i], sl + bo);
+                        if (fm_rt) lv_load<VW>(sv[i], sl + bo);
                         else {
 #pragma unroll
-                            for (int v = 0; v < VW; ++v) B.sv[i][v] = 0.f;
+                            for (int v = 0; v < VW; ++v) sv[i][v] = 0.f;
                         }
                     }
                     if (HAS_BAG) {                                      // pooled embedding of the bag (aliased layout: same offset)
                         const int bg = __shfl_sync(0xffffffffu, bag, r);
-                        if (bg && fm_rt) lv_load<VW>(B.eB[i], fel + go);
+                        if (bg && fm_rt) lv_load<VW>(eB[i], fel + go);
                         else {
 #pragma unroll
-                            for (int v = 0; v < VW; ++v) B.eB[i][v] = 0.f;
+                            for (int v = 0; v < VW; ++v) eB[i][v] = 0.f;
                         }
                     }
-                    if (need_w && w_in_batch && ((hm >> i) & 1u) && (FULL || r0 + i < n_live)) {   // the table row of a segment head
-                        const int f = __shfl_sync(0xffffffffu, fl, r);
-                        const unsigned long long wo = __shfl_sync(0xffffffffu, wofs, r);
-                        lv_load<VW>(B.w[i], t_field[f].w2 + wo + lane * VW);
-                        if (need_w1) B.w1[i] = __ldg(t_field[f].w1 + wo / (unsigned)tdim);
-                    }
                 }
-            };
-            auto consume_batch = [&](const Batch& B, int r0, auto full_tag) {
-                constexpr bool FULL = decltype(full_tag)::value;
-                const unsigned hm = headmask >> r0;
 #pragma unroll
                 for (int i = 0; i < NB; ++i) {
                     const int r = r0 + i;
-                    if (!FULL && r >= n_live) break;
-                    if ((hm >> i) & 1u) {
+                    if (r >= n_live) break;
+                    if ((headmask >> r) & 1u) {
                         if (st.cur != PAD) seg2_close<VW>(P, GR, a, t_field, coef, need_w, lane, unit_idx, st);
                         st.cur = __shfl_sync(0xffffffffu, key, r);
                         st.f = __shfl_sync(0xffffffffu, fl, r);
                         st.seg_start = (int)(p + r); st.lead = false; st.a1 = 0.f; st.gs = 0.f;
 #pragma unroll
-                        for (int v = 0; v < VW; ++v) { st.acc[v] = 0.f; st.w[v] = B.w[i][v]; }
-                        st.w1 = B.w1[i];
-                        if (need_w && !w_in_batch) {
+                        for (int v = 0; v < VW; ++v) st.acc[v] = 0.f;
+                        ++n_heads;
+                        if (need_w) {                                   // requested now, used when the segment ends
                             const FieldB& fb = t_field[st.f];
                             const size_t row = (size_t)(st.cur - fb.row_base);
                             lv_load<VW>(st.w, fb.w2 + row * tdim + lane * VW);
-                            if (need_w1) st.w1 = __ldg(fb.w1 + row);
+                            if (coef != 0.f) st.w1 = __ldg(fb.w1 + row);
                         }
-                        ++n_heads;
                     }
                     const float mr = (HAS_FM || DIRECT) ? __shfl_sync(0xffffffffu, m, r) : 0.f;
                     const float orr = __shfl_sync(0xffffffffu, o, r);
@@ -1017,43 +982,21 @@ seg2_kernel(const __grid_constant__ DevPlan P, const __grid_constant__ DevGrads 
                     if (HAS_BAG) { cr = __shfl_sync(0xffffffffu, c, r); bg = __shfl_sync(0xffffffffu, bag, r); }
 #pragma unroll
                     for (int v = 0; v < VW; ++v) {
-                        float t = B.gA[i][v];
-                        if (HAS_FIELD) t += B.gB[i][v];
-                        if (HAS_FM && !DIRECT) t = fmaf(mr, HAS_BAG ? B.sv[i][v] - B.eB[i][v] : B.sv[i][v], t);
+                        float t = gA[i][v];
+                        if (HAS_FIELD) t += gB[i][v];
+                        if (HAS_FM && !DIRECT) t = fmaf(mr, HAS_BAG ? sv[i][v] - eB[i][v] : sv[i][v], t);
                         if (HAS_BAG) t *= cr;
                         st.acc[v] += t;
                     }
                     if (!HAS_BAG || !bg) st.gs += mr;                   // bag members carry their e term themselves
                     st.a1 += orr;
-                }
-                n_valid += FULL ? NB : ((n_live - r0 < NB) ? (n_live - r0 > 0 ? n_live - r0 : 0) : NB);
-            };
-            // ---- consume the tile in sorted order, two batches in flight
-            Batch B0, B1;
-            if (n_live == 32) {
-                const std::true_type full{};
-                load_batch(B0, 0, full);
-#pragma unroll
-                for (int r0 = 0; r0 < 32; r0 += 2 * NB) {       // fully unrolled: every shuffle lane / head bit is an immediate
-                    load_batch(B1, r0 + NB, full);
-                    consume_batch(B0, r0, full);
-                    if (r0 + 2 * NB < 32) load_batch(B0, r0 + 2 * NB, full);
-                    consume_batch(B1, r0 + NB, full);
-                }
-            } else {
-                const std::false_type part{};
-                if (n_live > 0) load_batch(B0, 0, part);
-                for (int r0 = 0; r0 < n_live; r0 += 2 * NB) {
-                    if (r0 + NB < n_live) load_batch(B1, r0 + NB, part);
-                    consume_batch(B0, r0, part);
-                    if (r0 + 2 * NB < n_live) load_batch(B0, r0 + 2 * NB, part);
-                    if (r0 + NB < n_live) consume_batch(B1, r0 + NB, part);
+                    ++n_valid;
                 }
             }
         }
         // ---- the span's last segment: finished here, or handed to the stitch pass
         if (st.cur != PAD) {
-            const bool continues = !ended && p_hi < a.N && __ldg(skeys + p_hi) == st.cur;
+            const bool continues = !ended && p_hi < a.N && __ldg(a.skeys + p_hi) == st.cur;
             if (st.lead || !continues) {
                 seg2_close<VW>(P, GR, a, t_field, coef, need_w, lane, unit_idx, st);
             } else {
@@ -1073,28 +1016,19 @@ seg2_kernel(const __grid_constant__ DevPlan P, const __grid_constant__ DevGrads 
         atomicAdd(a.counters + threadIdx.x, (unsigned long long)s_cnt[threadIdx.x]);
 }
 
-static int seg2_cfg() { const char* e = getenv("DFM_SEG2_CFG"); return (e && atoi(e) == 1) ? 1 : 0; }
-
-template <int VW, int CFG>
-static void launch_seg2_cfg(bool direct, bool has_fm, bool has_field, bool has_bag, unsigned blocks, cudaStream_t st,
-                            const DevPlan& P, const DevGrads& GR, const BwdArgs& a, long long unit) {
-    if (direct) { seg2_kernel<VW, false, false, false, true, CFG><<<blocks, 256, 0, st>>>(P, GR, a, unit); return; }
-    if (has_bag) {
-        if (has_field) seg2_kernel<VW, true, true, true, false, CFG><<<blocks, 256, 0, st>>>(P, GR, a, unit);
-        else seg2_kernel<VW, true, false, true, false, CFG><<<blocks, 256, 0, st>>>(P, GR, a, unit);
-        return;
-    }
-    if (has_fm && has_field) seg2_kernel<VW, true, true, false, false, CFG><<<blocks, 256, 0, st>>>(P, GR, a, unit);
-    else if (has_fm) seg2_kernel<VW, true, false, false, false, CFG><<<blocks, 256, 0, st>>>(P, GR, a, unit);
-    else if (has_field) seg2_kernel<VW, false, true, false, false, CFG><<<blocks, 256, 0, st>>>(P, GR, a, unit);
-    else seg2_kernel<VW, false, false, false, false, CFG><<<blocks, 256, 0, st>>>(P, GR, a, unit);
-}
-
 template <int VW>
 static void launch_seg2(bool direct, bool has_fm, bool has_field, bool has_bag, unsigned blocks, cudaStream_t st,
                         const DevPlan& P, const DevGrads& GR, const BwdArgs& a, long long unit) {
-    if (seg2_cfg() == 1) launch_seg2_cfg<VW, 1>(direct, has_fm, has_field, has_bag, blocks, st, P, GR, a, unit);
-    else launch_seg2_cfg<VW, 0>(direct, has_fm, has_field, has_bag, blocks, st, P, GR, a, unit);
+    if (direct) { seg2_kernel<VW, false, false, false, true><<<blocks, 256, 0, st>>>(P, GR, a, unit); return; }
+    if (has_bag) {
+        if (has_field) seg2_kernel<VW, true, true, true, false><<<blocks, 256, 0, st>>>(P, GR, a, unit);
+        else seg2_kernel<VW, true, false, true, false><<<blocks, 256, 0, st>>>(P, GR, a, unit);
+        return;
+    }
+    if (has_fm && has_field) seg2_kernel<VW, true, true, false, false><<<blocks, 256, 0, st>>>(P, GR, a, unit);
+    else if (has_fm) seg2_kernel<VW, true, false, false, false><<<blocks, 256, 0, st>>>(P, GR, a, unit);
+    else if (has_field) seg2_kernel<VW, false, true, false, false><<<blocks, 256, 0, st>>>(P, GR, a, unit);
+    else seg2_kernel<VW, false, false, false, false><<<blocks, 256, 0, st>>>(P, GR, a, unit);
 }
 
 // ---- DENSE-field Linear grads and projection grads -------------------------------------
@@ -1324,7 +1258,7 @@ static int make_layout(const dfm_plan* plan, long long B, BwdLayout& L, long lon
     const long long N = direct_rows >= 0 ? direct_rows : B * plan->S;
     L.cub_bytes = 0;
     if (N > 0) { int rc = sort_temp_bytes(N, plan->key_bits, &L.cub_bytes); if (rc) return rc; }
-    L.n_chunks = ceil_div(N > 0 ? N : 1, 8 * CHUNK);   // units: >= 8 chunks per segreduce block
+    L.n_chunks = ceil_div(N > 0 ? N : 1, SEG2_UNIT);   // units: seg2 spans (segreduce blocks cover >= 256 positions)
     int vals = 0, n_pf = 0;
     for (int f = 0; f < plan->n_fields; ++f) { int n = pg_count_vals(plan, f); if (n) { vals += n; ++n_pf; } }
     L.vals_per_slice = vals;
@@ -1481,7 +1415,6 @@ static int embed_bwd_impl(const dfm_plan* plan, int64_t batch, long long direct_
     a.direct = direct ? 1 : 0;
     a.row_stride = plan->max_tdim + 4;
     a.pad_key = (unsigned)plan->total_rows;
-    { const char* e = getenv("DFM_SEG2_DBG"); a.dbg = e ? atoi(e) : 0; }
     if (direct && g_first) { a.g_sc = g_first; a.g_first = nullptr; }    // split layout of the exchanged rows (dfm_rows_bwd)
     a.counters = n_valid ? reinterpret_cast<unsigned long long*>(n_valid)
                          : reinterpret_cast<unsigned long long*>(ws + L.off_counters);
@@ -1489,6 +1422,7 @@ static int embed_bwd_impl(const dfm_plan* plan, int64_t batch, long long direct_
     a.open_list = a.open_count + 1;
     a.long_count = reinterpret_cast<unsigned*>(ws + L.off_long);
     a.long_list = a.long_count + 2;
+    a.span_counter = a.long_count + 1;
     const int fill_blocks = 8 * sm_count();
 
     // 1. dense mode: every element of every table gradient starts as 2*l2*w (or 0)
@@ -1512,7 +1446,7 @@ static int embed_bwd_impl(const dfm_plan* plan, int64_t batch, long long direct_
             if (rc) return rc;
         }
         DFM_CHECK_CUDA(cudaMemsetAsync(a.open_count, 0, 4, st));
-        DFM_CHECK_CUDA(cudaMemsetAsync(a.long_count, 0, 4, st));
+        DFM_CHECK_CUDA(cudaMemsetAsync(a.long_count, 0, 8, st));      // + the span counter next to it
         const int gpb = 256 / G;
         bool any_generic = false, any_generic_proj = false, any_bag = false;
         for (int f = 0; f < plan->n_fields; ++f) {
@@ -1532,10 +1466,10 @@ static int embed_bwd_impl(const dfm_plan* plan, int64_t batch, long long direct_
                     "dfm_rows_bwd: the split (vector, scalar) row layout needs embedding_dim == fm_embed_dim in {32, 64, 128}");
         if (fast) {
             const int vw = plan->fm_dim / 32;
-            const long long warps_max = 8LL * seg2_blocks_per_sm(seg2_cfg()) * sm_count();   // one wave of resident warps
-            unit = ceil_div(ceil_div(N, warps_max), 32) * 32;
-            if (unit < 256) unit = 256;                               // carry records are sized for spans >= 256 (make_layout)
-            const unsigned blocks = (unsigned)ceil_div(ceil_div(N, unit), 8);
+            unit = SEG2_UNIT;                                           // spans are claimed dynamically by the resident warps
+            long long want_blocks = ceil_div(ceil_div(N, unit), 8);
+            if (want_blocks > 4LL * sm_count()) want_blocks = 4LL * sm_count();   // 4 resident blocks of 8 warps per SM (64 registers)
+            const unsigned blocks = (unsigned)want_blocks;
             const bool hf = g_fm != nullptr, hg = g_field != nullptr;
             if (vw == 1) launch_seg2<1>(direct, hf, hg, any_bag, blocks, st, *P, *GR, a, unit);
             else if (vw == 2) launch_seg2<2>(direct, hf, hg, any_bag, blocks, st, *P, *GR, a, unit);
@@ -1742,8 +1676,8 @@ int dfm_shard_bwd_peer(const dfm_plan* plan, int64_t batch, const float* g_first
     a.counters = reinterpret_cast<unsigned long long*>(ws + L.off_counters);
     a.open_count = reinterpret_cast<unsigned*>(ws + L.off_open); a.open_list = a.open_count + 1;
     a.long_count = reinterpret_cast<unsigned*>(ws + L.off_long); a.long_list = a.long_count + 2;
+    a.span_counter = a.long_count + 1;
     a.pad_key = pad_key;
-    { const char* e = getenv("DFM_SEG2_DBG"); a.dbg = e ? atoi(e) : 0; }
     a.peer_n = n_peers; a.uidx = uidx; a.peer_scale = grad_scale;
     for (int q = 0; q < n_peers; ++q) {
         DFM_REQUIRE(peer_vec[q] && peer_sc[q] && al16(peer_vec[q]) && al16(peer_sc[q]) && peer_start[q] <= peer_start[q + 1], DFM_ERR_INVALID,
@@ -1753,12 +1687,12 @@ int dfm_shard_bwd_peer(const dfm_plan* plan, int64_t batch, const float* g_first
     a.peer_start[n_peers] = peer_start[n_peers];
     DFM_CHECK_CUDA(cudaMemsetAsync(a.counters, 0, 16, st));
     DFM_CHECK_CUDA(cudaMemsetAsync(a.open_count, 0, 4, st));
-    DFM_CHECK_CUDA(cudaMemsetAsync(a.long_count, 0, 4, st));
+    DFM_CHECK_CUDA(cudaMemsetAsync(a.long_count, 0, 8, st));
     const long long N = n_sorted;
-    const long long warps_max = 8LL * seg2_blocks_per_sm(seg2_cfg()) * sm_count();   // one wave of resident warps
-    long long unit = ceil_div(ceil_div(N, warps_max), 32) * 32;
-    if (unit < 256) unit = 256;
-    const unsigned blocks = (unsigned)ceil_div(ceil_div(N, unit), 8);
+    const long long unit = SEG2_UNIT;
+    long long want_blocks = ceil_div(ceil_div(N, unit), 8);
+    if (want_blocks > 4LL * sm_count()) want_blocks = 4LL * sm_count();
+    const unsigned blocks = (unsigned)want_blocks;
     const bool hf = g_fm != nullptr, hg = g_field != nullptr;
     const int vw = D / 32;
     if (vw == 1) launch_seg2<1>(false, hf, hg, any_bag, blocks, st, *P, *GR, a, unit);
