@@ -350,14 +350,15 @@ def run_ours(args, rank: int, local_rank: int, n_gpus: int):
         if reducer is not None:
             reducer.finish()
 
-    def step(batch, labels, next_batch=None):
+    def step(batch, labels, next_batch=None, next_ready=None):
+        if next_batch is not None and sharded:
+            # input pipeline: route the NEXT batch on a side stream, under this step
+            model.embedding.prefetch(next_batch, ready_event=next_ready)
         model.zero_grad(set_to_none=True)
         logits = model(batch).squeeze(1)
         loss = bce(logits, labels) + model.get_l2_reg_loss()
         loss.backward()
         allreduce_dense()
-        if next_batch is not None and sharded:
-            model.embedding.prefetch(next_batch)      # input pipeline: route the next batch behind this step
         return loss
 
     def prepare(batch):
@@ -435,8 +436,9 @@ def run_ours(args, rank: int, local_rank: int, n_gpus: int):
     def e2e_step(i):
         batch, labels, ev = pending.pop()
         main_stream.wait_event(ev)
-        loss = step(batch, labels)                 # every kernel of step i is enqueued ...
-        pending.append(issue_copy(i + 1))          # ... then the host issues the copies of step i + 1 (they overlap step i)
+        nxt = issue_copy(i + 1)                    # the copies of step i + 1 travel while step i computes ...
+        pending.append(nxt)
+        loss = step(batch, labels, nxt[0] if sharded else None, nxt[2])   # ... and its ids are routed behind their copy
         return loss.item()
 
     for i in range(2):

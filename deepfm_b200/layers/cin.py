@@ -30,11 +30,18 @@ class _CINFn(torch.autograd.Function):
         _lib.check(lib.dfm_cin_sizes(F, D, n, sizes, int(mod.split_half), B, info), "dfm_cin_sizes")
         out = torch.empty((B, info[0]), device=x0.device, dtype=torch.float32)
         acts = torch.empty((max(info[1] // 4, 1),), device=x0.device, dtype=torch.float32)
+        prec = mod.precision_code_for(B)
         _lib.check(lib.dfm_cin_fwd(x0.data_ptr(), B, F, D, n, sizes, int(mod.split_half), _lib.ptr_array(weights),
-                                   _lib.ptr_array(biases), mod.precision_code, out.data_ptr(), acts.data_ptr(),
+                                   _lib.ptr_array(biases), prec, out.data_ptr(), acts.data_ptr(),
                                    _lib.stream_ptr()), "dfm_cin_fwd")
         ctx.mod, ctx.ws_bytes = mod, int(info[2])
+        ctx.prec = prec
         ctx.save_for_backward(x0, acts, *weights)
+        if mod.keep_activations:          # test aid: the post-ReLU activations (B, L_i, D) per layer, i.e. the ReLU decisions
+            mod.last_activations, off = [], 0
+            for L in mod.layer_sizes:
+                mod.last_activations.append(acts[off: off + B * L * D].view(B, L, D))
+                off += B * L * D
         return out
 
     @staticmethod
@@ -51,15 +58,17 @@ class _CINFn(torch.autograd.Function):
         g_b = [torch.empty((w.shape[0],), device=w.device, dtype=torch.float32) for w in weights]
         ws = torch.empty((max(ctx.ws_bytes, 16),), device=x0.device, dtype=torch.uint8)
         _lib.check(lib.dfm_cin_bwd(x0.data_ptr(), g_out.data_ptr(), B, F, D, n, sizes, int(mod.split_half),
-                                   _lib.ptr_array(weights), mod.precision_code, acts.data_ptr(), g_x0.data_ptr(),
+                                   _lib.ptr_array(weights), mod.backward_precision_code(ctx.prec), acts.data_ptr(), g_x0.data_ptr(),
                                    _lib.ptr_array(g_w), _lib.ptr_array(g_b), ws.data_ptr(), ws.numel(),
                                    _lib.stream_ptr()), "dfm_cin_bwd")
         return (None, g_x0, *g_w, *g_b)
 
 
 class CIN(nn.Module):
-    # "fp32": CUDA cores, reference-exact up to summation order.  "tf32": forward GEMMs on tcgen05 tensor
-    # cores (TF32 inputs, FP32 accumulate; ~1e-3 relative); the backward stays fp32.
+    # "fp32": CUDA cores, reference-exact up to summation order.  "tf32": forward AND backward contractions on the
+    # tcgen05 tensor cores (TF32 inputs, FP32 accumulate: 2e-3 forward, 3e-3 gradients on shared ReLU decisions).
+    # "auto" (default): tf32 when the contraction is big enough to be tensor-bound (num_fields * widest layer >= 1024
+    # and at least 4096 GEMM rows), fp32 -- the reference's arithmetic -- otherwise (ML-100K-sized models, tests).
     PRECISIONS = {"fp32": 0, "tf32": 1}
 
     def __init__(self, num_fields: int, embed_dim: int, layer_sizes: Optional[List[int]] = None,
@@ -87,11 +96,24 @@ class CIN(nn.Module):
                 self.next_sizes.append(size)
                 maps = size
         self.output_dim = sum(self.direct_sizes)
-        self.precision = "fp32"
+        self.precision = "auto"
+        self.keep_activations = False
+        self.last_activations = None
+
+    def precision_code_for(self, batch: int) -> int:
+        if self.precision == "auto":
+            big = self.num_fields * max(self.layer_sizes) >= 1024 and batch * self.embed_dim >= 4096
+            return 1 if big else 0
+        return self.PRECISIONS[self.precision]
+
+    def backward_precision_code(self, forward_code: int) -> int:
+        """The precision is read again at backward time (tests back-propagate one graph at both precisions);
+        "auto" follows what the forward chose."""
+        return forward_code if self.precision == "auto" else self.PRECISIONS[self.precision]
 
     @property
     def precision_code(self) -> int:
-        return self.PRECISIONS[self.precision]
+        return self.PRECISIONS.get(self.precision, 0)
 
     def forward(self, field_embeddings: torch.Tensor) -> torch.Tensor:
         _lib.require_cuda(field_embeddings, "field_embeddings")

@@ -791,22 +791,40 @@ class ShardedFeatureEmbedding(IndexStatusMixin, nn.Module):
         return table_grads
 
     # -- input pipeline hook ------------------------------------------------------------------
-    def prefetch(self, batch) -> None:
-        """Route a FUTURE batch now (routing depends on the ids only, not on the weights): the routing
-        kernels and the count exchange are enqueued behind the current step, the W x W counts travel to
-        pinned host memory asynchronously, and the forward of that batch starts without a host sync.
+    def prefetch(self, batch, ready_event=None) -> None:
+        """Route a FUTURE batch now (routing depends on the ids only, not on the weights).  The routing kernels, the
+        count exchange and the copy of the W x W counts to pinned host memory run on the module's side stream, so
+        calling this at the START of a step (for the next batch) hides all of it -- including the host's wait for the
+        counts -- under the current step; the forward of that batch then starts without a host sync.
         Every rank must call this at the same point of its step (it contains a collective)."""
         inputs = self._prepare(batch)
-        route = self.route(inputs)
-        pending = self.comm.exchange_counts_async(route.counts)
-        self._prefetched = (tuple(t.data_ptr() for t in inputs), inputs, route, pending)
+        dev = inputs[0].device
+        cur = torch.cuda.current_stream(dev)
+        side = self._side_stream(dev)
+        side.wait_stream(cur)                                  # the batch is ready on the caller's stream ...
+        if ready_event is not None:
+            side.wait_event(ready_event)                       # ... or when this event (e.g. its host -> device copy) fires
+        with torch.cuda.stream(side):
+            route = self.route(inputs)
+            pending = self.comm.exchange_counts_async(route.counts)
+            ev = torch.cuda.Event()
+            ev.record(side)
+        for t in inputs:
+            t.record_stream(side)
+        self._prefetched = (tuple(t.data_ptr() for t in inputs), inputs, route, pending, ev)
 
     def _take_prefetch(self, inputs):
         pref = getattr(self, "_prefetched", None)
         if pref is None or pref[0] != tuple(t.data_ptr() for t in inputs):
             return None
         self._prefetched = None
-        return pref[2], pref[3]
+        cur = torch.cuda.current_stream(inputs[0].device)
+        cur.wait_event(pref[4])                                 # the routing tensors were produced on the side stream
+        route = pref[2]
+        for t in (route.send_keys, route.counts, route.pos, route.skeys, route.spay, route.uidx):
+            if t is not None:
+                t.record_stream(cur)
+        return route, pref[3]
 
     # -- module API ---------------------------------------------------------------------------
     def _prepare(self, batch):
@@ -873,11 +891,12 @@ class DenseGradReducer:
 
     @staticmethod
     def _scatter(flat, params, world):
+        """The averaged bucket becomes the parameters' gradients: views, no per-parameter copies."""
         flat.div_(world)
         off = 0
         for p in params:
             n = p.grad.numel()
-            p.grad.copy_(flat[off:off + n].view_as(p.grad))
+            p.grad = flat[off:off + n].view_as(p.grad)
             off += n
 
     def finish(self) -> None:

@@ -263,10 +263,13 @@ def cin_plan(num_fields: int, layer_sizes: Sequence[int], split_half: bool):
 
 
 def cin_forward(x0: np.ndarray, weights: List[np.ndarray], biases: List[np.ndarray],
-                split_half: bool, keep: bool = False):
+                split_half: bool, keep: bool = False, masks: Optional[List[np.ndarray]] = None):
     """CIN.forward (cin.py:66-105).  weights[i]: (L_i, K_i) (Conv1d weight squeezed), K index = h*F + f.
 
     Split is ``[direct first, next second]`` along channels (cin.py:93-96).
+    masks (test aid): per layer a boolean (B, L_i, D) array that REPLACES the ReLU decision ``pre > 0`` -- the
+    decisions a reduced-precision implementation took -- so that its gradients can be compared entry by entry
+    (a pre-activation within rounding distance of zero may legitimately land on either side).
     """
     B, F, D = x0.shape
     n = len(weights)
@@ -277,7 +280,7 @@ def cin_forward(x0: np.ndarray, weights: List[np.ndarray], biases: List[np.ndarr
         H = hidden.shape[1]
         z = (hidden[:, :, None, :] * x0[:, None, :, :]).reshape(B, H * F, D)     # cin.py:84-87
         pre = np.einsum("lk,bkd->bld", weights[i], z) + biases[i][None, :, None]  # conv k=1
-        act = np.maximum(pre, 0)                                                  # cin.py:91
+        act = np.maximum(pre, 0) if masks is None else pre * masks[i]              # cin.py:91
         if keep:
             saved.append((hidden, act))
         if split_half and i < n - 1:
@@ -307,15 +310,15 @@ def cin_relu_margin(x0, weights, biases, split_half) -> float:
     return margin
 
 
-def cin_backward(x0, weights, biases, split_half, g_out):
+def cin_backward(x0, weights, biases, split_half, g_out, masks: Optional[List[np.ndarray]] = None):
     """Gradients of CIN.forward w.r.t. x0, every conv weight and bias.
 
-    g_out: (B, output_dim).  Z is recomputed, never stored.
+    g_out: (B, output_dim).  Z is recomputed, never stored.  masks: see cin_forward.
     """
     B, F, D = x0.shape
     n = len(weights)
     direct, nxt, _ = cin_plan(F, [w.shape[0] for w in weights], split_half)
-    _, saved = cin_forward(x0, weights, biases, split_half, keep=True)
+    _, saved = cin_forward(x0, weights, biases, split_half, keep=True, masks=masks)
     gx0 = np.zeros_like(x0)
     gW = [None] * n
     gb = [None] * n
@@ -333,7 +336,7 @@ def cin_backward(x0, weights, biases, split_half, g_out):
             g_act += gd
             if g_hidden_next is not None:
                 g_act += g_hidden_next
-        g_pre = g_act * (act > 0)
+        g_pre = g_act * ((act > 0) if masks is None else masks[i])
         H = hidden.shape[1]
         z = (hidden[:, :, None, :] * x0[:, None, :, :]).reshape(B, H * F, D)
         gW[i] = np.einsum("bld,bkd->lk", g_pre, z)

@@ -195,3 +195,31 @@ def test_cin_tcgen05_backward_matches_fp32_backward_on_same_activations(B, F, D,
     for i in range(len(sizes)):
         assert_close_rel(grads["tf32"][1][i].cpu(), grads["fp32"][1][i].cpu(), 3e-3, f"gW{i}")
         assert_close_rel(grads["tf32"][2][i].cpu(), grads["fp32"][2][i].cpu(), 3e-3, f"gb{i}")
+
+
+@pytest.mark.parametrize("B,F,D,sizes", [(130, 16, 16, [128, 128, 64]), (70, 39, 64, [128, 128])])
+def test_cin_tcgen05_backward_vs_oracle_on_the_kernels_own_relu_decisions(B, F, D, sizes):
+    """the TF32 tensor-core backward against the fp64 ORACLE (not the repo's fp32 kernel), entry
+    by entry.  The only legitimate difference between a TF32 forward and the oracle is which side of zero a
+    pre-activation within rounding distance of it lands on, so the oracle is evaluated with the ReLU decisions the
+    kernel took (its post-ReLU activations > 0); what is left is TF32 rounding: 3e-3 per-tensor max-norm relative."""
+    rng = np.random.default_rng(B + F)
+    torch.manual_seed(B + F)
+    cin = CIN(F, D, sizes, True).cuda()
+    cin.precision = "tf32"
+    cin.keep_activations = True
+    x = (rng.standard_normal((B, F, D)) * 0.5).astype(np.float32)
+    W = [c.weight.detach().cpu().numpy()[:, :, 0].astype(np.float64) for c in cin.conv_layers]
+    b = [c.bias.detach().cpu().numpy().astype(np.float64) for c in cin.conv_layers]
+    xt = torch.from_numpy(x).cuda().requires_grad_(True)
+    out = cin(xt)
+    masks = [a.detach().cpu().numpy() > 0 for a in cin.last_activations]
+    g = rng.standard_normal(tuple(out.shape)).astype(np.float32)
+    out.backward(torch.from_numpy(g).cuda())
+    want_out = O.cin_forward(x.astype(np.float64), W, b, True, masks=masks)
+    assert_close_rel(out.detach().cpu(), want_out, 2e-3, "cin tf32 out (shared ReLU decisions)")
+    gx, gW, gb = O.cin_backward(x.astype(np.float64), W, b, True, g.astype(np.float64), masks=masks)
+    assert_close_rel(xt.grad.cpu(), gx, 3e-3, "gx")
+    for i, c in enumerate(cin.conv_layers):
+        assert_close_rel(c.weight.grad.cpu().numpy()[:, :, 0], gW[i], 3e-3, f"gW{i}")
+        assert_close_rel(c.bias.grad.cpu(), gb[i], 3e-3, f"gb{i}")
