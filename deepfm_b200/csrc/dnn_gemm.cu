@@ -49,8 +49,15 @@ struct Args {
     int mask_hi;                         // 1: write x_hi back over the raw tile (0, default: kind::tf32 ignores the low 13
                                          // mantissa bits of its operands -- measured: identical results -- so raw IS hi)
     int b_lo_tma;                        // 1: B_lo was precomputed in global memory (weights) and arrives by TMA (mapBlo)
+    int ts_all;                          // 1: A_hi goes to tensor memory too, all three products run in the TS form (the
+                                         // tensor core then reads only B tiles from shared memory: 48 KB instead of 80 KB
+                                         // per k-block -- shared-memory bandwidth, not the tensor pipe, bounds this kernel)
+    int tma_store;                       // 1: the epilogue stages 32 x 32 boxes in shared memory and stores them by TMA
+                                         // (coalesced 128-byte rows; a thread-per-row float4 store touches 32 half-written
+                                         // sectors per instruction and made the LSU the bound of every small-K product)
     uint32_t tmem_cols;
 };
+constexpr int EPI_BYTES = 4 * 2 * 4096; // 4 promoter warps x 2 buffers x (32 rows x 128 B)
 
 // MN-major 32-bit operand: cute::UMMA::LayoutType::SWIZZLE_128B_BASE32B (canonical layout ((8,n),(4,k)):((1,LBO),(8,SBO))
 // in 16-byte units): 32 MN elements are contiguous (128 B), 4 k-rows of 128 B form one 512-byte swizzle atom (32-byte
@@ -70,13 +77,14 @@ __device__ __forceinline__ float tf32_hi(float x) { return __uint_as_float(__flo
 
 __global__ void __launch_bounds__(THREADS, 1)
 gemm3_kernel(const __grid_constant__ Args a, const __grid_constant__ CUtensorMap mapA, const __grid_constant__ CUtensorMap mapB,
-             const __grid_constant__ CUtensorMap mapBlo) {
+             const __grid_constant__ CUtensorMap mapBlo, const __grid_constant__ CUtensorMap mapD) {
     using namespace tc;
     extern __shared__ unsigned char smem_raw[];
     unsigned char* smem = smem_raw + ((1024u - (smem_u32(smem_raw) & 1023u)) & 1023u);
     const int b_bytes = a.tn * 128;
     const int stage_bytes = A_BYTES + 2 * b_bytes;          // [A raw -> hi][B raw -> hi][B lo]
-    uint64_t* bars = reinterpret_cast<uint64_t*>(smem + (size_t)a.nstage * stage_bytes);
+    unsigned char* epi = smem + (size_t)a.nstage * stage_bytes;                    // 1024-byte aligned (stages are multiples of 4 KB)
+    uint64_t* bars = reinterpret_cast<uint64_t*>(epi + (a.tma_store ? EPI_BYTES : 0));
     uint64_t* full_raw = bars;                 // TMA landed
     uint64_t* full_split = bars + MAXST;       // hi / lo tiles ready
     uint64_t* empty = bars + 2 * MAXST;        // MMAs of the stage retired
@@ -97,7 +105,8 @@ gemm3_kernel(const __grid_constant__ Args a, const __grid_constant__ CUtensorMap
     __syncthreads();
     tc_fence_after();
     const uint32_t tmem_base = *tmem_slot;
-    const uint32_t alo_col0 = (uint32_t)(2 * a.tn);          // TMEM columns of the A_lo ring (32 per stage)
+    const uint32_t alo_col0 = (uint32_t)(2 * a.tn);          // TMEM columns of the A ring: per stage [A_lo 32][A_hi 32 if ts_all]
+    const uint32_t a_cols = a.ts_all ? 64u : 32u;
     const long long n_units = (long long)a.n_mt * a.n_nt * a.n_split;
 
     auto unit_of = [&](long long u, int& mt, int& nt, int& sp) {
@@ -172,12 +181,22 @@ gemm3_kernel(const __grid_constant__ Args a, const __grid_constant__ CUtensorMap
                     const uint64_t da = a.a_mn ? make_desc_mn(sa) : make_desc(sa);
                     const uint64_t db = a.b_mn ? make_desc_mn(sa + A_BYTES) : make_desc(sa + A_BYTES);
                     const uint64_t dbl = a.b_mn ? make_desc_mn(sa + A_BYTES + b_bytes) : make_desc(sa + A_BYTES + b_bytes);
-                    const uint32_t talo = tmem_base + alo_col0 + s * 32;
+                    const uint32_t talo = tmem_base + alo_col0 + s * a_cols;
+                    if (a.ts_all) {
+                        const uint32_t tahi = talo + 32;
 #pragma unroll
-                    for (int k = 0; k < KB / 8; ++k) {
-                        umma_tf32(tacc, da + adv_a * k, db + adv_b * k, idesc_ss, ((kb % CH) | k) ? 1u : 0u);   // hi * hi
-                        umma_tf32(tacc, da + adv_a * k, dbl + adv_b * k, idesc_ss, 1u);                         // hi * lo
-                        umma_tf32_ts(tacc, talo + k * 8, db + adv_b * k, idesc_ts, 1u);                         // lo * hi
+                        for (int k = 0; k < KB / 8; ++k) {
+                            umma_tf32_ts(tacc, tahi + k * 8, db + adv_b * k, idesc_ts, ((kb % CH) | k) ? 1u : 0u);  // hi * hi
+                            umma_tf32_ts(tacc, tahi + k * 8, dbl + adv_b * k, idesc_ts, 1u);                        // hi * lo
+                            umma_tf32_ts(tacc, talo + k * 8, db + adv_b * k, idesc_ts, 1u);                         // lo * hi
+                        }
+                    } else {
+#pragma unroll
+                        for (int k = 0; k < KB / 8; ++k) {
+                            umma_tf32(tacc, da + adv_a * k, db + adv_b * k, idesc_ss, ((kb % CH) | k) ? 1u : 0u);   // hi * hi
+                            umma_tf32(tacc, da + adv_a * k, dbl + adv_b * k, idesc_ss, 1u);                         // hi * lo
+                            umma_tf32_ts(tacc, talo + k * 8, db + adv_b * k, idesc_ts, 1u);                         // lo * hi
+                        }
                     }
                     umma_commit(empty + s);
                     if (++s == (uint32_t)a.nstage) { s = 0; ph ^= 1u; }
@@ -199,7 +218,7 @@ gemm3_kernel(const __grid_constant__ Args a, const __grid_constant__ CUtensorMap
             for (int kb = 0; kb < nkb; ++kb) {
                 mbar_wait(full_raw + s, ph);
                 unsigned char* sa = smem + (size_t)s * stage_bytes;
-                float lo[32];
+                float lo[32], hi[32];                    // hi = the raw value: kind::tf32 ignores the low 13 mantissa bits
                 if (!a.a_mn) {                           // row r: 8 chunks of 4 k, chunk c at ((c ^ (r & 7)) << 4)
                     unsigned char* rowp = sa + r * 128;
 #pragma unroll
@@ -208,6 +227,7 @@ gemm3_kernel(const __grid_constant__ Args a, const __grid_constant__ CUtensorMap
                         const float4 v = *p;
                         const float4 h = make_float4(tf32_hi(v.x), tf32_hi(v.y), tf32_hi(v.z), tf32_hi(v.w));
                         if (a.mask_hi) *p = h;
+                        hi[4 * c] = v.x; hi[4 * c + 1] = v.y; hi[4 * c + 2] = v.z; hi[4 * c + 3] = v.w;
                         lo[4 * c] = v.x - h.x; lo[4 * c + 1] = v.y - h.y; lo[4 * c + 2] = v.z - h.z; lo[4 * c + 3] = v.w - h.w;
                     }
                 } else {                                 // element (k, mn = r): box r / 32, row k, 32-byte chunk ((r % 32) / 8) ^ (k & 3)
@@ -219,10 +239,12 @@ gemm3_kernel(const __grid_constant__ Args a, const __grid_constant__ CUtensorMap
                         const float v = *p;
                         const float h = tf32_hi(v);
                         if (a.mask_hi) *p = h;
+                        hi[k] = v;
                         lo[k] = v - h;
                     }
                 }
-                tmem_st32(tmem_base + ((uint32_t)(q * 32) << 16) + alo_col0 + s * 32, lo);
+                tmem_st32(tmem_base + ((uint32_t)(q * 32) << 16) + alo_col0 + s * a_cols, lo);
+                if (a.ts_all) tmem_st32(tmem_base + ((uint32_t)(q * 32) << 16) + alo_col0 + s * a_cols + 32, hi);
                 float4* bh = reinterpret_cast<float4*>(sa + A_BYTES);
                 float4* bl = reinterpret_cast<float4*>(sa + A_BYTES + b_bytes);
                 const int nchunk = a.b_lo_tma ? 0 : (b_bytes >> 4);
@@ -244,6 +266,7 @@ gemm3_kernel(const __grid_constant__ Args a, const __grid_constant__ CUtensorMap
         const int q = warp & 3;
         const int r = q * 32 + lane;
         long long it = 0;
+        uint32_t n_stores = 0;                                            // TMA stores issued by this warp (buffer = parity)
         const bool vec_ok = (a.ldd & 3) == 0 && (reinterpret_cast<uintptr_t>(a.D) & 15u) == 0 && (a.split_stride & 3) == 0;
         for (long long u = blockIdx.x; u < n_units; u += gridDim.x) {
             int mt, nt, sp;
@@ -273,6 +296,32 @@ gemm3_kernel(const __grid_constant__ Args a, const __grid_constant__ CUtensorMap
                 if (lane == 0) mbar_arrive(acc_empty + acc);
             }
             const long long row = (long long)mt * TM + r;
+            if (a.tma_store) {
+                // each warp owns rows [q*32, q*32+32) of the tile: per 32-column chunk, lane = row writes its 128 bytes into
+                // a 128-byte-swizzled 4 KB box (16-byte chunk index ^ (row & 7): conflict-free), one lane stores the box by TMA
+                unsigned char* wbuf = epi + q * 8192;
+#pragma unroll
+                for (int c = 0; c < TN_MAX / 32; ++c) {
+                    const long long col0 = (long long)nt * a.tn + c * 32;
+                    if (c * 32 < a.tn && col0 < a.N && (long long)mt * TM + q * 32 < a.M) {      // warp-uniform
+                        if (a.bias) {
+#pragma unroll
+                            for (int i = 0; i < 32; ++i) if (col0 + i < a.N) macc[c * 32 + i] += __ldg(a.bias + col0 + i);
+                        }
+                        unsigned char* buf = wbuf + (n_stores++ & 1u) * 4096;
+                        if (lane == 0) tma_store_wait_read<1>();       // the store that last read this buffer (two groups ago)
+                        __syncwarp();
+#pragma unroll
+                        for (int i = 0; i < 8; ++i)
+                            *reinterpret_cast<float4*>(buf + lane * 128 + ((i ^ (lane & 7)) << 4)) =
+                                make_float4(macc[c * 32 + 4 * i], macc[c * 32 + 4 * i + 1], macc[c * 32 + 4 * i + 2], macc[c * 32 + 4 * i + 3]);
+                        fence_proxy_async();
+                        __syncwarp();
+                        if (lane == 0) tma_store_3d(&mapD, buf, (int)col0, mt * TM + q * 32, sp);
+                    }
+                }
+                continue;
+            }
             float* out = a.D + (size_t)sp * a.split_stride + (size_t)row * a.ldd;
 #pragma unroll
             for (int c = 0; c < TN_MAX / 32; ++c) {
@@ -295,6 +344,7 @@ gemm3_kernel(const __grid_constant__ Args a, const __grid_constant__ CUtensorMap
             }
         }
     }
+    if (a.tma_store && warp >= 6 && lane == 0) tma_store_wait_all();      // shared memory must outlive the bulk stores
     __syncthreads();
     if (warp == 1) tmem_dealloc(tmem_base, a.tmem_cols);
 }
@@ -319,11 +369,17 @@ splitk_reduce_kernel(const float* __restrict__ partial, int n_split, long long s
 }
 
 struct Plan {
-    int tn, n_mt, n_nt, n_split, nstage;
+    int tn, n_mt, n_nt, n_split, nstage, tma_store;
     long long k_per_split;
     size_t smem, ws_bytes;
     uint32_t tmem_cols;
 };
+
+static int ts_all_enabled() {
+    static int v = -1;
+    if (v < 0) { const char* e = getenv("DFM_G3_TS_ALL"); v = (e && e[0] == '0') ? 0 : 1; }
+    return v;
+}
 
 static int make_plan(int mode, long long M, long long N, long long K, Plan& p) {
     DFM_REQUIRE(mode >= 0 && mode <= 2 && M > 0 && N > 0 && K > 0, DFM_ERR_INVALID, "dfm_gemm3: bad mode / shape");
@@ -337,22 +393,38 @@ static int make_plan(int mode, long long M, long long N, long long K, Plan& p) {
     p.n_mt = (int)ceil_div(M, TM);
     p.n_split = 1;
     if (mode == 2) {
-        const long long base = (long long)p.n_mt * p.n_nt;
-        long long want = ceil_div(2LL * sm_count(), base);
+        // split K so that the persistent grid runs whole waves: units = tiles * splits; a unit count just above a
+        // multiple of the SM count leaves most SMs idle for a full unit (40 tiles x 8 splits = 2.16 waves -> 3 rounds)
+        const long long base = (long long)p.n_mt * p.n_nt, sms = sm_count();
+        long long want = ceil_div(2LL * sms, base);
         const long long max_split = ceil_div(K, 8LL * KB);            // at least 8 k-blocks per split
         if (want > max_split) want = max_split;
         if (want < 1) want = 1;
-        p.n_split = (int)want;
+        long long best = want;
+        double best_eff = 0.0;
+        for (long long s = (want + 1) / 2; s <= max_split && s <= 3 * want; ++s) {
+            const long long units = base * s;
+            const double eff = (double)units / (double)(ceil_div(units, sms) * sms);
+            if (eff > best_eff + 1e-9) { best_eff = eff; best = s; }
+            if (eff >= 0.97) break;                                    // the smallest split count that fills its waves
+        }
+        p.n_split = (int)best;
     }
     p.k_per_split = ceil_div(ceil_div(K, p.n_split), KB) * KB;
     p.n_split = (int)ceil_div(K, p.k_per_split);
     const int stage_bytes = A_BYTES + 2 * p.tn * 128;
-    const size_t fixed = (3 * MAXST + 4) * 8 + 16 + 1024;
+    const size_t fixed0 = (3 * MAXST + 4) * 8 + 16 + 1024;
     p.nstage = MAXST;
-    while (p.nstage > 2 && ((size_t)p.nstage * stage_bytes + fixed > 227 * 1024 || 2 * p.tn + p.nstage * 32 > 512)) --p.nstage;
+    const int a_cols = ts_all_enabled() ? 64 : 32;
+    {   // TMA-store epilogue: 16-byte global strides (N % 4 == 0); DFM_G3_TMA_STORE=0 keeps the per-thread stores
+        const char* e = getenv("DFM_G3_TMA_STORE");
+        p.tma_store = (N % 4 == 0 && !(e && e[0] == '0')) ? 1 : 0;
+    }
+    const size_t fixed = fixed0 + (p.tma_store ? EPI_BYTES : 0);
+    while (p.nstage > 2 && ((size_t)p.nstage * stage_bytes + fixed > 227 * 1024 || 2 * p.tn + p.nstage * a_cols > 512)) --p.nstage;
     p.smem = (size_t)p.nstage * stage_bytes + fixed;
     uint32_t cols = 32;
-    while (cols < (uint32_t)(2 * p.tn + p.nstage * 32)) cols <<= 1;
+    while (cols < (uint32_t)(2 * p.tn + p.nstage * a_cols)) cols <<= 1;
     p.tmem_cols = cols;
     p.ws_bytes = p.n_split > 1 ? (size_t)p.n_split * M * N * 4 : 0;
     if (mode != 2) p.ws_bytes += align_up((size_t)N * K * 4, 256);      // B_lo of the weight operand
@@ -392,6 +464,8 @@ int dfm_gemm3(int mode, const float* A, const float* B, float* D, const float* b
     a.a_mn = mode == 2 ? 1 : 0; a.b_mn = mode == 0 ? 0 : 1;
     a.mask_hi = getenv("DFM_G3_MASK") ? 1 : 0;
     a.b_lo_tma = (mode != 2 && !getenv("DFM_G3_SPLIT_B_IN_KERNEL")) ? 1 : 0;
+    a.ts_all = ts_all_enabled();
+    a.tma_store = p.tma_store;
     a.bias = bias;
     if (p.n_split > 1) { a.D = static_cast<float*>(workspace); a.ldd = N; a.split_stride = M * N; }
     else { a.D = D; a.ldd = N; a.split_stride = 0; }
@@ -411,10 +485,16 @@ int dfm_gemm3(int mode, const float* A, const float* B, float* D, const float* b
         rc = a.b_mn ? tc::make_tmap_2d(&mapBlo, blo, K, N, 32, true) : tc::make_tmap_2d(&mapBlo, blo, N, K, p.tn);
         if (rc) return rc;
     }
+    CUtensorMap mapD = mapA;
+    if (a.tma_store) {
+        DFM_REQUIRE((reinterpret_cast<uintptr_t>(a.D) & 15u) == 0, DFM_ERR_UNSUPPORTED, "dfm_gemm3: output must be 16-byte aligned");
+        rc = tc::make_tmap_out_3d(&mapD, a.D, p.n_split, M, N, a.ldd, a.split_stride);
+        if (rc) return rc;
+    }
     DFM_CHECK_CUDA(cudaFuncSetAttribute(gemm3_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)p.smem));
     long long grid = (long long)p.n_mt * p.n_nt * p.n_split;
     if (grid > sm_count()) grid = sm_count();
-    gemm3_kernel<<<(unsigned)grid, THREADS, p.smem, st>>>(a, mapA, mapB, mapBlo);
+    gemm3_kernel<<<(unsigned)grid, THREADS, p.smem, st>>>(a, mapA, mapB, mapBlo, mapD);
     if (p.n_split > 1) {
         const long long n = M * N;
         long long blocks = ceil_div(n, 256);

@@ -136,5 +136,42 @@ inline int make_tmap_2d(CUtensorMap* map, const float* base, long long rows, lon
     return DFM_OK;
 }
 
+// 3-D fp32 tensor map of an output (cols, rows, planes) with box = 32 floats x 32 rows x 1 plane, SWIZZLE_128B: the
+// epilogue's TMA store (rows / columns beyond the tensor are clipped by the hardware)
+inline int make_tmap_out_3d(CUtensorMap* map, float* base, long long planes, long long rows, long long cols,
+                            long long row_stride_floats, long long plane_stride_floats) {
+    static EncodeTiledFn encode = nullptr;
+    if (!encode) {
+        void* fn = nullptr;
+        cudaDriverEntryPointQueryResult qres;
+        if (cudaGetDriverEntryPoint("cuTensorMapEncodeTiled", &fn, cudaEnableDefault, &qres) != cudaSuccess || !fn ||
+            qres != cudaDriverEntryPointSuccess) {
+            set_error("cuTensorMapEncodeTiled is not available");
+            return DFM_ERR_CUDA;
+        }
+        encode = reinterpret_cast<EncodeTiledFn>(fn);
+    }
+    const cuuint64_t dims[3] = {(cuuint64_t)cols, (cuuint64_t)rows, (cuuint64_t)(planes > 0 ? planes : 1)};
+    const cuuint64_t strides[2] = {(cuuint64_t)row_stride_floats * 4, (cuuint64_t)(plane_stride_floats > 0 ? plane_stride_floats : rows * row_stride_floats) * 4};
+    const cuuint32_t box[3] = {32u, 32u, 1u};
+    const cuuint32_t estr[3] = {1, 1, 1};
+    CUresult cr = encode(map, CU_TENSOR_MAP_DATA_TYPE_FLOAT32, 3, base, dims, strides, box, estr,
+                         CU_TENSOR_MAP_INTERLEAVE_NONE, CU_TENSOR_MAP_SWIZZLE_128B, CU_TENSOR_MAP_L2_PROMOTION_NONE,
+                         CU_TENSOR_MAP_FLOAT_OOB_FILL_NONE);
+    if (cr != CUDA_SUCCESS) { set_error("cuTensorMapEncodeTiled (output) failed (%d)", (int)cr); return DFM_ERR_CUDA; }
+    return DFM_OK;
+}
+
+// TMA store of one 32 x 32 fp32 box (128-byte-swizzled in shared memory) -> global, bulk-group completion
+__device__ __forceinline__ void tma_store_3d(const CUtensorMap* map, const void* src, int x, int y, int z) {
+    asm volatile(
+        "cp.async.bulk.tensor.3d.global.shared::cta.bulk_group [%0, {%1, %2, %3}], [%4];"
+        ::"l"(reinterpret_cast<uint64_t>(map)), "r"(x), "r"(y), "r"(z), "r"(smem_u32(src)) : "memory");
+    asm volatile("cp.async.bulk.commit_group;" ::: "memory");
+}
+template <int N>
+__device__ __forceinline__ void tma_store_wait_read() { asm volatile("cp.async.bulk.wait_group.read %0;" ::"n"(N) : "memory"); }
+__device__ __forceinline__ void tma_store_wait_all() { asm volatile("cp.async.bulk.wait_group 0;" ::: "memory"); }
+
 }  // namespace tc
 }  // namespace dfm

@@ -1,0 +1,10 @@
+for v in "DFM_G3_TS_ALL=0" "DFM_G3_TS_ALL=1" "DFM_G3_TS_ALL=1 DFM_G3_SPLIT_B_IN_KERNEL=1" "DFM_G3_TS_ALL=0 DFM_G3_SPLIT_B_IN_KERNEL=1"; do
+  env $v timeout 120 python scripts/perf_gemm3.py 2>&1 | grep -v Warning
+done > gpurun_out/r2_g3_variants.log 2>&1
+timeout 300 python -m pytest tests/test_dnn_gpu.py -q -m gpu 2>&1 | tail -3 >> gpurun_out/r2_g3_variants.log
+timeout 300 python bench.py --steps 10 --warmup 3 --no-cpu-baseline > gpurun_out/r2_b9.json 2> gpurun_out/r2_b9.err
+cat gpurun_out/r2_g3_variants.log; cut -c1-300 gpurun_out/r2_b9.json; python - <<'PY'
+import json
+d=json.loads(open("gpurun_out/r2_b9.json").read().strip().splitlines()[-1])
+print(d["ms_per_step"], d["e2e"], d.get("roofline_bwd",{}).get("ms"), d.get("roofline_path",{}).get("frac"))
+PY

@@ -156,7 +156,10 @@ def test_deepfm_on_criteo_shape_vs_reference_port():
 @pytest.mark.parametrize("name,cin", [("deepfm", None), ("xdeepfm", [64]), ("xdeepfm", [128, 128, 64]), ("attention_deepfm", None)])
 def test_models_on_ml100k_schema_vs_reference_port(name, cin):
     """BASELINE configs 1-3: the ML-100K schema (16 fields, 14 of them projected to fm_embed_dim 16, one mean bag)."""
-    _whole_model_vs_port(name, W.ml100k_schema(), _bench_cfg(16, cin), B=4096, seed=7)
+    # CIN "auto" would pick the TF32 tensor-core path at this batch (2e-3 tolerance, pinned in test_cin_attention_gpu);
+    # the whole-model fp32 bound is checked on the reference's own arithmetic.
+    _whole_model_vs_port(name, W.ml100k_schema(), _bench_cfg(16, cin), B=4096, seed=7,
+                         cin_precision="fp32" if cin is not None else None)
 
 
 def test_xdeepfm_on_multihot_criteo_schema_vs_reference_port():

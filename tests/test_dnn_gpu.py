@@ -16,7 +16,8 @@ from tests.helpers import assert_close_rel
 pytestmark = pytest.mark.gpu
 
 
-@pytest.mark.parametrize("M,N,K", [(128, 64, 32), (300, 100, 36), (4096, 256, 2496), (1000, 2496, 256), (777, 64, 128)])
+@pytest.mark.parametrize("M,N,K", [(128, 64, 32), (300, 100, 36), (4096, 256, 2496), (1000, 2496, 256), (777, 64, 128),
+                                   (65, 32, 64), (33, 8, 256)])
 def test_gemm3_nt_nn_tn_vs_fp64(M, N, K):
     torch.manual_seed(M + N + K)
     x = torch.randn(M, K, device="cuda")

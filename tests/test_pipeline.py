@@ -88,3 +88,23 @@ def test_loader_feeds_the_embedding_and_presorts_on_gpu(resident):
             assert all(torch.equal(a, b) for a, b in zip(per_a[k], v)), k
         lo = hi
     assert lo == n
+
+
+def test_packed_batch_layout_round_trips_every_column():
+    """One contiguous buffer per batch (a single host -> device copy): the column views keep the reference's dtypes
+    and shapes (dataset.py:28-38) and start on 256-byte boundaries."""
+    from deepfm_b200.pipeline import PackedBatchLayout
+    from deepfm_b200 import workloads as W
+    schema = W.ml100k_schema()
+    batch = W.synthetic_batch(schema, 37, seed=3)
+    labels = W.synthetic_labels(37, seed=3)
+    layout = PackedBatchLayout(batch, labels)
+    buf = layout.pack(batch, labels, pin=False)
+    assert buf.dtype == torch.uint8 and buf.numel() == layout.nbytes
+    assert all(off % 256 == 0 for _, _, _, off, _ in layout.columns)
+    feats, lab = layout.views(buf.clone())
+    assert list(feats) == list(batch)
+    for k, v in batch.items():
+        assert feats[k].dtype == v.dtype and feats[k].shape == v.shape and torch.equal(feats[k], v)
+    assert torch.equal(lab, labels)
+    assert layout.payload_bytes == sum(v.numel() * v.element_size() for v in batch.values()) + labels.numel() * 4
