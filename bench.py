@@ -42,8 +42,8 @@ BATCH = 65536
 EMBED_DIM = 64
 WORKLOAD = "deepfm_criteo_13dense_26sparse_d64_b65536_per_gpu"
 K1_BYTES_PER_SAMPLE = 26 * (8 + 4 * EMBED_DIM + 4) + 13 * 4 + 4 * 39 * EMBED_DIM + 8   # 17012
-K1_DRAM_TRAFFIC = 741_201_408          # bytes per launch, ncu --set full (profiles/r1_ncu_full_kernels.csv: 112.9 MB read + 628.3 MB written)
-K1_TRAFFIC_SOURCE = "profiles/r1_ncu_full_kernels.csv (dram__bytes_read+write, one launch)"
+K1_DRAM_TRAFFIC = 746_396_672          # bytes per launch, ncu --set full (profiles/r2_ncu_full_kernels.csv: 116.8 MB read + 629.6 MB written)
+K1_TRAFFIC_SOURCE = "profiles/r2_ncu_full_kernels.csv (dram__bytes_read+write, one launch)"
 CPU_SAMPLE_BATCH = 8192
 CPU_SAMPLE_MAX_VOCAB = 1_000_000
 
@@ -344,7 +344,10 @@ def run_ours(args, rank: int, local_rank: int, n_gpus: int):
         emb_ids = {id(p) for p in emb.parameters()}
         early = [p for p in dense_params if id(p) not in emb_ids]
         late = [p for p in dense_params if id(p) in emb_ids]
-        reducer = DenseGradReducer(early, late, n_gpus)    # allreduce of the DNN grads overlaps the table backward
+        # allreduce of the DNN grads overlaps the table backward (launched by the sharded embedding's backward)
+        reducer = DenseGradReducer(early, late, n_gpus, embedding=emb if sharded else None)
+
+    all_params = list(model.parameters())
 
     def allreduce_dense():
         if reducer is not None:
@@ -354,7 +357,8 @@ def run_ours(args, rank: int, local_rank: int, n_gpus: int):
         if next_batch is not None and sharded:
             # input pipeline: route the NEXT batch on a side stream, under this step
             model.embedding.prefetch(next_batch, ready_event=next_ready)
-        model.zero_grad(set_to_none=True)
+        for p in all_params:                       # == optimizer.zero_grad(set_to_none=True): no module-tree walk per step
+            p.grad = None
         logits = model(batch).squeeze(1)
         loss = bce(logits, labels) + model.get_l2_reg_loss()
         loss.backward()
@@ -402,6 +406,23 @@ def run_ours(args, rank: int, local_rank: int, n_gpus: int):
         prepare(devb[(W_ + i + 1) % n_batches])
         return step(devb[(W_ + i) % n_batches], devy[(W_ + i) % n_batches], devb[(W_ + i + 1) % n_batches])
 
+    if os.environ.get("DFM_BENCH_CPROFILE") and rank == 0:      # development aid: where the HOST time of a step goes
+        import cProfile, pstats
+        pr = cProfile.Profile()
+        barrier()
+        pr.enable()
+        for i in range(10):
+            value_step(i)
+        torch.cuda.synchronize()
+        pr.disable()
+        with open(os.environ["DFM_BENCH_CPROFILE"], "w") as fh:
+            st = pstats.Stats(pr, stream=fh)
+            st.sort_stats("tottime").print_stats(60)
+            st.sort_stats("cumulative").print_stats(80)
+    elif os.environ.get("DFM_BENCH_CPROFILE"):
+        barrier()
+        for i in range(10):
+            value_step(i)
     total_ms = timed(value_step, K_)
     ev = model.embedding.profile_events
     model.embedding.profile_events = None
@@ -476,8 +497,13 @@ def run_ours(args, rank: int, local_rank: int, n_gpus: int):
         if os.environ.get("DFM_BENCH_TRACE"):     # development aid: host + device timeline of two steady-state steps
             step(devb[0], devy[0], devb[1])
             with profile(activities=[ProfilerActivity.CUDA, ProfilerActivity.CPU]) as tprof:
-                step(devb[1], devy[1], devb[2])
-                step(devb[2], devy[2], devb[3])
+                sync_each = bool(os.environ.get("DFM_BENCH_TRACE_E2E"))     # .item() after every step, like the e2e region
+                l1 = step(devb[1], devy[1], devb[2])
+                if sync_each:
+                    l1.item()
+                l2 = step(devb[2], devy[2], devb[3])
+                if sync_each:
+                    l2.item()
                 torch.cuda.synchronize()
             tprof.export_chrome_trace(os.environ["DFM_BENCH_TRACE"])
             step(devb[3], devy[3])

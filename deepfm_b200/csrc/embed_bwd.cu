@@ -1425,6 +1425,34 @@ static int embed_bwd_impl(const dfm_plan* plan, int64_t batch, long long direct_
     a.span_counter = a.long_count + 1;
     const int fill_blocks = 8 * sm_count();
 
+    // The DENSE-field / projection gradients (step 3) read only the upstream gradients and the inputs: they run on an
+    // internal side stream forked HERE and joined at the end, underneath the sort / segmented reduction / stitch kernels
+    // (the stitch kernels are latency-bound and leave the memory system idle; dense_stream is a pure HBM stream).
+    // From the caller's point of view everything is still ordered on `stream`.
+    cudaStream_t st3 = st;
+    cudaEvent_t ev_join = nullptr;
+    if (!direct && batch > 0 && N > 0 && !skip_tables && getenv("DFM_K2_FORK") == nullptr) {
+        static cudaStream_t aux[16] = {};
+        static cudaEvent_t ev_f[16] = {}, ev_j[16] = {};
+        int dev = 0;
+        DFM_CHECK_CUDA(cudaGetDevice(&dev));
+        if (dev >= 0 && dev < 16) {
+            if (!aux[dev]) {
+                DFM_CHECK_CUDA(cudaStreamCreateWithFlags(&aux[dev], cudaStreamNonBlocking));
+                DFM_CHECK_CUDA(cudaEventCreateWithFlags(&ev_f[dev], cudaEventDisableTiming));
+                DFM_CHECK_CUDA(cudaEventCreateWithFlags(&ev_j[dev], cudaEventDisableTiming));
+            }
+            DFM_CHECK_CUDA(cudaEventRecord(ev_f[dev], st));
+            DFM_CHECK_CUDA(cudaStreamWaitEvent(aux[dev], ev_f[dev], 0));
+            st3 = aux[dev];
+            ev_join = ev_j[dev];
+        }
+    }
+    struct Join {      // every exit path re-joins the side stream
+        cudaStream_t main, side; cudaEvent_t ev;
+        ~Join() { if (ev) { cudaEventRecord(ev, side); cudaStreamWaitEvent(main, ev, 0); } }
+    } join{st, st3, ev_join};
+
     // 1. dense mode: every element of every table gradient starts as 2*l2*w (or 0)
     if (mode == DFM_GRAD_DENSE) {
         for (int f = 0; f < plan->n_fields; ++f) {
@@ -1552,15 +1580,15 @@ static int embed_bwd_impl(const dfm_plan* plan, int64_t batch, long long direct_
         if (smem > 48 * 1024)
             DFM_CHECK_CUDA(cudaFuncSetAttribute(pgrads_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
         if (batch > 0 && pg->n_tile > 0)
-            pgrads_kernel<<<dim3(pg->n_slices, pg->n_tile), PG_THREADS, smem, st>>>(*P, a, *pg);
+            pgrads_kernel<<<dim3(pg->n_slices, pg->n_tile), PG_THREADS, smem, st3>>>(*P, a, *pg);
         if (batch > 0 && pg->n_runs > 0) {
             const dim3 grid(pg->n_slices, pg->n_runs);
-            if (V == 4 && g_field) dense_stream_kernel<4, true><<<grid, PG_THREADS, 0, st>>>(*P, a, *pg, stream_lanes);
-            else if (V == 4) dense_stream_kernel<4, false><<<grid, PG_THREADS, 0, st>>>(*P, a, *pg, stream_lanes);
-            else if (g_field) dense_stream_kernel<1, true><<<grid, PG_THREADS, 0, st>>>(*P, a, *pg, stream_lanes);
-            else dense_stream_kernel<1, false><<<grid, PG_THREADS, 0, st>>>(*P, a, *pg, stream_lanes);
+            if (V == 4 && g_field) dense_stream_kernel<4, true><<<grid, PG_THREADS, 0, st3>>>(*P, a, *pg, stream_lanes);
+            else if (V == 4) dense_stream_kernel<4, false><<<grid, PG_THREADS, 0, st3>>>(*P, a, *pg, stream_lanes);
+            else if (g_field) dense_stream_kernel<1, true><<<grid, PG_THREADS, 0, st3>>>(*P, a, *pg, stream_lanes);
+            else dense_stream_kernel<1, false><<<grid, PG_THREADS, 0, st3>>>(*P, a, *pg, stream_lanes);
         }
-        pgrads_finish_kernel<<<dim3((unsigned)ceil_div(max_vals, 32), pg->n_pf), 256, 0, st>>>(*P, *GR, a, *pg);
+        pgrads_finish_kernel<<<dim3((unsigned)ceil_div(max_vals, 32), pg->n_pf), 256, 0, st3>>>(*P, *GR, a, *pg);
         DFM_CHECK_LAUNCH();
     }
     return DFM_OK;

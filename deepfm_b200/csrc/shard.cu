@@ -525,6 +525,30 @@ static int fill_peer(PeerDst& pd, int n_peers, const int64_t* peer_start, float*
     return DFM_OK;
 }
 
+// All-ranks barrier on the stream, through peer-mapped flag words (one array of RT_MAXW_ words per rank, in the same
+// symmetric allocation as the exchange buffers).  Lane r publishes `epoch` in word [rank] of rank r's array (system-scope
+// release: every peer store this stream issued before is visible first), then waits until word [r] of its own array
+// reaches `epoch` (acquire).  Epochs only grow (wrap-safe signed compare), so no reset pass is needed.  A peer that never
+// arrives trips a ~4 s watchdog (trap) instead of hanging the GPU.
+struct PeerFlags { uint32_t* flags[RT_MAXW_]; };
+
+__global__ void peer_barrier_kernel(PeerFlags pf, int world, int rank, uint32_t epoch) {
+    const int r = threadIdx.x;
+    if (r >= world) return;
+    __threadfence_system();
+    asm volatile("st.release.sys.global.u32 [%0], %1;" ::"l"(pf.flags[r] + rank), "r"(epoch) : "memory");
+    const uint32_t* mine = pf.flags[rank] + r;
+    const long long t0 = clock64();
+    for (;;) {
+        uint32_t v;
+        asm volatile("ld.acquire.sys.global.u32 %0, [%1];" : "=r"(v) : "l"(mine) : "memory");
+        if ((int32_t)(v - epoch) >= 0) break;
+        if (clock64() - t0 > 8000000000LL) { printf("dfm peer barrier: rank %d timed out waiting for rank %d (epoch %u, saw %u)\n", rank, r, epoch, v); __trap(); }
+        __nanosleep(64);
+    }
+    __threadfence_system();
+}
+
 extern "C" {
 
 static int shard_gather_impl(const dfm_plan* local_plan, int world, int rank, const int64_t* global_row_base,
@@ -781,6 +805,20 @@ int dfm_shard_gather2(const dfm_plan* local_plan, int world, int rank, int64_t n
     cudaStream_t st = static_cast<cudaStream_t>(stream);
     if (v4) shard_gather2_kernel<4><<<(unsigned)blocks, 256, 0, st>>>(*a, n_keys, local_keys, G, backward_keys, *pd);
     else shard_gather2_kernel<1><<<(unsigned)blocks, 256, 0, st>>>(*a, n_keys, local_keys, G, backward_keys, *pd);
+    DFM_CHECK_LAUNCH();
+    return DFM_OK;
+}
+
+int dfm_peer_barrier(uint32_t* const* peer_flags, int world, int rank, uint32_t epoch, void* stream) {
+    DFM_REQUIRE(peer_flags && world >= 1 && world <= RT_MAXW_ && rank >= 0 && rank < world, DFM_ERR_INVALID,
+                "dfm_peer_barrier: 1..%d ranks", RT_MAXW_);
+    PeerFlags pf;
+    memset(&pf, 0, sizeof(pf));
+    for (int r = 0; r < world; ++r) {
+        DFM_REQUIRE(peer_flags[r], DFM_ERR_INVALID, "dfm_peer_barrier: null flag array of rank %d", r);
+        pf.flags[r] = peer_flags[r];
+    }
+    peer_barrier_kernel<<<1, 32, 0, static_cast<cudaStream_t>(stream)>>>(pf, world, rank, epoch);
     DFM_CHECK_LAUNCH();
     return DFM_OK;
 }

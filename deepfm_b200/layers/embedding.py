@@ -289,8 +289,17 @@ class FeatureEmbedding(IndexStatusMixin, nn.Module):
             except Exception:
                 pass
 
+    def _apply(self, fn, *args, **kwargs):
+        self._ordered_cache = None        # .to() / .cuda() may replace the Parameter objects
+        self._l2_split = None
+        return super()._apply(fn, *args, **kwargs)
+
     def _ordered_params(self) -> List[torch.Tensor]:
-        """Present parameters in kernel order; also records which are tables / their slot 5f+k."""
+        """Present parameters in kernel order; also records which are tables / their slot 5f+k.  Cached: the module
+        tree walk costs ~0.2 ms and the step asks for the list several times."""
+        cached = getattr(self, "_ordered_cache", None)
+        if cached is not None:
+            return cached
         out, is_table, slots = [], [], []
         for f, name in enumerate(self.field_names):
             second, first = self.second_order_embeddings[name], self.first_order_embeddings[name]
@@ -308,6 +317,7 @@ class FeatureEmbedding(IndexStatusMixin, nn.Module):
                 is_table.append(tab)
                 slots.append(5 * f + k)
         self._param_is_table, self._slot_of_param = is_table, slots
+        self._ordered_cache = out
         return out
 
     def _param_ptrs(self, tensors) -> C.Array:

@@ -65,7 +65,11 @@ class TableNormCache:
 
 
 def _split_params(emb):
-    """(tables, small): the id tables (cached) and everything else (reduced every call)."""
+    """(tables, small): the id tables (cached) and everything else (reduced every call).  The split itself is cached on
+    the module (cleared by its ``_apply``, i.e. by ``.to()`` / ``.cuda()``): two module-tree walks per step otherwise."""
+    cached = getattr(emb, "_l2_split", None)
+    if cached is not None:
+        return cached[0], cached[1]
     params = [p for p in emb.parameters()]
     table_ids = set()
     ordered = getattr(emb, "_ordered_params", None)
@@ -74,6 +78,8 @@ def _split_params(emb):
         table_ids = {id(p) for p, is_table in zip(op, emb._param_is_table) if is_table}
     tables = [p for p in params if id(p) in table_ids]
     small = [p for p in params if id(p) not in table_ids]
+    if hasattr(emb, "_ordered_cache"):       # only modules that invalidate the cache in _apply
+        emb._l2_split = (tables, small, params)
     return tables, small
 
 
@@ -141,7 +147,11 @@ class _L2PenaltyFn(torch.autograd.Function):
 
 
 def l2_penalty(emb, lam: float) -> torch.Tensor:
-    params: List[torch.Tensor] = [p.contiguous() for p in emb.parameters()]
+    cached = getattr(emb, "_l2_split", None)
+    if cached is None:
+        _split_params(emb)
+        cached = getattr(emb, "_l2_split", None)
+    params: List[torch.Tensor] = [p.contiguous() for p in (cached[2] if cached is not None else emb.parameters())]
     for p in params:
         _lib.require_cuda(p, "FeatureEmbedding parameter")
     anchor = getattr(emb, "_live_anchor", None)

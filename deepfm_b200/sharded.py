@@ -132,10 +132,19 @@ class TorchDistComm:
     def exchange_counts_async(self, counts: torch.Tensor):
         """Same exchange, but the W x W matrix is copied to pinned host memory without blocking; call
         ``finish_counts`` later (normally the copy finished long before)."""
-        rows = [torch.empty_like(counts) for _ in range(self.world)]
-        self.dist.all_gather(rows, counts.contiguous(), group=self.group)
-        mat = torch.stack(rows)
-        host = torch.empty(mat.shape, dtype=mat.dtype, pin_memory=mat.is_cuda)
+        if counts.is_cuda:
+            mat = torch.empty((self.world, counts.numel()), dtype=counts.dtype, device=counts.device)
+            self.dist.all_gather_into_tensor(mat, counts.contiguous(), group=self.group)
+            ring = self.__dict__.setdefault("_pinned_ring", [])
+            if len(ring) < 4:
+                ring.append(torch.empty(mat.shape, dtype=mat.dtype, pin_memory=True))
+            host = ring[self.__dict__.setdefault("_pinned_i", 0) % len(ring)]
+            self._pinned_i += 1
+        else:
+            rows = [torch.empty_like(counts) for _ in range(self.world)]
+            self.dist.all_gather(rows, counts.contiguous(), group=self.group)
+            mat = torch.stack(rows)
+            host = torch.empty(mat.shape, dtype=mat.dtype)
         host.copy_(mat, non_blocking=True)
         ev = torch.cuda.Event() if mat.is_cuda else None
         if ev is not None:
@@ -176,12 +185,14 @@ class PeerExchange:
         self.dim, self.cap = int(dim), (int(capacity_rows) + 63) // 64 * 64      # every block starts on a 256-byte boundary
         group = comm.group if comm.group is not None else comm.dist.group.WORLD
         n = 4 * self.cap * (self.dim + 4)
-        self.buf, self.hdl = _peer.symmetric_empty(n, device, group)
+        self.buf, self.hdl = _peer.symmetric_empty(n + 64, device, group)     # + 64 words: the barrier's flag array
         self.buf.zero_()                                     # row 0 of both got buffers is the reserved zero row
         self.peer_base = [int(p) for p in self.hdl.buffer_ptrs]
+        self._flag_ptrs = _lib.ptr_array([b + 4 * n for b in self.peer_base])
+        self._epoch = 0
         self.step = 0
         torch.cuda.synchronize(device)
-        self.hdl.barrier(channel=0)
+        self.hdl.barrier(channel=0)                          # setup only: every rank's flags are zero before any epoch
 
     def _offsets(self, kind: int, parity: int):
         """Float offsets of the (vector, scalar) buffers of (kind, parity) inside a rank's allocation."""
@@ -206,8 +217,13 @@ class PeerExchange:
         recv = max(sum(matrix[s][r] for s in range(W)) for r in range(W))
         return sent + 1 <= self.cap and recv <= self.cap
 
-    def barrier(self, channel: int) -> None:
-        self.hdl.barrier(channel=channel)
+    def barrier(self, channel: int = 0) -> None:
+        """All-ranks barrier on the current stream: one 32-thread kernel of our own over peer-mapped flag words
+        (``dfm_peer_barrier``).  torch's ``handle.barrier`` costs ~1 ms of HOST time per call (measured with cProfile
+        at W = 2: 1.9 of the 5.9 ms step), which made the sharded step host-bound."""
+        self._epoch += 1
+        _lib.check(_lib.lib().dfm_peer_barrier(self._flag_ptrs, self.world, self.rank, self._epoch & 0xFFFFFFFF,
+                                               _lib.stream_ptr()), "dfm_peer_barrier")
 
 
 class _ShardedEmbedFn(torch.autograd.Function):
@@ -260,6 +276,9 @@ class _ShardedEmbedFn(torch.autograd.Function):
     def backward(ctx, g_first, g_field, g_flat, g_fm, _g_anchor=None):
         mod: ShardedFeatureEmbedding = ctx.mod
         mod._live_anchor = None
+        cb = mod.__dict__.get("on_backward_start")
+        if cb is not None:        # e.g. DenseGradReducer: every parameter downstream of the embedding has its gradient now
+            cb()
         saved = ctx.saved_tensors
         field, flat, fm_sum, got_vec, got_sc, aux = saved[:6]
         n_f = len(mod.field_names)
@@ -486,7 +505,15 @@ class ShardedFeatureEmbedding(IndexStatusMixin, nn.Module):
                 except Exception:
                     pass
 
+    def _apply(self, fn, *args, **kwargs):
+        self._ordered_cache = None        # .to() / .cuda() may replace the Parameter objects
+        self._l2_split = None
+        return super()._apply(fn, *args, **kwargs)
+
     def _ordered_params(self) -> List[torch.Tensor]:
+        cached = getattr(self, "_ordered_cache", None)
+        if cached is not None:
+            return cached
         out, is_table, slots = [], [], []
         for f, name in enumerate(self.field_names):
             second, first = self.second_order_embeddings[name], self.first_order_embeddings[name]
@@ -499,6 +526,7 @@ class ShardedFeatureEmbedding(IndexStatusMixin, nn.Module):
                 is_table.append(tab)
                 slots.append(5 * f + k)
         self._param_is_table, self._slot_of_param = is_table, slots
+        self._ordered_cache = out
         return out
 
     def _ptrs(self, tensors, override: Optional[Dict[int, torch.Tensor]] = None) -> C.Array:
@@ -727,12 +755,26 @@ class ShardedFeatureEmbedding(IndexStatusMixin, nn.Module):
         dev = flat.device
         b = flat.shape[0]
         dense_grads: Dict[int, torch.Tensor] = {}
-        grads = []
-        for i, (p, tab) in enumerate(zip(params, self._param_is_table)):
-            g = None if tab else torch.empty_like(p)
-            grads.append(g)
-            if g is not None:
-                dense_grads[i] = g
+        # all data-parallel gradients of the embedding live in ONE flat buffer (one allocation instead of ~65, and the
+        # reducer all-reduces the buffer itself: no torch.cat, no copy back)
+        layout = self.__dict__.get("_dense_layout")
+        if layout is None or layout[0] != len(params):
+            items, off = [], 0
+            for i, (p, tab) in enumerate(zip(params, self._param_is_table)):
+                if not tab:
+                    items.append((i, off, p.numel(), tuple(p.shape)))
+                    off += (p.numel() + 3) // 4 * 4
+            layout = self.__dict__["_dense_layout"] = (len(params), items, off)
+        _, items, total = layout
+        flat_g = torch.empty((max(total, 1),), device=dev, dtype=torch.float32)
+        if total and any((n + 3) // 4 * 4 != n for _, _, n, _ in items):
+            flat_g.zero_()                                    # alignment gaps travel through the allreduce: keep them finite
+        grads: List[Optional[torch.Tensor]] = [None] * len(params)
+        for i, off, n, shape in items:
+            g = flat_g[off:off + n].view(shape)
+            grads[i] = g
+            dense_grads[i] = g
+        self.dense_grad_flat = flat_g if items else None
         if dense_grads:
             keys = keys if self._repl_idx else None
             mode = _lib.GRAD_DENSE if keys is not None else _lib.GRAD_SKIP_TABLES
@@ -811,13 +853,18 @@ class ShardedFeatureEmbedding(IndexStatusMixin, nn.Module):
             ev.record(side)
         for t in inputs:
             t.record_stream(side)
-        self._prefetched = (tuple(t.data_ptr() for t in inputs), inputs, route, pending, ev)
+        # keyed by the batch's tensors: the prefetch of batch i + 1 is issued at the START of step i, i.e. before the
+        # forward of batch i has taken its own entry (a single slot would be overwritten every step)
+        store = self.__dict__.setdefault("_prefetched", {})
+        while len(store) >= 2:
+            store.pop(next(iter(store)))
+        store[tuple(t.data_ptr() for t in inputs)] = (None, inputs, route, pending, ev)
 
     def _take_prefetch(self, inputs):
-        pref = getattr(self, "_prefetched", None)
-        if pref is None or pref[0] != tuple(t.data_ptr() for t in inputs):
+        store = self.__dict__.get("_prefetched")
+        pref = store.pop(tuple(t.data_ptr() for t in inputs), None) if store else None
+        if pref is None:
             return None
-        self._prefetched = None
         cur = torch.cuda.current_stream(inputs[0].device)
         cur.wait_event(pref[4])                                 # the routing tensors were produced on the side stream
         route = pref[2]
@@ -867,27 +914,40 @@ class ShardedFeatureEmbedding(IndexStatusMixin, nn.Module):
 class DenseGradReducer:
     """Data-parallel averaging of the replicated parameters' gradients, overlapped with the table backward.
 
-    ``early`` parameters (DNN / CIN / attention / head Linears) have their gradients before the embedding
-    backward starts: as soon as the last of them is accumulated (post-accumulate-grad hooks, the order the
-    autograd engine guarantees on every rank) ONE flat NCCL allreduce is launched asynchronously, so it runs on
-    NCCL's stream underneath the gradient exchange and the owner-side reduction.  ``late`` parameters (the
-    DENSE-field Linears inside the embedding) follow in a second, tiny allreduce in ``finish()``."""
+    ``early`` parameters (DNN / CIN / attention / head Linears) have their gradients before the embedding backward
+    starts: the autograd engine runs AccumulateGrad nodes ahead of every other ready node (they carry the maximal
+    sequence number), and every early parameter sits downstream of the embedding, so when the embedding's backward node
+    starts all of them are accumulated.  With ``embedding=`` the sharded module calls ``launch`` at that moment (one
+    callback per step); without it, per-parameter post-accumulate-grad hooks count the arrivals.  Either way ONE flat
+    NCCL allreduce is launched asynchronously and runs on NCCL's stream underneath the gradient exchange and the
+    owner-side reduction.  ``late`` parameters (the DENSE-field Linears and replicated tables inside the embedding)
+    follow in a second allreduce in ``finish()`` -- directly on the embedding's flat gradient buffer when it has one."""
 
-    def __init__(self, early, late, world: int, group=None):
+    def __init__(self, early, late, world: int, group=None, embedding=None):
         import torch.distributed as dist
         self.dist, self.group, self.world = dist, group, world
         self.early = [p for p in early if p.requires_grad]
         self.late = [p for p in late if p.requires_grad]
+        self.embedding = embedding
         self._pending, self._work, self._flat = 0, None, None
+        self._shapes = [(p.numel(), tuple(p.shape)) for p in self.early]
         if world > 1:
-            for p in self.early:
-                p.register_post_accumulate_grad_hook(self._hook)
+            if embedding is not None and hasattr(embedding, "forward_fused"):
+                embedding.on_backward_start = self.launch
+            else:
+                for p in self.early:
+                    p.register_post_accumulate_grad_hook(self._hook)
+
+    def launch(self) -> None:
+        if self._work is not None or any(p.grad is None for p in self.early):
+            return                        # already launched / a parameter has no gradient yet: finish() handles it
+        self._flat = torch.cat([p.grad.reshape(-1) for p in self.early])
+        self._work = self.dist.all_reduce(self._flat, group=self.group, async_op=True)
 
     def _hook(self, _param) -> None:
         self._pending += 1
         if self._pending == len(self.early):
-            self._flat = torch.cat([p.grad.reshape(-1) for p in self.early])
-            self._work = self.dist.all_reduce(self._flat, group=self.group, async_op=True)
+            self.launch()
 
     @staticmethod
     def _scatter(flat, params, world):
@@ -913,7 +973,12 @@ class DenseGradReducer:
             self._work.wait()
             self._scatter(self._flat, self.early, self.world)
         late = [p for p in self.late if p.grad is not None]
-        if late:
+        buf = getattr(self.embedding, "dense_grad_flat", None) if self.embedding is not None else None
+        if buf is not None and late and sum(p.grad.numel() for p in late) <= buf.numel() \
+                and all(p.grad.untyped_storage().data_ptr() == buf.untyped_storage().data_ptr() for p in (late[0], late[-1])):
+            self.dist.all_reduce(buf, group=self.group)      # the gradients ARE views of this buffer
+            buf.div_(self.world)
+        elif late:
             flat = torch.cat([p.grad.reshape(-1) for p in late])
             self.dist.all_reduce(flat, group=self.group)
             self._scatter(flat, late, self.world)

@@ -67,7 +67,8 @@ def check_against_unsharded(model_name: str, schema, cfg, batch: Dict[str, torch
     table_ids = {id(p) for p, t in zip(ordered, emb._param_is_table) if t}
     dense_params = [p for p in shard.parameters() if id(p) not in table_ids]
     emb_ids = {id(p) for p in emb.parameters()}
-    reducer = DenseGradReducer([p for p in dense_params if id(p) not in emb_ids], [p for p in dense_params if id(p) in emb_ids], world)
+    reducer = DenseGradReducer([p for p in dense_params if id(p) not in emb_ids], [p for p in dense_params if id(p) in emb_ids], world,
+                               embedding=emb)       # the product wiring: launched from the sharded backward, flat late bucket
     bce = torch.nn.BCEWithLogitsLoss()
     out: Dict[str, float] = {}
 

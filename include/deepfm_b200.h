@@ -309,6 +309,13 @@ DFM_API int dfm_shard_bwd_peer(const dfm_plan* plan, int64_t batch, const float*
                                const uint32_t* unique_index, int64_t n_sorted, uint32_t pad_key, int n_peers,
                                const int64_t* peer_start, float* const* peer_vec, float* const* peer_sc,
                                float grad_scale, void* workspace, size_t workspace_bytes, void* stream);
+/* Device-side barrier between the ranks' streams over peer-mapped memory (no reference counterpart: the reference is
+ * single-device).  peer_flags[r] = device address, valid on THIS GPU, of rank r's flag array (>= world uint32 words,
+ * zero-initialised, in memory every rank has mapped: the symmetric exchange allocation).  Enqueues one tiny kernel on
+ * `stream`: it publishes `epoch` to every rank and waits until every rank has published an epoch >= `epoch`; all peer
+ * stores enqueued on the stream before the call are visible to the peers' kernels enqueued after their call.  Every
+ * rank must call it with the same, growing epoch sequence. */
+DFM_API int dfm_peer_barrier(uint32_t* const* peer_flags, int world, int rank, uint32_t epoch, void* stream);
 /* Per-field table source of a plan: row_stride / w1_stride (floats, 0 = dim / 1) let K1 read the field's rows
  * out of a strided buffer (the received reply rows); foreign = 1 marks a table whose gradient is produced
  * elsewhere: K1 emits no sort key for its ids and dfm_embed_bwd / dfm_rows_bwd ignore it.  On the sample-side
