@@ -356,7 +356,7 @@ def run_ours(args, rank: int, local_rank: int, n_gpus: int):
     def step(batch, labels, next_batch=None, next_ready=None):
         if next_batch is not None and sharded:
             # input pipeline: route the NEXT batch on a side stream, under this step
-            model.embedding.prefetch(next_batch, ready_event=next_ready)
+            model.embedding.queue_prefetch(next_batch, ready_event=next_ready)
         for p in all_params:                       # == optimizer.zero_grad(set_to_none=True): no module-tree walk per step
             p.grad = None
         logits = model(batch).squeeze(1)
@@ -402,9 +402,19 @@ def run_ours(args, rank: int, local_rank: int, n_gpus: int):
     if rank == 0:
         sampler.start()
     model.embedding.profile_events = {}
+    ahead = int(os.environ.get("DFM_BENCH_MAX_AHEAD", "-1"))      # >= 0: the host enqueues at most this many steps ahead
+    done_events = []
+
     def value_step(i):
+        if ahead >= 0 and len(done_events) > ahead:
+            done_events.pop(0).synchronize()
         prepare(devb[(W_ + i + 1) % n_batches])
-        return step(devb[(W_ + i) % n_batches], devy[(W_ + i) % n_batches], devb[(W_ + i + 1) % n_batches])
+        out = step(devb[(W_ + i) % n_batches], devy[(W_ + i) % n_batches], devb[(W_ + i + 1) % n_batches])
+        if ahead >= 0:
+            ev_ = torch.cuda.Event()
+            ev_.record()
+            done_events.append(ev_)
+        return out
 
     if os.environ.get("DFM_BENCH_CPROFILE") and rank == 0:      # development aid: where the HOST time of a step goes
         import cProfile, pstats
@@ -496,7 +506,8 @@ def run_ours(args, rank: int, local_rank: int, n_gpus: int):
         from torch.profiler import ProfilerActivity, profile
         if os.environ.get("DFM_BENCH_TRACE"):     # development aid: host + device timeline of two steady-state steps
             step(devb[0], devy[0], devb[1])
-            with profile(activities=[ProfilerActivity.CUDA, ProfilerActivity.CPU]) as tprof:
+            acts = [ProfilerActivity.CUDA] if os.environ.get("DFM_BENCH_TRACE_CUDA_ONLY") else [ProfilerActivity.CUDA, ProfilerActivity.CPU]
+            with profile(activities=acts) as tprof:
                 sync_each = bool(os.environ.get("DFM_BENCH_TRACE_E2E"))     # .item() after every step, like the e2e region
                 l1 = step(devb[1], devy[1], devb[2])
                 if sync_each:
@@ -504,6 +515,9 @@ def run_ours(args, rank: int, local_rank: int, n_gpus: int):
                 l2 = step(devb[2], devy[2], devb[3])
                 if sync_each:
                     l2.item()
+                else:                                  # four more: the host runs ahead, the last steps are steady state
+                    for j in range(4):
+                        step(devb[(3 + j) % 4], devy[(3 + j) % 4], devb[(4 + j) % 4])
                 torch.cuda.synchronize()
             tprof.export_chrome_trace(os.environ["DFM_BENCH_TRACE"])
             step(devb[3], devy[3])
@@ -523,8 +537,12 @@ def run_ours(args, rank: int, local_rank: int, n_gpus: int):
                                  f"{100.0 * e.device_time_total / tot:.2f}\n")
     else:
         if os.environ.get("DFM_BENCH_TRACE"):
-            for i in range(4):
-                step(devb[i], devy[i], devb[i + 1] if i < 3 else None)
+            for i in range(3):
+                step(devb[i], devy[i], devb[i + 1])
+            if not os.environ.get("DFM_BENCH_TRACE_E2E"):
+                for j in range(4):
+                    step(devb[(3 + j) % 4], devy[(3 + j) % 4], devb[(4 + j) % 4])
+            step(devb[3], devy[3])
         step(devb[0], devy[0])
         torch.cuda.synchronize()
 

@@ -118,6 +118,31 @@ __global__ void l2_fill_kernel(const float* __restrict__ p, float* __restrict__ 
     }
 }
 
+// The same fill for a LIST of small tensors in one launch (blockIdx.y = tensor): dense-mode plans with many small
+// tables (the replicated tables of the sharded path: 28 tensors) paid one launch per tensor.
+struct L2FillList { const float* p[64]; float* g[64]; long long n[64]; };
+
+__global__ void l2_fill_multi_kernel(const __grid_constant__ L2FillList L, float l2x2, const float* __restrict__ gscale) {
+    const float coef = l2x2 * (gscale ? __ldg(gscale) : 1.f);
+    const float* __restrict__ p = L.p[blockIdx.y];
+    float* __restrict__ g = L.g[blockIdx.y];
+    const long long n = L.n[blockIdx.y];
+    const long long stride = (long long)gridDim.x * blockDim.x;
+    const bool al = ((reinterpret_cast<uintptr_t>(p) | reinterpret_cast<uintptr_t>(g)) & 15u) == 0;
+    long long i = (long long)blockIdx.x * blockDim.x + threadIdx.x;
+    if (al) {
+        const long long n4 = n >> 2;
+        for (; i < n4; i += stride) {
+            float4 w = make_float4(0.f, 0.f, 0.f, 0.f);
+            if (coef != 0.f) w = __ldcs(reinterpret_cast<const float4*>(p) + i);
+            __stcs(reinterpret_cast<float4*>(g) + i, make_float4(coef * w.x, coef * w.y, coef * w.z, coef * w.w));
+        }
+        for (i = (n4 << 2) + (long long)blockIdx.x * blockDim.x + threadIdx.x; i < n; i += stride) g[i] = coef != 0.f ? coef * p[i] : 0.f;
+    } else {
+        for (; i < n; i += stride) g[i] = coef != 0.f ? coef * p[i] : 0.f;
+    }
+}
+
 // ---- upstream gradient of one id slot, chunk c (V floats) of the raw embedding row
 template <int V>
 __device__ __forceinline__ VecF<V> slot_grad(const DevPlan& P, const BwdArgs& a, const FieldDev& fd,
@@ -1455,14 +1480,29 @@ static int embed_bwd_impl(const dfm_plan* plan, int64_t batch, long long direct_
 
     // 1. dense mode: every element of every table gradient starts as 2*l2*w (or 0)
     if (mode == DFM_GRAD_DENSE) {
+        // small tensors (<= 1 M floats) are batched into one launch per 64; big tables keep their own full-width launch
+        L2FillList* fl = new L2FillList;
+        struct G3 { L2FillList* p; ~G3() { delete p; } } g3{fl};
+        int nl = 0;
+        auto flush = [&]() {
+            if (nl > 0) l2_fill_multi_kernel<<<dim3(16, nl), 256, 0, st>>>(*fl, a.l2x2, l2_gscale);
+            nl = 0;
+        };
+        auto add = [&](const float* p, float* g, long long n) {
+            if (n > (1LL << 20)) {
+                int b = (int)(ceil_div(n, 1024) < fill_blocks ? ceil_div(n, 1024) : fill_blocks);
+                l2_fill_kernel<<<b, 256, 0, st>>>(p, g, n, a.l2x2, l2_gscale);
+                return;
+            }
+            fl->p[nl] = p; fl->g[nl] = g; fl->n[nl] = n;
+            if (++nl == 64) flush();
+        };
         for (int f = 0; f < plan->n_fields; ++f) {
             if (plan->kind[f] == DFM_DENSE || plan->foreign[f]) continue;
-            const long long n2 = plan->vocab[f] * plan->dim[f], n1 = plan->vocab[f];
-            int b2 = (int)(ceil_div(n2, 1024) < fill_blocks ? ceil_div(n2, 1024) : fill_blocks);
-            int b1 = (int)(ceil_div(n1, 1024) < fill_blocks ? ceil_div(n1, 1024) : fill_blocks);
-            l2_fill_kernel<<<b2, 256, 0, st>>>(params[5 * f + 0], grads[5 * f + 0], n2, a.l2x2, l2_gscale);
-            l2_fill_kernel<<<b1, 256, 0, st>>>(params[5 * f + 2], grads[5 * f + 2], n1, a.l2x2, l2_gscale);
+            add(params[5 * f + 0], grads[5 * f + 0], plan->vocab[f] * plan->dim[f]);
+            add(params[5 * f + 2], grads[5 * f + 2], plan->vocab[f]);
         }
+        flush();
         DFM_CHECK_LAUNCH();
     }
     // 2. sort + segmented reduction of the id slots

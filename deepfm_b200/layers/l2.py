@@ -124,12 +124,12 @@ class _L2PenaltyFn(torch.autograd.Function):
         # node is an ancestor of this one and is guaranteed to run later in the same backward pass.
         live = emb._live_ctx() if getattr(emb, "_live_ctx", None) is not None else None
         ctx.live = live if anchor is not None else None
-        ctx.save_for_backward(*params)
+        ctx.params = params           # inputs of this node (leaf parameters): plain references, not ~90 saved tensors
         return out
 
     @staticmethod
     def backward(ctx, g):
-        params = ctx.saved_tensors
+        params = ctx.params
         emb, lam = ctx.emb, ctx.lam
         g = g.contiguous().float()
         live = ctx.live

@@ -8,6 +8,11 @@ ev = json.loads(raw)["traceEvents"]
 k = [e for e in ev if e.get("cat") in ("kernel", "gpu_memcpy", "gpu_memset") and "dur" in e]
 cpu = [e for e in ev if e.get("cat") in ("cpu_op", "user_annotation", "cuda_runtime", "cuda_driver") and "dur" in e]
 k.sort(key=lambda e: e["ts"])
+import os
+if os.environ.get("TRACE_FROM"):          # keep only the tail of the trace (fraction of the span), e.g. the steady-state steps
+    a0, a1 = k[0]["ts"], max(e["ts"] + e["dur"] for e in k)
+    cut = a0 + float(os.environ["TRACE_FROM"]) * (a1 - a0)
+    k = [e for e in k if e["ts"] >= cut]
 t0, t1 = k[0]["ts"], max(e["ts"] + e["dur"] for e in k)
 print(f"device span {t1 - t0:.0f} us, {len(k)} device activities, streams: {sorted({e['args'].get('stream') for e in k})}")
 busy, cur_s, cur_e, gaps = 0.0, None, None, []
