@@ -70,6 +70,8 @@ SIGNATURES = {
     "dfm_shard_unique_workspace_bytes": (_sz, [_i64]),
     "dfm_shard_unique": (C.c_int, [_vp, C.c_int, C.c_int, _i64, _i64, _vp, _vp, _vp, _vp, _vp, _vp, _vp, _sz, _vp]),
     "dfm_shard_gather2": (C.c_int, [_vp, C.c_int, C.c_int, _i64, _vp, _pp, C.c_int, _pi64, _pp, _pp, _vp, _vp]),
+    "dfm_shard_push_counts": (C.c_int, [_vp, C.c_int, C.c_int, _vp, _vp]),
+    "dfm_shard_push_keys": (C.c_int, [_vp, _vp, C.c_int, C.c_int, _i64, _vp, _vp]),
     "dfm_peer_barrier": (C.c_int, [_vp, C.c_int, C.c_int, C.c_uint32, _vp]),
     "dfm_shard_bwd_peer": (C.c_int, [_vp, _i64, _vp, _vp, _vp, _vp, _vp, _vp, _vp, _vp, _vp, _vp, _i64, C.c_uint32, C.c_int,
                                      _pi64, _pp, _pp, _f32, _vp, _sz, _vp]),

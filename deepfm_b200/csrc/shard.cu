@@ -531,6 +531,41 @@ static int fill_peer(PeerDst& pd, int n_peers, const int64_t* peer_start, float*
 // reaches `epoch` (acquire).  Epochs only grow (wrap-safe signed compare), so no reset pass is needed.  A peer that never
 // arrives trips a ~4 s watchdog (trap) instead of hanging the GPU.
 struct PeerFlags { uint32_t* flags[RT_MAXW_]; };
+struct PeerI64 { long long* p[RT_MAXW_]; };
+struct PeerU32 { uint32_t* p[RT_MAXW_]; };
+
+// counts (W) of this rank -> row `rank` of the W x W count matrix of EVERY rank (peer-mapped stores)
+__global__ void push_counts_kernel(const long long* __restrict__ counts, int world, int rank, PeerI64 dst) {
+    const int t = threadIdx.x;
+    if (t < world * world) dst.p[t / world][(size_t)rank * world + (t % world)] = counts[t % world];
+}
+
+// This rank's unique keys (send order: grouped by owner) -> the owners' receive buffers.  Offsets come from the count
+// matrix M (device memory, complete after the barrier that follows push_counts): my segment for owner q starts at
+// sum_{r<q} M[rank][r] in the send order and lands at sum_{s<rank} M[s][q] in q's receive order (grouped by source).
+__global__ void __launch_bounds__(256)
+push_keys_kernel(const uint32_t* __restrict__ send_keys, const long long* __restrict__ M, int world, int rank, long long cap,
+                 PeerU32 dst) {
+    __shared__ long long s_send[RT_MAXW_ + 1], s_recv[RT_MAXW_];
+    if (threadIdx.x == 0) {
+        long long acc = 0;
+        for (int q = 0; q < world; ++q) { s_send[q] = acc; acc += M[(size_t)rank * world + q]; }
+        s_send[world] = acc;
+        for (int q = 0; q < world; ++q) {
+            long long r = 0;
+            for (int sr = 0; sr < rank; ++sr) r += M[(size_t)sr * world + q];
+            s_recv[q] = r;
+        }
+    }
+    __syncthreads();
+    const long long n = s_send[world];
+    for (long long i = (long long)blockIdx.x * blockDim.x + threadIdx.x; i < n; i += (long long)gridDim.x * blockDim.x) {
+        int q = 0;
+        while (q + 1 < world && i >= s_send[q + 1]) ++q;
+        const long long j = s_recv[q] + (i - s_send[q]);
+        if (j < cap) dst.p[q][j] = send_keys[i];      // a receive buffer that would overflow is detected on the host (fits())
+    }
+}
 
 __global__ void peer_barrier_kernel(PeerFlags pf, int world, int rank, uint32_t epoch) {
     const int r = threadIdx.x;
@@ -805,6 +840,36 @@ int dfm_shard_gather2(const dfm_plan* local_plan, int world, int rank, int64_t n
     cudaStream_t st = static_cast<cudaStream_t>(stream);
     if (v4) shard_gather2_kernel<4><<<(unsigned)blocks, 256, 0, st>>>(*a, n_keys, local_keys, G, backward_keys, *pd);
     else shard_gather2_kernel<1><<<(unsigned)blocks, 256, 0, st>>>(*a, n_keys, local_keys, G, backward_keys, *pd);
+    DFM_CHECK_LAUNCH();
+    return DFM_OK;
+}
+
+int dfm_shard_push_counts(const int64_t* counts, int world, int rank, int64_t* const* peer_matrix, void* stream) {
+    DFM_REQUIRE(counts && peer_matrix && world >= 1 && world <= RT_MAXW_ && rank >= 0 && rank < world, DFM_ERR_INVALID,
+                "dfm_shard_push_counts: 1..%d ranks", RT_MAXW_);
+    PeerI64 d;
+    memset(&d, 0, sizeof(d));
+    for (int r = 0; r < world; ++r) {
+        DFM_REQUIRE(peer_matrix[r], DFM_ERR_INVALID, "dfm_shard_push_counts: null matrix of rank %d", r);
+        d.p[r] = reinterpret_cast<long long*>(peer_matrix[r]);
+    }
+    push_counts_kernel<<<1, 256, 0, static_cast<cudaStream_t>(stream)>>>(reinterpret_cast<const long long*>(counts), world, rank, d);
+    DFM_CHECK_LAUNCH();
+    return DFM_OK;
+}
+
+int dfm_shard_push_keys(const uint32_t* send_keys, const int64_t* matrix, int world, int rank, int64_t capacity,
+                        uint32_t* const* peer_keys, void* stream) {
+    DFM_REQUIRE(send_keys && matrix && peer_keys && world >= 1 && world <= RT_MAXW_ && rank >= 0 && rank < world && capacity > 0,
+                DFM_ERR_INVALID, "dfm_shard_push_keys: bad argument (1..%d ranks)", RT_MAXW_);
+    PeerU32 d;
+    memset(&d, 0, sizeof(d));
+    for (int r = 0; r < world; ++r) {
+        DFM_REQUIRE(peer_keys[r], DFM_ERR_INVALID, "dfm_shard_push_keys: null key buffer of rank %d", r);
+        d.p[r] = peer_keys[r];
+    }
+    push_keys_kernel<<<2 * sm_count(), 256, 0, static_cast<cudaStream_t>(stream)>>>(send_keys, reinterpret_cast<const long long*>(matrix),
+                                                                                   world, rank, capacity, d);
     DFM_CHECK_LAUNCH();
     return DFM_OK;
 }

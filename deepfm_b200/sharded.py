@@ -33,6 +33,7 @@ the routing logic (pure torch ops) runs on CPU tensors under gloo.
 from __future__ import annotations
 
 import ctypes as C
+import os
 import weakref
 from dataclasses import dataclass
 from typing import Dict, List, Optional, Sequence
@@ -186,12 +187,21 @@ class PeerExchange:
         self.dim, self.cap = int(dim), (int(capacity_rows) + 63) // 64 * 64      # every block starts on a 256-byte boundary
         group = comm.group if comm.group is not None else comm.dist.group.WORLD
         n = 4 * self.cap * (self.dim + 4)
-        self.buf, self.hdl = _peer.symmetric_empty(n + 64, device, group)     # + 64 words: the barrier's flag array
+        W = self.world
+        # tail of the allocation: [64 flag words: 4 barrier channels x 16 ranks][2 count matrices W x W int64][2 key
+        # receive buffers of cap int32] -- the id exchange of the prefetch (dfm_shard_push_counts / _keys)
+        self._off_flags = n
+        self._off_matrix = n + 64
+        self._mat_words = (2 * W * W + 3) // 4 * 4
+        self._off_keys = self._off_matrix + 2 * self._mat_words
+        total = self._off_keys + 2 * self.cap
+        self.buf, self.hdl = _peer.symmetric_empty(total, device, group)
         self.buf.zero_()                                     # row 0 of both got buffers is the reserved zero row
         self.peer_base = [int(p) for p in self.hdl.buffer_ptrs]
-        self._flag_ptrs = _lib.ptr_array([b + 4 * n for b in self.peer_base])
-        self._epoch = 0
+        self._flag_ptrs = [_lib.ptr_array([b + 4 * (n + 16 * ch) for b in self.peer_base]) for ch in range(4)]
+        self._epoch = [0, 0, 0, 0]
         self.step = 0
+        self.pf_step = 0                                     # prefetches issued (parity of the id-exchange buffers)
         torch.cuda.synchronize(device)
         self.hdl.barrier(channel=0)                          # setup only: every rank's flags are zero before any epoch
 
@@ -221,10 +231,51 @@ class PeerExchange:
     def barrier(self, channel: int = 0) -> None:
         """All-ranks barrier on the current stream: one 32-thread kernel of our own over peer-mapped flag words
         (``dfm_peer_barrier``).  torch's ``handle.barrier`` costs ~1 ms of HOST time per call (measured with cProfile
-        at W = 2: 1.9 of the 5.9 ms step), which made the sharded step host-bound."""
-        self._epoch += 1
-        _lib.check(_lib.lib().dfm_peer_barrier(self._flag_ptrs, self.world, self.rank, self._epoch & 0xFFFFFFFF,
-                                               _lib.stream_ptr()), "dfm_peer_barrier")
+        at W = 2: 1.9 of the 5.9 ms step), which made the sharded step host-bound.  Barriers issued on different
+        streams use different channels (own flag words, own epoch): channels 0 / 1 the step's stream (forward,
+        backward), channel 2 the prefetch stream."""
+        self._epoch[channel] += 1
+        _lib.check(_lib.lib().dfm_peer_barrier(self._flag_ptrs[channel], self.world, self.rank,
+                                               self._epoch[channel] & 0xFFFFFFFF, _lib.stream_ptr()), "dfm_peer_barrier")
+
+    def matrix_ptrs(self, parity: int):
+        return _lib.ptr_array([b + 4 * (self._off_matrix + parity * self._mat_words) for b in self.peer_base])
+
+    def matrix_view(self, parity: int) -> torch.Tensor:
+        o = self._off_matrix + parity * self._mat_words
+        return self.buf[o: o + 2 * self.world * self.world].view(torch.int64).view(self.world, self.world)
+
+    def key_ptrs(self, parity: int):
+        return _lib.ptr_array([b + 4 * (self._off_keys + parity * self.cap) for b in self.peer_base])
+
+    def keys_view(self, parity: int, n: int) -> torch.Tensor:
+        o = self._off_keys + parity * self.cap
+        return self.buf[o: o + n].view(torch.int32)
+
+    def push_ids(self, route: "Route"):
+        """Prefetch-stream half of the id exchange: counts -> every rank's matrix, barrier, keys -> their owners' receive
+        buffers, barrier; returns (pinned host matrix, event, parity).  No NCCL call, ~5 kernel launches."""
+        lib = _lib.lib()
+        p = self.pf_step & 1
+        self.pf_step += 1
+        st = _lib.stream_ptr()
+        _lib.check(lib.dfm_shard_push_counts(_lib.ptr(route.counts), self.world, self.rank, self.matrix_ptrs(p), st),
+                   "dfm_shard_push_counts")
+        self.barrier(2)
+        mat = self.matrix_view(p)
+        _lib.check(lib.dfm_shard_push_keys(_lib.ptr(route.send_keys), mat.data_ptr(), self.world, self.rank, self.cap,
+                                           self.key_ptrs(p), st), "dfm_shard_push_keys")
+        self.barrier(2)
+        ring = self.__dict__.get("_pinned_ring")
+        if ring is None:
+            ring = self._pinned_ring = [torch.empty((self.world, self.world), dtype=torch.int64, pin_memory=True) for _ in range(4)]
+            self._pinned_i = 0
+        host = ring[self._pinned_i % 4]
+        self._pinned_i += 1
+        host.copy_(mat, non_blocking=True)
+        ev = torch.cuda.Event()
+        ev.record()
+        return host, ev, p
 
 
 class _ShardedEmbedFn(torch.autograd.Function):
@@ -233,17 +284,24 @@ class _ShardedEmbedFn(torch.autograd.Function):
         inputs, params = tensors[:n_inputs], tensors[n_inputs:]
         comm = mod.comm
         pref = mod._take_prefetch(inputs)
+        pushed = None
         if pref is not None:      # routed ahead of time (prefetch): the counts are already on the host
             route, pending = pref
+            if len(pending) == 3:                 # ids exchanged by peer stores: (host matrix, event, parity)
+                pushed = pending[2]
+                pending = pending[:2]
             send_counts, recv_counts = comm.finish_counts(pending)
         else:
             route = mod.route(inputs)
             send_counts, recv_counts = comm.exchange_counts(route.counts)     # the only host sync of the step
         n_send, n_recv = int(sum(send_counts)), int(sum(recv_counts))
-        recv_keys = comm.all_to_all(route.send_keys[:n_send], send_counts, recv_counts)
         px = mod.peer_exchange(inputs[0].device)
         matrix = getattr(comm, "last_matrix", None)
         use_p2p = px is not None and matrix is not None and px.fits(matrix)
+        if pushed is not None and use_p2p:
+            recv_keys = px.keys_view(pushed, n_recv)          # landed before the prefetch event this stream waited on
+        else:
+            recv_keys = comm.all_to_all(route.send_keys[:n_send], send_counts, recv_counts)
         parity = 0
         if use_p2p:
             # owners store every reply row straight into the requester's got buffers (NVLink P2P), then one barrier
@@ -863,9 +921,13 @@ class ShardedFeatureEmbedding(IndexStatusMixin, nn.Module):
         side.wait_stream(cur)                                  # the batch is ready on the caller's stream ...
         if ready_event is not None:
             side.wait_event(ready_event)                       # ... or when this event (e.g. its host -> device copy) fires
+        px = self._px if isinstance(self._px, PeerExchange) else None
         with torch.cuda.stream(side):
             route = self.route(inputs)
-            pending = self.comm.exchange_counts_async(route.counts)
+            if px is not None and route.skeys is not None and os.environ.get("DFM_SHARD_P2P_IDS", "1") != "0":
+                pending = px.push_ids(route)             # counts + keys as peer stores: no NCCL call in the prefetch
+            else:
+                pending = self.comm.exchange_counts_async(route.counts)
             ev = torch.cuda.Event()
             ev.record(side)
         for t in inputs:

@@ -16,6 +16,8 @@ the unsharded model:
 
 from __future__ import annotations
 
+import os
+
 from typing import Dict
 
 import torch
@@ -72,11 +74,19 @@ def check_against_unsharded(model_name: str, schema, cfg, batch: Dict[str, torch
     bce = torch.nn.BCEWithLogitsLoss()
     out: Dict[str, float] = {}
 
-    # ---- the product path on this rank's batch
+    # ---- the product path on this rank's batch: once cold (routing inside the forward, ids by NCCL all-to-all), then the
+    # way the training loop runs it -- the batch routed ahead by prefetch() (ids exchanged as peer stores when the
+    # peer-memory buffers exist); the second pass is the one compared below, the first must agree with it bit for bit
     shard.zero_grad(set_to_none=True)
+    logits0 = shard(batch).squeeze(1)
+    (bce(logits0, labels) + shard.get_l2_reg_loss()).backward()
+    reducer.finish()
+    shard.zero_grad(set_to_none=True)
+    emb.prefetch(batch)
     logits = shard(batch).squeeze(1)
     (bce(logits, labels) + shard.get_l2_reg_loss()).backward()
     reducer.finish()
+    out["prefetched_equals_cold"] = float(torch.equal(logits.detach(), logits0.detach()))
     # ---- unsharded model: this rank's samples (logits) ...
     with torch.no_grad():
         ref_logits = full(batch).squeeze(1)
@@ -138,11 +148,12 @@ def check_against_unsharded(model_name: str, schema, cfg, batch: Dict[str, torch
     out["dense_grad_max_rel_err"] = worst_dense
     out["p2p"] = float(emb._px not in (None, False))
     # worst over ranks
-    t = torch.tensor([1.0 - out["logits_bit_identical"], out["logits_max_rel_err"], out["table_grad_max_rel_err"],
-                      out["dense_grad_max_rel_err"]], device=dev, dtype=torch.float64)
+    t = torch.tensor([1.0 - min(out["logits_bit_identical"], out["prefetched_equals_cold"]), out["logits_max_rel_err"],
+                      out["table_grad_max_rel_err"], out["dense_grad_max_rel_err"]], device=dev, dtype=torch.float64)
     dist.all_reduce(t, op=dist.ReduceOp.MAX)
     n = torch.tensor([out["table_rows_checked"]], device=dev, dtype=torch.float64)
     dist.all_reduce(n)
     return {"logits_bit_identical": bool(t[0].item() == 0.0), "logits_max_rel_err": t[1].item(),
             "table_grad_max_rel_err": t[2].item(), "dense_grad_max_rel_err": t[3].item(),
-            "table_rows_checked": int(n.item()), "p2p": bool(out["p2p"]), "world": world}
+            "table_rows_checked": int(n.item()), "p2p": bool(out["p2p"]), "world": world,
+            "ids_by_peer_stores": bool(out["p2p"]) and os.environ.get("DFM_SHARD_P2P_IDS", "1") != "0"}

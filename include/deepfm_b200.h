@@ -315,6 +315,15 @@ DFM_API int dfm_shard_bwd_peer(const dfm_plan* plan, int64_t batch, const float*
  * `stream`: it publishes `epoch` to every rank and waits until every rank has published an epoch >= `epoch`; all peer
  * stores enqueued on the stream before the call are visible to the peers' kernels enqueued after their call.  Every
  * rank must call it with the same, growing epoch sequence. */
+/* Id exchange of the sharded path as peer-memory stores (replaces the count all-gather and the key all-to-all of
+ * SURVEY 8(e) step (1); no reference counterpart).  dfm_shard_push_counts: this rank's per-owner unique-key counts (W)
+ * become row `rank` of the W x W count matrix of every rank (peer_matrix[r] = rank r's matrix, int64).  After a
+ * dfm_peer_barrier the matrix is complete everywhere; dfm_shard_push_keys then stores this rank's keys (send order,
+ * grouped by owner) into each owner's receive buffer at the offset the matrix implies (receive order = grouped by
+ * source rank); entries that would fall beyond `capacity` are dropped (the host sees the overflow in the matrix). */
+DFM_API int dfm_shard_push_counts(const int64_t* counts, int world, int rank, int64_t* const* peer_matrix, void* stream);
+DFM_API int dfm_shard_push_keys(const uint32_t* send_keys, const int64_t* matrix, int world, int rank, int64_t capacity,
+                                uint32_t* const* peer_keys, void* stream);
 DFM_API int dfm_peer_barrier(uint32_t* const* peer_flags, int world, int rank, uint32_t epoch, void* stream);
 /* Per-field table source of a plan: row_stride / w1_stride (floats, 0 = dim / 1) let K1 read the field's rows
  * out of a strided buffer (the received reply rows); foreign = 1 marks a table whose gradient is produced
