@@ -9,8 +9,12 @@ os.makedirs(dst, exist_ok=True)
 # 1. launch list: share of every kernel in the bench command
 lines = [l for l in open(os.path.join(src, f"launches_{tag}.csv")) if not l.startswith("==")]
 agg = collections.OrderedDict()
+started = False       # everything before the first K1 launch is model construction (table initialisation), not the step
 for row in csv.DictReader(lines):
     if row.get("Metric Name") != "gpu__time_duration.sum":
+        continue
+    started = started or "embed_fwd_kernel" in row["Kernel Name"]
+    if not started:
         continue
     v = float(row["Metric Value"].replace(",", ""))
     v = v / 1e3 if row["Metric Unit"] == "ns" else v * 1e3 if row["Metric Unit"] == "ms" else v
@@ -21,10 +25,10 @@ for row in csv.DictReader(lines):
 tot = sum(a[1] for a in agg.values())
 with open(os.path.join(dst, f"{tag}_launches_summary.csv"), "w") as fh:
     fh.write("# ncu --metrics gpu__time_duration.sum --clock-control none : python bench.py --steps 2 --warmup 3 --no-cpu-baseline\n")
-    fh.write("# per-launch times are cold-cache and serialised: compare SHARES, not absolutes\n")
+    fh.write("# per-launch times are cold-cache and serialised: compare SHARES, not absolutes; launches before the first K1 (table initialisation) are skipped\n")
     fh.write("kernel,launches,total_us,avg_us,share_pct,ours\n")
     for k, (c, t) in sorted(agg.items(), key=lambda kv: -kv[1][1]):
-        ours = int("dfm::" in k or "DeviceRadixSort" in k)
+        ours = int(any(t in k for t in ("dfm::", "g3::", "tw::", "peer_barrier", "DeviceRadixSort")))     # CUB sort: library, listed with the path
         fh.write(f"\"{k}\",{c},{t:.1f},{t / c:.2f},{100 * t / tot:.2f},{ours}\n")
 with gzip.open(os.path.join(dst, f"{tag}_launches_raw.csv.gz"), "wt") as fh:
     fh.writelines(lines)
@@ -78,3 +82,24 @@ if os.path.exists(rep3):
         fh.write(",".join(f"{w} [{units[i]}]" for w, i in idx) + "\n")
         for r in rows[2:]:
             fh.write(",".join('"' + r[i].replace('"', "'")[:80] + '"' if w == "Kernel Name" else r[i].replace(",", "") for w, i in idx) + "\n")
+
+
+# 5. dfm_gemm3 (DNN tower GEMMs): the three products of the first layer at the bench shape
+rep5 = os.path.join(src, f"prof_{tag}_gemm3.ncu-rep")
+if os.path.exists(rep5):
+    raw = subprocess.run(["ncu", "-i", rep5, "--page", "raw", "--csv"], capture_output=True, text=True).stdout
+    rows = list(csv.reader(raw.splitlines()))
+    hdr, units = rows[0], rows[1]
+    want5 = want + ["sm__pipe_tensor_cycles_active.avg.pct_of_peak_sustained_elapsed", "l1tex__m_xbar2l1tex_read_bytes.sum",
+                    "l1tex__m_xbar2l1tex_read_bytes.sum.per_second", "l1tex__data_pipe_tc_wavefronts_mem_shared.sum.pct_of_peak_sustained_elapsed",
+                    "l1tex__data_pipe_lsu_wavefronts_mem_shared.sum.pct_of_peak_sustained_elapsed", "lts__throughput.avg.pct_of_peak_sustained_elapsed",
+                    "smsp__average_warps_issue_stalled_mio_throttle_per_issue_active.ratio", "smsp__average_warps_issue_stalled_lg_throttle_per_issue_active.ratio",
+                    "smsp__average_warps_issue_stalled_short_scoreboard_per_issue_active.ratio", "smsp__average_warps_issue_stalled_long_scoreboard_per_issue_active.ratio"]
+    idx = [(w, hdr.index(w)) for w in want5 if w in hdr]
+    with open(os.path.join(dst, f"{tag}_ncu_gemm3.csv"), "w") as fh:
+        fh.write("# ncu --set full --clock-control none --import-source on -k regex:gemm3_kernel : python scripts/ncu_gemm3.py "
+                 "(B=65536, 2496->256: launches = forward Y=XW^T, dX=dY W, dW=dY^T X)\n")
+        fh.write(",".join(f"{w} [{units[i]}]" for w, i in idx) + "\n")
+        for r in rows[2:]:
+            fh.write(",".join('"' + r[i].replace('"', "'")[:60] + '"' if w == "Kernel Name" else r[i].replace(",", "") for w, i in idx) + "\n")
+    print(open(os.path.join(dst, f"{tag}_ncu_gemm3.csv")).read()[:2500])
