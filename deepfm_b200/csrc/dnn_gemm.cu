@@ -55,6 +55,7 @@ struct Args {
     int tma_store;                       // 1: the epilogue stages 32 x 32 boxes in shared memory and stores them by TMA
                                          // (coalesced 128-byte rows; a thread-per-row float4 store touches 32 half-written
                                          // sectors per instruction and made the LSU the bound of every small-K product)
+    int transpose_out;                   // 1: the tile is stored transposed (D[n][m]): the swapped weight-gradient product
     uint32_t tmem_cols;
 };
 constexpr int EPI_BYTES = 4 * 2 * 4096; // 4 promoter warps x 2 buffers x (32 rows x 128 B)
@@ -311,13 +312,24 @@ gemm3_kernel(const __grid_constant__ Args a, const __grid_constant__ CUtensorMap
                         unsigned char* buf = wbuf + (n_stores++ & 1u) * 4096;
                         if (lane == 0) tma_store_wait_read<1>();       // the store that last read this buffer (two groups ago)
                         __syncwarp();
+                        if (a.transpose_out) {
+                            // box rows = n (32 columns of the tile), box columns = m (this warp's 32 rows): lane m writes
+                            // element (n = i, m) -- 32 consecutive floats per instruction, chunk (m / 4) ^ (n & 7)
 #pragma unroll
-                        for (int i = 0; i < 8; ++i)
-                            *reinterpret_cast<float4*>(buf + lane * 128 + ((i ^ (lane & 7)) << 4)) =
-                                make_float4(macc[c * 32 + 4 * i], macc[c * 32 + 4 * i + 1], macc[c * 32 + 4 * i + 2], macc[c * 32 + 4 * i + 3]);
+                            for (int i = 0; i < 32; ++i)
+                                *reinterpret_cast<float*>(buf + i * 128 + ((((lane >> 2) ^ (i & 7)) << 4) | ((lane & 3) << 2))) = macc[c * 32 + i];
+                        } else {
+#pragma unroll
+                            for (int i = 0; i < 8; ++i)
+                                *reinterpret_cast<float4*>(buf + lane * 128 + ((i ^ (lane & 7)) << 4)) =
+                                    make_float4(macc[c * 32 + 4 * i], macc[c * 32 + 4 * i + 1], macc[c * 32 + 4 * i + 2], macc[c * 32 + 4 * i + 3]);
+                        }
                         fence_proxy_async();
                         __syncwarp();
-                        if (lane == 0) tma_store_3d(&mapD, buf, (int)col0, mt * TM + q * 32, sp);
+                        if (lane == 0) {
+                            if (a.transpose_out) tma_store_3d(&mapD, buf, mt * TM + q * 32, (int)col0, sp);
+                            else tma_store_3d(&mapD, buf, (int)col0, mt * TM + q * 32, sp);
+                        }
                     }
                 }
                 continue;
@@ -369,8 +381,9 @@ splitk_reduce_kernel(const float* __restrict__ partial, int n_split, long long s
 }
 
 struct Plan {
-    int tn, n_mt, n_nt, n_split, nstage, tma_store;
+    int tn, n_mt, n_nt, n_split, nstage, tma_store, swap;
     long long k_per_split;
+    size_t blo_off;
     size_t smem, ws_bytes;
     uint32_t tmem_cols;
 };
@@ -381,8 +394,19 @@ static int ts_all_enabled() {
     return v;
 }
 
+// mode 2 (weight gradient dW[M][N] = sum_k dY[k][M] X[k][N]) runs SWAPPED when the TMA-store epilogue is available: the
+// kernel computes dW^T = X^T dY (rows = N of the caller, columns = M) and stores every tile transposed.  The operand that
+// goes through the splitter warps and tensor memory is then X, and dY -- the small one (K x M floats) -- becomes the B
+// operand whose lo part is precomputed by one split_lo pass and arrives by TMA, exactly like the weights of modes 0 / 1:
+// the in-kernel split of a 16 KB B tile per k-block was what bounded the un-swapped product (tensor pipe 32 %).
 static int make_plan(int mode, long long M, long long N, long long K, Plan& p) {
     DFM_REQUIRE(mode >= 0 && mode <= 2 && M > 0 && N > 0 && K > 0, DFM_ERR_INVALID, "dfm_gemm3: bad mode / shape");
+    p.swap = 0;
+    if (mode == 2 && N % 4 == 0 && M % 4 == 0) {
+        const char* e = getenv("DFM_G3_TMA_STORE");
+        const char* w = getenv("DFM_G3_DW_SWAP");
+        if (!(e && e[0] == '0') && !(w && w[0] == '0')) { p.swap = 1; const long long t = M; M = N; N = t; }
+    }
     DFM_REQUIRE(M < (1LL << 31) && N < (1LL << 31) && K < (1LL << 31), DFM_ERR_UNSUPPORTED, "dfm_gemm3: dimension too large");
     // TMA needs 16-byte global strides: the contiguous extent of each operand must be a multiple of 4 floats
     const long long a_inner = mode == 2 ? M : K, b_inner = mode == 0 ? K : N;
@@ -418,7 +442,7 @@ static int make_plan(int mode, long long M, long long N, long long K, Plan& p) {
     const int a_cols = ts_all_enabled() ? 64 : 32;
     {   // TMA-store epilogue: 16-byte global strides (N % 4 == 0); DFM_G3_TMA_STORE=0 keeps the per-thread stores
         const char* e = getenv("DFM_G3_TMA_STORE");
-        p.tma_store = (N % 4 == 0 && !(e && e[0] == '0')) ? 1 : 0;
+        p.tma_store = ((p.swap ? M : N) % 4 == 0 && !(e && e[0] == '0')) ? 1 : 0;
     }
     const size_t fixed = fixed0 + (p.tma_store ? EPI_BYTES : 0);
     while (p.nstage > 2 && ((size_t)p.nstage * stage_bytes + fixed > 227 * 1024 || 2 * p.tn + p.nstage * a_cols > 512)) --p.nstage;
@@ -426,8 +450,9 @@ static int make_plan(int mode, long long M, long long N, long long K, Plan& p) {
     uint32_t cols = 32;
     while (cols < (uint32_t)(2 * p.tn + p.nstage * a_cols)) cols <<= 1;
     p.tmem_cols = cols;
-    p.ws_bytes = p.n_split > 1 ? (size_t)p.n_split * M * N * 4 : 0;
-    if (mode != 2) p.ws_bytes += align_up((size_t)N * K * 4, 256);      // B_lo of the weight operand
+    p.ws_bytes = p.n_split > 1 ? align_up((size_t)p.n_split * M * N * 4, 256) : 0;
+    p.blo_off = p.ws_bytes;
+    if (mode != 2 || p.swap) p.ws_bytes += align_up((size_t)N * K * 4, 256);      // B_lo of the weight / dY operand
     return DFM_OK;
 }
 
@@ -457,18 +482,24 @@ int dfm_gemm3(int mode, const float* A, const float* B, float* D, const float* b
                 "dfm_gemm3: workspace %zu < %zu", workspace_bytes, p.ws_bytes);
     DFM_REQUIRE(p.n_split == 1 || !bias, DFM_ERR_UNSUPPORTED, "dfm_gemm3: bias with split-K is not supported");
     cudaStream_t st = static_cast<cudaStream_t>(stream);
+    if (p.swap) {                       // internal product: rows = the caller's N (operand B), columns = the caller's M (operand A)
+        const float* t = A; A = B; B = t;
+        const int64_t m = M; M = N; N = m;
+    }
     Args a;
     memset(&a, 0, sizeof(a));
+    a.transpose_out = p.swap;
     a.M = M; a.N = N; a.K = K; a.tn = p.tn; a.n_mt = p.n_mt; a.n_nt = p.n_nt; a.n_split = p.n_split;
     a.k_per_split = p.k_per_split; a.nstage = p.nstage; a.tmem_cols = p.tmem_cols;
     a.a_mn = mode == 2 ? 1 : 0; a.b_mn = mode == 0 ? 0 : 1;
     a.mask_hi = getenv("DFM_G3_MASK") ? 1 : 0;
-    a.b_lo_tma = (mode != 2 && !getenv("DFM_G3_SPLIT_B_IN_KERNEL")) ? 1 : 0;
+    a.b_lo_tma = ((mode != 2 || p.swap) && !getenv("DFM_G3_SPLIT_B_IN_KERNEL")) ? 1 : 0;
     a.ts_all = ts_all_enabled();
     a.tma_store = p.tma_store;
     a.bias = bias;
-    if (p.n_split > 1) { a.D = static_cast<float*>(workspace); a.ldd = N; a.split_stride = M * N; }
-    else { a.D = D; a.ldd = N; a.split_stride = 0; }
+    // (transposed output: the stored matrix is [N][M], row stride M)
+    if (p.n_split > 1) { a.D = static_cast<float*>(workspace); a.ldd = p.swap ? M : N; a.split_stride = M * N; }
+    else { a.D = D; a.ldd = p.swap ? M : N; a.split_stride = 0; }
     CUtensorMap mapA, mapB;
     // K-major operand [rows][K]: box {32 k, rows};  MN-major operand [K][MN]: box {32 mn, 32 k}
     rc = a.a_mn ? tc::make_tmap_2d(&mapA, A, K, M, 32, true) : tc::make_tmap_2d(&mapA, A, M, K, TM);
@@ -477,7 +508,7 @@ int dfm_gemm3(int mode, const float* A, const float* B, float* D, const float* b
     if (rc) return rc;
     CUtensorMap mapBlo = mapB;
     if (a.b_lo_tma) {
-        float* blo = static_cast<float*>(workspace);      // mode 0 / 1 never split K: the workspace is all ours
+        float* blo = reinterpret_cast<float*>(static_cast<char*>(workspace) + p.blo_off);   // behind the split-K partials
         const long long nb = N * K;
         long long blocks = ceil_div(nb, 256 * 4);
         if (blocks > 4LL * sm_count()) blocks = 4LL * sm_count();
@@ -488,7 +519,8 @@ int dfm_gemm3(int mode, const float* A, const float* B, float* D, const float* b
     CUtensorMap mapD = mapA;
     if (a.tma_store) {
         DFM_REQUIRE((reinterpret_cast<uintptr_t>(a.D) & 15u) == 0, DFM_ERR_UNSUPPORTED, "dfm_gemm3: output must be 16-byte aligned");
-        rc = tc::make_tmap_out_3d(&mapD, a.D, p.n_split, M, N, a.ldd, a.split_stride);
+        rc = p.swap ? tc::make_tmap_out_3d(&mapD, a.D, p.n_split, N, M, a.ldd, a.split_stride)
+                    : tc::make_tmap_out_3d(&mapD, a.D, p.n_split, M, N, a.ldd, a.split_stride);
         if (rc) return rc;
     }
     DFM_CHECK_CUDA(cudaFuncSetAttribute(gemm3_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)p.smem));
