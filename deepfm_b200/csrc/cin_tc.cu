@@ -11,6 +11,8 @@
 // back to the producers through mbarriers.  The epilogue reads the accumulators with
 // `tcgen05.ld.32x32b`, adds the bias, applies ReLU and writes the (B, L, D) activation.
 // Persistent grid: one CTA per SM walks 256-row super-tiles.
+#include <stdlib.h>
+
 #include "tc_common.cuh"
 
 namespace dfm {
@@ -48,7 +50,12 @@ __global__ void cin_pad_w_kernel(const float* __restrict__ w, int L, int H, int 
 // A_TMEM = true: the synthesised A tiles go registers -> tensor memory (tcgen05.st) and the MMA reads A from
 // TMEM, B from shared memory: shared-memory traffic per k-block drops from 144 KB to 80 KB (the SS form
 // at N = 128 is shared-memory-bandwidth bound).  Needs 2*Np + NSTAGE*64 <= 512 TMEM columns (Np <= 128).
-template <bool A_TMEM>
+// SFP (static FP): 40 (F = 37..40, the Criteo shapes) or 16 (F <= 16, the ML-100K shapes) -- with A_TMEM the thread's whole
+// x0 row then lives in REGISTERS and the (h, f) of every k of a k-block is a compile-time constant of the k-block's
+// position in the period lcm(32, FP) / 32 (5 k-blocks for FP = 40, 1 for FP = 16): a k-block costs the producer 32 FMUL +
+// one tcgen05.st instead of 8 LDS.128 + ~150 instructions of index arithmetic and selects (267 -> ~60 warp instructions per
+// warp per k-block against a 512-cycle MMA budget).  SFP = 0: the generic loop (x0 row in shared memory).
+template <bool A_TMEM, int SFP>
 __global__ void __launch_bounds__(THREADS, 1)
 cin_tc_fwd_kernel(const __grid_constant__ CinTcArgs a, const __grid_constant__ CUtensorMap wmap) {
     extern __shared__ unsigned char smem_raw[];
@@ -101,6 +108,7 @@ cin_tc_fwd_kernel(const __grid_constant__ CinTcArgs a, const __grid_constant__ C
             const float* xrow = a.x0 + b * a.x_bs + d;
             const float* hrow = a.hid + b * a.h_bs + d;
             float* xr = s_x0 + (size_t)r * FPS;          // this thread's x0 row, zero padded to FP
+            if (!(A_TMEM && SFP > 0))
             for (int f0 = 0; f0 < a.FP; f0 += 8) {       // 8 independent loads in flight, then 2 STS.128
                 float t[8];
 #pragma unroll
@@ -108,6 +116,45 @@ cin_tc_fwd_kernel(const __grid_constant__ CinTcArgs a, const __grid_constant__ C
                 *reinterpret_cast<float4*>(xr + f0) = make_float4(t[0], t[1], t[2], t[3]);
                 if (f0 + 4 < a.FP) *reinterpret_cast<float4*>(xr + f0 + 4) = make_float4(t[4], t[5], t[6], t[7]);
             }
+            if (A_TMEM && SFP > 0) {
+                constexpr int FPc = SFP > 0 ? SFP : 32;
+                constexpr int PER = FPc == 40 ? 5 : 1;                 // k-blocks per period
+                constexpr int HPP = PER * 32 / FPc;                    // h values per period (4 for FP = 40, 2 for FP = 16)
+                float xreg[FPc];
+#pragma unroll
+                for (int f = 0; f < FPc; ++f) xreg[f] = (live && f < a.F) ? __ldg(xrow + (size_t)f * a.D) : 0.f;
+                auto ldh = [&](int hh) { return (live && hh < a.H) ? __ldg(hrow + (size_t)hh * a.D) : 0.f; };
+                float hw[HPP], hnext[HPP];
+#pragma unroll
+                for (int i = 0; i < HPP; ++i) hw[i] = ldh(i);
+                for (int kb0 = 0, hb = 0; kb0 < n_kb; kb0 += PER, hb += HPP) {
+#pragma unroll
+                    for (int i = 0; i < HPP; ++i) hnext[i] = ldh(hb + HPP + i);      // next period's h values, one period ahead
+#pragma unroll
+                    for (int pp = 0; pp < PER; ++pp) {
+                        if (kb0 + pp >= n_kb) break;                   // uniform over the CTA
+                        mbar_wait(empty + s, ph ^ 1u);
+                        if (r == 0) {
+                            mbar_arrive_expect_tx(full + s, (uint32_t)a.Np * 128u);
+                            tma_load_2d(stage0 + (size_t)s * stage_bytes + a_bytes, &wmap, (kb0 + pp) * KB, 0, full + s);
+                        }
+                        float z[32];
+#pragma unroll
+                        for (int k = 0; k < 32; ++k) {
+                            constexpr int dummy = 0; (void)dummy;
+                            const int kk = pp * 32 + k;                // position inside the period: compile-time after unrolling
+                            z[k] = hw[kk / FPc] * xreg[kk % FPc];
+                        }
+                        tmem_st32(tmem_base + ((uint32_t)((warp & 3) * 32) << 16) + a_col0 + s * 64 + tile * 32, z);
+                        tc_fence_before();
+                        __syncwarp();
+                        if (lane == 0) mbar_arrive(full + s);
+                        if (++s == (uint32_t)a.nstage) { s = 0; ph ^= 1u; }
+                    }
+#pragma unroll
+                    for (int i = 0; i < HPP; ++i) hw[i] = hnext[i];
+                }
+            } else {
             // hidden values of the current and the next two h (a k-block of 32 spans at most 3: FP >= 16)
             int h = 0, f4 = 0;
             auto ldh = [&](int hh) { return (live && hh < a.H) ? __ldg(hrow + (size_t)hh * a.D) : 0.f; };
@@ -160,6 +207,7 @@ cin_tc_fwd_kernel(const __grid_constant__ CinTcArgs a, const __grid_constant__ C
                 if (lane == 0) mbar_arrive(full + s);
                 if (++s == (uint32_t)a.nstage) { s = 0; ph ^= 1u; }
             }
+            }   // generic producer loop
             // ---- epilogue: TMEM -> registers -> bias + ReLU -> act[b][l][d]
             mbar_wait(acc_full, acc_phase);
             acc_phase ^= 1u;
@@ -243,16 +291,21 @@ int cin_layer_fwd_tc(const float* x0, long long x_bs, const float* hid, long lon
     a.nstage = nstage;
     const size_t smem = (size_t)nstage * stage_bytes + fixed;
     DFM_REQUIRE(smem <= 227 * 1024, DFM_ERR_UNSUPPORTED, "cin tcgen05: %d fields need %zu B shared memory", F, smem);
-    DFM_CHECK_CUDA(cudaFuncSetAttribute(cin_tc_fwd_kernel<true>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
-    DFM_CHECK_CUDA(cudaFuncSetAttribute(cin_tc_fwd_kernel<false>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
+    DFM_CHECK_CUDA(cudaFuncSetAttribute(cin_tc_fwd_kernel<true, 0>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
+    DFM_CHECK_CUDA(cudaFuncSetAttribute(cin_tc_fwd_kernel<true, 40>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
+    DFM_CHECK_CUDA(cudaFuncSetAttribute(cin_tc_fwd_kernel<true, 16>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
+    DFM_CHECK_CUDA(cudaFuncSetAttribute(cin_tc_fwd_kernel<false, 0>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
     long long grid = ceil_div(a.M, ROWS);
     if (grid > sm_count()) grid = sm_count();
     // tensor map of the padded weight: (Kp inner, Np outer) fp32, box 32 x Np, 128-byte swizzle
     CUtensorMap wmap;
     int rc = make_tmap_2d(&wmap, wpad, Np, Kp, Np);
     if (rc) return rc;
-    if (a_tmem) cin_tc_fwd_kernel<true><<<(unsigned)grid, THREADS, smem, st>>>(a, wmap);
-    else cin_tc_fwd_kernel<false><<<(unsigned)grid, THREADS, smem, st>>>(a, wmap);
+    const bool stat = getenv("DFM_CIN_GENERIC") == nullptr;
+    if (a_tmem && stat && FP == 40) cin_tc_fwd_kernel<true, 40><<<(unsigned)grid, THREADS, smem, st>>>(a, wmap);
+    else if (a_tmem && stat && FP == 16) cin_tc_fwd_kernel<true, 16><<<(unsigned)grid, THREADS, smem, st>>>(a, wmap);
+    else if (a_tmem) cin_tc_fwd_kernel<true, 0><<<(unsigned)grid, THREADS, smem, st>>>(a, wmap);
+    else cin_tc_fwd_kernel<false, 0><<<(unsigned)grid, THREADS, smem, st>>>(a, wmap);
     DFM_CHECK_LAUNCH();
     return DFM_OK;
 }
