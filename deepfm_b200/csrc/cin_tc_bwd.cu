@@ -309,10 +309,12 @@ namespace dfm {
 namespace tc {
 
 constexpr int DW_NSTAGE = 4;
-constexpr int DW_PD = 4;                        // prefetch distance of the producers' global loads, in k-blocks
+constexpr int DW_RB = 64;                       // reduction rows per k-block (stage): 2 TMA boxes of 32, 8 MMAs of K = 8
+constexpr int DW_PD = 2;                        // prefetch distance of the producers' global loads, in k-blocks
+constexpr int DW_NQ = 5;                        // staged quads per producer thread and k-block: (nh + F) * 16 <= 5 * 256
 constexpr int DW_PRODUCERS = 256;
 constexpr int DW_THREADS = DW_PRODUCERS + 64;   // + MMA warp + TMA warp
-constexpr int SLAB = 36;                        // floats per staged channel row: 32 r + 4 pad (bank spread)
+constexpr int SLAB = DW_RB + 4;                 // floats per staged channel row: 64 r + 4 pad (bank spread)
 
 __device__ __forceinline__ void tmem_st16(uint32_t addr, const float* v) {
     const uint32_t* r = reinterpret_cast<const uint32_t*>(v);
@@ -330,6 +332,7 @@ struct DwTcArgs {
     float* part;                 // (n_slices, Kt, Lp)   Kt = n_ktiles * 128
     long long M, slice_rows;
     int F, FP, H, D, Lp, Kt;
+    int nstage;                  // B / A ring depth (<= DW_NSTAGE; fewer when Lp = 256 fills the shared memory)
 };
 
 __global__ void __launch_bounds__(DW_THREADS, 1)
@@ -337,13 +340,14 @@ cin_tc_dw_kernel(const __grid_constant__ DwTcArgs a, const __grid_constant__ CUt
     extern __shared__ unsigned char smem_raw[];
     unsigned char* smem = smem_raw + ((1024u - (smem_u32(smem_raw) & 1023u)) & 1023u);
     const int ktile = blockIdx.x, slice = blockIdx.y;
-    const int b_stage = (a.Lp * 128 + 1023) & ~1023;
+    const int b_box = (a.Lp * 128 + 1023) & ~1023;          // one TMA box: 32 r x Lp rows
+    const int b_stage = (DW_RB / 32) * b_box;
     const int h_lo = (ktile * 128) / a.FP;
     const int h_hi = (ktile * 128 + 127) / a.FP;
     const int nh = h_hi - h_lo + 1;
     const int nch = nh + a.F;                               // staged channels: nh hidden rows, then F x0 rows
     unsigned char* sB = smem;
-    float* slab = reinterpret_cast<float*>(smem + (size_t)DW_NSTAGE * b_stage);          // [2][nch][SLAB]
+    float* slab = reinterpret_cast<float*>(smem + (size_t)a.nstage * b_stage);           // [2][nch][SLAB]
     uint64_t* bars = reinterpret_cast<uint64_t*>(slab + (size_t)2 * nch * SLAB);
     uint64_t* full = bars;                   // [DW_NSTAGE] 8 producer warps + TMA
     uint64_t* empty = bars + DW_NSTAGE;      // [DW_NSTAGE] MMA commit
@@ -364,7 +368,7 @@ cin_tc_dw_kernel(const __grid_constant__ DwTcArgs a, const __grid_constant__ CUt
     const uint32_t a_col0 = (uint32_t)a.Lp;                 // A ring behind the accumulator
     const long long r_lo = (long long)slice * a.slice_rows;
     const long long r_hi = (r_lo + a.slice_rows < a.M) ? r_lo + a.slice_rows : a.M;
-    const int n_kb = (int)((r_hi - r_lo + 31) / 32);
+    const int n_kb = (int)((r_hi - r_lo + DW_RB - 1) / DW_RB);
     const uint32_t idesc = (1u << 4) | (2u << 7) | (2u << 10) | ((uint32_t)(a.Lp >> 3) << 17) | ((128u >> 4) << 24);
 
     if (warp < 8) {
@@ -373,21 +377,22 @@ cin_tc_dw_kernel(const __grid_constant__ DwTcArgs a, const __grid_constant__ CUt
         const int kp = ktile * 128 + row;
         const int h = kp / a.FP, f = kp - h * a.FP;
         const bool row_ok = h < a.H && f < a.F;
-        const int hs = (h - h_lo) * SLAB + half * 16, xs = (nh + f) * SLAB + half * 16;
+        const int hs = (h - h_lo) * SLAB + half * (DW_RB / 2), xs = (nh + f) * SLAB + half * (DW_RB / 2);
         // slab staging assignment: quads of 4 consecutive r of one channel.  Loads are issued DW_PD k-blocks ahead of
         // their use (registers pre[j][u]): one k-block is only 4 MMAs = 256 tensor cycles, a global / L2 load takes
         // ~1000, so a prefetch distance of one k-block left the tensor pipe idle 85 % of the time.  Addresses advance
         // incrementally (b, d += 32 rows per k-block): no division in the loop.
-        const int n_quads = nch * 8;
-        const float* qbase[3];      // channel base pointer (hidden row h_lo + c, or x0 row c - nh); null = all-zero channel
-        long long qbs[3];           // batch stride of that tensor
-        long long qb[3];            // sample index of the NEXT load of this quad
-        int qd[3];                  // d of the next load
-        long long qr[3];            // global row r of the next load
+        constexpr int QPC = DW_RB / 4;       // quads per channel
+        const int n_quads = nch * QPC;
+        const float* qbase[DW_NQ];  // channel base pointer (hidden row h_lo + c, or x0 row c - nh); null = all-zero channel
+        long long qbs[DW_NQ];       // batch stride of that tensor
+        long long qb[DW_NQ];        // sample index of the NEXT load of this quad
+        int qd[DW_NQ];              // d of the next load
+        long long qr[DW_NQ];        // global row r of the next load
 #pragma unroll
-        for (int u = 0; u < 3; ++u) {
+        for (int u = 0; u < DW_NQ; ++u) {
             const int idx = t + u * DW_PRODUCERS;
-            const int c = idx >> 3, q = idx & 7;
+            const int c = idx / QPC, q = idx % QPC;
             const bool ok = idx < n_quads && !(c < nh && h_lo + c >= a.H);
             qbase[u] = !ok ? nullptr : (c < nh ? a.hid + (size_t)(h_lo + c) * a.D : a.x0 + (size_t)(c - nh) * a.D);
             qbs[u] = c < nh ? a.h_bs : a.x_bs;
@@ -398,16 +403,16 @@ cin_tc_dw_kernel(const __grid_constant__ DwTcArgs a, const __grid_constant__ CUt
         auto next_quad = [&](int u) -> float4 {          // load the quad at (qb, qd), then advance it by one k-block (32 rows)
             float4 v = make_float4(0.f, 0.f, 0.f, 0.f);
             if (qbase[u] && qr[u] < r_hi) v = __ldg(reinterpret_cast<const float4*>(qbase[u] + qb[u] * qbs[u] + qd[u]));
-            qr[u] += 32;
-            qd[u] += 32;
+            qr[u] += DW_RB;
+            qd[u] += DW_RB;
             while (qd[u] >= a.D) { qd[u] -= a.D; ++qb[u]; }
             return v;
         };
-        float4 pre[DW_PD][3];
+        float4 pre[DW_PD][DW_NQ];
 #pragma unroll
         for (int j = 0; j < DW_PD; ++j)
 #pragma unroll
-            for (int u = 0; u < 3; ++u) pre[j][u] = next_quad(u);       // k-blocks beyond the slice read as zeros (r >= r_hi)
+            for (int u = 0; u < DW_NQ; ++u) pre[j][u] = next_quad(u);   // k-blocks beyond the slice read as zeros (r >= r_hi)
         uint32_t s = 0, ph = 0;
         for (int kb0 = 0; kb0 < n_kb; kb0 += DW_PD) {
 #pragma unroll
@@ -416,31 +421,31 @@ cin_tc_dw_kernel(const __grid_constant__ DwTcArgs a, const __grid_constant__ CUt
             if (kb >= n_kb) break;                           // uniform over the 256 producers
             float* sl = slab + (size_t)(kb & 1) * nch * SLAB;
 #pragma unroll
-            for (int u = 0; u < 3; ++u) {
+            for (int u = 0; u < DW_NQ; ++u) {
                 const int idx = t + u * DW_PRODUCERS;
-                if (idx < n_quads) *reinterpret_cast<float4*>(sl + (idx >> 3) * SLAB + (idx & 7) * 4) = pre[j][u];
+                if (idx < n_quads) *reinterpret_cast<float4*>(sl + (idx / QPC) * SLAB + (idx % QPC) * 4) = pre[j][u];
             }
             producer_bar();                                  // slab kb complete (slab kb-1 was consumed before its own bar)
 #pragma unroll
-            for (int u = 0; u < 3; ++u) pre[j][u] = next_quad(u);      // k-block kb + DW_PD
-            float z[16];
+            for (int u = 0; u < DW_NQ; ++u) pre[j][u] = next_quad(u);  // k-block kb + DW_PD
+            float z[DW_RB / 2];
             if (row_ok) {
 #pragma unroll
-                for (int q = 0; q < 4; ++q) {
+                for (int q = 0; q < DW_RB / 8; ++q) {
                     const float4 hv = *reinterpret_cast<const float4*>(sl + hs + 4 * q);
                     const float4 xv = *reinterpret_cast<const float4*>(sl + xs + 4 * q);
                     z[4 * q] = hv.x * xv.x; z[4 * q + 1] = hv.y * xv.y; z[4 * q + 2] = hv.z * xv.z; z[4 * q + 3] = hv.w * xv.w;
                 }
             } else {
 #pragma unroll
-                for (int i = 0; i < 16; ++i) z[i] = 0.f;
+                for (int i = 0; i < DW_RB / 2; ++i) z[i] = 0.f;
             }
             mbar_wait(empty + s, ph ^ 1u);
-            tmem_st16(tmem_base + ((uint32_t)((warp & 3) * 32) << 16) + a_col0 + s * 32 + half * 16, z);
+            tmem_st32(tmem_base + ((uint32_t)((warp & 3) * 32) << 16) + a_col0 + s * DW_RB + half * (DW_RB / 2), z);
             tc_fence_before();
             __syncwarp();
             if (lane == 0) mbar_arrive(full + s);
-            if (++s == DW_NSTAGE) { s = 0; ph ^= 1u; }
+            if (++s == (uint32_t)a.nstage) { s = 0; ph ^= 1u; }
           }
         }
         // ---------------------------------------------------------------- epilogue (warps 0-3: lane = k' row)
@@ -461,9 +466,11 @@ cin_tc_dw_kernel(const __grid_constant__ DwTcArgs a, const __grid_constant__ CUt
         uint32_t s = 0, ph = 0;
         for (int kb = 0; kb < n_kb; ++kb) {
             mbar_wait(empty + s, ph ^ 1u);
-            mbar_arrive_expect_tx(full + s, (uint32_t)a.Lp * 128u);
-            tma_load_2d(sB + (size_t)s * b_stage, &gmap, (int)(r_lo + (long long)kb * 32), 0, full + s);
-            if (++s == DW_NSTAGE) { s = 0; ph ^= 1u; }
+            mbar_arrive_expect_tx(full + s, (uint32_t)(DW_RB / 32) * (uint32_t)a.Lp * 128u);
+#pragma unroll
+            for (int bx = 0; bx < DW_RB / 32; ++bx)       // rows beyond M are zero-filled by the TMA unit
+                tma_load_2d(sB + (size_t)s * b_stage + (size_t)bx * b_box, &gmap, (int)(r_lo + (long long)kb * DW_RB + 32 * bx), 0, full + s);
+            if (++s == (uint32_t)a.nstage) { s = 0; ph ^= 1u; }
         }
     } else if (warp == 8 && lane == 0) {
         // ---------------------------------------------------------------- MMA issuer
@@ -471,12 +478,13 @@ cin_tc_dw_kernel(const __grid_constant__ DwTcArgs a, const __grid_constant__ CUt
         for (int kb = 0; kb < n_kb; ++kb) {
             mbar_wait(full + s, ph);
             tc_fence_after();
-            const uint64_t db = make_desc(smem_u32(sB + (size_t)s * b_stage));
 #pragma unroll
-            for (int k = 0; k < 4; ++k)
-                umma_tf32_ts(tmem_base, tmem_base + a_col0 + s * 32 + k * 8, db + (uint64_t)(k * 2), idesc, (kb | k) ? 1u : 0u);
+            for (int k = 0; k < DW_RB / 8; ++k) {
+                const uint64_t db = make_desc(smem_u32(sB + (size_t)s * b_stage + (size_t)(k >> 2) * b_box));
+                umma_tf32_ts(tmem_base, tmem_base + a_col0 + s * DW_RB + k * 8, db + (uint64_t)((k & 3) * 2), idesc, (kb | k) ? 1u : 0u);
+            }
             umma_commit(empty + s);
-            if (++s == DW_NSTAGE) { s = 0; ph ^= 1u; }
+            if (++s == (uint32_t)a.nstage) { s = 0; ph ^= 1u; }
         }
         umma_commit(acc_full);
     }
@@ -618,7 +626,9 @@ __global__ void cin_db_final_kernel(const float* __restrict__ part, int n, int L
 }  // namespace tc
 
 static int dw_tc_slices(long long M, int n_ktiles) {
-    long long want = ceil_div(2LL * sm_count(), n_ktiles);
+    // one CTA per SM (shared-memory bound): k-tiles x slices must not spill into a third, nearly empty wave
+    // (20 k-tiles x ceil(296 / 20) = 300 CTAs ran 3 rounds on 148 SMs: tensor pipe 30 % active but 20 % elapsed)
+    long long want = (2LL * sm_count()) / n_ktiles;
     long long max_s = ceil_div(M, 4096);
     if (want > max_s) want = max_s;
     if (want < 1) want = 1;
@@ -643,7 +653,9 @@ bool cin_tc_bwd_supported(long long B, int F, int H, int D, int L) {
     const size_t a_bytes = (size_t)(Lp / 32) * 128 * 128, b_stage = ((size_t)NT * 128 + 1023) & ~(size_t)1023;
     if (a_bytes + b_stage + 256 + 1024 > 227 * 1024) return false;
     const int nh_max = 127 / FP + 2;
-    const size_t smem = (size_t)tc::DW_NSTAGE * ((Lp * 128 + 1023) & ~1023) + (size_t)2 * (nh_max + F) * tc::SLAB * 4 + 256 + 1024;
+    // dW kernel: at least 2 stages of (DW_RB / 32) boxes + the double-buffered slab, and the staging assignment must fit
+    const size_t smem = (size_t)2 * (tc::DW_RB / 32) * ((Lp * 128 + 1023) & ~1023) + (size_t)2 * (nh_max + F) * tc::SLAB * 4 + 256 + 1024;
+    if ((nh_max + F) * (tc::DW_RB / 4) > tc::DW_NQ * tc::DW_PRODUCERS) return false;
     return smem <= 227 * 1024 && (size_t)L * (D + 1) * 4 <= 64 * 1024;
 }
 
@@ -677,7 +689,7 @@ int cin_layer_dw_tc(const float* g_pre, const float* x0, long long x_bs, const f
     const long long M = B * D;
     const int n_ktiles = (int)ceil_div((long long)H * FP, 128), Kt = n_ktiles * 128;
     const int ns = dw_tc_slices(M, n_ktiles);
-    const long long slice_rows = ceil_div(ceil_div(M, ns), 32) * 32;
+    const long long slice_rows = ceil_div(ceil_div(M, ns), DW_RB) * DW_RB;
     const int real_slices = (int)ceil_div(M, slice_rows);
     float* gLM = scratch;
     float* part = scratch + (((size_t)Lp * M + 63) & ~(size_t)63);
@@ -693,7 +705,13 @@ int cin_layer_dw_tc(const float* g_pre, const float* x0, long long x_bs, const f
     a.x0 = x0; a.x_bs = x_bs; a.hid = hid; a.h_bs = h_bs; a.part = part; a.M = M; a.slice_rows = slice_rows;
     a.F = F; a.FP = FP; a.H = H; a.D = D; a.Lp = Lp; a.Kt = Kt;
     const int nh_max = 127 / FP + 2;
-    const size_t smem = (size_t)DW_NSTAGE * ((Lp * 128 + 1023) & ~1023) + (size_t)2 * (nh_max + F) * SLAB * 4 + 256 + 1024;
+    DFM_REQUIRE((nh_max + F) * (DW_RB / 4) <= DW_NQ * DW_PRODUCERS, DFM_ERR_UNSUPPORTED, "cin tcgen05 dW: %d staged channels", nh_max + F);
+    const size_t b_stage = (size_t)(DW_RB / 32) * ((Lp * 128 + 1023) & ~1023);
+    const size_t fixed = (size_t)2 * (nh_max + F) * SLAB * 4 + 256 + 1024;
+    int nstage = DW_NSTAGE;
+    while (nstage > 2 && ((size_t)nstage * b_stage + fixed > 227 * 1024 || Lp + nstage * DW_RB > 512)) --nstage;
+    a.nstage = nstage;
+    const size_t smem = (size_t)nstage * b_stage + fixed;
     DFM_REQUIRE(smem <= 227 * 1024, DFM_ERR_UNSUPPORTED, "cin tcgen05 dW: %zu B shared memory", smem);
     DFM_CHECK_CUDA(cudaFuncSetAttribute(cin_tc_dw_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
     cin_tc_dw_kernel<<<dim3(n_ktiles, real_slices), DW_THREADS, smem, st>>>(a, gmap);
