@@ -44,12 +44,19 @@ __device__ __forceinline__ float act_df(float z, int act) {
     }
 }
 // counter-based uniform in [0, 1): splitmix64 of (seed, element index) -- the backward regenerates the same mask
-__device__ __forceinline__ float u01(unsigned long long seed, unsigned long long idx) {
-    unsigned long long z = seed + (idx + 1ull) * 0x9E3779B97F4A7C15ull;
+// One splitmix64 per FOUR consecutive elements (16 bits each: the keep decision has a resolution of 1 / 65536): the three
+// 64-bit multiplies per element were a third of the instructions of every element-wise pass.
+__device__ __forceinline__ unsigned long long mix64(unsigned long long seed, unsigned long long idx4) {
+    unsigned long long z = seed + (idx4 + 1ull) * 0x9E3779B97F4A7C15ull;
     z = (z ^ (z >> 30)) * 0xBF58476D1CE4E5B9ull;
     z = (z ^ (z >> 27)) * 0x94D049BB133111EBull;
-    z ^= z >> 31;
-    return (float)(z >> 40) * (1.0f / 16777216.0f);
+    return z ^ (z >> 31);
+}
+__device__ __forceinline__ float u01_of(unsigned long long z, int field) {
+    return (float)((unsigned)(z >> (16 * field)) & 0xffffu) * (1.0f / 65536.0f);
+}
+__device__ __forceinline__ float u01(unsigned long long seed, unsigned long long idx) {
+    return u01_of(mix64(seed, idx >> 2), (int)(idx & 3ull));
 }
 
 struct Ew {                      // element-wise context of one layer
@@ -72,14 +79,14 @@ __device__ __forceinline__ float pre_act(const Ew& e, float y, int c, float& xha
 // A block owns SLAB_ROWS rows x (32 * VC) columns: thread (tx, ty) walks rows ty, ty + RT, ... of VC consecutive
 // columns (one 128-bit load when VC = 4), UR rows in flight; fp32 terms, fp64 running sums.
 template <int OP>
-__device__ __forceinline__ void colsum_term(const Ew& e, float y, float d, size_t i, int c, double& a0, double& a1) {
+__device__ __forceinline__ void colsum_term(const Ew& e, float y, float d, float u, int c, double& a0, double& a1) {
     if (OP == 0) {
         a0 += (double)y; a1 += (double)y * (double)y;
     } else if (OP == 1) {
         float xhat;
         const float z = pre_act(e, y, c, xhat);
         float g = d * act_df(z, e.act);
-        if (e.p > 0.f) g = u01(e.seed, i) >= e.p ? g * e.keep_scale : 0.f;
+        if (e.p > 0.f) g = u >= e.p ? g * e.keep_scale : 0.f;
         a0 += (double)g * (double)xhat; a1 += (double)g;
     } else {
         a0 += (double)d;
@@ -117,9 +124,15 @@ colsum_partial_kernel(const __grid_constant__ Ew e, const float* __restrict__ da
             for (int u = 0; u < UR; ++u) {
                 const long long rr = r + (long long)u * RT;
                 if (rr >= r1) break;
+                const size_t i0 = (size_t)rr * e.C + c0;
+                unsigned long long zr = 0ull;
+                if (OP == 1 && e.p > 0.f && VC == 4) zr = mix64(e.seed, i0 >> 2);       // c0 and C are multiples of 4 here
 #pragma unroll
-                for (int v = 0; v < VC; ++v)
-                    colsum_term<OP>(e, OP != 2 ? yv[u][v] : 0.f, OP != 0 ? dv[u][v] : 0.f, (size_t)rr * e.C + c0 + v, c0 + v, a0[v], a1[v]);
+                for (int v = 0; v < VC; ++v) {
+                    float uu = 0.f;
+                    if (OP == 1 && e.p > 0.f) uu = VC == 4 ? u01_of(zr, v) : u01(e.seed, i0 + v);
+                    colsum_term<OP>(e, OP != 2 ? yv[u][v] : 0.f, OP != 0 ? dv[u][v] : 0.f, uu, c0 + v, a0[v], a1[v]);
+                }
             }
         }
     }
@@ -195,17 +208,21 @@ template <int VE>
 __global__ void __launch_bounds__(256)
 bn_act_fwd_kernel(const __grid_constant__ Ew e, float* __restrict__ out) {
     const long long n = e.M * e.C / VE;
+    const bool small = n < 0x7fffffffLL;          // 32-bit column arithmetic (a 64-bit modulo per vector otherwise)
+    const unsigned cvec = (unsigned)(e.C / VE);
     for (long long iv = (long long)blockIdx.x * blockDim.x + threadIdx.x; iv < n; iv += (long long)gridDim.x * blockDim.x) {
         const long long i = iv * VE;
-        const int c = (int)(i % e.C);
+        const int c = small ? (int)(((unsigned)iv % cvec) * VE) : (int)(i % e.C);
         float y[VE], a[VE];
         if (VE == 4) { const float4 t = __ldcs(reinterpret_cast<const float4*>(e.y + i)); y[0] = t.x; y[1] = t.y; y[2] = t.z; y[3] = t.w; }
         else y[0] = __ldcs(e.y + i);
+        unsigned long long zr = 0ull;
+        if (e.p > 0.f && VE == 4) zr = mix64(e.seed, (unsigned long long)iv);
 #pragma unroll
         for (int v = 0; v < VE; ++v) {
             float xhat;
             a[v] = act_f(pre_act(e, y[v], c + v, xhat), e.act);
-            if (e.p > 0.f) a[v] = u01(e.seed, (unsigned long long)(i + v)) >= e.p ? a[v] * e.keep_scale : 0.f;
+            if (e.p > 0.f) a[v] = (VE == 4 ? u01_of(zr, v) : u01(e.seed, (unsigned long long)(i + v))) >= e.p ? a[v] * e.keep_scale : 0.f;
         }
         if (VE == 4) *reinterpret_cast<float4*>(out + i) = make_float4(a[0], a[1], a[2], a[3]);
         else out[i] = a[0];
@@ -219,11 +236,15 @@ __global__ void __launch_bounds__(256)
 bn_act_bwd_apply_kernel(const __grid_constant__ Ew e, const float* __restrict__ da, const float* __restrict__ dgamma,
                         const float* __restrict__ dbeta, float* __restrict__ dy) {
     const long long n = e.M * e.C / VE;
+    const bool small = n < 0x7fffffffLL;
+    const unsigned cvec = (unsigned)(e.C / VE);
     const float inv_m = 1.f / (float)e.M;
     for (long long iv = (long long)blockIdx.x * blockDim.x + threadIdx.x; iv < n; iv += (long long)gridDim.x * blockDim.x) {
         const long long i = iv * VE;
-        const int c = (int)(i % e.C);
+        const int c = small ? (int)(((unsigned)iv % cvec) * VE) : (int)(i % e.C);
         float y[VE], d[VE], g[VE];
+        unsigned long long zr = 0ull;
+        if (e.p > 0.f && VE == 4) zr = mix64(e.seed, (unsigned long long)iv);
         if (VE == 4) {
             const float4 t = __ldcs(reinterpret_cast<const float4*>(e.y + i)); y[0] = t.x; y[1] = t.y; y[2] = t.z; y[3] = t.w;
             const float4 u = __ldcs(reinterpret_cast<const float4*>(da + i)); d[0] = u.x; d[1] = u.y; d[2] = u.z; d[3] = u.w;
@@ -233,7 +254,7 @@ bn_act_bwd_apply_kernel(const __grid_constant__ Ew e, const float* __restrict__ 
             float xhat;
             const float z = pre_act(e, y[v], c + v, xhat);
             g[v] = d[v] * act_df(z, e.act);
-            if (e.p > 0.f) g[v] = u01(e.seed, (unsigned long long)(i + v)) >= e.p ? g[v] * e.keep_scale : 0.f;
+            if (e.p > 0.f) g[v] = (VE == 4 ? u01_of(zr, v) : u01(e.seed, (unsigned long long)(i + v))) >= e.p ? g[v] * e.keep_scale : 0.f;
             if (e.bn == BN_BATCH)
                 g[v] = __ldg(e.gamma + c + v) * __ldg(e.rstd + c + v) * (g[v] - __ldg(dbeta + c + v) * inv_m - xhat * __ldg(dgamma + c + v) * inv_m);
             else if (e.bn == BN_FIXED)
