@@ -33,6 +33,7 @@ import sys
 import threading
 import time
 
+
 ROOT = os.path.dirname(os.path.abspath(__file__))
 sys.path.insert(0, ROOT)
 
@@ -114,39 +115,67 @@ def base_line(args, n_gpus):
 
 # ------------------------------------------------------------------------------------ clocks
 class ClockSampler:
+    """SM clock and throttle reasons sampled DURING the timed regions -- INLINE, from the benchmark's own host thread between
+    steps (`poll()` every few steps: two NVML queries, ~50 us), while the launch queue is full and the GPU is busy.
+    History: `nvidia-smi -lms 100` as a subprocess (the recipe's line) stalled free-running multi-rank steps for 10-120 ms at
+    a time (spikes in the per-step times at N = 2 that vanish without the sampler); an in-process NVML thread polling every
+    50 ms still produced an occasional burst.  A handful of inline samples per region has not.  Falls back to one-shot
+    `nvidia-smi` calls when pynvml is missing."""
     FIELDS = ("clocks.sm,clocks.max.sm,clocks_event_reasons.hw_slowdown,clocks_event_reasons.hw_thermal_slowdown,"
               "clocks_event_reasons.sw_thermal_slowdown,clocks_event_reasons.sw_power_cap")
+    BITS = (("hw_slowdown", 0x8), ("hw_thermal_slowdown", 0x40), ("sw_thermal_slowdown", 0x20), ("sw_power_cap", 0x4))
 
     def __init__(self, index: int):
-        self.index, self.rows, self.proc = index, [], None
+        self.index, self.rows, self.mode = index, [], None
+        self.nv = self.handle = self.get_reasons = None
+        self.mx = None
 
     def start(self):
         try:
-            self.proc = subprocess.Popen(["nvidia-smi", f"--id={self.index}", f"--query-gpu={self.FIELDS}",
-                                          "--format=csv,noheader,nounits", "-lms", "100"],
-                                         stdout=subprocess.PIPE, stderr=subprocess.DEVNULL, text=True)
-            threading.Thread(target=self._read, daemon=True).start()
+            import pynvml as nv
+            nv.nvmlInit()
+            try:
+                import torch
+                uuid = str(torch.cuda.get_device_properties(self.index).uuid)
+                self.handle = nv.nvmlDeviceGetHandleByUUID(("GPU-" + uuid if not uuid.startswith("GPU-") else uuid).encode())
+            except Exception:
+                self.handle = nv.nvmlDeviceGetHandleByIndex(self.index)
+            self.get_reasons = getattr(nv, "nvmlDeviceGetCurrentClocksEventReasons", None) or nv.nvmlDeviceGetCurrentClocksThrottleReasons
+            self.mx = nv.nvmlDeviceGetMaxClockInfo(self.handle, nv.NVML_CLOCK_SM)
+            self.nv, self.mode = nv, "nvml"
+            self.poll()                 # the first query of each kind costs several ms (lazy NVML state): keep it out of the timed region
+            self.rows.clear()
         except Exception:
-            self.proc = None
+            self.mode = "nvidia-smi"
 
-    def _read(self):
-        for line in self.proc.stdout:
-            self.rows.append([c.strip() for c in line.split(",")])
+    def poll(self):
+        """One sample (call it between steps inside a timed region)."""
+        if self.mode == "nvml":
+            try:
+                sm = self.nv.nvmlDeviceGetClockInfo(self.handle, self.nv.NVML_CLOCK_SM)
+                r = int(self.get_reasons(self.handle))
+                self.rows.append([str(sm), str(self.mx)] + ["Active" if r & b else "Not Active" for _, b in self.BITS])
+            except Exception:
+                pass
+        elif self.mode == "nvidia-smi":
+            try:
+                out = subprocess.run(["nvidia-smi", f"--id={self.index}", f"--query-gpu={self.FIELDS}", "--format=csv,noheader,nounits"],
+                                     capture_output=True, text=True, timeout=5).stdout.strip().splitlines()
+                if out:
+                    self.rows.append([c.strip() for c in out[-1].split(",")])
+            except Exception:
+                pass
 
     def stop(self):
-        if self.proc is None:
-            return {"sm_mhz": None, "sm_max_mhz": None, "reasons": ["nvidia-smi unavailable"]}
-        self.proc.terminate()
-        try:
-            self.proc.wait(timeout=2)
-        except Exception:
-            pass
+        if self.mode is None or not self.rows:
+            return {"sm_mhz": None, "sm_max_mhz": None, "reasons": ["nvidia-smi / NVML unavailable"], "samples": 0}
         sm = sorted(int(r[0]) for r in self.rows if r and r[0].isdigit())
         mx = [int(r[1]) for r in self.rows if len(r) > 1 and r[1].isdigit()]
-        names = ["hw_slowdown", "hw_thermal_slowdown", "sw_thermal_slowdown", "sw_power_cap"]
+        names = [n for n, _ in self.BITS]
         reasons = sorted({n for r in self.rows if len(r) >= 6 for n, v in zip(names, r[2:6]) if v.lower().startswith("active")})
-        return {"sm_mhz": sm[len(sm) // 2] if sm else None, "sm_max_mhz": max(mx) if mx else None,
-                "reasons": reasons, "samples": len(sm)}
+        return {"sm_mhz": sm[len(sm) // 2] if sm else None, "sm_max_mhz": max(mx) if mx else None, "reasons": reasons,
+                "samples": len(sm), "source": ("NVML queries" if self.mode == "nvml" else "nvidia-smi calls") +
+                " from the host loop between steps of the timed regions"}
 
 
 # ------------------------------------------------------------------------------------ CPU arm
@@ -377,14 +406,28 @@ def run_ours(args, rank: int, local_rank: int, n_gpus: int):
             dist.barrier()
         torch.cuda.synchronize()
 
+    sampler = None
+
     def timed(fn, steps):
         barrier()
         a, b = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+        per_step = [] if os.environ.get("DFM_BENCH_STEP_TIMES") else None
         a.record()
+        every = max(steps // 4, 1)
         for i in range(steps):
             fn(i)
+            if rank == 0 and sampler is not None and i % every == every - 1:
+                sampler.poll()                         # clocks / throttle reasons while the region runs (GPU busy)
+            if per_step is not None:
+                e_ = torch.cuda.Event(enable_timing=True)
+                e_.record()
+                per_step.append(e_)
         b.record()
         barrier()
+        if per_step is not None:
+            ts = [a.elapsed_time(e_) for e_ in per_step]
+            print(f"[bench rank {rank}] step end times (ms): " + " ".join(f"{t:.2f}" for t in ts) + " | deltas: " +
+                  " ".join(f"{y - x:.2f}" for x, y in zip([0.0] + ts[:-1], ts)), file=sys.stderr, flush=True)
         ms = torch.tensor([a.elapsed_time(b)], device=dev)
         if n_gpus > 1:
             dist.all_reduce(ms, op=dist.ReduceOp.MAX)
@@ -398,8 +441,8 @@ def run_ours(args, rank: int, local_rank: int, n_gpus: int):
         prepare(devb[(i + 1) % n_batches])
         step(devb[i % n_batches], devy[i % n_batches], devb[(i + 1) % n_batches])
         dbg(f"warmup {i} done")
-    sampler = ClockSampler(local_rank)
-    if rank == 0:
+    if rank == 0 and not os.environ.get("DFM_BENCH_NO_SAMPLER"):
+        sampler = ClockSampler(local_rank)
         sampler.start()
     model.embedding.profile_events = {}
     ahead = int(os.environ.get("DFM_BENCH_MAX_AHEAD", "-1"))      # >= 0: the host enqueues at most this many steps ahead
@@ -496,7 +539,7 @@ def run_ours(args, rank: int, local_rank: int, n_gpus: int):
     for i in range(2):
         e2e_step(i)
     e2e_ms = timed(lambda i: e2e_step(i + 2), K_)
-    clocks = sampler.stop() if rank == 0 else None
+    clocks = sampler.stop() if sampler is not None else None
     h2d = layout.payload_bytes
 
     # launch count of OUR kernels in one step (profiled outside the timed region)

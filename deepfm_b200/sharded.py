@@ -570,6 +570,7 @@ class ShardedFeatureEmbedding(IndexStatusMixin, nn.Module):
         self._l2_split = None
         self.__dict__.pop("_ptrs_cache", None)
         self.__dict__.pop("_prepared_cache", None)
+        self.__dict__.pop("_dense_bucket", None)
         return super()._apply(fn, *args, **kwargs)
 
     def _ordered_params(self) -> List[torch.Tensor]:
@@ -841,12 +842,17 @@ class ShardedFeatureEmbedding(IndexStatusMixin, nn.Module):
                     off += (p.numel() + 3) // 4 * 4
             layout = self.__dict__["_dense_layout"] = (len(params), items, off)
         _, items, total = layout
-        flat_g = torch.empty((max(total, 1),), device=dev, dtype=torch.float32)
-        if total and any((n + 3) // 4 * 4 != n for _, _, n, _ in items):
-            flat_g.zero_()                                    # alignment gaps travel through the allreduce: keep them finite
+        # The bucket is PERSISTENT (like DDP's gradient_as_bucket_view): allocated once, its ~65 per-parameter views built
+        # once; every step K2 overwrites it in place.  Safe in stream order: the previous step's allreduce on it was waited
+        # for in DenseGradReducer.finish() before this step's backward was enqueued.
+        bucket = self.__dict__.get("_dense_bucket")
+        if bucket is None or bucket[0].numel() != max(total, 1) or bucket[0].device != dev:
+            flat_g = torch.zeros((max(total, 1),), device=dev, dtype=torch.float32)   # zeros: alignment gaps stay finite
+            views = [(i, flat_g[off:off + n].view(shape)) for i, off, n, shape in items]
+            bucket = self.__dict__["_dense_bucket"] = (flat_g, views)
+        flat_g, views = bucket
         grads: List[Optional[torch.Tensor]] = [None] * len(params)
-        for i, off, n, shape in items:
-            g = flat_g[off:off + n].view(shape)
+        for i, g in views:
             grads[i] = g
             dense_grads[i] = g
         self.dense_grad_flat = flat_g if items else None
