@@ -373,7 +373,10 @@ DFM_API int dfm_rows_sumsq(const dfm_plan* plan, int64_t n_sorted, const uint32_
  *         mode 0  D[M][N] = A[M][K] * B[N][K]^T (+ bias[N])     nn.Linear forward       (ATen addmm)
  *         mode 1  D[M][N] = A[M][K] * B[K][N]                   grad wrt the input       (ATen mm)
  *         mode 2  D[M][N] = A[K][M]^T * B[K][N]                 grad wrt the weight      (ATen mm), split-K with a
- *                 fixed-order reduction: workspace >= dfm_gemm3_workspace_bytes().
+ *                 fixed-order reduction: workspace >= dfm_gemm3_workspace_bytes().  Internally the product runs
+ *                 swapped (D^T = B^T A, tiles stored transposed) so that the lo part of the SMALL operand A is
+ *                 precomputed like a weight's; same result, same interface.
+ *       Every mode needs workspace >= dfm_gemm3_workspace_bytes() (lo part of the B-side operand, split-K partials).
  *       The contiguous extent of each operand must be a multiple of 4 floats and 16-byte aligned
  *       (DFM_ERR_UNSUPPORTED otherwise).
  *   dfm_bn_stats: training-mode BatchNorm1d statistics of y (M, C): mean, rstd = 1/sqrt(biased var + eps);
