@@ -568,6 +568,8 @@ def run_ours(args, rank: int, local_rank: int, n_gpus: int):
             step(devb[0], devy[0])
             torch.cuda.synchronize()
         launches = sum(e.count for e in prof.key_averages() if "dfm::" in e.key or "DeviceRadixSort" in e.key)
+        gemm_us = sum(e.device_time_total for e in prof.key_averages() if "gemm3_kernel" in e.key)
+        cin_tc_us = sum(e.device_time_total for e in prof.key_averages() if "cin_tc" in e.key)
         if args.profile_step:      # per-kernel device time of one warm step (concurrent streams as they run), for profiles/
             with open(args.profile_step, "w") as fh:
                 fh.write(f"# torch.profiler, one warm step of: bench.py --workload {wl} --gpus {n_gpus} --sort {args.sort}\n")
@@ -675,6 +677,31 @@ def run_ours(args, rank: int, local_rank: int, n_gpus: int):
                             "traffic": None, "note": "per-kernel roofline is reported by the N=1 run (unsharded K1)"}
         if k1_ms:
             line["roofline"]["k1_ms"], line["roofline"]["k2_ms"] = k1_ms, k2_ms
+    # tensor-bound pieces, from the per-kernel device times of one warm step (torch.profiler, outside the timed regions)
+    bf16_peak = float(peaks.get("bf16_tflops_sustained", peaks.get("bf16_tflops", 1344.1)))
+    tf32_peak = 0.5 * bf16_peak
+    if args.dnn_gemm == "own" and launches and gemm_us > 0 and hasattr(model, "dnn"):
+        dims, width = [], model.dnn.mlp[0].in_features
+        for u in cfg.dnn.hidden_units:
+            dims.append((width, u))
+            width = u
+        useful = 3 * 2.0 * BATCH * sum(a_ * b_ for a_, b_ in dims)              # forward + dX + dW of every Linear
+        line["roofline_dnn"] = {"kernel": "dfm::g3::gemm3_kernel (tcgen05 kind::tf32, 3xTF32: 3 tensor-core products per fp32 product)",
+                                "bound": "tensor", "achieved": 3 * useful / (gemm_us * 1e-6) / 1e12, "peak": tf32_peak,
+                                "unit": "TFLOP/s", "frac": 3 * useful / (gemm_us * 1e-6) / 1e12 / tf32_peak,
+                                "useful_fp32_tflops": useful / (gemm_us * 1e-6) / 1e12, "ms": gemm_us * 1e-3, "launches": 3 * len(dims),
+                                "peak_source": "tf32 dense = 1/2 of the measured sustained bf16 rate (MEASURED_PEAKS.json)"}
+    if launches and cin_tc_us > 0 and getattr(model, "cin", None) is not None:
+        F_, D_ = schema.num_fields, cfg.feature.fm_embed_dim
+        ks, prev = [], F_
+        for i_, L_ in enumerate(model.cin.layer_sizes):
+            ks.append(L_ * prev * F_)
+            prev = model.cin.next_sizes[i_]
+        cin_flops = 6.0 * D_ * sum(ks) * BATCH                                   # fwd + bwd = 6 D sum(L_i K_i) per sample
+        line["roofline_cin"] = {"kernel": "cin_tc_fwd / cin_tc_bwd_data / cin_tc_dw (tcgen05 kind::tf32)", "bound": "tensor",
+                                "achieved": cin_flops / (cin_tc_us * 1e-6) / 1e12, "peak": tf32_peak, "unit": "TFLOP/s",
+                                "frac": cin_flops / (cin_tc_us * 1e-6) / 1e12 / tf32_peak, "ms": cin_tc_us * 1e-3,
+                                "peak_source": "tf32 dense = 1/2 of the measured sustained bf16 rate (MEASURED_PEAKS.json)"}
     if parity is not None:
         line["parity"] = parity
     if n_gpus == 1 and not args.no_cpu_baseline:
