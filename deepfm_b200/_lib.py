@@ -72,6 +72,10 @@ SIGNATURES = {
     "dfm_shard_gather2": (C.c_int, [_vp, C.c_int, C.c_int, _i64, _vp, _pp, C.c_int, _pi64, _pp, _pp, _vp, _vp]),
     "dfm_shard_push_counts": (C.c_int, [_vp, C.c_int, C.c_int, _vp, _vp]),
     "dfm_shard_push_keys": (C.c_int, [_vp, _vp, C.c_int, C.c_int, _i64, _vp, _vp]),
+    "dfm_tower_store_floats": (C.c_size_t, [C.c_int, _vp, _i64, _vp]),
+    "dfm_tower_seq_workspace_bytes": (C.c_size_t, [C.c_int, _vp, _i64, C.c_int]),
+    "dfm_tower_fwd": (C.c_int, [C.c_int, _vp, _i64, _vp, _vp, _vp, _vp, _vp, _vp, C.c_int, C.c_float, _vp, _vp, _vp, _vp, C.c_size_t, _vp]),
+    "dfm_tower_bwd": (C.c_int, [C.c_int, _vp, _i64, _vp, _vp, _vp, _vp, C.c_int, C.c_float, _vp, _vp, _vp, _vp, _vp, _vp, C.c_size_t, _vp]),
     "dfm_peer_barrier": (C.c_int, [_vp, C.c_int, C.c_int, C.c_uint32, _vp]),
     "dfm_shard_bwd_peer": (C.c_int, [_vp, _i64, _vp, _vp, _vp, _vp, _vp, _vp, _vp, _vp, _vp, _vp, _i64, C.c_uint32, C.c_int,
                                      _pi64, _pp, _pp, _f32, _vp, _sz, _vp]),

@@ -105,6 +105,56 @@ class _LinearBnActFn(torch.autograd.Function):
         return dx, dw, dbias, dgamma, dbeta, None
 
 
+class _TowerFn(torch.autograd.Function):
+    """The whole tower as ONE autograd node over two C-ABI calls (dfm_tower_fwd / dfm_tower_bwd sequence the same per-block
+    kernels): the host side of a step -- three nodes, ~45 ctypes calls, ~50 allocations -- was what bounded multi-rank steps."""
+
+    @staticmethod
+    def forward(ctx, x, cfg, *params):
+        # cfg: (dims, bn modes, act, p, seeds, eps list, momentum list, running tensors [2 per block or None], fixed pairs)
+        dims, bn, act, p, seeds, eps, mom, running, fixed = cfg
+        lib = _lib.lib()
+        n = len(bn)
+        x = x.contiguous()
+        M = x.shape[0]
+        dev = x.device
+        c_dims = _lib.i64_array(dims)
+        store = torch.empty((lib.dfm_tower_store_floats(n, c_dims, M, None),), device=dev, dtype=torch.float32)
+        out = torch.empty((M, dims[-1]), device=dev, dtype=torch.float32)
+        ws = torch.empty((lib.dfm_tower_seq_workspace_bytes(n, c_dims, M, 0),), device=dev, dtype=torch.uint8)
+        run_or_fixed = [(fixed[i] if bn[i // 2] == BN_FIXED else running[i]) for i in range(2 * n)]
+        c_params = _lib.ptr_array(list(params))
+        c_bn = _lib.i32_array(bn)
+        c_seeds = (_lib.C.c_uint64 * n)(*[int(v) for v in seeds])
+        _lib.check(lib.dfm_tower_fwd(n, c_dims, M, x.data_ptr(), c_params, c_bn, _lib.ptr_array(run_or_fixed),
+                                     (_lib.C.c_float * n)(*eps), (_lib.C.c_float * n)(*mom), act, float(p), c_seeds,
+                                     store.data_ptr(), out.data_ptr(), ws.data_ptr(), ws.numel(), _lib.stream_ptr()), "dfm_tower_fwd")
+        ctx.cfg = (dims, bn, act, p, seeds, fixed)
+        ctx.params = params                      # inputs of the node: plain references
+        ctx.save_for_backward(x, store)
+        return out
+
+    @staticmethod
+    def backward(ctx, g_out):
+        x, store = ctx.saved_tensors
+        dims, bn, act, p, seeds, fixed = ctx.cfg
+        params = ctx.params
+        lib = _lib.lib()
+        n = len(bn)
+        M = x.shape[0]
+        dev = x.device
+        g_out = g_out.contiguous()
+        c_dims = _lib.i64_array(dims)
+        grads = [None if t is None else torch.empty_like(t) for t in params]
+        dx = torch.empty((M, dims[0]), device=dev, dtype=torch.float32) if ctx.needs_input_grad[0] else None
+        ws = torch.empty((lib.dfm_tower_seq_workspace_bytes(n, c_dims, M, 1),), device=dev, dtype=torch.uint8)
+        _lib.check(lib.dfm_tower_bwd(n, c_dims, M, x.data_ptr(), _lib.ptr_array(list(params)), _lib.i32_array(bn),
+                                     _lib.ptr_array(list(fixed)), act, float(p), (_lib.C.c_uint64 * n)(*[int(v) for v in seeds]),
+                                     store.data_ptr(), g_out.data_ptr(), _lib.ptr(dx), _lib.ptr_array(grads), ws.data_ptr(),
+                                     ws.numel(), _lib.stream_ptr()), "dfm_tower_bwd")
+        return (dx, None, *grads)
+
+
 class _HeadFn(torch.autograd.Function):
     @staticmethod
     def forward(ctx, x, weight, bias):
@@ -145,6 +195,7 @@ def linear_head(module: nn.Linear, x: torch.Tensor) -> torch.Tensor:
 class DNN(nn.Module):
     ACTIVATIONS = _ACTIVATIONS
     fused = True            # class-wide switch: False runs the plain nn.Sequential (library GEMMs) everywhere
+    single_call = True      # the whole tower as one autograd node over dfm_tower_fwd / dfm_tower_bwd (False: one node per block)
 
     def __init__(self, input_dim: int, hidden_units: List[int], activation: str = "relu",
                  dropout: float = 0.1, use_batch_norm: bool = True) -> None:
@@ -196,9 +247,56 @@ class DNN(nn.Module):
         cfg = (bn, self._act_code, p, seed, eps, momentum, run_mean, run_var, fmean, frstd)
         return _LinearBnActFn.apply(x, lin.weight, lin.bias, gamma, beta, cfg)
 
+    def _tower_single_call(self, x: torch.Tensor) -> Optional[torch.Tensor]:
+        """Every block in one autograd node (``_TowerFn``); None when some block needs the per-block route."""
+        dims, bn, eps, mom, running, fixed, params = [x.shape[1]], [], [], [], [], [], []
+        p = None
+        for li, bi, di in self._blocks:
+            lin: nn.Linear = self.mlp[li]
+            bn_mod = self.mlp[bi] if bi is not None else None
+            if not gemm3_supported(x.shape[0], lin.out_features, lin.in_features):
+                return None
+            pp = float(self.mlp[di].p) if self.training else 0.0
+            if p is not None and pp != p:
+                return None                      # one dropout probability per tower (the reference's DNN has one)
+            p = pp
+            mode, e_, m_, rm, rv, fm, fr = BN_NONE, 1e-5, 0.1, None, None, None, None
+            if bn_mod is not None:
+                if not (bn_mod.affine and bn_mod.weight is not None):
+                    return None
+                e_ = bn_mod.eps
+                if self.training or bn_mod.running_mean is None:
+                    mode = BN_BATCH
+                    if self.training and bn_mod.track_running_stats and bn_mod.running_mean is not None:
+                        if bn_mod.momentum is None:
+                            return None          # cumulative moving average needs the step count on the host
+                        m_, rm, rv = bn_mod.momentum, bn_mod.running_mean, bn_mod.running_var
+                else:
+                    mode = BN_FIXED
+                    fm, fr = bn_mod.running_mean, torch.rsqrt(bn_mod.running_var + e_)
+            dims.append(lin.out_features)
+            bn.append(mode); eps.append(float(e_)); mom.append(float(m_))
+            running += [rm, rv]; fixed += [fm, fr]
+            params += [lin.weight, lin.bias, bn_mod.weight if bn_mod is not None else None,
+                       bn_mod.bias if bn_mod is not None else None]
+        seeds = [0] * len(bn)
+        if p and p > 0.0:        # one 63-bit seed per block and step from torch's CPU generator (follows torch.manual_seed)
+            seeds = torch.randint(0, 2 ** 62, (len(bn),)).tolist()
+        if self.training:
+            nbt = [self.mlp[bi].num_batches_tracked for _, bi, _ in self._blocks
+                   if bi is not None and self.mlp[bi].track_running_stats and self.mlp[bi].num_batches_tracked is not None]
+            if nbt:
+                torch._foreach_add_(nbt, 1)
+        cfg = (dims, bn, self._act_code, p or 0.0, seeds, eps, mom, running, fixed)
+        return _TowerFn.apply(x, cfg, *params)
+
     def forward(self, x: torch.Tensor) -> torch.Tensor:
         if not (DNN.fused and x.is_cuda and x.dim() == 2 and x.dtype == torch.float32 and x.shape[0] > 0):
             return self.mlp(x)
+        if DNN.single_call:
+            out = self._tower_single_call(x)
+            if out is not None:
+                return out
         for li, bi, di in self._blocks:
             lin = self.mlp[li]
             bn_ok = bi is None or (self.mlp[bi].affine and self.mlp[bi].weight is not None)

@@ -401,6 +401,23 @@ DFM_API int dfm_bn_act_bwd(const float* da, const float* y, int64_t M, int C, in
                            const float* rstd, const float* gamma, const float* beta, float drop_p, uint64_t seed,
                            float* dy, float* dgamma, float* dbeta, float* dbias, void* workspace,
                            size_t workspace_bytes, void* stream);
+/* The whole tower in two calls (same arithmetic: they sequence dfm_gemm3 / dfm_bn_stats / dfm_bn_act_fwd / _bwd block by
+ * block on `stream`; one autograd node per tower instead of one per block -- the host side of a multi-rank step was the
+ * bottleneck).  dims: n_layers + 1 widths (input, h_1 .. h_n).  params: per block W (h, din), bias, gamma, beta (NULL where
+ * absent).  bn per block: 0 none, 1 batch statistics (running: running_mean / running_var updated with momentum[l], or NULL),
+ * 2 fixed statistics (forward: running = (mean, rstd) pair; backward: fixed = the same pair).  store: the activations the
+ * backward needs (dfm_tower_store_floats floats: pre-activations, block outputs, batch statistics).  grads: per block
+ * dW, dbias, dgamma, dbeta (NULL where absent); dx optional. */
+DFM_API size_t dfm_tower_store_floats(int n_layers, const int64_t* dims, int64_t M, int64_t* offsets);
+DFM_API size_t dfm_tower_seq_workspace_bytes(int n_layers, const int64_t* dims, int64_t M, int backward);
+DFM_API int dfm_tower_fwd(int n_layers, const int64_t* dims, int64_t M, const float* x, const float* const* params,
+                          const int* bn, float* const* running, const float* eps, const float* momentum, int act,
+                          float drop_p, const uint64_t* seeds, float* store, float* out, void* workspace,
+                          size_t workspace_bytes, void* stream);
+DFM_API int dfm_tower_bwd(int n_layers, const int64_t* dims, int64_t M, const float* x, const float* const* params,
+                          const int* bn, const float* const* fixed, int act, float drop_p, const uint64_t* seeds,
+                          const float* store, const float* g_out, float* dx, float* const* grads, void* workspace,
+                          size_t workspace_bytes, void* stream);
 DFM_API int dfm_head_fwd(const float* a, const float* w, const float* b, int64_t M, int C, float* out, void* stream);
 DFM_API int dfm_head_bwd(const float* a, const float* w, const float* g, int64_t M, int C, float* da, float* dw, float* db,
                          void* workspace, size_t workspace_bytes, void* stream);

@@ -42,8 +42,11 @@ def test_gemm3_rejects_unaligned_extent():
         _gemm3(0, x, w, torch.empty(64, 16, device="cuda"), None, 64, 16, 30)
 
 
+@pytest.mark.parametrize("single", [True, False])
 @pytest.mark.parametrize("act,bn,p", [("relu", True, 0.0), ("gelu", True, 0.0), ("tanh", False, 0.0), ("leaky_relu", True, 0.0)])
-def test_tower_matches_eager_fp64(act, bn, p):
+def test_tower_matches_eager_fp64(act, bn, p, single, monkeypatch):
+    # single = True: the whole tower as one autograd node (dfm_tower_fwd / dfm_tower_bwd); False: one node per block
+    monkeypatch.setattr(DNN, "single_call", single)
     torch.manual_seed(3)
     B, width = 2048, 364
     tower = DNN(width, [256, 128, 64], activation=act, dropout=p, use_batch_norm=bn).cuda().train()
@@ -85,7 +88,9 @@ def test_tower_matches_eager_fp64(act, bn, p):
     assert_close_rel(e1.cpu(), e2.cpu(), 1e-5, "eval output")
 
 
-def test_tower_dropout_mask_is_regenerated_in_backward():
+@pytest.mark.parametrize("single", [True, False])
+def test_tower_dropout_mask_is_regenerated_in_backward(single, monkeypatch):
+    monkeypatch.setattr(DNN, "single_call", single)
     torch.manual_seed(5)
     B = 4096
     tower = DNN(64, [128], activation="relu", dropout=0.5, use_batch_norm=False).cuda().train()
