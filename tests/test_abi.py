@@ -104,3 +104,35 @@ def test_cpu_tensors_are_refused_not_silently_computed():
         emb(batch)
     with pytest.raises(RuntimeError, match="no CPU"):
         FMInteraction()(torch.randn(2, 3, 4))
+
+
+def test_tower_store_layout_and_workspaces_are_consistent():
+    """Host-only entry points of the sequenced DNN tower (no GPU work): the activation store holds, per block, the
+    pre-activation, the block output (not for the last block: that is the caller's `out`) and the batch statistics, every
+    piece 256-byte aligned and non-overlapping; workspaces cover every product of every block."""
+    lib = _lib.lib()
+    dims = [2496, 256, 128, 64]
+    M, n = 4096, 3
+    c_dims = _lib.i64_array(dims)
+    offs = (C.c_int64 * (4 * n))()
+    total = lib.dfm_tower_store_floats(n, c_dims, M, offs)
+    assert total == lib.dfm_tower_store_floats(n, c_dims, M, None)
+    pieces = []
+    for l in range(n):
+        h = dims[l + 1]
+        oy, oa, om, orr = (offs[4 * l + k] for k in range(4))
+        assert (oa == -1) == (l == n - 1)
+        pieces += [(oy, M * h), (om, h), (orr, h)] + ([(oa, M * h)] if oa >= 0 else [])
+    pieces.sort()
+    for (o0, n0), (o1, _) in zip(pieces, pieces[1:]):
+        assert o0 % 64 == 0 and o0 + n0 <= o1
+    assert pieces[-1][0] + pieces[-1][1] <= total
+    fwd = lib.dfm_tower_seq_workspace_bytes(n, c_dims, M, 0)
+    bwd = lib.dfm_tower_seq_workspace_bytes(n, c_dims, M, 1)
+    need = max(lib.dfm_gemm3_workspace_bytes(0, M, dims[l + 1], dims[l]) + lib.dfm_tower_workspace_bytes(M, dims[l + 1]) for l in range(n))
+    assert fwd >= need
+    need_b = max(max(lib.dfm_gemm3_workspace_bytes(1, M, dims[l], dims[l + 1]), lib.dfm_gemm3_workspace_bytes(2, dims[l + 1], dims[l], M))
+                 for l in range(n)) + 3 * M * max(dims[1:]) * 4
+    assert bwd >= need_b and bwd > fwd
+    # mode 2 (weight gradient) runs swapped: its workspace holds the split-K partials AND the lo part of dY (K x M floats)
+    assert lib.dfm_gemm3_workspace_bytes(2, 256, 2496, 65536) >= 65536 * 256 * 4
