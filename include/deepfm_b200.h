@@ -173,7 +173,9 @@ DFM_API int dfm_axpy(const float* p, int64_t numel, float coef, const float* sca
  * CIN (deepfm/models/layers/cin.py:26-105; ATen einsum + reshape + conv1d(k=1) + relu + split +
  * sum).  layer_sizes[i] = L_i; weights[i] (L_i, K_i) with K_i = H_i * F, channel k = h*F + f;
  * split is [direct first, next second] (cin.py:93-96).  The (B, H*F, D) outer product is never
- * written to memory.  precision 0 = fp32 CUDA cores (reference-exact up to summation order).
+ * written to memory.  precision 0 = fp32 CUDA cores (reference-exact up to summation order); precision 1 = TF32 on the
+ * tcgen05 tensor cores, forward AND backward (fp32 accumulation in tensor memory; 2e-3 forward / 3e-3 gradient tolerance),
+ * for layers the tensor-core tiles cover (F <= 64, L <= 256, D % 4 == 0), CUDA cores otherwise.
  *   dfm_cin_sizes: out[0] = output_dim, out[1] = bytes of `acts` (post-ReLU activations of every
  *   layer, kept for the backward), out[2] = bytes of the backward workspace, out[3] = activation
  *   floats per sample.
