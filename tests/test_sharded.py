@@ -263,6 +263,68 @@ def _reducer_worker(rank, world, port, out):
     dist.destroy_process_group()
 
 
+def _reducer_callback_worker(rank, world, port, out):
+    """The product wiring: no per-parameter hooks -- the embedding's backward calls ``launch`` when it starts, and the
+    embedding's own data-parallel gradients are views of ONE flat buffer that is all-reduced in place."""
+    import torch.distributed as dist
+    os.environ.update(MASTER_ADDR="127.0.0.1", MASTER_PORT=str(port))
+    dist.init_process_group("gloo", rank=rank, world_size=world)
+    from deepfm_b200.sharded import DenseGradReducer
+
+    class _Emb:                                           # what DenseGradReducer needs from ShardedFeatureEmbedding
+        forward_fused = True
+        on_backward_start = None
+        dense_grad_flat = None
+
+    torch.manual_seed(0)
+    early = torch.nn.Sequential(torch.nn.Linear(6, 5), torch.nn.ReLU(), torch.nn.Linear(5, 1))
+    late = torch.nn.Linear(3, 6)
+    emb = _Emb()
+    red = DenseGradReducer(list(early.parameters()), list(late.parameters()), world, embedding=emb)
+    ok = emb.on_backward_start is not None and not any(p._post_accumulate_grad_hooks for p in early.parameters()
+                                                       if getattr(p, "_post_accumulate_grad_hooks", None))
+    for step in range(2):
+        gen = torch.Generator().manual_seed(10 * step + rank)
+        x = torch.randn(7, 3, generator=gen)
+        for p in list(early.parameters()) + list(late.parameters()):
+            p.grad = None
+        h = late(x)
+        h.register_hook(lambda g: (emb.on_backward_start(), g)[1])      # fires where the embedding's backward node would start
+        early(h).sum().backward()
+        mine = [p.grad.clone() for p in list(early.parameters()) + list(late.parameters())]
+        ok = ok and red._work is not None                                 # launched from the callback, before finish()
+        # the embedding's gradients live in one flat bucket (views), like ShardedFeatureEmbedding.local_grads makes them
+        lp = list(late.parameters())
+        flat = torch.cat([p.grad.reshape(-1) for p in lp])
+        off = 0
+        for p in lp:
+            p.grad = flat[off:off + p.numel()].view_as(p)
+            off += p.numel()
+        emb.dense_grad_flat = flat
+        red.finish()
+        ok = ok and all(p.grad.untyped_storage().data_ptr() == flat.untyped_storage().data_ptr() for p in lp)   # reduced in place
+        for p, g in zip(list(early.parameters()) + lp, mine):
+            parts = [torch.empty_like(g) for _ in range(world)]
+            dist.all_gather(parts, g)
+            ok = ok and torch.allclose(p.grad, sum(parts) / world, atol=1e-6)
+    out.put((rank, ok))
+    dist.destroy_process_group()
+
+
+def test_dense_grad_reducer_callback_and_flat_bucket_gloo_world2():
+    ctx = mp.get_context("spawn")
+    q = ctx.Queue()
+    port = 35000 + os.getpid() % 2000
+    procs = [ctx.Process(target=_reducer_callback_worker, args=(r, 2, port, q)) for r in range(2)]
+    for p in procs:
+        p.start()
+    res = [q.get(timeout=120) for _ in procs]
+    for p in procs:
+        p.join(timeout=60)
+        assert p.exitcode == 0
+    assert all(r[1] for r in res), res
+
+
 def test_dense_grad_reducer_gloo_world2():
     ctx = mp.get_context("spawn")
     q = ctx.Queue()
