@@ -845,11 +845,16 @@ class ShardedFeatureEmbedding(IndexStatusMixin, nn.Module):
         # The bucket is PERSISTENT (like DDP's gradient_as_bucket_view): allocated once, its ~65 per-parameter views built
         # once; every step K2 overwrites it in place.  Safe in stream order: the previous step's allreduce on it was waited
         # for in DenseGradReducer.finish() before this step's backward was enqueued.
+        # (Gradient accumulation -- a second backward while the parameters still hold the previous gradients, which are
+        # views of the bucket -- must not overwrite them: that pass gets a fresh buffer.)
         bucket = self.__dict__.get("_dense_bucket")
-        if bucket is None or bucket[0].numel() != max(total, 1) or bucket[0].device != dev:
+        accumulating = any(getattr(params[i], "grad", None) is not None for i, _, _, _ in items)
+        if accumulating or bucket is None or bucket[0].numel() != max(total, 1) or bucket[0].device != dev:
             flat_g = torch.zeros((max(total, 1),), device=dev, dtype=torch.float32)   # zeros: alignment gaps stay finite
             views = [(i, flat_g[off:off + n].view(shape)) for i, off, n, shape in items]
-            bucket = self.__dict__["_dense_bucket"] = (flat_g, views)
+            bucket = (flat_g, views)
+            if not accumulating:
+                self.__dict__["_dense_bucket"] = bucket
         flat_g, views = bucket
         grads: List[Optional[torch.Tensor]] = [None] * len(params)
         for i, g in views:
