@@ -1009,6 +1009,12 @@ class ShardedFeatureEmbedding(IndexStatusMixin, nn.Module):
             raise RuntimeError("ShardedFeatureEmbedding needs a communicator (e.g. TorchDistComm())")
         self._ensure_plans()
         params = self._ordered_params()
+        # the cached pointer array is validated against every parameter's storage once per forward (a `p.data = ...`
+        # assignment between steps is the one way a pointer can change without going through _apply)
+        sig = tuple(p.data_ptr() for p in params)
+        if sig != self.__dict__.get("_ptr_sig"):
+            self.__dict__["_ptr_sig"] = sig
+            self.__dict__.pop("_ptrs_cache", None)
         inputs = self._prepare(batch)
         if not self.p2p_capacity_rows:    # every rank derives the same capacity (same batch size and schema)
             self.p2p_capacity_rows = inputs[0].shape[0] * max(self._S, 1) + 16
